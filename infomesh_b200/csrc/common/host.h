@@ -1,0 +1,45 @@
+// Host-side helpers shared by all launchers: error handling, TMA tensor-map construction
+// (driver entry point resolved at run time so the library links without libcuda on the
+// CPU-only build box), and the exported-symbol macro.
+#pragma once
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#define IM_API extern "C" __attribute__((visibility("default")))
+
+namespace im {
+
+// Last error text, readable from Python through im_last_error().
+char* last_error_buf();
+
+inline int set_error(const char* what, const char* detail) {
+  snprintf(last_error_buf(), 512, "%s: %s", what, detail ? detail : "");
+  return -1;
+}
+
+#define IM_CUDA_OK(expr)                                                 \
+  do {                                                                   \
+    cudaError_t _e = (expr);                                             \
+    if (_e != cudaSuccess) return im::set_error(#expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+#define IM_LAUNCH_OK(name)                                                        \
+  do {                                                                            \
+    cudaError_t _e = cudaGetLastError();                                          \
+    if (_e != cudaSuccess) return im::set_error(name, cudaGetErrorString(_e));    \
+  } while (0)
+
+enum TmapSwizzle { TMAP_SW_NONE = 0, TMAP_SW_32 = 1, TMAP_SW_64 = 2, TMAP_SW_128 = 3 };
+
+// 2-D row-major tensor [rows, cols] of `elem_bytes` elements with row pitch `row_stride_bytes`;
+// box = [box_rows, box_cols].  Out-of-bounds elements are zero-filled on load.
+int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
+                 uint32_t box_rows, uint32_t box_cols, int elem_bytes, TmapSwizzle swizzle);
+
+int sm_count();
+
+}  // namespace im

@@ -1,0 +1,336 @@
+// K6/K8 — persistent warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   C[M,N] = epilogue( A[M,K] · B[N,K]^T )        A, B bf16 row-major (K contiguous, "TN")
+//
+// Replaces the encoder / reranker / summariser linear layers that the reference reaches through
+// sentence-transformers / an external LLM server (reference infomesh/index/vector_store.py:104-125,
+// infomesh/summarizer/engine.py:126-141).  Structure (one CTA per SM, 6 warps):
+//   warp 0      TMA producer      cp.async.bulk.tensor 128B-swizzled A/B tiles -> smem ring (mbarrier tx)
+//   warp 1      MMA issuer        one thread issues tcgen05.mma.kind::f16 128xBNx16, accumulators in TMEM
+//   warps 2..5  epilogue          tcgen05.ld 32 lanes x 32 cols -> bias / activation / residual -> bf16 stores
+// The TMEM accumulator is double buffered (2 x BN columns) so the epilogue of tile i overlaps the MMAs
+// of tile i+1.  Fused-collective hooks (used by parallel/tp.py):
+//   * a_ready flags: the producer acquires a per-row-block flag before loading A (all-gather -> GEMM:
+//     comm CTAs / peers publish row blocks as they land),
+//   * peer_c: the epilogue pushes each output row block straight into the owning rank's receive slot over
+//     NVLink (GEMM -> reduce-scatter) and bumps a per-row-block arrival counter there.
+#include "../common/host.h"
+#include "../common/ptx.cuh"
+#include "../common/tmap_cache.h"
+
+namespace im {
+
+struct GemmEpilogue {
+  void* c;                  // output (bf16 or fp32), row pitch ldc elements
+  const float* bias;        // [N] or null
+  const __nv_bfloat16* residual;  // [M, ldr] or null
+  int ldc, ldr;
+  int act;                  // 0 none, 1 gelu(erf), 2 relu, 3 gelu(tanh)
+  int out_fp32;
+  float alpha;
+  // --- fused reduce-scatter push (null => local store) ---
+  void* const* peer_c;      // [tp] receive-buffer base of every rank: [tp_src][rows_per_rank][ldc]
+  uint32_t* const* peer_flags;  // [tp] arrival counters of every rank: [tp_src][rows_per_rank/128]
+  int rank, rows_per_rank;
+  // --- fused all-gather wait (null => no wait) ---
+  const uint32_t* a_ready;  // [ceil(M/128)] local flags, row block is loadable once flag >= a_epoch
+  uint32_t a_epoch;
+  int m_rotate;             // first row block processed (so the local shard goes first)
+};
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kGemmThreads = 192;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStageBytes = (kBM + BN) * kBK * 2;
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kTmemCols = 2 * BN;  // 256 or 512: both powers of two
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == 1) return gelu_erf(x);
+  if (act == 2) return fmaxf(x, 0.0f);
+  if (act == 3) return gelu_tanh(x);
+  return x;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const GemmEpilogue ep, int M, int N, int K) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tmem_full = empty_bar + Cfg::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const uint32_t warp = warp_id();
+  const uint32_t lane = lane_id();
+  const int num_m = (M + kBM - 1) / kBM;
+  const int num_n = (N + BN - 1) / BN;
+  const int num_k = (K + kBK - 1) / kBK;
+  const int num_tiles = num_m * num_n;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------- TMA producer -------------------------------
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        int m_blk = t / num_n, n_blk = t % num_n;
+        m_blk = (m_blk + ep.m_rotate) % num_m;
+        if (ep.a_ready != nullptr) {
+          uint32_t spins = 0;
+          while (ld_acquire_sys(ep.a_ready + m_blk) < ep.a_epoch) {
+            if (++spins > IM_WAIT_LIMIT) {
+              printf("[infomesh_b200] gemm a_ready timeout m_blk=%d\n", m_blk);
+              __trap();
+            }
+          }
+        }
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + kBM * kBK * 2;
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBK, m_blk * kBM);
+          tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * kBK, n_blk * BN);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer ---------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(kBM, BN);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t b0 = a0 + kBM * kBK * 2;
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            umma_bf16(d_tmem, umma_desc_k_sw128(a0 + k * 32), umma_desc_k_sw128(b0 + k * 32), idesc,
+                      (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ------------------------------- epilogue warps ------------------------------
+    const uint32_t quad = warp & 3u;  // TMEM lane quadrant this warp may touch
+    const uint32_t row_in_tile = quad * 32u + lane;
+    uint32_t acc = 0, acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      int m_blk = t / num_n, n_blk = t % num_n;
+      m_blk = (m_blk + ep.m_rotate) % num_m;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_blk * kBM + static_cast<int>(row_in_tile);
+      const bool row_ok = row < M;
+      // destination row pointer (local C, or the owner's receive slot for fused reduce-scatter)
+      uint8_t* c_row = nullptr;
+      int owner = 0;
+      if (ep.peer_c != nullptr) {
+        owner = (m_blk * kBM) / ep.rows_per_rank;
+        const int local_row = row - owner * ep.rows_per_rank;
+        uint8_t* base = reinterpret_cast<uint8_t*>(ep.peer_c[owner]);
+        c_row = base + (static_cast<size_t>(ep.rank) * ep.rows_per_rank + local_row) * ep.ldc * (ep.out_fp32 ? 4 : 2);
+      } else {
+        c_row = reinterpret_cast<uint8_t*>(ep.c) + static_cast<size_t>(row) * ep.ldc * (ep.out_fp32 ? 4 : 2);
+      }
+      const __nv_bfloat16* r_row = ep.residual ? ep.residual + static_cast<size_t>(row) * ep.ldr : nullptr;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + ((quad * 32u) << 16) + acc * BN + c, v);
+        tmem_ld_wait();
+        const int col0 = n_blk * BN + c;
+        if (!row_ok || col0 >= N) continue;
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * ep.alpha;
+        const bool full_chunk = (col0 + 32 <= N);
+        if (ep.bias != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (full_chunk || col0 + i < N) f[i] += __ldg(ep.bias + col0 + i);
+        }
+        if (ep.act != 0) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = apply_act(f[i], ep.act);
+        }
+        if (r_row != nullptr) {
+          if (full_chunk) {
+            const uint4* rp = reinterpret_cast<const uint4*>(r_row + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 q = __ldg(rp + j);
+              float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), cc = unpack_bf16x2(q.z), d = unpack_bf16x2(q.w);
+              f[j * 8 + 0] += a.x; f[j * 8 + 1] += a.y; f[j * 8 + 2] += b.x; f[j * 8 + 3] += b.y;
+              f[j * 8 + 4] += cc.x; f[j * 8 + 5] += cc.y; f[j * 8 + 6] += d.x; f[j * 8 + 7] += d.y;
+            }
+          } else {
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i < N) f[i] += __bfloat162float(r_row[col0 + i]);
+          }
+        }
+        if (ep.out_fp32) {
+          float* out = reinterpret_cast<float*>(c_row) + col0;
+          if (full_chunk) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              reinterpret_cast<float4*>(out)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          } else {
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i < N) out[i] = f[i];
+          }
+        } else {
+          __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(c_row) + col0;
+          if (full_chunk) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 q;
+              q.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+              q.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+              q.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+              q.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+              reinterpret_cast<uint4*>(out)[j] = q;
+            }
+          } else {
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i < N) out[i] = __float2bfloat16(f[i]);
+          }
+        }
+      }
+      // TMEM reads done -> hand the accumulator stage back to the MMA warp
+      tc_fence_before();
+      if (ep.peer_c != nullptr) __threadfence_system();  // pushed rows visible before the arrival counter
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&tmem_empty[acc]);
+        if (ep.peer_c != nullptr) {
+          const int blk_local = (m_blk * kBM - owner * ep.rows_per_rank) / kBM;
+          uint32_t* flag = ep.peer_flags[owner] + static_cast<size_t>(ep.rank) * (ep.rows_per_rank / kBM) + blk_local;
+          asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(flag) : "memory");
+        }
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M, int N, int K,
+                       int max_ctas, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    IM_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int tiles = ((M + kBM - 1) / kBM) * ((N + BN - 1) / BN);
+  int grid = tiles < sm_count() ? tiles : sm_count();
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+  if (grid < 1) grid = 1;
+  gemm_bf16_tn_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, ep, M, N, K);
+  IM_LAUNCH_OK("gemm_bf16_tn_kernel");
+  return 0;
+}
+
+}  // namespace im
+
+// C[M,N] = act(alpha * A[M,K] B[N,K]^T + bias) + residual.  bn = 0 picks the tile width.
+IM_API int im_gemm_bf16_tn(const void* A, const void* B, void* C, const float* bias, const void* residual, int M, int N,
+                           int K, int lda, int ldb, int ldc, int ldr, int act, int out_fp32, float alpha, int bn,
+                           void* const* peer_c, uint32_t* const* peer_flags, int rank, int rows_per_rank,
+                           const uint32_t* a_ready, uint32_t a_epoch, int m_rotate, int max_ctas, void* stream) {
+  using namespace im;
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if ((lda % 8) || (ldb % 8) || (ldc % 8)) return set_error("im_gemm_bf16_tn", "leading dims must be multiples of 8");
+  if (peer_c != nullptr && (rows_per_rank % kBM) != 0)
+    return set_error("im_gemm_bf16_tn", "rows_per_rank must be a multiple of 128 for the fused reduce-scatter");
+  if (bn == 0) {
+    const int tiles256 = ((M + kBM - 1) / kBM) * ((N + 255) / 256);
+    bn = (N % 256 == 0 && tiles256 >= sm_count()) ? 256 : 128;
+  }
+  CUtensorMap ta, tb;
+  if (get_tmap_2d(&ta, A, M, K, static_cast<uint64_t>(lda) * 2, kBM, kBK, 2, TMAP_SW_128)) return -1;
+  if (get_tmap_2d(&tb, B, N, K, static_cast<uint64_t>(ldb) * 2, bn, kBK, 2, TMAP_SW_128)) return -1;
+  GemmEpilogue ep;
+  ep.c = C;
+  ep.bias = bias;
+  ep.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
+  ep.ldc = ldc;
+  ep.ldr = ldr;
+  ep.act = act;
+  ep.out_fp32 = out_fp32;
+  ep.alpha = alpha;
+  ep.peer_c = peer_c;
+  ep.peer_flags = peer_flags;
+  ep.rank = rank;
+  ep.rows_per_rank = rows_per_rank > 0 ? rows_per_rank : M;
+  ep.a_ready = a_ready;
+  ep.a_epoch = a_epoch;
+  const int num_m = (M + kBM - 1) / kBM;
+  ep.m_rotate = num_m > 0 ? ((m_rotate % num_m) + num_m) % num_m : 0;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (bn == 256) return launch_gemm<256>(ta, tb, ep, M, N, K, max_ctas, s);
+  return launch_gemm<128>(ta, tb, ep, M, N, K, max_ctas, s);
+}

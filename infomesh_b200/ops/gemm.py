@@ -1,0 +1,60 @@
+"""tcgen05 GEMM (csrc/gemm/gemm_bf16.cu): ``C = act(alpha * A @ B^T + bias) + residual``.
+
+K6/K8 of SURVEY.md §2.4 — the linear layers the reference runs through sentence-transformers
+(reference infomesh/index/vector_store.py:104-125).  ``linear_ref`` is the fp32 oracle.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from infomesh_b200 import _native
+
+ACT = {None: 0, "none": 0, "gelu": 1, "relu": 2, "gelu_tanh": 3}
+
+
+def linear_ref(a, w, bias=None, residual=None, act=None, alpha=1.0):
+    """fp32 PyTorch reference of :func:`linear`."""
+    y = alpha * (a.float() @ w.float().t())
+    if bias is not None:
+        y = y + bias.float()
+    if act in ("gelu", 1):
+        y = torch.nn.functional.gelu(y)
+    elif act in ("relu", 2):
+        y = torch.relu(y)
+    elif act in ("gelu_tanh", 3):
+        y = torch.nn.functional.gelu(y, approximate="tanh")
+    if residual is not None:
+        y = y + residual.float()
+    return y
+
+
+def linear(a, w, bias=None, residual=None, act=None, alpha=1.0, out=None, out_dtype=torch.bfloat16, bn=0,
+           max_ctas=0):
+    """``a[M,K] @ w[N,K]^T`` with fused bias / activation / residual on the tcgen05 kernel."""
+    assert a.is_cuda and w.is_cuda and a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+    assert a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1]
+    assert a.stride(1) == 1 and w.stride(1) == 1
+    m, k = a.shape
+    n = w.shape[0]
+    if out is None:
+        out = torch.empty((m, n), device=a.device, dtype=out_dtype)
+    assert out.stride(1) == 1 and out.dtype in (torch.bfloat16, torch.float32)
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == n
+    if residual is not None:
+        assert residual.dtype == torch.bfloat16 and residual.shape == (m, n) and residual.stride(1) == 1
+    L = _native.require()
+    rc = L.im_gemm_bf16_tn(
+        _native.ptr(a), _native.ptr(w), _native.ptr(out), _native.ptr(bias), _native.ptr(residual),
+        ctypes.c_int(m), ctypes.c_int(n), ctypes.c_int(k),
+        ctypes.c_int(a.stride(0)), ctypes.c_int(w.stride(0)), ctypes.c_int(out.stride(0)),
+        ctypes.c_int(residual.stride(0) if residual is not None else 0),
+        ctypes.c_int(ACT[act] if not isinstance(act, int) else act),
+        ctypes.c_int(1 if out.dtype == torch.float32 else 0), ctypes.c_float(alpha), ctypes.c_int(bn),
+        ctypes.c_void_p(0), ctypes.c_void_p(0), ctypes.c_int(0), ctypes.c_int(0),
+        ctypes.c_void_p(0), ctypes.c_uint32(0), ctypes.c_int(0), ctypes.c_int(max_ctas), _native.stream_ptr())
+    _native.check(rc, "im_gemm_bf16_tn")
+    _native.count_launch()
+    return out
