@@ -1,0 +1,383 @@
+// K7 — flash-style attention forward on tcgen05 (encoder bidirectional, causal, cross, T5 relative bias).
+//
+// One CTA = (128 query rows, one head, one sequence).  Per 128-key chunk:
+//   MMA1  S[128q x 128k] = Q · K^T          tcgen05.mma, operands TMA-loaded K-major, S lives in TMEM
+//   softmax (thread t owns query row t = TMEM lane t: no cross-lane reductions), two passes over TMEM:
+//         row max, then p = exp2(s - m) packed to bf16 into a 128B-swizzled K-major smem tile
+//   MMA2  O_c[128q x HD] = P · V_c          V tile consumed MN-major straight from its natural [keys, HD] layout
+//   merge O_c into fp32 register accumulators with the usual online-softmax rescale
+// K_{c+1} is prefetched as soon as MMA1(c) retires and V_{c+1} as soon as MMA2(c) retires, so a single K and V
+// buffer (80 KB smem per CTA, 256 TMEM columns) lets two CTAs share an SM and overlap each other's
+// softmax with tensor-core work.  This is the "summarizer's attention" hot path of the north-star; the reference
+// has no attention code of its own (it calls sentence-transformers / an HTTP LLM: infomesh/index/vector_store.py:124,
+// infomesh/summarizer/engine.py:126-141).
+#include <math_constants.h>
+
+#include "../common/host.h"
+#include "../common/ptx.cuh"
+#include "../common/tmap_cache.h"
+
+namespace im {
+
+struct AttnParams {
+  __nv_bfloat16* out;     // [B*Sq, ldo], head h at column h*HD
+  int ldo;
+  int Sq, Sk;             // padded per-sequence lengths (rows per batch element in the q / kv buffers)
+  const int* kv_lens;     // [B] valid keys per sequence (null => Sk)
+  int causal;             // key j visible to query i iff j <= i + causal_offset
+  int causal_offset;
+  float scale_log2;       // softmax scale * log2(e)
+  const float* rel_bias;  // [nH, Sq + Sk - 1] additive bias indexed by (j - i) + (Sq - 1), or null (already * log2e)
+};
+
+constexpr int kAttnThreads = 128;
+constexpr int kAttnBQ = 128;
+constexpr int kAttnBKV = 128;
+constexpr float kNegBig = -1.0e30f;
+
+template <int HD>
+struct AttnCfg {
+  static constexpr int kRowBytes = HD * 2;                 // 128 (SW128) or 64 (SW64)
+  static constexpr int kTileBytes = kAttnBQ * kRowBytes;   // Q / K / V tile
+  static constexpr int kPBytes = kAttnBQ * kAttnBKV * 2;   // 32 KB, two [128 x 64] SW128 k-blocks
+  static constexpr int kTmemCols = 256;                    // S: 128, O: HD (<= 128)
+  static constexpr int kGroupBytes = 8 * kRowBytes;        // 8-row swizzle group (SBO)
+};
+
+template <int HD>
+__device__ __forceinline__ uint64_t desc_k_major(uint32_t saddr) {
+  return HD == 64 ? umma_desc_k_sw128(saddr) : umma_desc_k_sw64(saddr);
+}
+template <int HD>
+__device__ __forceinline__ uint64_t desc_mn_major(uint32_t saddr) {
+  return HD == 64 ? umma_desc_mn_sw128(saddr, 16) : umma_desc_mn_sw64(saddr, 16);
+}
+
+template <int HD>
+__global__ void __launch_bounds__(kAttnThreads)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+  using Cfg = AttnCfg<HD>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Cfg::kTileBytes;
+  uint8_t* sV = sK + Cfg::kTileBytes;
+  uint8_t* sP = sV + Cfg::kTileBytes;  // offsets stay multiples of 1024 (tile bytes are 8 KB or 16 KB)
+  uint64_t* q_bar = reinterpret_cast<uint64_t*>(sP + Cfg::kPBytes);
+  uint64_t* k_bar = q_bar + 1;
+  uint64_t* v_bar = q_bar + 2;
+  uint64_t* s_bar = q_bar + 3;
+  uint64_t* o_bar = q_bar + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_bar + 5);
+  float* s_bias = reinterpret_cast<float*>(q_bar + 6);
+
+  const int tid = threadIdx.x;
+  const uint32_t warp = warp_id();
+  const int qb = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+  const int q_row0 = b * p.Sq + qb * kAttnBQ;  // first query row of this tile in the q buffer
+  const int kv_row0 = b * p.Sk;
+  const int q_idx = qb * kAttnBQ + tid;        // position of this thread's query within its sequence
+
+  int kv_limit = p.kv_lens ? min(p.kv_lens[b], p.Sk) : p.Sk;
+  if (p.causal) kv_limit = min(kv_limit, qb * kAttnBQ + kAttnBQ + p.causal_offset);
+  const int num_chunks = max(0, (kv_limit + kAttnBKV - 1) / kAttnBKV);
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    mbar_init(q_bar, 1);
+    mbar_init(k_bar, 1);
+    mbar_init(v_bar, 1);
+    mbar_init(s_bar, 1);
+    mbar_init(o_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  if (p.rel_bias != nullptr) {
+    const int nb = p.Sq + p.Sk - 1;
+    for (int i = tid; i < nb; i += kAttnThreads) s_bias[i] = p.rel_bias[static_cast<size_t>(head) * nb + i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_s = tmem_base;        // 128 columns
+  const uint32_t tmem_o = tmem_base + 128;  // HD columns
+  const uint32_t lane_base = (warp * 32u) << 16;
+
+  if (tid == 0 && num_chunks > 0) {
+    mbar_expect_tx(q_bar, Cfg::kTileBytes);
+    tma_load_2d(sQ, &tmap_q, q_bar, head * HD, q_row0);
+    mbar_expect_tx(k_bar, Cfg::kTileBytes);
+    tma_load_2d(sK, &tmap_k, k_bar, head * HD, kv_row0);
+    mbar_expect_tx(v_bar, Cfg::kTileBytes);
+    tma_load_2d(sV, &tmap_v, v_bar, head * HD, kv_row0);
+  }
+
+  float o_acc[HD];
+#pragma unroll
+  for (int i = 0; i < HD; ++i) o_acc[i] = 0.f;
+  float m_run = kNegBig, l_run = 0.f;
+  const int kv_len = p.kv_lens ? min(p.kv_lens[b], p.Sk) : p.Sk;
+
+  for (int c = 0; c < num_chunks; ++c) {
+    const uint32_t ph = c & 1;
+    // ---------------- MMA1: S = Q K^T ----------------
+    if (tid == 0) {
+      if (c == 0) mbar_wait(q_bar, 0);
+      mbar_wait(k_bar, ph);
+      tc_fence_after();
+      constexpr uint32_t idesc1 = umma_idesc_f16(kAttnBQ, kAttnBKV);
+      const uint32_t a0 = smem_u32(sQ), b0 = smem_u32(sK);
+#pragma unroll
+      for (int k = 0; k < HD / 16; ++k)
+        umma_bf16(tmem_s, desc_k_major<HD>(a0 + k * 32), desc_k_major<HD>(b0 + k * 32), idesc1, k != 0 ? 1u : 0u);
+      umma_commit(s_bar);
+    }
+    __syncwarp();
+    mbar_wait(s_bar, ph);
+    tc_fence_after();
+    if (tid == 0 && c + 1 < num_chunks) {  // K buffer is free: prefetch the next chunk under the softmax
+      mbar_expect_tx(k_bar, Cfg::kTileBytes);
+      tma_load_2d(sK, &tmap_k, k_bar, head * HD, kv_row0 + (c + 1) * kAttnBKV);
+    }
+    __syncwarp();
+
+    // ---------------- softmax over this thread's row ----------------
+    const int key0 = c * kAttnBKV;
+    int vis_end = kv_len;  // keys [0, vis_end) visible
+    if (p.causal) vis_end = min(vis_end, q_idx + p.causal_offset + 1);
+    const float* bias_row = p.rel_bias ? s_bias + (p.Sq - 1 - min(q_idx, p.Sq - 1)) : nullptr;  // index by key j
+    float m_c = kNegBig;
+#pragma unroll 1
+    for (int cc = 0; cc < kAttnBKV; cc += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tmem_s + lane_base + cc, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int j = key0 + cc + i;
+        float s = __uint_as_float(v[i]) * p.scale_log2;
+        if (bias_row) s += bias_row[min(j, p.Sk - 1)];
+        s = (j < vis_end) ? s : kNegBig;
+        m_c = fmaxf(m_c, s);
+      }
+    }
+    float l_c = 0.f;
+#pragma unroll 1
+    for (int cc = 0; cc < kAttnBKV; cc += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tmem_s + lane_base + cc, v);
+      tmem_ld_wait();
+      uint32_t packed[16];
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        float e[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int j = key0 + cc + i + u;
+          float s = __uint_as_float(v[i + u]) * p.scale_log2;
+          if (bias_row) s += bias_row[min(j, p.Sk - 1)];
+          e[u] = (j < vis_end) ? exp2f(s - m_c) : 0.f;
+        }
+        // accumulate the bf16-rounded value so numerator and denominator agree
+        const uint32_t pk = pack_bf16x2(e[0], e[1]);
+        const float2 r = unpack_bf16x2(pk);
+        l_c += r.x + r.y;
+        packed[i >> 1] = pk;
+      }
+      const int kb = cc >> 6;               // which [128 x 64] k-block
+      const int ch0 = (cc & 63) >> 3;       // first 16-byte chunk inside the 128-byte row
+      uint8_t* prow = sP + kb * (kAttnBQ * 128) + tid * 128;
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const int ch = (ch0 + q4) ^ (tid & 7);
+        *reinterpret_cast<uint4*>(prow + (ch << 4)) =
+            make_uint4(packed[q4 * 4 + 0], packed[q4 * 4 + 1], packed[q4 * 4 + 2], packed[q4 * 4 + 3]);
+      }
+    }
+    fence_proxy_async_smem();  // st.shared P -> visible to tcgen05.mma (async proxy)
+    tc_fence_before();
+    __syncthreads();
+
+    // ---------------- MMA2: O_c = P V_c ----------------
+    if (tid == 0) {
+      mbar_wait(v_bar, ph);
+      tc_fence_after();
+      constexpr uint32_t idesc2 = umma_idesc_f16(kAttnBQ, HD, 1, false, true);
+      const uint32_t a0 = smem_u32(sP), b0 = smem_u32(sV);
+#pragma unroll
+      for (int ks = 0; ks < kAttnBKV / 16; ++ks) {
+        const uint32_t a_addr = a0 + (ks >> 2) * (kAttnBQ * 128) + (ks & 3) * 32;
+        const uint32_t b_addr = b0 + ks * 2 * Cfg::kGroupBytes;  // 16 keys = two 8-row swizzle groups
+        umma_bf16(tmem_o, umma_desc_k_sw128(a_addr), desc_mn_major<HD>(b_addr), idesc2, ks != 0 ? 1u : 0u);
+      }
+      umma_commit(o_bar);
+    }
+    __syncwarp();
+    mbar_wait(o_bar, ph);
+    tc_fence_after();
+    if (tid == 0 && c + 1 < num_chunks) {  // V buffer is free
+      mbar_expect_tx(v_bar, Cfg::kTileBytes);
+      tma_load_2d(sV, &tmap_v, v_bar, head * HD, kv_row0 + (c + 1) * kAttnBKV);
+    }
+    __syncwarp();
+
+    // ---------------- merge into the running accumulators ----------------
+    const float m_new = fmaxf(m_run, m_c);
+    const float alpha = exp2f(m_run - m_new);
+    const float beta = exp2f(m_c - m_new);
+    l_run = l_run * alpha + l_c * beta;
+    m_run = m_new;
+#pragma unroll
+    for (int cc = 0; cc < HD; cc += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tmem_o + lane_base + cc, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o_acc[cc + i] = o_acc[cc + i] * alpha + __uint_as_float(v[i]) * beta;
+    }
+    tc_fence_before();
+    __syncthreads();  // everyone is done with S / O / P before the next chunk's MMAs overwrite them
+  }
+
+  // ---------------- normalise + store ----------------
+  if (q_idx < p.Sq) {
+    const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
+    __nv_bfloat16* orow = p.out + static_cast<size_t>(q_row0 + tid) * p.ldo + head * HD;
+#pragma unroll
+    for (int i = 0; i < HD; i += 8) {
+      uint4 q;
+      q.x = pack_bf16x2(o_acc[i + 0] * inv, o_acc[i + 1] * inv);
+      q.y = pack_bf16x2(o_acc[i + 2] * inv, o_acc[i + 3] * inv);
+      q.z = pack_bf16x2(o_acc[i + 4] * inv, o_acc[i + 5] * inv);
+      q.w = pack_bf16x2(o_acc[i + 6] * inv, o_acc[i + 7] * inv);
+      *reinterpret_cast<uint4*>(orow + i) = q;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// Single-query decode attention against a KV cache (T5 decoder step): one warp per (batch, head).
+// q: [B, nH*HD]; k/v cache: [B, S_max, nH*HD]; keys [0, kv_len[b]) visible.  CUDA-core, latency-bound by design.
+template <int HD>
+__global__ void __launch_bounds__(128)
+attn_decode_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ kc,
+                   const __nv_bfloat16* __restrict__ vc, int ld_kv, int s_max, const int* __restrict__ kv_lens,
+                   int kv_len_all, float scale_log2, const float* __restrict__ rel_bias, int bias_len, int q_pos,
+                   int n_heads, int n_pairs, __nv_bfloat16* __restrict__ out, int ldo) {
+  const int pair = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (pair >= n_pairs) return;
+  const int b = pair / n_heads, h = pair % n_heads;
+  const int len = kv_lens ? kv_lens[b] : kv_len_all;
+  constexpr int PER = HD / 32;  // dims per lane (1 or 2)
+  float qv[PER];
+#pragma unroll
+  for (int i = 0; i < PER; ++i) qv[i] = __bfloat162float(q[static_cast<size_t>(b) * ldq + h * HD + lane * PER + i]);
+  float m = kNegBig, l = 0.f, acc[PER];
+#pragma unroll
+  for (int i = 0; i < PER; ++i) acc[i] = 0.f;
+  const __nv_bfloat16* kb = kc + static_cast<size_t>(b) * s_max * ld_kv + h * HD;
+  const __nv_bfloat16* vb = vc + static_cast<size_t>(b) * s_max * ld_kv + h * HD;
+  for (int j = 0; j < len; ++j) {
+    float d = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) d += qv[i] * __bfloat162float(kb[static_cast<size_t>(j) * ld_kv + lane * PER + i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    float s = d * scale_log2;
+    if (rel_bias) {
+      int bi = j - q_pos + (bias_len - 1) / 2;  // table centred on relative position 0
+      bi = max(0, min(bias_len - 1, bi));
+      s += rel_bias[static_cast<size_t>(h) * bias_len + bi];
+    }
+    const float m_new = fmaxf(m, s);
+    const float a = exp2f(m - m_new), pj = exp2f(s - m_new);
+    l = l * a + pj;
+#pragma unroll
+    for (int i = 0; i < PER; ++i)
+      acc[i] = acc[i] * a + pj * __bfloat162float(vb[static_cast<size_t>(j) * ld_kv + lane * PER + i]);
+    m = m_new;
+  }
+  const float inv = l > 0.f ? 1.f / l : 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i)
+    out[static_cast<size_t>(b) * ldo + h * HD + lane * PER + i] = __float2bfloat16(acc[i] * inv);
+}
+
+}  // namespace im
+
+// q: [B*Sq, ldq] with head h at column h*HD (pass base pointer already offset to the Q block); k, v likewise.
+IM_API int im_attn_fwd(const void* q, const void* k, const void* v, void* out, int B, int n_heads, int head_dim, int Sq,
+                       int Sk, int ldq, int ldk, int ldv, int ldo, const int* kv_lens, int causal, int causal_offset,
+                       float scale, const float* rel_bias_log2, void* stream) {
+  using namespace im;
+  if (B <= 0 || Sq <= 0 || Sk <= 0) return 0;
+  if (head_dim != 64 && head_dim != 32) return set_error("im_attn_fwd", "head_dim must be 32 or 64");
+  if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 8)) return set_error("im_attn_fwd", "row pitches must be multiples of 8");
+  const TmapSwizzle sw = head_dim == 64 ? TMAP_SW_128 : TMAP_SW_64;
+  CUtensorMap tq, tk, tv;
+  const uint64_t cols = static_cast<uint64_t>(n_heads) * head_dim;
+  if (get_tmap_2d(&tq, q, static_cast<uint64_t>(B) * Sq, cols, static_cast<uint64_t>(ldq) * 2, kAttnBQ, head_dim, 2, sw))
+    return -1;
+  if (get_tmap_2d(&tk, k, static_cast<uint64_t>(B) * Sk, cols, static_cast<uint64_t>(ldk) * 2, kAttnBKV, head_dim, 2, sw))
+    return -1;
+  if (get_tmap_2d(&tv, v, static_cast<uint64_t>(B) * Sk, cols, static_cast<uint64_t>(ldv) * 2, kAttnBKV, head_dim, 2, sw))
+    return -1;
+  AttnParams p;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.ldo = ldo;
+  p.Sq = Sq;
+  p.Sk = Sk;
+  p.kv_lens = kv_lens;
+  p.causal = causal;
+  p.causal_offset = causal_offset;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.rel_bias = rel_bias_log2;
+  const int bias_bytes = rel_bias_log2 ? (Sq + Sk) * 4 : 0;
+  dim3 grid((Sq + kAttnBQ - 1) / kAttnBQ, n_heads, B);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (head_dim == 64) {
+    const int smem = 3 * AttnCfg<64>::kTileBytes + AttnCfg<64>::kPBytes + 1024 + 64 + bias_bytes;
+    IM_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attn_fwd_kernel<64><<<grid, kAttnThreads, smem, s>>>(tq, tk, tv, p);
+  } else {
+    const int smem = 3 * AttnCfg<32>::kTileBytes + AttnCfg<32>::kPBytes + 1024 + 64 + bias_bytes;
+    IM_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attn_fwd_kernel<32><<<grid, kAttnThreads, smem, s>>>(tq, tk, tv, p);
+  }
+  IM_LAUNCH_OK("attn_fwd_kernel");
+  return 0;
+}
+
+IM_API int im_attn_decode(const void* q, int ldq, const void* kc, const void* vc, int ld_kv, int s_max,
+                          const int* kv_lens, int kv_len_all, float scale, const float* rel_bias_log2, int bias_len,
+                          int q_pos, int B, int n_heads, int head_dim, void* out, int ldo, void* stream) {
+  using namespace im;
+  const int n_pairs = B * n_heads;
+  if (n_pairs <= 0) return 0;
+  const float sl2 = scale * 1.4426950408889634f;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = (n_pairs + 3) / 4;
+  if (head_dim == 64)
+    attn_decode_kernel<64><<<grid, 128, 0, s>>>((const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)kc,
+                                               (const __nv_bfloat16*)vc, ld_kv, s_max, kv_lens, kv_len_all, sl2,
+                                               rel_bias_log2, bias_len, q_pos, n_heads, n_pairs, (__nv_bfloat16*)out, ldo);
+  else if (head_dim == 32)
+    attn_decode_kernel<32><<<grid, 128, 0, s>>>((const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)kc,
+                                               (const __nv_bfloat16*)vc, ld_kv, s_max, kv_lens, kv_len_all, sl2,
+                                               rel_bias_log2, bias_len, q_pos, n_heads, n_pairs, (__nv_bfloat16*)out, ldo);
+  else
+    return set_error("im_attn_decode", "head_dim must be 32 or 64");
+  IM_LAUNCH_OK("attn_decode_kernel");
+  return 0;
+}

@@ -1,0 +1,363 @@
+// K5 / K9 — memory-bound transformer glue kernels (one warp per token row, 8-byte vector I/O):
+//   embed_ln        word + position + token-type embedding gather fused with LayerNorm
+//   sum_ln          out = LN( sum_p in_p[row] (+ residual) )   — P = 1 is plain (post-)LayerNorm;
+//                   P = tp consumes the partial rows pushed by the fused GEMM->reduce-scatter
+//                   (waits on the per-row-block arrival counters first)
+//   rmsnorm         T5 LayerNorm (no mean, no bias)
+//   pool_norm       CLS / mean pooling + L2 normalisation (sentence embedding)
+//   cls_head        XLM-R style classification head: w2 · tanh(W1 h + b1) + b2
+//   row_argmax      fp32 logits -> (max, argmax) per row (LM-head greedy decode)
+// These replace what sentence-transformers / the external LLM server does around the GEMMs
+// (reference infomesh/index/vector_store.py:120-125, infomesh/search/reranker.py:124-159).
+#include <math_constants.h>
+
+#include "../common/host.h"
+#include "../common/ptx.cuh"
+
+namespace im {
+
+constexpr int kRowsPerBlock = 8;  // 8 warps / block
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ void load4(const __nv_bfloat16* p, float (&f)[4]) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+}
+__device__ __forceinline__ void store4(__nv_bfloat16* p, const float (&f)[4]) {
+  uint2 u;
+  u.x = pack_bf16x2(f[0], f[1]);
+  u.y = pack_bf16x2(f[2], f[3]);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+// H must be a multiple of 128 and <= 1024 (VEC = H / 128 chunks of 4 per lane)
+template <int VEC>
+__device__ __forceinline__ void ln_finish(float (&x)[VEC][4], const float* gamma, const float* beta, float eps,
+                                          __nv_bfloat16* out_row, int lane, bool rms_only) {
+  constexpr int H = VEC * 128;
+  float s = 0.f;
+#pragma unroll
+  for (int v = 0; v < VEC; ++v)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s += x[v][j];
+  const float mean = rms_only ? 0.f : warp_sum(s) * (1.0f / H);
+  float q = 0.f;
+#pragma unroll
+  for (int v = 0; v < VEC; ++v)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float d = x[v][j] - mean;
+      q += d * d;
+    }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / H) + eps);
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    const int col = v * 128 + lane * 4;
+    const float4 g = *reinterpret_cast<const float4*>(gamma + col);
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (beta != nullptr) b = *reinterpret_cast<const float4*>(beta + col);
+    float o[4];
+    o[0] = (x[v][0] - mean) * rstd * g.x + b.x;
+    o[1] = (x[v][1] - mean) * rstd * g.y + b.y;
+    o[2] = (x[v][2] - mean) * rstd * g.z + b.z;
+    o[3] = (x[v][3] - mean) * rstd * g.w + b.w;
+    store4(out_row + col, o);
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kRowsPerBlock * 32)
+embed_ln_kernel(const int* __restrict__ ids, const int* __restrict__ pos_ids, const int* __restrict__ type_ids,
+                const __nv_bfloat16* __restrict__ word, const __nv_bfloat16* __restrict__ pos,
+                const __nv_bfloat16* __restrict__ type, const float* __restrict__ gamma, const float* __restrict__ beta,
+                float eps, int n_tokens, int seq_len, int pos_offset, int vocab, int max_pos,
+                __nv_bfloat16* __restrict__ out) {
+  constexpr int H = VEC * 128;
+  const int row = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n_tokens) return;
+  int id = ids[row];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  int p = pos_ids ? pos_ids[row] : (row % seq_len) + pos_offset;
+  p = p < 0 ? 0 : (p >= max_pos ? max_pos - 1 : p);
+  const int ty = type_ids ? type_ids[row] : 0;
+  float x[VEC][4];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    const int col = v * 128 + lane * 4;
+    float a[4], b[4];
+    load4(word + static_cast<size_t>(id) * H + col, a);
+    if (pos != nullptr) {
+      load4(pos + static_cast<size_t>(p) * H + col, b);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) a[j] += b[j];
+    }
+    if (type != nullptr) {
+      load4(type + static_cast<size_t>(ty) * H + col, b);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) a[j] += b[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) x[v][j] = a[j];
+  }
+  if (gamma == nullptr) {  // plain gather (T5: no embedding LayerNorm)
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) store4(out + static_cast<size_t>(row) * H + v * 128 + lane * 4, x[v]);
+    return;
+  }
+  ln_finish<VEC>(x, gamma, beta, eps, out + static_cast<size_t>(row) * H, lane, false);
+}
+
+// out[row] = LN( sum_{p<P} in[p][row] + residual[row] );  in_stride_p = elements between partial p and p+1
+template <int VEC>
+__global__ void __launch_bounds__(kRowsPerBlock * 32)
+sum_ln_kernel(const __nv_bfloat16* __restrict__ in, size_t in_stride_p, int P,
+              const __nv_bfloat16* __restrict__ residual, const float* __restrict__ gamma,
+              const float* __restrict__ beta, float eps, int rms_only, int n_rows, __nv_bfloat16* __restrict__ out,
+              __nv_bfloat16* __restrict__ sum_out, const uint32_t* __restrict__ arrive_flags, uint32_t arrive_target,
+              int blocks_per_src) {
+  constexpr int H = VEC * 128;
+  const int row = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n_rows) return;
+  if (arrive_flags != nullptr) {
+    // fused reduce-scatter: every source rank bumps flags[src][row/128] once per epilogue warp and N tile
+    const int blk = row >> 7;
+    if (lane < P) {
+      uint32_t spins = 0;
+      while (ld_acquire_sys(arrive_flags + lane * blocks_per_src + blk) < arrive_target) {
+        if (++spins > IM_WAIT_LIMIT) {
+          printf("[infomesh_b200] sum_ln arrival timeout src=%d blk=%d\n", lane, blk);
+          __trap();
+        }
+      }
+    }
+    __syncwarp();
+  }
+  float x[VEC][4];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) x[v][j] = 0.f;
+  for (int p = 0; p < P; ++p) {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      float a[4];
+      load4(in + p * in_stride_p + static_cast<size_t>(row) * H + v * 128 + lane * 4, a);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) x[v][j] += a[j];
+    }
+  }
+  if (residual != nullptr) {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      float a[4];
+      load4(residual + static_cast<size_t>(row) * H + v * 128 + lane * 4, a);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) x[v][j] += a[j];
+    }
+  }
+  if (sum_out != nullptr) {  // pre-norm architectures keep the un-normalised residual stream
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) store4(sum_out + static_cast<size_t>(row) * H + v * 128 + lane * 4, x[v]);
+  }
+  if (out != nullptr) ln_finish<VEC>(x, gamma, beta, eps, out + static_cast<size_t>(row) * H, lane, rms_only != 0);
+}
+
+// sentence embedding: mode 0 = CLS token, 1 = mean over valid tokens; L2 normalised; one block per sequence
+__global__ void __launch_bounds__(256)
+pool_norm_kernel(const __nv_bfloat16* __restrict__ h, const int* __restrict__ lengths, int seq_len, int H, int mode,
+                 int normalize, __nv_bfloat16* __restrict__ out, float* __restrict__ out_f32) {
+  extern __shared__ float pooled[];
+  __shared__ float red[8];
+  const int b = blockIdx.x;
+  const int len = lengths ? max(1, min(lengths[b], seq_len)) : seq_len;
+  const __nv_bfloat16* base = h + static_cast<size_t>(b) * seq_len * H;
+  float sq = 0.f;
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
+    float acc;
+    if (mode == 0) {
+      acc = __bfloat162float(base[c]);
+    } else {
+      acc = 0.f;
+      for (int t = 0; t < len; ++t) acc += __bfloat162float(base[static_cast<size_t>(t) * H + c]);
+      acc /= static_cast<float>(len);
+    }
+    pooled[c] = acc;
+    sq += acc * acc;
+  }
+  sq = warp_sum(sq);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
+  __syncthreads();
+  float tot = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
+  const float inv = normalize ? rsqrtf(fmaxf(tot, 1e-24f)) : 1.0f;
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
+    const float v = pooled[c] * inv;
+    if (out) out[static_cast<size_t>(b) * H + c] = __float2bfloat16(v);
+    if (out_f32) out_f32[static_cast<size_t>(b) * H + c] = v;
+  }
+}
+
+// logits[b] = w2 · tanh(W1 · h[b, 0, :] + b1) + b2   (one block per sequence, H <= 1024)
+__global__ void __launch_bounds__(256)
+cls_head_kernel(const __nv_bfloat16* __restrict__ h, int seq_len, int H, const __nv_bfloat16* __restrict__ w1,
+                const float* __restrict__ b1, const __nv_bfloat16* __restrict__ w2, const float* __restrict__ b2,
+                float* __restrict__ logits) {
+  extern __shared__ float xs[];  // [H] cls vector, then [H] hidden
+  float* hid = xs + H;
+  __shared__ float red[8];
+  const int b = blockIdx.x;
+  const __nv_bfloat16* x = h + static_cast<size_t>(b) * seq_len * H;
+  for (int c = threadIdx.x; c < H; c += blockDim.x) xs[c] = __bfloat162float(x[c]);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int o = warp; o < H; o += (blockDim.x >> 5)) {
+    const __nv_bfloat16* wr = w1 + static_cast<size_t>(o) * H;
+    float acc = 0.f;
+    for (int c = lane * 2; c < H; c += 64) {
+      const float2 w = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(wr + c));
+      acc += w.x * xs[c] + w.y * xs[c + 1];
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) hid[o] = tanhf(acc + (b1 ? b1[o] : 0.f));
+  }
+  __syncthreads();
+  float acc = 0.f;
+  for (int c = threadIdx.x; c < H; c += blockDim.x) acc += hid[c] * __bfloat162float(w2[c]);
+  acc = warp_sum(acc);
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    logits[b] = t + (b2 ? b2[0] : 0.f);
+  }
+}
+
+// (max, argmax) of each fp32 row; id_offset added so vocab-parallel shards report global ids
+__global__ void __launch_bounds__(256)
+row_argmax_kernel(const float* __restrict__ x, int n_cols, int ld, int id_offset, float* __restrict__ out_val,
+                  int* __restrict__ out_idx) {
+  __shared__ float rv[8];
+  __shared__ int ri[8];
+  const float* row = x + static_cast<size_t>(blockIdx.x) * ld;
+  float bv = -CUDART_INF_F;
+  int bi = 0x7fffffff;
+  for (int c = threadIdx.x; c < n_cols; c += blockDim.x) {
+    const float v = row[c];
+    if (v > bv || (v == bv && c < bi)) {
+      bv = v;
+      bi = c;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > bv || (ov == bv && oi < bi)) {
+      bv = ov;
+      bi = oi;
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+    rv[threadIdx.x >> 5] = bv;
+    ri[threadIdx.x >> 5] = bi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i)
+      if (rv[i] > bv || (rv[i] == bv && ri[i] < bi)) {
+        bv = rv[i];
+        bi = ri[i];
+      }
+    out_val[blockIdx.x] = bv;
+    out_idx[blockIdx.x] = bi + id_offset;
+  }
+}
+
+}  // namespace im
+
+#define IM_DISPATCH_VEC(H, CALL)                    \
+  switch ((H) / 128) {                              \
+    case 1: { constexpr int VEC = 1; CALL; } break; \
+    case 2: { constexpr int VEC = 2; CALL; } break; \
+    case 3: { constexpr int VEC = 3; CALL; } break; \
+    case 4: { constexpr int VEC = 4; CALL; } break; \
+    case 6: { constexpr int VEC = 6; CALL; } break; \
+    case 8: { constexpr int VEC = 8; CALL; } break; \
+    default: return im::set_error("hidden size", "H must be 128*{1,2,3,4,6,8}"); \
+  }
+
+IM_API int im_embed_ln(const int* ids, const int* pos_ids, const int* type_ids, const void* word, const void* pos,
+                       const void* type, const float* gamma, const float* beta, float eps, int n_tokens, int seq_len,
+                       int pos_offset, int vocab, int max_pos, int H, void* out, void* stream) {
+  using namespace im;
+  if (n_tokens <= 0) return 0;
+  if (H % 128) return set_error("im_embed_ln", "H must be a multiple of 128");
+  const int grid = (n_tokens + kRowsPerBlock - 1) / kRowsPerBlock;
+  auto s = reinterpret_cast<cudaStream_t>(stream);
+  IM_DISPATCH_VEC(H, (embed_ln_kernel<VEC><<<grid, kRowsPerBlock * 32, 0, s>>>(
+                         ids, pos_ids, type_ids, (const __nv_bfloat16*)word, (const __nv_bfloat16*)pos,
+                         (const __nv_bfloat16*)type, gamma, beta, eps, n_tokens, seq_len, pos_offset, vocab, max_pos,
+                         (__nv_bfloat16*)out)));
+  IM_LAUNCH_OK("embed_ln_kernel");
+  return 0;
+}
+
+IM_API int im_sum_ln(const void* in, long long in_stride_p, int P, const void* residual, const float* gamma,
+                     const float* beta, float eps, int rms_only, int n_rows, int H, void* out, void* sum_out,
+                     const uint32_t* arrive_flags, uint32_t arrive_target, int blocks_per_src, void* stream) {
+  using namespace im;
+  if (n_rows <= 0) return 0;
+  if (H % 128) return set_error("im_sum_ln", "H must be a multiple of 128");
+  const int grid = (n_rows + kRowsPerBlock - 1) / kRowsPerBlock;
+  auto s = reinterpret_cast<cudaStream_t>(stream);
+  IM_DISPATCH_VEC(H, (sum_ln_kernel<VEC><<<grid, kRowsPerBlock * 32, 0, s>>>(
+                         (const __nv_bfloat16*)in, (size_t)in_stride_p, P, (const __nv_bfloat16*)residual, gamma, beta,
+                         eps, rms_only, n_rows, (__nv_bfloat16*)out, (__nv_bfloat16*)sum_out, arrive_flags,
+                         arrive_target, blocks_per_src)));
+  IM_LAUNCH_OK("sum_ln_kernel");
+  return 0;
+}
+
+IM_API int im_pool_norm(const void* h, const int* lengths, int batch, int seq_len, int H, int mode, int normalize,
+                        void* out_bf16, float* out_f32, void* stream) {
+  using namespace im;
+  if (batch <= 0) return 0;
+  pool_norm_kernel<<<batch, 256, H * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
+      (const __nv_bfloat16*)h, lengths, seq_len, H, mode, normalize, (__nv_bfloat16*)out_bf16, out_f32);
+  IM_LAUNCH_OK("pool_norm_kernel");
+  return 0;
+}
+
+IM_API int im_cls_head(const void* h, int batch, int seq_len, int H, const void* w1, const float* b1, const void* w2,
+                       const float* b2, float* logits, void* stream) {
+  using namespace im;
+  if (batch <= 0) return 0;
+  if (H % 64) return set_error("im_cls_head", "H must be a multiple of 64");
+  cls_head_kernel<<<batch, 256, 2 * H * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
+      (const __nv_bfloat16*)h, seq_len, H, (const __nv_bfloat16*)w1, b1, (const __nv_bfloat16*)w2, b2, logits);
+  IM_LAUNCH_OK("cls_head_kernel");
+  return 0;
+}
+
+IM_API int im_row_argmax(const float* x, int n_rows, int n_cols, int ld, int id_offset, float* out_val, int* out_idx,
+                         void* stream) {
+  using namespace im;
+  if (n_rows <= 0) return 0;
+  row_argmax_kernel<<<n_rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, n_cols, ld, id_offset, out_val,
+                                                                               out_idx);
+  IM_LAUNCH_OK("row_argmax_kernel");
+  return 0;
+}

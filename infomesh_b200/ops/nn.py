@@ -1,0 +1,121 @@
+"""Transformer glue kernels (csrc/nn/norm_embed.cu) and their fp32 PyTorch oracles (K5/K9)."""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from infomesh_b200 import _native
+
+
+# ----------------------------------------------------------------------------- references
+def embed_ln_ref(ids, word, pos, type_emb, gamma, beta, eps, seq_len, pos_ids=None, type_ids=None, pos_offset=0):
+    n = ids.numel()
+    x = word.float()[ids.long().view(-1)]
+    if pos is not None:
+        p = pos_ids.long().view(-1) if pos_ids is not None else (torch.arange(n, device=ids.device) % seq_len) + pos_offset
+        x = x + pos.float()[p]
+    if type_emb is not None:
+        t = type_ids.long().view(-1) if type_ids is not None else torch.zeros(n, dtype=torch.long, device=ids.device)
+        x = x + type_emb.float()[t]
+    if gamma is None:
+        return x
+    return torch.nn.functional.layer_norm(x, (x.shape[-1],), gamma.float(), beta.float() if beta is not None else None, eps)
+
+
+def layernorm_ref(x, gamma, beta, eps, residual=None, rms_only=False):
+    x = x.float()
+    if residual is not None:
+        x = x + residual.float()
+    if rms_only:
+        return x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps) * gamma.float()
+    return torch.nn.functional.layer_norm(x, (x.shape[-1],), gamma.float(), beta.float() if beta is not None else None, eps)
+
+
+def pool_norm_ref(h, lengths, mode="cls", normalize=True):
+    hf = h.float()
+    if mode == "cls":
+        e = hf[:, 0]
+    else:
+        B, S, _ = hf.shape
+        m = (torch.arange(S, device=h.device)[None] < lengths.view(B, 1)).float()[..., None]
+        e = (hf * m).sum(1) / m.sum(1).clamp(min=1)
+    return torch.nn.functional.normalize(e, dim=-1) if normalize else e
+
+
+# ----------------------------------------------------------------------------- kernels
+def embed_ln(ids, word, pos, type_emb, gamma, beta, eps, seq_len, pos_ids=None, type_ids=None, pos_offset=0, out=None):
+    n = ids.numel()
+    H = word.shape[1]
+    assert ids.dtype == torch.int32 and word.dtype == torch.bfloat16
+    if out is None:
+        out = torch.empty((n, H), device=word.device, dtype=torch.bfloat16)
+    L = _native.require()
+    rc = L.im_embed_ln(_native.ptr(ids), _native.ptr(pos_ids), _native.ptr(type_ids), _native.ptr(word),
+                       _native.ptr(pos), _native.ptr(type_emb), _native.ptr(gamma), _native.ptr(beta),
+                       ctypes.c_float(eps), ctypes.c_int(n), ctypes.c_int(seq_len), ctypes.c_int(pos_offset),
+                       ctypes.c_int(word.shape[0]), ctypes.c_int(pos.shape[0] if pos is not None else 1),
+                       ctypes.c_int(H), _native.ptr(out), _native.stream_ptr())
+    _native.check(rc, "im_embed_ln")
+    _native.count_launch()
+    return out
+
+
+def layernorm(x, gamma, beta=None, eps=1e-12, residual=None, rms_only=False, out=None, sum_out=None, partials=1,
+              partial_stride=0, arrive_flags=None, arrive_target=0, blocks_per_src=0, want_norm=True):
+    """``out = LN(sum_p x[p] + residual)``; ``x``: [n, H] (or [P, n, H] with ``partials=P``)."""
+    H = x.shape[-1]
+    n = x.shape[-2]
+    assert x.dtype == torch.bfloat16 and x.stride(-1) == 1
+    if out is None and want_norm:
+        out = torch.empty((n, H), device=x.device, dtype=torch.bfloat16)
+    L = _native.require()
+    rc = L.im_sum_ln(_native.ptr(x), ctypes.c_longlong(partial_stride if partials > 1 else 0), ctypes.c_int(partials),
+                     _native.ptr(residual), _native.ptr(gamma), _native.ptr(beta), ctypes.c_float(eps),
+                     ctypes.c_int(1 if rms_only else 0), ctypes.c_int(n), ctypes.c_int(H),
+                     _native.ptr(out if want_norm else None), _native.ptr(sum_out), _native.ptr(arrive_flags),
+                     ctypes.c_uint32(arrive_target), ctypes.c_int(blocks_per_src), _native.stream_ptr())
+    _native.check(rc, "im_sum_ln")
+    _native.count_launch()
+    return out
+
+
+def pool_norm(h, lengths=None, mode="cls", normalize=True, out=None, out_f32=None):
+    B, S, H = h.shape
+    assert h.is_contiguous() and h.dtype == torch.bfloat16
+    if out is None:
+        out = torch.empty((B, H), device=h.device, dtype=torch.bfloat16)
+    L = _native.require()
+    rc = L.im_pool_norm(_native.ptr(h), _native.ptr(lengths), ctypes.c_int(B), ctypes.c_int(S), ctypes.c_int(H),
+                        ctypes.c_int(0 if mode == "cls" else 1), ctypes.c_int(1 if normalize else 0),
+                        _native.ptr(out), _native.ptr(out_f32), _native.stream_ptr())
+    _native.check(rc, "im_pool_norm")
+    _native.count_launch()
+    return out
+
+
+def cls_head(h, w1, b1, w2, b2, out=None):
+    B, S, H = h.shape
+    if out is None:
+        out = torch.empty((B,), device=h.device, dtype=torch.float32)
+    L = _native.require()
+    rc = L.im_cls_head(_native.ptr(h), ctypes.c_int(B), ctypes.c_int(S), ctypes.c_int(H), _native.ptr(w1),
+                       _native.ptr(b1), _native.ptr(w2), _native.ptr(b2), _native.ptr(out), _native.stream_ptr())
+    _native.check(rc, "im_cls_head")
+    _native.count_launch()
+    return out
+
+
+def row_argmax(x, id_offset=0, out_val=None, out_idx=None):
+    n, c = x.shape
+    assert x.dtype == torch.float32 and x.stride(1) == 1
+    if out_val is None:
+        out_val = torch.empty((n,), device=x.device, dtype=torch.float32)
+    if out_idx is None:
+        out_idx = torch.empty((n,), device=x.device, dtype=torch.int32)
+    L = _native.require()
+    rc = L.im_row_argmax(_native.ptr(x), ctypes.c_int(n), ctypes.c_int(c), ctypes.c_int(x.stride(0)),
+                         ctypes.c_int(id_offset), _native.ptr(out_val), _native.ptr(out_idx), _native.stream_ptr())
+    _native.check(rc, "im_row_argmax")
+    _native.count_launch()
+    return out_val, out_idx

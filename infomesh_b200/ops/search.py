@@ -1,0 +1,80 @@
+"""Dense retrieval kernels (csrc/search/sim_topk.cu): fused similarity-GEMM + top-k, and the
+candidate-list merge (K3/K4 of SURVEY.md §2.4).
+
+Reference behaviour being replaced: ``VectorStore.search`` -> ``collection.query`` (hnswlib ANN,
+reference infomesh/index/vector_store.py:187-254) and the per-peer result merge
+(reference infomesh/search/query.py:492-508).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from infomesh_b200 import _native
+
+
+def sim_topk_ref(q, docs, k, alive=None):
+    """fp32 oracle: exact top-k of ``q @ docs.T`` (score desc, id asc on ties)."""
+    scores = q.float() @ docs.float().t()
+    if alive is not None:
+        scores = scores.masked_fill(~alive.bool()[None, :], float("-inf"))
+    k = min(k, docs.shape[0])
+    vals, idx = torch.topk(scores, k, dim=1, largest=True, sorted=True)
+    return vals, idx
+
+
+def sim_topk_partials(q, docs, ktop=16, alive=None, max_ctas=0):
+    """Run the fused kernel; returns per-CTA candidate lists ``(scores[P,nq,ktop], ids[P,nq,ktop])``."""
+    assert q.is_cuda and docs.is_cuda and q.dtype == torch.bfloat16 and docs.dtype == torch.bfloat16
+    assert q.stride(1) == 1 and docs.stride(1) == 1 and q.shape[1] == docs.shape[1]
+    nq, dim = q.shape
+    n_docs = docs.shape[0]
+    L = _native.require()
+    sms = L.im_sm_count()
+    tiles = (n_docs + 127) // 128
+    grid = max(1, min(tiles, sms if max_ctas <= 0 else min(sms, max_ctas)))
+    out_s = torch.empty((grid, nq, ktop), device=q.device, dtype=torch.float32)
+    out_i = torch.empty((grid, nq, ktop), device=q.device, dtype=torch.int32)
+    if alive is not None:
+        assert alive.dtype == torch.uint8 and alive.numel() >= n_docs
+    rc = L.im_sim_topk(_native.ptr(q), _native.ptr(docs), ctypes.c_int(nq), ctypes.c_int(n_docs), ctypes.c_int(dim),
+                       ctypes.c_int(q.stride(0)), ctypes.c_int(docs.stride(0)), ctypes.c_int(ktop),
+                       _native.ptr(alive), _native.ptr(out_s), _native.ptr(out_i), ctypes.c_int(max_ctas),
+                       _native.stream_ptr())
+    if rc < 0:
+        _native.check(rc, "im_sim_topk")
+    assert rc == grid, (rc, grid)
+    _native.count_launch()
+    return out_s, out_i
+
+
+def topk_merge(cand_scores, cand_ids, k_out, id_offset=0, out_scores=None, out_ids=None):
+    """Merge ``[P, nq, k_in]`` candidate lists into ``[nq, k_out]`` (score desc, id asc)."""
+    P, nq, k_in = cand_scores.shape
+    assert cand_scores.dtype == torch.float32 and cand_ids.dtype in (torch.int32, torch.int64)
+    cand_scores = cand_scores.contiguous()
+    cand_ids = cand_ids.contiguous()
+    if out_scores is None:
+        out_scores = torch.empty((nq, k_out), device=cand_scores.device, dtype=torch.float32)
+    if out_ids is None:
+        out_ids = torch.empty((nq, k_out), device=cand_scores.device, dtype=torch.int64)
+    L = _native.require()
+    is64 = cand_ids.dtype == torch.int64
+    rc = L.im_topk_merge(_native.ptr(cand_scores), _native.ptr(cand_ids if is64 else None),
+                         _native.ptr(None if is64 else cand_ids), ctypes.c_int(P), ctypes.c_int(nq),
+                         ctypes.c_int(k_in), ctypes.c_int(k_out), ctypes.c_int64(id_offset),
+                         _native.ptr(out_scores), _native.ptr(out_ids), ctypes.c_void_p(0), ctypes.c_void_p(0),
+                         ctypes.c_void_p(0), ctypes.c_int(1), ctypes.c_int(0), ctypes.c_void_p(0),
+                         ctypes.c_uint32(0), _native.stream_ptr())
+    _native.check(rc, "im_topk_merge")
+    _native.count_launch()
+    return out_scores, out_ids
+
+
+def sim_topk(q, docs, k=10, alive=None, id_offset=0):
+    """Exact top-``k`` cosine/dot search of ``q[nq<=128, dim]`` against ``docs[n, dim]``."""
+    ktop = 16 if k <= 16 else 32
+    assert k <= 32, "k > 32 is served by chunked search at the index level"
+    ps, pi = sim_topk_partials(q, docs, ktop=ktop, alive=alive)
+    return topk_merge(ps, pi, k, id_offset=id_offset)
