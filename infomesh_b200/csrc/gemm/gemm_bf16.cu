@@ -25,7 +25,8 @@ struct GemmEpilogue {
   const float* bias;        // [N] or null
   const __nv_bfloat16* residual;  // [M, ldr] or null
   int ldc, ldr;
-  int act;                  // 0 none, 1 gelu(erf), 2 relu, 3 gelu(tanh)
+  int act;                  // 0 none, 1 gelu(erf), 2 relu, 3 gelu(tanh), 4 tanh
+  int tma_store;            // bf16 output staged through swizzled smem and written by TMA (coalesced)
   int out_fp32;
   float alpha;
   // --- fused reduce-scatter push (null => local store) ---
@@ -47,29 +48,51 @@ struct GemmCfg {
   static constexpr int kStageBytes = (kBM + BN) * kBK * 2;
   static constexpr int kStages = (BN == 256) ? 4 : 6;
   static constexpr int kTmemCols = 2 * BN;  // 256 or 512: both powers of two
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kStoreBytes = 4 /*warps*/ * 2 /*buffers*/ * 4096;  // [32 rows x 64 bf16] staging tiles
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStoreBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-__device__ __forceinline__ float apply_act(float x, int act) {
-  if (act == 1) return gelu_erf(x);
-  if (act == 2) return fmaxf(x, 0.0f);
-  if (act == 3) return gelu_tanh(x);
-  return x;
+// Activation over a 32-value register chunk.  The switch sits OUTSIDE the element loops on purpose: a per-element
+// if-chain gets if-converted by ptxas and then evaluates every activation for every element.
+__device__ __forceinline__ void apply_act32(float (&f)[32], int act) {
+  switch (act) {
+    case 1:
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
+      break;
+    case 2:
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.0f);
+      break;
+    case 3:
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = gelu_tanh(f[i]);
+      break;
+    case 4:
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = tanh_approx(f[i]);
+      break;
+    default:
+      break;
+  }
 }
 
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r,
                     const GemmEpilogue ep, int M, int N, int K) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* smem_store = smem + Cfg::kStages * Cfg::kStageBytes;  // 1024-aligned (stage bytes are multiples of 1 KB)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_store + Cfg::kStoreBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* tmem_full = empty_bar + Cfg::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* res_bar = tmem_empty + 2;  // [4 warps][2 buffers] residual-tile arrival
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 8);
 
   const uint32_t warp = warp_id();
   const uint32_t lane = lane_id();
@@ -91,6 +114,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 4);
     }
+    for (int i = 0; i < 8; ++i) mbar_init(&res_bar[i], 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -168,7 +192,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // ------------------------------- epilogue warps ------------------------------
     const uint32_t quad = warp & 3u;  // TMEM lane quadrant this warp may touch
     const uint32_t row_in_tile = quad * 32u + lane;
-    uint32_t acc = 0, acc_phase = 0;
+    uint32_t acc = 0, acc_phase = 0, store_cnt = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       int m_blk = t / num_n, n_blk = t % num_n;
       m_blk = (m_blk + ep.m_rotate) % num_m;
@@ -188,6 +212,75 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         c_row = reinterpret_cast<uint8_t*>(ep.c) + static_cast<size_t>(row) * ep.ldc * (ep.out_fp32 ? 4 : 2);
       }
       const __nv_bfloat16* r_row = ep.residual ? ep.residual + static_cast<size_t>(row) * ep.ldr : nullptr;
+      if (ep.tma_store) {
+        // ---- coalesced path: TMEM -> regs -> 128B-swizzled smem tile [32 rows x 64 cols] -> TMA store ----
+        const uint32_t ew = warp - 2;  // 0..3
+        const int tile_row0 = m_blk * kBM + static_cast<int>(quad * 32u);
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 64) {
+          const int col0 = n_blk * BN + c;
+          if (col0 >= N) break;
+          const uint32_t buf = store_cnt & 1u;
+          uint8_t* stage = smem_store + (ew * 2 + buf) * 4096;
+          if (lane == 0) tma_store_wait_read<1>();  // the store issued from this buffer two chunks ago has drained
+          __syncwarp();
+          if (ep.residual != nullptr) {
+            if (lane == 0) {
+              mbar_expect_tx(&res_bar[ew * 2 + buf], 4096);
+              tma_load_2d(stage, &tmap_r, &res_bar[ew * 2 + buf], col0, tile_row0);
+            }
+          }
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(tmem_base + ((quad * 32u) << 16) + acc * BN + c + half * 32, v);
+            tmem_ld_wait();
+            float f[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * ep.alpha;
+            const int cb = col0 + half * 32;
+            if (ep.bias != nullptr) {
+              if (cb + 32 <= N) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + cb) + j);
+                  f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (cb + i < N) f[i] += __ldg(ep.bias + cb + i);
+              }
+            }
+            apply_act32(f, ep.act);
+            if (ep.residual != nullptr && half == 0) mbar_wait(&res_bar[ew * 2 + buf], (store_cnt >> 1) & 1u);
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const int ch = (half * 4 + q4) ^ static_cast<int>(lane & 7u);
+              uint4* slot = reinterpret_cast<uint4*>(stage + lane * 128 + (ch << 4));
+              if (ep.residual != nullptr) {
+                const uint4 rq = *slot;
+                float2 a = unpack_bf16x2(rq.x), b = unpack_bf16x2(rq.y), cc = unpack_bf16x2(rq.z), d = unpack_bf16x2(rq.w);
+                f[q4 * 8 + 0] += a.x; f[q4 * 8 + 1] += a.y; f[q4 * 8 + 2] += b.x; f[q4 * 8 + 3] += b.y;
+                f[q4 * 8 + 4] += cc.x; f[q4 * 8 + 5] += cc.y; f[q4 * 8 + 6] += d.x; f[q4 * 8 + 7] += d.y;
+              }
+              uint4 q;
+              q.x = pack_bf16x2(f[q4 * 8 + 0], f[q4 * 8 + 1]);
+              q.y = pack_bf16x2(f[q4 * 8 + 2], f[q4 * 8 + 3]);
+              q.z = pack_bf16x2(f[q4 * 8 + 4], f[q4 * 8 + 5]);
+              q.w = pack_bf16x2(f[q4 * 8 + 6], f[q4 * 8 + 7]);
+              *slot = q;
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmap_c, stage, col0, tile_row0);
+            tma_store_commit();
+          }
+          ++store_cnt;
+        }
+      } else
 #pragma unroll 1
       for (int c = 0; c < BN; c += 32) {
         uint32_t v[32];
@@ -204,10 +297,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           for (int i = 0; i < 32; ++i)
             if (full_chunk || col0 + i < N) f[i] += __ldg(ep.bias + col0 + i);
         }
-        if (ep.act != 0) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = apply_act(f[i], ep.act);
-        }
+        apply_act32(f, ep.act);
         if (r_row != nullptr) {
           if (full_chunk) {
             const uint4* rp = reinterpret_cast<const uint4*>(r_row + col0);
@@ -268,6 +358,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         acc_phase ^= 1;
       }
     }
+    if (ep.tma_store && lane == 0) tma_store_wait_all<0>();
   }
 
   tc_fence_before();
@@ -276,8 +367,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 }
 
 template <int BN>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M, int N, int K,
-                       int max_ctas, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tr,
+                       const GemmEpilogue& ep, int M, int N, int K, int max_ctas, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool configured = false;
   if (!configured) {
@@ -289,7 +380,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmE
   int grid = tiles < sm_count() ? tiles : sm_count();
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   if (grid < 1) grid = 1;
-  gemm_bf16_tn_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, ep, M, N, K);
+  gemm_bf16_tn_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, tr, ep, M, N, K);
   IM_LAUNCH_OK("gemm_bf16_tn_kernel");
   return 0;
 }
@@ -303,7 +394,7 @@ IM_API int im_gemm_bf16_tn(const void* A, const void* B, void* C, const float* b
                            const uint32_t* a_ready, uint32_t a_epoch, int m_rotate, int max_ctas, void* stream) {
   using namespace im;
   if (M <= 0 || N <= 0 || K <= 0) return 0;
-  if ((lda % 8) || (ldb % 8) || (ldc % 8)) return set_error("im_gemm_bf16_tn", "leading dims must be multiples of 8");
+  if ((lda % 8) || (ldb % 8) || (ldc % 8) || (residual != nullptr && (ldr % 8))) return set_error("im_gemm_bf16_tn", "leading dims must be multiples of 8");
   if (peer_c != nullptr && (rows_per_rank % kBM) != 0)
     return set_error("im_gemm_bf16_tn", "rows_per_rank must be a multiple of 128 for the fused reduce-scatter");
   if (bn == 0) {
@@ -330,7 +421,16 @@ IM_API int im_gemm_bf16_tn(const void* A, const void* B, void* C, const float* b
   ep.a_epoch = a_epoch;
   const int num_m = (M + kBM - 1) / kBM;
   ep.m_rotate = num_m > 0 ? ((m_rotate % num_m) + num_m) % num_m : 0;
+  // coalesced TMA-store epilogue for plain local bf16 outputs
+  CUtensorMap tc = ta, tr = ta;
+  ep.tma_store = (!out_fp32 && peer_c == nullptr) ? 1 : 0;
+  if (ep.tma_store) {
+    if (get_tmap_2d(&tc, C, M, N, static_cast<uint64_t>(ldc) * 2, 32, 64, 2, TMAP_SW_128)) return -1;
+    if (residual != nullptr &&
+        get_tmap_2d(&tr, residual, M, N, static_cast<uint64_t>(ldr) * 2, 32, 64, 2, TMAP_SW_128))
+      return -1;
+  }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (bn == 256) return launch_gemm<256>(ta, tb, ep, M, N, K, max_ctas, s);
-  return launch_gemm<128>(ta, tb, ep, M, N, K, max_ctas, s);
+  if (bn == 256) return launch_gemm<256>(ta, tb, tc, tr, ep, M, N, K, max_ctas, s);
+  return launch_gemm<128>(ta, tb, tc, tr, ep, M, N, K, max_ctas, s);
 }

@@ -3,13 +3,14 @@
 // Replaces ChromaDB/hnswlib ANN search (reference infomesh/index/vector_store.py:187-254,
 // `collection.query(query_embeddings, n_results)`): the whole shard D[n_docs, dim] (bf16, rows
 // L2-normalised so dot == cosine) is streamed once from HBM by TMA, multiplied against the resident
-// query tile Q[<=128, dim] on tcgen05 (queries = MMA M rows -> TMEM lanes, documents = MMA N columns),
-// and every epilogue thread keeps the running top-K of ITS query row straight out of TMEM.  The
+// query tile Q[<=128, dim] on tcgen05 (documents = MMA M rows -> TMEM lanes, queries = MMA N columns);
+// every epilogue thread owns one document row, compares its scores against per-query thresholds in smem and,
+// on the rare hit, the warp cooperatively inserts into the CTA's sorted per-query list (lane i = entry i).  The
 // B x n_docs score matrix is never materialised; HBM traffic is exactly one pass over the shard.
 //
 //   warp 0      TMA producer  (Q once, then 128-doc x 64-dim tiles through an 8-deep ring)
 //   warp 1      MMA issuer    (tcgen05.mma 128x128x16, TMEM accumulator double-buffered)
-//   warps 2..5  epilogue      (tcgen05.ld -> per-thread sorted top-K in registers)
+//   warps 2..5  epilogue      (tcgen05.ld -> threshold filter -> warp-cooperative sorted insert in smem)
 //
 // Each persistent CTA writes one candidate list per query; topk_merge (below) reduces the per-CTA
 // lists, and the same kernel merges the per-GPU lists after the NVLink exchange (K4).
@@ -21,62 +22,68 @@
 
 namespace im {
 
-constexpr int kSimBM = 128;  // query rows (zero padded by TMA)
-constexpr int kSimBN = 128;  // documents per tile
+constexpr int kSimBM = 128;  // documents per tile (MMA M rows -> TMEM lanes)
 constexpr int kSimBK = 64;
 constexpr int kSimThreads = 192;
-constexpr int kSimTileBytes = kSimBN * kSimBK * 2;  // 16 KB
+constexpr int kSimTileBytes = kSimBM * kSimBK * 2;  // 16 KB
 constexpr int kSimMaxSmem = 227 * 1024;
 
-template <int KTOP>
-struct TopK {
-  float v[KTOP];
-  int id[KTOP];
-  __device__ __forceinline__ void init() {
-#pragma unroll
-    for (int i = 0; i < KTOP; ++i) {
-      v[i] = -CUDART_INF_F;
-      id[i] = -1;
+// Warp-cooperative insert of (s, d) into THIS WARP's sorted list of query j (score desc, id asc): lane i holds
+// entry i.  Lists are private to a warp (no locks); `thr[j]` is a CTA-shared lower bound (max of the warps'
+// K-th values, updated with a benign race) used only to reject candidates early.
+__device__ __forceinline__ void list_insert(volatile float* lv, volatile int* li, volatile float* thr, int K, int j,
+                                            float s, int d, uint32_t lane) {
+  const bool in = static_cast<int>(lane) < K;
+  float v = in ? lv[j * K + lane] : -CUDART_INF_F;
+  int id = in ? li[j * K + lane] : 0x7fffffff;
+  const bool before = in && ((v > s) || (v == s && id >= 0 && id < d));
+  const int pos = __popc(__ballot_sync(0xffffffffu, before));
+  if (pos < K) {
+    const float vu = __shfl_up_sync(0xffffffffu, v, 1);
+    const int iu = __shfl_up_sync(0xffffffffu, id, 1);
+    if (static_cast<int>(lane) == pos) {
+      v = s;
+      id = d;
+    } else if (static_cast<int>(lane) > pos) {
+      v = vu;
+      id = iu;
     }
-  }
-  __device__ __forceinline__ float vmin() const { return v[KTOP - 1]; }
-  // sorted descending; ties keep the earlier (lower id) entry because callers scan ids ascending
-  __device__ __forceinline__ void insert(float s, int d) {
-    v[KTOP - 1] = s;
-    id[KTOP - 1] = d;
-#pragma unroll
-    for (int i = KTOP - 1; i > 0; --i) {
-      const bool sw = v[i] > v[i - 1];
-      const float tv = v[i];
-      const int ti = id[i];
-      v[i] = sw ? v[i - 1] : v[i];
-      id[i] = sw ? id[i - 1] : id[i];
-      v[i - 1] = sw ? tv : v[i - 1];
-      id[i - 1] = sw ? ti : id[i - 1];
+    if (in && static_cast<int>(lane) >= pos) {
+      lv[j * K + lane] = v;
+      li[j * K + lane] = id;
     }
+    if (static_cast<int>(lane) == K - 1 && v > thr[j]) thr[j] = v;
   }
-};
+  __syncwarp();
+}
 
-template <int KTOP>
+// NPAD = queries padded to the MMA N granule (16); documents are the MMA M dimension so that every epilogue
+// thread owns ONE document row and compares its NPAD scores against per-query thresholds held in smem.
+template <int NPAD>
 __global__ void __launch_bounds__(kSimThreads, 1)
 sim_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_d, int nq,
-                int n_docs, int dim, int stages, const uint8_t* __restrict__ alive, float* __restrict__ out_scores,
-                int* __restrict__ out_ids) {
+                int n_docs, int dim, int stages, int ktop, const uint8_t* __restrict__ alive,
+                float* __restrict__ out_scores, int* __restrict__ out_ids) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   const int num_kb = dim / kSimBK;
-  uint8_t* smem_q = smem;                                   // num_kb tiles of [128 x 64] bf16
-  uint8_t* smem_d = smem + num_kb * (kSimBM * kSimBK * 2);  // ring of [128 docs x 64] tiles
+  constexpr int kQTileBytes = NPAD * kSimBK * 2;
+  uint8_t* smem_q = smem;                          // num_kb tiles of [NPAD x 64] bf16 (resident)
+  uint8_t* smem_d = smem + num_kb * kQTileBytes;   // ring of [128 docs x 64] tiles; NPAD*128 B keeps 1024 alignment
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_d + stages * kSimTileBytes);
   uint64_t* empty_bar = full_bar + stages;
   uint64_t* q_bar = empty_bar + stages;
   uint64_t* tmem_full = q_bar + 1;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* thr = reinterpret_cast<float*>(tmem_slot + 2);   // [NPAD] CTA-wide lower bound of the K-th best per query
+  float* list_v = reinterpret_cast<float*>(thr + NPAD);     // [4 warps][nq][ktop]
+  int* list_i = reinterpret_cast<int*>(list_v + 4 * nq * ktop);
 
+  constexpr uint32_t kTmemCols = (2 * NPAD) < 32 ? 32 : (2 * NPAD);
   const uint32_t warp = warp_id(), lane = lane_id();
-  const int num_tiles = (n_docs + kSimBN - 1) / kSimBN;
+  const int num_tiles = (n_docs + kSimBM - 1) / kSimBM;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
@@ -95,8 +102,13 @@ sim_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, 2 * kSimBN);
+    tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < NPAD; i += kSimThreads) thr[i] = -CUDART_INF_F;
+  for (int i = threadIdx.x; i < 4 * nq * ktop; i += kSimThreads) {
+    list_v[i] = -CUDART_INF_F;
+    list_i[i] = -1;
   }
   tc_fence_before();
   __syncthreads();
@@ -105,17 +117,15 @@ sim_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
   if (warp == 0) {
     if (lane == 0) {
-      // queries: resident for the whole kernel (re-read by every MMA)
-      mbar_expect_tx(q_bar, num_kb * kSimBM * kSimBK * 2);
-      for (int kb = 0; kb < num_kb; ++kb)
-        tma_load_2d(smem_q + kb * (kSimBM * kSimBK * 2), &tmap_q, q_bar, kb * kSimBK, 0);
+      mbar_expect_tx(q_bar, num_kb * kQTileBytes);
+      for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(smem_q + kb * kQTileBytes, &tmap_q, q_bar, kb * kSimBK, 0);
       const uint64_t pol = l2_policy_evict_first();  // the shard is streamed exactly once
       uint32_t stage = 0, phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], kSimTileBytes);
-          tma_load_2d_hint(smem_d + stage * kSimTileBytes, &tmap_d, &full_bar[stage], kb * kSimBK, t * kSimBN, pol);
+          tma_load_2d_hint(smem_d + stage * kSimTileBytes, &tmap_d, &full_bar[stage], kb * kSimBK, t * kSimBM, pol);
           if (++stage == (uint32_t)stages) {
             stage = 0;
             phase ^= 1;
@@ -125,19 +135,19 @@ sim_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(kSimBM, kSimBN);
+      constexpr uint32_t idesc = umma_idesc_f16(kSimBM, NPAD);
       mbar_wait(q_bar, 0);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       const uint32_t q0 = smem_u32(smem_q);
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * kSimBN;
+        const uint32_t d_tmem = tmem_base + acc * NPAD;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a0 = q0 + kb * (kSimBM * kSimBK * 2);
-          const uint32_t b0 = smem_u32(smem_d + stage * kSimTileBytes);
+          const uint32_t a0 = smem_u32(smem_d + stage * kSimTileBytes);  // documents: A operand
+          const uint32_t b0 = q0 + kb * kQTileBytes;                      // queries:   B operand
 #pragma unroll
           for (int k = 0; k < kSimBK / 16; ++k)
             umma_bf16(d_tmem, umma_desc_k_sw128(a0 + k * 32), umma_desc_k_sw128(b0 + k * 32), idesc,
@@ -157,36 +167,45 @@ sim_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
   } else {
     const uint32_t quad = warp & 3u;
-    const int qrow = static_cast<int>(quad * 32u + lane);
-    const bool warp_has_queries = static_cast<int>(quad * 32u) < nq;
-    TopK<KTOP> top;
-    top.init();
+    float* my_v = list_v + quad * nq * ktop;
+    int* my_i = list_i + quad * nq * ktop;
     uint32_t acc = 0, acc_phase = 0;
+    constexpr int kChunk = NPAD < 32 ? 16 : 32;  // TMEM columns per load
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      if (warp_has_queries) {
-        const int doc_base = t * kSimBN;
+      const int doc = t * kSimBM + static_cast<int>(quad * 32u + lane);
+      bool doc_ok = doc < n_docs;
+      if (doc_ok && alive != nullptr) doc_ok = alive[doc] != 0;
 #pragma unroll 1
-        for (int c = 0; c < kSimBN; c += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tmem_base + ((quad * 32u) << 16) + acc * kSimBN + c, v);
-          tmem_ld_wait();
-          float mx = __uint_as_float(v[0]);
+      for (int c = 0; c < NPAD; c += kChunk) {
+        uint32_t v[kChunk];
+        if constexpr (kChunk == 32) tmem_ld_32x32b_x32(tmem_base + ((quad * 32u) << 16) + acc * NPAD + c, v);
+        else tmem_ld_32x32b_x16(tmem_base + ((quad * 32u) << 16) + acc * NPAD + c, v);
+        tmem_ld_wait();
 #pragma unroll
-          for (int i = 1; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-          const bool row_ok = qrow < nq;
-          // warp-uniform fast reject: no lane (query) can improve its top-K from these 32 documents
-          if (__any_sync(0xffffffffu, row_ok && mx > top.vmin())) {
+        for (int g = 0; g < kChunk; g += 8) {
+          if (c + g >= nq) break;  // warp-uniform: padded query columns
+          const float4 t0 = *reinterpret_cast<const float4*>(thr + c + g);
+          const float4 t1 = *reinterpret_cast<const float4*>(thr + c + g + 4);
+          const float th[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+          uint32_t mask = 0;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float s = __uint_as_float(v[i]);
-              const int d = doc_base + c + i;
-              bool hit = row_ok && s > top.vmin() && d < n_docs;
-              if (hit && alive != nullptr) hit = alive[d] != 0;
-              // the (predicated, fully unrolled) insertion only runs for documents some lane actually wants
-              if (__any_sync(0xffffffffu, hit)) {
-                if (hit) top.insert(s, d);
+          for (int q = 0; q < 8; ++q) mask |= (__uint_as_float(v[g + q]) > th[q]) ? (1u << q) : 0u;
+          if (!doc_ok) mask = 0;
+          if (__any_sync(0xffffffffu, mask != 0)) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int j = c + g + q;
+              uint32_t hits = __ballot_sync(0xffffffffu, (mask >> q) & 1u);
+              if (j >= nq) hits = 0;
+              while (hits) {
+                const int src = __ffs(hits) - 1;
+                hits &= hits - 1;
+                const float s = __shfl_sync(0xffffffffu, __uint_as_float(v[g + q]), src);
+                const int d = __shfl_sync(0xffffffffu, doc, src);
+                if (s > *reinterpret_cast<volatile float*>(thr + j))
+                  list_insert(my_v, my_i, thr, ktop, j, s, d, lane);
               }
             }
           }
@@ -200,20 +219,32 @@ sim_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         acc_phase ^= 1;
       }
     }
-    if (qrow < nq) {
-      float* os = out_scores + (static_cast<size_t>(blockIdx.x) * nq + qrow) * KTOP;
-      int* oi = out_ids + (static_cast<size_t>(blockIdx.x) * nq + qrow) * KTOP;
-#pragma unroll
-      for (int i = 0; i < KTOP; ++i) {
-        os[i] = top.v[i];
-        oi[i] = top.id[i];
+    // all four epilogue warps are done inserting -> fold the per-warp lists into warp 0's (each warp owns the
+    // queries j == quad mod 4), then publish one candidate list per query for this CTA
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    for (int j = static_cast<int>(quad); j < nq; j += 4) {
+      for (int w = 1; w < 4; ++w) {
+        for (int e = 0; e < ktop; ++e) {
+          const float s = reinterpret_cast<volatile float*>(list_v)[(w * nq + j) * ktop + e];
+          const int d = reinterpret_cast<volatile int*>(list_i)[(w * nq + j) * ktop + e];
+          if (d < 0) break;
+          const float kth = reinterpret_cast<volatile float*>(list_v)[j * ktop + ktop - 1];
+          if (s < kth) break;  // sources are sorted: nothing further can enter
+          list_insert(list_v, list_i, thr, ktop, j, s, d, lane);
+        }
       }
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int et = static_cast<int>(threadIdx.x) - 64;
+    for (int i = et; i < nq * ktop; i += 128) {
+      out_scores[static_cast<size_t>(blockIdx.x) * nq * ktop + i] = list_v[i];
+      out_ids[static_cast<size_t>(blockIdx.x) * nq * ktop + i] = list_i[i];
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, 2 * kSimBN);
+  if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -346,37 +377,42 @@ topk_merge_kernel(const float* __restrict__ cand_scores, const int64_t* __restri
 }  // namespace im
 
 // Per-CTA candidate lists: out_scores/out_ids are [grid, nq, ktop]; returns grid (CTA count) or <0.
-IM_API int im_sim_topk(const void* Q, const void* D, int nq, int n_docs, int dim, int ldq, int ldd, int ktop,
-                       const uint8_t* alive, float* out_scores, int* out_ids, int max_ctas, void* stream) {
+template <int NPAD>
+static int launch_sim(const void* Q, const void* D, int nq, int n_docs, int dim, int ldq, int ldd, int ktop,
+                      const uint8_t* alive, float* out_scores, int* out_ids, int max_ctas, cudaStream_t s) {
   using namespace im;
-  if (nq < 1 || nq > kSimBM) return set_error("im_sim_topk", "nq must be in [1,128]");
-  if (dim % kSimBK != 0 || dim > 512) return set_error("im_sim_topk", "dim must be a multiple of 64 and <= 512");
-  if (ktop != 16 && ktop != 32) return set_error("im_sim_topk", "ktop must be 16 or 32");
   const int num_kb = dim / kSimBK;
-  const int q_bytes = num_kb * kSimBM * kSimBK * 2;
-  int stages = (kSimMaxSmem - 1024 - 512 - q_bytes) / kSimTileBytes;
+  const int q_bytes = num_kb * NPAD * kSimBK * 2;
+  const int misc = 1024 /*align*/ + 512 /*barriers*/ + NPAD * 4 + 4 * nq * ktop * 8;
+  int stages = (kSimMaxSmem - misc - q_bytes) / kSimTileBytes;
   if (stages > 12) stages = 12;
   if (stages < 2) return set_error("im_sim_topk", "not enough shared memory for the document ring");
-  const int smem_bytes = q_bytes + stages * kSimTileBytes + 1024 + 512;
-  const int num_tiles = (n_docs + kSimBN - 1) / kSimBN;
+  const int smem_bytes = q_bytes + stages * kSimTileBytes + misc;
+  const int num_tiles = (n_docs + kSimBM - 1) / kSimBM;
   int grid = num_tiles < sm_count() ? num_tiles : sm_count();
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   if (grid < 1) grid = 1;
   CUtensorMap tq, td;
-  if (get_tmap_2d(&tq, Q, nq, dim, static_cast<uint64_t>(ldq) * 2, kSimBM, kSimBK, 2, TMAP_SW_128)) return -1;
-  if (get_tmap_2d(&td, D, n_docs, dim, static_cast<uint64_t>(ldd) * 2, kSimBN, kSimBK, 2, TMAP_SW_128)) return -1;
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (ktop == 16) {
-    IM_CUDA_OK(cudaFuncSetAttribute(sim_topk_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    sim_topk_kernel<16><<<grid, kSimThreads, smem_bytes, s>>>(tq, td, nq, n_docs, dim, stages, alive, out_scores,
-                                                                 out_ids);
-  } else {
-    IM_CUDA_OK(cudaFuncSetAttribute(sim_topk_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    sim_topk_kernel<32><<<grid, kSimThreads, smem_bytes, s>>>(tq, td, nq, n_docs, dim, stages, alive, out_scores,
-                                                                 out_ids);
-  }
+  if (get_tmap_2d(&tq, Q, nq, dim, static_cast<uint64_t>(ldq) * 2, NPAD, kSimBK, 2, TMAP_SW_128)) return -1;
+  if (get_tmap_2d(&td, D, n_docs, dim, static_cast<uint64_t>(ldd) * 2, kSimBM, kSimBK, 2, TMAP_SW_128)) return -1;
+  IM_CUDA_OK(cudaFuncSetAttribute(sim_topk_kernel<NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  sim_topk_kernel<NPAD><<<grid, kSimThreads, smem_bytes, s>>>(tq, td, nq, n_docs, dim, stages, ktop, alive, out_scores,
+                                                               out_ids);
   IM_LAUNCH_OK("sim_topk_kernel");
   return grid;
+}
+
+IM_API int im_sim_topk(const void* Q, const void* D, int nq, int n_docs, int dim, int ldq, int ldd, int ktop,
+                       const uint8_t* alive, float* out_scores, int* out_ids, int max_ctas, void* stream) {
+  using namespace im;
+  if (nq < 1 || nq > 128) return set_error("im_sim_topk", "nq must be in [1,128]");
+  if (dim % kSimBK != 0 || dim > 512) return set_error("im_sim_topk", "dim must be a multiple of 64 and <= 512");
+  if (ktop < 1 || ktop > 32) return set_error("im_sim_topk", "ktop must be in [1,32]");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (nq <= 16) return launch_sim<16>(Q, D, nq, n_docs, dim, ldq, ldd, ktop, alive, out_scores, out_ids, max_ctas, s);
+  if (nq <= 32) return launch_sim<32>(Q, D, nq, n_docs, dim, ldq, ldd, ktop, alive, out_scores, out_ids, max_ctas, s);
+  if (nq <= 64) return launch_sim<64>(Q, D, nq, n_docs, dim, ldq, ldd, ktop, alive, out_scores, out_ids, max_ctas, s);
+  return launch_sim<128>(Q, D, nq, n_docs, dim, ldq, ldd, ktop, alive, out_scores, out_ids, max_ctas, s);
 }
 
 IM_API int im_topk_merge(const float* cand_scores, const int64_t* cand_ids64, const int* cand_ids32, int P, int nq,

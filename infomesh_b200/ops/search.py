@@ -74,7 +74,6 @@ def topk_merge(cand_scores, cand_ids, k_out, id_offset=0, out_scores=None, out_i
 
 def sim_topk(q, docs, k=10, alive=None, id_offset=0):
     """Exact top-``k`` cosine/dot search of ``q[nq<=128, dim]`` against ``docs[n, dim]``."""
-    ktop = 16 if k <= 16 else 32
-    assert k <= 32, "k > 32 is served by chunked search at the index level"
-    ps, pi = sim_topk_partials(q, docs, ktop=ktop, alive=alive)
+    assert 1 <= k <= 32, "k > 32 is served by chunked search at the index level"
+    ps, pi = sim_topk_partials(q, docs, ktop=k, alive=alive)
     return topk_merge(ps, pi, k, id_offset=id_offset)

@@ -1,0 +1,87 @@
+"""Model-side tokenisers.
+
+There is no network access for vocabulary files, so the default is a deterministic **hash word-piece**
+tokeniser: words (``\\w+`` runs, lower-cased) map to ``first_id + fnv1a(word) % (vocab - first_id)``.
+It has the right shape (one id per word, special tokens, truncation, padding) for the randomly initialised
+models; a real ``vocab.txt`` can be supplied to use exact WordPiece lookup instead.
+"""
+from __future__ import annotations
+
+import re
+from dataclasses import dataclass
+from pathlib import Path
+
+_WORD = re.compile(r"\w+", re.UNICODE)
+
+
+def fnv1a(data: bytes) -> int:
+    h = 0xCBF29CE484222325
+    for b in data:
+        h ^= b
+        h = (h * 0x100000001B3) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+@dataclass
+class SpecialTokens:
+    cls: int = 101
+    sep: int = 102
+    pad: int = 0
+    unk: int = 100
+    first_regular: int = 1000
+
+
+BERT_SPECIALS = SpecialTokens()
+XLMR_SPECIALS = SpecialTokens(cls=0, sep=2, pad=1, unk=3, first_regular=1000)
+T5_SPECIALS = SpecialTokens(cls=0, sep=1, pad=0, unk=2, first_regular=1000)
+
+
+class HashTokenizer:
+    def __init__(self, vocab_size: int, specials: SpecialTokens = BERT_SPECIALS, vocab_file: str | None = None):
+        self.vocab_size = vocab_size
+        self.sp = specials
+        self.vocab: dict[str, int] | None = None
+        if vocab_file and Path(vocab_file).exists():
+            self.vocab = {w.rstrip("\n"): i for i, w in enumerate(Path(vocab_file).read_text("utf-8").splitlines())}
+
+    def word_id(self, word: str) -> int:
+        if self.vocab is not None:
+            return self.vocab.get(word, self.sp.unk)
+        span = self.vocab_size - self.sp.first_regular
+        return self.sp.first_regular + fnv1a(word.encode("utf-8")) % span
+
+    def words(self, text: str) -> list[str]:
+        return _WORD.findall(text.lower())
+
+    def encode(self, text: str, max_len: int = 512, add_special: bool = True) -> list[int]:
+        ids = [self.word_id(w) for w in self.words(text)]
+        if add_special:
+            ids = [self.sp.cls] + ids[:max_len - 2] + [self.sp.sep]
+        return ids[:max_len]
+
+    def encode_plain(self, text: str, max_len: int) -> list[int]:
+        return [self.word_id(w) for w in self.words(text)][:max_len]
+
+    def encode_batch(self, texts: list[str], max_len: int = 512, pad_to_multiple: int = 8):
+        """-> (ids int32 [B, S], lengths int32 [B]) as torch CPU tensors (pinned when CUDA is present)."""
+        import torch
+
+        enc = [self.encode(t, max_len) for t in texts]
+        longest = max((len(e) for e in enc), default=1)
+        S = min(max_len, ((longest + pad_to_multiple - 1) // pad_to_multiple) * pad_to_multiple)
+        ids = torch.full((len(enc), S), self.sp.pad, dtype=torch.int32)
+        lens = torch.zeros((len(enc),), dtype=torch.int32)
+        for i, e in enumerate(enc):
+            ids[i, :len(e)] = torch.tensor(e, dtype=torch.int32)
+            lens[i] = len(e)
+        if torch.cuda.is_available():
+            ids, lens = ids.pin_memory(), lens.pin_memory()
+        return ids, lens
+
+    def decode(self, ids) -> str:
+        if self.vocab is None:
+            return " ".join(f"<{int(i)}>" for i in ids)
+        inv = getattr(self, "_inv", None)
+        if inv is None:
+            inv = self._inv = {i: w for w, i in self.vocab.items()}
+        return " ".join(inv.get(int(i), "[UNK]") for i in ids)
