@@ -128,7 +128,8 @@ bm25_and_topk_kernel(const long long* __restrict__ post_off, const int* __restri
         }
       }
       matched += hit ? 1 : 0;
-      uint32_t cand = __ballot_sync(0xffffffffu, hit && score > top.kth());
+      const float kth = top.kth();  // all lanes take part in the shuffle BEFORE the (short-circuiting) predicate
+      uint32_t cand = __ballot_sync(0xffffffffu, hit && score > kth);
       while (cand) {
         const int src = __ffs(cand) - 1;
         cand &= cand - 1;
