@@ -1,0 +1,263 @@
+"""GPU numerics: every CUDA kernel against a plain PyTorch fp32 (or NumPy / pure-Python) reference of the same op."""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _native_required():
+    from infomesh_b200 import _native
+
+    _native.require()          # fail loudly if the extension is missing on a GPU box
+    torch.manual_seed(0)
+
+
+@pytest.mark.parametrize("m,n,k,bias,act,resid,bn,fp32", [
+    (128, 128, 64, False, None, False, 0, False), (1000, 1152, 384, True, None, False, 0, False),
+    (2048, 1536, 384, True, "gelu", False, 0, False), (2048, 384, 1536, True, None, True, 0, False),
+    (4096, 768, 3072, True, None, True, 256, False), (300, 200, 72, False, None, False, 0, False),
+    (64, 384, 384, True, "relu", False, 0, True), (4096, 3072, 768, True, "gelu", False, 256, False),
+    (512, 512, 512, True, "tanh", False, 0, False),
+])
+def test_gemm_matches_fp32_reference(m, n, k, bias, act, resid, bn, fp32):
+    from infomesh_b200.ops.gemm import linear, linear_ref
+
+    a = (torch.randn(m, k, device=DEV) * 0.5).bfloat16()
+    w = (torch.randn(n, k, device=DEV) * 0.5).bfloat16()
+    b = torch.randn(n, device=DEV) if bias else None
+    r = torch.randn(m, n, device=DEV).bfloat16() if resid else None
+    out = linear(a, w, b, r, act, bn=bn, out_dtype=torch.float32 if fp32 else torch.bfloat16)
+    if act == "tanh":
+        ref = torch.tanh(a.float() @ w.float().t() + b)
+    else:
+        ref = linear_ref(a, w, b, r, act)
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 0.02 * ref.abs().max().item() + 0.05
+
+
+@pytest.mark.parametrize("nq,n,dim,k,alive", [(1, 1000, 384, 10, None), (7, 5000, 384, 10, None),
+                                               (64, 60000, 384, 10, None), (128, 100001, 384, 16, None),
+                                               (33, 30000, 384, 32, None), (64, 50000, 384, 10, 0.5),
+                                               (5, 130, 128, 10, None), (16, 20000, 512, 10, None)])
+def test_sim_topk_exact(nq, n, dim, k, alive):
+    from infomesh_b200.ops.search import sim_topk, sim_topk_ref
+
+    q = torch.nn.functional.normalize(torch.randn(nq, dim, device=DEV), dim=1).bfloat16()
+    d = torch.nn.functional.normalize(torch.randn(n, dim, device=DEV), dim=1).bfloat16()
+    mask = (torch.rand(n, device=DEV) < alive).to(torch.uint8) if alive is not None else None
+    s, i = sim_topk(q, d, k, alive=mask, id_offset=1000)
+    rs, ri = sim_topk_ref(q, d, k, alive=mask)
+    kk = rs.shape[1]
+    assert (s[:, :kk] - rs).abs().max().item() < 2e-3
+    assert (i[:, :kk] == ri + 1000).float().mean().item() > 0.98
+
+
+def test_topk_merge_dedup_and_order():
+    from infomesh_b200.ops.search import topk_merge
+
+    sc = torch.tensor([[[0.9, 0.5, 0.1]], [[0.9, 0.7, 0.2]]], device=DEV)                 # [P=2, nq=1, 3]
+    ids = torch.tensor([[[5, 8, 2]], [[3, 8, -1]]], device=DEV, dtype=torch.int64)
+    s, i = topk_merge(sc, ids, 4)
+    assert i[0].tolist() == [3, 5, 8, 2] and s[0, 0].item() == pytest.approx(0.9)          # tie -> lower id; 8 deduped
+
+
+@pytest.mark.parametrize("B,nH,hd,Sq,Sk,lens,causal,bias,scale,packed", [
+    (2, 12, 64, 128, 128, False, False, False, None, True), (2, 12, 64, 256, 256, True, False, False, None, True),
+    (3, 12, 32, 128, 128, False, False, False, None, True), (2, 12, 32, 384, 384, True, False, False, None, True),
+    (2, 8, 64, 256, 256, False, True, False, None, True), (2, 8, 64, 256, 256, True, False, True, 1.0, True),
+    (2, 8, 64, 128, 384, True, False, False, None, False), (2, 12, 64, 100, 100, True, False, False, None, True),
+    (1, 12, 32, 40, 40, False, False, False, None, True)])
+def test_attention_matches_reference(B, nH, hd, Sq, Sk, lens, causal, bias, scale, packed):
+    from infomesh_b200.ops.attention import attention, attention_ref
+
+    HH = nH * hd
+    if packed and Sq == Sk:
+        qkv = (torch.randn(B, Sq, 3 * HH, device=DEV) * 0.7).bfloat16()
+        q, k, v = qkv[..., :HH], qkv[..., HH:2 * HH], qkv[..., 2 * HH:]
+    else:
+        q = (torch.randn(B, Sq, HH, device=DEV) * 0.7).bfloat16()
+        kv = (torch.randn(B, Sk, 2 * HH, device=DEV) * 0.7).bfloat16()
+        k, v = kv[..., :HH], kv[..., HH:]
+    kv_lens = torch.randint(1, Sk + 1, (B,), device=DEV, dtype=torch.int32) if lens else None
+    rb = (torch.randn(nH, Sq + Sk - 1, device=DEV) * 0.5) if bias else None
+    off = Sk - Sq if causal else 0
+    o = attention(q, k, v, nH, kv_lens, causal, off, scale, rb)
+    ref = attention_ref(q, k, v, nH, kv_lens, causal, off, scale, rb)
+    assert (o.float() - ref).abs().max().item() < 0.03
+
+
+def test_attention_decode_matches_reference():
+    from infomesh_b200.ops.attention import attention_decode, attention_ref
+
+    B, nH, hd, S = 3, 8, 64, 50
+    q = (torch.randn(B, nH * hd, device=DEV) * 0.7).bfloat16()
+    kc = (torch.randn(B, 64, nH * hd, device=DEV) * 0.7).bfloat16()
+    vc = (torch.randn(B, 64, nH * hd, device=DEV) * 0.7).bfloat16()
+    lens = torch.tensor([S, 7, 64], device=DEV, dtype=torch.int32)
+    o = attention_decode(q, kc, vc, nH, lens)
+    ref = attention_ref(q[:, None], kc, vc, nH, kv_lens=lens)[:, 0]
+    assert (o.float() - ref).abs().max().item() < 0.03
+
+
+@pytest.mark.parametrize("H", [384, 768, 512])
+def test_norm_embed_pool_heads(H):
+    from infomesh_b200.ops import nn as N
+
+    V, S, B = 1000, 64, 4
+    ids = torch.randint(0, V, (B * S,), device=DEV, dtype=torch.int32)
+    word, pos, typ = (torch.randn(n, H, device=DEV).bfloat16() for n in (V, 512, 2))
+    g = torch.rand(H, device=DEV) + 0.5
+    b = torch.randn(H, device=DEV)
+    close = lambda x, y, tol: (x.float() - y.float()).abs().max().item() < tol  # noqa: E731
+    assert close(N.embed_ln(ids, word, pos, typ, g, b, 1e-12, S), N.embed_ln_ref(ids, word, pos, typ, g, b, 1e-12, S), 0.06)
+    x = torch.randn(B * S, H, device=DEV).bfloat16()
+    r = torch.randn(B * S, H, device=DEV).bfloat16()
+    assert close(N.layernorm(x, g, b, 1e-12, residual=r), N.layernorm_ref(x, g, b, 1e-12, r), 0.06)
+    assert close(N.layernorm(x, g, None, 1e-6, rms_only=True), N.layernorm_ref(x, g, None, 1e-6, None, True), 0.06)
+    parts = torch.randn(3, B * S, H, device=DEV).bfloat16()
+    assert close(N.layernorm(parts, g, b, 1e-5, partials=3, partial_stride=B * S * H),
+                 N.layernorm_ref(parts.float().sum(0), g, b, 1e-5), 0.08)
+    h = torch.randn(B, S, H, device=DEV).bfloat16()
+    lens = torch.tensor([64, 10, 33, 1], device=DEV, dtype=torch.int32)
+    assert close(N.pool_norm(h, lens, "cls"), N.pool_norm_ref(h, lens, "cls"), 0.01)
+    assert close(N.pool_norm(h, lens, "mean"), N.pool_norm_ref(h, lens, "mean"), 0.01)
+    w1 = (torch.randn(H, H, device=DEV) / math.sqrt(H)).bfloat16()
+    b1 = torch.randn(H, device=DEV) * 0.1
+    w2 = (torch.randn(1, H, device=DEV) / math.sqrt(H)).bfloat16()
+    b2 = torch.randn(1, device=DEV)
+    ref = (torch.tanh(h[:, 0].float() @ w1.float().t() + b1) @ w2.float().t()).squeeze(1) + b2
+    assert close(N.cls_head(h, w1, b1, w2, b2), ref, 0.02)
+    lg = torch.randn(7, 32128, device=DEV)
+    _, idx = N.row_argmax(lg, id_offset=5)
+    assert (idx.long() == lg.argmax(1) + 5).all()
+
+
+def test_bert_models_match_fp32_reference():
+    from infomesh_b200.models.bert import BGE_RERANKER_BASE, BGE_SMALL, BertModel
+
+    m = BertModel(BGE_SMALL, device=DEV, seed=1)
+    ids = torch.randint(5, 30000, (6, 128), device=DEV, dtype=torch.int32)
+    lens = torch.randint(40, 129, (6,), device=DEV, dtype=torch.int32)
+    e, r = m.embed(ids, lens).float(), m.embed_ref(ids, lens)
+    assert torch.nn.functional.cosine_similarity(e, r, dim=1).min().item() > 0.999
+    rr = BertModel(BGE_RERANKER_BASE, device=DEV, seed=2)
+    ids = torch.randint(5, 250000, (4, 128), device=DEV, dtype=torch.int32)
+    lens = torch.tensor([128, 77, 30, 100], device=DEV, dtype=torch.int32)
+    s, ref = rr.score(ids, lens), rr.score_ref(ids, lens)
+    assert (s - ref).abs().max().item() < 0.02
+
+
+def test_bm25_kernel_matches_oracle():
+    from infomesh_b200.engine.synth import SynthConfig, SynthShard, make_queries
+    from infomesh_b200.ops import bm25 as BM
+
+    cfg = SynthConfig(n_docs=40_000, n_docs_global=40_000, vocab_terms=4_000, doc_len=48, passage_len=64)
+    sh = SynthShard(cfg, device=DEV, build_chunk=15_000)
+    csr = dict(off=sh.bm25.off.cpu().numpy(), doc=sh.bm25.doc.cpu().numpy(), tf=sh.bm25.tf.cpu().numpy(),
+               doc_len=np.full(cfg.n_docs, cfg.doc_len, np.int32), df=sh.df_local.cpu().numpy())
+    qt, _, _, _ = make_queries(cfg, 32, device=DEV)
+    extra = torch.tensor([[5, -1, -1, -1, -1, -1, -1, -1], [3999, 3, -1, -1, -1, -1, -1, -1],
+                          [7000, 1, -1, -1, -1, -1, -1, -1], [-1] * 8], dtype=torch.int32)
+    qt = torch.cat([qt, extra])
+    s, i = sh.bm25.search(qt.to(DEV), k=20)
+    for q in range(qt.shape[0]):
+        ref = BM.bm25_ref(csr, qt[q].tolist(), k=20)
+        got = [(a, b) for a, b in zip(s[q].tolist(), i[q].tolist()) if b >= 0]
+        assert len(got) == len(ref)
+        for (rs, _), (gs, _) in zip(ref, got):
+            assert abs(rs - gs) <= 1e-3 * max(rs, 1e-6)
+        if ref and ref[-1][0] < ref[0][0] * 0.999:          # ids must agree wherever scores are not tied
+            assert got[0][1] == ref[0][1] or abs(ref[0][0] - ref[1][0]) < 1e-6
+
+
+def test_passage_simhash_hamming_fuse_kernels():
+    from infomesh_b200.ops import bm25 as BM
+    from infomesh_b200.ops import dedup as DD
+    from infomesh_b200.ops import fuse as F
+
+    tok = torch.randint(0, 50, (5000,), dtype=torch.int32)
+    pass_off = torch.tensor(sorted(set([0, 5000] + torch.randint(1, 4999, (60,)).tolist())), dtype=torch.int64)
+    n_pass = pass_off.numel() - 1
+    doc_pass = torch.tensor([0, n_pass // 3, n_pass // 3, n_pass], dtype=torch.int64)
+    qt = torch.tensor([[1, 2, 3, -1], [7, 9, 49, -1], [60, 61, -1, -1]], dtype=torch.int32)
+    pd = torch.tensor([0, 2, 1, 2, 0], dtype=torch.int32)
+    pq = torch.tensor([0, 1, 0, 2, 1], dtype=torch.int32)
+    os_, op_ = BM.passage_score(tok.to(DEV), pass_off.to(DEV), doc_pass.to(DEV), pd.to(DEV), pq.to(DEV), qt.to(DEV))
+    for p in range(5):
+        d, q = int(pd[p]), int(pq[p])
+        if doc_pass[d + 1] > doc_pass[d]:
+            rs, rp = BM.passage_score_ref(tok.numpy(), pass_off[doc_pass[d]:doc_pass[d + 1] + 1].tolist(), qt[q].tolist())
+        else:
+            rs, rp = 0.0, -1
+        assert rp == int(op_[p]) and abs(rs - float(os_[p])) < 1e-5
+
+    texts = ["The quick brown fox jumps over the lazy dog " * 3, "", "one", "one two", "Héllo wörld ünïcode " * 5,
+             "x" * 300 + " long words " + "y" * 70] + [f"doc number {i} about gpus {i * i}" for i in range(100)]
+    fp = DD.simhash_batch(texts, device=DEV)
+    want = np.asarray([DD.simhash_py(t) for t in texts], dtype=np.uint64).view(np.int64)
+    assert (fp.cpu().numpy() == want).all()                                   # bit-exact with md5(shingle)[:8] BE
+    table = torch.from_numpy(np.random.default_rng(0).integers(0, 2**63, 100_001, dtype=np.int64)).to(DEV)
+    probes = table[[5, 77, 100_000]].clone()
+    probes[0] ^= 0b101
+    probes[1] ^= (1 << 40) | (1 << 3) | (1 << 9) | (1 << 20)
+    dist, idx = DD.unpack_best(DD.hamming_scan(table, probes, 3))
+    assert dist.tolist() == [2, -1, 0] and idx.tolist() == [5, -1, 100_000]
+
+    g = torch.Generator().manual_seed(0)
+    ids_a = torch.stack([torch.randperm(60, generator=g)[:20] for _ in range(64)]).long()
+    ids_b = torch.stack([torch.randperm(60, generator=g)[:20] for _ in range(64)]).long()
+    ids_a[3, 10:] = -1
+    ids_b[4, :] = -1
+    ids_a[5, :] = -1
+    ids_b[5, :] = -1
+    rs, ri = F.rrf_fuse_ref(ids_a, ids_b, 20)
+    gs, gi = F.rrf_fuse(ids_a.to(DEV), ids_b.to(DEV), 20)
+    assert (gi.cpu() == ri).all() and torch.allclose(gs.cpu()[ri >= 0], rs[ri >= 0], atol=1e-6)
+    tok_store = torch.randint(1000, 5000, (60, 24), dtype=torch.int32)
+    len_store = torch.randint(0, 25, (60,), dtype=torch.int32)
+    q_tok = torch.randint(1000, 5000, (64, 8), dtype=torch.int32)
+    q_len = torch.randint(1, 9, (64,), dtype=torch.int32)
+    rp, rl = F.build_pairs_ref(q_tok, q_len, ri, tok_store, len_store, 24, 48)
+    ts, ls = tok_store.to(DEV), len_store.to(DEV)
+    gp, gl = F.build_pairs(q_tok.to(DEV), q_len.to(DEV), gi, F.ptr_table([ts], DEV), F.ptr_table([ls], DEV), 60, 24, 48)
+    assert (gp.cpu() == rp).all() and (gl.cpu() == rl).all()
+    logits = torch.randn(64, 20)
+    logits[2, 3] = float("nan")
+    _, si = F.rerank_select(logits.to(DEV), gi, 10)
+    for q in range(64):
+        lq = logits[q].clone()
+        lq[(ri[q] < 0) | torch.isnan(lq)] = float("-inf")
+        order = sorted(range(20), key=lambda c: (-lq[c].item(), c))[:10]
+        assert [int(ri[q][c]) for c in order] == si[q].cpu().tolist()
+
+
+def test_hybrid_engine_end_to_end_matches_torch_backend():
+    """The fused pipeline and the PyTorch (cuBLAS/SDPA) build of the same pipeline agree on the retrieved ids."""
+    from infomesh_b200.engine.hybrid import HybridConfig, HybridEngine
+    from infomesh_b200.engine.synth import SynthConfig, SynthShard, make_queries
+    from infomesh_b200.models.bert import BertConfig, BertModel
+
+    cfg = SynthConfig(n_docs=30_000, n_docs_global=30_000, vocab_terms=5_000, doc_len=32, passage_len=48)
+    shard = SynthShard(cfg, device=DEV)
+    enc = BertModel(BertConfig(name="t-enc", layers=2), device=DEV, seed=1)
+    qt, qtok, qlen, _ = make_queries(cfg, 16, device=DEV)
+    enc_ids = torch.zeros((16, 32), dtype=torch.int32)
+    enc_ids[:, 0] = 101
+    enc_ids[:, 1:4] = (qtok[:, :3] % 20000) + 1000
+    enc_ids[:, 4] = 102
+    enc_len = torch.full((16,), 5, dtype=torch.int32)
+    outs = {}
+    for backend in ("fused", "torch"):
+        eng = HybridEngine(shard, HybridConfig(nq=16, rerank=False, backend=backend, use_graph=(backend == "fused")),
+                           encoder=enc)
+        s, i = eng.search_batch(enc_ids.to(DEV), enc_len.to(DEV), qtok.to(DEV), qlen.to(DEV), qt.to(DEV))
+        outs[backend] = i
+    agree = (outs["fused"] == outs["torch"]).float().mean().item()
+    assert agree > 0.9 and (outs["fused"][:, 0] >= 0).all()
