@@ -1,0 +1,87 @@
+"""Language identification without external models: Unicode script shares first, then function-word frequency for
+Latin / Cyrillic languages (reference infomesh/crawler/lang_detect.py:302-445)."""
+from __future__ import annotations
+
+import re
+from dataclasses import dataclass
+
+
+@dataclass(frozen=True)
+class LanguageDetection:
+    language: str          # ISO 639-1, "und" when undetermined
+    confidence: float      # 0..1
+    script: str = "latin"
+
+
+_SCRIPTS: tuple[tuple[str, str, re.Pattern[str]], ...] = (
+    ("ko", "hangul", re.compile(r"[가-힯ᄀ-ᇿ㄰-㆏]")),
+    ("ja", "kana", re.compile(r"[぀-ゟ゠-ヿ]")),
+    ("zh", "han", re.compile(r"[一-鿿㐀-䶿]")),
+    ("th", "thai", re.compile(r"[฀-๿]")),
+    ("ar", "arabic", re.compile(r"[؀-ۿݐ-ݿ]")),
+    ("hi", "devanagari", re.compile(r"[ऀ-ॿ]")),
+    ("ru", "cyrillic", re.compile(r"[Ѐ-ӿ]")),
+    ("el", "greek", re.compile(r"[Ͱ-Ͽ]")),
+    ("he", "hebrew", re.compile(r"[֐-׿]")),
+)
+_WORD = re.compile(r"[^\W\d_]+", re.UNICODE)
+
+_COMMON: dict[str, frozenset[str]] = {
+    "en": frozenset("the of and to in is that it for was on are with as be this have from or by not but what all "
+                    "were when we there can an your which their said if will each about how up out them then she".split()),
+    "es": frozenset("de la que el en y a los del se las por un para con no una su al lo como más pero sus le ya o "
+                    "este sí porque esta entre cuando muy sin sobre también me hasta hay donde quien desde".split()),
+    "fr": frozenset("de la le et les des en un du une que est pour qui dans par plus pas au sur ne se ce il sont "
+                    "avec son lui nous comme mais on ou si leur y dont elle tout aux ces être cette été".split()),
+    "de": frozenset("der die und in den von zu das mit sich des auf für ist im dem nicht ein eine als auch es an "
+                    "werden aus er hat dass sie nach wird bei einer um am sind noch wie einem über einen so zum".split()),
+    "pt": frozenset("de a o que e do da em um para é com não uma os no se na por mais as dos como mas foi ao ele "
+                    "das tem à seu sua ou ser quando muito há nos já está eu também só pelo pela até isso".split()),
+    "it": frozenset("di e il la che in a per un è del non con le si una i da al sono come più ma lo ha dei nel "
+                    "alla delle gli anche questo su se o della quando era ci essere tra tutti".split()),
+    "nl": frozenset("de van het een en in is dat op te zijn voor met die niet aan er om ook als dan maar bij of "
+                    "uit nog naar door over ze zich heeft worden tot deze kan wordt hij".split()),
+    "tr": frozenset("ve bir bu da de için ile olarak çok daha ama en gibi ne o var mi mı ya hem ki kadar sonra "
+                    "önce her şey ben sen biz değil yok olan oldu".split()),
+    "vi": frozenset("và của là có trong cho không được với các một những này đó khi đã sẽ đang từ đến như về "
+                    "tại bởi vì nên nhưng hoặc nếu thì mà cũng rất".split()),
+    "id": frozenset("yang dan di ke dari untuk pada dengan ini itu adalah tidak akan atau juga oleh sebagai dalam "
+                    "ada saya kami kita anda dia mereka telah sudah bisa dapat harus karena".split()),
+    "ru": frozenset("и в не на я что он с как а то все она так его но да ты к у же вы за бы по только ее мне "
+                    "было вот от меня еще нет о из ему".split()),
+    "uk": frozenset("і в не на я що він з як а то все вона так його але та ти до у ж ви за би по тільки її мені "
+                    "було ось від мене ще немає про із йому це є".split()),
+}
+_CYRILLIC = ("ru", "uk")
+
+
+def detect_language(text: str) -> LanguageDetection:
+    if not text or not text.strip():
+        return LanguageDetection("und", 0.0, "unknown")
+    sample = text[:5000]
+    letters = sum(1 for ch in sample if ch.isalpha())
+    if letters == 0:
+        return LanguageDetection("und", 0.0, "unknown")
+    shares = {lang: (script, len(rx.findall(sample)) / letters) for lang, script, rx in _SCRIPTS}
+    # Japanese text mixes kana with han: any meaningful kana share wins over "zh"
+    if shares["ja"][1] >= 0.05:
+        return LanguageDetection("ja", min(1.0, 0.6 + shares["ja"][1] + shares["zh"][1]), "kana")
+    best_lang, (best_script, best_share) = max(shares.items(), key=lambda kv: kv[1][1])
+    if best_share >= 0.3 and best_lang != "ru":
+        return LanguageDetection(best_lang, min(1.0, 0.5 + best_share / 2), best_script)
+    words = [w.lower() for w in _WORD.findall(sample)]
+    if not words:
+        return LanguageDetection("und", 0.0, "unknown")
+    cyrillic = best_lang == "ru" and best_share >= 0.3
+    pool = _CYRILLIC if cyrillic else [k for k in _COMMON if k not in _CYRILLIC]
+    hits = {lang: sum(1 for w in words if w in _COMMON[lang]) for lang in pool}
+    lang = max(hits, key=lambda k: hits[k])
+    total = hits[lang]
+    if total == 0:
+        return LanguageDetection("ru" if cyrillic else "und", 0.35 if cyrillic else 0.0,
+                                 "cyrillic" if cyrillic else "latin")
+    ranked = sorted(hits.values(), reverse=True)
+    margin = (ranked[0] - ranked[1]) / ranked[0] if len(ranked) > 1 else 1.0
+    density = min(1.0, total / max(len(words), 1) * 4)
+    return LanguageDetection(lang, round(min(1.0, 0.25 + 0.45 * density + 0.3 * margin), 3),
+                             "cyrillic" if cyrillic else "latin")

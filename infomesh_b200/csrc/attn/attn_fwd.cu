@@ -28,6 +28,7 @@ struct AttnParams {
   int causal_offset;
   float scale_log2;       // softmax scale * log2(e)
   const float* rel_bias;  // [nH, Sq + Sk - 1] additive bias indexed by (j - i) + (Sq - 1), or null (already * log2e)
+  int alias_p;            // single-chunk, HD == 64: P overwrites the (dead) Q+K tiles -> 48 KB smem, 4 CTAs / SM
 };
 
 constexpr int kAttnThreads = 128;
@@ -40,7 +41,7 @@ struct AttnCfg {
   static constexpr int kRowBytes = HD * 2;                 // 128 (SW128) or 64 (SW64)
   static constexpr int kTileBytes = kAttnBQ * kRowBytes;   // Q / K / V tile
   static constexpr int kPBytes = kAttnBQ * kAttnBKV * 2;   // 32 KB, two [128 x 64] SW128 k-blocks
-  static constexpr int kTmemCols = 256;                    // S: 128, O: HD (<= 128)
+  static constexpr int kTmemCols = 128;                    // S: 128 columns; O_c reuses S[0, HD) once P left TMEM
   static constexpr int kGroupBytes = 8 * kRowBytes;        // 8-row swizzle group (SBO)
 };
 
@@ -64,8 +65,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + Cfg::kTileBytes;
   uint8_t* sV = sK + Cfg::kTileBytes;
-  uint8_t* sP = sV + Cfg::kTileBytes;  // offsets stay multiples of 1024 (tile bytes are 8 KB or 16 KB)
-  uint64_t* q_bar = reinterpret_cast<uint64_t*>(sP + Cfg::kPBytes);
+  // offsets stay multiples of 1024 (tile bytes are 8 KB or 16 KB)
+  uint8_t* sP = p.alias_p ? sQ : sV + Cfg::kTileBytes;
+  uint64_t* q_bar = reinterpret_cast<uint64_t*>(sV + Cfg::kTileBytes + (p.alias_p ? 0 : Cfg::kPBytes));
   uint64_t* k_bar = q_bar + 1;
   uint64_t* v_bar = q_bar + 2;
   uint64_t* s_bar = q_bar + 3;
@@ -108,7 +110,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_s = tmem_base;        // 128 columns
-  const uint32_t tmem_o = tmem_base + 128;  // HD columns
+  const uint32_t tmem_o = tmem_base;        // HD columns, aliasing S (S is dead once P sits in smem)
   const uint32_t lane_base = (warp * 32u) << 16;
 
   if (tid == 0 && num_chunks > 0) {
@@ -343,11 +345,12 @@ IM_API int im_attn_fwd(const void* q, const void* k, const void* v, void* out, i
   p.causal_offset = causal_offset;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.rel_bias = rel_bias_log2;
+  p.alias_p = (head_dim == 64 && Sk <= kAttnBKV) ? 1 : 0;
   const int bias_bytes = rel_bias_log2 ? (Sq + Sk) * 4 : 0;
   dim3 grid((Sq + kAttnBQ - 1) / kAttnBQ, n_heads, B);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (head_dim == 64) {
-    const int smem = 3 * AttnCfg<64>::kTileBytes + AttnCfg<64>::kPBytes + 1024 + 64 + bias_bytes;
+    const int smem = 3 * AttnCfg<64>::kTileBytes + (p.alias_p ? 0 : AttnCfg<64>::kPBytes) + 1024 + 64 + bias_bytes;
     IM_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attn_fwd_kernel<64><<<grid, kAttnThreads, smem, s>>>(tq, tk, tv, p);
   } else {
