@@ -272,7 +272,11 @@ def main() -> int:
         }
         if lat_b1 is not None:
             result["latency_batch1_p50_ms"] = round(lat_b1, 4)
-        print(json.dumps(result))
+        print(json.dumps(result), flush=True)
+    # graphs hold references to the NCCL communicator: drop them before tearing the group down
+    eng._graph = None
+    if lat_b1 is not None:
+        eng1._graph = None
     D.shutdown()
     return 0
 

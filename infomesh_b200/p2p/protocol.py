@@ -58,6 +58,17 @@ class MessageType(IntEnum):
     PEX_RESPONSE = 91
     ERROR = 99
     SIGNED_ENVELOPE = 100
+    # --- built-in transport / Kademlia RPCs (the reference delegates these to py-libp2p's own protocols)
+    HELLO = 110
+    HELLO_ACK = 111
+    DHT_FIND_NODE = 120
+    DHT_NODES = 121
+    DHT_FIND_VALUE = 122
+    DHT_VALUE = 123
+    DHT_STORE = 124
+    DHT_STORE_ACK = 125
+    LLM_REQUEST = 130
+    LLM_RESPONSE = 131
 
 
 def _now() -> float:

@@ -59,10 +59,35 @@ def ctx() -> DistContext:
     return _ctx if _ctx is not None else init()
 
 
-def shutdown() -> None:
+def shutdown(grace_s: float = 15.0) -> None:
+    """Tear the process group down.  NCCL communicators that were captured into CUDA graphs can make
+    ``destroy_process_group`` block forever; the teardown therefore runs under a watchdog and the process leaves
+    with ``os._exit(0)`` (after flushing stdio) if it has not finished within ``grace_s``."""
     global _ctx
     if dist.is_initialized():
-        dist.destroy_process_group()
+        import os
+        import sys
+        import threading
+
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        try:
+            dist.barrier()
+        except Exception:  # noqa: BLE001
+            pass
+        done = threading.Event()
+
+        def _destroy():
+            try:
+                dist.destroy_process_group()
+            finally:
+                done.set()
+
+        threading.Thread(target=_destroy, daemon=True, name="pg-destroy").start()
+        if not done.wait(grace_s):
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
     _ctx = None
 
 
