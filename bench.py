@@ -118,6 +118,8 @@ def main() -> int:
     ap.add_argument("--pair-seq", type=int, default=128)
     ap.add_argument("--no-rerank", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="multi-GPU candidate exchange: fused peer-memory kernels or NCCL all-gathers (baseline)")
     ap.add_argument("--latency-b1", action="store_true", help="also measure batch-1 p50 latency")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -152,7 +154,7 @@ def main() -> int:
     build_s = time.time() - t0
 
     hcfg = HybridConfig(nq=args.batch, pair_seq=args.pair_seq, rerank=not args.no_rerank, backend=args.impl,
-                        use_graph=not args.no_graph)
+                        use_graph=not args.no_graph, exchange=args.exchange)
     eng = HybridEngine(shard, hcfg, docs_per_shard=(n_global if world > 1 else n_local))
 
     # ---- query batches on pinned host memory (distinct per step so nothing is cached between iterations) ----
@@ -221,7 +223,7 @@ def main() -> int:
     lat_b1 = None
     if args.latency_b1:
         cfg1 = HybridConfig(nq=world, pair_seq=args.pair_seq, rerank=not args.no_rerank, backend=args.impl,
-                            use_graph=not args.no_graph)
+                            use_graph=not args.no_graph, exchange=args.exchange)
         eng1 = HybridEngine(shard, cfg1, encoder=eng.encoder, reranker=eng.reranker,
                             docs_per_shard=(n_global if world > 1 else n_local))
         b1 = [tuple(x[:world] for x in b) for b in dev_batches]
@@ -260,6 +262,7 @@ def main() -> int:
                 "l2_policy": "inputs larger than L2: every step streams the whole shard "
                              f"({shard.nbytes() / 1e9:.1f} GB/rank) and uses a distinct query batch",
                 "cuda_graph": bool(eng._graph is not None),
+                "exchange": ("none" if world == 1 else ("p2p-fused" if eng.heap is not None else "nccl")),
                 "index_build_s": round(build_s, 1),
             },
             "e2e": {"value": round(qps_e2e, 2), "unit": "queries/s", "ms_per_step": round(e2e_ms / args.steps, 4),

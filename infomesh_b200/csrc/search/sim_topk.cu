@@ -260,7 +260,7 @@ topk_merge_kernel(const float* __restrict__ cand_scores, const int64_t* __restri
                   float* __restrict__ out_scores, int64_t* __restrict__ out_ids,
                   // fused exchange (all optional)
                   float* const* peer_scores, int64_t* const* peer_ids, uint32_t* const* peer_flags, int world, int rank,
-                  const uint32_t* wait_flags, uint32_t epoch) {
+                  const uint32_t* wait_flags, const uint32_t* step_ptr) {
   extern __shared__ uint8_t msm[];
   const int q = blockIdx.x;
   const int n = P * k_in;
@@ -270,18 +270,28 @@ topk_merge_kernel(const float* __restrict__ cand_scores, const int64_t* __restri
   __shared__ int64_t red_i[kMergeThreads / 32];
   __shared__ int red_p[kMergeThreads / 32];
   __shared__ int win_pos;
+  __shared__ int64_t win_id;
 
+  // Exchange protocol (see comm/symm.cu): receive areas are [2][world][nq][k] double-buffered on step parity,
+  // arrival counters are cumulative: one arrival per query block per step.
+  const uint32_t step = step_ptr != nullptr ? *step_ptr : 0u;
   if (wait_flags != nullptr) {
-    if (threadIdx.x < static_cast<unsigned>(world)) {
+    if (threadIdx.x < static_cast<unsigned>(P)) {
+      const uint32_t target = (step + 1u) * static_cast<uint32_t>(nq);
       uint32_t spins = 0;
-      while (ld_acquire_sys(wait_flags + threadIdx.x) < epoch) {
+      while (static_cast<int32_t>(ld_acquire_sys(wait_flags + threadIdx.x) - target) < 0) {
         if (++spins > IM_WAIT_LIMIT) {
           printf("[infomesh_b200] topk_merge flag timeout peer=%d\n", (int)threadIdx.x);
           __trap();
         }
+        __nanosleep(20);
       }
     }
     __syncthreads();
+    const size_t par = static_cast<size_t>(step & 1u) * P * nq * k_in;
+    cand_scores += par;
+    if (cand_ids64 != nullptr) cand_ids64 += par;
+    if (cand_ids32 != nullptr) cand_ids32 += par;
   }
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const int p = i / k_in, j = i % k_in;
@@ -335,13 +345,14 @@ topk_merge_kernel(const float* __restrict__ cand_scores, const int64_t* __restri
       win_pos = bp;
       const float osc = bp >= 0 ? bv : -CUDART_INF_F;
       const int64_t oid = bp >= 0 ? bi : -1;
+      win_id = oid;
       if (out_scores != nullptr) {
         out_scores[static_cast<size_t>(q) * k_out + r] = osc;
         out_ids[static_cast<size_t>(q) * k_out + r] = oid;
       }
       if (peer_scores != nullptr) {
         for (int p = 0; p < world; ++p) {
-          const size_t dst = (static_cast<size_t>(rank) * nq + q) * k_out + r;
+          const size_t dst = ((static_cast<size_t>(step & 1u) * world + rank) * nq + q) * k_out + r;
           peer_scores[p][dst] = osc;
           peer_ids[p][dst] = oid;
         }
@@ -354,7 +365,7 @@ topk_merge_kernel(const float* __restrict__ cand_scores, const int64_t* __restri
     __syncthreads();
     // duplicate suppression across lists: any other candidate with the same id is retired
     if (win_pos >= 0) {
-      const int64_t wid = out_ids != nullptr ? out_ids[static_cast<size_t>(q) * k_out + r] : -2;
+      const int64_t wid = win_id;
       if (wid >= 0)
         for (int i = threadIdx.x; i < n; i += blockDim.x)
           if (s_id[i] == wid) s_id[i] = -1;
@@ -418,7 +429,7 @@ IM_API int im_sim_topk(const void* Q, const void* D, int nq, int n_docs, int dim
 IM_API int im_topk_merge(const float* cand_scores, const int64_t* cand_ids64, const int* cand_ids32, int P, int nq,
                          int k_in, int k_out, int64_t id_offset, float* out_scores, int64_t* out_ids,
                          float* const* peer_scores, int64_t* const* peer_ids, uint32_t* const* peer_flags, int world,
-                         int rank, const uint32_t* wait_flags, uint32_t epoch, void* stream) {
+                         int rank, const uint32_t* wait_flags, const uint32_t* step_ptr, void* stream) {
   using namespace im;
   if (nq <= 0) return 0;
   const size_t n = static_cast<size_t>(P) * k_in;
@@ -428,7 +439,7 @@ IM_API int im_topk_merge(const float* cand_scores, const int64_t* cand_ids64, co
     IM_CUDA_OK(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   topk_merge_kernel<<<nq, kMergeThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
       cand_scores, cand_ids64, cand_ids32, P, nq, k_in, k_out, id_offset, out_scores, out_ids, peer_scores, peer_ids,
-      peer_flags, world, rank, wait_flags, epoch);
+      peer_flags, world, rank, wait_flags, step_ptr);
   IM_LAUNCH_OK("topk_merge_kernel");
   return 0;
 }

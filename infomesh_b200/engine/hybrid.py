@@ -37,6 +37,7 @@ class HybridConfig:
     rerank: bool = True
     backend: str = "fused"    # "fused" | "torch"
     use_graph: bool = True
+    exchange: str = "p2p"     # multi-GPU list exchange: "p2p" (fused peer-memory kernels) | "nccl" (baseline collectives)
 
 
 class HybridEngine:
@@ -73,6 +74,18 @@ class HybridEngine:
         self.out_ids = torch.full((cfg.nq, cfg.k_out), -1, device=dev, dtype=torch.int64)
         self._graph = None
         self._graph_failed = False
+        self.heap = None
+        if self.ctx.is_dist and cfg.backend == "fused" and cfg.exchange == "p2p":
+            from infomesh_b200.parallel import symm
+
+            self.heap = symm.SymmetricHeap(8 << 20, self.ctx)
+            self.ch_dense = symm.TopkChannel(self.heap, cfg.nq, cfg.k_fetch)
+            self.ch_bm25 = symm.TopkChannel(self.heap, cfg.nq, cfg.k_fetch)
+            n_log = self.nq_local * cfg.n_rerank
+            self._log_pad = (n_log + 3) // 4 * 4           # 16-byte blocks
+            self.ch_logits = symm.AllGatherChannel(self.heap, (self._log_pad,), torch.float32)
+            self._log_stage = torch.zeros((self._log_pad,), device=dev, dtype=torch.float32)
+            self.heap.barrier()
 
     # ------------------------------------------------------------------ stages
     def _encode(self):
@@ -86,16 +99,25 @@ class HybridEngine:
             sc = q_emb @ sh.vectors.t()
             v, i = torch.topk(sc.float(), min(cfg.k_fetch, sh.vectors.shape[0]), dim=1)
             return v, i.long() + sh.cfg.doc_base
-        return S.sim_topk(q_emb, sh.vectors, cfg.k_fetch, alive=sh.alive, id_offset=sh.cfg.doc_base)
+        return S.sim_topk(q_emb, sh.vectors, cfg.k_fetch, alive=sh.alive, id_offset=sh.cfg.doc_base,
+                          push=self.ch_dense if self.heap is not None else None)
 
     def _bm25_local(self):
         sh = self.shard
-        return sh.bm25.search(self.in_terms, k=self.cfg.k_fetch, alive=sh.alive, id_offset=sh.cfg.doc_base)
+        s, i = sh.bm25.search(self.in_terms, k=self.cfg.k_fetch, alive=sh.alive, id_offset=sh.cfg.doc_base)
+        if self.heap is not None:      # 1-list "merge" whose epilogue pushes the shard's list to every peer
+            S.topk_merge(s.unsqueeze(0), i.unsqueeze(0), self.cfg.k_fetch, push=self.ch_bm25)
+        return s, i
 
-    def _exchange(self, scores, ids):
-        """per-shard top-k lists [nq, k] -> global top-k on every rank (all-gather + merge)."""
+    def _exchange(self, scores, ids, chan=None):
+        """per-shard top-k lists [nq, k] -> global top-k on every rank.
+
+        p2p: the producers already pushed their lists into every rank's receive area; one merge kernel waits on the
+        arrival counters and merges.  nccl: all-gather + merge (baseline)."""
         if not self.ctx.is_dist:
             return scores, ids
+        if self.heap is not None:
+            return S.topk_merge(chan.cand_scores, chan.cand_ids, scores.shape[1], wait=chan)
         gs = D.all_gather_cat(scores)
         gi = D.all_gather_cat(ids)
         if self.cfg.backend == "torch":
@@ -121,6 +143,10 @@ class HybridEngine:
             logits = self.reranker.score_torch(pair_ids, pair_lens)
         else:
             logits = self.reranker.score(pair_ids, pair_lens)
+        if self.heap is not None:
+            n = logits.numel()
+            self._log_stage[:n].copy_(logits.reshape(-1).float())
+            return self.ch_logits(self._log_stage)[:, :n].reshape(-1)
         if c.is_dist:
             logits = D.all_gather_cat(logits.contiguous()).reshape(-1)
         return logits
@@ -131,8 +157,8 @@ class HybridEngine:
         q_emb = self._encode()
         de_s, de_i = self._dense_local(q_emb)
         bm_s, bm_i = self._bm25_local()
-        de_s, de_i = self._exchange(de_s, de_i)
-        bm_s, bm_i = self._exchange(bm_s, bm_i)
+        de_s, de_i = self._exchange(de_s, de_i, getattr(self, "ch_dense", None))
+        bm_s, bm_i = self._exchange(bm_s, bm_i, getattr(self, "ch_bm25", None))
         fu_s, fu_i = self._fuse(bm_i, de_i)
         if cfg.rerank:
             logits = self._rerank(fu_i)
@@ -140,6 +166,8 @@ class HybridEngine:
         else:
             self.out_scores.copy_(fu_s[:, :cfg.k_out])
             self.out_ids.copy_(fu_i[:, :cfg.k_out])
+        if self.heap is not None:
+            self.heap.bump()
 
     def load_inputs(self, enc_ids, enc_len, q_tok, q_len, terms):
         """Async H2D (or D2D) copy of one batch into the static input buffers."""

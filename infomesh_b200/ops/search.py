@@ -49,8 +49,12 @@ def sim_topk_partials(q, docs, ktop=16, alive=None, max_ctas=0):
     return out_s, out_i
 
 
-def topk_merge(cand_scores, cand_ids, k_out, id_offset=0, out_scores=None, out_ids=None):
-    """Merge ``[P, nq, k_in]`` candidate lists into ``[nq, k_out]`` (score desc, id asc)."""
+def topk_merge(cand_scores, cand_ids, k_out, id_offset=0, out_scores=None, out_ids=None, push=None, wait=None):
+    """Merge ``[P, nq, k_in]`` candidate lists into ``[nq, k_out]`` (score desc, id asc).
+
+    ``push`` / ``wait`` are :class:`infomesh_b200.parallel.symm.TopkChannel` objects: with ``push`` the merged list is
+    also stored into slot[rank] of every peer's receive area (fused exchange, no NCCL call); with ``wait`` the
+    candidates are this rank's receive area and the kernel spins on the arrival counters first."""
     P, nq, k_in = cand_scores.shape
     assert cand_scores.dtype == torch.float32 and cand_ids.dtype in (torch.int32, torch.int64)
     cand_scores = cand_scores.contiguous()
@@ -64,16 +68,21 @@ def topk_merge(cand_scores, cand_ids, k_out, id_offset=0, out_scores=None, out_i
     rc = L.im_topk_merge(_native.ptr(cand_scores), _native.ptr(cand_ids if is64 else None),
                          _native.ptr(None if is64 else cand_ids), ctypes.c_int(P), ctypes.c_int(nq),
                          ctypes.c_int(k_in), ctypes.c_int(k_out), ctypes.c_int64(id_offset),
-                         _native.ptr(out_scores), _native.ptr(out_ids), ctypes.c_void_p(0), ctypes.c_void_p(0),
-                         ctypes.c_void_p(0), ctypes.c_int(1), ctypes.c_int(0), ctypes.c_void_p(0),
-                         ctypes.c_uint32(0), _native.stream_ptr())
+                         _native.ptr(out_scores), _native.ptr(out_ids),
+                         ctypes.c_void_p(push.peer_scores_ptr if push else 0),
+                         ctypes.c_void_p(push.peer_ids_ptr if push else 0),
+                         ctypes.c_void_p(push.peer_flags_ptr if push else 0),
+                         ctypes.c_int(push.world if push else 1), ctypes.c_int(push.rank if push else 0),
+                         ctypes.c_void_p(wait.local_flags_ptr if wait else 0),
+                         ctypes.c_void_p((push or wait).step_ptr if (push or wait) else 0), _native.stream_ptr())
     _native.check(rc, "im_topk_merge")
     _native.count_launch()
     return out_scores, out_ids
 
 
-def sim_topk(q, docs, k=10, alive=None, id_offset=0):
-    """Exact top-``k`` cosine/dot search of ``q[nq<=128, dim]`` against ``docs[n, dim]``."""
+def sim_topk(q, docs, k=10, alive=None, id_offset=0, push=None):
+    """Exact top-``k`` cosine/dot search of ``q[nq<=128, dim]`` against ``docs[n, dim]``.  With ``push`` the shard's
+    result is also written into every peer's receive area by the merge kernel (fused top-k exchange)."""
     assert 1 <= k <= 32, "k > 32 is served by chunked search at the index level"
     ps, pi = sim_topk_partials(q, docs, ktop=k, alive=alive)
-    return topk_merge(ps, pi, k, id_offset=id_offset)
+    return topk_merge(ps, pi, k, id_offset=id_offset, push=push)
