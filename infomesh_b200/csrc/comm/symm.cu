@@ -7,12 +7,14 @@
 //     stores its slice into slot[rank] of every peer with 16-byte NVLink writes, publishes an arrival count with
 //     red.release.sys, waits for every peer's count, then copies the gathered slots to a private output.  One
 //     launch, no host involvement, CUDA-graph safe (the step counter lives in device memory).
-//   * p2p_barrier_kernel / step_bump_kernel — device barrier across ranks and the engine-wide step counter.
+//   * p2p_barrier_kernel — device barrier across ranks.
 //
-// Flag protocol: counters only grow.  A channel whose producers arrive `c` times per step is complete for step s
-// when flag >= (s + 1) * c.  Payload buffers are double-buffered on (s & 1); a peer cannot run two steps ahead
-// because finishing step s + 1 needs this rank's step s + 1 arrivals, which are stream-ordered after this rank's
-// step s reads.
+// Flag protocol: every channel owns a private {step, done} pair in local memory and `world` arrival counters in the
+// symmetric heap.  Counters only grow: a channel whose producers arrive `c` times per use is complete for use s when
+// flag >= (s + 1) * c.  The consuming kernel advances `step` itself (last CTA out), so a channel may be used any
+// number of times per engine step, or skipped, without a host-side epoch.  Payload buffers are double-buffered on
+// (s & 1); a peer cannot run two uses ahead because finishing use s + 1 needs this rank's use s + 1 arrivals, which
+// are stream-ordered after this rank's use s reads.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -34,13 +36,26 @@ __device__ __forceinline__ void flag_wait(const uint32_t* flag, uint32_t target,
   }
 }
 
+// Last CTA out advances the channel: every CTA has read state[0] before it can have counted itself done.
+__device__ __forceinline__ void channel_advance(uint32_t* state) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(state + 1, 1u) == gridDim.x * gridDim.y - 1u) {
+      state[1] = 0u;
+      state[0] += 1u;
+      __threadfence();
+    }
+  }
+}
+
 // src: this rank's block (`bytes`, multiple of 16).  peer_buf[p]: base of rank p's receive area
 // [2][world][bytes]; peer_flag[p]: rank p's counters [world].  out: [world][bytes] private copy.
 __global__ void __launch_bounds__(kAgThreads)
 p2p_allgather_kernel(const uint8_t* __restrict__ src, size_t bytes, uint8_t* const* __restrict__ peer_buf,
-                     uint32_t* const* __restrict__ peer_flag, const uint32_t* __restrict__ step_ptr, int world, int rank,
+                     uint32_t* const* __restrict__ peer_flag, uint32_t* __restrict__ state, int world, int rank,
                      uint8_t* __restrict__ out) {
-  const uint32_t step = *step_ptr;
+  const uint32_t step = *reinterpret_cast<volatile uint32_t*>(state);
   const size_t par_off = static_cast<size_t>(step & 1u) * world * bytes;
   const size_t n16 = bytes / 16;
   const size_t per_cta = (n16 + gridDim.x - 1) / gridDim.x;
@@ -68,20 +83,20 @@ p2p_allgather_kernel(const uint8_t* __restrict__ src, size_t bytes, uint8_t* con
     uint4* d4 = reinterpret_cast<uint4*>(out + static_cast<size_t>(p) * bytes);
     for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) d4[i] = s4[i];
   }
+  channel_advance(state);
 }
 
-__global__ void p2p_barrier_kernel(uint32_t* const* __restrict__ peer_flag, const uint32_t* __restrict__ step_ptr,
-                                   int world, int rank) {
-  const uint32_t step = *step_ptr;
+__global__ void p2p_barrier_kernel(uint32_t* const* __restrict__ peer_flag, uint32_t* __restrict__ state, int world,
+                                   int rank) {
+  const uint32_t step = *reinterpret_cast<volatile uint32_t*>(state);
   if (threadIdx.x < static_cast<unsigned>(world)) {
     __threadfence_system();
     uint32_t* f = peer_flag[threadIdx.x] + rank;
     asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(f) : "memory");
     flag_wait(peer_flag[rank] + threadIdx.x, step + 1u, "p2p_barrier", threadIdx.x);
   }
+  channel_advance(state);
 }
-
-__global__ void step_bump_kernel(uint32_t* step_ptr) { *step_ptr += 1u; }
 
 }  // namespace im
 
@@ -129,7 +144,7 @@ IM_API int im_can_access_peer(int dev, int peer) {
 
 // ---------------------------------------------------------------- device primitives
 IM_API int im_p2p_allgather(const void* src, size_t bytes, void* const* peer_buf, uint32_t* const* peer_flag,
-                            const uint32_t* step_ptr, int world, int rank, void* out, int ctas, void* stream) {
+                            uint32_t* state, int world, int rank, void* out, int ctas, void* stream) {
   if (bytes == 0 || (bytes % 16) != 0) return set_error("im_p2p_allgather", "block size must be a non-zero multiple of 16 bytes");
   if (world < 1 || world > 32) return set_error("im_p2p_allgather", "world must be 1..32");
   const size_t n16 = bytes / 16;
@@ -137,21 +152,16 @@ IM_API int im_p2p_allgather(const void* src, size_t bytes, void* const* peer_buf
   if (grid < 1) grid = 1;
   if (grid > 32) grid = 32;   // every CTA spins on peers: stay far below one wave so all are co-resident
   p2p_allgather_kernel<<<grid, kAgThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      static_cast<const uint8_t*>(src), bytes, reinterpret_cast<uint8_t* const*>(peer_buf), peer_flag, step_ptr, world,
+      static_cast<const uint8_t*>(src), bytes, reinterpret_cast<uint8_t* const*>(peer_buf), peer_flag, state, world,
       rank, static_cast<uint8_t*>(out));
   IM_LAUNCH_OK("p2p_allgather_kernel");
   return grid;
 }
 
-IM_API int im_p2p_barrier(uint32_t* const* peer_flag, const uint32_t* step_ptr, int world, int rank, void* stream) {
+IM_API int im_p2p_barrier(uint32_t* const* peer_flag, uint32_t* state, int world, int rank, void* stream) {
   if (world < 1 || world > 32) return set_error("im_p2p_barrier", "world must be 1..32");
-  p2p_barrier_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(peer_flag, step_ptr, world, rank);
+  p2p_barrier_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(peer_flag, state, world, rank);
   IM_LAUNCH_OK("p2p_barrier_kernel");
   return 0;
 }
 
-IM_API int im_step_bump(uint32_t* step_ptr, void* stream) {
-  step_bump_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(step_ptr);
-  IM_LAUNCH_OK("step_bump_kernel");
-  return 0;
-}

@@ -260,7 +260,7 @@ topk_merge_kernel(const float* __restrict__ cand_scores, const int64_t* __restri
                   float* __restrict__ out_scores, int64_t* __restrict__ out_ids,
                   // fused exchange (all optional)
                   float* const* peer_scores, int64_t* const* peer_ids, uint32_t* const* peer_flags, int world, int rank,
-                  const uint32_t* wait_flags, const uint32_t* step_ptr) {
+                  const uint32_t* wait_flags, uint32_t* state) {
   extern __shared__ uint8_t msm[];
   const int q = blockIdx.x;
   const int n = P * k_in;
@@ -274,7 +274,7 @@ topk_merge_kernel(const float* __restrict__ cand_scores, const int64_t* __restri
 
   // Exchange protocol (see comm/symm.cu): receive areas are [2][world][nq][k] double-buffered on step parity,
   // arrival counters are cumulative: one arrival per query block per step.
-  const uint32_t step = step_ptr != nullptr ? *step_ptr : 0u;
+  const uint32_t step = state != nullptr ? *reinterpret_cast<volatile uint32_t*>(state) : 0u;
   if (wait_flags != nullptr) {
     if (threadIdx.x < static_cast<unsigned>(P)) {
       const uint32_t target = (step + 1u) * static_cast<uint32_t>(nq);
@@ -383,6 +383,18 @@ topk_merge_kernel(const float* __restrict__ cand_scores, const int64_t* __restri
       }
     }
   }
+  if (wait_flags != nullptr && state != nullptr) {
+    // consumer side: the last query block out advances the channel (see comm/symm.cu)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(state + 1, 1u) == gridDim.x - 1u) {
+        state[1] = 0u;
+        state[0] += 1u;
+        __threadfence();
+      }
+    }
+  }
 }
 
 }  // namespace im
@@ -429,7 +441,7 @@ IM_API int im_sim_topk(const void* Q, const void* D, int nq, int n_docs, int dim
 IM_API int im_topk_merge(const float* cand_scores, const int64_t* cand_ids64, const int* cand_ids32, int P, int nq,
                          int k_in, int k_out, int64_t id_offset, float* out_scores, int64_t* out_ids,
                          float* const* peer_scores, int64_t* const* peer_ids, uint32_t* const* peer_flags, int world,
-                         int rank, const uint32_t* wait_flags, const uint32_t* step_ptr, void* stream) {
+                         int rank, const uint32_t* wait_flags, uint32_t* state, void* stream) {
   using namespace im;
   if (nq <= 0) return 0;
   const size_t n = static_cast<size_t>(P) * k_in;
@@ -439,7 +451,7 @@ IM_API int im_topk_merge(const float* cand_scores, const int64_t* cand_ids64, co
     IM_CUDA_OK(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   topk_merge_kernel<<<nq, kMergeThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
       cand_scores, cand_ids64, cand_ids32, P, nq, k_in, k_out, id_offset, out_scores, out_ids, peer_scores, peer_ids,
-      peer_flags, world, rank, wait_flags, step_ptr);
+      peer_flags, world, rank, wait_flags, state);
   IM_LAUNCH_OK("topk_merge_kernel");
   return 0;
 }

@@ -166,8 +166,6 @@ class HybridEngine:
         else:
             self.out_scores.copy_(fu_s[:, :cfg.k_out])
             self.out_ids.copy_(fu_i[:, :cfg.k_out])
-        if self.heap is not None:
-            self.heap.bump()
 
     def load_inputs(self, enc_ids, enc_len, q_tok, q_len, terms):
         """Async H2D (or D2D) copy of one batch into the static input buffers."""

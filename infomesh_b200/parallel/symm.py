@@ -60,9 +60,6 @@ class SymmetricHeap:
         self._local = torch.as_tensor(_RawCuda(self.local_base, self.nbytes), device=c.device)
         self._top = 0
         self._tables: list[torch.Tensor] = []
-        # engine-wide step counter (private memory) shared by every channel of this heap
-        self.step = torch.zeros(1, dtype=torch.int32, device=c.device)
-        self._bar_step = torch.zeros(1, dtype=torch.int32, device=c.device)
         self._bar = FlagChannel(self)
 
     # ------------------------------------------------------------------ allocation
@@ -86,23 +83,12 @@ class SymmetricHeap:
         self._tables.append(t)
         return t
 
-    @property
-    def step_ptr(self) -> int:
-        return self.step.data_ptr()
-
-    def bump(self) -> None:
-        """Advance the step counter (one 1-thread kernel; stream-ordered, graph-capturable)."""
-        L = _native.require()
-        _native.check(L.im_step_bump(ctypes.c_void_p(self.step_ptr), _native.stream_ptr()), "im_step_bump")
-        _native.count_launch()
-
     def barrier(self) -> None:
         L = _native.require()
-        _native.check(L.im_p2p_barrier(ctypes.c_void_p(self._bar.peer_flags_ptr), ctypes.c_void_p(self._bar_step.data_ptr()),
+        _native.check(L.im_p2p_barrier(ctypes.c_void_p(self._bar.peer_flags_ptr), ctypes.c_void_p(self._bar.step_ptr),
                                        ctypes.c_int(self.ctx.world), ctypes.c_int(self.ctx.rank), _native.stream_ptr()),
                       "im_p2p_barrier")
-        _native.check(L.im_step_bump(ctypes.c_void_p(self._bar_step.data_ptr()), _native.stream_ptr()), "im_step_bump")
-        _native.count_launch(2)
+        _native.count_launch()
 
     def close(self) -> None:
         L = _native.lib()
@@ -119,7 +105,8 @@ class SymmetricHeap:
 
 
 class FlagChannel:
-    """``world`` cumulative arrival counters on every rank."""
+    """``world`` cumulative arrival counters on every rank (symmetric) + a private ``{step, done}`` pair that the
+    consuming kernel advances."""
 
     def __init__(self, heap: SymmetricHeap):
         self.heap, self.world, self.rank = heap, heap.ctx.world, heap.ctx.rank
@@ -127,7 +114,8 @@ class FlagChannel:
         self._flag_tab = heap.peer_table(off)
         self.peer_flags_ptr = self._flag_tab.data_ptr()
         self.local_flags_ptr = self.flags.data_ptr()
-        self.step_ptr = heap.step_ptr
+        self.state = torch.zeros(2, dtype=torch.int32, device=heap.ctx.device)
+        self.step_ptr = self.state.data_ptr()
 
 
 class AllGatherChannel(FlagChannel):

@@ -266,6 +266,7 @@ def test_hybrid_engine_end_to_end_matches_torch_backend():
 @pytest.mark.gpu
 def test_symmetric_heap_single_rank_selfpush():
     """World-size-1 degenerate case of the peer-memory backend: self-push all-gather and fused top-k exchange."""
+    from infomesh_b200.ops import search as S
     from infomesh_b200.parallel import symm
 
     dev = torch.device("cuda:0")
@@ -274,7 +275,6 @@ def test_symmetric_heap_single_rank_selfpush():
     for step in range(3):
         src = torch.randn(1024, device=dev)
         out = ag(src)
-        heap.bump()
         assert torch.equal(out[0], src)
     ch = symm.TopkChannel(heap, 8, 10)
     sc = torch.rand((4, 8, 10), device=dev).sort(dim=2, descending=True).values
@@ -282,7 +282,6 @@ def test_symmetric_heap_single_rank_selfpush():
     for step in range(3):
         ls, li = S.topk_merge(sc, ids, 10, push=ch)
         gs, gi = S.topk_merge(ch.cand_scores, ch.cand_ids, 10, wait=ch)
-        heap.bump()
         assert torch.equal(ls, gs) and torch.equal(li, gi)
     torch.cuda.synchronize()
     heap.close()
