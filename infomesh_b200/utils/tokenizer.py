@@ -85,3 +85,50 @@ class HashTokenizer:
         if inv is None:
             inv = self._inv = {i: w for w, i in self.vocab.items()}
         return " ".join(inv.get(int(i), "[UNK]") for i in ids)
+
+
+class Seq2SeqTokenizer:
+    """T5-side tokeniser: SentencePiece when ``spiece.model`` is available, hash word ids otherwise.
+    ``encode`` appends EOS (id 1); ``decode`` stops at EOS and drops padding."""
+
+    def __init__(self, vocab_size: int = 32128, model_file: str | None = None):
+        self.vocab_size = vocab_size
+        self._sp = None
+        self._hash = HashTokenizer(vocab_size, T5_SPECIALS)
+        self._seen: dict[int, str] = {}
+        if model_file and Path(model_file).exists():
+            try:
+                import sentencepiece as spm
+
+                self._sp = spm.SentencePieceProcessor(model_file=str(model_file))
+            except Exception:  # noqa: BLE001 — fall back to hash ids
+                self._sp = None
+
+    def encode(self, text: str, max_len: int = 512, add_eos: bool = True) -> list[int]:
+        if self._sp is not None:
+            ids = list(self._sp.encode(text))
+        else:
+            words = self._hash.words(text)
+            ids = [self._hash.word_id(w) for w in words]
+            for i, w in zip(ids, words):
+                self._seen.setdefault(i, w)       # lets decode() echo words this process has encoded
+        ids = ids[:max_len - 1 if add_eos else max_len]
+        return ids + [1] if add_eos else ids
+
+    def decode(self, ids) -> str:
+        toks = []
+        for i in ids:
+            i = int(i)
+            if i == 1:
+                break
+            if i != 0:
+                toks.append(i)
+        if self._sp is not None:
+            return self._sp.decode(toks)
+        return " ".join(self._seen.get(i, f"<{i}>") for i in toks)
+
+
+def load_tokenizer(name_or_dir: str, vocab_size: int = 32128) -> Seq2SeqTokenizer:
+    p = Path(name_or_dir)
+    model_file = str(p / "spiece.model") if p.is_dir() else None
+    return Seq2SeqTokenizer(vocab_size, model_file)
