@@ -185,3 +185,111 @@ def test_format_fetch_result():
     assert "is_cached: true" in out and "stale_warning" in out and out.endswith("\n\nbody")
     out = format_fetch_result(title="T", url="https://a.b/c", text="body", is_cached=False, is_paywall=True)
     assert "paywall_warning" in out and "freshly crawled" in out
+
+
+def _rr(url, title, snippet, score, crawled_at=None, **kw):
+    import time as _t
+
+    from infomesh_b200.index.ranking import RankedResult
+    return RankedResult(doc_id=url, url=url, title=title, snippet=snippet, bm25_score=kw.get("bm25", score), freshness_score=kw.get("fresh", 0.9),
+                        trust_score=0.5, authority_score=0.1, combined_score=score, crawled_at=crawled_at or _t.time())
+
+
+def test_reranker_parsing_and_llm_fallbacks():
+    import asyncio
+
+    from infomesh_b200.search import reranker as RR
+    from infomesh_b200.summarizer.engine import LLMBackend, LLMRuntime, ModelInfo
+
+    assert RR._parse_ranking_response("sure: [3, 1, 3, 9, 2]", 4) == [2, 0, 1, 3]
+    assert RR._parse_ranking_response("[]", 3) == [0, 1, 2] and RR._parse_ranking_response("no array", 3) is None
+    res = [_rr(f"https://e/{i}", f"T{i}", f"snippet {i}", 1.0 - i * 0.1) for i in range(4)]
+
+    class Fixed(LLMBackend):
+        def __init__(self, reply, up=True):
+            self.reply, self.up = reply, up
+
+        async def generate(self, prompt, *, max_tokens=512):
+            assert "1. [T0] snippet 0" in prompt
+            if self.reply is None:
+                raise RuntimeError("down")
+            return self.reply
+
+        async def is_available(self):
+            return self.up
+
+        async def model_info(self):
+            return ModelInfo("m", LLMRuntime.OLLAMA, None, None, self.up)
+
+    out = asyncio.run(RR.rerank_with_llm("q", res, Fixed("[4, 2]"), max_candidates=3))
+    assert [r.title for r in out] == ["T1", "T0", "T2", "T3"]          # 4 is out of range for 3 candidates; tail kept
+    assert asyncio.run(RR.rerank_with_llm("q", res, Fixed(None))) == res
+    assert asyncio.run(RR.rerank_with_llm("q", res, Fixed("[2,1]", up=False))) == res
+    assert asyncio.run(RR.rerank_with_llm("q", res, object())) == res
+    assert [r.title for r in asyncio.run(RR.rerank_with_llm("q", res, Fixed("[2, 1]"), top_n=1))] == ["T1"]
+
+
+def test_explain_facets_quality_crossval_rag_extended():
+    import asyncio
+    import time
+
+    from infomesh_b200.search import cross_validate as CV
+    from infomesh_b200.search import explain as EX
+    from infomesh_b200.search import extended as XT
+    from infomesh_b200.search import facets as FA
+    from infomesh_b200.search import quality as Q
+    from infomesh_b200.search import rag as RG
+
+    now = time.time()
+    rs = [_rr("https://docs.python.org/a", "Python asyncio guide", "asyncio event loop tutorial for Python tasks", 0.9, now - 3600, bm25=0.95),
+          _rr("https://docs.python.org/a/", "Python asyncio guide", "asyncio event loop tutorial for Python tasks", 0.8, now - 3600),
+          _rr("https://blog.example/b", "Rust ownership", "ownership borrowing lifetimes explained with examples", 0.7, now - 40 * 86400, fresh=0.1),
+          _rr("https://news.example/c", "Asyncio news", "asyncio event loop changes announced in Python 3.13", 0.6, now - 400 * 86400)]
+    ex = EX.explain_query("asyncio", "asyncio", rs, 1.25).to_dict()
+    assert ex["results"][0]["weighted_contributions"]["bm25"] == round(0.95 * 0.4, 4) and "Strong keyword match" in ex["results"][0]["notes"]
+    assert "Stale content — may need recrawl" in ex["results"][2]["notes"] and ex["pipeline"][0] == "sanitize_fts_query"
+    f = FA.compute_facets(rs)
+    assert f.domains["docs.python.org"] == 2 and f.date_ranges == {"today": 2, "this_year": 1, "older": 1}
+    assert [r.url for r in FA.dedup_results(rs)] == [rs[0].url, rs[2].url, rs[3].url]
+    assert FA.highlight_snippet("The asyncio Event loop", "event ASYNCIO") == "The **asyncio** **Event** loop"
+    cl = FA.cluster_results(rs)
+    assert cl and cl[0].label in ("asyncio", "python", "event", "loop") and len(cl[0].results) >= 2
+    assert Q.ndcg_at_k([3, 2, 1]) == 1.0 and Q.ndcg_at_k([1, 2, 3]) < 1.0 and Q.mrr([1, 2, 0]) == 0.5
+    ab = Q.ABTest("t")
+    assert ab.compare("q", [1, 2, 3], [3, 2, 1]).winner == "B" and ab.summary()["B_wins"] == 1
+    assert Q.detect_domain_category("https://docs.python.org/3") == "tech-docs" and Q.get_profile("news").freshness_weight == 0.45
+    assert Q.extract_temporal_hint("rust news last 3 days") == 3 and Q.extract_temporal_hint("latest gpu") == 7 and Q.extract_temporal_hint("gpu") is None
+    ic = Q.QueryIntentClassifier()
+    assert ic.classify("how to install docker") == "how_to" and ic.classify("tensor memory") == "informational"
+    assert ic.classify_with_confidence("python error exception traceback")[0] == "error_debug"
+    dv = Q.diversify_results([{"url": f"https://a.com/{i}"} for i in range(4)] + [{"url": "https://b.com/1"}], max_per_domain=2)
+    assert [d["url"] for d in dv] == ["https://a.com/0", "https://b.com/1", "https://a.com/1"]
+    P = CV.PeerResult
+    rep = CV.cross_validate_results("q", {"p1": [P("p1", "u1", "t", "alpha beta gamma", 1.0), P("p1", "fake", "t", "x", 9.0)],
+                                          "p2": [P("p2", "u1", "t", "alpha beta gamma delta", 1.1)],
+                                          "p3": [P("p3", "u1", "t", "alpha beta", 0.9)]})
+    by = {v.url: v for v in rep.results}
+    assert by["u1"].verdict == CV.VERDICT_TRUSTED and by["fake"].verdict == CV.VERDICT_FABRICATED and rep.fabricated_count == 1
+    assert CV.cross_validate_results("q", {"p1": [P("p1", "u", "t", "s", 1.0)]}).results[0].verdict == CV.VERDICT_UNVERIFIED
+    rag = RG.format_rag_output("asyncio", rs, chunk_size=20, max_chunks=3)
+    assert len(rag.chunks) == 3 and rag.chunks[1].chunk_index == 1 and "[Source: Python asyncio guide" in rag.context_window
+    ans = RG.extract_answers("asyncio event loop", rs)
+    assert ans and ans[0].confidence > 0.5 and "Search Results:" in RG.build_summary_prompt("q", rs)
+    ents = RG.extract_entities("Python and Docker with Python by Guido Van Rossum", source_url="u")
+    assert ents[0].text == "Python" and ents[0].count == 2 and any(e.entity_type == "NAME" for e in ents)
+    assert RG.compute_toxicity_score("scam phishing malware here") > 0.3 and len(RG.filter_by_toxicity(rs)) == 4
+    assert '"index" and "score"' in RG.build_cot_rerank_prompt("q", rs)
+
+    async def fn(q, k, lang):
+        if q == "bad":
+            raise ValueError("boom")
+        return [{"q": q, "k": k}]
+
+    br = asyncio.run(XT.batch_search([XT.BatchQuery("a", 2), XT.BatchQuery("bad")], fn))
+    assert br.total_queries == 2 and br.results[0].results == [{"q": "a", "k": 2}] and br.results[1].error == "boom"
+    sc = XT.SummaryCache(max_entries=2, ttl_seconds=100)
+    sc.put("Q one", "s1", ["u"])
+    sc.put("q two", "s2", [])
+    sc.put("q three", "s3", [])
+    assert sc.size == 2 and sc.get("q ONE ") is None and sc.get("q three").summary == "s3"
+    assert XT.translate_query_keywords("파이썬 설치 오류", "ko") == ["install", "error"] and XT.translate_query_keywords("x", "xx") == []
