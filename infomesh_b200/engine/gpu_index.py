@@ -1,0 +1,217 @@
+"""HBM-resident mirror of a :class:`LocalStore`, searchable through the fused hybrid pipeline.
+
+This is the bridge between the CPU plane (SQLite documents, the reference's ``search_hybrid`` API surface,
+infomesh/search/query.py:244-319) and the device plane (``engine.hybrid.HybridEngine``).  A rebuild streams the
+store once and produces, on the GPU:
+
+* dense vectors  — encoder forward over ``title + text`` in batches (replaces ChromaDB/hnswlib, N2/N3);
+* BM25 postings  — C++ ``IndexBuilder`` tokenises on the host, CSR arrays are uploaded once (replaces FTS5 scoring, N1);
+* passage tokens — the leading ``passage_len`` reranker tokens of every document for pair assembly.
+
+Queries are answered in batches: ``search_many`` tokenises on the host, copies three small int tensors from pinned
+memory, replays the captured CUDA graph and maps the winning doc rows back to URLs / titles / snippets through SQLite.
+Deleted documents are masked with the ``alive`` byte map until the next rebuild.
+"""
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass
+from typing import Any
+
+import numpy as np
+import torch
+
+from infomesh_b200.engine.hybrid import HybridConfig, HybridEngine
+from infomesh_b200.models.bert import BGE_RERANKER_BASE, BGE_SMALL, BertModel
+from infomesh_b200.ops.bm25 import Bm25Index, HostIndexBuilder
+from infomesh_b200.utils.log import get_logger
+from infomesh_b200.utils.tokenizer import BERT_SPECIALS, XLMR_SPECIALS, HashTokenizer
+
+logger = get_logger(__name__)
+
+UNKNOWN_TERM = -2       # out-of-vocabulary query term: makes the implicit AND empty (FTS5 semantics)
+
+
+@dataclass
+class _ShardCfg:
+    doc_base: int = 0
+
+
+class _StoreShard:
+    """The attribute set HybridEngine expects from a shard."""
+
+    def __init__(self, device, vectors, bm25, passage_tok, passage_len, alive):
+        self.device, self.vectors, self.bm25 = device, vectors, bm25
+        self.passage_tok, self.passage_len, self.alive = passage_tok, passage_len, alive
+        self.cfg = _ShardCfg(0)
+
+    def nbytes(self) -> int:
+        return self.vectors.numel() * 2 + self.bm25.nbytes() + self.passage_tok.numel() * 4 + self.passage_len.numel() * 4
+
+
+class GpuSearchIndex:
+    def __init__(self, store: Any, *, device: str | torch.device = "cuda:0", encoder: BertModel | None = None,
+                 reranker: BertModel | None = None, rerank: bool = True, query_batch: int = 64, passage_len: int = 96,
+                 enc_doc_tokens: int = 128, embed_batch: int = 256, use_graph: bool = True, seed: int = 0):
+        self.store = store
+        self.device = torch.device(device)
+        self.encoder = encoder or BertModel(BGE_SMALL, device=self.device, seed=seed + 1)
+        self.reranker = (reranker or BertModel(BGE_RERANKER_BASE, device=self.device, seed=seed + 2)) if rerank else None
+        self.enc_tok = HashTokenizer(self.encoder.cfg.vocab_size, BERT_SPECIALS)
+        self.rr_tok = HashTokenizer(BGE_RERANKER_BASE.vocab_size, XLMR_SPECIALS)
+        self.rerank, self.nq, self.passage_len = rerank, query_batch, passage_len
+        self.enc_doc_tokens, self.embed_batch, self.use_graph = enc_doc_tokens, embed_batch, use_graph
+        self.builder: HostIndexBuilder | None = None
+        self.engine: HybridEngine | None = None
+        self.doc_ids = np.zeros(0, dtype=np.int64)      # row -> LocalStore doc_id
+        self._row_of: dict[int, int] = {}
+        self._pending = 0
+        self.built_at = 0.0
+        self.build_seconds = 0.0
+
+    # ------------------------------------------------------------------ build
+    @property
+    def n_docs(self) -> int:
+        return int(self.doc_ids.size)
+
+    def rebuild(self) -> int:
+        """Stream the store and (re)create every device structure.  Returns the number of documents."""
+        t0 = time.time()
+        dev = self.device
+        builder = HostIndexBuilder()
+        ids: list[int] = []
+        vec_chunks: list[torch.Tensor] = []
+        pt_rows: list[list[int]] = []
+        batch_text: list[str] = []
+
+        def flush():
+            if batch_text:
+                tok, lens = self.enc_tok.encode_batch(batch_text, max_len=self.enc_doc_tokens)
+                vec_chunks.append(self.encoder.embed(tok.to(dev, non_blocking=True), lens.to(dev, non_blocking=True)))
+                batch_text.clear()
+
+        for doc in self.store.iter_documents():
+            body = f"{doc.title}\n{doc.text}"
+            builder.add_text(body)
+            ids.append(int(doc.doc_id))
+            pt_rows.append(self.rr_tok.encode_plain(body, self.passage_len))
+            batch_text.append(body[:2000])                   # the reference embeds the first 2000 chars (vector_store.py:156)
+            if len(batch_text) >= self.embed_batch:
+                flush()
+        flush()
+        n = len(ids)
+        self.doc_ids = np.asarray(ids, dtype=np.int64)
+        self._row_of = {d: i for i, d in enumerate(ids)}
+        self._pending = 0
+        if n == 0:
+            self.engine, self.builder = None, builder
+            return 0
+        csr = builder.export()
+        bm25 = Bm25Index(csr, device=dev)
+        vectors = torch.cat(vec_chunks).contiguous()
+        ptok = torch.full((n, self.passage_len), self.rr_tok.sp.pad, dtype=torch.int32)
+        plen = torch.zeros((n,), dtype=torch.int32)
+        for i, row in enumerate(pt_rows):
+            if row:
+                ptok[i, :len(row)] = torch.tensor(row, dtype=torch.int32)
+            plen[i] = max(len(row), 1)
+        alive = torch.ones((n,), dtype=torch.uint8, device=dev)
+        shard = _StoreShard(dev, vectors, bm25, ptok.to(dev), plen.to(dev), alive)
+        k_fetch = min(20, 32)
+        cfg = HybridConfig(nq=self.nq, rerank=self.rerank, k_fetch=k_fetch, n_rerank=k_fetch, k_out=10,
+                           pair_seq=min(128, 32 + self.passage_len), use_graph=self.use_graph)
+        self.engine = HybridEngine(shard, cfg, encoder=self.encoder, reranker=self.reranker)
+        self.builder = builder
+        # pinned staging buffers for the per-batch H2D copies
+        pin = torch.cuda.is_available()
+        mk = lambda *shape, fill=0: torch.full(shape, fill, dtype=torch.int32).pin_memory() if pin else torch.full(shape, fill, dtype=torch.int32)  # noqa: E731
+        self._h_enc, self._h_enc_len = mk(cfg.nq, cfg.enc_seq), mk(cfg.nq, fill=1)
+        self._h_qtok, self._h_qlen = mk(cfg.nq, cfg.max_q_tokens, fill=self.rr_tok.sp.pad), mk(cfg.nq, fill=1)
+        self._h_terms = mk(cfg.nq, cfg.max_terms, fill=-1)
+        self._h_scores = torch.empty((cfg.nq, cfg.k_out), dtype=torch.float32)
+        self._h_ids = torch.empty((cfg.nq, cfg.k_out), dtype=torch.int64)
+        if pin:
+            self._h_scores, self._h_ids = self._h_scores.pin_memory(), self._h_ids.pin_memory()
+        self.built_at, self.build_seconds = time.time(), time.time() - t0
+        logger.info("gpu_index_built", docs=n, seconds=round(self.build_seconds, 2), hbm_mb=round(shard.nbytes() / 2 ** 20, 1))
+        return n
+
+    def mark_deleted(self, doc_id: int) -> bool:
+        row = self._row_of.get(int(doc_id))
+        if row is None or self.engine is None:
+            return False
+        self.engine.shard.alive[row] = 0
+        return True
+
+    def note_added(self, n: int = 1) -> None:
+        """New documents become searchable on the GPU at the next rebuild; callers rebuild past a threshold."""
+        self._pending += n
+
+    @property
+    def stale(self) -> bool:
+        return self._pending > 0
+
+    # ------------------------------------------------------------------ query
+    def _stage(self, queries: list[str]) -> None:
+        cfg = self.engine.cfg
+        self._h_enc.zero_()
+        self._h_enc_len.fill_(2)
+        self._h_qtok.fill_(self.rr_tok.sp.pad)
+        self._h_qlen.fill_(1)
+        self._h_terms.fill_(-1)
+        for i, q in enumerate(queries):
+            e = self.enc_tok.encode(q, cfg.enc_seq)
+            self._h_enc[i, :len(e)] = torch.tensor(e, dtype=torch.int32)
+            self._h_enc_len[i] = len(e)
+            t = self.rr_tok.encode_plain(q, cfg.max_q_tokens) or [self.rr_tok.sp.unk]
+            self._h_qtok[i, :len(t)] = torch.tensor(t, dtype=torch.int32)
+            self._h_qlen[i] = len(t)
+            terms = [int(x) if x >= 0 else UNKNOWN_TERM for x in dict.fromkeys(self.builder.tokenize(q).tolist())][:cfg.max_terms]
+            if terms:
+                self._h_terms[i, :len(terms)] = torch.tensor(terms, dtype=torch.int32)
+        for i in range(len(queries), cfg.nq):        # padding rows: a CLS/SEP-only query with no terms
+            e = [self.enc_tok.sp.cls, self.enc_tok.sp.sep]
+            self._h_enc[i, :2] = torch.tensor(e, dtype=torch.int32)
+
+    def search_many(self, queries: list[str], k: int = 10) -> list[list[dict[str, object]]]:
+        """One device pass per ``query_batch`` queries.  Each hit: doc_id, url, title, snippet, score."""
+        if self.engine is None or not queries:
+            return [[] for _ in queries]
+        out: list[list[dict[str, object]]] = []
+        nq = self.engine.cfg.nq
+        for a in range(0, len(queries), nq):
+            chunk = queries[a:a + nq]
+            self._stage(chunk)
+            self.engine.search_batch(self._h_enc, self._h_enc_len, self._h_qtok, self._h_qlen, self._h_terms, self._h_scores, self._h_ids)
+            torch.cuda.current_stream(self.device).synchronize()
+            scores, rows = self._h_scores.numpy(), self._h_ids.numpy()
+            for i, q in enumerate(chunk):
+                hits = []
+                for s, r in zip(scores[i], rows[i]):
+                    if r < 0 or r >= self.n_docs or len(hits) >= k:
+                        continue
+                    doc = self.store.get_document(int(self.doc_ids[r]))
+                    if doc is None:
+                        continue
+                    hits.append({"doc_id": doc.doc_id, "url": doc.url, "title": doc.title, "snippet": _snippet(doc.text, q),
+                                 "score": float(s), "crawled_at": doc.crawled_at})
+                out.append(hits)
+        return out
+
+    def search(self, query: str, k: int = 10) -> list[dict[str, object]]:
+        return self.search_many([query], k)[0]
+
+    def stats(self) -> dict[str, object]:
+        sh = self.engine.shard if self.engine else None
+        return {"documents": self.n_docs, "pending": self._pending, "built_at": self.built_at, "build_seconds": round(self.build_seconds, 2),
+                "hbm_bytes": sh.nbytes() if sh else 0, "vocab": self.builder.vocab if self.builder else 0,
+                "query_batch": self.nq, "rerank": self.rerank, "cuda_graph": bool(self.engine and self.engine._graph is not None)}
+
+
+def _snippet(text: str, query: str, width: int = 200) -> str:
+    """Window around the first query-term occurrence (cheap host-side stand-in for FTS5 snippet())."""
+    low = text.lower()
+    pos = min((p for p in (low.find(t) for t in query.lower().split()) if p >= 0), default=0)
+    a = max(0, pos - width // 4)
+    s = text[a:a + width].strip()
+    return ("…" if a > 0 else "") + s + ("…" if a + width < len(text) else "")

@@ -285,3 +285,61 @@ def test_symmetric_heap_single_rank_selfpush():
         assert torch.equal(ls, gs) and torch.equal(li, gi)
     torch.cuda.synchronize()
     heap.close()
+
+
+@pytest.mark.gpu
+def test_t5_encoder_and_greedy_decode_match_fp32_reference():
+    from infomesh_b200.models.t5 import T5_TINY, T5Model
+
+    dev = torch.device("cuda:0")
+    m = T5Model(T5_TINY, device=dev, seed=3)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    ids = torch.randint(2, T5_TINY.vocab_size, (3, 40), generator=g, dtype=torch.int32).to(dev)
+    lens = torch.tensor([40, 17, 33], dtype=torch.int32, device=dev)
+    enc = m.encode(ids, lens).float()
+    ref = m.encode_ref(ids, lens)
+    for b in range(3):                                   # padded positions are don't-care
+        L = int(lens[b])
+        err = (enc[b, :L] - ref[b, :L]).abs().max().item()
+        assert err < 0.08, err
+    T = 6
+    toks = m.generate(ids, lens, max_new_tokens=T)
+    rtoks, rlogits = m.generate_ref(ids, lens, max_new_tokens=T, enc_states=ref)
+    # greedy paths agree wherever the reference's top-2 margin is larger than bf16 noise
+    top2 = rlogits.topk(2, dim=-1).values
+    margin = (top2[..., 0] - top2[..., 1])
+    same = (toks[:, :T].cpu() == rtoks.cpu())
+    assert bool((same | (margin.cpu() < 0.05)).all()), (toks, rtoks, margin)
+
+
+@pytest.mark.gpu
+def test_gpu_search_index_over_local_store(tmp_path):
+    from infomesh_b200.engine.gpu_index import GpuSearchIndex
+    from infomesh_b200.index.local_store import LocalStore
+    from infomesh_b200.models.bert import BertConfig, BertModel
+
+    store = LocalStore(tmp_path / "idx.db")
+    topics = ["tensor memory accumulators on blackwell", "kademlia routing table buckets", "sqlite full text search ranking",
+              "merkle tree audit proofs", "simhash near duplicate detection"]
+    for i in range(60):
+        t = topics[i % len(topics)]
+        store.add_document(url=f"https://example.org/{i}", title=f"Doc {i} {t.split()[0]}", text=f"{t} sample number {i}. " * 6,
+                           raw_html_hash=f"r{i}", text_hash=f"t{i}", language="en")
+    dev = torch.device("cuda:0")
+    small = BertConfig(name="tiny-enc", vocab_size=30522, hidden=384, layers=2, heads=12, ffn=1536, max_pos=512)
+    rr = BertConfig(name="tiny-rr", vocab_size=250002, hidden=768, layers=2, heads=12, ffn=3072, max_pos=514, pos_offset=2,
+                    type_vocab=1, classifier=True)
+    gi = GpuSearchIndex(store, device=dev, encoder=BertModel(small, device=dev, seed=1), reranker=BertModel(rr, device=dev, seed=2),
+                        query_batch=8)
+    assert gi.rebuild() == 60
+    res = gi.search_many(["kademlia buckets", "merkle audit proofs", "zzzunknownterm kademlia"], k=5)
+    assert len(res) == 3 and len(res[0]) == 5 and all("url" in h and "snippet" in h for h in res[0])
+    # BM25 AND semantics put the on-topic documents into the candidate set: every hit for query 0 comes from the topic
+    assert sum("kademlia" in h["snippet"].lower() or "kademlia" in h["title"].lower() for h in res[0]) >= 3
+    st = gi.stats()
+    assert st["documents"] == 60 and st["hbm_bytes"] > 0
+    first = res[1][0]["doc_id"]
+    assert gi.mark_deleted(first)
+    again = gi.search("merkle audit proofs", k=5)
+    assert all(h["doc_id"] != first for h in again)
+    store.close()
