@@ -1,0 +1,39 @@
+"""One pass over every hot kernel at its benchmark shape, for `ncu --set full` (each kernel: 1 warm + 1 profiled
+launch; run with `-k regex:<names> --launch-skip <n>`).  Shapes: sim_topk 10M x 384 (batch 1 and 64), reranker
+layer GEMMs / attention at B=1280 S=128, encoder at B=64 S=32, BM25 / merge / RRF / pair assembly on a 1M-doc shard."""
+import sys
+from dataclasses import replace
+
+import torch
+
+from infomesh_b200.engine.synth import SynthConfig, SynthShard, make_queries
+from infomesh_b200.models.bert import BGE_RERANKER_BASE, BGE_SMALL, BertModel
+from infomesh_b200.ops import fuse as F
+from infomesh_b200.ops.search import sim_topk
+
+dev = torch.device("cuda:0")
+n_docs = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
+rr = BertModel(replace(BGE_RERANKER_BASE, layers=2), device=dev, seed=1)
+enc = BertModel(replace(BGE_SMALL, layers=2), device=dev, seed=2)
+docs = torch.nn.functional.normalize(torch.randn(n_docs, 384, device=dev), dim=1).bfloat16()
+q1 = torch.nn.functional.normalize(torch.randn(1, 384, device=dev), dim=1).bfloat16()
+q64 = torch.nn.functional.normalize(torch.randn(64, 384, device=dev), dim=1).bfloat16()
+ids = torch.randint(5, 1000, (1280, 128), device=dev, dtype=torch.int32)
+lens = torch.full((1280,), 128, device=dev, dtype=torch.int32)
+eids = torch.randint(5, 1000, (64, 32), device=dev, dtype=torch.int32)
+elens = torch.full((64,), 32, device=dev, dtype=torch.int32)
+scfg = SynthConfig(n_docs=1_000_000, n_docs_global=1_000_000)
+shard = SynthShard(scfg, device=dev)
+terms, qtok, qlen, _ = make_queries(scfg, 64, device=dev)
+terms = terms.to(dev)
+torch.cuda.synchronize()
+for it in range(2):
+    sim_topk(q1, docs, 20)
+    sim_topk(q64, docs, 20)
+    rr.score(ids, lens)
+    enc.embed(eids, elens)
+    bs, bi = shard.bm25.search(terms, k=20)
+    ds, di = sim_topk(q64, shard.vectors, 20)
+    fs, fi = F.rrf_fuse(bi.contiguous(), di.contiguous(), 20)
+    torch.cuda.synchronize()
+print("done")

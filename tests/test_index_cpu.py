@@ -117,3 +117,44 @@ def test_wire_protocol_codec():
     assert P.decode_signed_envelope(env) == {"sender": "p", "sig": b"s"} and P.decode_signed_envelope(msg) is None
     assert P.dataclass_to_payload(P.PeerPointer("p", 1, "u", 0.5))["title"] == ""
     assert P.PROTOCOL_SEARCH == "/infomesh/search/1.0.0" and len(P.ALL_PROTOCOLS) == 10
+
+
+def test_commoncrawl_wet_import_and_starter_helpers(tmp_path):
+    import asyncio
+    import gzip
+
+    from infomesh_b200.index import commoncrawl as CC
+    from infomesh_b200.index import starter as ST
+    from infomesh_b200.index.local_store import LocalStore
+
+    def rec(kind, url, body):
+        return f"WARC/1.0\r\nWARC-Type: {kind}\r\nWARC-Target-URI: {url}\r\nWARC-Date: 2026-01-01T00:00:00Z\r\nContent-Length: {len(body)}\r\n\r\n{body}\r\n\r\n"
+
+    long_a = "Blackwell tensor cores accumulate into tensor memory.\n" + "fifth generation tensor core details " * 5
+    long_b = "Kademlia routing tables keep k buckets of contacts.\n" + "iterative lookups with alpha parallel requests " * 5
+    wet = rec("warcinfo", "", "software: x") + rec("conversion", "https://a.example/1", long_a) + rec("conversion", "https://a.example/2", long_b) \
+        + rec("conversion", "https://a.example/dup", long_a) + rec("conversion", "https://a.example/short", "tiny")
+    recs = CC.parse_wet_content(wet)
+    assert [r.url for r in recs] == ["https://a.example/1", "https://a.example/2", "https://a.example/dup"]
+    p = tmp_path / "sample.wet.gz"
+    p.write_bytes(gzip.compress(wet.encode()))
+    store = LocalStore(tmp_path / "cc.db")
+    imp = CC.CommonCrawlImporter(store)
+    st = asyncio.run(imp.import_wet_file(str(p)))
+    assert (st.total_records, st.imported, st.skipped_duplicate) == (3, 2, 1)
+    assert store.get_document_by_url("https://a.example/1").title.startswith("Blackwell tensor cores")
+    ul = tmp_path / "urls.txt"
+    ul.write_text("# list\nhttps://b.example/x\nhttps://b.example/y\nhttps://a.example/1\n")
+    st2 = asyncio.run(imp.import_url_list(ul))
+    assert (st2.total_records, st2.imported, st2.skipped_duplicate) == (3, 2, 1)
+    import io
+    import pytest
+    with pytest.raises(ValueError, match="exceeds"):
+        CC._read_binary_limited(io.BytesIO(b"x" * 100), "mem", limit=10)
+    store.close()
+    rel = [{"tag_name": "v2", "assets": [{"name": "other.bin"}]},
+           {"tag_name": "v1", "assets": [{"name": ST.SNAPSHOT_ASSET_NAME, "browser_download_url": "https://x/s", "size": 2 ** 21, "created_at": "c"}]}]
+    info = ST.pick_asset(rel)
+    assert info.release_tag == "v1" and info.size_mb == 2.0 and ST.pick_asset([]) is None
+    ST._write_cache(tmp_path, info)
+    assert ST._read_cache(tmp_path).download_url == "https://x/s" and ST.needs_starter(3) and not ST.needs_starter(10)
