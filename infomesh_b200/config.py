@@ -151,6 +151,9 @@ class GpuConfig:
     reranker_model: str = "bge-reranker-base"
     summarizer_model: str = "t5-small"
     autotune_cache: str = ""
+    device: int = 0                  # CUDA ordinal used by the single-process serving path
+    query_batch: int = 64            # queries packed into one device pass by the store-backed GPU index
+    rerank: bool = True              # cross-encoder second stage on the device
 
 
 @dataclass(frozen=True)

@@ -103,12 +103,15 @@ class FactCheckResult:
 
 def cross_reference_results(claim: str, results: list[Any], *, min_overlap: float = 0.3) -> FactCheckResult:
     """How many results' snippets share >= ``min_overlap`` of the claim's words."""
-    words = set(claim.lower().split())
+    import re
+
+    tok = lambda t: set(re.findall(r"\w+", re.sub(r"</?(?:b|mark|em)>", "", t).lower()))  # noqa: E731 — ignores snippet highlight tags
+    words = tok(claim)
     if not words:
         return FactCheckResult(claim, 0, 0, 0.0, verdict="unverified")
     support, urls = 0, []
     for r in results:
-        have = set((getattr(r, "snippet", "") or "").lower().split())
+        have = tok(getattr(r, "snippet", "") or "")
         if len(words & have) / len(words) >= min_overlap:
             support += 1
             urls.append(r.url)

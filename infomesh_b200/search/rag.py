@@ -52,6 +52,10 @@ def format_rag_output(query: str, results: list[RankedResult], *, chunk_size: in
     return RAGOutput(query, chunks, len(results), window)
 
 
+_WORDS = re.compile(r"\w+")
+_MARKUP = re.compile(r"</?(?:b|mark|em)>")
+
+
 @dataclass(frozen=True)
 class ExtractedAnswer:
     answer: str
@@ -63,14 +67,16 @@ class ExtractedAnswer:
 
 def extract_answers(query: str, results: list[RankedResult], *, max_answers: int = 3) -> list[ExtractedAnswer]:
     """Sentences sharing terms with the query; confidence = 0.8 * term coverage + 0.2 * result score."""
-    terms = set(query.lower().split())
+    terms = set(_WORDS.findall(query.lower()))
     found: list[ExtractedAnswer] = []
+    seen: set[str] = set()
     for r in results:
-        text = r.snippet or ""
+        text = _MARKUP.sub("", r.snippet or "")          # FTS snippet() highlight markers are not part of the answer
         for sent in (s.strip() for s in re.split(r"[.!?]+", text)):
-            if len(sent) < 10:
+            if len(sent) < 10 or sent in seen:
                 continue
-            overlap = len(terms & set(sent.lower().split()))
+            seen.add(sent)
+            overlap = len(terms & set(_WORDS.findall(sent.lower())))
             if not overlap:
                 continue
             conf = min(overlap / max(len(terms), 1) * 0.8 + r.combined_score * 0.2, 1.0)
