@@ -127,3 +127,52 @@ def test_mcp_server_lists_and_calls_tools(tmp_path, monkeypatch):
     assert "invalid or missing api_key" in denied.root.content[0].text and json.loads(ok.root.content[0].text)["status"] == "ok"
     pstore.close()
     ctx.close()
+
+
+def test_admin_api_routes(tmp_path, monkeypatch):
+    from fastapi.testclient import TestClient
+
+    from infomesh_b200.api import extensions as X
+    from infomesh_b200.api.local_api import _format_duration, create_admin_app
+    from infomesh_b200.mcp.handlers import ToolRuntime
+
+    ctx = _ctx(tmp_path)
+    app = create_admin_app(ctx.config, runtime=ToolRuntime(ctx))
+    c = TestClient(app)
+    assert c.get("/health").json() == {"status": "ok"} and c.get("/health?detail=1").json()["db"] == "ok"
+    assert c.get("/readiness").status_code == 200
+    s = c.get("/search", params={"q": "asyncio event loop", "limit": 50}).json()
+    assert s["results"] and s["results"][0]["url"].endswith("asyncio.html") and len(s["results"][0]["snippet"]) <= 300
+    assert c.get("/search").json()["error"] == "query required"
+    assert c.get("/status").json()["index"]["document_count"] == 3 and c.get("/index/compression").json()["documents"] == 3
+    cfg = c.get("/config").json()
+    assert isinstance(cfg["node"]["data_dir"], str) and "crawl" in cfg
+    assert c.post("/config/reload").json() == {"status": "reloaded"}
+    import time as _t
+    _t.sleep(1.05)                       # stay under the 10 requests / second limiter
+    assert "balance" in c.get("/credits/balance").json() and c.get("/network/peers").json()["connected"] == 0
+    assert c.get("/analytics").json()["total_searches"] == 1 and c.get("/analytics/tools").json()["tool_usage"]["web_search"] == 1
+    m = c.get("/metrics")
+    assert "infomesh_search_total 1.0" in m.text and m.headers["x-frame-options"] == "DENY"
+    assert c.get("/gpu/stats").json() == {"enabled": False} and c.post("/index/submit", content=b"x").status_code == 404
+    spec = c.get("/openapi-spec").json()
+    assert spec["openapi"] == "3.1.0" and "/search" in spec["paths"] and "web_search" in spec["components"]["schemas"]
+    _t.sleep(1.05)
+    assert "<title>InfoMesh node</title>" in c.get("/dashboard").text
+    monkeypatch.setenv("INFOMESH_API_KEY", "k1")
+    assert c.get("/health").status_code == 401 and c.get("/health", headers={"x-api-key": "k1"}).status_code == 200
+    monkeypatch.delenv("INFOMESH_API_KEY")
+    _t.sleep(1.05)
+    codes = [c.get("/health").status_code for _ in range(15)]
+    assert 429 in codes
+    assert TestClient(app, client=("8.8.8.8", 1234)).get("/health").status_code == 403
+    assert _format_duration(59) == "59s" and _format_duration(3700).startswith("1h")
+    rl = X.RateLimiter(X.RateLimitConfig(requests_per_minute=2))
+    assert rl.check("a") and rl.check("a") and not rl.check("a") and rl.remaining("a") == 0 and rl.remaining("b") == 2
+    km = X.APIKeyManager()
+    k = km.create_key("ci", expires_in_days=1, permissions=["search"])
+    assert k.key.startswith("im_") and len(k.key) == 51 and km.validate(k.key) is k
+    k2 = km.rotate(k.key)
+    assert km.validate(k.key) is None and km.validate(k2.key).permissions == ["search"] and len(km.list_keys()) == 2
+    assert "complete -F _infomesh_complete infomesh" in X.generate_bash_completion() and "#compdef infomesh" in X.generate_zsh_completion()
+    ctx.close()
