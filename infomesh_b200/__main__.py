@@ -1,0 +1,5 @@
+"""``python -m infomesh_b200`` — the ``infomesh`` command line."""
+from infomesh_b200.cli import cli
+
+if __name__ == "__main__":
+    cli()

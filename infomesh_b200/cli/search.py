@@ -1,0 +1,129 @@
+"""``infomesh search QUERY [-n] [--local] [--vector] [--gpu]`` and ``infomesh feedback stats | top-urls``
+(reference infomesh/cli/search.py:16-277)."""
+from __future__ import annotations
+
+import asyncio
+import time
+
+import click
+
+from infomesh_b200.config import load_config
+
+
+def _print_ranked(results, elapsed_ms: float, source: str) -> None:
+    if not results:
+        click.echo("No results found.")
+        return
+    click.secho(f"Found {len(results)} results ({elapsed_ms:.0f} ms, {source}):\n", bold=True)
+    for i, r in enumerate(results, 1):
+        get = (lambda k, d="": r.get(k, d)) if isinstance(r, dict) else (lambda k, d="": getattr(r, k, d))
+        score = get("combined_score", None)
+        score = get("score", 0.0) if score in (None, "") else score
+        peer = get("peer_id", "")
+        click.secho(f"{i}. {get('title') or get('url')}", fg="cyan")
+        click.echo(f"   {get('url')}")
+        click.echo(f"   score {float(score):.4f}" + (f"  · peer {str(peer)[:12]}" if peer else ""))
+        snip = str(get("snippet")).replace("<b>", "").replace("</b>", "").replace("\n", " ")
+        click.echo(f"   {snip[:220]}\n")
+
+
+async def _wait_for_peer(node, timeout: float = 8.0) -> bool:
+    deadline = time.monotonic() + timeout
+    while time.monotonic() < deadline:
+        if node.get_connected_peers():
+            return True
+        await asyncio.sleep(0.25)
+    return False
+
+
+@click.command()
+@click.argument("query")
+@click.option("--limit", "-n", default=10, type=click.IntRange(1, 100), help="Number of results")
+@click.option("--local", "--local-only", "local_only", is_flag=True, help="Search the local index only")
+@click.option("--vector", is_flag=True, help="Hybrid keyword + vector search")
+@click.option("--gpu", is_flag=True, help="Use the fused GPU pipeline (builds the HBM index first)")
+def search(query: str, limit: int, local_only: bool, vector: bool, gpu: bool) -> None:
+    """Search the index (network search first, local fallback)."""
+    from infomesh_b200.index.local_store import LocalStore
+    from infomesh_b200.search import query as Q
+
+    cfg = load_config()
+    store = LocalStore(db_path=cfg.index.db_path, tokenizer=cfg.index.fts_tokenizer, compression_enabled=cfg.storage.compression_enabled,
+                       compression_level=cfg.storage.compression_level)
+    try:
+        if gpu:
+            from infomesh_b200.engine.gpu_index import GpuSearchIndex
+
+            gi = GpuSearchIndex(store, query_batch=8)
+            gi.rebuild()
+            t0 = time.monotonic()
+            hits = gi.search(query, limit)
+            _print_ranked(hits, (time.monotonic() - t0) * 1000, "gpu hybrid")
+            return
+        if vector:
+            from infomesh_b200.index.vector_store import VectorStore
+
+            vs = VectorStore(persist_dir=cfg.node.data_dir / "vectors", model_name=cfg.index.embedding_model)
+            try:
+                res = Q.search_hybrid(store, vs, query, limit=limit)
+            finally:
+                vs.close()
+            _print_ranked(res.results, res.elapsed_ms, "hybrid")
+            return
+        if not local_only:
+            from infomesh_b200.services import bootstrap_p2p, create_local_search_fn
+
+            node, dist_index = bootstrap_p2p(cfg, local_search_fn=create_local_search_fn(cfg, store), enable_mdns=False)
+            if node is not None:
+                try:
+                    async def go():
+                        await _wait_for_peer(node)
+                        return await Q.search_distributed(store, dist_index, query, limit=limit, network_search_fn=node.search_network)
+
+                    res = asyncio.run(go())
+                    _print_ranked(res.results, res.elapsed_ms, f"distributed: {res.local_count} local + {res.remote_count} remote")
+                    return
+                finally:
+                    node.stop()
+        res = Q.search_local(store, query, limit=limit)
+        _print_ranked(res.results, res.elapsed_ms, "local")
+    finally:
+        store.close()
+
+
+@click.group("feedback")
+def feedback_group() -> None:
+    """Implicit search-quality feedback (stored locally only)."""
+
+
+def _feedback_store():
+    from infomesh_b200.search.feedback import FeedbackStore
+
+    return FeedbackStore(str(load_config().node.data_dir / "feedback.db"))
+
+
+@feedback_group.command("stats")
+def feedback_stats() -> None:
+    """Signal counts and the strongest boosts."""
+    fb = _feedback_store()
+    try:
+        click.echo(f"Signals recorded: {fb.signal_count()}")
+        top = fb.top_boosted_urls(5)
+        if top:
+            click.echo("Top boosted URLs:")
+            for u in top:
+                click.echo(f"  {u.boost_score:+.2f}  fetch {u.fetch_count} · skip {u.skip_count} · cite {u.cite_count}  {u.url}")
+    finally:
+        fb.close()
+
+
+@feedback_group.command("top-urls")
+@click.option("--limit", "-n", default=20, help="Number of URLs to show")
+def feedback_top_urls(limit: int) -> None:
+    """URLs ranked by accumulated positive feedback."""
+    fb = _feedback_store()
+    try:
+        for i, u in enumerate(fb.top_boosted_urls(limit), 1):
+            click.echo(f"{i:3d}. {u.boost_score:+.2f}  {u.url}")
+    finally:
+        fb.close()

@@ -11,7 +11,7 @@ import torch
 
 from infomesh_b200 import _native
 
-ACT = {None: 0, "none": 0, "gelu": 1, "relu": 2, "gelu_tanh": 3}
+ACT = {None: 0, "none": 0, "gelu": 1, "relu": 2, "gelu_tanh": 3, "tanh": 4}
 
 
 def linear_ref(a, w, bias=None, residual=None, act=None, alpha=1.0):
@@ -25,6 +25,8 @@ def linear_ref(a, w, bias=None, residual=None, act=None, alpha=1.0):
         y = torch.relu(y)
     elif act in ("gelu_tanh", 3):
         y = torch.nn.functional.gelu(y, approximate="tanh")
+    elif act in ("tanh", 4):
+        y = torch.tanh(y)
     if residual is not None:
         y = y + residual.float()
     return y
