@@ -34,8 +34,9 @@ struct GemmEpilogue {
   uint32_t* const* peer_flags;  // [tp] arrival counters of every rank: [tp_src][rows_per_rank/128]
   int rank, rows_per_rank;
   // --- fused all-gather wait (null => no wait) ---
-  const uint32_t* a_ready;  // [ceil(M/128)] local flags, row block is loadable once flag >= a_epoch
-  uint32_t a_epoch;
+  const uint32_t* a_ready;  // [ceil(M/128)] cumulative per-row arrival counters (one bump per landed row)
+  uint32_t* a_state;        // {use, done}: block m is loadable once a_ready[m] >= (use + 1) * rows_in_block(m);
+                            // the last CTA out advances `use` (see comm/symm.cu for the protocol)
   int m_rotate;             // first row block processed (so the local shard goes first)
 };
 
@@ -130,16 +131,19 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // ------------------------------- TMA producer -------------------------------
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
+      const uint32_t a_use = ep.a_state != nullptr ? *reinterpret_cast<volatile uint32_t*>(ep.a_state) : 0u;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         int m_blk = t / num_n, n_blk = t % num_n;
         m_blk = (m_blk + ep.m_rotate) % num_m;
         if (ep.a_ready != nullptr) {
+          const uint32_t target = (a_use + 1u) * static_cast<uint32_t>(min(kBM, M - m_blk * kBM));
           uint32_t spins = 0;
-          while (ld_acquire_sys(ep.a_ready + m_blk) < ep.a_epoch) {
+          while (static_cast<int32_t>(ld_acquire_sys(ep.a_ready + m_blk) - target) < 0) {
             if (++spins > IM_WAIT_LIMIT) {
               printf("[infomesh_b200] gemm a_ready timeout m_blk=%d\n", m_blk);
               __trap();
             }
+            __nanosleep(20);
           }
         }
         for (int kb = 0; kb < num_k; ++kb) {
@@ -364,6 +368,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  if (ep.a_state != nullptr && threadIdx.x == 0) {  // last CTA out advances the all-gather channel
+    __threadfence();
+    if (atomicAdd(ep.a_state + 1, 1u) == gridDim.x - 1u) {
+      ep.a_state[1] = 0u;
+      ep.a_state[0] += 1u;
+      __threadfence();
+    }
+  }
 }
 
 template <int BN>
@@ -391,7 +403,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
 IM_API int im_gemm_bf16_tn(const void* A, const void* B, void* C, const float* bias, const void* residual, int M, int N,
                            int K, int lda, int ldb, int ldc, int ldr, int act, int out_fp32, float alpha, int bn,
                            void* const* peer_c, uint32_t* const* peer_flags, int rank, int rows_per_rank,
-                           const uint32_t* a_ready, uint32_t a_epoch, int m_rotate, int max_ctas, void* stream) {
+                           const uint32_t* a_ready, uint32_t* a_state, int m_rotate, int max_ctas, void* stream) {
   using namespace im;
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if ((lda % 8) || (ldb % 8) || (ldc % 8) || (residual != nullptr && (ldr % 8))) return set_error("im_gemm_bf16_tn", "leading dims must be multiples of 8");
@@ -418,7 +430,7 @@ IM_API int im_gemm_bf16_tn(const void* A, const void* B, void* C, const float* b
   ep.rank = rank;
   ep.rows_per_rank = rows_per_rank > 0 ? rows_per_rank : M;
   ep.a_ready = a_ready;
-  ep.a_epoch = a_epoch;
+  ep.a_state = a_state;
   const int num_m = (M + kBM - 1) / kBM;
   ep.m_rotate = num_m > 0 ? ((m_rotate % num_m) + num_m) % num_m : 0;
   // coalesced TMA-store epilogue for plain local bf16 outputs

@@ -43,7 +43,9 @@ __device__ __forceinline__ void store4(__nv_bfloat16* p, const float (&f)[4]) {
 // H must be a multiple of 128 and <= 1024 (VEC = H / 128 chunks of 4 per lane)
 template <int VEC>
 __device__ __forceinline__ void ln_finish(float (&x)[VEC][4], const float* gamma, const float* beta, float eps,
-                                          __nv_bfloat16* out_row, int lane, bool rms_only) {
+                                          __nv_bfloat16* out_row, int lane, bool rms_only,
+                                          __nv_bfloat16* const* peer_rows = nullptr, size_t peer_off = 0, int n_peer = 0,
+                                          int skip_peer = -1) {
   constexpr int H = VEC * 128;
   float s = 0.f;
 #pragma unroll
@@ -71,7 +73,10 @@ __device__ __forceinline__ void ln_finish(float (&x)[VEC][4], const float* gamma
     o[1] = (x[v][1] - mean) * rstd * g.y + b.y;
     o[2] = (x[v][2] - mean) * rstd * g.z + b.z;
     o[3] = (x[v][3] - mean) * rstd * g.w + b.w;
-    store4(out_row + col, o);
+    if (out_row != nullptr) store4(out_row + col, o);
+    // fused all-gather: the normalised row also lands in every peer's full-sequence buffer (NVLink stores)
+    for (int p = 0; p < n_peer; ++p)
+      if (p != skip_peer) store4(peer_rows[p] + peer_off + col, o);
   }
 }
 
@@ -119,59 +124,104 @@ embed_ln_kernel(const int* __restrict__ ids, const int* __restrict__ pos_ids, co
 }
 
 // out[row] = LN( sum_{p<P} in[p][row] + residual[row] );  in_stride_p = elements between partial p and p+1
+//
+// Tensor-parallel hooks (parallel/tp.py):
+//   * fused reduce-scatter consumer: `arrive_flags[src][row/128]` are cumulative arrival counters bumped by the
+//     row-parallel GEMM epilogues of every source rank (4 epilogue warps x N tiles per use); the kernel waits for
+//     (use + 1) * arrivals_per_block, `use` being read from arrive_state[0], and the last CTA out advances it;
+//   * fused all-gather producer: the normalised row is also stored into every peer's [M_total, H] buffer at
+//     `out_row_offset + row`, and `peer_out_flags[p][(out_row_offset + row) / 128]` is bumped once per row so the
+//     column-parallel GEMM on the peer can start on a row block as soon as its 128 rows have landed.
+struct SumLnComm {
+  const uint32_t* arrive_flags;
+  uint32_t* arrive_state;
+  uint32_t arrivals_per_block;
+  int blocks_per_src;
+  __nv_bfloat16* const* peer_out;
+  uint32_t* const* peer_out_flags;
+  int out_row_offset;
+  int world;
+  int rank;
+};
+
 template <int VEC>
 __global__ void __launch_bounds__(kRowsPerBlock * 32)
 sum_ln_kernel(const __nv_bfloat16* __restrict__ in, size_t in_stride_p, int P,
               const __nv_bfloat16* __restrict__ residual, const float* __restrict__ gamma,
               const float* __restrict__ beta, float eps, int rms_only, int n_rows, __nv_bfloat16* __restrict__ out,
-              __nv_bfloat16* __restrict__ sum_out, const uint32_t* __restrict__ arrive_flags, uint32_t arrive_target,
-              int blocks_per_src) {
+              __nv_bfloat16* __restrict__ sum_out, const SumLnComm cm) {
   constexpr int H = VEC * 128;
   const int row = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (row >= n_rows) return;
-  if (arrive_flags != nullptr) {
-    // fused reduce-scatter: every source rank bumps flags[src][row/128] once per epilogue warp and N tile
-    const int blk = row >> 7;
-    if (lane < P) {
-      uint32_t spins = 0;
-      while (ld_acquire_sys(arrive_flags + lane * blocks_per_src + blk) < arrive_target) {
-        if (++spins > IM_WAIT_LIMIT) {
-          printf("[infomesh_b200] sum_ln arrival timeout src=%d blk=%d\n", lane, blk);
-          __trap();
+  const uint32_t use = cm.arrive_state != nullptr ? *reinterpret_cast<volatile uint32_t*>(cm.arrive_state) : 0u;
+  if (row < n_rows) {
+    if (cm.arrive_flags != nullptr) {
+      const int blk = row >> 7;
+      if (lane < P) {
+        const uint32_t target = (use + 1u) * cm.arrivals_per_block;
+        uint32_t spins = 0;
+        while (static_cast<int32_t>(ld_acquire_sys(cm.arrive_flags + lane * cm.blocks_per_src + blk) - target) < 0) {
+          if (++spins > IM_WAIT_LIMIT) {
+            printf("[infomesh_b200] sum_ln arrival timeout src=%d blk=%d\n", lane, blk);
+            __trap();
+          }
+          __nanosleep(20);
+        }
+      }
+      __syncwarp();
+    }
+    float x[VEC][4];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) x[v][j] = 0.f;
+    for (int p = 0; p < P; ++p) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        float a[4];
+        load4(in + p * in_stride_p + static_cast<size_t>(row) * H + v * 128 + lane * 4, a);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[v][j] += a[j];
+      }
+    }
+    if (residual != nullptr) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        float a[4];
+        load4(residual + static_cast<size_t>(row) * H + v * 128 + lane * 4, a);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[v][j] += a[j];
+      }
+    }
+    if (sum_out != nullptr) {  // pre-norm architectures keep the un-normalised residual stream
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) store4(sum_out + static_cast<size_t>(row) * H + v * 128 + lane * 4, x[v]);
+    }
+    if (out != nullptr || cm.peer_out != nullptr) {
+      const size_t grow = static_cast<size_t>(cm.out_row_offset) + row;
+      ln_finish<VEC>(x, gamma, beta, eps, out != nullptr ? out + static_cast<size_t>(row) * H : nullptr, lane, rms_only != 0,
+                     cm.peer_out, grow * H, cm.peer_out != nullptr ? cm.world : 0);
+      if (cm.peer_out_flags != nullptr) {
+        __threadfence_system();
+        __syncwarp();
+        if (lane < cm.world) {
+          uint32_t* f = cm.peer_out_flags[lane] + (grow >> 7);
+          asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(f) : "memory");
         }
       }
     }
-    __syncwarp();
   }
-  float x[VEC][4];
-#pragma unroll
-  for (int v = 0; v < VEC; ++v)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) x[v][j] = 0.f;
-  for (int p = 0; p < P; ++p) {
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-      float a[4];
-      load4(in + p * in_stride_p + static_cast<size_t>(row) * H + v * 128 + lane * 4, a);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) x[v][j] += a[j];
+  if (cm.arrive_state != nullptr) {  // last CTA out advances the reduce-scatter channel
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(cm.arrive_state + 1, 1u) == gridDim.x - 1u) {
+        cm.arrive_state[1] = 0u;
+        cm.arrive_state[0] += 1u;
+        __threadfence();
+      }
     }
   }
-  if (residual != nullptr) {
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-      float a[4];
-      load4(residual + static_cast<size_t>(row) * H + v * 128 + lane * 4, a);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) x[v][j] += a[j];
-    }
-  }
-  if (sum_out != nullptr) {  // pre-norm architectures keep the un-normalised residual stream
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) store4(sum_out + static_cast<size_t>(row) * H + v * 128 + lane * 4, x[v]);
-  }
-  if (out != nullptr) ln_finish<VEC>(x, gamma, beta, eps, out + static_cast<size_t>(row) * H, lane, rms_only != 0);
 }
 
 // sentence embedding: mode 0 = CLS token, 1 = mean over valid tokens; L2 normalised; one block per sequence
@@ -317,16 +367,28 @@ IM_API int im_embed_ln(const int* ids, const int* pos_ids, const int* type_ids, 
 
 IM_API int im_sum_ln(const void* in, long long in_stride_p, int P, const void* residual, const float* gamma,
                      const float* beta, float eps, int rms_only, int n_rows, int H, void* out, void* sum_out,
-                     const uint32_t* arrive_flags, uint32_t arrive_target, int blocks_per_src, void* stream) {
+                     const uint32_t* arrive_flags, uint32_t* arrive_state, unsigned arrivals_per_block, int blocks_per_src,
+                     void* const* peer_out, uint32_t* const* peer_out_flags, int out_row_offset, int world, int rank,
+                     void* stream) {
   using namespace im;
   if (n_rows <= 0) return 0;
   if (H % 128) return set_error("im_sum_ln", "H must be a multiple of 128");
+  if (arrive_flags != nullptr && P > 32) return set_error("im_sum_ln", "at most 32 partial sources");
+  SumLnComm cm;
+  cm.arrive_flags = arrive_flags;
+  cm.arrive_state = arrive_state;
+  cm.arrivals_per_block = arrivals_per_block;
+  cm.blocks_per_src = blocks_per_src;
+  cm.peer_out = reinterpret_cast<__nv_bfloat16* const*>(peer_out);
+  cm.peer_out_flags = peer_out_flags;
+  cm.out_row_offset = out_row_offset;
+  cm.world = world;
+  cm.rank = rank;
   const int grid = (n_rows + kRowsPerBlock - 1) / kRowsPerBlock;
   auto s = reinterpret_cast<cudaStream_t>(stream);
   IM_DISPATCH_VEC(H, (sum_ln_kernel<VEC><<<grid, kRowsPerBlock * 32, 0, s>>>(
                          (const __nv_bfloat16*)in, (size_t)in_stride_p, P, (const __nv_bfloat16*)residual, gamma, beta,
-                         eps, rms_only, n_rows, (__nv_bfloat16*)out, (__nv_bfloat16*)sum_out, arrive_flags,
-                         arrive_target, blocks_per_src)));
+                         eps, rms_only, n_rows, (__nv_bfloat16*)out, (__nv_bfloat16*)sum_out, cm)));
   IM_LAUNCH_OK("sum_ln_kernel");
   return 0;
 }

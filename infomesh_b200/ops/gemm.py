@@ -33,15 +33,24 @@ def linear_ref(a, w, bias=None, residual=None, act=None, alpha=1.0):
 
 
 def linear(a, w, bias=None, residual=None, act=None, alpha=1.0, out=None, out_dtype=torch.bfloat16, bn=0,
-           max_ctas=0):
-    """``a[M,K] @ w[N,K]^T`` with fused bias / activation / residual on the tcgen05 kernel."""
+           max_ctas=0, rs=None, ag=None):
+    """``a[M,K] @ w[N,K]^T`` with fused bias / activation / residual on the tcgen05 kernel.
+
+    Tensor-parallel hooks (``parallel.tp``): ``rs`` = :class:`ReduceScatterChannel` — the epilogue pushes every
+    128-row block of the partial product into the owning rank's receive slot over NVLink instead of storing locally;
+    ``ag`` = :class:`AllGatherInput` — ``a`` is a full-sequence buffer that peers are still filling, the TMA producer
+    waits per row block on the arrival counters and starts with this rank's own rows."""
     assert a.is_cuda and w.is_cuda and a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
     assert a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1]
     assert a.stride(1) == 1 and w.stride(1) == 1
     m, k = a.shape
     n = w.shape[0]
-    if out is None:
+    if out is None and rs is None:
         out = torch.empty((m, n), device=a.device, dtype=out_dtype)
+    if rs is not None:
+        assert m == rs.rows_per_rank * rs.world and n == rs.n_cols and residual is None
+        out = rs.recv[rs.rank]                     # placeholder view: the kernel addresses peers through rs.peer_c
+        out = out.view(rs.rows_per_rank, n)
     assert out.stride(1) == 1 and out.dtype in (torch.bfloat16, torch.float32)
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() == n
@@ -55,8 +64,10 @@ def linear(a, w, bias=None, residual=None, act=None, alpha=1.0, out=None, out_dt
         ctypes.c_int(residual.stride(0) if residual is not None else 0),
         ctypes.c_int(ACT[act] if not isinstance(act, int) else act),
         ctypes.c_int(1 if out.dtype == torch.float32 else 0), ctypes.c_float(alpha), ctypes.c_int(bn),
-        ctypes.c_void_p(0), ctypes.c_void_p(0), ctypes.c_int(0), ctypes.c_int(0),
-        ctypes.c_void_p(0), ctypes.c_uint32(0), ctypes.c_int(0), ctypes.c_int(max_ctas), _native.stream_ptr())
+        ctypes.c_void_p(rs.peer_c_ptr if rs else 0), ctypes.c_void_p(rs.peer_flags_ptr if rs else 0),
+        ctypes.c_int(rs.rank if rs else 0), ctypes.c_int(rs.rows_per_rank if rs else 0),
+        ctypes.c_void_p(ag.flags_ptr if ag else 0), ctypes.c_void_p(ag.state_ptr if ag else 0),
+        ctypes.c_int(ag.m_rotate if ag else 0), ctypes.c_int(max_ctas), _native.stream_ptr())
     _native.check(rc, "im_gemm_bf16_tn")
     _native.count_launch()
     return out

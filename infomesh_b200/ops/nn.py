@@ -62,8 +62,12 @@ def embed_ln(ids, word, pos, type_emb, gamma, beta, eps, seq_len, pos_ids=None, 
 
 
 def layernorm(x, gamma, beta=None, eps=1e-12, residual=None, rms_only=False, out=None, sum_out=None, partials=1,
-              partial_stride=0, arrive_flags=None, arrive_target=0, blocks_per_src=0, want_norm=True):
-    """``out = LN(sum_p x[p] + residual)``; ``x``: [n, H] (or [P, n, H] with ``partials=P``)."""
+              partial_stride=0, want_norm=True, rs=None, ag_push=None):
+    """``out = LN(sum_p x[p] + residual)``; ``x``: [n, H] (or [P, n, H] with ``partials=P``).
+
+    ``rs``: consume a fused reduce-scatter (wait on the arrival counters of ``rs`` before summing its receive
+    slots); ``ag_push``: also store the normalised rows into every peer's full-sequence buffer and bump their
+    per-row-block counters (fused all-gather producer)."""
     H = x.shape[-1]
     n = x.shape[-2]
     assert x.dtype == torch.bfloat16 and x.stride(-1) == 1
@@ -73,8 +77,13 @@ def layernorm(x, gamma, beta=None, eps=1e-12, residual=None, rms_only=False, out
     rc = L.im_sum_ln(_native.ptr(x), ctypes.c_longlong(partial_stride if partials > 1 else 0), ctypes.c_int(partials),
                      _native.ptr(residual), _native.ptr(gamma), _native.ptr(beta), ctypes.c_float(eps),
                      ctypes.c_int(1 if rms_only else 0), ctypes.c_int(n), ctypes.c_int(H),
-                     _native.ptr(out if want_norm else None), _native.ptr(sum_out), _native.ptr(arrive_flags),
-                     ctypes.c_uint32(arrive_target), ctypes.c_int(blocks_per_src), _native.stream_ptr())
+                     _native.ptr(out if want_norm else None), _native.ptr(sum_out),
+                     ctypes.c_void_p(rs.local_flags_ptr if rs else 0), ctypes.c_void_p(rs.step_ptr if rs else 0),
+                     ctypes.c_uint(rs.arrivals_per_block if rs else 0), ctypes.c_int(rs.blocks_per_src if rs else 0),
+                     ctypes.c_void_p(ag_push.peer_buf_ptr if ag_push else 0),
+                     ctypes.c_void_p(ag_push.peer_flags_ptr if ag_push else 0),
+                     ctypes.c_int(ag_push.row_offset if ag_push else 0), ctypes.c_int(ag_push.world if ag_push else 0),
+                     ctypes.c_int(ag_push.rank if ag_push else 0), _native.stream_ptr())
     _native.check(rc, "im_sum_ln")
     _native.count_launch()
     return out
