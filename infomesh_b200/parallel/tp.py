@@ -22,7 +22,7 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
-from infomesh_b200.models.bert import BertConfig, BertWeights
+from infomesh_b200.models.bert import BertConfig, BertWeights, classifier_head
 from infomesh_b200.ops import attention as A
 from infomesh_b200.ops import gemm as G
 from infomesh_b200.ops import nn as N
@@ -152,7 +152,7 @@ class TPBertModel:
         assert self.cfg.classifier
         w = self.w
         h = self.hidden_states_local(ids, lengths)
-        local = N.cls_head(h, w.cls_w1, w.cls_b1, w.cls_w2, w.cls_b2)
+        local = classifier_head(h, w)
         n = local.numel()
         if self.comm == "fused":
             self._log_stage[:n].copy_(local)
