@@ -40,6 +40,10 @@ struct GemmEpilogue {
   int m_rotate;             // first row block processed (so the local shard goes first)
 };
 
+struct PeerMaps {
+  CUtensorMap m[8];  // store maps over every rank's reduce-scatter receive area [tp * rows_per_rank, N]
+};
+
 constexpr int kBM = 128;
 constexpr int kBK = 64;
 constexpr int kGemmThreads = 192;
@@ -82,7 +86,7 @@ template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r,
-                    const GemmEpilogue ep, int M, int N, int K) {
+                    const __grid_constant__ PeerMaps tmap_peers, const GemmEpilogue ep, int M, int N, int K) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -220,6 +224,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         // ---- coalesced path: TMEM -> regs -> 128B-swizzled smem tile [32 rows x 64 cols] -> TMA store ----
         const uint32_t ew = warp - 2;  // 0..3
         const int tile_row0 = m_blk * kBM + static_cast<int>(quad * 32u);
+        // fused reduce-scatter: same staged tiles, but the TMA store targets the owner's receive slot over NVLink
+        const CUtensorMap* store_map = ep.peer_c != nullptr ? &tmap_peers.m[owner] : &tmap_c;
+        const int store_row0 = ep.peer_c != nullptr ? (ep.rank - owner) * ep.rows_per_rank + tile_row0 : tile_row0;
 #pragma unroll 1
         for (int c = 0; c < BN; c += 64) {
           const int col0 = n_blk * BN + c;
@@ -279,7 +286,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(&tmap_c, stage, col0, tile_row0);
+            tma_store_2d(store_map, stage, col0, store_row0);
             tma_store_commit();
           }
           ++store_cnt;
@@ -347,7 +354,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
       // TMEM reads done -> hand the accumulator stage back to the MMA warp
       tc_fence_before();
-      if (ep.peer_c != nullptr) __threadfence_system();  // pushed rows visible before the arrival counter
+      if (ep.peer_c != nullptr) {
+        if (ep.tma_store && lane == 0) tma_store_wait_all<0>();  // this warp's bulk stores have completed (not just been read)
+        __threadfence_system();  // pushed rows visible before the arrival counter
+      }
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(&tmem_empty[acc]);
@@ -380,7 +390,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
 template <int BN>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tr,
-                       const GemmEpilogue& ep, int M, int N, int K, int max_ctas, cudaStream_t stream) {
+                       const PeerMaps& tp, const GemmEpilogue& ep, int M, int N, int K, int max_ctas, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool configured = false;
   if (!configured) {
@@ -392,7 +402,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   int grid = tiles < sm_count() ? tiles : sm_count();
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   if (grid < 1) grid = 1;
-  gemm_bf16_tn_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, tr, ep, M, N, K);
+  gemm_bf16_tn_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, tr, tp, ep, M, N, K);
   IM_LAUNCH_OK("gemm_bf16_tn_kernel");
   return 0;
 }
@@ -403,7 +413,8 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
 IM_API int im_gemm_bf16_tn(const void* A, const void* B, void* C, const float* bias, const void* residual, int M, int N,
                            int K, int lda, int ldb, int ldc, int ldr, int act, int out_fp32, float alpha, int bn,
                            void* const* peer_c, uint32_t* const* peer_flags, int rank, int rows_per_rank,
-                           const uint32_t* a_ready, uint32_t* a_state, int m_rotate, int max_ctas, void* stream) {
+                           const uint32_t* a_ready, uint32_t* a_state, int m_rotate, int max_ctas, void* stream,
+                           const void* const* peer_c_host, int world) {
   using namespace im;
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if ((lda % 8) || (ldb % 8) || (ldc % 8) || (residual != nullptr && (ldr % 8))) return set_error("im_gemm_bf16_tn", "leading dims must be multiples of 8");
@@ -435,14 +446,24 @@ IM_API int im_gemm_bf16_tn(const void* A, const void* B, void* C, const float* b
   ep.m_rotate = num_m > 0 ? ((m_rotate % num_m) + num_m) % num_m : 0;
   // coalesced TMA-store epilogue for plain local bf16 outputs
   CUtensorMap tc = ta, tr = ta;
-  ep.tma_store = (!out_fp32 && peer_c == nullptr) ? 1 : 0;
-  if (ep.tma_store) {
+  PeerMaps tp;
+  for (auto& m : tp.m) m = ta;
+  const bool peer_tma = peer_c != nullptr && peer_c_host != nullptr && !out_fp32 && residual == nullptr && world >= 1 && world <= 8;
+  if (peer_tma) {
+    // one store map per owner: its receive area seen as [tp * rows_per_rank, N] with row pitch ldc
+    for (int p = 0; p < world; ++p)
+      if (get_tmap_2d(&tp.m[p], peer_c_host[p], static_cast<uint64_t>(world) * rows_per_rank, N, static_cast<uint64_t>(ldc) * 2, 32,
+                      64, 2, TMAP_SW_128))
+        return -1;
+  }
+  ep.tma_store = (!out_fp32 && (peer_c == nullptr || peer_tma)) ? 1 : 0;
+  if (ep.tma_store && peer_c == nullptr) {
     if (get_tmap_2d(&tc, C, M, N, static_cast<uint64_t>(ldc) * 2, 32, 64, 2, TMAP_SW_128)) return -1;
     if (residual != nullptr &&
         get_tmap_2d(&tr, residual, M, N, static_cast<uint64_t>(ldr) * 2, 32, 64, 2, TMAP_SW_128))
       return -1;
   }
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (bn == 256) return launch_gemm<256>(ta, tb, tc, tr, ep, M, N, K, max_ctas, s);
-  return launch_gemm<128>(ta, tb, tc, tr, ep, M, N, K, max_ctas, s);
+  if (bn == 256) return launch_gemm<256>(ta, tb, tc, tr, tp, ep, M, N, K, max_ctas, s);
+  return launch_gemm<128>(ta, tb, tc, tr, tp, ep, M, N, K, max_ctas, s);
 }

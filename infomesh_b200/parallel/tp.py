@@ -49,6 +49,9 @@ class ReduceScatterChannel:
         self.flags, fo = heap.alloc((c.world, self.blocks_per_src), torch.int32)
         self._c_tab, self._f_tab = heap.peer_table(ro), heap.peer_table(fo)
         self.peer_c_ptr, self.peer_flags_ptr = self._c_tab.data_ptr(), self._f_tab.data_ptr()
+        import ctypes
+
+        self.peer_c_host = (ctypes.c_void_p * c.world)(*[b + ro for b in heap.bases])   # host copy: TMA store maps
         self.local_flags_ptr = self.flags.data_ptr()
         self.state = torch.zeros(2, dtype=torch.int32, device=c.device)
         self.step_ptr = self.state.data_ptr()
