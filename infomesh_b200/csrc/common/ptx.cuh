@@ -288,7 +288,7 @@ __device__ __forceinline__ float gelu_erf_precise(float x) { return 0.5f * x * (
 // half a bf16 ulp of the result everywhere.  5 FMA-class ops + 1 MUFU.TANH per element instead of 12 + 2 MUFU, which
 // is what keeps the FFN-up epilogue (N = 3072, only 12 k-blocks of MMA per tile) under the MMA time of its tile.
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float x2 = x * x;
+  const float x2 = fminf(x * x, 40.0f);   // beyond |x| ~ 6.3 the tanh is saturated; the clamp keeps the quartic term from flipping the sign
   float p = fmaf(-3.51516790e-4f, x2, 3.70056460e-2f);
   p = fmaf(p, x2, 7.97507884e-1f);
   const float hx = 0.5f * x;
