@@ -4,10 +4,10 @@
 //
 // Replaces the encoder / reranker / summariser linear layers that the reference reaches through
 // sentence-transformers / an external LLM server (reference infomesh/index/vector_store.py:104-125,
-// infomesh/summarizer/engine.py:126-141).  Structure (one CTA per SM, 6 warps):
+// infomesh/summarizer/engine.py:126-141).  Structure (one CTA per SM, 10 warps):
 //   warp 0      TMA producer      cp.async.bulk.tensor 128B-swizzled A/B tiles -> smem ring (mbarrier tx)
 //   warp 1      MMA issuer        one thread issues tcgen05.mma.kind::f16 128xBNx16, accumulators in TMEM
-//   warps 2..5  epilogue          tcgen05.ld 32 lanes x 32 cols -> bias / activation / residual -> bf16 stores
+//   warps 2..9  epilogue          tcgen05.ld 32 lanes x 32 cols -> bias / activation / residual -> bf16 stores
 // The TMEM accumulator is double buffered (2 x BN columns) so the epilogue of tile i overlaps the MMAs
 // of tile i+1.  Fused-collective hooks (used by parallel/tp.py):
 //   * a_ready flags: the producer acquires a per-row-block flag before loading A (all-gather -> GEMM:
@@ -46,14 +46,16 @@ struct PeerMaps {
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;
-constexpr int kGemmThreads = 192;
+constexpr int kEpiWarps = 8;   // two per TMEM lane quadrant: each takes half of the tile's columns, and the pair hides
+                               // each other's TMEM-load / MUFU / bias-load latency on the shared scheduler
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 
 template <int BN>
 struct GemmCfg {
   static constexpr int kStageBytes = (kBM + BN) * kBK * 2;
   static constexpr int kStages = (BN == 256) ? 4 : 6;
   static constexpr int kTmemCols = 2 * BN;  // 256 or 512: both powers of two
-  static constexpr int kStoreBytes = 4 /*warps*/ * 2 /*buffers*/ * 4096;  // [32 rows x 64 bf16] staging tiles
+  static constexpr int kStoreBytes = kEpiWarps * 4096;  // one [32 rows x 64 bf16] staging tile per epilogue warp
   static constexpr int kSmemBytes = kStages * kStageBytes + kStoreBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
@@ -96,7 +98,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* tmem_full = empty_bar + Cfg::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* res_bar = tmem_empty + 2;  // [4 warps][2 buffers] residual-tile arrival
+  uint64_t* res_bar = tmem_empty + 2;  // [8 epilogue warps] residual-tile arrival
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 8);
 
   const uint32_t warp = warp_id();
@@ -117,9 +119,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);
+      mbar_init(&tmem_empty[i], kEpiWarps);
     }
-    for (int i = 0; i < 8; ++i) mbar_init(&res_bar[i], 1);
+    for (int i = 0; i < kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -199,6 +201,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else {
     // ------------------------------- epilogue warps ------------------------------
     const uint32_t quad = warp & 3u;  // TMEM lane quadrant this warp may touch
+    const uint32_t ew = warp - 2;     // 0..7
+    const int c_lo = static_cast<int>(ew >> 2) * (BN / 2), c_hi = c_lo + BN / 2;  // this warp's half of the tile columns
     const uint32_t row_in_tile = quad * 32u + lane;
     uint32_t acc = 0, acc_phase = 0, store_cnt = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -222,23 +226,21 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const __nv_bfloat16* r_row = ep.residual ? ep.residual + static_cast<size_t>(row) * ep.ldr : nullptr;
       if (ep.tma_store) {
         // ---- coalesced path: TMEM -> regs -> 128B-swizzled smem tile [32 rows x 64 cols] -> TMA store ----
-        const uint32_t ew = warp - 2;  // 0..3
         const int tile_row0 = m_blk * kBM + static_cast<int>(quad * 32u);
         // fused reduce-scatter: same staged tiles, but the TMA store targets the owner's receive slot over NVLink
         const CUtensorMap* store_map = ep.peer_c != nullptr ? &tmap_peers.m[owner] : &tmap_c;
         const int store_row0 = ep.peer_c != nullptr ? (ep.rank - owner) * ep.rows_per_rank + tile_row0 : tile_row0;
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 64) {
+        for (int c = c_lo; c < c_hi; c += 64) {
           const int col0 = n_blk * BN + c;
           if (col0 >= N) break;
-          const uint32_t buf = store_cnt & 1u;
-          uint8_t* stage = smem_store + (ew * 2 + buf) * 4096;
-          if (lane == 0) tma_store_wait_read<1>();  // the store issued from this buffer two chunks ago has drained
+          uint8_t* stage = smem_store + ew * 4096;
+          if (lane == 0) tma_store_wait_read<0>();  // the previous store from this buffer has been read out
           __syncwarp();
           if (ep.residual != nullptr) {
             if (lane == 0) {
-              mbar_expect_tx(&res_bar[ew * 2 + buf], 4096);
-              tma_load_2d(stage, &tmap_r, &res_bar[ew * 2 + buf], col0, tile_row0);
+              mbar_expect_tx(&res_bar[ew], 4096);
+              tma_load_2d(stage, &tmap_r, &res_bar[ew], col0, tile_row0);
             }
           }
 #pragma unroll
@@ -247,24 +249,30 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             tmem_ld_32x32b_x32(tmem_base + ((quad * 32u) << 16) + acc * BN + c + half * 32, v);
             tmem_ld_wait();
             float f[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * ep.alpha;
             const int cb = col0 + half * 32;
-            if (ep.bias != nullptr) {
-              if (cb + 32 <= N) {
+            if (ep.bias != nullptr && cb + 32 <= N) {
+              // common case: one FFMA per element (alpha * acc + bias)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + cb) + j);
-                  f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
-                }
-              } else {
+              for (int j = 0; j < 8; ++j) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + cb) + j);
+                f[4 * j] = fmaf(__uint_as_float(v[4 * j]), ep.alpha, b4.x);
+                f[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), ep.alpha, b4.y);
+                f[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), ep.alpha, b4.z);
+                f[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), ep.alpha, b4.w);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * ep.alpha;
+            }
+            if (ep.bias != nullptr && cb + 32 > N) {
+              {
 #pragma unroll
                 for (int i = 0; i < 32; ++i)
                   if (cb + i < N) f[i] += __ldg(ep.bias + cb + i);
               }
             }
             apply_act32(f, ep.act);
-            if (ep.residual != nullptr && half == 0) mbar_wait(&res_bar[ew * 2 + buf], (store_cnt >> 1) & 1u);
+            if (ep.residual != nullptr && half == 0) mbar_wait(&res_bar[ew], store_cnt & 1u);
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4) {
               const int ch = (half * 4 + q4) ^ static_cast<int>(lane & 7u);
@@ -293,7 +301,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
       } else
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = c_lo; c < c_hi; c += 32) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_base + ((quad * 32u) << 16) + acc * BN + c, v);
         tmem_ld_wait();

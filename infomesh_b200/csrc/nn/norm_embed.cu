@@ -127,7 +127,7 @@ embed_ln_kernel(const int* __restrict__ ids, const int* __restrict__ pos_ids, co
 //
 // Tensor-parallel hooks (parallel/tp.py):
 //   * fused reduce-scatter consumer: `arrive_flags[src][row/128]` are cumulative arrival counters bumped by the
-//     row-parallel GEMM epilogues of every source rank (4 epilogue warps x N tiles per use); the kernel waits for
+//     row-parallel GEMM epilogues of every source rank (8 epilogue warps x N tiles per use); the kernel waits for
 //     (use + 1) * arrivals_per_block, `use` being read from arrive_state[0], and the last CTA out advances it;
 //   * fused all-gather producer: the normalised row is also stored into every peer's [M_total, H] buffer at
 //     `out_row_offset + row`, and `peer_out_flags[p][(out_row_offset + row) / 128]` is bumped once per row so the

@@ -56,7 +56,7 @@ class ReduceScatterChannel:
         self.state = torch.zeros(2, dtype=torch.int32, device=c.device)
         self.step_ptr = self.state.data_ptr()
         self.bn = _bn_for(n_cols, rows_per_rank * c.world)
-        self.arrivals_per_block = 4 * ((n_cols + self.bn - 1) // self.bn)     # 4 epilogue warps x N tiles
+        self.arrivals_per_block = 8 * ((n_cols + self.bn - 1) // self.bn)     # 8 epilogue warps x N tiles
 
 
 class _AgPush:
