@@ -124,7 +124,8 @@ def index_import_urls(url_file: str, max_urls: int) -> None:
 
 @index_group.command("gpu-build")
 @click.option("--no-rerank", is_flag=True, help="Skip loading the cross-encoder")
-def index_gpu_build(no_rerank: bool) -> None:
+@click.option("--save", "save_dir", default=None, help="Also write the device segments + manifest to this directory")
+def index_gpu_build(no_rerank: bool, save_dir: str | None) -> None:
     """Build the HBM-resident mirror of the index on cuda:0 and report its footprint."""
     from infomesh_b200.engine.gpu_index import GpuSearchIndex
 
@@ -132,4 +133,7 @@ def index_gpu_build(no_rerank: bool) -> None:
         gi = GpuSearchIndex(st, rerank=not no_rerank)
         n = gi.rebuild()
         info = gi.stats()
+        if save_dir and n:
+            man = gi.save(save_dir)
+            click.echo(f"  segments written to {save_dir} ({sum(f['bytes'] for f in man['files'].values()) / 2 ** 20:.1f} MB)")
     click.secho(f"✔ {n} documents resident: {info['hbm_bytes'] / 2 ** 20:.1f} MB HBM, vocabulary {info['vocab']}, built in {info['build_seconds']} s", fg="green")

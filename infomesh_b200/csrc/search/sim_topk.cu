@@ -260,7 +260,7 @@ topk_merge_kernel(const float* __restrict__ cand_scores, const int64_t* __restri
                   float* __restrict__ out_scores, int64_t* __restrict__ out_ids,
                   // fused exchange (all optional)
                   float* const* peer_scores, int64_t* const* peer_ids, uint32_t* const* peer_flags, int world, int rank,
-                  const uint32_t* wait_flags, uint32_t* state) {
+                  const uint32_t* wait_flags, uint32_t* state, uint32_t* status, uint32_t wait_limit) {
   extern __shared__ uint8_t msm[];
   const int q = blockIdx.x;
   const int n = P * k_in;
@@ -275,14 +275,24 @@ topk_merge_kernel(const float* __restrict__ cand_scores, const int64_t* __restri
   // Exchange protocol (see comm/symm.cu): receive areas are [2][world][nq][k] double-buffered on step parity,
   // arrival counters are cumulative: one arrival per query block per step.
   const uint32_t step = state != nullptr ? *reinterpret_cast<volatile uint32_t*>(state) : 0u;
+  __shared__ uint32_t dead_mask;  // bit p: shard p did not deliver in time -> its list is ignored ("search is never blocked")
+  if (threadIdx.x == 0) dead_mask = status != nullptr ? *reinterpret_cast<volatile uint32_t*>(status) : 0u;
+  __syncthreads();
   if (wait_flags != nullptr) {
-    if (threadIdx.x < static_cast<unsigned>(P)) {
+    if (threadIdx.x < static_cast<unsigned>(P) && !((dead_mask >> threadIdx.x) & 1u)) {
       const uint32_t target = (step + 1u) * static_cast<uint32_t>(nq);
+      const uint32_t limit = wait_limit != 0u ? wait_limit : IM_WAIT_LIMIT;
       uint32_t spins = 0;
       while (static_cast<int32_t>(ld_acquire_sys(wait_flags + threadIdx.x) - target) < 0) {
-        if (++spins > IM_WAIT_LIMIT) {
-          printf("[infomesh_b200] topk_merge flag timeout peer=%d\n", (int)threadIdx.x);
-          __trap();
+        if (++spins > limit) {
+          if (status == nullptr) {
+            printf("[infomesh_b200] topk_merge flag timeout peer=%d\n", (int)threadIdx.x);
+            __trap();
+          }
+          // degraded mode: remember the silent shard (sticky until the host clears the word) and answer without it
+          atomicOr(&dead_mask, 1u << threadIdx.x);
+          atomicOr(status, 1u << threadIdx.x);
+          break;
         }
         __nanosleep(20);
       }
@@ -298,6 +308,7 @@ topk_merge_kernel(const float* __restrict__ cand_scores, const int64_t* __restri
     const size_t src = (static_cast<size_t>(p) * nq + q) * k_in + j;
     float sc = cand_scores[src];
     int64_t id = cand_ids64 ? cand_ids64[src] : static_cast<int64_t>(cand_ids32[src]);
+    if (wait_flags != nullptr && ((dead_mask >> p) & 1u)) id = -1;
     if (id < 0) sc = -CUDART_INF_F;
     else if (cand_ids64 == nullptr) id += id_offset;
     s_sc[i] = sc;
@@ -441,7 +452,8 @@ IM_API int im_sim_topk(const void* Q, const void* D, int nq, int n_docs, int dim
 IM_API int im_topk_merge(const float* cand_scores, const int64_t* cand_ids64, const int* cand_ids32, int P, int nq,
                          int k_in, int k_out, int64_t id_offset, float* out_scores, int64_t* out_ids,
                          float* const* peer_scores, int64_t* const* peer_ids, uint32_t* const* peer_flags, int world,
-                         int rank, const uint32_t* wait_flags, uint32_t* state, void* stream) {
+                         int rank, const uint32_t* wait_flags, uint32_t* state, void* stream, uint32_t* status,
+                         unsigned wait_limit) {
   using namespace im;
   if (nq <= 0) return 0;
   const size_t n = static_cast<size_t>(P) * k_in;
@@ -451,7 +463,7 @@ IM_API int im_topk_merge(const float* cand_scores, const int64_t* cand_ids64, co
     IM_CUDA_OK(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   topk_merge_kernel<<<nq, kMergeThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
       cand_scores, cand_ids64, cand_ids32, P, nq, k_in, k_out, id_offset, out_scores, out_ids, peer_scores, peer_ids,
-      peer_flags, world, rank, wait_flags, state);
+      peer_flags, world, rank, wait_flags, state, status, wait_limit);
   IM_LAUNCH_OK("topk_merge_kernel");
   return 0;
 }

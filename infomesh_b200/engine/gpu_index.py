@@ -107,7 +107,6 @@ class GpuSearchIndex:
             self.engine, self.builder = None, builder
             return 0
         csr = builder.export()
-        bm25 = Bm25Index(csr, device=dev)
         vectors = torch.cat(vec_chunks).contiguous()
         ptok = torch.full((n, self.passage_len), self.rr_tok.sp.pad, dtype=torch.int32)
         plen = torch.zeros((n,), dtype=torch.int32)
@@ -115,16 +114,110 @@ class GpuSearchIndex:
             if row:
                 ptok[i, :len(row)] = torch.tensor(row, dtype=torch.int32)
             plen[i] = max(len(row), 1)
-        alive = torch.ones((n,), dtype=torch.uint8, device=dev)
-        shard = _StoreShard(dev, vectors, bm25, ptok.to(dev), plen.to(dev), alive)
-        k_fetch = min(20, 32)
-        cfg = HybridConfig(nq=self.nq, rerank=self.rerank, k_fetch=k_fetch, n_rerank=k_fetch, k_out=10,
-                           pair_seq=min(128, 32 + self.passage_len), use_graph=self.use_graph)
+        self._install(builder, csr, vectors, ptok.to(dev), plen.to(dev), torch.ones((n,), dtype=torch.uint8, device=dev))
+        shard = self.engine.shard
+        self.built_at, self.build_seconds = time.time(), time.time() - t0
+        logger.info("gpu_index_built", docs=n, seconds=round(self.build_seconds, 2), hbm_mb=round(shard.nbytes() / 2 ** 20, 1))
+        return n
+
+    # ------------------------------------------------------------------ persistence
+    _FILES = ("vectors.bin", "csr_off.bin", "csr_doc.bin", "csr_tf.bin", "doc_len.bin", "df.bin", "passage_tok.bin",
+              "passage_len.bin", "doc_ids.bin", "alive.bin", "vocab.txt")
+
+    def _model_tag(self) -> str:
+        """Identifies the encoder whose vectors are stored: config + a checksum of its first projection matrix."""
+        import hashlib
+
+        w = self.encoder.w.layers[0]["wqkv"][:8].float().cpu().numpy().tobytes()
+        return f"{self.encoder.cfg.name}:{self.encoder.cfg.hidden}x{self.encoder.cfg.layers}:{hashlib.sha256(w).hexdigest()[:16]}"
+
+    def save(self, directory) -> dict:
+        """Write the device structures as flat binary segments + ``manifest.json`` (sizes, sha256, model tag) so a node
+        cold-starts with file reads and ``cudaMemcpy`` instead of re-encoding and re-tokenising the corpus."""
+        import hashlib
+        import json
+        from pathlib import Path
+
+        if self.engine is None:
+            raise RuntimeError("nothing to save: call rebuild() first")
+        d = Path(directory)
+        d.mkdir(parents=True, exist_ok=True)
+        sh, bm = self.engine.shard, self.engine.shard.bm25
+        csr = self._csr
+        arrays = {"vectors.bin": sh.vectors.view(torch.int16).cpu().numpy(), "csr_off.bin": csr["off"], "csr_doc.bin": csr["doc"],
+                  "csr_tf.bin": csr["tf"], "doc_len.bin": csr["doc_len"], "df.bin": csr["df"],
+                  "passage_tok.bin": sh.passage_tok.cpu().numpy(), "passage_len.bin": sh.passage_len.cpu().numpy(),
+                  "doc_ids.bin": self.doc_ids, "alive.bin": sh.alive.cpu().numpy()}
+        files = {}
+        for name, arr in arrays.items():
+            arr = np.ascontiguousarray(arr)
+            arr.tofile(d / name)
+            files[name] = {"bytes": int(arr.nbytes), "dtype": str(arr.dtype), "sha256": hashlib.sha256(arr.tobytes()).hexdigest()}
+        vocab = "\n".join(self.builder.term(t) for t in range(self.builder.vocab))
+        (d / "vocab.txt").write_text(vocab, encoding="utf-8")
+        files["vocab.txt"] = {"bytes": len(vocab.encode()), "dtype": "utf-8", "sha256": hashlib.sha256(vocab.encode()).hexdigest()}
+        manifest = {"format": 1, "n_docs": self.n_docs, "dim": int(sh.vectors.shape[1]), "passage_len": self.passage_len, "vocab": self.builder.vocab,
+                    "avg_len": bm.avg_len, "model": self._model_tag(), "doc_id_range": [int(self.doc_ids.min()), int(self.doc_ids.max())],
+                    "saved_at": time.time(), "files": files}
+        (d / "manifest.json").write_text(json.dumps(manifest, indent=1))
+        return manifest
+
+    def load(self, directory, *, verify: bool = True) -> int:
+        """Inverse of :meth:`save`.  Refuses segments written for a different encoder or with a failing checksum."""
+        import hashlib
+        import json
+        from pathlib import Path
+
+        d = Path(directory)
+        man = json.loads((d / "manifest.json").read_text())
+        if man.get("format") != 1:
+            raise ValueError("unknown segment format")
+        if man["model"] != self._model_tag():
+            raise ValueError(f"segments were built for encoder {man['model']}, this index uses {self._model_tag()}")
+        t0 = time.time()
+
+        def read(name, dtype):
+            raw = np.fromfile(d / name, dtype=dtype)
+            meta = man["files"][name]
+            if raw.nbytes != meta["bytes"] or (verify and hashlib.sha256(raw.tobytes()).hexdigest() != meta["sha256"]):
+                raise ValueError(f"segment {name} is corrupt")
+            return raw
+
+        n, dim, dev = man["n_docs"], man["dim"], self.device
+        csr = {"off": read("csr_off.bin", np.int64), "doc": read("csr_doc.bin", np.int32), "tf": read("csr_tf.bin", np.uint8),
+               "doc_len": read("doc_len.bin", np.int32), "df": read("df.bin", np.int32)}
+        vectors = torch.from_numpy(read("vectors.bin", np.int16)).view(torch.bfloat16).view(n, dim).to(dev)
+        ptok = torch.from_numpy(read("passage_tok.bin", np.int32)).view(n, man["passage_len"]).to(dev)
+        plen = torch.from_numpy(read("passage_len.bin", np.int32)).to(dev)
+        alive = torch.from_numpy(read("alive.bin", np.uint8)).to(dev)
+        self.doc_ids = read("doc_ids.bin", np.int64)
+        self._row_of = {int(x): i for i, x in enumerate(self.doc_ids)}
+        builder = HostIndexBuilder()
+        terms = (d / "vocab.txt").read_text(encoding="utf-8")
+        if terms:
+            builder.tokenize(terms.replace("\n", " "), add=True)       # re-registers the terms in id order
+        if builder.vocab != man["vocab"]:
+            raise ValueError("vocabulary does not round-trip")
+        self.passage_len = man["passage_len"]
+        self._install(builder, csr, vectors, ptok, plen, alive)
+        self.built_at, self.build_seconds = time.time(), time.time() - t0
+        return n
+
+    def _install(self, builder, csr, vectors, ptok, plen, alive) -> None:
+        """Adopt device structures (fresh build or loaded segments) and (re)create the engine + pinned staging."""
+        dev = self.device
+        self._csr = csr
+        shard = _StoreShard(dev, vectors, Bm25Index(csr, device=dev), ptok, plen, alive)
+        cfg = HybridConfig(nq=self.nq, rerank=self.rerank, k_fetch=20, n_rerank=20, k_out=10, pair_seq=min(128, 32 + self.passage_len),
+                           use_graph=self.use_graph)
         self.engine = HybridEngine(shard, cfg, encoder=self.encoder, reranker=self.reranker)
         self.builder = builder
-        # pinned staging buffers for the per-batch H2D copies
         pin = torch.cuda.is_available()
-        mk = lambda *shape, fill=0: torch.full(shape, fill, dtype=torch.int32).pin_memory() if pin else torch.full(shape, fill, dtype=torch.int32)  # noqa: E731
+
+        def mk(*shape, fill=0):
+            t = torch.full(shape, fill, dtype=torch.int32)
+            return t.pin_memory() if pin else t
+
         self._h_enc, self._h_enc_len = mk(cfg.nq, cfg.enc_seq), mk(cfg.nq, fill=1)
         self._h_qtok, self._h_qlen = mk(cfg.nq, cfg.max_q_tokens, fill=self.rr_tok.sp.pad), mk(cfg.nq, fill=1)
         self._h_terms = mk(cfg.nq, cfg.max_terms, fill=-1)
@@ -132,9 +225,6 @@ class GpuSearchIndex:
         self._h_ids = torch.empty((cfg.nq, cfg.k_out), dtype=torch.int64)
         if pin:
             self._h_scores, self._h_ids = self._h_scores.pin_memory(), self._h_ids.pin_memory()
-        self.built_at, self.build_seconds = time.time(), time.time() - t0
-        logger.info("gpu_index_built", docs=n, seconds=round(self.build_seconds, 2), hbm_mb=round(shard.nbytes() / 2 ** 20, 1))
-        return n
 
     def mark_deleted(self, doc_id: int) -> bool:
         row = self._row_of.get(int(doc_id))

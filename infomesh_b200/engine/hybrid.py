@@ -38,6 +38,8 @@ class HybridConfig:
     backend: str = "fused"    # "fused" | "torch"
     use_graph: bool = True
     exchange: str = "p2p"     # multi-GPU list exchange: "p2p" (fused peer-memory kernels) | "nccl" (baseline collectives)
+    degraded_ok: bool = False  # p2p exchange: drop a silent shard after ``wait_limit`` polls instead of trapping
+    wait_limit: int = 0        # 0 = library default (~1 s)
 
 
 class HybridEngine:
@@ -75,12 +77,17 @@ class HybridEngine:
         self._graph = None
         self._graph_failed = False
         self.heap = None
+        self._inject_drop = False
         if self.ctx.is_dist and cfg.backend == "fused" and cfg.exchange == "p2p":
             from infomesh_b200.parallel import symm
 
             self.heap = symm.SymmetricHeap(8 << 20, self.ctx)
-            self.ch_dense = symm.TopkChannel(self.heap, cfg.nq, cfg.k_fetch)
-            self.ch_bm25 = symm.TopkChannel(self.heap, cfg.nq, cfg.k_fetch)
+            kw = dict(degraded_ok=cfg.degraded_ok, wait_limit=cfg.wait_limit)
+            self.ch_dense = symm.TopkChannel(self.heap, cfg.nq, cfg.k_fetch, **kw)
+            self.ch_bm25 = symm.TopkChannel(self.heap, cfg.nq, cfg.k_fetch, **kw)
+            import os
+
+            self._inject_drop = os.environ.get("INFOMESH_B200_INJECT_DROP_RANK", "") == str(self.ctx.rank)   # fault-injection hook
             n_log = self.nq_local * cfg.n_rerank
             self._log_pad = (n_log + 3) // 4 * 4           # 16-byte blocks
             self.ch_logits = symm.AllGatherChannel(self.heap, (self._log_pad,), torch.float32)
@@ -99,13 +106,13 @@ class HybridEngine:
             sc = q_emb @ sh.vectors.t()
             v, i = torch.topk(sc.float(), min(cfg.k_fetch, sh.vectors.shape[0]), dim=1)
             return v, i.long() + sh.cfg.doc_base
-        return S.sim_topk(q_emb, sh.vectors, cfg.k_fetch, alive=sh.alive, id_offset=sh.cfg.doc_base,
-                          push=self.ch_dense if self.heap is not None else None)
+        push = self.ch_dense if (self.heap is not None and not self._inject_drop) else None
+        return S.sim_topk(q_emb, sh.vectors, cfg.k_fetch, alive=sh.alive, id_offset=sh.cfg.doc_base, push=push)
 
     def _bm25_local(self):
         sh = self.shard
         s, i = sh.bm25.search(self.in_terms, k=self.cfg.k_fetch, alive=sh.alive, id_offset=sh.cfg.doc_base)
-        if self.heap is not None:      # 1-list "merge" whose epilogue pushes the shard's list to every peer
+        if self.heap is not None and not self._inject_drop:      # 1-list "merge" whose epilogue pushes the shard's list to every peer
             S.topk_merge(s.unsqueeze(0), i.unsqueeze(0), self.cfg.k_fetch, push=self.ch_bm25)
         return s, i
 
@@ -216,6 +223,12 @@ class HybridEngine:
         out_scores_host.copy_(self.out_scores, non_blocking=True)
         out_ids_host.copy_(self.out_ids, non_blocking=True)
         return out_scores_host, out_ids_host
+
+    def degraded_shards(self) -> list[int]:
+        """Ranks whose lists were dropped from a merge because they stayed silent (p2p exchange, ``degraded_ok``)."""
+        if self.heap is None:
+            return []
+        return sorted(set(self.ch_dense.dead_ranks()) | set(self.ch_bm25.dead_ranks()))
 
     def launches_per_step(self) -> int:
         from infomesh_b200 import _native

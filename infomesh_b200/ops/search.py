@@ -74,7 +74,9 @@ def topk_merge(cand_scores, cand_ids, k_out, id_offset=0, out_scores=None, out_i
                          ctypes.c_void_p(push.peer_flags_ptr if push else 0),
                          ctypes.c_int(push.world if push else 1), ctypes.c_int(push.rank if push else 0),
                          ctypes.c_void_p(wait.local_flags_ptr if wait else 0),
-                         ctypes.c_void_p((push or wait).step_ptr if (push or wait) else 0), _native.stream_ptr())
+                         ctypes.c_void_p((push or wait).step_ptr if (push or wait) else 0), _native.stream_ptr(),
+                         ctypes.c_void_p(wait.status_ptr if (wait is not None and wait.degraded_ok) else 0),
+                         ctypes.c_uint(wait.wait_limit if wait is not None else 0))
     _native.check(rc, "im_topk_merge")
     _native.count_launch()
     return out_scores, out_ids

@@ -154,13 +154,25 @@ class TopkChannel(FlagChannel):
     Producer: ``topk_merge(..., push=chan)`` — the local merge kernel stores its result into slot[rank] of every peer.
     Consumer: ``topk_merge(chan.recv_scores_view, chan.recv_ids_view, k, wait=chan)`` — waits for all arrivals."""
 
-    def __init__(self, heap: SymmetricHeap, nq: int, k: int):
+    def __init__(self, heap: SymmetricHeap, nq: int, k: int, *, degraded_ok: bool = False, wait_limit: int = 0):
         super().__init__(heap)
         self.nq, self.k = nq, k
+        # degraded mode: a shard that stays silent for ``wait_limit`` polls is dropped from the merge and recorded in
+        # ``status`` (bit per rank, sticky) instead of trapping the kernel
+        self.degraded_ok, self.wait_limit = degraded_ok, wait_limit
+        self.status = torch.zeros(1, dtype=torch.int32, device=heap.ctx.device)
+        self.status_ptr = self.status.data_ptr()
         self.recv_scores, so = heap.alloc((2, self.world, nq, k), torch.float32)
         self.recv_ids, io = heap.alloc((2, self.world, nq, k), torch.int64)
         self._s_tab, self._i_tab = heap.peer_table(so), heap.peer_table(io)
         self.peer_scores_ptr, self.peer_ids_ptr = self._s_tab.data_ptr(), self._i_tab.data_ptr()
+
+    def dead_ranks(self) -> list[int]:
+        m = int(self.status.item()) & 0xFFFFFFFF
+        return [r for r in range(self.world) if (m >> r) & 1]
+
+    def clear_status(self) -> None:
+        self.status.zero_()
 
     @property
     def cand_scores(self) -> torch.Tensor:       # parity is applied inside the kernel

@@ -38,6 +38,20 @@ def main():
         ok &= good
         if c.rank == 0:
             print("topk exchange step", step, "ok" if good else "MISMATCH")
+    # ---- degraded mode: rank (world-1) never pushes; every rank drops that shard after the poll limit and says so
+    chd = symm.TopkChannel(heap, nq, k, degraded_ok=True, wait_limit=200_000)
+    sc = torch.rand((2, nq, k), device=dev, generator=g).sort(dim=2, descending=True).values
+    ids = torch.randint(0, 1 << 30, (2, nq, k), device=dev, generator=g) * c.world + c.rank
+    silent = c.world - 1
+    for step in range(2):
+        ls, li = S.topk_merge(sc, ids, k, push=None if c.rank == silent else chd)
+        gs, gi = S.topk_merge(chd.cand_scores, chd.cand_ids, k, wait=chd)
+        all_s, all_i = D.all_gather_cat(ls), D.all_gather_cat(li)
+        rs, ri = S.topk_merge(all_s[:silent].contiguous(), all_i[:silent].contiguous(), k)
+        good = torch.equal(gs, rs) and torch.equal(gi, ri) and chd.dead_ranks() == [silent]
+        ok &= good
+        if c.rank == 0:
+            print("degraded exchange step", step, "ok" if good else f"MISMATCH dead={chd.dead_ranks()}")
     # ---- graph replay
     src = torch.zeros((4096,), device=dev)
     s = torch.cuda.Stream()

@@ -340,6 +340,16 @@ def test_gpu_search_index_over_local_store(tmp_path):
     assert sum("kademlia" in h["snippet"].lower() or "kademlia" in h["title"].lower() for h in res[0]) >= 3
     st = gi.stats()
     assert st["documents"] == 60 and st["hbm_bytes"] > 0
+    # segments round-trip: a second index loads them (no re-encoding) and answers identically
+    man = gi.save(tmp_path / "segments")
+    assert man["n_docs"] == 60 and set(man["files"]) == set(GpuSearchIndex._FILES)
+    gi2 = GpuSearchIndex(store, device=dev, encoder=gi.encoder, reranker=gi.reranker, query_batch=8)
+    assert gi2.load(tmp_path / "segments") == 60
+    again2 = gi2.search_many(["kademlia buckets", "merkle audit proofs"], k=5)
+    assert [h["doc_id"] for h in again2[0]] == [h["doc_id"] for h in res[0]]
+    (tmp_path / "segments" / "csr_tf.bin").write_bytes(b"\0" * man["files"]["csr_tf.bin"]["bytes"])
+    with pytest.raises(ValueError, match="corrupt"):
+        gi2.load(tmp_path / "segments")
     first = res[1][0]["doc_id"]
     assert gi.mark_deleted(first)
     again = gi.search("merkle audit proofs", k=5)
