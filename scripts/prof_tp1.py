@@ -32,4 +32,9 @@ def t(fn, n=20):
     return a.elapsed_time(b) / n
 
 
+if len(sys.argv) > 3 and sys.argv[3] == "tp-only":
+    for _ in range(3):
+        tpm.score(ids, lens)
+    torch.cuda.synchronize()
+    sys.exit(0)
 print(f"B={B} S={S} layers={layers}: plain {t(lambda: plain.score(ids, lens)):.3f} ms   fused-tp(world=1) {t(lambda: tpm.score(ids, lens)):.3f} ms")
