@@ -205,6 +205,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int c_lo = static_cast<int>(ew >> 2) * (BN / 2), c_hi = c_lo + BN / 2;  // this warp's half of the tile columns
     const uint32_t row_in_tile = quad * 32u + lane;
     uint32_t acc = 0, acc_phase = 0, store_cnt = 0;
+    constexpr int kChunks = BN / 128;     // bulk-store groups this warp commits per tile
+    uint32_t* pending_flag = nullptr;     // fused reduce-scatter: arrival counter of the previous tile (lane 0)
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       int m_blk = t / num_n, n_blk = t % num_n;
       m_blk = (m_blk + ep.m_rotate) % num_m;
@@ -230,10 +232,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         // fused reduce-scatter: same staged tiles, but the TMA store targets the owner's receive slot over NVLink
         const CUtensorMap* store_map = ep.peer_c != nullptr ? &tmap_peers.m[owner] : &tmap_c;
         const int store_row0 = ep.peer_c != nullptr ? (ep.rank - owner) * ep.rows_per_rank + tile_row0 : tile_row0;
+        int n_commit = 0;
 #pragma unroll 1
         for (int c = c_lo; c < c_hi; c += 64) {
           const int col0 = n_blk * BN + c;
           if (col0 >= N) break;
+          ++n_commit;
           uint8_t* stage = smem_store + ew * 4096;
           if (lane == 0) tma_store_wait_read<0>();  // the previous store from this buffer has been read out
           __syncwarp();
@@ -299,6 +303,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
           ++store_cnt;
         }
+        // always kChunks groups per tile so wait_group<kChunks> below means "the previous tile has landed"
+        if (ep.peer_c != nullptr && lane == 0)
+          for (; n_commit < kChunks; ++n_commit) tma_store_commit();
       } else
 #pragma unroll 1
       for (int c = c_lo; c < c_hi; c += 32) {
@@ -362,17 +369,24 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
       // TMEM reads done -> hand the accumulator stage back to the MMA warp
       tc_fence_before();
-      if (ep.peer_c != nullptr) {
-        if (ep.tma_store && lane == 0) tma_store_wait_all<0>();  // this warp's bulk stores have completed (not just been read)
-        __threadfence_system();  // pushed rows visible before the arrival counter
-      }
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(&tmem_empty[acc]);
         if (ep.peer_c != nullptr) {
           const int blk_local = (m_blk * kBM - owner * ep.rows_per_rank) / kBM;
           uint32_t* flag = ep.peer_flags[owner] + static_cast<size_t>(ep.rank) * (ep.rows_per_rank / kBM) + blk_local;
-          asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(flag) : "memory");
+          if (ep.tma_store) {
+            // deferred arrival: the counter of tile t-1 is bumped once its bulk stores have COMPLETED (not merely been
+            // read out of smem), which by now costs nothing -- tile t's stores are the only groups still in flight.
+            // red.release.sys orders the completed async-proxy writes before the bump for the acquiring consumer.
+            if (pending_flag != nullptr) {
+              tma_store_wait_all<kChunks>();
+              asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(pending_flag) : "memory");
+            }
+            pending_flag = flag;
+          } else {
+            asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(flag) : "memory");
+          }
         }
       }
       if (++acc == 2) {
@@ -380,7 +394,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         acc_phase ^= 1;
       }
     }
-    if (ep.tma_store && lane == 0) tma_store_wait_all<0>();
+    if (ep.tma_store && lane == 0) {
+      tma_store_wait_all<0>();
+      if (pending_flag != nullptr)
+        asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(pending_flag) : "memory");
+    }
   }
 
   tc_fence_before();

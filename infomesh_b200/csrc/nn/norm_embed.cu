@@ -154,22 +154,23 @@ sum_ln_kernel(const __nv_bfloat16* __restrict__ in, size_t in_stride_p, int P,
   const int row = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const uint32_t use = cm.arrive_state != nullptr ? *reinterpret_cast<volatile uint32_t*>(cm.arrive_state) : 0u;
-  if (row < n_rows) {
-    if (cm.arrive_flags != nullptr) {
-      const int blk = row >> 7;
-      if (lane < P) {
-        const uint32_t target = (use + 1u) * cm.arrivals_per_block;
-        uint32_t spins = 0;
-        while (static_cast<int32_t>(ld_acquire_sys(cm.arrive_flags + lane * cm.blocks_per_src + blk) - target) < 0) {
-          if (++spins > IM_WAIT_LIMIT) {
-            printf("[infomesh_b200] sum_ln arrival timeout src=%d blk=%d\n", lane, blk);
-            __trap();
-          }
-          __nanosleep(20);
+  if (cm.arrive_flags != nullptr) {
+    // one poll per CTA: its kRowsPerBlock rows all live in the same 128-row arrival block
+    const int blk = (blockIdx.x * kRowsPerBlock) >> 7;
+    if (threadIdx.x < static_cast<unsigned>(P)) {
+      const uint32_t target = (use + 1u) * cm.arrivals_per_block;
+      uint32_t spins = 0;
+      while (static_cast<int32_t>(ld_acquire_sys(cm.arrive_flags + threadIdx.x * cm.blocks_per_src + blk) - target) < 0) {
+        if (++spins > IM_WAIT_LIMIT) {
+          printf("[infomesh_b200] sum_ln arrival timeout src=%d blk=%d\n", static_cast<int>(threadIdx.x), blk);
+          __trap();
         }
+        __nanosleep(20);
       }
-      __syncwarp();
     }
+    __syncthreads();
+  }
+  if (row < n_rows) {
     float x[VEC][4];
 #pragma unroll
     for (int v = 0; v < VEC; ++v)
@@ -201,14 +202,16 @@ sum_ln_kernel(const __nv_bfloat16* __restrict__ in, size_t in_stride_p, int P,
       const size_t grow = static_cast<size_t>(cm.out_row_offset) + row;
       ln_finish<VEC>(x, gamma, beta, eps, out != nullptr ? out + static_cast<size_t>(row) * H : nullptr, lane, rms_only != 0,
                      cm.peer_out, grow * H, cm.peer_out != nullptr ? cm.world : 0);
-      if (cm.peer_out_flags != nullptr) {
-        __threadfence_system();
-        __syncwarp();
-        if (lane < cm.world) {
-          uint32_t* f = cm.peer_out_flags[lane] + (grow >> 7);
-          asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(f) : "memory");
-        }
-      }
+    }
+  }
+  if (cm.peer_out_flags != nullptr) {
+    // one release per CTA and peer (not per row): bar.sync orders every warp's pushed rows before the counter bump
+    __syncthreads();
+    const int row0 = blockIdx.x * kRowsPerBlock;
+    const int n_valid = min(kRowsPerBlock, n_rows - row0);
+    if (threadIdx.x < static_cast<unsigned>(cm.world) && n_valid > 0) {
+      uint32_t* f = cm.peer_out_flags[threadIdx.x] + ((static_cast<size_t>(cm.out_row_offset) + row0) >> 7);
+      asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(f), "r"(static_cast<uint32_t>(n_valid)) : "memory");
     }
   }
   if (cm.arrive_state != nullptr) {  // last CTA out advances the reduce-scatter channel

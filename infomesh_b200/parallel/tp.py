@@ -96,9 +96,8 @@ class TPBertModel:
         self.w = BertWeights(cfg, device=c.device, seed=seed, tp_rank=c.rank, tp_size=self.tp)
         H = cfg.hidden
         if comm == "fused":
-            need = 2 * self.M * H * 2 + 2 * self.tp * self.rows * H * 2 + 2 * 2 * self.rows * H * 2 + (1 << 20)
+            need = 2 * self.M * H * 2 + 2 * self.tp * self.rows * H * 2 + (1 << 20)
             self.heap = heap or SymmetricHeap(need + (8 << 20), c)
-            self.ag0 = AllGatherChannel(self.heap, (self.rows, H), torch.bfloat16, ctas=32)
             self.ag1 = AllGatherInput(self.heap, self.M, H, self.rows)
             self.ag2 = AllGatherInput(self.heap, self.M, H, self.rows)
             self.rs1 = ReduceScatterChannel(self.heap, self.rows, H)
@@ -116,12 +115,14 @@ class TPBertModel:
         cfg, w, c = self.cfg, self.w, self.ctx
         B, S, H, tp = self.B, self.S, cfg.hidden, self.tp
         assert tuple(ids.shape) == (B, S)
-        b0 = c.rank * (B // tp)
-        my_ids = ids[b0:b0 + B // tp].reshape(-1).contiguous()
-        x_loc = N.embed_ln(my_ids, w.word, w.pos, w.type, w.emb_g, w.emb_b, cfg.eps, S, pos_offset=cfg.pos_offset)
+        # ids are replicated, so every rank embeds the whole batch itself: ~0.2 ms of redundant gather+LN at B=1280
+        # instead of a [M, H] all-gather in front of the first QKV GEMM
+        x_full = N.embed_ln(ids.reshape(-1).contiguous(), w.word, w.pos, w.type, w.emb_g, w.emb_b, cfg.eps, S,
+                            pos_offset=cfg.pos_offset)
+        r0 = c.rank * self.rows
+        x_loc = x_full[r0:r0 + self.rows]
         hs, heads = H // tp, cfg.heads // tp
         fused = self.comm == "fused"
-        x_full = self.ag0(x_loc).view(self.M, H) if fused else self._nccl_ag(x_loc)
         n_layers = len(w.layers)
         for li, lay in enumerate(w.layers):
             # ---- attention block: column-parallel QKV (all-gather consumer) -> local heads -> row-parallel out-proj
@@ -129,9 +130,12 @@ class TPBertModel:
             ctx_ = A.attention(qkv[..., :hs], qkv[..., hs:2 * hs], qkv[..., 2 * hs:], heads, kv_lens=lengths)
             if fused:
                 G.linear(ctx_.view(self.M, hs), lay["wo"], lay["bo"], rs=self.rs1, bn=self.rs1.bn)
-                x1 = N.layernorm(self.rs1.recv.view(tp, self.rows, H), lay["ln1_g"], lay["ln1_b"], cfg.eps, residual=x_loc, partials=tp,
-                                 partial_stride=self.rows * H, rs=self.rs1, ag_push=self.ag2.push)
+                # the normalised rows land straight in every rank's full-sequence buffer (own copy included): the local
+                # shard used as the next residual is a view of that buffer, so there is no separate local write
+                N.layernorm(self.rs1.recv.view(tp, self.rows, H), lay["ln1_g"], lay["ln1_b"], cfg.eps, residual=x_loc, partials=tp,
+                            partial_stride=self.rows * H, rs=self.rs1, ag_push=self.ag2.push, want_norm=False)
                 x_full2 = self.ag2.buf
+                x1 = x_full2[r0:r0 + self.rows]
             else:
                 part = G.linear(ctx_.view(self.M, hs), lay["wo"], lay["bo"])
                 x1 = N.layernorm(self._nccl_rs(part), lay["ln1_g"], lay["ln1_b"], cfg.eps, residual=x_loc)
@@ -142,8 +146,11 @@ class TPBertModel:
             if fused:
                 G.linear(h, lay["w2"], lay["b2"], rs=self.rs2, bn=self.rs2.bn)
                 x_loc = N.layernorm(self.rs2.recv.view(tp, self.rows, H), lay["ln2_g"], lay["ln2_b"], cfg.eps, residual=x1, partials=tp,
-                                    partial_stride=self.rows * H, rs=self.rs2, ag_push=None if last else self.ag1.push)
+                                    partial_stride=self.rows * H, rs=self.rs2, ag_push=None if last else self.ag1.push,
+                                    want_norm=last)
                 x_full = self.ag1.buf
+                if not last:
+                    x_loc = x_full[r0:r0 + self.rows]
             else:
                 part = G.linear(h, lay["w2"], lay["b2"])
                 x_loc = N.layernorm(self._nccl_rs(part), lay["ln2_g"], lay["ln2_b"], cfg.eps, residual=x1)
