@@ -63,7 +63,8 @@ template <int NPAD>
 __global__ void __launch_bounds__(kSimThreads, 1)
 sim_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_d, int nq,
                 int n_docs, int dim, int stages, int ktop, const uint8_t* __restrict__ alive,
-                float* __restrict__ out_scores, int* __restrict__ out_ids) {
+                float* __restrict__ out_scores, int* __restrict__ out_ids, const float* __restrict__ thr_init,
+                int thr_stride) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -105,7 +106,16 @@ sim_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < NPAD; i += kSimThreads) thr[i] = -CUDART_INF_F;
+  // thr_init[j]: a known lower bound of query j's K-th best score (the K-th best of a sample, see ops/search.py).
+  // One ulp below it, so the sampled document that defines the bound still passes the strict `>` filter.
+  for (int i = threadIdx.x; i < NPAD; i += kSimThreads) {
+    float t0 = -CUDART_INF_F;
+    if (thr_init != nullptr && i < nq) {
+      const float b = thr_init[static_cast<size_t>(i) * thr_stride];
+      if (b > -CUDART_INF_F && b == b) t0 = __uint_as_float(b > 0.f ? __float_as_uint(b) - 1u : (b < 0.f ? __float_as_uint(b) + 1u : 0x80000001u));
+    }
+    thr[i] = t0;
+  }
   for (int i = threadIdx.x; i < 4 * nq * ktop; i += kSimThreads) {
     list_v[i] = -CUDART_INF_F;
     list_i[i] = -1;
@@ -413,7 +423,8 @@ topk_merge_kernel(const float* __restrict__ cand_scores, const int64_t* __restri
 // Per-CTA candidate lists: out_scores/out_ids are [grid, nq, ktop]; returns grid (CTA count) or <0.
 template <int NPAD>
 static int launch_sim(const void* Q, const void* D, int nq, int n_docs, int dim, int ldq, int ldd, int ktop,
-                      const uint8_t* alive, float* out_scores, int* out_ids, int max_ctas, cudaStream_t s) {
+                      const uint8_t* alive, float* out_scores, int* out_ids, int max_ctas, const float* thr_init,
+                      int thr_stride, cudaStream_t s) {
   using namespace im;
   const int num_kb = dim / kSimBK;
   const int q_bytes = num_kb * NPAD * kSimBK * 2;
@@ -431,22 +442,23 @@ static int launch_sim(const void* Q, const void* D, int nq, int n_docs, int dim,
   if (get_tmap_2d(&td, D, n_docs, dim, static_cast<uint64_t>(ldd) * 2, kSimBM, kSimBK, 2, TMAP_SW_128)) return -1;
   IM_CUDA_OK(cudaFuncSetAttribute(sim_topk_kernel<NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   sim_topk_kernel<NPAD><<<grid, kSimThreads, smem_bytes, s>>>(tq, td, nq, n_docs, dim, stages, ktop, alive, out_scores,
-                                                               out_ids);
+                                                               out_ids, thr_init, thr_stride);
   IM_LAUNCH_OK("sim_topk_kernel");
   return grid;
 }
 
 IM_API int im_sim_topk(const void* Q, const void* D, int nq, int n_docs, int dim, int ldq, int ldd, int ktop,
-                       const uint8_t* alive, float* out_scores, int* out_ids, int max_ctas, void* stream) {
+                       const uint8_t* alive, float* out_scores, int* out_ids, int max_ctas, const float* thr_init,
+                       int thr_stride, void* stream) {
   using namespace im;
   if (nq < 1 || nq > 128) return set_error("im_sim_topk", "nq must be in [1,128]");
   if (dim % kSimBK != 0 || dim > 512) return set_error("im_sim_topk", "dim must be a multiple of 64 and <= 512");
   if (ktop < 1 || ktop > 32) return set_error("im_sim_topk", "ktop must be in [1,32]");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (nq <= 16) return launch_sim<16>(Q, D, nq, n_docs, dim, ldq, ldd, ktop, alive, out_scores, out_ids, max_ctas, s);
-  if (nq <= 32) return launch_sim<32>(Q, D, nq, n_docs, dim, ldq, ldd, ktop, alive, out_scores, out_ids, max_ctas, s);
-  if (nq <= 64) return launch_sim<64>(Q, D, nq, n_docs, dim, ldq, ldd, ktop, alive, out_scores, out_ids, max_ctas, s);
-  return launch_sim<128>(Q, D, nq, n_docs, dim, ldq, ldd, ktop, alive, out_scores, out_ids, max_ctas, s);
+  if (nq <= 16) return launch_sim<16>(Q, D, nq, n_docs, dim, ldq, ldd, ktop, alive, out_scores, out_ids, max_ctas, thr_init, thr_stride, s);
+  if (nq <= 32) return launch_sim<32>(Q, D, nq, n_docs, dim, ldq, ldd, ktop, alive, out_scores, out_ids, max_ctas, thr_init, thr_stride, s);
+  if (nq <= 64) return launch_sim<64>(Q, D, nq, n_docs, dim, ldq, ldd, ktop, alive, out_scores, out_ids, max_ctas, thr_init, thr_stride, s);
+  return launch_sim<128>(Q, D, nq, n_docs, dim, ldq, ldd, ktop, alive, out_scores, out_ids, max_ctas, thr_init, thr_stride, s);
 }
 
 IM_API int im_topk_merge(const float* cand_scores, const int64_t* cand_ids64, const int* cand_ids32, int P, int nq,

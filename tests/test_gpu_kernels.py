@@ -45,7 +45,8 @@ def test_gemm_matches_fp32_reference(m, n, k, bias, act, resid, bn, fp32):
 @pytest.mark.parametrize("nq,n,dim,k,alive", [(1, 1000, 384, 10, None), (7, 5000, 384, 10, None),
                                                (64, 60000, 384, 10, None), (128, 100001, 384, 16, None),
                                                (33, 30000, 384, 32, None), (64, 50000, 384, 10, 0.5),
-                                               (5, 130, 128, 10, None), (16, 20000, 512, 10, None)])
+                                               (5, 130, 128, 10, None), (16, 20000, 512, 10, None),
+                                               (64, 200000, 384, 20, 0.7), (20, 400000, 384, 20, None)])
 def test_sim_topk_exact(nq, n, dim, k, alive):
     from infomesh_b200.ops.search import sim_topk, sim_topk_ref
 
