@@ -149,6 +149,49 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// One 64-wide K block (4 x K=16 bf16 MMAs) + the commit that frees its smem stage, as ONE asm statement, called by
+// ALL 32 lanes of the (converged) MMA warp; `elect.sync` inside picks the issuing lane.
+//
+// Why not `if (lane == 0) { tcgen05.mma ... }`: in divergent code ptxas must assume any subset of lanes is active, so
+// it wraps every tcgen05 instruction in an ELECT / vote / BRA.U.ANY serialisation loop and re-materialises the
+// uniform-register descriptors each time (~25 SASS instructions per MMA; the issue loop then takes as long as the
+// MMAs themselves and the tensor pipe idles ~45 %).  With warp-uniform control flow and an elect.sync predicate the
+// MMAs compile to back-to-back `@UP UTCHMMA`.  The descriptors' 14-bit address field is stepped in place
+// (+2 = 32 bytes per K=16 step inside the 128B swizzle atom).
+__device__ __forceinline__ void umma_bf16_kblock64_warp(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                        uint32_t accumulate_first, uint64_t* commit_bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q, pe;\n"
+      ".reg .b64 a1, a2, a3, b1, b2, b3;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "setp.eq.b32 q, %4, %4;\n"
+      "add.s64 a1, %1, 2;\n"
+      "add.s64 b1, %2, 2;\n"
+      "add.s64 a2, %1, 4;\n"
+      "add.s64 b2, %2, 4;\n"
+      "add.s64 a3, %1, 6;\n"
+      "add.s64 b3, %2, 6;\n"
+      "elect.sync _|pe, 0xffffffff;\n"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, q;\n"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, q;\n"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, q;\n"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate_first), "r"(smem_u32(commit_bar))
+      : "memory");
+}
+// tcgen05.commit from one elected lane of a converged warp
+__device__ __forceinline__ void umma_commit_warp(uint64_t* bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred pe;\n"
+      "elect.sync _|pe, 0xffffffff;\n"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+      "}\n" ::"r"(smem_u32(bar))
+      : "memory");
+}
 // fp8 (e4m3/e5m2) dense MMA, K = 32 per instruction.
 __device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                         uint32_t accumulate) {

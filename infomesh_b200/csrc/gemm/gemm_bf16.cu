@@ -168,8 +168,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer ---------------------------------
-    if (lane == 0) {
+    // The whole warp runs the loop (warp-uniform control flow); one elected lane issues (see umma_bf16_kblock64_warp).
+    {
       constexpr uint32_t idesc = umma_idesc_f16(kBM, BN);
+      static_assert(kBK == 64, "umma_bf16_kblock64_warp issues exactly one 64-wide K block");
+      // stage s operands live at smem + s * kStageBytes (A) / + kBM*kBK*2 (B): descriptors differ only in the
+      // address field (16-byte units), so they are built once and stepped with integer adds
+      const uint64_t a_desc0 = umma_desc_k_sw128(smem_u32(smem));
+      const uint64_t b_desc0 = umma_desc_k_sw128(smem_u32(smem) + kBM * kBK * 2);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -178,20 +184,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a0 = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t b0 = a0 + kBM * kBK * 2;
-#pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            umma_bf16(d_tmem, umma_desc_k_sw128(a0 + k * 32), umma_desc_k_sw128(b0 + k * 32), idesc,
-                      (kb | k) != 0 ? 1u : 0u);
-          }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          const uint64_t soff = static_cast<uint64_t>(stage * (Cfg::kStageBytes >> 4));
+          umma_bf16_kblock64_warp(d_tmem, a_desc0 + soff, b_desc0 + soff, idesc, kb != 0 ? 1u : 0u, &empty_bar[stage]);
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        umma_commit_warp(&tmem_full[acc]);  // accumulator complete -> epilogue
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
