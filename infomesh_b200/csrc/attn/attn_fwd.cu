@@ -268,6 +268,198 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   if (warp == 0) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Single-chunk fast path (Sk <= 128, HD == 64, no relative bias): the cross-encoder / BERT-encoder shape that is
+// ~11 % of the serving step.  Same math as attn_fwd_kernel, restructured for latency:
+//   * 256 threads: TWO threads per query row (warps w and w+4 share TMEM lane quadrant w%4), each owning 64 of the
+//     128 key columns, so the serial per-row softmax chain is half as long and 32 warps/SM hide TMEM/MUFU latency
+//   * row max of the RAW scores (scale > 0), then one FFMA + EX2 per element; partner halves exchange max / sum
+//     through smem with a 64-thread named barrier
+//   * both MMAs are issued by warp 0 as fused elect.sync blocks (back-to-back UTCHMMA)
+//   * P overwrites the dead Q+K tiles and the normalised O tile overwrites the dead V tile (48 KB smem, 4 CTAs/SM);
+//     O leaves through one coalesced TMA store instead of 128-byte-per-thread row stores
+// ------------------------------------------------------------------------------------------------
+constexpr int kAttn1Threads = 256;
+
+__global__ void __launch_bounds__(kAttn1Threads, 4)
+attn_fwd_1chunk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                       const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
+                       const AttnParams p, int tma_out) {
+  constexpr int HD = 64;
+  using Cfg = AttnCfg<HD>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Cfg::kTileBytes;
+  uint8_t* sV = sK + Cfg::kTileBytes;
+  uint8_t* sP = sQ;  // [2 k-blocks][128 rows][128 B] over the dead Q + K tiles
+  uint8_t* sO = sV;  // [128 rows][128 B] over the dead V tile
+  uint64_t* qk_bar = reinterpret_cast<uint64_t*>(sV + Cfg::kTileBytes);
+  uint64_t* v_bar = qk_bar + 1;
+  uint64_t* s_bar = qk_bar + 2;
+  uint64_t* o_bar = qk_bar + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(qk_bar + 4);
+  float* s_m = reinterpret_cast<float*>(qk_bar + 6);  // [2 halves][128 rows] partial row max (raw score units)
+  float* s_l = s_m + 2 * kAttnBQ;                     // [2 halves][128 rows] partial row sums
+
+  const int tid = threadIdx.x;
+  const uint32_t warp = warp_id(), lane = lane_id();
+  const uint32_t quad = warp & 3u, half = warp >> 2;
+  const int row = static_cast<int>(quad * 32u + lane);  // query row inside the tile == TMEM lane
+  const int head = blockIdx.y, b = blockIdx.z;
+  const int q_row0 = b * p.Sq;
+  const int kv_row0 = b * p.Sk;
+
+  const int kv_len = p.kv_lens ? min(p.kv_lens[b], p.Sk) : p.Sk;
+  int vis_end = kv_len;
+  if (p.causal) vis_end = min(vis_end, row + p.causal_offset + 1);
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    if (tma_out) tma_prefetch_desc(&tmap_o);
+    mbar_init(qk_bar, 1);
+    mbar_init(v_bar, 1);
+    mbar_init(s_bar, 1);
+    mbar_init(o_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t lane_base = (quad * 32u) << 16;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(qk_bar, 2 * Cfg::kTileBytes);
+      tma_load_2d(sQ, &tmap_q, qk_bar, head * HD, q_row0);
+      tma_load_2d(sK, &tmap_k, qk_bar, head * HD, kv_row0);
+      mbar_expect_tx(v_bar, Cfg::kTileBytes);
+      tma_load_2d(sV, &tmap_v, v_bar, head * HD, kv_row0);
+    }
+    __syncwarp();
+    // ---------------- MMA1: S[128q x 128k] = Q K^T (one 64-wide K block) ----------------
+    mbar_wait(qk_bar, 0);
+    tc_fence_after();
+    constexpr uint32_t idesc1 = umma_idesc_f16(kAttnBQ, kAttnBKV);
+    umma_bf16_kblock64_warp(tmem_base, umma_desc_k_sw128(smem_u32(sQ)), umma_desc_k_sw128(smem_u32(sK)), idesc1, 0u, s_bar);
+  }
+  mbar_wait(s_bar, 0);
+  tc_fence_after();
+
+  // ---------------- softmax: this thread owns row `row`, key columns [64*half, 64*half + 64) ----------------
+  const int col0 = static_cast<int>(half) * 64;
+  const int n_vis = max(0, min(64, vis_end - col0));  // visible columns of this half: [0, n_vis)
+  float m_raw = kNegBig;
+#pragma unroll
+  for (int cc = 0; cc < 64; cc += 32) {
+    uint32_t v[32];
+    tmem_ld_32x32b_x32(tmem_base + lane_base + col0 + cc, v);
+    tmem_ld_wait();
+    if (cc + 32 <= n_vis) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) m_raw = fmaxf(m_raw, __uint_as_float(v[i]));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) m_raw = fmaxf(m_raw, (cc + i < n_vis) ? __uint_as_float(v[i]) : kNegBig);
+    }
+  }
+  s_m[half * kAttnBQ + row] = m_raw;
+  asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");  // the two warps of this quadrant
+  m_raw = fmaxf(m_raw, s_m[(half ^ 1u) * kAttnBQ + row]);
+  const float m_s = m_raw * p.scale_log2;  // scale > 0: max of scaled == scaled max
+  float l_half = 0.f;
+  uint8_t* prow = sP + half * (kAttnBQ * 128) + row * 128;
+#pragma unroll
+  for (int cc = 0; cc < 64; cc += 32) {
+    uint32_t v[32];
+    tmem_ld_32x32b_x32(tmem_base + lane_base + col0 + cc, v);
+    tmem_ld_wait();
+    uint32_t packed[16];
+    const bool full = cc + 32 <= n_vis;
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      float e0 = exp2f(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_s));
+      float e1 = exp2f(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -m_s));
+      if (!full) {
+        e0 = (cc + i < n_vis) ? e0 : 0.f;
+        e1 = (cc + i + 1 < n_vis) ? e1 : 0.f;
+      }
+      l_half += e0 + e1;
+      packed[i >> 1] = pack_bf16x2(e0, e1);
+    }
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+      const int ch = ((cc >> 3) + q4) ^ (row & 7);
+      *reinterpret_cast<uint4*>(prow + (ch << 4)) =
+          make_uint4(packed[q4 * 4 + 0], packed[q4 * 4 + 1], packed[q4 * 4 + 2], packed[q4 * 4 + 3]);
+    }
+  }
+  s_l[half * kAttnBQ + row] = l_half;
+  fence_proxy_async_smem();  // st.shared P -> visible to tcgen05.mma (async proxy)
+  tc_fence_before();
+  __syncthreads();           // all S reads done (O aliases S), P complete, partial sums published
+
+  // ---------------- MMA2: O[128q x 64] = P V (8 K=16 steps over the 128 keys) ----------------
+  if (warp == 0) {
+    mbar_wait(v_bar, 0);
+    tc_fence_after();
+    constexpr uint32_t idesc2 = umma_idesc_f16(kAttnBQ, HD, 1, false, true);
+    const uint64_t pa = umma_desc_k_sw128(smem_u32(sP));
+    const uint64_t vb = umma_desc_mn_sw128(smem_u32(sV), 16);
+    // A: +32 B per step inside a k-block, second k-block 16 KB further; B (MN-major): 16 keys = 2 KB per step
+    umma_bf16_x4_warp(tmem_base, pa, vb, 2u, 128u, idesc2, 0u);
+    umma_bf16_x4_warp(tmem_base, pa + ((kAttnBQ * 128) >> 4), vb + 4u * 128u, 2u, 128u, idesc2, 1u);
+    umma_commit_warp(o_bar);
+  }
+  const float l_tot = l_half + s_l[(half ^ 1u) * kAttnBQ + row];
+  const float inv = l_tot > 0.f ? 1.0f / l_tot : 0.f;
+  mbar_wait(o_bar, 0);
+  tc_fence_after();
+
+  // ---------------- normalise + store: this thread owns O columns [32*half, 32*half + 32) of its row ----------------
+  {
+    uint32_t v[32];
+    tmem_ld_32x32b_x32(tmem_base + lane_base + half * 32u, v);
+    tmem_ld_wait();
+    uint4 q[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      q[j].x = pack_bf16x2(__uint_as_float(v[8 * j + 0]) * inv, __uint_as_float(v[8 * j + 1]) * inv);
+      q[j].y = pack_bf16x2(__uint_as_float(v[8 * j + 2]) * inv, __uint_as_float(v[8 * j + 3]) * inv);
+      q[j].z = pack_bf16x2(__uint_as_float(v[8 * j + 4]) * inv, __uint_as_float(v[8 * j + 5]) * inv);
+      q[j].w = pack_bf16x2(__uint_as_float(v[8 * j + 6]) * inv, __uint_as_float(v[8 * j + 7]) * inv);
+    }
+    if (tma_out) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int ch = (static_cast<int>(half) * 4 + j) ^ (row & 7);
+        *reinterpret_cast<uint4*>(sO + row * 128 + (ch << 4)) = q[j];
+      }
+    } else if (row < p.Sq) {
+      __nv_bfloat16* orow = p.out + static_cast<size_t>(q_row0 + row) * p.ldo + head * HD + half * 32;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) reinterpret_cast<uint4*>(orow)[j] = q[j];
+    }
+  }
+  tc_fence_before();
+  if (tma_out) fence_proxy_async_smem();
+  __syncthreads();
+  if (tma_out && tid == 0) {
+    tma_store_2d(&tmap_o, sO, head * HD, q_row0);
+    tma_store_commit();
+    tma_store_wait_read<0>();  // smem must stay valid until the bulk store has read it
+  }
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
 // Single-query decode attention against a KV cache (T5 decoder step): one warp per (batch, head).
 // q: [B, nH*HD]; k/v cache: [B, S_max, nH*HD]; keys [0, kv_len[b]) visible.  CUDA-core, latency-bound by design.
 template <int HD>
@@ -349,7 +541,17 @@ IM_API int im_attn_fwd(const void* q, const void* k, const void* v, void* out, i
   const int bias_bytes = rel_bias_log2 ? (Sq + Sk) * 4 : 0;
   dim3 grid((Sq + kAttnBQ - 1) / kAttnBQ, n_heads, B);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (head_dim == 64) {
+  if (head_dim == 64 && Sk <= kAttnBKV && Sq <= kAttnBQ && rel_bias_log2 == nullptr && scale > 0.f) {
+    // single-chunk fast path; O goes out through TMA when a 128-row box cannot spill into the next sequence
+    const int tma_out = (Sq == kAttnBQ) ? 1 : 0;
+    CUtensorMap to = tq;
+    if (tma_out &&
+        get_tmap_2d(&to, out, static_cast<uint64_t>(B) * Sq, cols, static_cast<uint64_t>(ldo) * 2, kAttnBQ, head_dim, 2, sw))
+      return -1;
+    const int smem = 3 * AttnCfg<64>::kTileBytes + 1024 + 64 + 4 * kAttnBQ * 4;
+    IM_CUDA_OK(cudaFuncSetAttribute(attn_fwd_1chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attn_fwd_1chunk_kernel<<<dim3(1, n_heads, B), kAttn1Threads, smem, s>>>(tq, tk, tv, to, p, tma_out);
+  } else if (head_dim == 64) {
     const int smem = 3 * AttnCfg<64>::kTileBytes + (p.alias_p ? 0 : AttnCfg<64>::kPBytes) + 1024 + 64 + bias_bytes;
     IM_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attn_fwd_kernel<64><<<grid, kAttnThreads, smem, s>>>(tq, tk, tv, p);

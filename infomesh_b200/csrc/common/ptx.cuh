@@ -182,6 +182,33 @@ __device__ __forceinline__ void umma_bf16_kblock64_warp(uint32_t tmem_d, uint64_
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate_first), "r"(smem_u32(commit_bar))
       : "memory");
 }
+// Four bf16 MMAs with register descriptor strides (address-field units of 16 bytes), issued by one elected lane of a
+// converged warp; no commit.  Used where the K steps are not contiguous inside one swizzle atom (P.V in attention).
+__device__ __forceinline__ void umma_bf16_x4_warp(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t a_step,
+                                                  uint32_t b_step, uint32_t idesc, uint32_t accumulate_first) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q, pe;\n"
+      ".reg .b64 sa, sb, a1, a2, a3, b1, b2, b3;\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "setp.eq.b32 q, %6, %6;\n"
+      "cvt.u64.u32 sa, %3;\n"
+      "cvt.u64.u32 sb, %4;\n"
+      "add.s64 a1, %1, sa;\n"
+      "add.s64 b1, %2, sb;\n"
+      "add.s64 a2, a1, sa;\n"
+      "add.s64 b2, b1, sb;\n"
+      "add.s64 a3, a2, sa;\n"
+      "add.s64 b3, b2, sb;\n"
+      "elect.sync _|pe, 0xffffffff;\n"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %5, p;\n"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %5, q;\n"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %5, q;\n"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %5, q;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(a_step), "r"(b_step), "r"(idesc), "r"(accumulate_first)
+      : "memory");
+}
 // tcgen05.commit from one elected lane of a converged warp
 __device__ __forceinline__ void umma_commit_warp(uint64_t* bar) {
   asm volatile(

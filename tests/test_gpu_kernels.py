@@ -74,7 +74,9 @@ def test_topk_merge_dedup_and_order():
     (3, 12, 32, 128, 128, False, False, False, None, True), (2, 12, 32, 384, 384, True, False, False, None, True),
     (2, 8, 64, 256, 256, False, True, False, None, True), (2, 8, 64, 256, 256, True, False, True, 1.0, True),
     (2, 8, 64, 128, 384, True, False, False, None, False), (2, 12, 64, 100, 100, True, False, False, None, True),
-    (1, 12, 32, 40, 40, False, False, False, None, True)])
+    (1, 12, 32, 40, 40, False, False, False, None, True), (5, 12, 64, 128, 128, True, False, False, None, True),
+    (2, 8, 64, 128, 128, False, True, False, None, True), (3, 4, 64, 32, 32, True, False, False, None, True),
+    (2, 8, 64, 64, 128, True, False, False, None, False)])
 def test_attention_matches_reference(B, nH, hd, Sq, Sk, lens, causal, bias, scale, packed):
     from infomesh_b200.ops.attention import attention, attention_ref
 
