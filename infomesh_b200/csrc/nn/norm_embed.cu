@@ -28,19 +28,73 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
-__device__ __forceinline__ void load4(const __nv_bfloat16* p, float (&f)[4]) {
-  const uint2 u = *reinterpret_cast<const uint2*>(p);
-  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+// ---- row access: a warp owns one row of H = VEC * 128 elements.  With VEC even, lane l owns 8 contiguous elements
+// per 256-element chunk (16-byte loads/stores); otherwise 4 per 128-element chunk (8-byte).  x[v] is always 4 floats;
+// in the wide layout x[2c] and x[2c+1] are the two halves of chunk c.
+template <int VEC>
+__device__ __forceinline__ int row_col(int v, int lane) {
+  if constexpr (VEC % 2 == 0) return (v >> 1) * 256 + lane * 8 + (v & 1) * 4;
+  else return v * 128 + lane * 4;
+}
+__device__ __forceinline__ void unpack4(uint32_t lo, uint32_t hi, float (&f)[4]) {
+  const float2 a = unpack_bf16x2(lo), b = unpack_bf16x2(hi);
   f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
 }
-__device__ __forceinline__ void store4(__nv_bfloat16* p, const float (&f)[4]) {
-  uint2 u;
-  u.x = pack_bf16x2(f[0], f[1]);
-  u.y = pack_bf16x2(f[2], f[3]);
-  *reinterpret_cast<uint2*>(p) = u;
+// x (+)= row
+template <int VEC, bool ACC>
+__device__ __forceinline__ void load_row(const __nv_bfloat16* row, int lane, float (&x)[VEC][4]) {
+  if constexpr (VEC % 2 == 0) {
+    uint4 u[VEC / 2];
+#pragma unroll
+    for (int c = 0; c < VEC / 2; ++c) u[c] = *reinterpret_cast<const uint4*>(row + c * 256 + lane * 8);
+#pragma unroll
+    for (int c = 0; c < VEC / 2; ++c) {
+      float f0[4], f1[4];
+      unpack4(u[c].x, u[c].y, f0);
+      unpack4(u[c].z, u[c].w, f1);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        x[2 * c][j] = ACC ? x[2 * c][j] + f0[j] : f0[j];
+        x[2 * c + 1][j] = ACC ? x[2 * c + 1][j] + f1[j] : f1[j];
+      }
+    }
+  } else {
+    uint2 u[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) u[v] = *reinterpret_cast<const uint2*>(row + v * 128 + lane * 4);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      float f[4];
+      unpack4(u[v].x, u[v].y, f);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) x[v][j] = ACC ? x[v][j] + f[j] : f[j];
+    }
+  }
+}
+template <int VEC>
+__device__ __forceinline__ void store_row(__nv_bfloat16* __restrict__ row, int lane, const float (&o)[VEC][4]) {
+  if constexpr (VEC % 2 == 0) {
+#pragma unroll
+    for (int c = 0; c < VEC / 2; ++c) {
+      uint4 u;
+      u.x = pack_bf16x2(o[2 * c][0], o[2 * c][1]);
+      u.y = pack_bf16x2(o[2 * c][2], o[2 * c][3]);
+      u.z = pack_bf16x2(o[2 * c + 1][0], o[2 * c + 1][1]);
+      u.w = pack_bf16x2(o[2 * c + 1][2], o[2 * c + 1][3]);
+      *reinterpret_cast<uint4*>(row + c * 256 + lane * 8) = u;
+    }
+  } else {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      uint2 u;
+      u.x = pack_bf16x2(o[v][0], o[v][1]);
+      u.y = pack_bf16x2(o[v][2], o[v][3]);
+      *reinterpret_cast<uint2*>(row + v * 128 + lane * 4) = u;
+    }
+  }
 }
 
-// H must be a multiple of 128 and <= 1024 (VEC = H / 128 chunks of 4 per lane)
+// H must be a multiple of 128 and <= 1024 (VEC = H / 128 groups of 4 per lane)
 template <int VEC>
 __device__ __forceinline__ void ln_finish(float (&x)[VEC][4], const float* gamma, const float* beta, float eps,
                                           __nv_bfloat16* out_row, int lane, bool rms_only,
@@ -64,20 +118,19 @@ __device__ __forceinline__ void ln_finish(float (&x)[VEC][4], const float* gamma
   const float rstd = rsqrtf(warp_sum(q) * (1.0f / H) + eps);
 #pragma unroll
   for (int v = 0; v < VEC; ++v) {
-    const int col = v * 128 + lane * 4;
-    const float4 g = *reinterpret_cast<const float4*>(gamma + col);
+    const int col = row_col<VEC>(v, lane);
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + col));
     float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (beta != nullptr) b = *reinterpret_cast<const float4*>(beta + col);
-    float o[4];
-    o[0] = (x[v][0] - mean) * rstd * g.x + b.x;
-    o[1] = (x[v][1] - mean) * rstd * g.y + b.y;
-    o[2] = (x[v][2] - mean) * rstd * g.z + b.z;
-    o[3] = (x[v][3] - mean) * rstd * g.w + b.w;
-    if (out_row != nullptr) store4(out_row + col, o);
-    // fused all-gather: the normalised row also lands in every peer's full-sequence buffer (NVLink stores)
-    for (int p = 0; p < n_peer; ++p)
-      if (p != skip_peer) store4(peer_rows[p] + peer_off + col, o);
+    if (beta != nullptr) b = __ldg(reinterpret_cast<const float4*>(beta + col));
+    x[v][0] = (x[v][0] - mean) * rstd * g.x + b.x;
+    x[v][1] = (x[v][1] - mean) * rstd * g.y + b.y;
+    x[v][2] = (x[v][2] - mean) * rstd * g.z + b.z;
+    x[v][3] = (x[v][3] - mean) * rstd * g.w + b.w;
   }
+  if (out_row != nullptr) store_row<VEC>(out_row, lane, x);
+  // fused all-gather: the normalised row also lands in every peer's full-sequence buffer (NVLink stores)
+  for (int p = 0; p < n_peer; ++p)
+    if (p != skip_peer) store_row<VEC>(peer_rows[p] + peer_off, lane, x);
 }
 
 template <int VEC>
@@ -97,27 +150,11 @@ embed_ln_kernel(const int* __restrict__ ids, const int* __restrict__ pos_ids, co
   p = p < 0 ? 0 : (p >= max_pos ? max_pos - 1 : p);
   const int ty = type_ids ? type_ids[row] : 0;
   float x[VEC][4];
-#pragma unroll
-  for (int v = 0; v < VEC; ++v) {
-    const int col = v * 128 + lane * 4;
-    float a[4], b[4];
-    load4(word + static_cast<size_t>(id) * H + col, a);
-    if (pos != nullptr) {
-      load4(pos + static_cast<size_t>(p) * H + col, b);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) a[j] += b[j];
-    }
-    if (type != nullptr) {
-      load4(type + static_cast<size_t>(ty) * H + col, b);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) a[j] += b[j];
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) x[v][j] = a[j];
-  }
+  load_row<VEC, false>(word + static_cast<size_t>(id) * H, lane, x);
+  if (pos != nullptr) load_row<VEC, true>(pos + static_cast<size_t>(p) * H, lane, x);
+  if (type != nullptr) load_row<VEC, true>(type + static_cast<size_t>(ty) * H, lane, x);
   if (gamma == nullptr) {  // plain gather (T5: no embedding LayerNorm)
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) store4(out + static_cast<size_t>(row) * H + v * 128 + lane * 4, x[v]);
+    store_row<VEC>(out + static_cast<size_t>(row) * H, lane, x);
     return;
   }
   ln_finish<VEC>(x, gamma, beta, eps, out + static_cast<size_t>(row) * H, lane, false);
@@ -146,8 +183,9 @@ struct SumLnComm {
 
 template <int VEC>
 __global__ void __launch_bounds__(kRowsPerBlock * 32)
-sum_ln_kernel(const __nv_bfloat16* __restrict__ in, size_t in_stride_p, int P,
-              const __nv_bfloat16* __restrict__ residual, const float* __restrict__ gamma,
+sum_ln_kernel(const __nv_bfloat16* in, size_t in_stride_p, int P,  // in / residual: NOT __restrict__ -- in TP mode peers
+              const __nv_bfloat16* residual,                       // write them while the kernel waits (no ld.global.nc)
+              const float* __restrict__ gamma,
               const float* __restrict__ beta, float eps, int rms_only, int n_rows, __nv_bfloat16* __restrict__ out,
               __nv_bfloat16* __restrict__ sum_out, const SumLnComm cm) {
   constexpr int H = VEC * 128;
@@ -172,32 +210,11 @@ sum_ln_kernel(const __nv_bfloat16* __restrict__ in, size_t in_stride_p, int P,
   }
   if (row < n_rows) {
     float x[VEC][4];
-#pragma unroll
-    for (int v = 0; v < VEC; ++v)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) x[v][j] = 0.f;
-    for (int p = 0; p < P; ++p) {
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        float a[4];
-        load4(in + p * in_stride_p + static_cast<size_t>(row) * H + v * 128 + lane * 4, a);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) x[v][j] += a[j];
-      }
-    }
-    if (residual != nullptr) {
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        float a[4];
-        load4(residual + static_cast<size_t>(row) * H + v * 128 + lane * 4, a);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) x[v][j] += a[j];
-      }
-    }
-    if (sum_out != nullptr) {  // pre-norm architectures keep the un-normalised residual stream
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) store4(sum_out + static_cast<size_t>(row) * H + v * 128 + lane * 4, x[v]);
-    }
+    load_row<VEC, false>(in + static_cast<size_t>(row) * H, lane, x);
+    for (int p = 1; p < P; ++p) load_row<VEC, true>(in + p * in_stride_p + static_cast<size_t>(row) * H, lane, x);
+    if (residual != nullptr) load_row<VEC, true>(residual + static_cast<size_t>(row) * H, lane, x);
+    if (sum_out != nullptr)  // pre-norm architectures keep the un-normalised residual stream
+      store_row<VEC>(sum_out + static_cast<size_t>(row) * H, lane, x);
     if (out != nullptr || cm.peer_out != nullptr) {
       const size_t grow = static_cast<size_t>(cm.out_row_offset) + row;
       ln_finish<VEC>(x, gamma, beta, eps, out != nullptr ? out + static_cast<size_t>(row) * H : nullptr, lane, rms_only != 0,
