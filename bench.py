@@ -118,6 +118,7 @@ def main() -> int:
     ap.add_argument("--pair-seq", type=int, default=128)
     ap.add_argument("--no-rerank", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-varlen", action="store_true", help="run the cross-encoder on padded [pairs, seq_len] batches")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU candidate exchange: fused peer-memory kernels or NCCL all-gathers (baseline)")
     ap.add_argument("--latency-b1", action="store_true", help="also measure batch-1 p50 latency")
@@ -154,7 +155,7 @@ def main() -> int:
     build_s = time.time() - t0
 
     hcfg = HybridConfig(nq=args.batch, pair_seq=args.pair_seq, rerank=not args.no_rerank, backend=args.impl,
-                        use_graph=not args.no_graph, exchange=args.exchange)
+                        use_graph=not args.no_graph, exchange=args.exchange, varlen=not args.no_varlen)
     eng = HybridEngine(shard, hcfg, docs_per_shard=(n_global if world > 1 else n_local))
 
     # ---- query batches on pinned host memory (distinct per step so nothing is cached between iterations) ----
@@ -235,6 +236,14 @@ def main() -> int:
         _, s1 = timed(step_b1, args.warmup, max(args.steps, 10))
         lat_b1 = statistics.median(s1)
 
+    pad_note = "padded [pairs, seq_len] cross-encoder batches"
+    if hcfg.rerank and getattr(eng, "last_pair_lens", None) is not None:
+        mean_len = float(eng.last_pair_lens.float().mean().item())
+        if hcfg.varlen and args.impl == "fused":
+            pad_note = (f"cross-encoder runs unpadded (varlen): pairs are <= {args.pair_seq} tokens, mean "
+                        f"{mean_len:.1f} in this synthetic batch; padding tokens are not computed")
+        else:
+            pad_note += f" (mean real pair length {mean_len:.1f})"
     if rank == 0:
         qps = B * args.steps / (total_ms / 1e3)
         qps_e2e = B * args.steps / (e2e_ms / 1e3)
@@ -259,8 +268,10 @@ def main() -> int:
                 "query_tokens": hcfg.enc_seq, "candidates_per_query": hcfg.n_rerank, "top_k": hcfg.k_out,
                 "rerank": hcfg.rerank,
                 "parallelism": f"doc-sharded index x{world} + data-parallel reranker x{world}",
-                "l2_policy": "inputs larger than L2: every step streams the whole shard "
-                             f"({shard.nbytes() / 1e9:.1f} GB/rank) and uses a distinct query batch",
+                "l2_policy": "inputs larger than L2: every step streams this rank's dense shard "
+                             f"({shard.vectors.numel() * 2 / 1e9:.2f} GB/rank) plus the query terms' postings, and uses "
+                             "a distinct query batch",
+                "padding": pad_note,
                 "cuda_graph": bool(eng._graph is not None),
                 "exchange": ("none" if world == 1 else ("p2p-fused" if eng.heap is not None else "nccl")),
                 "index_build_s": round(build_s, 1),

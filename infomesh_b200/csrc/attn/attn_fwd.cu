@@ -29,6 +29,7 @@ struct AttnParams {
   float scale_log2;       // softmax scale * log2(e)
   const float* rel_bias;  // [nH, Sq + Sk - 1] additive bias indexed by (j - i) + (Sq - 1), or null (already * log2e)
   int alias_p;            // single-chunk, HD == 64: P overwrites the (dead) Q+K tiles -> 48 KB smem, 4 CTAs / SM
+  const int* cu_seqlens;  // [B+1] packed (unpadded) batch: sequence b owns rows [cu[b], cu[b+1]) of q / k / v / out
 };
 
 constexpr int kAttnThreads = 128;
@@ -308,10 +309,12 @@ attn_fwd_1chunk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
   const uint32_t quad = warp & 3u, half = warp >> 2;
   const int row = static_cast<int>(quad * 32u + lane);  // query row inside the tile == TMEM lane
   const int head = blockIdx.y, b = blockIdx.z;
-  const int q_row0 = b * p.Sq;
-  const int kv_row0 = b * p.Sk;
-
-  const int kv_len = p.kv_lens ? min(p.kv_lens[b], p.Sk) : p.Sk;
+  int q_row0 = b * p.Sq, kv_row0 = b * p.Sk, q_len = p.Sq;
+  int kv_len = p.kv_lens ? min(p.kv_lens[b], p.Sk) : p.Sk;
+  if (p.cu_seqlens != nullptr) {  // packed self-attention: the 128-row TMA boxes run into the following sequences,
+    q_row0 = kv_row0 = p.cu_seqlens[b];  // whose keys are masked and whose query rows are never stored
+    q_len = kv_len = min(p.cu_seqlens[b + 1] - q_row0, kAttnBKV);
+  }
   int vis_end = kv_len;
   if (p.causal) vis_end = min(vis_end, row + p.causal_offset + 1);
 
@@ -403,7 +406,15 @@ attn_fwd_1chunk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
     }
   }
   s_l[half * kAttnBQ + row] = l_half;
-  fence_proxy_async_smem();  // st.shared P -> visible to tcgen05.mma (async proxy)
+  if (kv_len < kAttnBKV) {
+    // P is exactly 0 for keys >= kv_len, but 0 * NaN = NaN: the V rows behind a short sequence may be another
+    // sequence's data (finite) or, at the tail of a packed batch, never-written memory.  Zero them in smem.
+    mbar_wait(v_bar, 0);
+    const int n16 = (kAttnBKV - kv_len) * 8;
+    uint4* bad = reinterpret_cast<uint4*>(sV + kv_len * 128);
+    for (int c = tid; c < n16; c += kAttn1Threads) bad[c] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  fence_proxy_async_smem();  // st.shared P (and V fix-up) -> visible to tcgen05.mma (async proxy)
   tc_fence_before();
   __syncthreads();           // all S reads done (O aliases S), P complete, partial sums published
 
@@ -443,7 +454,7 @@ attn_fwd_1chunk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
         const int ch = (static_cast<int>(half) * 4 + j) ^ (row & 7);
         *reinterpret_cast<uint4*>(sO + row * 128 + (ch << 4)) = q[j];
       }
-    } else if (row < p.Sq) {
+    } else if (row < q_len) {
       __nv_bfloat16* orow = p.out + static_cast<size_t>(q_row0 + row) * p.ldo + head * HD + half * 32;
 #pragma unroll
       for (int j = 0; j < 4; ++j) reinterpret_cast<uint4*>(orow)[j] = q[j];
@@ -513,9 +524,11 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bflo
 // q: [B*Sq, ldq] with head h at column h*HD (pass base pointer already offset to the Q block); k, v likewise.
 IM_API int im_attn_fwd(const void* q, const void* k, const void* v, void* out, int B, int n_heads, int head_dim, int Sq,
                        int Sk, int ldq, int ldk, int ldv, int ldo, const int* kv_lens, int causal, int causal_offset,
-                       float scale, const float* rel_bias_log2, void* stream) {
+                       float scale, const float* rel_bias_log2, void* stream, const int* cu_seqlens) {
   using namespace im;
   if (B <= 0 || Sq <= 0 || Sk <= 0) return 0;
+  if (cu_seqlens != nullptr && !(head_dim == 64 && Sq == Sk && Sk <= kAttnBKV && rel_bias_log2 == nullptr && !causal && scale > 0.f))
+    return set_error("im_attn_fwd", "packed (cu_seqlens) attention: head_dim 64, self-attention, max_seqlen <= 128");
   if (head_dim != 64 && head_dim != 32) return set_error("im_attn_fwd", "head_dim must be 32 or 64");
   if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 8)) return set_error("im_attn_fwd", "row pitches must be multiples of 8");
   const TmapSwizzle sw = head_dim == 64 ? TMAP_SW_128 : TMAP_SW_64;
@@ -538,12 +551,13 @@ IM_API int im_attn_fwd(const void* q, const void* k, const void* v, void* out, i
   p.scale_log2 = scale * 1.4426950408889634f;
   p.rel_bias = rel_bias_log2;
   p.alias_p = (head_dim == 64 && Sk <= kAttnBKV) ? 1 : 0;
+  p.cu_seqlens = cu_seqlens;
   const int bias_bytes = rel_bias_log2 ? (Sq + Sk) * 4 : 0;
   dim3 grid((Sq + kAttnBQ - 1) / kAttnBQ, n_heads, B);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (head_dim == 64 && Sk <= kAttnBKV && Sq <= kAttnBQ && rel_bias_log2 == nullptr && scale > 0.f) {
     // single-chunk fast path; O goes out through TMA when a 128-row box cannot spill into the next sequence
-    const int tma_out = (Sq == kAttnBQ) ? 1 : 0;
+    const int tma_out = (Sq == kAttnBQ && cu_seqlens == nullptr) ? 1 : 0;
     CUtensorMap to = tq;
     if (tma_out &&
         get_tmap_2d(&to, out, static_cast<uint64_t>(B) * Sq, cols, static_cast<uint64_t>(ldo) * 2, kAttnBQ, head_dim, 2, sw))

@@ -38,6 +38,8 @@ struct GemmEpilogue {
   uint32_t* a_state;        // {use, done}: block m is loadable once a_ready[m] >= (use + 1) * rows_in_block(m);
                             // the last CTA out advances `use` (see comm/symm.cu for the protocol)
   int m_rotate;             // first row block processed (so the local shard goes first)
+  const int* m_dev;         // optional device-side row count (unpadded / varlen batches inside a CUDA graph): rows
+                            // beyond min(M, *m_dev) are neither loaded nor computed
 };
 
 struct PeerMaps {
@@ -103,6 +105,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   const uint32_t warp = warp_id();
   const uint32_t lane = lane_id();
+  if (ep.m_dev != nullptr) M = min(M, max(0, *ep.m_dev));
   const int num_m = (M + kBM - 1) / kBM;
   const int num_n = (N + BN - 1) / BN;
   const int num_k = (K + kBK - 1) / kBK;
@@ -440,7 +443,7 @@ IM_API int im_gemm_bf16_tn(const void* A, const void* B, void* C, const float* b
                            int K, int lda, int ldb, int ldc, int ldr, int act, int out_fp32, float alpha, int bn,
                            void* const* peer_c, uint32_t* const* peer_flags, int rank, int rows_per_rank,
                            const uint32_t* a_ready, uint32_t* a_state, int m_rotate, int max_ctas, void* stream,
-                           const void* const* peer_c_host, int world) {
+                           const void* const* peer_c_host, int world, const int* m_dev) {
   using namespace im;
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if ((lda % 8) || (ldb % 8) || (ldc % 8) || (residual != nullptr && (ldr % 8))) return set_error("im_gemm_bf16_tn", "leading dims must be multiples of 8");
@@ -470,6 +473,7 @@ IM_API int im_gemm_bf16_tn(const void* A, const void* B, void* C, const float* b
   ep.a_state = a_state;
   const int num_m = (M + kBM - 1) / kBM;
   ep.m_rotate = num_m > 0 ? ((m_rotate % num_m) + num_m) % num_m : 0;
+  ep.m_dev = m_dev;
   // coalesced TMA-store epilogue for plain local bf16 outputs
   CUtensorMap tc = ta, tr = ta;
   PeerMaps tp;

@@ -139,11 +139,11 @@ embed_ln_kernel(const int* __restrict__ ids, const int* __restrict__ pos_ids, co
                 const __nv_bfloat16* __restrict__ word, const __nv_bfloat16* __restrict__ pos,
                 const __nv_bfloat16* __restrict__ type, const float* __restrict__ gamma, const float* __restrict__ beta,
                 float eps, int n_tokens, int seq_len, int pos_offset, int vocab, int max_pos,
-                __nv_bfloat16* __restrict__ out) {
+                __nv_bfloat16* __restrict__ out, const int* __restrict__ n_rows_dev) {
   constexpr int H = VEC * 128;
   const int row = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (row >= n_tokens) return;
+  if (row >= n_tokens || (n_rows_dev != nullptr && row >= *n_rows_dev)) return;
   int id = ids[row];
   id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
   int p = pos_ids ? pos_ids[row] : (row % seq_len) + pos_offset;
@@ -179,6 +179,7 @@ struct SumLnComm {
   int out_row_offset;
   int world;
   int rank;
+  const int* n_rows_dev;  // optional device-side row count (unpadded batches): rows >= *n_rows_dev are skipped
 };
 
 template <int VEC>
@@ -208,6 +209,7 @@ sum_ln_kernel(const __nv_bfloat16* in, size_t in_stride_p, int P,  // in / resid
     }
     __syncthreads();
   }
+  if (cm.n_rows_dev != nullptr) n_rows = min(n_rows, *cm.n_rows_dev);
   if (row < n_rows) {
     float x[VEC][4];
     load_row<VEC, false>(in + static_cast<size_t>(row) * H, lane, x);
@@ -356,6 +358,46 @@ row_argmax_kernel(const float* __restrict__ x, int n_cols, int ld, int id_offset
   }
 }
 
+// Unpadded ("varlen") batches: sequence p of a padded [n, S] id matrix owns rows [cu[p], cu[p+1]) of the packed
+// token stream.  One block per sequence; every block recomputes its own prefix (n is a few thousand at most), so the
+// whole pack is ONE launch: cu_seqlens, the total row count (device scalar consumed by the GEMM / LN kernels), the
+// packed ids and the per-row position ids.
+__global__ void __launch_bounds__(128)
+seq_pack_kernel(const int* __restrict__ ids, const int* __restrict__ lens, int n, int S, int pos_offset,
+                int* __restrict__ cu, int* __restrict__ total, int* __restrict__ packed_ids,
+                int* __restrict__ packed_pos) {
+  __shared__ int red[4];
+  const int p = blockIdx.x;
+  int part = 0;
+  for (int i = threadIdx.x; i < p; i += blockDim.x) part += max(0, min(lens[i], S));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+  __syncthreads();
+  const int start = red[0] + red[1] + red[2] + red[3];
+  const int len = max(0, min(lens[p], S));
+  if (threadIdx.x == 0) {
+    cu[p] = start;
+    if (p == n - 1) {
+      cu[n] = start + len;
+      *total = start + len;
+    }
+  }
+  for (int t = threadIdx.x; t < len; t += blockDim.x) {
+    packed_ids[start + t] = ids[static_cast<size_t>(p) * S + t];
+    packed_pos[start + t] = t + pos_offset;
+  }
+}
+
+// out[b, :] = in[idx[b], :]  (bf16 rows of H elements, H % 8 == 0): CLS rows of a packed batch
+__global__ void __launch_bounds__(128)
+gather_rows_kernel(const __nv_bfloat16* __restrict__ in, const int* __restrict__ idx, int H, int ld_in,
+                   __nv_bfloat16* __restrict__ out) {
+  const uint4* src = reinterpret_cast<const uint4*>(in + static_cast<size_t>(idx[blockIdx.x]) * ld_in);
+  uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(blockIdx.x) * H);
+  for (int c = threadIdx.x; c < H / 8; c += blockDim.x) dst[c] = src[c];
+}
+
 }  // namespace im
 
 #define IM_DISPATCH_VEC(H, CALL)                    \
@@ -371,7 +413,7 @@ row_argmax_kernel(const float* __restrict__ x, int n_cols, int ld, int id_offset
 
 IM_API int im_embed_ln(const int* ids, const int* pos_ids, const int* type_ids, const void* word, const void* pos,
                        const void* type, const float* gamma, const float* beta, float eps, int n_tokens, int seq_len,
-                       int pos_offset, int vocab, int max_pos, int H, void* out, void* stream) {
+                       int pos_offset, int vocab, int max_pos, int H, void* out, void* stream, const int* n_rows_dev) {
   using namespace im;
   if (n_tokens <= 0) return 0;
   if (H % 128) return set_error("im_embed_ln", "H must be a multiple of 128");
@@ -380,7 +422,7 @@ IM_API int im_embed_ln(const int* ids, const int* pos_ids, const int* type_ids, 
   IM_DISPATCH_VEC(H, (embed_ln_kernel<VEC><<<grid, kRowsPerBlock * 32, 0, s>>>(
                          ids, pos_ids, type_ids, (const __nv_bfloat16*)word, (const __nv_bfloat16*)pos,
                          (const __nv_bfloat16*)type, gamma, beta, eps, n_tokens, seq_len, pos_offset, vocab, max_pos,
-                         (__nv_bfloat16*)out)));
+                         (__nv_bfloat16*)out, n_rows_dev)));
   IM_LAUNCH_OK("embed_ln_kernel");
   return 0;
 }
@@ -389,7 +431,7 @@ IM_API int im_sum_ln(const void* in, long long in_stride_p, int P, const void* r
                      const float* beta, float eps, int rms_only, int n_rows, int H, void* out, void* sum_out,
                      const uint32_t* arrive_flags, uint32_t* arrive_state, unsigned arrivals_per_block, int blocks_per_src,
                      void* const* peer_out, uint32_t* const* peer_out_flags, int out_row_offset, int world, int rank,
-                     void* stream) {
+                     void* stream, const int* n_rows_dev) {
   using namespace im;
   if (n_rows <= 0) return 0;
   if (H % 128) return set_error("im_sum_ln", "H must be a multiple of 128");
@@ -404,6 +446,7 @@ IM_API int im_sum_ln(const void* in, long long in_stride_p, int P, const void* r
   cm.out_row_offset = out_row_offset;
   cm.world = world;
   cm.rank = rank;
+  cm.n_rows_dev = n_rows_dev;
   const int grid = (n_rows + kRowsPerBlock - 1) / kRowsPerBlock;
   auto s = reinterpret_cast<cudaStream_t>(stream);
   IM_DISPATCH_VEC(H, (sum_ln_kernel<VEC><<<grid, kRowsPerBlock * 32, 0, s>>>(
@@ -441,5 +484,25 @@ IM_API int im_row_argmax(const float* x, int n_rows, int n_cols, int ld, int id_
   row_argmax_kernel<<<n_rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, n_cols, ld, id_offset, out_val,
                                                                                out_idx);
   IM_LAUNCH_OK("row_argmax_kernel");
+  return 0;
+}
+
+IM_API int im_seq_pack(const int* ids, const int* lens, int n, int S, int pos_offset, int* cu, int* total,
+                       int* packed_ids, int* packed_pos, void* stream) {
+  using namespace im;
+  if (n <= 0) return 0;
+  seq_pack_kernel<<<n, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(ids, lens, n, S, pos_offset, cu, total,
+                                                                         packed_ids, packed_pos);
+  IM_LAUNCH_OK("seq_pack_kernel");
+  return 0;
+}
+
+IM_API int im_gather_rows(const void* in, const int* idx, int n, int H, int ld_in, void* out, void* stream) {
+  using namespace im;
+  if (n <= 0) return 0;
+  if (H % 8 || ld_in % 8) return set_error("im_gather_rows", "H and the row pitch must be multiples of 8");
+  gather_rows_kernel<<<n, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>((const __nv_bfloat16*)in, idx, H, ld_in,
+                                                                            (__nv_bfloat16*)out);
+  IM_LAUNCH_OK("gather_rows_kernel");
   return 0;
 }

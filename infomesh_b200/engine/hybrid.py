@@ -33,6 +33,7 @@ class HybridConfig:
     k_fetch: int = 20         # candidates per source (reference fetches limit*2, query.py:124)
     n_rerank: int = 20        # reference reranks <= 20 candidates (reranker.py:20)
     k_out: int = 10
+    varlen: bool = True       # cross-encoder runs on the unpadded token stream (padding never reaches a kernel)
     pair_seq: int = 128       # <s> q </s></s> passage </s>
     rerank: bool = True
     backend: str = "fused"    # "fused" | "torch"
@@ -146,8 +147,11 @@ class HybridEngine:
         pair_ids, pair_lens = F.build_pairs(self.in_q_tok[q0:q0 + self.nq_local].contiguous(),
                                             self.in_q_len[q0:q0 + self.nq_local].contiguous(), my_c, self.tok_ptrs,
                                             self.len_ptrs, self.docs_per_shard, self.passage_len, cfg.pair_seq)
+        self.last_pair_lens = pair_lens          # (graph-static buffer) token count of every reranked pair
         if cfg.backend == "torch":
             logits = self.reranker.score_torch(pair_ids, pair_lens)
+        elif cfg.varlen and pair_ids.shape[1] <= 128 and self.reranker.cfg.head_dim == 64:
+            logits = self.reranker.score_packed(pair_ids, pair_lens)
         else:
             logits = self.reranker.score(pair_ids, pair_lens)
         if self.heap is not None:

@@ -150,6 +150,46 @@ class BertModel:
             x = N.layernorm(y2, lay["ln2_g"], lay["ln2_b"], cfg.eps)
         return x.view(B, S, H)
 
+    def hidden_states_packed(self, ids: torch.Tensor, lengths: torch.Tensor):
+        """Unpadded forward: ids int32 [B, S<=128] + lengths [B] -> (hidden bf16 [B*S, H] of which the first
+        ``total`` rows are the packed tokens, cu_seqlens int32 [B+1], total int32 [1]).
+
+        Padding tokens are never embedded, multiplied or normalised: every GEMM / LayerNorm reads the token count
+        from a device scalar, and attention walks ``cu_seqlens``.  Shapes stay static, so the whole forward still
+        captures into one CUDA graph even though the amount of work follows the batch."""
+        from infomesh_b200.ops import attention as A
+        from infomesh_b200.ops import gemm as G
+        from infomesh_b200.ops import nn as N
+
+        cfg, w = self.cfg, self.w
+        B, S = ids.shape
+        H = cfg.hidden
+        assert S <= 128 and cfg.head_dim == 64, "packed path: max_seqlen <= 128, head_dim 64"
+        pk_ids, pk_pos, cu, total = N.seq_pack(ids.contiguous(), lengths, cfg.pos_offset)
+        x = N.embed_ln(pk_ids, w.word, w.pos, w.type, w.emb_g, w.emb_b, cfg.eps, S, pos_ids=pk_pos, n_rows_dev=total)
+        for lay in w.layers:
+            qkv = G.linear(x, lay["wqkv"], lay["bqkv"], m_dev=total)
+            q3 = qkv.view(B, S, 3 * H)
+            ctx = A.attention(q3[..., :H], q3[..., H:2 * H], q3[..., 2 * H:], cfg.heads, cu_seqlens=cu)
+            y = G.linear(ctx.view(B * S, H), lay["wo"], lay["bo"], residual=x, m_dev=total)
+            x1 = N.layernorm(y, lay["ln1_g"], lay["ln1_b"], cfg.eps, n_rows_dev=total)
+            h = G.linear(x1, lay["w1"], lay["b1"], act="gelu", m_dev=total)
+            y2 = G.linear(h, lay["w2"], lay["b2"], residual=x1, m_dev=total)
+            x = N.layernorm(y2, lay["ln2_g"], lay["ln2_b"], cfg.eps, n_rows_dev=total)
+        return x, cu, total
+
+    def score_packed(self, ids, lengths) -> torch.Tensor:
+        """Cross-encoder logits fp32 [B], computed on the unpadded token stream (see :meth:`hidden_states_packed`)."""
+        from infomesh_b200.ops import gemm as G
+        from infomesh_b200.ops import nn as N
+
+        assert self.cfg.classifier
+        w = self.w
+        x, cu, _ = self.hidden_states_packed(ids, lengths)
+        cls = N.gather_rows(x, cu, ids.shape[0])          # <s> is the first token of every sequence
+        hcls = G.linear(cls, w.cls_w1, w.cls_b1, act="tanh")
+        return G.linear(hcls, w.cls_w2p, w.cls_b2p, out_dtype=torch.float32)[:, 0].contiguous()
+
     def embed(self, ids, lengths=None) -> torch.Tensor:
         """Sentence embeddings, L2-normalised bf16 [B, H]."""
         from infomesh_b200.ops import nn as N

@@ -43,8 +43,12 @@ def attention_ref(q, k, v, n_heads, kv_lens=None, causal=False, causal_offset=0,
     return o.transpose(1, 2).reshape(B, Sq, HH)
 
 
-def attention(q, k, v, n_heads, kv_lens=None, causal=False, causal_offset=0, scale=None, rel_bias=None, out=None):
-    """Fused attention.  ``q``: [B, Sq, nH*hd] view (may be a column slice of a packed QKV buffer)."""
+def attention(q, k, v, n_heads, kv_lens=None, causal=False, causal_offset=0, scale=None, rel_bias=None, out=None,
+              cu_seqlens=None):
+    """Fused attention.  ``q``: [B, Sq, nH*hd] view (may be a column slice of a packed QKV buffer).
+
+    ``cu_seqlens`` (int32 ``[B+1]``): the buffers hold an UNPADDED batch -- sequence b owns rows
+    ``[cu[b], cu[b+1])`` of the flattened ``[B*Sq, .]`` storage (``Sq`` = max sequence length <= 128)."""
     assert q.is_cuda and q.dtype == torch.bfloat16 and k.dtype == torch.bfloat16 and v.dtype == torch.bfloat16
     B, Sq, HH = q.shape
     Sk = k.shape[1]
@@ -67,7 +71,7 @@ def attention(q, k, v, n_heads, kv_lens=None, causal=False, causal_offset=0, sca
                        ctypes.c_int(q.stride(1)), ctypes.c_int(k.stride(1)), ctypes.c_int(v.stride(1)),
                        ctypes.c_int(out.stride(1)), _native.ptr(kv_lens), ctypes.c_int(1 if causal else 0),
                        ctypes.c_int(causal_offset), ctypes.c_float(scale), _native.ptr(bias_dev),
-                       _native.stream_ptr())
+                       _native.stream_ptr(), _native.ptr(cu_seqlens))
     _native.check(rc, "im_attn_fwd")
     _native.count_launch()
     return out

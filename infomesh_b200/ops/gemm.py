@@ -33,8 +33,11 @@ def linear_ref(a, w, bias=None, residual=None, act=None, alpha=1.0):
 
 
 def linear(a, w, bias=None, residual=None, act=None, alpha=1.0, out=None, out_dtype=torch.bfloat16, bn=0,
-           max_ctas=0, rs=None, ag=None):
+           max_ctas=0, rs=None, ag=None, m_dev=None):
     """``a[M,K] @ w[N,K]^T`` with fused bias / activation / residual on the tcgen05 kernel.
+
+    ``m_dev``: optional int32 device scalar with the number of valid rows (<= M) -- the kernel reads it at run time,
+    so unpadded batches whose token count changes per step still replay from one CUDA graph.
 
     Tensor-parallel hooks (``parallel.tp``): ``rs`` = :class:`ReduceScatterChannel` — the epilogue pushes every
     128-row block of the partial product into the owning rank's receive slot over NVLink instead of storing locally;
@@ -68,7 +71,8 @@ def linear(a, w, bias=None, residual=None, act=None, alpha=1.0, out=None, out_dt
         ctypes.c_int(rs.rank if rs else 0), ctypes.c_int(rs.rows_per_rank if rs else 0),
         ctypes.c_void_p(ag.flags_ptr if ag else 0), ctypes.c_void_p(ag.state_ptr if ag else 0),
         ctypes.c_int(ag.m_rotate if ag else 0), ctypes.c_int(max_ctas), _native.stream_ptr(),
-        rs.peer_c_host if rs else ctypes.c_void_p(0), ctypes.c_int(rs.world if rs else 0))
+        rs.peer_c_host if rs else ctypes.c_void_p(0), ctypes.c_int(rs.world if rs else 0),
+        _native.ptr(m_dev))
     _native.check(rc, "im_gemm_bf16_tn")
     _native.count_launch()
     return out

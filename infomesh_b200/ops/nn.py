@@ -44,7 +44,8 @@ def pool_norm_ref(h, lengths, mode="cls", normalize=True):
 
 
 # ----------------------------------------------------------------------------- kernels
-def embed_ln(ids, word, pos, type_emb, gamma, beta, eps, seq_len, pos_ids=None, type_ids=None, pos_offset=0, out=None):
+def embed_ln(ids, word, pos, type_emb, gamma, beta, eps, seq_len, pos_ids=None, type_ids=None, pos_offset=0, out=None,
+             n_rows_dev=None):
     n = ids.numel()
     H = word.shape[1]
     assert ids.dtype == torch.int32 and word.dtype == torch.bfloat16
@@ -55,14 +56,14 @@ def embed_ln(ids, word, pos, type_emb, gamma, beta, eps, seq_len, pos_ids=None, 
                        _native.ptr(pos), _native.ptr(type_emb), _native.ptr(gamma), _native.ptr(beta),
                        ctypes.c_float(eps), ctypes.c_int(n), ctypes.c_int(seq_len), ctypes.c_int(pos_offset),
                        ctypes.c_int(word.shape[0]), ctypes.c_int(pos.shape[0] if pos is not None else 1),
-                       ctypes.c_int(H), _native.ptr(out), _native.stream_ptr())
+                       ctypes.c_int(H), _native.ptr(out), _native.stream_ptr(), _native.ptr(n_rows_dev))
     _native.check(rc, "im_embed_ln")
     _native.count_launch()
     return out
 
 
 def layernorm(x, gamma, beta=None, eps=1e-12, residual=None, rms_only=False, out=None, sum_out=None, partials=1,
-              partial_stride=0, want_norm=True, rs=None, ag_push=None):
+              partial_stride=0, want_norm=True, rs=None, ag_push=None, n_rows_dev=None):
     """``out = LN(sum_p x[p] + residual)``; ``x``: [n, H] (or [P, n, H] with ``partials=P``).
 
     ``rs``: consume a fused reduce-scatter (wait on the arrival counters of ``rs`` before summing its receive
@@ -83,8 +84,42 @@ def layernorm(x, gamma, beta=None, eps=1e-12, residual=None, rms_only=False, out
                      ctypes.c_void_p(ag_push.peer_buf_ptr if ag_push else 0),
                      ctypes.c_void_p(ag_push.peer_flags_ptr if ag_push else 0),
                      ctypes.c_int(ag_push.row_offset if ag_push else 0), ctypes.c_int(ag_push.world if ag_push else 0),
-                     ctypes.c_int(ag_push.rank if ag_push else 0), _native.stream_ptr())
+                     ctypes.c_int(ag_push.rank if ag_push else 0), _native.stream_ptr(), _native.ptr(n_rows_dev))
     _native.check(rc, "im_sum_ln")
+    _native.count_launch()
+    return out
+
+
+def seq_pack(ids, lens, pos_offset=0):
+    """Padded ``ids[n, S]`` + ``lens[n]`` -> ``(packed_ids[n*S], packed_pos[n*S], cu_seqlens[n+1], total[1])``.
+
+    Only the first ``total`` rows of the packed arrays are meaningful; ``total`` stays on the device (the GEMM / LN
+    kernels read it at run time), so the unpadded forward replays from a CUDA graph whatever the batch's lengths."""
+    n, S = ids.shape
+    assert ids.dtype == torch.int32 and lens.dtype == torch.int32 and ids.is_contiguous()
+    dev = ids.device
+    packed_ids = torch.zeros((n * S,), device=dev, dtype=torch.int32)
+    packed_pos = torch.zeros((n * S,), device=dev, dtype=torch.int32)
+    cu = torch.empty((n + 1,), device=dev, dtype=torch.int32)
+    total = torch.empty((1,), device=dev, dtype=torch.int32)
+    L = _native.require()
+    rc = L.im_seq_pack(_native.ptr(ids), _native.ptr(lens), ctypes.c_int(n), ctypes.c_int(S), ctypes.c_int(pos_offset),
+                       _native.ptr(cu), _native.ptr(total), _native.ptr(packed_ids), _native.ptr(packed_pos),
+                       _native.stream_ptr())
+    _native.check(rc, "im_seq_pack")
+    _native.count_launch()
+    return packed_ids, packed_pos, cu, total
+
+
+def gather_rows(x, idx, n):
+    """``out[b] = x[idx[b]]`` for the first ``n`` entries of the int32 index vector (bf16 rows)."""
+    assert x.dtype == torch.bfloat16 and x.stride(1) == 1 and idx.dtype == torch.int32
+    H = x.shape[1]
+    out = torch.empty((n, H), device=x.device, dtype=torch.bfloat16)
+    L = _native.require()
+    rc = L.im_gather_rows(_native.ptr(x), _native.ptr(idx), ctypes.c_int(n), ctypes.c_int(H), ctypes.c_int(x.stride(0)),
+                          _native.ptr(out), _native.stream_ptr())
+    _native.check(rc, "im_gather_rows")
     _native.count_launch()
     return out
 

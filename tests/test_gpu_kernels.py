@@ -382,3 +382,30 @@ def test_tensor_parallel_encoder_world1_matches_plain_model():
         assert (got - want).abs().max().item() < 0.03
     torch.cuda.synchronize()
     tpm.heap.close()
+
+
+def test_packed_cross_encoder_matches_padded():
+    """Unpadded (varlen) forward == padded forward on the valid tokens: logits agree, pad rows never computed."""
+    from dataclasses import replace
+
+    from infomesh_b200.models.bert import BGE_RERANKER_BASE, BertModel
+
+    cfg = replace(BGE_RERANKER_BASE, layers=3)
+    m = BertModel(cfg, device=DEV, seed=5)
+    B, S = 37, 128
+    g = torch.Generator(device="cpu").manual_seed(3)
+    ids = torch.randint(5, 5000, (B, S), generator=g, dtype=torch.int32).to(DEV)
+    lens = torch.randint(1, S + 1, (B,), generator=g, dtype=torch.int32).to(DEV)
+    lens[0], lens[-1] = S, 1
+    a = m.score(ids, lens)
+    b = m.score_packed(ids, lens)
+    assert torch.isfinite(b).all()
+    assert (a - b).abs().max().item() < 0.03
+    # garbage (even NaN) behind the packed rows must not leak into valid outputs
+    x, cu, total = m.hidden_states_packed(ids, lens)
+    assert int(total.item()) == int(lens.sum().item()) and cu[-1].item() == total.item()
+    ref = m.hidden_states(ids, lens)
+    for bi in (0, 5, B - 1):
+        n = int(lens[bi].item())
+        s0 = int(cu[bi].item())
+        assert (x[s0:s0 + n].float() - ref[bi, :n].float()).abs().max().item() < 0.12
