@@ -119,6 +119,7 @@ def main() -> int:
     ap.add_argument("--no-rerank", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-varlen", action="store_true", help="run the cross-encoder on padded [pairs, seq_len] batches")
+    ap.add_argument("--no-padded-arm", action="store_true", help="skip the extra padded-cross-encoder measurement")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU candidate exchange: fused peer-memory kernels or NCCL all-gathers (baseline)")
     ap.add_argument("--latency-b1", action="store_true", help="also measure batch-1 p50 latency")
@@ -221,6 +222,25 @@ def main() -> int:
     # sanity: results are real document ids
     ids_ok = bool((out_i_host[:, 0] >= 0).float().mean() > 0.5)
 
+    # ---- (c) the same pipeline with the cross-encoder forced onto padded [pairs, seq_len] batches, for transparency:
+    #          `value` is the product (unpadded); this is what the step costs when every pair is computed at seq_len
+    padded = None
+    if hcfg.rerank and hcfg.varlen and args.impl == "fused" and not args.no_padded_arm:
+        from dataclasses import replace as _replace
+
+        eng_p = HybridEngine(shard, _replace(hcfg, varlen=False), encoder=eng.encoder, reranker=eng.reranker,
+                             docs_per_shard=(n_global if world > 1 else n_local))
+
+        def step_pad(i):
+            eng_p.load_inputs(*dev_batches[i % n_batches])
+            eng_p.run()
+
+        pad_ms, _ = timed(step_pad, args.warmup, args.steps)
+        padded = {"value": round(B * args.steps / (pad_ms / 1e3), 2), "unit": "queries/s",
+                  "ms_per_step": round(pad_ms / args.steps, 4),
+                  "note": f"cross-encoder on padded [{B * hcfg.n_rerank // world} x {args.pair_seq}] batches per rank"}
+        del eng_p
+
     lat_b1 = None
     if args.latency_b1:
         cfg1 = HybridConfig(nq=world, pair_seq=args.pair_seq, rerank=not args.no_rerank, backend=args.impl,
@@ -284,11 +304,14 @@ def main() -> int:
             "clocks": clocks,
             "results_valid": ids_ok,
         }
+        if padded is not None:
+            result["padded_cross_encoder"] = padded
         if lat_b1 is not None:
             result["latency_batch1_p50_ms"] = round(lat_b1, 4)
         print(json.dumps(result), flush=True)
     # graphs hold references to the NCCL communicator: drop them before tearing the group down
     eng._graph = None
+    eng_p = None
     if lat_b1 is not None:
         eng1._graph = None
     D.shutdown()
