@@ -79,6 +79,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const int tid = threadIdx.x;
   const uint32_t warp = warp_id();
   const int qb = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
+  pdl_trigger();
+  pdl_wait();  // (kv_lens / rel_bias are read right below: no prologue to overlap in this kernel, only launch latency)
   const int q_row0 = b * p.Sq + qb * kAttnBQ;  // first query row of this tile in the q buffer
   const int kv_row0 = b * p.Sk;
   const int q_idx = qb * kAttnBQ + tid;        // position of this thread's query within its sequence
@@ -309,14 +311,7 @@ attn_fwd_1chunk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
   const uint32_t quad = warp & 3u, half = warp >> 2;
   const int row = static_cast<int>(quad * 32u + lane);  // query row inside the tile == TMEM lane
   const int head = blockIdx.y, b = blockIdx.z;
-  int q_row0 = b * p.Sq, kv_row0 = b * p.Sk, q_len = p.Sq;
-  int kv_len = p.kv_lens ? min(p.kv_lens[b], p.Sk) : p.Sk;
-  if (p.cu_seqlens != nullptr) {  // packed self-attention: the 128-row TMA boxes run into the following sequences,
-    q_row0 = kv_row0 = p.cu_seqlens[b];  // whose keys are masked and whose query rows are never stored
-    q_len = kv_len = min(p.cu_seqlens[b + 1] - q_row0, kAttnBKV);
-  }
-  int vis_end = kv_len;
-  if (p.causal) vis_end = min(vis_end, row + p.causal_offset + 1);
+  pdl_trigger();
 
   if (tid == 0) {
     tma_prefetch_desc(&tmap_q);
@@ -338,6 +333,16 @@ attn_fwd_1chunk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t lane_base = (quad * 32u) << 16;
+
+  pdl_wait();  // prologue above overlapped the producer GEMM's tail; q/k/v, kv_lens and cu_seqlens are its outputs
+  int q_row0 = b * p.Sq, kv_row0 = b * p.Sk, q_len = p.Sq;
+  int kv_len = p.kv_lens ? min(p.kv_lens[b], p.Sk) : p.Sk;
+  if (p.cu_seqlens != nullptr) {  // packed self-attention: the 128-row TMA boxes run into the following sequences,
+    q_row0 = kv_row0 = p.cu_seqlens[b];  // whose keys are masked and whose query rows are never stored
+    q_len = kv_len = min(p.cu_seqlens[b + 1] - q_row0, kAttnBKV);
+  }
+  int vis_end = kv_len;
+  if (p.causal) vis_end = min(vis_end, row + p.causal_offset + 1);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -564,15 +569,15 @@ IM_API int im_attn_fwd(const void* q, const void* k, const void* v, void* out, i
       return -1;
     const int smem = 3 * AttnCfg<64>::kTileBytes + 1024 + 64 + 4 * kAttnBQ * 4;
     IM_CUDA_OK(cudaFuncSetAttribute(attn_fwd_1chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attn_fwd_1chunk_kernel<<<dim3(1, n_heads, B), kAttn1Threads, smem, s>>>(tq, tk, tv, to, p, tma_out);
+    IM_CUDA_OK(launch_pdl(attn_fwd_1chunk_kernel, dim3(1, n_heads, B), dim3(kAttn1Threads), smem, s, tq, tk, tv, to, p, tma_out));
   } else if (head_dim == 64) {
     const int smem = 3 * AttnCfg<64>::kTileBytes + (p.alias_p ? 0 : AttnCfg<64>::kPBytes) + 1024 + 64 + bias_bytes;
     IM_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attn_fwd_kernel<64><<<grid, kAttnThreads, smem, s>>>(tq, tk, tv, p);
+    IM_CUDA_OK(launch_pdl(attn_fwd_kernel<64>, grid, dim3(kAttnThreads), smem, s, tq, tk, tv, p));
   } else {
     const int smem = 3 * AttnCfg<32>::kTileBytes + AttnCfg<32>::kPBytes + 1024 + 64 + bias_bytes;
     IM_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attn_fwd_kernel<32><<<grid, kAttnThreads, smem, s>>>(tq, tk, tv, p);
+    IM_CUDA_OK(launch_pdl(attn_fwd_kernel<32>, grid, dim3(kAttnThreads), smem, s, tq, tk, tv, p));
   }
   IM_LAUNCH_OK("attn_fwd_kernel");
   return 0;

@@ -1,5 +1,7 @@
 #include "host.h"
 
+#include <stdlib.h>
+
 #include <mutex>
 
 namespace im {
@@ -61,7 +63,18 @@ int sm_count() {
   return n;
 }
 
+static int g_pdl = -1;
+bool pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("INFOMESH_B200_PDL");
+    g_pdl = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return g_pdl != 0;
+}
+
 }  // namespace im
+
+IM_API void im_set_pdl(int on) { im::g_pdl = on ? 1 : 0; }
 
 IM_API const char* im_last_error() { return im::last_error_buf(); }
 IM_API int im_sm_count() { return im::sm_count(); }

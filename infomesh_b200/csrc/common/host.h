@@ -42,4 +42,26 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
 
 int sm_count();
 
+// Programmatic dependent launch (PDL): the kernel may start while its stream predecessor is still draining; it runs
+// its prologue (barrier init, TMEM alloc, descriptor prefetch) and blocks at pdl_wait() (ptx.cuh) until the predecessor
+// has completed and flushed.  Captured into CUDA graphs as programmatic dependency edges.  INFOMESH_B200_PDL=0
+// turns it off (plain stream-ordered launches).
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<Args&&>(args)...);
+}
+
 }  // namespace im

@@ -72,6 +72,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // ---------------------------------------------------------------------------------
+// Programmatic dependent launch: pdl_trigger() lets the NEXT kernel in the stream start its prologue while this one
+// still runs; pdl_wait() blocks until the PREVIOUS kernel has completed and its writes are visible.  Both are no-ops
+// when the kernel was launched without the programmatic-serialization attribute (host.h launch_pdl).
+// Rule: nothing produced by an earlier kernel may be read, and nothing global may be written, before pdl_wait().
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor) — tensor maps are built on the host (tmap.h)
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {

@@ -105,11 +105,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   const uint32_t warp = warp_id();
   const uint32_t lane = lane_id();
-  if (ep.m_dev != nullptr) M = min(M, max(0, *ep.m_dev));
-  const int num_m = (M + kBM - 1) / kBM;
-  const int num_n = (N + BN - 1) / BN;
-  const int num_k = (K + kBK - 1) / kBK;
-  const int num_tiles = num_m * num_n;
+  pdl_trigger();  // the next kernel may start its prologue now; it cannot touch our data before we complete
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -135,6 +131,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+
+  pdl_wait();  // ---- everything above overlapped the previous kernel's tail; from here on we read its output ----
+  if (ep.m_dev != nullptr) M = min(M, max(0, *ep.m_dev));
+  const int num_m = (M + kBM - 1) / kBM;
+  const int num_n = (N + BN - 1) / BN;
+  const int num_k = (K + kBK - 1) / kBK;
+  const int num_tiles = num_m * num_n;
 
   if (warp == 0) {
     // ------------------------------- TMA producer -------------------------------
@@ -431,7 +434,8 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   int grid = tiles < sm_count() ? tiles : sm_count();
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   if (grid < 1) grid = 1;
-  gemm_bf16_tn_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, tr, tp, ep, M, N, K);
+  IM_CUDA_OK(launch_pdl(gemm_bf16_tn_kernel<BN>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, ta, tb, tc, tr,
+                        tp, ep, M, N, K));
   IM_LAUNCH_OK("gemm_bf16_tn_kernel");
   return 0;
 }

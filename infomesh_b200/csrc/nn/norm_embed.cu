@@ -143,6 +143,8 @@ embed_ln_kernel(const int* __restrict__ ids, const int* __restrict__ pos_ids, co
   constexpr int H = VEC * 128;
   const int row = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  pdl_trigger();
+  pdl_wait();
   if (row >= n_tokens || (n_rows_dev != nullptr && row >= *n_rows_dev)) return;
   int id = ids[row];
   id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
@@ -192,6 +194,8 @@ sum_ln_kernel(const __nv_bfloat16* in, size_t in_stride_p, int P,  // in / resid
   constexpr int H = VEC * 128;
   const int row = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  pdl_trigger();
+  pdl_wait();
   const uint32_t use = cm.arrive_state != nullptr ? *reinterpret_cast<volatile uint32_t*>(cm.arrive_state) : 0u;
   if (cm.arrive_flags != nullptr) {
     // one poll per CTA: its kRowsPerBlock rows all live in the same 128-row arrival block
@@ -419,10 +423,10 @@ IM_API int im_embed_ln(const int* ids, const int* pos_ids, const int* type_ids, 
   if (H % 128) return set_error("im_embed_ln", "H must be a multiple of 128");
   const int grid = (n_tokens + kRowsPerBlock - 1) / kRowsPerBlock;
   auto s = reinterpret_cast<cudaStream_t>(stream);
-  IM_DISPATCH_VEC(H, (embed_ln_kernel<VEC><<<grid, kRowsPerBlock * 32, 0, s>>>(
-                         ids, pos_ids, type_ids, (const __nv_bfloat16*)word, (const __nv_bfloat16*)pos,
-                         (const __nv_bfloat16*)type, gamma, beta, eps, n_tokens, seq_len, pos_offset, vocab, max_pos,
-                         (__nv_bfloat16*)out, n_rows_dev)));
+  IM_DISPATCH_VEC(H, IM_CUDA_OK(launch_pdl(embed_ln_kernel<VEC>, dim3(grid), dim3(kRowsPerBlock * 32), 0, s, ids, pos_ids,
+                                           type_ids, (const __nv_bfloat16*)word, (const __nv_bfloat16*)pos,
+                                           (const __nv_bfloat16*)type, gamma, beta, eps, n_tokens, seq_len, pos_offset,
+                                           vocab, max_pos, (__nv_bfloat16*)out, n_rows_dev)));
   IM_LAUNCH_OK("embed_ln_kernel");
   return 0;
 }
@@ -449,9 +453,10 @@ IM_API int im_sum_ln(const void* in, long long in_stride_p, int P, const void* r
   cm.n_rows_dev = n_rows_dev;
   const int grid = (n_rows + kRowsPerBlock - 1) / kRowsPerBlock;
   auto s = reinterpret_cast<cudaStream_t>(stream);
-  IM_DISPATCH_VEC(H, (sum_ln_kernel<VEC><<<grid, kRowsPerBlock * 32, 0, s>>>(
-                         (const __nv_bfloat16*)in, (size_t)in_stride_p, P, (const __nv_bfloat16*)residual, gamma, beta,
-                         eps, rms_only, n_rows, (__nv_bfloat16*)out, (__nv_bfloat16*)sum_out, cm)));
+  IM_DISPATCH_VEC(H, IM_CUDA_OK(launch_pdl(sum_ln_kernel<VEC>, dim3(grid), dim3(kRowsPerBlock * 32), 0, s,
+                                           (const __nv_bfloat16*)in, (size_t)in_stride_p, P,
+                                           (const __nv_bfloat16*)residual, gamma, beta, eps, rms_only, n_rows,
+                                           (__nv_bfloat16*)out, (__nv_bfloat16*)sum_out, cm)));
   IM_LAUNCH_OK("sum_ln_kernel");
   return 0;
 }
