@@ -453,25 +453,30 @@ attn_fwd_1chunk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
       q[j].z = pack_bf16x2(__uint_as_float(v[8 * j + 4]) * inv, __uint_as_float(v[8 * j + 5]) * inv);
       q[j].w = pack_bf16x2(__uint_as_float(v[8 * j + 6]) * inv, __uint_as_float(v[8 * j + 7]) * inv);
     }
-    if (tma_out) {
+    // stage the normalised [128 x 64] tile in smem (128B-swizzled rows, over the dead V tile)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int ch = (static_cast<int>(half) * 4 + j) ^ (row & 7);
-        *reinterpret_cast<uint4*>(sO + row * 128 + (ch << 4)) = q[j];
-      }
-    } else if (row < q_len) {
-      __nv_bfloat16* orow = p.out + static_cast<size_t>(q_row0 + row) * p.ldo + head * HD + half * 32;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) reinterpret_cast<uint4*>(orow)[j] = q[j];
+    for (int j = 0; j < 4; ++j) {
+      const int ch = (static_cast<int>(half) * 4 + j) ^ (row & 7);
+      *reinterpret_cast<uint4*>(sO + row * 128 + (ch << 4)) = q[j];
     }
   }
   tc_fence_before();
   if (tma_out) fence_proxy_async_smem();
   __syncthreads();
-  if (tma_out && tid == 0) {
-    tma_store_2d(&tmap_o, sO, head * HD, q_row0);
-    tma_store_commit();
-    tma_store_wait_read<0>();  // smem must stay valid until the bulk store has read it
+  if (tma_out) {
+    if (tid == 0) {
+      tma_store_2d(&tmap_o, sO, head * HD, q_row0);
+      tma_store_commit();
+      tma_store_wait_read<0>();  // smem must stay valid until the bulk store has read it
+    }
+  } else {
+    // short / packed sequences: only rows < q_len exist.  8 lanes move one 128-byte row, so a warp writes four
+    // full rows per instruction instead of 32 scattered 16-byte pieces.
+    const int c = tid & 7;
+    for (int r = tid >> 3; r < q_len; r += kAttn1Threads / 8) {
+      const uint4 val = *reinterpret_cast<const uint4*>(sO + r * 128 + ((c ^ (r & 7)) << 4));
+      *reinterpret_cast<uint4*>(p.out + static_cast<size_t>(q_row0 + r) * p.ldo + head * HD + c * 8) = val;
+    }
   }
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }

@@ -175,6 +175,53 @@ sim_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         }
       }
     }
+  } else if (ktop == 0) {
+    // ---- threshold pre-pass: per-thread running maximum of every query column, no candidate lists.  Each epilogue
+    // warp ends up with the best score of the documents it saw (a distinct document per warp and query), which is all
+    // sample_threshold() needs; branch-free FMNMX instead of the insert path, so the pass stays HBM-bound.
+    const uint32_t quad = warp & 3u;
+    constexpr int kChunk = NPAD < 32 ? 16 : 32;
+    float rmax[NPAD];
+#pragma unroll
+    for (int i = 0; i < NPAD; ++i) rmax[i] = -CUDART_INF_F;
+    uint32_t acc = 0, acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int doc = t * kSimBM + static_cast<int>(quad * 32u + lane);
+      bool doc_ok = doc < n_docs;
+      if (doc_ok && alive != nullptr) doc_ok = alive[doc] != 0;
+#pragma unroll
+      for (int c = 0; c < NPAD; c += kChunk) {
+        uint32_t v[kChunk];
+        if constexpr (kChunk == 32) tmem_ld_32x32b_x32(tmem_base + ((quad * 32u) << 16) + acc * NPAD + c, v);
+        else tmem_ld_32x32b_x16(tmem_base + ((quad * 32u) << 16) + acc * NPAD + c, v);
+        tmem_ld_wait();
+        if (doc_ok) {
+#pragma unroll
+          for (int i = 0; i < kChunk; ++i) rmax[c + i] = fmaxf(rmax[c + i], __uint_as_float(v[i]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+    // one list entry per (warp, query): out is [grid * 4, nq, 1]; the id only has to be unique and non-negative
+    const int slot = blockIdx.x * 4 + static_cast<int>(quad);
+#pragma unroll
+    for (int j = 0; j < NPAD; ++j) {
+      float m = rmax[j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if (lane == 0 && j < nq) {
+        out_scores[static_cast<size_t>(slot) * nq + j] = m;
+        out_ids[static_cast<size_t>(slot) * nq + j] = m > -CUDART_INF_F ? slot : -1;
+      }
+    }
   } else {
     const uint32_t quad = warp & 3u;
     float* my_v = list_v + quad * nq * ktop;
@@ -453,7 +500,7 @@ IM_API int im_sim_topk(const void* Q, const void* D, int nq, int n_docs, int dim
   using namespace im;
   if (nq < 1 || nq > 128) return set_error("im_sim_topk", "nq must be in [1,128]");
   if (dim % kSimBK != 0 || dim > 512) return set_error("im_sim_topk", "dim must be a multiple of 64 and <= 512");
-  if (ktop < 1 || ktop > 32) return set_error("im_sim_topk", "ktop must be in [1,32]");
+  if (ktop < 0 || ktop > 32) return set_error("im_sim_topk", "ktop must be in [0,32] (0 = per-warp maxima only)");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (nq <= 16) return launch_sim<16>(Q, D, nq, n_docs, dim, ldq, ldd, ktop, alive, out_scores, out_ids, max_ctas, thr_init, thr_stride, s);
   if (nq <= 32) return launch_sim<32>(Q, D, nq, n_docs, dim, ldq, ldd, ktop, alive, out_scores, out_ids, max_ctas, thr_init, thr_stride, s);

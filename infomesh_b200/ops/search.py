@@ -37,8 +37,10 @@ def sim_topk_partials(q, docs, ktop=16, alive=None, max_ctas=0, thr_init=None):
     sms = L.im_sm_count()
     tiles = (n_docs + 127) // 128
     grid = max(1, min(tiles, sms if max_ctas <= 0 else min(sms, max_ctas)))
-    out_s = torch.empty((grid, nq, ktop), device=q.device, dtype=torch.float32)
-    out_i = torch.empty((grid, nq, ktop), device=q.device, dtype=torch.int32)
+    # ktop == 0: threshold pre-pass, one (max score, slot id) per epilogue warp -> [grid * 4, nq, 1]
+    lists, width = (grid * 4, 1) if ktop == 0 else (grid, ktop)
+    out_s = torch.empty((lists, nq, width), device=q.device, dtype=torch.float32)
+    out_i = torch.empty((lists, nq, width), device=q.device, dtype=torch.int32)
     if alive is not None:
         assert alive.dtype == torch.uint8 and alive.numel() >= n_docs
     rc = L.im_sim_topk(_native.ptr(q), _native.ptr(docs), ctypes.c_int(nq), ctypes.c_int(n_docs), ctypes.c_int(dim),
@@ -103,15 +105,16 @@ def sample_threshold(q, docs, k, alive=None):
 
     A persistent CTA starts with empty candidate lists, so without a bound the first tiles of every CTA insert almost
     every document (~k*ln(n/k) sorted inserts per query per warp -- a fixed ~1.9 ms at 64 queries that does not
-    shrink with the shard).  The pre-pass runs the same kernel with ``ktop=1`` over ``n/32`` documents (each CTA
-    reports its best document per query), and the k-th largest of those per-CTA maxima -- k distinct documents --
+    shrink with the shard).  The pre-pass runs the same kernel in max-only mode (``ktop=0``) over ``n/32`` documents
+    (each epilogue warp reports the best score it saw per query, branch-free), and the k-th largest of those
+    per-warp maxima -- k distinct documents --
     bounds the k-th best of the whole shard from below.  The main pass then inserts ~k*32 candidates per query
     per GPU in total.  Returns a strided fp32 ``[nq]`` view or ``None`` when the shard is too small to bother."""
     n = docs.shape[0]
     n_s = max(SAMPLE_MIN_DOCS, n // SAMPLE_FRACTION)
     if n < 2 * n_s or k > 32:
         return None
-    ps, pi = sim_topk_partials(q, docs[:n_s], ktop=1, alive=alive)
+    ps, pi = sim_topk_partials(q, docs[:n_s], ktop=0, alive=alive)
     if ps.shape[0] < k:
         return None
     ms, _ = topk_merge(ps, pi, k)

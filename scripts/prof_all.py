@@ -1,5 +1,5 @@
-"""One pass over every hot kernel at its benchmark shape, for `ncu --set full` (each kernel: 1 warm + 1 profiled
-launch; run with `-k regex:<names> --launch-skip <n>`).  Shapes: sim_topk 10M x 384 (batch 1 and 64), reranker
+"""One pass over every hot kernel at its benchmark shape, for `ncu --set full --profile-from-start off` (iteration 0
+warms up; iteration 1 runs between cudaProfilerStart/Stop so ncu captures exactly one launch of each kernel).  Shapes: sim_topk 10M x 384 (batch 1 and 64), reranker
 layer GEMMs / attention at B=1280 S=128, encoder at B=64 S=32, BM25 / merge / RRF / pair assembly on a 1M-doc shard."""
 import sys
 from dataclasses import replace
@@ -27,13 +27,19 @@ shard = SynthShard(scfg, device=dev)
 terms, qtok, qlen, _ = make_queries(scfg, 64, device=dev)
 terms = terms.to(dev)
 torch.cuda.synchronize()
+plens = torch.randint(40, 101, (1280,), device=dev, dtype=torch.int32)     # unpadded batch, mean ~70 tokens
 for it in range(2):
+    if it == 1:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
     sim_topk(q1, docs, 20)
     sim_topk(q64, docs, 20)
     rr.score(ids, lens)
+    rr.score_packed(ids, plens)
     enc.embed(eids, elens)
     bs, bi = shard.bm25.search(terms, k=20)
     ds, di = sim_topk(q64, shard.vectors, 20)
     fs, fi = F.rrf_fuse(bi.contiguous(), di.contiguous(), 20)
     torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print("done")
