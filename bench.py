@@ -261,7 +261,8 @@ def main() -> int:
         mean_len = float(eng.last_pair_lens.float().mean().item())
         if hcfg.varlen and args.impl == "fused":
             pad_note = (f"cross-encoder runs unpadded (varlen): pairs are <= {args.pair_seq} tokens, mean "
-                        f"{mean_len:.1f} in this synthetic batch; padding tokens are not computed")
+                        f"{mean_len:.1f} in this synthetic batch; padding tokens are not computed; the last encoder "
+                        "layer evaluates its query / FFN rows only for the <s> token the classifier reads (same logits)")
         else:
             pad_note += f" (mean real pair length {mean_len:.1f})"
     if rank == 0:

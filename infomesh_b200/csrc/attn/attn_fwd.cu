@@ -488,7 +488,8 @@ __global__ void __launch_bounds__(128)
 attn_decode_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ kc,
                    const __nv_bfloat16* __restrict__ vc, int ld_kv, int s_max, const int* __restrict__ kv_lens,
                    int kv_len_all, float scale_log2, const float* __restrict__ rel_bias, int bias_len, int q_pos,
-                   int n_heads, int n_pairs, __nv_bfloat16* __restrict__ out, int ldo) {
+                   int n_heads, int n_pairs, __nv_bfloat16* __restrict__ out, int ldo,
+                   const int* __restrict__ seq_start) {
   const int pair = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (pair >= n_pairs) return;
@@ -501,8 +502,10 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bflo
   float m = kNegBig, l = 0.f, acc[PER];
 #pragma unroll
   for (int i = 0; i < PER; ++i) acc[i] = 0.f;
-  const __nv_bfloat16* kb = kc + static_cast<size_t>(b) * s_max * ld_kv + h * HD;
-  const __nv_bfloat16* vb = vc + static_cast<size_t>(b) * s_max * ld_kv + h * HD;
+  // seq_start: keys of sequence b begin at row seq_start[b] of a packed (unpadded) K/V buffer instead of b * s_max
+  const size_t row0 = seq_start != nullptr ? static_cast<size_t>(seq_start[b]) : static_cast<size_t>(b) * s_max;
+  const __nv_bfloat16* kb = kc + row0 * ld_kv + h * HD;
+  const __nv_bfloat16* vb = vc + row0 * ld_kv + h * HD;
   for (int j = 0; j < len; ++j) {
     float d = 0.f;
 #pragma unroll
@@ -590,7 +593,8 @@ IM_API int im_attn_fwd(const void* q, const void* k, const void* v, void* out, i
 
 IM_API int im_attn_decode(const void* q, int ldq, const void* kc, const void* vc, int ld_kv, int s_max,
                           const int* kv_lens, int kv_len_all, float scale, const float* rel_bias_log2, int bias_len,
-                          int q_pos, int B, int n_heads, int head_dim, void* out, int ldo, void* stream) {
+                          int q_pos, int B, int n_heads, int head_dim, void* out, int ldo, void* stream,
+                          const int* seq_start) {
   using namespace im;
   const int n_pairs = B * n_heads;
   if (n_pairs <= 0) return 0;
@@ -600,11 +604,11 @@ IM_API int im_attn_decode(const void* q, int ldq, const void* kc, const void* vc
   if (head_dim == 64)
     attn_decode_kernel<64><<<grid, 128, 0, s>>>((const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)kc,
                                                (const __nv_bfloat16*)vc, ld_kv, s_max, kv_lens, kv_len_all, sl2,
-                                               rel_bias_log2, bias_len, q_pos, n_heads, n_pairs, (__nv_bfloat16*)out, ldo);
+                                               rel_bias_log2, bias_len, q_pos, n_heads, n_pairs, (__nv_bfloat16*)out, ldo, seq_start);
   else if (head_dim == 32)
     attn_decode_kernel<32><<<grid, 128, 0, s>>>((const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)kc,
                                                (const __nv_bfloat16*)vc, ld_kv, s_max, kv_lens, kv_len_all, sl2,
-                                               rel_bias_log2, bias_len, q_pos, n_heads, n_pairs, (__nv_bfloat16*)out, ldo);
+                                               rel_bias_log2, bias_len, q_pos, n_heads, n_pairs, (__nv_bfloat16*)out, ldo, seq_start);
   else
     return set_error("im_attn_decode", "head_dim must be 32 or 64");
   IM_LAUNCH_OK("attn_decode_kernel");

@@ -150,15 +150,14 @@ class BertModel:
             x = N.layernorm(y2, lay["ln2_g"], lay["ln2_b"], cfg.eps)
         return x.view(B, S, H)
 
-    def hidden_states_packed(self, ids: torch.Tensor, lengths: torch.Tensor):
+    def hidden_states_packed(self, ids: torch.Tensor, lengths: torch.Tensor, cls_only_last: bool = False):
         """Unpadded forward: ids int32 [B, S<=128] + lengths [B] -> (hidden bf16 [B*S, H] of which the first
         ``total`` rows are the packed tokens, cu_seqlens int32 [B+1], total int32 [1]).
 
         Padding tokens are never embedded, multiplied or normalised: every GEMM / LayerNorm reads the token count
         from a device scalar, and attention walks ``cu_seqlens``.  Shapes stay static, so the whole forward still
-        captures into one CUDA graph even though the amount of work follows the batch."""
-        from infomesh_b200.ops import attention as A
-        from infomesh_b200.ops import gemm as G
+        captures into one CUDA graph even though the amount of work follows the batch.  ``cls_only_last`` stops
+        before the last layer (see :meth:`_cls_last_layer`)."""
         from infomesh_b200.ops import nn as N
 
         cfg, w = self.cfg, self.w
@@ -167,26 +166,54 @@ class BertModel:
         assert S <= 128 and cfg.head_dim == 64, "packed path: max_seqlen <= 128, head_dim 64"
         pk_ids, pk_pos, cu, total = N.seq_pack(ids.contiguous(), lengths, cfg.pos_offset)
         x = N.embed_ln(pk_ids, w.word, w.pos, w.type, w.emb_g, w.emb_b, cfg.eps, S, pos_ids=pk_pos, n_rows_dev=total)
-        for lay in w.layers:
-            qkv = G.linear(x, lay["wqkv"], lay["bqkv"], m_dev=total)
-            q3 = qkv.view(B, S, 3 * H)
-            ctx = A.attention(q3[..., :H], q3[..., H:2 * H], q3[..., 2 * H:], cfg.heads, cu_seqlens=cu)
-            y = G.linear(ctx.view(B * S, H), lay["wo"], lay["bo"], residual=x, m_dev=total)
-            x1 = N.layernorm(y, lay["ln1_g"], lay["ln1_b"], cfg.eps, n_rows_dev=total)
-            h = G.linear(x1, lay["w1"], lay["b1"], act="gelu", m_dev=total)
-            y2 = G.linear(h, lay["w2"], lay["b2"], residual=x1, m_dev=total)
-            x = N.layernorm(y2, lay["ln2_g"], lay["ln2_b"], cfg.eps, n_rows_dev=total)
+        layers = w.layers[:-1] if cls_only_last else w.layers
+        for lay in layers:
+            x = self._packed_layer(x, lay, B, S, cu, total)
         return x, cu, total
+
+    def _packed_layer(self, x, lay, B, S, cu, total):
+        from infomesh_b200.ops import attention as A
+        from infomesh_b200.ops import gemm as G
+        from infomesh_b200.ops import nn as N
+
+        cfg, H = self.cfg, self.cfg.hidden
+        qkv = G.linear(x, lay["wqkv"], lay["bqkv"], m_dev=total)
+        q3 = qkv.view(B, S, 3 * H)
+        ctx = A.attention(q3[..., :H], q3[..., H:2 * H], q3[..., 2 * H:], cfg.heads, cu_seqlens=cu)
+        y = G.linear(ctx.view(B * S, H), lay["wo"], lay["bo"], residual=x, m_dev=total)
+        x1 = N.layernorm(y, lay["ln1_g"], lay["ln1_b"], cfg.eps, n_rows_dev=total)
+        h = G.linear(x1, lay["w1"], lay["b1"], act="gelu", m_dev=total)
+        y2 = G.linear(h, lay["w2"], lay["b2"], residual=x1, m_dev=total)
+        return N.layernorm(y2, lay["ln2_g"], lay["ln2_b"], cfg.eps, n_rows_dev=total)
+
+    def _cls_last_layer(self, x, lay, B, lengths, cu, total):
+        """Last encoder layer for a classifier that reads only the <s> token: keys / values for every token, but the
+        query, attention output, out-projection, both LayerNorms and the whole FFN only for the B CLS rows (exactly
+        the same logits; ~3/4 of the layer's GEMM flops never happen)."""
+        from infomesh_b200.ops import attention as A
+        from infomesh_b200.ops import gemm as G
+        from infomesh_b200.ops import nn as N
+
+        cfg, H = self.cfg, self.cfg.hidden
+        kv = G.linear(x, lay["wqkv"][H:], lay["bqkv"][H:], m_dev=total)          # [rows, 2H]: K | V for every token
+        x_cls = N.gather_rows(x, cu, B)                                           # [B, H]
+        q_cls = G.linear(x_cls, lay["wqkv"][:H], lay["bqkv"][:H])
+        kv3 = kv.view(1, kv.shape[0], 2 * H)
+        ctx = A.attention_decode(q_cls, kv3[..., :H], kv3[..., H:], cfg.heads, lengths, seq_start=cu)
+        y = G.linear(ctx, lay["wo"], lay["bo"], residual=x_cls)
+        x1 = N.layernorm(y, lay["ln1_g"], lay["ln1_b"], cfg.eps)
+        h = G.linear(x1, lay["w1"], lay["b1"], act="gelu")
+        y2 = G.linear(h, lay["w2"], lay["b2"], residual=x1)
+        return N.layernorm(y2, lay["ln2_g"], lay["ln2_b"], cfg.eps)               # [B, H] final CLS states
 
     def score_packed(self, ids, lengths) -> torch.Tensor:
         """Cross-encoder logits fp32 [B], computed on the unpadded token stream (see :meth:`hidden_states_packed`)."""
         from infomesh_b200.ops import gemm as G
-        from infomesh_b200.ops import nn as N
 
         assert self.cfg.classifier
         w = self.w
-        x, cu, _ = self.hidden_states_packed(ids, lengths)
-        cls = N.gather_rows(x, cu, ids.shape[0])          # <s> is the first token of every sequence
+        x, cu, total = self.hidden_states_packed(ids, lengths, cls_only_last=True)
+        cls = self._cls_last_layer(x, w.layers[-1], ids.shape[0], lengths, cu, total)
         hcls = G.linear(cls, w.cls_w1, w.cls_b1, act="tanh")
         return G.linear(hcls, w.cls_w2p, w.cls_b2p, out_dtype=torch.float32)[:, 0].contiguous()
 

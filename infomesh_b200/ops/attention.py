@@ -77,8 +77,12 @@ def attention(q, k, v, n_heads, kv_lens=None, causal=False, causal_offset=0, sca
     return out
 
 
-def attention_decode(q, k_cache, v_cache, n_heads, kv_len, scale=None, rel_bias_log2=None, q_pos=0, out=None):
-    """One query token per sequence against a KV cache ``[B, S_max, nH*hd]``; ``kv_len`` int or int32 tensor."""
+def attention_decode(q, k_cache, v_cache, n_heads, kv_len, scale=None, rel_bias_log2=None, q_pos=0, out=None,
+                     seq_start=None):
+    """One query token per sequence against a KV cache ``[B, S_max, nH*hd]``; ``kv_len`` int or int32 tensor.
+
+    ``seq_start`` (int32 ``[B]``): the caches are one packed ``[1, rows, nH*hd]`` buffer and sequence b's keys start
+    at row ``seq_start[b]`` (CLS-only last layer of an unpadded cross-encoder)."""
     B, HH = q.shape
     hd = HH // n_heads
     s_max = k_cache.shape[1]
@@ -93,7 +97,7 @@ def attention_decode(q, k_cache, v_cache, n_heads, kv_len, scale=None, rel_bias_
                           ctypes.c_int(0 if lens_t is not None else int(kv_len)), ctypes.c_float(scale),
                           _native.ptr(rel_bias_log2), ctypes.c_int(bias_len), ctypes.c_int(q_pos), ctypes.c_int(B),
                           ctypes.c_int(n_heads), ctypes.c_int(hd), _native.ptr(out), ctypes.c_int(out.stride(0)),
-                          _native.stream_ptr())
+                          _native.stream_ptr(), _native.ptr(seq_start))
     _native.check(rc, "im_attn_decode")
     _native.count_launch()
     return out
