@@ -373,6 +373,53 @@ __device__ __forceinline__ float gelu_erf(float x) {
   const float hx = 0.5f * x;
   return fmaf(hx, tanh_approx(p * x), hx);
 }
+// ---- packed fp32x2 math (sm_100: FFMA2 / FMUL2 / FADD2 issue two fp32 lanes per instruction).  A pair lives in one
+// 64-bit register; pk2 / upk2 are register renames, not instructions.
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t pk2u(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2_pair(uint64_t v) {
+  float lo, hi;
+  upk2(v, lo, hi);
+  return pack_bf16x2(lo, hi);
+}
+// gelu_erf on a pair: 6 packed FMA-class instructions + 2 FMNMX + 2 MUFU.TANH for two elements
+__device__ __forceinline__ uint64_t gelu_erf2(uint64_t x) {
+  float a, b;
+  upk2(mul2(x, x), a, b);
+  const uint64_t x2 = pk2(fminf(a, 40.0f), fminf(b, 40.0f));
+  uint64_t p = fma2(pk2(-3.51516790e-4f, -3.51516790e-4f), x2, pk2(3.70056460e-2f, 3.70056460e-2f));
+  p = fma2(p, x2, pk2(7.97507884e-1f, 7.97507884e-1f));
+  upk2(mul2(p, x), a, b);
+  const uint64_t th = pk2(tanh_approx(a), tanh_approx(b));
+  const uint64_t hx = mul2(x, pk2(0.5f, 0.5f));
+  return fma2(hx, th, hx);
+}
 __device__ __forceinline__ float gelu_tanh(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
   return 0.5f * x * (1.0f + tanh_approx(k0 * fmaf(k1 * x * x, x, x)));

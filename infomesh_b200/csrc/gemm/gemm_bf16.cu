@@ -258,30 +258,40 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             uint32_t v[32];
             tmem_ld_32x32b_x32(tmem_base + ((quad * 32u) << 16) + acc * BN + c + half * 32, v);
             tmem_ld_wait();
-            float f[32];
             const int cb = col0 + half * 32;
+            uint64_t g[16];  // 32 fp32 values as 16 packed pairs (FFMA2 path)
             if (ep.bias != nullptr && cb + 32 <= N) {
-              // common case: one FFMA per element (alpha * acc + bias)
+              // common case: one FFMA2 per element PAIR (alpha * acc + bias)
+              const uint64_t al2 = pk2(ep.alpha, ep.alpha);
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + cb) + j);
-                f[4 * j] = fmaf(__uint_as_float(v[4 * j]), ep.alpha, b4.x);
-                f[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), ep.alpha, b4.y);
-                f[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), ep.alpha, b4.z);
-                f[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), ep.alpha, b4.w);
+                g[2 * j] = fma2(pk2u(v[4 * j], v[4 * j + 1]), al2, pk2(b4.x, b4.y));
+                g[2 * j + 1] = fma2(pk2u(v[4 * j + 2], v[4 * j + 3]), al2, pk2(b4.z, b4.w));
               }
             } else {
+              float f[32];
 #pragma unroll
               for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * ep.alpha;
-            }
-            if (ep.bias != nullptr && cb + 32 > N) {
-              {
+              if (ep.bias != nullptr) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i)
                   if (cb + i < N) f[i] += __ldg(ep.bias + cb + i);
               }
+#pragma unroll
+              for (int i = 0; i < 16; ++i) g[i] = pk2(f[2 * i], f[2 * i + 1]);
             }
-            apply_act32(f, ep.act);
+            if (ep.act == 1) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) g[i] = gelu_erf2(g[i]);
+            } else if (ep.act != 0) {
+              float f[32];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) upk2(g[i], f[2 * i], f[2 * i + 1]);
+              apply_act32(f, ep.act);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) g[i] = pk2(f[2 * i], f[2 * i + 1]);
+            }
             if (ep.residual != nullptr && half == 0) mbar_wait(&res_bar[ew], store_cnt & 1u);
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4) {
@@ -289,15 +299,17 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               uint4* slot = reinterpret_cast<uint4*>(stage + lane * 128 + (ch << 4));
               if (ep.residual != nullptr) {
                 const uint4 rq = *slot;
-                float2 a = unpack_bf16x2(rq.x), b = unpack_bf16x2(rq.y), cc = unpack_bf16x2(rq.z), d = unpack_bf16x2(rq.w);
-                f[q4 * 8 + 0] += a.x; f[q4 * 8 + 1] += a.y; f[q4 * 8 + 2] += b.x; f[q4 * 8 + 3] += b.y;
-                f[q4 * 8 + 4] += cc.x; f[q4 * 8 + 5] += cc.y; f[q4 * 8 + 6] += d.x; f[q4 * 8 + 7] += d.y;
+                const float2 a = unpack_bf16x2(rq.x), b = unpack_bf16x2(rq.y), cc = unpack_bf16x2(rq.z), d = unpack_bf16x2(rq.w);
+                g[q4 * 4 + 0] = add2(g[q4 * 4 + 0], pk2(a.x, a.y));
+                g[q4 * 4 + 1] = add2(g[q4 * 4 + 1], pk2(b.x, b.y));
+                g[q4 * 4 + 2] = add2(g[q4 * 4 + 2], pk2(cc.x, cc.y));
+                g[q4 * 4 + 3] = add2(g[q4 * 4 + 3], pk2(d.x, d.y));
               }
               uint4 q;
-              q.x = pack_bf16x2(f[q4 * 8 + 0], f[q4 * 8 + 1]);
-              q.y = pack_bf16x2(f[q4 * 8 + 2], f[q4 * 8 + 3]);
-              q.z = pack_bf16x2(f[q4 * 8 + 4], f[q4 * 8 + 5]);
-              q.w = pack_bf16x2(f[q4 * 8 + 6], f[q4 * 8 + 7]);
+              q.x = pack_bf16x2_pair(g[q4 * 4 + 0]);
+              q.y = pack_bf16x2_pair(g[q4 * 4 + 1]);
+              q.z = pack_bf16x2_pair(g[q4 * 4 + 2]);
+              q.w = pack_bf16x2_pair(g[q4 * 4 + 3]);
               *slot = q;
             }
           }
