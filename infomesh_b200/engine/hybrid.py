@@ -34,6 +34,7 @@ class HybridConfig:
     n_rerank: int = 20        # reference reranks <= 20 candidates (reranker.py:20)
     k_out: int = 10
     varlen: bool = True       # cross-encoder runs on the unpadded token stream (padding never reaches a kernel)
+    rerank_chunks: int = 1    # split the rank's pairs into this many sub-batches so activations stay L2-resident
     pair_seq: int = 128       # <s> q </s></s> passage </s>
     rerank: bool = True
     backend: str = "fused"    # "fused" | "torch"
@@ -140,18 +141,31 @@ class HybridEngine:
         # (no PyTorch equivalent exists for BM25 / RRF / pair assembly: both backends use the kernels here)
         return F.rrf_fuse(bm_ids.contiguous(), de_ids.contiguous(), self.cfg.n_rerank)
 
-    def _rerank(self, cand_ids):
+    def _pairs(self, cand_ids, out_ids=None, out_lens=None):
+        """(query, passage) token sequences for this rank's slice of the queries."""
         cfg, c = self.cfg, self.ctx
         q0 = c.rank * self.nq_local
         my_c = cand_ids[q0:q0 + self.nq_local].contiguous()
         pair_ids, pair_lens = F.build_pairs(self.in_q_tok[q0:q0 + self.nq_local].contiguous(),
                                             self.in_q_len[q0:q0 + self.nq_local].contiguous(), my_c, self.tok_ptrs,
-                                            self.len_ptrs, self.docs_per_shard, self.passage_len, cfg.pair_seq)
+                                            self.len_ptrs, self.docs_per_shard, self.passage_len, cfg.pair_seq,
+                                            out_ids=out_ids, out_lens=out_lens)
         self.last_pair_lens = pair_lens          # (graph-static buffer) token count of every reranked pair
+        return pair_ids, pair_lens
+
+    def _score(self, pair_ids, pair_lens):
+        """Cross-encoder logits of every rank's pairs, gathered on every rank (fp32 [nq * n_rerank])."""
+        cfg, c = self.cfg, self.ctx
         if cfg.backend == "torch":
             logits = self.reranker.score_torch(pair_ids, pair_lens)
         elif cfg.varlen and pair_ids.shape[1] <= 128 and self.reranker.cfg.head_dim == 64:
-            logits = self.reranker.score_packed(pair_ids, pair_lens)
+            n_pairs, ch = pair_ids.shape[0], max(1, cfg.rerank_chunks)
+            if ch > 1 and n_pairs % ch == 0:
+                step = n_pairs // ch
+                logits = torch.cat([self.reranker.score_packed(pair_ids[i:i + step], pair_lens[i:i + step].contiguous())
+                                    for i in range(0, n_pairs, step)])
+            else:
+                logits = self.reranker.score_packed(pair_ids, pair_lens)
         else:
             logits = self.reranker.score(pair_ids, pair_lens)
         if self.heap is not None:
@@ -161,6 +175,9 @@ class HybridEngine:
         if c.is_dist:
             logits = D.all_gather_cat(logits.contiguous()).reshape(-1)
         return logits
+
+    def _rerank(self, cand_ids):
+        return self._score(*self._pairs(cand_ids))
 
     # ------------------------------------------------------------------ one batch
     def _forward(self):
@@ -227,6 +244,151 @@ class HybridEngine:
         out_scores_host.copy_(self.out_scores, non_blocking=True)
         out_ids_host.copy_(self.out_ids, non_blocking=True)
         return out_scores_host, out_ids_host
+
+    # ------------------------------------------------------------------ pipelined serving (throughput mode)
+    #
+    # A step has two halves with opposite characters: retrieval (query encoder, BM25 + dense search, the fused top-k
+    # exchange, RRF, pair assembly) is a chain of small latency-bound kernels plus one HBM stream; the cross-encoder is
+    # tensor-core bound.  `submit()` overlaps them across batches with three CUDA graphs per parity on two streams:
+    #
+    #   stream SA:  A(i)  retrieval + pair assembly ............ then  C(i-1)  logit all-gather + final selection + D2H
+    #   stream SB:  B(i)  cross-encoder on this rank's pairs (purely local compute)
+    #
+    # Every kernel that spins on a PEER (exchange merge, logit all-gather) lives on SA; SB never waits on anything
+    # remote.  That is what makes the overlap deadlock-free: the persistent GEMM / sim_topk CTAs need (nearly) all of an
+    # SM's shared memory, so a resident spinning CTA can keep one of them off its SM -- harmless as long as the spinner's
+    # peer-side producer never needs this GPU's blocked kernel, which holds because every producer sits on a peer's SA
+    # and SA only ever blocks on stream-level events of its own (spinner-free) SB.  Each p2p channel is used by one
+    # stream only, so its use counter still advances in stream order on every rank.  NCCL exchange mode does not
+    # pipeline (one communicator, two streams).
+    def pipeline_supported(self) -> bool:
+        cfg = self.cfg
+        return (cfg.backend == "fused" and cfg.rerank and cfg.use_graph and not self._graph_failed
+                and (not self.ctx.is_dist or self.heap is not None))
+
+    def _local_logits(self, pair_ids, pair_lens):
+        cfg = self.cfg
+        if cfg.varlen and pair_ids.shape[1] <= 128 and self.reranker.cfg.head_dim == 64:
+            return self.reranker.score_packed(pair_ids, pair_lens)
+        return self.reranker.score(pair_ids, pair_lens)
+
+    def _pipe_init(self):
+        from types import SimpleNamespace
+
+        cfg, dev = self.cfg, self.device
+        n_pairs = self.nq_local * cfg.n_rerank
+        n_log = getattr(self, "_log_pad", n_pairs)
+        self._pbuf = [SimpleNamespace(
+            fu_s=torch.zeros((cfg.nq, cfg.n_rerank), device=dev, dtype=torch.float32),
+            fu_i=torch.full((cfg.nq, cfg.n_rerank), -1, device=dev, dtype=torch.int64),
+            pair_ids=torch.ones((n_pairs, cfg.pair_seq), device=dev, dtype=torch.int32),
+            pair_lens=torch.ones((n_pairs,), device=dev, dtype=torch.int32),
+            logits=torch.zeros((n_log,), device=dev, dtype=torch.float32),
+            out_scores=torch.zeros((cfg.nq, cfg.k_out), device=dev, dtype=torch.float32),
+            out_ids=torch.full((cfg.nq, cfg.k_out), -1, device=dev, dtype=torch.int64),
+            host=None, done=None) for _ in range(2)]
+        self._sa, self._sb = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        cur = torch.cuda.current_stream()
+        self._sa.wait_stream(cur)
+        self._sb.wait_stream(cur)
+
+        def stage_a(b):
+            q_emb = self._encode()
+            de_s, de_i = self._dense_local(q_emb)
+            bm_s, bm_i = self._bm25_local()
+            de_s, de_i = self._exchange(de_s, de_i, getattr(self, "ch_dense", None))
+            bm_s, bm_i = self._exchange(bm_s, bm_i, getattr(self, "ch_bm25", None))
+            F.rrf_fuse(bm_i.contiguous(), de_i.contiguous(), cfg.n_rerank, out_scores=b.fu_s, out_ids=b.fu_i)
+            self._pairs(b.fu_i, out_ids=b.pair_ids, out_lens=b.pair_lens)
+
+        def stage_b(b):
+            lg = self._local_logits(b.pair_ids, b.pair_lens)
+            b.logits[:n_pairs].copy_(lg.reshape(-1).float())
+
+        def stage_c(b):
+            if self.heap is not None:
+                lg = self.ch_logits(b.logits)[:, :n_pairs].reshape(-1)
+            else:
+                lg = b.logits[:n_pairs]
+            F.rerank_select(lg.contiguous(), b.fu_i, cfg.k_out, b.out_scores, b.out_ids)
+
+        # warm every stage eagerly in pipeline order (identical on every rank), then capture one graph per stage / parity
+        for b in self._pbuf:
+            with torch.cuda.stream(self._sa):
+                stage_a(b)
+            self._sb.wait_stream(self._sa)
+            with torch.cuda.stream(self._sb):
+                stage_b(b)
+            self._sa.wait_stream(self._sb)
+            with torch.cuda.stream(self._sa):
+                stage_c(b)
+        torch.cuda.synchronize()
+
+        def cap(fn, stream):
+            out = []
+            for b in self._pbuf:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=stream):
+                    fn(b)
+                out.append(g)
+            torch.cuda.synchronize()
+            return out
+
+        self._ga, self._gb, self._gc = cap(stage_a, self._sa), cap(stage_b, self._sb), cap(stage_c, self._sa)
+        self._ev_a = [torch.cuda.Event() for _ in range(2)]
+        self._ev_b = [torch.cuda.Event() for _ in range(2)]
+        self._tick = 0
+        self._pending = None      # parity whose stage C has not been enqueued yet
+
+    def _enqueue_c(self, par):
+        b = self._pbuf[par]
+        with torch.cuda.stream(self._sa):
+            self._sa.wait_event(self._ev_b[par])
+            self._gc[par].replay()
+            if b.host is not None:
+                b.host[0].copy_(b.out_scores, non_blocking=True)
+                b.host[1].copy_(b.out_ids, non_blocking=True)
+            if b.done is not None:
+                b.done.record(self._sa)
+
+    def submit(self, enc_ids, enc_len, q_tok, q_len, terms, out_scores_host=None, out_ids_host=None, done_event=None):
+        """Enqueue one batch into the pipeline and return immediately.  Its results are copied into the given (pinned)
+        host tensors when its final stage runs -- one `submit` later, or at :meth:`drain`; ``done_event`` is recorded
+        right after those copies.  Always finish a stream of submits with :meth:`drain`."""
+        if getattr(self, "_ga", None) is None:
+            self._pipe_init()
+        par = self._tick & 1
+        b = self._pbuf[par]
+        self._tick += 1
+        with torch.cuda.stream(self._sa):
+            # (buffers of this parity are free: C of the batch two submits ago precedes this point on SA)
+            self.load_inputs(enc_ids, enc_len, q_tok, q_len, terms)
+            self._ga[par].replay()
+            self._ev_a[par].record(self._sa)
+        b.host = (out_scores_host, out_ids_host) if out_scores_host is not None else None
+        b.done = done_event
+        with torch.cuda.stream(self._sb):
+            self._sb.wait_event(self._ev_a[par])
+            self._gb[par].replay()
+            self._ev_b[par].record(self._sb)
+        if self._pending is not None:
+            self._enqueue_c(self._pending)     # previous batch: all-gather + select, behind this batch's retrieval on SA
+        self._pending = par
+
+    def drain(self):
+        """Finish the last batch's final stage and wait until everything submitted has completed."""
+        if getattr(self, "_sa", None) is None:
+            return
+        if self._pending is not None:
+            self._enqueue_c(self._pending)
+            self._pending = None
+        self._sa.synchronize()
+        self._sb.synchronize()
+
+    def pipeline_streams(self):
+        if getattr(self, "_ga", None) is None:
+            self._pipe_init()
+        return self._sa, self._sb
 
     def degraded_shards(self) -> list[int]:
         """Ranks whose lists were dropped from a merge because they stayed silent (p2p exchange, ``degraded_ok``)."""
