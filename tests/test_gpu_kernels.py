@@ -409,3 +409,41 @@ def test_packed_cross_encoder_matches_padded():
         n = int(lens[bi].item())
         s0 = int(cu[bi].item())
         assert (x[s0:s0 + n].float() - ref[bi, :n].float()).abs().max().item() < 0.12
+
+
+def test_pipelined_engine_matches_single_batch_path():
+    """submit()/drain() (two batches in flight on two streams, 3 graphs per parity) returns exactly what run() returns,
+    batch for batch, and the smoke() configuration of the driver runs through the unpadded cross-encoder."""
+    import __graft_entry__ as entry
+    from infomesh_b200.engine.hybrid import HybridConfig, HybridEngine
+    from infomesh_b200.engine.synth import SynthConfig, SynthShard, make_queries
+    from infomesh_b200.models.bert import BertConfig, BertModel
+
+    entry.smoke()
+    cfg = SynthConfig(n_docs=30_000, n_docs_global=30_000, vocab_terms=5_000, doc_len=32, passage_len=48)
+    shard = SynthShard(cfg, device=DEV)
+    enc = BertModel(BertConfig(name="t-enc", layers=2), device=DEV, seed=1)
+    rr = BertModel(BertConfig(name="t-rr", vocab_size=250002, hidden=768, layers=2, heads=12, ffn=3072, max_pos=514,
+                              type_vocab=1, eps=1e-5, pos_offset=2, classifier=True), device=DEV, seed=2)
+    nq, nb = 8, 5
+    eng = HybridEngine(shard, HybridConfig(nq=nq, pair_seq=64, use_graph=True), encoder=enc, reranker=rr)
+    assert eng.pipeline_supported()
+    qt, qtok, qlen, _ = make_queries(cfg, nq * nb, device=DEV)
+    enc_ids = torch.zeros((nq * nb, 32), dtype=torch.int32, device=DEV)
+    enc_ids[:, 0] = 101
+    enc_ids[:, 1:4] = (qtok[:, :3].to(DEV) % 20000) + 1000
+    enc_ids[:, 4] = 102
+    enc_len = torch.full((nq * nb,), 5, dtype=torch.int32, device=DEV)
+    batches = [tuple(x[i * nq:(i + 1) * nq].to(DEV).contiguous() for x in (enc_ids, enc_len, qtok, qlen, qt)) for i in range(nb)]
+    ref = []
+    for b in batches:
+        s, i = eng.search_batch(*b)
+        ref.append((s.clone(), i.clone()))
+    outs = [(torch.empty((nq, 10), dtype=torch.float32).pin_memory(), torch.empty((nq, 10), dtype=torch.int64).pin_memory())
+            for _ in range(nb)]
+    for b, (hs, hi) in zip(batches, outs):
+        eng.submit(*b, out_scores_host=hs, out_ids_host=hi)
+    eng.drain()
+    for (rs, ri), (hs, hi) in zip(ref, outs):
+        assert torch.equal(ri.cpu(), hi)
+        assert (rs.cpu() - hs).abs().max().item() < 1e-3
