@@ -284,21 +284,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 // ------------------------------------------------------------------------------------------------
 constexpr int kAttn1Threads = 256;
 
-__global__ void __launch_bounds__(kAttn1Threads, 4)
+template <int HD>
+__global__ void __launch_bounds__(kAttn1Threads, HD == 64 ? 4 : 3)
 attn_fwd_1chunk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                        const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
                        const AttnParams p, int tma_out) {
-  constexpr int HD = 64;
   using Cfg = AttnCfg<HD>;
+  constexpr int kRow = Cfg::kRowBytes;  // bytes per Q/K/V/O row: 128 (SW128 tiles) or 64 (SW64 tiles)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + Cfg::kTileBytes;
   uint8_t* sV = sK + Cfg::kTileBytes;
-  uint8_t* sP = sQ;  // [2 k-blocks][128 rows][128 B] over the dead Q + K tiles
-  uint8_t* sO = sV;  // [128 rows][128 B] over the dead V tile
-  uint64_t* qk_bar = reinterpret_cast<uint64_t*>(sV + Cfg::kTileBytes);
+  // P: [2 k-blocks][128 rows][128 B].  head_dim 64: over the dead Q + K tiles (2 x 16 KB); head_dim 32: its own 32 KB
+  uint8_t* sP = HD == 64 ? sQ : sV + Cfg::kTileBytes;
+  uint8_t* sO = sV;  // [128 rows][kRow] over the dead V tile
+  uint64_t* qk_bar = reinterpret_cast<uint64_t*>(sV + Cfg::kTileBytes + (HD == 64 ? 0 : Cfg::kPBytes));
   uint64_t* v_bar = qk_bar + 1;
   uint64_t* s_bar = qk_bar + 2;
   uint64_t* o_bar = qk_bar + 3;
@@ -357,7 +359,10 @@ attn_fwd_1chunk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
     mbar_wait(qk_bar, 0);
     tc_fence_after();
     constexpr uint32_t idesc1 = umma_idesc_f16(kAttnBQ, kAttnBKV);
-    umma_bf16_kblock64_warp(tmem_base, umma_desc_k_sw128(smem_u32(sQ)), umma_desc_k_sw128(smem_u32(sK)), idesc1, 0u, s_bar);
+    if constexpr (HD == 64)
+      umma_bf16_kblock64_warp(tmem_base, umma_desc_k_sw128(smem_u32(sQ)), umma_desc_k_sw128(smem_u32(sK)), idesc1, 0u, s_bar);
+    else
+      umma_bf16_kblock32_warp(tmem_base, umma_desc_k_sw64(smem_u32(sQ)), umma_desc_k_sw64(smem_u32(sK)), idesc1, 0u, s_bar);
   }
   mbar_wait(s_bar, 0);
   tc_fence_after();
@@ -415,8 +420,8 @@ attn_fwd_1chunk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
     // P is exactly 0 for keys >= kv_len, but 0 * NaN = NaN: the V rows behind a short sequence may be another
     // sequence's data (finite) or, at the tail of a packed batch, never-written memory.  Zero them in smem.
     mbar_wait(v_bar, 0);
-    const int n16 = (kAttnBKV - kv_len) * 8;
-    uint4* bad = reinterpret_cast<uint4*>(sV + kv_len * 128);
+    const int n16 = (kAttnBKV - kv_len) * (kRow / 16);
+    uint4* bad = reinterpret_cast<uint4*>(sV + kv_len * kRow);
     for (int c = tid; c < n16; c += kAttn1Threads) bad[c] = make_uint4(0u, 0u, 0u, 0u);
   }
   fence_proxy_async_smem();  // st.shared P (and V fix-up) -> visible to tcgen05.mma (async proxy)
@@ -429,10 +434,12 @@ attn_fwd_1chunk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
     tc_fence_after();
     constexpr uint32_t idesc2 = umma_idesc_f16(kAttnBQ, HD, 1, false, true);
     const uint64_t pa = umma_desc_k_sw128(smem_u32(sP));
-    const uint64_t vb = umma_desc_mn_sw128(smem_u32(sV), 16);
-    // A: +32 B per step inside a k-block, second k-block 16 KB further; B (MN-major): 16 keys = 2 KB per step
-    umma_bf16_x4_warp(tmem_base, pa, vb, 2u, 128u, idesc2, 0u);
-    umma_bf16_x4_warp(tmem_base, pa + ((kAttnBQ * 128) >> 4), vb + 4u * 128u, 2u, 128u, idesc2, 1u);
+    const uint64_t vb = desc_mn_major<HD>(smem_u32(sV));
+    // A: +32 B per step inside a k-block, second k-block 16 KB further; B (MN-major): 16 keys = two 8-row swizzle
+    // groups = 2 KB (head_dim 64) or 1 KB (head_dim 32) per step
+    constexpr uint32_t kVStep = (2 * Cfg::kGroupBytes) >> 4;
+    umma_bf16_x4_warp(tmem_base, pa, vb, 2u, kVStep, idesc2, 0u);
+    umma_bf16_x4_warp(tmem_base, pa + ((kAttnBQ * 128) >> 4), vb + 4u * kVStep, 2u, kVStep, idesc2, 1u);
     umma_commit_warp(o_bar);
   }
   const float l_tot = l_half + s_l[(half ^ 1u) * kAttnBQ + row];
@@ -440,24 +447,28 @@ attn_fwd_1chunk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
   mbar_wait(o_bar, 0);
   tc_fence_after();
 
-  // ---------------- normalise + store: this thread owns O columns [32*half, 32*half + 32) of its row ----------------
+  // ---------------- normalise + store: this thread owns O columns [HD/2 * half, HD/2 * half + HD/2) of its row ------
   {
-    uint32_t v[32];
-    tmem_ld_32x32b_x32(tmem_base + lane_base + half * 32u, v);
+    constexpr int kCols = HD / 2;       // 32 or 16 fp32 columns per thread
+    uint32_t v[kCols];
+    if constexpr (HD == 64) tmem_ld_32x32b_x32(tmem_base + lane_base + half * kCols, v);
+    else tmem_ld_32x32b_x16(tmem_base + lane_base + half * kCols, v);
     tmem_ld_wait();
-    uint4 q[4];
+    uint4 q[kCols / 8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < kCols / 8; ++j) {
       q[j].x = pack_bf16x2(__uint_as_float(v[8 * j + 0]) * inv, __uint_as_float(v[8 * j + 1]) * inv);
       q[j].y = pack_bf16x2(__uint_as_float(v[8 * j + 2]) * inv, __uint_as_float(v[8 * j + 3]) * inv);
       q[j].z = pack_bf16x2(__uint_as_float(v[8 * j + 4]) * inv, __uint_as_float(v[8 * j + 5]) * inv);
       q[j].w = pack_bf16x2(__uint_as_float(v[8 * j + 6]) * inv, __uint_as_float(v[8 * j + 7]) * inv);
     }
-    // stage the normalised [128 x 64] tile in smem (128B-swizzled rows, over the dead V tile)
+    // stage the normalised [128 x HD] tile in smem over the dead V tile: 128B-swizzled rows for head_dim 64 (the layout
+    // the TMA store expects), plain rows for head_dim 32
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int ch = (static_cast<int>(half) * 4 + j) ^ (row & 7);
-      *reinterpret_cast<uint4*>(sO + row * 128 + (ch << 4)) = q[j];
+    for (int j = 0; j < kCols / 8; ++j) {
+      int ch = static_cast<int>(half) * (kCols / 8) + j;
+      if constexpr (HD == 64) ch ^= (row & 7);
+      *reinterpret_cast<uint4*>(sO + row * kRow + (ch << 4)) = q[j];
     }
   }
   tc_fence_before();
@@ -470,11 +481,13 @@ attn_fwd_1chunk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
       tma_store_wait_read<0>();  // smem must stay valid until the bulk store has read it
     }
   } else {
-    // short / packed sequences: only rows < q_len exist.  8 lanes move one 128-byte row, so a warp writes four
-    // full rows per instruction instead of 32 scattered 16-byte pieces.
-    const int c = tid & 7;
-    for (int r = tid >> 3; r < q_len; r += kAttn1Threads / 8) {
-      const uint4 val = *reinterpret_cast<const uint4*>(sO + r * 128 + ((c ^ (r & 7)) << 4));
+    // short / packed sequences: only rows < q_len exist.  kRow/16 lanes move one row, so a warp writes 4 (or 8) full
+    // rows per instruction instead of 32 scattered 16-byte pieces.
+    constexpr int kLanes = kRow / 16;
+    const int c = tid & (kLanes - 1);
+    for (int r = tid / kLanes; r < q_len; r += kAttn1Threads / kLanes) {
+      const int sc = HD == 64 ? (c ^ (r & 7)) : c;
+      const uint4 val = *reinterpret_cast<const uint4*>(sO + r * kRow + (sc << 4));
       *reinterpret_cast<uint4*>(p.out + static_cast<size_t>(q_row0 + r) * p.ldo + head * HD + c * 8) = val;
     }
   }
@@ -540,8 +553,8 @@ IM_API int im_attn_fwd(const void* q, const void* k, const void* v, void* out, i
                        float scale, const float* rel_bias_log2, void* stream, const int* cu_seqlens) {
   using namespace im;
   if (B <= 0 || Sq <= 0 || Sk <= 0) return 0;
-  if (cu_seqlens != nullptr && !(head_dim == 64 && Sq == Sk && Sk <= kAttnBKV && rel_bias_log2 == nullptr && !causal && scale > 0.f))
-    return set_error("im_attn_fwd", "packed (cu_seqlens) attention: head_dim 64, self-attention, max_seqlen <= 128");
+  if (cu_seqlens != nullptr && !(Sq == Sk && Sk <= kAttnBKV && rel_bias_log2 == nullptr && !causal && scale > 0.f))
+    return set_error("im_attn_fwd", "packed (cu_seqlens) attention: self-attention, max_seqlen <= 128, no bias");
   if (head_dim != 64 && head_dim != 32) return set_error("im_attn_fwd", "head_dim must be 32 or 64");
   if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 8)) return set_error("im_attn_fwd", "row pitches must be multiples of 8");
   const TmapSwizzle sw = head_dim == 64 ? TMAP_SW_128 : TMAP_SW_64;
@@ -568,16 +581,22 @@ IM_API int im_attn_fwd(const void* q, const void* k, const void* v, void* out, i
   const int bias_bytes = rel_bias_log2 ? (Sq + Sk) * 4 : 0;
   dim3 grid((Sq + kAttnBQ - 1) / kAttnBQ, n_heads, B);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (head_dim == 64 && Sk <= kAttnBKV && Sq <= kAttnBQ && rel_bias_log2 == nullptr && scale > 0.f) {
-    // single-chunk fast path; O goes out through TMA when a 128-row box cannot spill into the next sequence
-    const int tma_out = (Sq == kAttnBQ && cu_seqlens == nullptr) ? 1 : 0;
+  if (Sk <= kAttnBKV && Sq <= kAttnBQ && rel_bias_log2 == nullptr && scale > 0.f) {
+    // single-chunk fast path; head_dim 64: O goes out through TMA when a 128-row box cannot spill into the next sequence
+    const int tma_out = (head_dim == 64 && Sq == kAttnBQ && cu_seqlens == nullptr) ? 1 : 0;
     CUtensorMap to = tq;
     if (tma_out &&
         get_tmap_2d(&to, out, static_cast<uint64_t>(B) * Sq, cols, static_cast<uint64_t>(ldo) * 2, kAttnBQ, head_dim, 2, sw))
       return -1;
-    const int smem = 3 * AttnCfg<64>::kTileBytes + 1024 + 64 + 4 * kAttnBQ * 4;
-    IM_CUDA_OK(cudaFuncSetAttribute(attn_fwd_1chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    IM_CUDA_OK(launch_pdl(attn_fwd_1chunk_kernel, dim3(1, n_heads, B), dim3(kAttn1Threads), smem, s, tq, tk, tv, to, p, tma_out));
+    if (head_dim == 64) {
+      const int smem = 3 * AttnCfg<64>::kTileBytes + 1024 + 64 + 4 * kAttnBQ * 4;
+      IM_CUDA_OK(cudaFuncSetAttribute(attn_fwd_1chunk_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      IM_CUDA_OK(launch_pdl(attn_fwd_1chunk_kernel<64>, dim3(1, n_heads, B), dim3(kAttn1Threads), smem, s, tq, tk, tv, to, p, tma_out));
+    } else {
+      const int smem = 3 * AttnCfg<32>::kTileBytes + AttnCfg<32>::kPBytes + 1024 + 64 + 4 * kAttnBQ * 4;
+      IM_CUDA_OK(cudaFuncSetAttribute(attn_fwd_1chunk_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      IM_CUDA_OK(launch_pdl(attn_fwd_1chunk_kernel<32>, dim3(1, n_heads, B), dim3(kAttn1Threads), smem, s, tq, tk, tv, to, p, tma_out));
+    }
   } else if (head_dim == 64) {
     const int smem = 3 * AttnCfg<64>::kTileBytes + (p.alias_p ? 0 : AttnCfg<64>::kPBytes) + 1024 + 64 + bias_bytes;
     IM_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

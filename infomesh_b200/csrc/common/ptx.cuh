@@ -191,6 +191,25 @@ __device__ __forceinline__ void umma_bf16_kblock64_warp(uint32_t tmem_d, uint64_
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate_first), "r"(smem_u32(commit_bar))
       : "memory");
 }
+// 32-wide K block (2 x K=16 bf16 MMAs, e.g. head_dim 32) + commit; same calling convention as umma_bf16_kblock64_warp.
+__device__ __forceinline__ void umma_bf16_kblock32_warp(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                        uint32_t accumulate_first, uint64_t* commit_bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q, pe;\n"
+      ".reg .b64 a1, b1;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "setp.eq.b32 q, %4, %4;\n"
+      "add.s64 a1, %1, 2;\n"
+      "add.s64 b1, %2, 2;\n"
+      "elect.sync _|pe, 0xffffffff;\n"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, q;\n"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate_first), "r"(smem_u32(commit_bar))
+      : "memory");
+}
 // Four bf16 MMAs with register descriptor strides (address-field units of 16 bytes), issued by one elected lane of a
 // converged warp; no commit.  Used where the K steps are not contiguous inside one swizzle atom (P.V in attention).
 __device__ __forceinline__ void umma_bf16_x4_warp(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t a_step,
