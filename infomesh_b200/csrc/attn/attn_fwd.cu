@@ -494,55 +494,118 @@ attn_fwd_1chunk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
-// Single-query decode attention against a KV cache (T5 decoder step): one warp per (batch, head).
-// q: [B, nH*HD]; k/v cache: [B, S_max, nH*HD]; keys [0, kv_len[b]) visible.  CUDA-core, latency-bound by design.
+// Single-query decode attention against a KV cache (T5 decoder step, CLS-only last cross-encoder layer): one warp per
+// (batch, head), ONE KEY PER LANE.  Each lane keeps the query (HD registers), computes whole dot products for keys
+// lane, lane+32, ... with its own online-softmax state and a private HD-wide accumulator; the 32 partial states are
+// merged once at the end (log-sum-exp rescale + warp reductions).  No per-key shuffles -- the earlier
+// one-key-per-iteration version spent ~100 us on 256 keys in its dependent shuffle chain.
+// q: [B, nH*HD]; k/v cache: [B, S_max, nH*HD]; keys [0, kv_len[b]) visible.
 template <int HD>
 __global__ void __launch_bounds__(128)
 attn_decode_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ kc,
                    const __nv_bfloat16* __restrict__ vc, int ld_kv, int s_max, const int* __restrict__ kv_lens,
                    int kv_len_all, float scale_log2, const float* __restrict__ rel_bias, int bias_len, int q_pos,
                    int n_heads, int n_pairs, __nv_bfloat16* __restrict__ out, int ldo,
-                   const int* __restrict__ seq_start) {
+                   const int* __restrict__ seq_start, const int* __restrict__ step_dev) {
   const int pair = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (pair >= n_pairs) return;
   const int b = pair / n_heads, h = pair % n_heads;
+  // step_dev: decode step t kept on the device (CUDA-graph replay of one decoder step): keys [0, t], query position t
+  if (step_dev != nullptr) {
+    q_pos = *step_dev;
+    kv_len_all = q_pos + 1;
+  }
   const int len = kv_lens ? kv_lens[b] : kv_len_all;
-  constexpr int PER = HD / 32;  // dims per lane (1 or 2)
-  float qv[PER];
+  float qv[HD];
+  {
+    const uint4* qp = reinterpret_cast<const uint4*>(q + static_cast<size_t>(b) * ldq + h * HD);
 #pragma unroll
-  for (int i = 0; i < PER; ++i) qv[i] = __bfloat162float(q[static_cast<size_t>(b) * ldq + h * HD + lane * PER + i]);
-  float m = kNegBig, l = 0.f, acc[PER];
+    for (int c = 0; c < HD / 8; ++c) {
+      const uint4 u = __ldg(qp + c);
+      const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+      qv[8 * c + 0] = f0.x; qv[8 * c + 1] = f0.y; qv[8 * c + 2] = f1.x; qv[8 * c + 3] = f1.y;
+      qv[8 * c + 4] = f2.x; qv[8 * c + 5] = f2.y; qv[8 * c + 6] = f3.x; qv[8 * c + 7] = f3.y;
+    }
+  }
+  float m = kNegBig, l = 0.f, acc[HD];
 #pragma unroll
-  for (int i = 0; i < PER; ++i) acc[i] = 0.f;
+  for (int i = 0; i < HD; ++i) acc[i] = 0.f;
   // seq_start: keys of sequence b begin at row seq_start[b] of a packed (unpadded) K/V buffer instead of b * s_max
   const size_t row0 = seq_start != nullptr ? static_cast<size_t>(seq_start[b]) : static_cast<size_t>(b) * s_max;
   const __nv_bfloat16* kb = kc + row0 * ld_kv + h * HD;
   const __nv_bfloat16* vb = vc + row0 * ld_kv + h * HD;
-  for (int j = 0; j < len; ++j) {
+  for (int j = lane; j < len; j += 32) {
+    const uint4* kr = reinterpret_cast<const uint4*>(kb + static_cast<size_t>(j) * ld_kv);
     float d = 0.f;
 #pragma unroll
-    for (int i = 0; i < PER; ++i) d += qv[i] * __bfloat162float(kb[static_cast<size_t>(j) * ld_kv + lane * PER + i]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-    float s = d * scale_log2;
+    for (int c = 0; c < HD / 8; ++c) {
+      const uint4 u = kr[c];
+      const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+      d = fmaf(qv[8 * c + 0], f0.x, d); d = fmaf(qv[8 * c + 1], f0.y, d);
+      d = fmaf(qv[8 * c + 2], f1.x, d); d = fmaf(qv[8 * c + 3], f1.y, d);
+      d = fmaf(qv[8 * c + 4], f2.x, d); d = fmaf(qv[8 * c + 5], f2.y, d);
+      d = fmaf(qv[8 * c + 6], f3.x, d); d = fmaf(qv[8 * c + 7], f3.y, d);
+    }
+    float sc = d * scale_log2;
     if (rel_bias) {
       int bi = j - q_pos + (bias_len - 1) / 2;  // table centred on relative position 0
       bi = max(0, min(bias_len - 1, bi));
-      s += rel_bias[static_cast<size_t>(h) * bias_len + bi];
+      sc += rel_bias[static_cast<size_t>(h) * bias_len + bi];
     }
-    const float m_new = fmaxf(m, s);
-    const float a = exp2f(m - m_new), pj = exp2f(s - m_new);
-    l = l * a + pj;
-#pragma unroll
-    for (int i = 0; i < PER; ++i)
-      acc[i] = acc[i] * a + pj * __bfloat162float(vb[static_cast<size_t>(j) * ld_kv + lane * PER + i]);
+    const float m_new = fmaxf(m, sc);
+    const float a = exp2f(m - m_new), pj = exp2f(sc - m_new);
+    l = fmaf(l, a, pj);
     m = m_new;
+    const uint4* vr = reinterpret_cast<const uint4*>(vb + static_cast<size_t>(j) * ld_kv);
+#pragma unroll
+    for (int c = 0; c < HD / 8; ++c) {
+      const uint4 u = vr[c];
+      const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+      acc[8 * c + 0] = fmaf(acc[8 * c + 0], a, pj * f0.x); acc[8 * c + 1] = fmaf(acc[8 * c + 1], a, pj * f0.y);
+      acc[8 * c + 2] = fmaf(acc[8 * c + 2], a, pj * f1.x); acc[8 * c + 3] = fmaf(acc[8 * c + 3], a, pj * f1.y);
+      acc[8 * c + 4] = fmaf(acc[8 * c + 4], a, pj * f2.x); acc[8 * c + 5] = fmaf(acc[8 * c + 5], a, pj * f2.y);
+      acc[8 * c + 6] = fmaf(acc[8 * c + 6], a, pj * f3.x); acc[8 * c + 7] = fmaf(acc[8 * c + 7], a, pj * f3.y);
+    }
   }
-  const float inv = l > 0.f ? 1.f / l : 0.f;
+  // merge the 32 per-lane softmax states
+  float m_all = m;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m_all = fmaxf(m_all, __shfl_xor_sync(0xffffffffu, m_all, o));
+  const float f = exp2f(m - m_all);   // lanes that saw no key: m = kNegBig -> 0
+  float l_all = l * f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) l_all += __shfl_xor_sync(0xffffffffu, l_all, o);
+  const float inv = l_all > 0.f ? 1.f / l_all : 0.f;
+  constexpr int PER = HD / 32;  // output dims written per lane (1 or 2)
+  float mine[PER];
+#pragma unroll
+  for (int i = 0; i < HD; ++i) {
+    float t = acc[i] * f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (i / PER == lane) mine[i % PER] = t;
+  }
 #pragma unroll
   for (int i = 0; i < PER; ++i)
-    out[static_cast<size_t>(b) * ldo + h * HD + lane * PER + i] = __float2bfloat16(acc[i] * inv);
+    out[static_cast<size_t>(b) * ldo + h * HD + lane * PER + i] = __float2bfloat16(mine[i] * inv);
+}
+
+// Decoder KV-cache append with the step on the device: row *step_dev of sequence b in kc / vc <- the K / V slices of
+// this step's fused QKV row (one block per sequence).  Lets one decoder step replay from a CUDA graph.
+__global__ void __launch_bounds__(128)
+kv_append_kernel(const __nv_bfloat16* __restrict__ qkv, int ld_qkv, int inner, __nv_bfloat16* __restrict__ kc,
+                 __nv_bfloat16* __restrict__ vc, int s_max, const int* __restrict__ step_dev) {
+  const int b = blockIdx.x, t = *step_dev;
+  if (t < 0 || t >= s_max) return;
+  const uint4* src_k = reinterpret_cast<const uint4*>(qkv + static_cast<size_t>(b) * ld_qkv + inner);
+  const uint4* src_v = reinterpret_cast<const uint4*>(qkv + static_cast<size_t>(b) * ld_qkv + 2 * inner);
+  uint4* dst_k = reinterpret_cast<uint4*>(kc + (static_cast<size_t>(b) * s_max + t) * inner);
+  uint4* dst_v = reinterpret_cast<uint4*>(vc + (static_cast<size_t>(b) * s_max + t) * inner);
+  for (int c = threadIdx.x; c < inner / 8; c += blockDim.x) {
+    dst_k[c] = src_k[c];
+    dst_v[c] = src_v[c];
+  }
 }
 
 }  // namespace im
@@ -613,7 +676,7 @@ IM_API int im_attn_fwd(const void* q, const void* k, const void* v, void* out, i
 IM_API int im_attn_decode(const void* q, int ldq, const void* kc, const void* vc, int ld_kv, int s_max,
                           const int* kv_lens, int kv_len_all, float scale, const float* rel_bias_log2, int bias_len,
                           int q_pos, int B, int n_heads, int head_dim, void* out, int ldo, void* stream,
-                          const int* seq_start) {
+                          const int* seq_start, const int* step_dev) {
   using namespace im;
   const int n_pairs = B * n_heads;
   if (n_pairs <= 0) return 0;
@@ -623,13 +686,25 @@ IM_API int im_attn_decode(const void* q, int ldq, const void* kc, const void* vc
   if (head_dim == 64)
     attn_decode_kernel<64><<<grid, 128, 0, s>>>((const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)kc,
                                                (const __nv_bfloat16*)vc, ld_kv, s_max, kv_lens, kv_len_all, sl2,
-                                               rel_bias_log2, bias_len, q_pos, n_heads, n_pairs, (__nv_bfloat16*)out, ldo, seq_start);
+                                               rel_bias_log2, bias_len, q_pos, n_heads, n_pairs, (__nv_bfloat16*)out, ldo, seq_start, step_dev);
   else if (head_dim == 32)
     attn_decode_kernel<32><<<grid, 128, 0, s>>>((const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)kc,
                                                (const __nv_bfloat16*)vc, ld_kv, s_max, kv_lens, kv_len_all, sl2,
-                                               rel_bias_log2, bias_len, q_pos, n_heads, n_pairs, (__nv_bfloat16*)out, ldo, seq_start);
+                                               rel_bias_log2, bias_len, q_pos, n_heads, n_pairs, (__nv_bfloat16*)out, ldo, seq_start, step_dev);
   else
     return set_error("im_attn_decode", "head_dim must be 32 or 64");
   IM_LAUNCH_OK("attn_decode_kernel");
+  return 0;
+}
+
+IM_API int im_kv_append(const void* qkv, int ld_qkv, int inner, void* kc, void* vc, int s_max, int B, const int* step_dev,
+                        void* stream) {
+  using namespace im;
+  if (B <= 0) return 0;
+  if (inner % 8 || ld_qkv % 8) return set_error("im_kv_append", "inner and the qkv pitch must be multiples of 8");
+  kv_append_kernel<<<B, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>((const __nv_bfloat16*)qkv, ld_qkv, inner,
+                                                                         (__nv_bfloat16*)kc, (__nv_bfloat16*)vc, s_max,
+                                                                         step_dev);
+  IM_LAUNCH_OK("kv_append_kernel");
   return 0;
 }

@@ -322,15 +322,30 @@ cls_head_kernel(const __nv_bfloat16* __restrict__ h, int seq_len, int H, const _
 }
 
 // (max, argmax) of each fp32 row; id_offset added so vocab-parallel shards report global ids
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 row_argmax_kernel(const float* __restrict__ x, int n_cols, int ld, int id_offset, float* __restrict__ out_val,
                   int* __restrict__ out_idx) {
-  __shared__ float rv[8];
-  __shared__ int ri[8];
+  __shared__ float rv[32];
+  __shared__ int ri[32];
   const float* row = x + static_cast<size_t>(blockIdx.x) * ld;
   float bv = -CUDART_INF_F;
   int bi = 0x7fffffff;
-  for (int c = threadIdx.x; c < n_cols; c += blockDim.x) {
+  // greedy decoding has few rows (= batch) and a 32k-wide vocabulary: 1024 threads and 16-byte loads per row
+  const bool vec = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15u) == 0);
+  const int n4 = vec ? n_cols / 4 : 0;
+  for (int c4 = threadIdx.x; c4 < n4; c4 += blockDim.x) {
+    const float4 v4 = *reinterpret_cast<const float4*>(row + 4 * c4);
+    const float vs[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = 4 * c4 + k;
+      if (vs[k] > bv || (vs[k] == bv && c < bi)) {
+        bv = vs[k];
+        bi = c;
+      }
+    }
+  }
+  for (int c = 4 * n4 + threadIdx.x; c < n_cols; c += blockDim.x) {
     const float v = row[c];
     if (v > bv || (v == bv && c < bi)) {
       bv = v;
@@ -486,8 +501,8 @@ IM_API int im_row_argmax(const float* x, int n_rows, int n_cols, int ld, int id_
                          void* stream) {
   using namespace im;
   if (n_rows <= 0) return 0;
-  row_argmax_kernel<<<n_rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, n_cols, ld, id_offset, out_val,
-                                                                               out_idx);
+  row_argmax_kernel<<<n_rows, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, n_cols, ld, id_offset, out_val,
+                                                                                out_idx);
   IM_LAUNCH_OK("row_argmax_kernel");
   return 0;
 }

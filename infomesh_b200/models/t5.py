@@ -153,41 +153,64 @@ class T5Model:
     # ------------------------------------------------------------------ greedy decode
     @torch.no_grad()
     def generate(self, ids: torch.Tensor, lengths: torch.Tensor | None = None, max_new_tokens: int = 64,
-                 check_every: int = 16) -> torch.Tensor:
-        """Greedy decoding.  Returns int32 [B, T] (T <= max_new_tokens), positions after EOS filled with pad."""
+                 check_every: int = 16, use_graph: bool = True) -> torch.Tensor:
+        """Greedy decoding.  Returns int32 [B, T] (T <= max_new_tokens), positions after EOS filled with pad.
+
+        One decoder step is ~75 small kernels; launched eagerly it is bound by Python/launch overhead (~1.7 ms/step).
+        With ``use_graph`` the step is captured once per ``(B, S, T)`` shape -- the step counter lives on the device (KV-cache
+        append, self-attention length and relative-position offset all read it there), decode buffers are cached on the
+        model -- and replayed ``T`` times per call."""
         from infomesh_b200.ops import attention as A
         from infomesh_b200.ops import gemm as G
         from infomesh_b200.ops import nn as N
+
+        from types import SimpleNamespace
 
         cfg, w = self.cfg, self.w
         B, S = ids.shape
         inner, d = cfg.inner, cfg.d_model
         dev = self.device
-        if lengths is None:
-            lengths = torch.full((B,), S, dtype=torch.int32, device=dev)
-        enc = self.encode(ids, lengths).view(B * S, d)
         T = max_new_tokens
-        # cross-attention K/V once per layer; self-attention caches grow by one row per step
-        xk = [G.linear(enc, lay["wkv_x"]).view(B, S, 2 * inner) for lay in w.dec]
-        kc = [torch.zeros((B, T, inner), device=dev, dtype=torch.bfloat16) for _ in w.dec]
-        vc = [torch.zeros((B, T, inner), device=dev, dtype=torch.bfloat16) for _ in w.dec]
-        bias = self._dec_bias_table(T)
-        tok = torch.full((B,), cfg.decoder_start_id, dtype=torch.long, device=dev)
-        done = torch.zeros((B,), dtype=torch.bool, device=dev)
-        out = torch.full((B, T), cfg.pad_id, dtype=torch.int32, device=dev)
         alpha = d ** -0.5
-        for t in range(T):
-            x = w.emb[tok]                                                   # [B, d]
+        # decode state (static buffers + the captured step graph) is cached per shape: capture costs ~30 ms, a step ~0.3
+        cache = self.__dict__.setdefault("_dec_states", {})
+        st = cache.get((B, S, T))
+        if st is None:
+            st = SimpleNamespace(
+                lengths=torch.empty((B,), dtype=torch.int32, device=dev),
+                xk=[torch.empty((B * S, 2 * inner), device=dev, dtype=torch.bfloat16) for _ in w.dec],
+                kc=[torch.zeros((B, T, inner), device=dev, dtype=torch.bfloat16) for _ in w.dec],
+                vc=[torch.zeros((B, T, inner), device=dev, dtype=torch.bfloat16) for _ in w.dec],
+                bias=self._dec_bias_table(T),
+                tok=torch.empty((B,), dtype=torch.long, device=dev), done=torch.empty((B,), dtype=torch.bool, device=dev),
+                out=torch.empty((B, T), dtype=torch.int32, device=dev), step=torch.zeros((1,), dtype=torch.int32, device=dev),
+                col=torch.arange(T, device=dev, dtype=torch.int32)[None, :],
+                pad=torch.full((B,), cfg.pad_id, dtype=torch.int32, device=dev), graph=None, graph_failed=False)
+            if len(cache) >= 4:
+                cache.pop(next(iter(cache)))
+            cache[(B, S, T)] = st
+        st.lengths.copy_(lengths if lengths is not None else torch.full((B,), S, dtype=torch.int32, device=dev))
+        enc = self.encode(ids, st.lengths).view(B * S, d)
+        for li, lay in enumerate(w.dec):                       # cross-attention K/V once per layer
+            G.linear(enc, lay["wkv_x"], out=st.xk[li])
+        st.tok.fill_(cfg.decoder_start_id)
+        st.done.fill_(False)
+        st.out.fill_(cfg.pad_id)
+        st.step.zero_()
+        xk = [x.view(B, S, 2 * inner) for x in st.xk]
+
+        def one_step():
+            x = w.emb[st.tok]                                                # [B, d]
             for li, lay in enumerate(w.dec):
                 n1 = N.layernorm(x, lay["ln1"], None, cfg.eps, rms_only=True)
                 qkv = G.linear(n1, lay["wqkv"])
-                kc[li][:, t] = qkv[:, inner:2 * inner]
-                vc[li][:, t] = qkv[:, 2 * inner:]
-                ctx = A.attention_decode(qkv[:, :inner], kc[li], vc[li], cfg.heads, t + 1, scale=1.0, rel_bias_log2=bias, q_pos=t)
+                A.kv_append(qkv, st.kc[li], st.vc[li], st.step)               # self-attention caches grow by one row
+                ctx = A.attention_decode(qkv[:, :inner], st.kc[li], st.vc[li], cfg.heads, 0, scale=1.0,
+                                         rel_bias_log2=st.bias, step_dev=st.step)
                 x = G.linear(ctx, lay["wo"], residual=x)
                 nx = N.layernorm(x, lay["ln_x"], None, cfg.eps, rms_only=True)
                 qx = G.linear(nx, lay["wq_x"])
-                cx = A.attention_decode(qx, xk[li][..., :inner], xk[li][..., inner:], cfg.heads, lengths, scale=1.0)
+                cx = A.attention_decode(qx, xk[li][..., :inner], xk[li][..., inner:], cfg.heads, st.lengths, scale=1.0)
                 x = G.linear(cx, lay["wo_x"], residual=x)
                 n2 = N.layernorm(x, lay["ln2"], None, cfg.eps, rms_only=True)
                 h = G.linear(n2, lay["wi"], act="relu")
@@ -195,13 +218,37 @@ class T5Model:
             xf = N.layernorm(x, w.dec_final, None, cfg.eps, rms_only=True)
             logits = G.linear(xf, w.emb, alpha=alpha, out_dtype=torch.float32)
             _, nxt = N.row_argmax(logits)
-            nxt = torch.where(done, torch.full_like(nxt, cfg.pad_id), nxt)
-            out[:, t] = nxt
-            done = done | (nxt == cfg.eos_id)
-            tok = nxt.long()
-            if (t + 1) % check_every == 0 and bool(done.all()):
-                return out[:, :t + 1]
-        return out
+            nxt = torch.where(st.done, st.pad, nxt.to(torch.int32))
+            st.out.copy_(torch.where(st.col == st.step, nxt[:, None], st.out))   # out[:, t] = nxt with t on the device
+            st.done.logical_or_(nxt == cfg.eos_id)
+            st.tok.copy_(nxt)
+            st.step.add_(1)
+
+        t0 = 0
+        if use_graph and T > 2 and st.graph is None and not st.graph_failed:
+            one_step()                                                       # step 0 runs eagerly (also the warm-up)
+            t0 = 1
+            torch.cuda.synchronize()
+            try:
+                s = torch.cuda.Stream(device=dev)
+                s.wait_stream(torch.cuda.current_stream())
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=s):
+                    one_step()
+                torch.cuda.current_stream().wait_stream(s)
+                st.graph = g
+            except Exception:  # noqa: BLE001 — eager fallback
+                st.graph_failed = True
+                torch.cuda.synchronize()
+        graph = st.graph if use_graph else None
+        for t in range(t0, T):
+            if graph is not None:
+                graph.replay()
+            else:
+                one_step()
+            if (t + 1) % check_every == 0 and bool(st.done.all()):
+                return st.out[:, :t + 1].clone()
+        return st.out.clone()
 
     # ------------------------------------------------------------------ fp32 PyTorch oracle
     def _attn_ref(self, q, k, v, bias, mask):

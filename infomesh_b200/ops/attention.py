@@ -78,11 +78,13 @@ def attention(q, k, v, n_heads, kv_lens=None, causal=False, causal_offset=0, sca
 
 
 def attention_decode(q, k_cache, v_cache, n_heads, kv_len, scale=None, rel_bias_log2=None, q_pos=0, out=None,
-                     seq_start=None):
+                     seq_start=None, step_dev=None):
     """One query token per sequence against a KV cache ``[B, S_max, nH*hd]``; ``kv_len`` int or int32 tensor.
 
     ``seq_start`` (int32 ``[B]``): the caches are one packed ``[1, rows, nH*hd]`` buffer and sequence b's keys start
-    at row ``seq_start[b]`` (CLS-only last layer of an unpadded cross-encoder)."""
+    at row ``seq_start[b]`` (CLS-only last layer of an unpadded cross-encoder).  ``step_dev`` (int32 ``[1]``): decode
+    step ``t`` read on the device -- keys ``[0, t]``, query position ``t`` -- so one decoder step can replay from a
+    CUDA graph."""
     B, HH = q.shape
     hd = HH // n_heads
     s_max = k_cache.shape[1]
@@ -97,7 +99,21 @@ def attention_decode(q, k_cache, v_cache, n_heads, kv_len, scale=None, rel_bias_
                           ctypes.c_int(0 if lens_t is not None else int(kv_len)), ctypes.c_float(scale),
                           _native.ptr(rel_bias_log2), ctypes.c_int(bias_len), ctypes.c_int(q_pos), ctypes.c_int(B),
                           ctypes.c_int(n_heads), ctypes.c_int(hd), _native.ptr(out), ctypes.c_int(out.stride(0)),
-                          _native.stream_ptr(), _native.ptr(seq_start))
+                          _native.stream_ptr(), _native.ptr(seq_start), _native.ptr(step_dev))
     _native.check(rc, "im_attn_decode")
     _native.count_launch()
     return out
+
+
+def kv_append(qkv, k_cache, v_cache, step_dev):
+    """``k_cache[:, t] / v_cache[:, t] <- qkv[:, inner:2*inner] / qkv[:, 2*inner:]`` with ``t = step_dev[0]`` read on the
+    device.  ``qkv``: bf16 ``[B, 3*inner]``; caches: contiguous ``[B, S_max, inner]``."""
+    B, three = qkv.shape
+    inner = three // 3
+    assert k_cache.is_contiguous() and v_cache.is_contiguous() and k_cache.shape == (B, k_cache.shape[1], inner)
+    L = _native.require()
+    rc = L.im_kv_append(_native.ptr(qkv), ctypes.c_int(qkv.stride(0)), ctypes.c_int(inner), _native.ptr(k_cache),
+                        _native.ptr(v_cache), ctypes.c_int(k_cache.shape[1]), ctypes.c_int(B), _native.ptr(step_dev),
+                        _native.stream_ptr())
+    _native.check(rc, "im_kv_append")
+    _native.count_launch()
