@@ -288,7 +288,8 @@ template <int HD>
 __global__ void __launch_bounds__(kAttn1Threads, HD == 64 ? 4 : 3)
 attn_fwd_1chunk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                        const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o,
-                       const AttnParams p, int tma_out) {
+                       const __grid_constant__ CUtensorMap tmap_q32, const __grid_constant__ CUtensorMap tmap_k32,
+                       const __grid_constant__ CUtensorMap tmap_v32, const AttnParams p, int tma_out, int sub_boxes) {
   using Cfg = AttnCfg<HD>;
   constexpr int kRow = Cfg::kRowBytes;  // bytes per Q/K/V/O row: 128 (SW128 tiles) or 64 (SW64 tiles)
   extern __shared__ uint8_t smem_raw[];
@@ -320,6 +321,11 @@ attn_fwd_1chunk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
     tma_prefetch_desc(&tmap_k);
     tma_prefetch_desc(&tmap_v);
     if (tma_out) tma_prefetch_desc(&tmap_o);
+    if (sub_boxes) {
+      tma_prefetch_desc(&tmap_q32);
+      tma_prefetch_desc(&tmap_k32);
+      tma_prefetch_desc(&tmap_v32);
+    }
     mbar_init(qk_bar, 1);
     mbar_init(v_bar, 1);
     mbar_init(s_bar, 1);
@@ -348,11 +354,24 @@ attn_fwd_1chunk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(qk_bar, 2 * Cfg::kTileBytes);
-      tma_load_2d(sQ, &tmap_q, qk_bar, head * HD, q_row0);
-      tma_load_2d(sK, &tmap_k, qk_bar, head * HD, kv_row0);
-      mbar_expect_tx(v_bar, Cfg::kTileBytes);
-      tma_load_2d(sV, &tmap_v, v_bar, head * HD, kv_row0);
+      const int qg = (min(q_len, kAttnBQ) + 31) >> 5, kg = (kv_len + 31) >> 5;  // 32-row groups that hold real rows
+      if (sub_boxes && (qg < 4 || kg < 4)) {
+        // short sequence: fetch only the 32-row groups that contain its rows (the 32-row boxes land at the same smem
+        // offsets a 128-row box would use; the swizzle pattern repeats every 8 rows).  Whatever stale data sits in the
+        // groups that are not loaded is masked (K), zeroed (V, below) or belongs to rows that are never stored (Q).
+        constexpr int kGroup = 32 * kRow;
+        mbar_expect_tx(qk_bar, (qg + kg) * kGroup);
+        for (int g = 0; g < qg; ++g) tma_load_2d(sQ + g * kGroup, &tmap_q32, qk_bar, head * HD, q_row0 + 32 * g);
+        for (int g = 0; g < kg; ++g) tma_load_2d(sK + g * kGroup, &tmap_k32, qk_bar, head * HD, kv_row0 + 32 * g);
+        mbar_expect_tx(v_bar, kg * kGroup);
+        for (int g = 0; g < kg; ++g) tma_load_2d(sV + g * kGroup, &tmap_v32, v_bar, head * HD, kv_row0 + 32 * g);
+      } else {
+        mbar_expect_tx(qk_bar, 2 * Cfg::kTileBytes);
+        tma_load_2d(sQ, &tmap_q, qk_bar, head * HD, q_row0);
+        tma_load_2d(sK, &tmap_k, qk_bar, head * HD, kv_row0);
+        mbar_expect_tx(v_bar, Cfg::kTileBytes);
+        tma_load_2d(sV, &tmap_v, v_bar, head * HD, kv_row0);
+      }
     }
     __syncwarp();
     // ---------------- MMA1: S[128q x 128k] = Q K^T (one 64-wide K block) ----------------
@@ -651,14 +670,24 @@ IM_API int im_attn_fwd(const void* q, const void* k, const void* v, void* out, i
     if (tma_out &&
         get_tmap_2d(&to, out, static_cast<uint64_t>(B) * Sq, cols, static_cast<uint64_t>(ldo) * 2, kAttnBQ, head_dim, 2, sw))
       return -1;
+    // 32-row boxes for sequences that do not fill the 128-row tile (kv_lens / cu_seqlens known only on the device)
+    const int sub_boxes = (kv_lens != nullptr || cu_seqlens != nullptr || Sq < kAttnBQ) ? 1 : 0;
+    CUtensorMap tq32 = tq, tk32 = tk, tv32 = tv;
+    if (sub_boxes) {
+      if (get_tmap_2d(&tq32, q, static_cast<uint64_t>(B) * Sq, cols, static_cast<uint64_t>(ldq) * 2, 32, head_dim, 2, sw)) return -1;
+      if (get_tmap_2d(&tk32, k, static_cast<uint64_t>(B) * Sk, cols, static_cast<uint64_t>(ldk) * 2, 32, head_dim, 2, sw)) return -1;
+      if (get_tmap_2d(&tv32, v, static_cast<uint64_t>(B) * Sk, cols, static_cast<uint64_t>(ldv) * 2, 32, head_dim, 2, sw)) return -1;
+    }
     if (head_dim == 64) {
       const int smem = 3 * AttnCfg<64>::kTileBytes + 1024 + 64 + 4 * kAttnBQ * 4;
       IM_CUDA_OK(cudaFuncSetAttribute(attn_fwd_1chunk_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      IM_CUDA_OK(launch_pdl(attn_fwd_1chunk_kernel<64>, dim3(1, n_heads, B), dim3(kAttn1Threads), smem, s, tq, tk, tv, to, p, tma_out));
+      IM_CUDA_OK(launch_pdl(attn_fwd_1chunk_kernel<64>, dim3(1, n_heads, B), dim3(kAttn1Threads), smem, s, tq, tk, tv, to, tq32,
+                            tk32, tv32, p, tma_out, sub_boxes));
     } else {
       const int smem = 3 * AttnCfg<32>::kTileBytes + AttnCfg<32>::kPBytes + 1024 + 64 + 4 * kAttnBQ * 4;
       IM_CUDA_OK(cudaFuncSetAttribute(attn_fwd_1chunk_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      IM_CUDA_OK(launch_pdl(attn_fwd_1chunk_kernel<32>, dim3(1, n_heads, B), dim3(kAttn1Threads), smem, s, tq, tk, tv, to, p, tma_out));
+      IM_CUDA_OK(launch_pdl(attn_fwd_1chunk_kernel<32>, dim3(1, n_heads, B), dim3(kAttn1Threads), smem, s, tq, tk, tv, to, tq32,
+                            tk32, tv32, p, tma_out, sub_boxes));
     }
   } else if (head_dim == 64) {
     const int smem = 3 * AttnCfg<64>::kTileBytes + (p.alias_p ? 0 : AttnCfg<64>::kPBytes) + 1024 + 64 + bias_bytes;
