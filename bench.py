@@ -120,6 +120,8 @@ def main() -> int:
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-varlen", action="store_true", help="run the cross-encoder on padded [pairs, seq_len] batches")
     ap.add_argument("--no-padded-arm", action="store_true", help="skip the extra padded-cross-encoder measurement")
+    ap.add_argument("--precision", choices=["bf16", "fp8"], default="bf16",
+                    help="fp8: cross-encoder projections as e4m3 GEMMs (reported as dtype fp8; NOT the headline config)")
     ap.add_argument("--rerank-chunks", type=int, default=1, help="cross-encoder sub-batches per step (L2 residency)")
     ap.add_argument("--pipeline", choices=["auto", "on", "off"], default="auto",
                     help="keep two batches in flight (retrieval of batch i+1 overlaps the cross-encoder of batch i); "
@@ -160,7 +162,7 @@ def main() -> int:
     build_s = time.time() - t0
 
     hcfg = HybridConfig(nq=args.batch, pair_seq=args.pair_seq, rerank=not args.no_rerank, backend=args.impl,
-                        use_graph=not args.no_graph, exchange=args.exchange, varlen=not args.no_varlen, rerank_chunks=args.rerank_chunks)
+                        use_graph=not args.no_graph, exchange=args.exchange, varlen=not args.no_varlen, rerank_chunks=args.rerank_chunks, precision=args.precision)
     eng = HybridEngine(shard, hcfg, docs_per_shard=(n_global if world > 1 else n_local))
 
     # ---- query batches on pinned host memory (distinct per step so nothing is cached between iterations) ----
@@ -322,7 +324,7 @@ def main() -> int:
             "higher_is_better": True,
             "scaling": "strong",
             "vs_baseline": None,
-            "dtype": "bf16",
+            "dtype": "bf16" if args.precision == "bf16" else "fp8-e4m3 projections in the cross-encoder (fp32 accumulate), bf16 elsewhere",
             "data": "synthetic (Zipfian 10M-doc corpus, random unit vectors, random-init weights)",
             "impl": args.impl,
             "config": {

@@ -191,6 +191,33 @@ __device__ __forceinline__ void umma_bf16_kblock64_warp(uint32_t tmem_d, uint64_
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate_first), "r"(smem_u32(commit_bar))
       : "memory");
 }
+// fp8 (e4m3 / e5m2) flavour of umma_bf16_kblock64_warp: one 128-BYTE K block = 4 x (K = 32 fp8) kind::f8f6f4 MMAs.
+// Same smem tiles (128-byte swizzled rows) and the same +32-byte descriptor step as the bf16 version -- only the
+// instruction kind, the instruction descriptor and the number of elements per row differ.
+__device__ __forceinline__ void umma_f8_kblock128_warp(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                       uint32_t accumulate_first, uint64_t* commit_bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q, pe;\n"
+      ".reg .b64 a1, a2, a3, b1, b2, b3;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "setp.eq.b32 q, %4, %4;\n"
+      "add.s64 a1, %1, 2;\n"
+      "add.s64 b1, %2, 2;\n"
+      "add.s64 a2, %1, 4;\n"
+      "add.s64 b2, %2, 4;\n"
+      "add.s64 a3, %1, 6;\n"
+      "add.s64 b3, %2, 6;\n"
+      "elect.sync _|pe, 0xffffffff;\n"
+      "@pe tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n"
+      "@pe tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], a1, b1, %3, q;\n"
+      "@pe tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], a2, b2, %3, q;\n"
+      "@pe tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], a3, b3, %3, q;\n"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate_first), "r"(smem_u32(commit_bar))
+      : "memory");
+}
 // 32-wide K block (2 x K=16 bf16 MMAs, e.g. head_dim 32) + commit; same calling convention as umma_bf16_kblock64_warp.
 __device__ __forceinline__ void umma_bf16_kblock32_warp(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                                         uint32_t accumulate_first, uint64_t* commit_bar) {

@@ -38,6 +38,8 @@ struct GemmEpilogue {
   uint32_t* a_state;        // {use, done}: block m is loadable once a_ready[m] >= (use + 1) * rows_in_block(m);
                             // the last CTA out advances `use` (see comm/symm.cu for the protocol)
   int m_rotate;             // first row block processed (so the local shard goes first)
+  int fp8;                  // A and B are e4m3 bytes (kind::f8f6f4, 128 elements per K block); C / bias / residual as usual
+  const float* row_scale;   // optional per-row (per-token) dequantisation scale multiplied into alpha
   const int* m_dev;         // optional device-side row count (unpadded / varlen batches inside a CUDA graph): rows
                             // beyond min(M, *m_dev) are neither loaded nor computed
 };
@@ -136,7 +138,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (ep.m_dev != nullptr) M = min(M, max(0, *ep.m_dev));
   const int num_m = (M + kBM - 1) / kBM;
   const int num_n = (N + BN - 1) / BN;
-  const int num_k = (K + kBK - 1) / kBK;
+  const int kbk = ep.fp8 ? 2 * kBK : kBK;  // elements per 128-byte K block
+  const int num_k = (K + kbk - 1) / kbk;
   const int num_tiles = num_m * num_n;
 
   if (warp == 0) {
@@ -163,8 +166,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + kBM * kBK * 2;
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBK, m_blk * kBM);
-          tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * kBK, n_blk * BN);
+          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kbk, m_blk * kBM);
+          tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * kbk, n_blk * BN);
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1;
@@ -176,7 +179,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // ------------------------------- MMA issuer ---------------------------------
     // The whole warp runs the loop (warp-uniform control flow); one elected lane issues (see umma_bf16_kblock64_warp).
     {
-      constexpr uint32_t idesc = umma_idesc_f16(kBM, BN);
+      const uint32_t idesc = ep.fp8 ? umma_idesc_f8(kBM, BN) : umma_idesc_f16(kBM, BN);
       static_assert(kBK == 64, "umma_bf16_kblock64_warp issues exactly one 64-wide K block");
       // stage s operands live at smem + s * kStageBytes (A) / + kBM*kBK*2 (B): descriptors differ only in the
       // address field (16-byte units), so they are built once and stepped with integer adds
@@ -191,7 +194,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint64_t soff = static_cast<uint64_t>(stage * (Cfg::kStageBytes >> 4));
-          umma_bf16_kblock64_warp(d_tmem, a_desc0 + soff, b_desc0 + soff, idesc, kb != 0 ? 1u : 0u, &empty_bar[stage]);
+          if (ep.fp8)
+            umma_f8_kblock128_warp(d_tmem, a_desc0 + soff, b_desc0 + soff, idesc, kb != 0 ? 1u : 0u, &empty_bar[stage]);
+          else
+            umma_bf16_kblock64_warp(d_tmem, a_desc0 + soff, b_desc0 + soff, idesc, kb != 0 ? 1u : 0u, &empty_bar[stage]);
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1;
@@ -220,6 +226,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       tc_fence_after();
       const int row = m_blk * kBM + static_cast<int>(row_in_tile);
       const bool row_ok = row < M;
+      const float alpha_row = (ep.row_scale != nullptr && row_ok) ? ep.alpha * ep.row_scale[row] : ep.alpha;
       // destination row pointer (local C, or the owner's receive slot for fused reduce-scatter)
       uint8_t* c_row = nullptr;
       int owner = 0;
@@ -262,7 +269,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             uint64_t g[16];  // 32 fp32 values as 16 packed pairs (FFMA2 path)
             if (ep.bias != nullptr && cb + 32 <= N) {
               // common case: one FFMA2 per element PAIR (alpha * acc + bias)
-              const uint64_t al2 = pk2(ep.alpha, ep.alpha);
+              const uint64_t al2 = pk2(alpha_row, alpha_row);
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + cb) + j);
@@ -272,7 +279,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             } else {
               float f[32];
 #pragma unroll
-              for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * ep.alpha;
+              for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * alpha_row;
               if (ep.bias != nullptr) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i)
@@ -334,7 +341,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (!row_ok || col0 >= N) continue;
         float f[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * ep.alpha;
+        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * alpha_row;
         const bool full_chunk = (col0 + 32 <= N);
         if (ep.bias != nullptr) {
 #pragma unroll
@@ -459,7 +466,8 @@ IM_API int im_gemm_bf16_tn(const void* A, const void* B, void* C, const float* b
                            int K, int lda, int ldb, int ldc, int ldr, int act, int out_fp32, float alpha, int bn,
                            void* const* peer_c, uint32_t* const* peer_flags, int rank, int rows_per_rank,
                            const uint32_t* a_ready, uint32_t* a_state, int m_rotate, int max_ctas, void* stream,
-                           const void* const* peer_c_host, int world, const int* m_dev) {
+                           const void* const* peer_c_host, int world, const int* m_dev, int fp8,
+                           const float* row_scale) {
   using namespace im;
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if ((lda % 8) || (ldb % 8) || (ldc % 8) || (residual != nullptr && (ldr % 8))) return set_error("im_gemm_bf16_tn", "leading dims must be multiples of 8");
@@ -470,8 +478,10 @@ IM_API int im_gemm_bf16_tn(const void* A, const void* B, void* C, const float* b
     bn = (N % 256 == 0 && tiles256 >= sm_count()) ? 256 : 128;
   }
   CUtensorMap ta, tb;
-  if (get_tmap_2d(&ta, A, M, K, static_cast<uint64_t>(lda) * 2, kBM, kBK, 2, TMAP_SW_128)) return -1;
-  if (get_tmap_2d(&tb, B, N, K, static_cast<uint64_t>(ldb) * 2, bn, kBK, 2, TMAP_SW_128)) return -1;
+  const int eb = fp8 ? 1 : 2;                 // operand element bytes; a K block is always 128 bytes wide
+  if (fp8 && ((lda % 16) || (ldb % 16))) return set_error("im_gemm_bf16_tn", "fp8 operands: leading dims must be multiples of 16");
+  if (get_tmap_2d(&ta, A, M, K, static_cast<uint64_t>(lda) * eb, kBM, 128 / eb, eb, TMAP_SW_128)) return -1;
+  if (get_tmap_2d(&tb, B, N, K, static_cast<uint64_t>(ldb) * eb, bn, 128 / eb, eb, TMAP_SW_128)) return -1;
   GemmEpilogue ep;
   ep.c = C;
   ep.bias = bias;
@@ -490,6 +500,8 @@ IM_API int im_gemm_bf16_tn(const void* A, const void* B, void* C, const float* b
   const int num_m = (M + kBM - 1) / kBM;
   ep.m_rotate = num_m > 0 ? ((m_rotate % num_m) + num_m) % num_m : 0;
   ep.m_dev = m_dev;
+  ep.fp8 = fp8;
+  ep.row_scale = row_scale;
   // coalesced TMA-store epilogue for plain local bf16 outputs
   CUtensorMap tc = ta, tr = ta;
   PeerMaps tp;

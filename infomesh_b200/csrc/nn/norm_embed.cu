@@ -11,6 +11,8 @@
 // (reference infomesh/index/vector_store.py:120-125, infomesh/search/reranker.py:124-159).
 #include <math_constants.h>
 
+#include <cuda_fp8.h>
+
 #include "../common/host.h"
 #include "../common/ptx.cuh"
 
@@ -417,6 +419,41 @@ gather_rows_kernel(const __nv_bfloat16* __restrict__ in, const int* __restrict__
   for (int c = threadIdx.x; c < H / 8; c += blockDim.x) dst[c] = src[c];
 }
 
+// Per-row (per-token) dynamic fp8 quantisation for the e4m3 GEMM path: scale[r] = amax(x[r]) / 448, q = x / scale
+// rounded to e4m3 with saturation.  One warp per row, 16-byte loads, 8-byte stores; the second pass re-reads the row
+// from L1/L2.  The GEMM epilogue multiplies scale[r] (and the per-tensor weight scale) back in.
+__global__ void __launch_bounds__(kRowsPerBlock * 32)
+quantize_rows_fp8_kernel(const __nv_bfloat16* __restrict__ x, int ld, int K, int n_rows, uint8_t* __restrict__ q, int ldq,
+                         float* __restrict__ scale, const int* __restrict__ n_rows_dev) {
+  const int row = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n_rows_dev != nullptr) n_rows = min(n_rows, *n_rows_dev);
+  if (row >= n_rows) return;
+  const uint4* src = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * ld);
+  const int n8 = K / 8;
+  float amax = 0.f;
+  for (int c = lane; c < n8; c += 32) {
+    const uint4 u = src[c];
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), cc = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    amax = fmaxf(amax, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(b.x), fabsf(b.y))));
+    amax = fmaxf(amax, fmaxf(fmaxf(fabsf(cc.x), fabsf(cc.y)), fmaxf(fabsf(d.x), fabsf(d.y))));
+  }
+  amax = warp_max(amax);
+  const float sc = amax > 0.f ? amax * (1.0f / 448.0f) : 1.0f;
+  const float inv = 1.0f / sc;
+  if (lane == 0) scale[row] = sc;
+  uint2* dst = reinterpret_cast<uint2*>(q + static_cast<size_t>(row) * ldq);
+  for (int c = lane; c < n8; c += 32) {
+    const uint4 u = src[c];
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), cc = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    const uint32_t p0 = __nv_cvt_float2_to_fp8x2(make_float2(a.x * inv, a.y * inv), __NV_SATFINITE, __NV_E4M3);
+    const uint32_t p1 = __nv_cvt_float2_to_fp8x2(make_float2(b.x * inv, b.y * inv), __NV_SATFINITE, __NV_E4M3);
+    const uint32_t p2 = __nv_cvt_float2_to_fp8x2(make_float2(cc.x * inv, cc.y * inv), __NV_SATFINITE, __NV_E4M3);
+    const uint32_t p3 = __nv_cvt_float2_to_fp8x2(make_float2(d.x * inv, d.y * inv), __NV_SATFINITE, __NV_E4M3);
+    dst[c] = make_uint2(p0 | (p1 << 16), p2 | (p3 << 16));
+  }
+}
+
 }  // namespace im
 
 #define IM_DISPATCH_VEC(H, CALL)                    \
@@ -526,3 +563,16 @@ IM_API int im_gather_rows(const void* in, const int* idx, int n, int H, int ld_i
   IM_LAUNCH_OK("gather_rows_kernel");
   return 0;
 }
+
+IM_API int im_quantize_rows_fp8(const void* x, int ld, int K, int n_rows, void* q, int ldq, float* scale,
+                                const int* n_rows_dev, void* stream) {
+  using namespace im;
+  if (n_rows <= 0) return 0;
+  if ((K % 8) || (ld % 8) || (ldq % 16)) return set_error("im_quantize_rows_fp8", "K, ld must be multiples of 8 and ldq of 16");
+  const int grid = (n_rows + kRowsPerBlock - 1) / kRowsPerBlock;
+  quantize_rows_fp8_kernel<<<grid, kRowsPerBlock * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      (const __nv_bfloat16*)x, ld, K, n_rows, (uint8_t*)q, ldq, scale, n_rows_dev);
+  IM_LAUNCH_OK("quantize_rows_fp8_kernel");
+  return 0;
+}
+

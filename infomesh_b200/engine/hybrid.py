@@ -34,6 +34,7 @@ class HybridConfig:
     n_rerank: int = 20        # reference reranks <= 20 candidates (reranker.py:20)
     k_out: int = 10
     varlen: bool = True       # cross-encoder runs on the unpadded token stream (padding never reaches a kernel)
+    precision: str = "bf16"   # "fp8": cross-encoder projections as e4m3 GEMMs (opt-in; never the benchmark default)
     rerank_chunks: int = 1    # split the rank's pairs into this many sub-batches so activations stay L2-resident
     pair_seq: int = 128       # <s> q </s></s> passage </s>
     rerank: bool = True
@@ -165,7 +166,7 @@ class HybridEngine:
                 logits = torch.cat([self.reranker.score_packed(pair_ids[i:i + step], pair_lens[i:i + step].contiguous())
                                     for i in range(0, n_pairs, step)])
             else:
-                logits = self.reranker.score_packed(pair_ids, pair_lens)
+                logits = self.reranker.score_packed(pair_ids, pair_lens, precision=cfg.precision)
         else:
             logits = self.reranker.score(pair_ids, pair_lens)
         if self.heap is not None:
@@ -269,7 +270,7 @@ class HybridEngine:
     def _local_logits(self, pair_ids, pair_lens):
         cfg = self.cfg
         if cfg.varlen and pair_ids.shape[1] <= 128 and self.reranker.cfg.head_dim == 64:
-            return self.reranker.score_packed(pair_ids, pair_lens)
+            return self.reranker.score_packed(pair_ids, pair_lens, precision=cfg.precision)
         return self.reranker.score(pair_ids, pair_lens)
 
     def _pipe_init(self):

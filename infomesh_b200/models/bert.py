@@ -150,7 +150,8 @@ class BertModel:
             x = N.layernorm(y2, lay["ln2_g"], lay["ln2_b"], cfg.eps)
         return x.view(B, S, H)
 
-    def hidden_states_packed(self, ids: torch.Tensor, lengths: torch.Tensor, cls_only_last: bool = False):
+    def hidden_states_packed(self, ids: torch.Tensor, lengths: torch.Tensor, cls_only_last: bool = False,
+                             precision: str = "bf16"):
         """Unpadded forward: ids int32 [B, S<=128] + lengths [B] -> (hidden bf16 [B*S, H] of which the first
         ``total`` rows are the packed tokens, cu_seqlens int32 [B+1], total int32 [1]).
 
@@ -168,22 +169,41 @@ class BertModel:
         x = N.embed_ln(pk_ids, w.word, w.pos, w.type, w.emb_g, w.emb_b, cfg.eps, S, pos_ids=pk_pos, n_rows_dev=total)
         layers = w.layers[:-1] if cls_only_last else w.layers
         for lay in layers:
-            x = self._packed_layer(x, lay, B, S, cu, total)
+            x = self._packed_layer(x, lay, B, S, cu, total, fp8=(precision == "fp8"))
         return x, cu, total
 
-    def _packed_layer(self, x, lay, B, S, cu, total):
-        from infomesh_b200.ops import attention as A
+    def _fp8_weights(self, lay):
+        """Per-tensor e4m3 copies of a layer's four GEMM weights (made once, on first use of the fp8 path)."""
         from infomesh_b200.ops import gemm as G
+
+        if "wqkv_8" not in lay:
+            for name in ("wqkv", "wo", "w1", "w2"):
+                lay[name + "_8"], lay[name + "_s"] = G.quantize_weight_fp8(lay[name])
+        return lay
+
+    def _lin(self, x, lay, name, bias, fp8, total=None, **kw):
+        """One projection: bf16 GEMM, or (fp8) per-token dynamic e4m3 quantisation of the input + kind::f8f6f4 GEMM."""
+        from infomesh_b200.ops import gemm as G
+
+        if not fp8:
+            return G.linear(x, lay[name], bias, m_dev=total, **kw)
+        x8, rs = G.quantize_rows_fp8(x, n_rows_dev=total)
+        return G.linear(x8, lay[name + "_8"], bias, alpha=lay[name + "_s"], row_scale=rs, m_dev=total, **kw)
+
+    def _packed_layer(self, x, lay, B, S, cu, total, fp8=False):
+        from infomesh_b200.ops import attention as A
         from infomesh_b200.ops import nn as N
 
         cfg, H = self.cfg, self.cfg.hidden
-        qkv = G.linear(x, lay["wqkv"], lay["bqkv"], m_dev=total)
+        if fp8:
+            self._fp8_weights(lay)
+        qkv = self._lin(x, lay, "wqkv", lay["bqkv"], fp8, total)
         q3 = qkv.view(B, S, 3 * H)
         ctx = A.attention(q3[..., :H], q3[..., H:2 * H], q3[..., 2 * H:], cfg.heads, cu_seqlens=cu)
-        y = G.linear(ctx.view(B * S, H), lay["wo"], lay["bo"], residual=x, m_dev=total)
+        y = self._lin(ctx.view(B * S, H), lay, "wo", lay["bo"], fp8, total, residual=x)
         x1 = N.layernorm(y, lay["ln1_g"], lay["ln1_b"], cfg.eps, n_rows_dev=total)
-        h = G.linear(x1, lay["w1"], lay["b1"], act="gelu", m_dev=total)
-        y2 = G.linear(h, lay["w2"], lay["b2"], residual=x1, m_dev=total)
+        h = self._lin(x1, lay, "w1", lay["b1"], fp8, total, act="gelu")
+        y2 = self._lin(h, lay, "w2", lay["b2"], fp8, total, residual=x1)
         return N.layernorm(y2, lay["ln2_g"], lay["ln2_b"], cfg.eps, n_rows_dev=total)
 
     def _cls_last_layer(self, x, lay, B, lengths, cu, total):
@@ -206,13 +226,17 @@ class BertModel:
         y2 = G.linear(h, lay["w2"], lay["b2"], residual=x1)
         return N.layernorm(y2, lay["ln2_g"], lay["ln2_b"], cfg.eps)               # [B, H] final CLS states
 
-    def score_packed(self, ids, lengths) -> torch.Tensor:
-        """Cross-encoder logits fp32 [B], computed on the unpadded token stream (see :meth:`hidden_states_packed`)."""
+    def score_packed(self, ids, lengths, precision: str = "bf16") -> torch.Tensor:
+        """Cross-encoder logits fp32 [B], computed on the unpadded token stream (see :meth:`hidden_states_packed`).
+
+        ``precision="fp8"``: the four projections of layers 0..L-2 run as e4m3 tensor-core GEMMs (per-token dynamic
+        activation scales, per-tensor weight scales, fp32 accumulate); attention, norms, the CLS-only last layer and
+        the classifier stay bf16.  Opt-in -- the benchmark headline is bf16."""
         from infomesh_b200.ops import gemm as G
 
         assert self.cfg.classifier
         w = self.w
-        x, cu, total = self.hidden_states_packed(ids, lengths, cls_only_last=True)
+        x, cu, total = self.hidden_states_packed(ids, lengths, cls_only_last=True, precision=precision)
         cls = self._cls_last_layer(x, w.layers[-1], ids.shape[0], lengths, cu, total)
         hcls = G.linear(cls, w.cls_w1, w.cls_b1, act="tanh")
         return G.linear(hcls, w.cls_w2p, w.cls_b2p, out_dtype=torch.float32)[:, 0].contiguous()

@@ -447,3 +447,40 @@ def test_pipelined_engine_matches_single_batch_path():
     for (rs, ri), (hs, hi) in zip(ref, outs):
         assert torch.equal(ri.cpu(), hi)
         assert (rs.cpu() - hs).abs().max().item() < 1e-3
+
+
+@pytest.mark.parametrize("m,n,k,act,res", [(300, 512, 768, None, False), (1000, 768, 3072, "gelu", False),
+                                            (257, 2304, 704, None, True), (64, 256, 128, "relu", False)])
+def test_gemm_fp8_matches_dequantised_reference(m, n, k, act, res):
+    """e4m3 operands (per-token activation scales, per-tensor weight scale) through kind::f8f6f4 == fp32 GEMM of the
+    dequantised operands; the quantiser itself stays within e4m3 rounding of the input."""
+    from infomesh_b200.ops import gemm as G
+
+    a = (torch.randn(m, k, device=DEV) * 0.7).bfloat16()
+    w = (torch.randn(n, k, device=DEV) * 0.05).bfloat16()
+    b = torch.randn(n, device=DEV)
+    r = torch.randn(m, n, device=DEV).bfloat16() if res else None
+    a8, rs = G.quantize_rows_fp8(a)
+    w8, ws = G.quantize_weight_fp8(w)
+    deq = a8.view(torch.float8_e4m3fn).float() * rs[:, None]
+    assert ((deq - a.float()).abs() <= 0.0701 * a.float().abs() + 2e-3 * rs[:, None] * 448).all()   # e4m3: 3 mantissa bits
+    out = G.linear(a8, w8, bias=b, residual=r, act=act, alpha=ws, row_scale=rs)
+    ref = G.linear_fp8_ref(a8, rs, w8, ws, b, r, act)
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 0.02 * ref.abs().max().item() + 0.05, err
+
+
+def test_cross_encoder_fp8_tracks_bf16():
+    from dataclasses import replace
+
+    from infomesh_b200.models.bert import BGE_RERANKER_BASE, BertModel
+
+    m = BertModel(replace(BGE_RERANKER_BASE, layers=3), device=DEV, seed=5)
+    B, S = 24, 128
+    g = torch.Generator(device="cpu").manual_seed(4)
+    ids = torch.randint(5, 5000, (B, S), generator=g, dtype=torch.int32).to(DEV)
+    lens = torch.randint(20, S + 1, (B,), generator=g, dtype=torch.int32).to(DEV)
+    a = m.score_packed(ids, lens)
+    b = m.score_packed(ids, lens, precision="fp8")
+    assert torch.isfinite(b).all()
+    assert (a - b).abs().max().item() < 0.25 * max(1.0, a.abs().max().item())
