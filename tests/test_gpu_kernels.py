@@ -484,3 +484,17 @@ def test_cross_encoder_fp8_tracks_bf16():
     b = m.score_packed(ids, lens, precision="fp8")
     assert torch.isfinite(b).all()
     assert (a - b).abs().max().item() < 0.25 * max(1.0, a.abs().max().item())
+
+
+def test_pagerank_matches_numpy_power_iteration():
+    import numpy as np
+
+    from infomesh_b200.ops.graph import pagerank, pagerank_ref
+
+    rng = np.random.default_rng(0)
+    n, e = 5000, 60000
+    src, dst = rng.integers(0, n, e), rng.integers(0, n, e)
+    w = rng.integers(1, 5, e).astype(np.float64)
+    got = pagerank(src, dst, w, n).cpu().numpy()
+    ref = pagerank_ref(src, dst, w, n)
+    assert np.abs(got - ref).max() < 1e-6 and abs(got.sum() - ref.sum()) < 1e-3
