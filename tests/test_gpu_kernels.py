@@ -498,3 +498,47 @@ def test_pagerank_matches_numpy_power_iteration():
     got = pagerank(src, dst, w, n).cpu().numpy()
     ref = pagerank_ref(src, dst, w, n)
     assert np.abs(got - ref).max() < 1e-6 and abs(got.sum() - ref.sum()) < 1e-3
+
+
+def test_index_builder_dedups_within_and_across_batches():
+    """encode + SimHash + fingerprint scan pipeline (world 1): near-duplicates are dropped whether the original sits in
+    the same batch or in the index already; the keep-mask equals the Python SimHash oracle's."""
+    import random
+
+    from infomesh_b200.engine.index_build import IndexBuilder
+    from infomesh_b200.models.bert import BertConfig, BertModel
+    from infomesh_b200.ops import dedup as DD
+
+    rng = random.Random(0)
+    vocab = [f"w{i}" for i in range(3000)]
+    base = [" ".join(rng.choices(vocab, k=80)) for _ in range(96)]
+    b1 = base[:64] + [base[3], base[10] + " extra", base[20]]                 # 3 in-batch (near-)duplicates
+    b2 = base[64:] + [base[5], base[70]] + [" ".join(rng.choices(vocab, k=80)) for _ in range(30)]   # dup of indexed + in-batch
+    enc = BertModel(BertConfig(name="t-enc", layers=1), device=DEV, seed=1)
+    kept_fp: list[int] = []
+
+    def oracle(texts):
+        mask = []
+        for t in texts:
+            f = DD.simhash_py(t)
+            dup = any(DD.hamming(f, g) <= DD.HAMMING_THRESHOLD for g in kept_fp)
+            mask.append(not dup)
+            if not dup:
+                kept_fp.append(f)
+        return mask
+
+    first = 0
+    ib = None
+    for texts in (b1, b2):
+        n = len(texts)
+        if ib is None:
+            ib = IndexBuilder(1000, n, encoder=enc, device=DEV)
+        text, ws, we, off = DD.normalize_batch(texts)
+        arrs = [torch.from_numpy(x).to(DEV) for x in (text, ws, we, off)]
+        ids = torch.randint(1000, 20000, (n, 32), dtype=torch.int32, device=DEV)
+        lens = torch.full((n,), 32, dtype=torch.int32, device=DEV)
+        mask = ib.add_batch(ids, lens, *arrs, first_doc_id=first)
+        assert mask.cpu().tolist() == oracle(texts)
+        first += n
+    st = ib.stats()
+    assert st["indexed"] == len(kept_fp) and st["duplicates"] == st["seen"] - st["indexed"] and st["duplicates"] >= 4
