@@ -128,8 +128,8 @@ class BertModel:
 
     # ------------------------------------------------------------------ native path
     def hidden_states(self, ids: torch.Tensor, lengths: torch.Tensor | None = None,
-                      type_ids: torch.Tensor | None = None) -> torch.Tensor:
-        """ids: int32 [B, S] -> final hidden states bf16 [B, S, H]."""
+                      type_ids: torch.Tensor | None = None, skip_last: bool = False) -> torch.Tensor:
+        """ids: int32 [B, S] -> final hidden states bf16 [B, S, H] (``skip_last``: stop before the last layer)."""
         from infomesh_b200.ops import attention as A
         from infomesh_b200.ops import gemm as G
         from infomesh_b200.ops import nn as N
@@ -139,7 +139,7 @@ class BertModel:
         H = cfg.hidden
         x = N.embed_ln(ids.reshape(-1), w.word, w.pos, w.type, w.emb_g, w.emb_b, cfg.eps, S,
                        type_ids=type_ids.reshape(-1) if type_ids is not None else None, pos_offset=cfg.pos_offset)
-        for lay in w.layers:
+        for lay in (w.layers[:-1] if skip_last else w.layers):
             qkv = G.linear(x, lay["wqkv"], lay["bqkv"])
             q3 = qkv.view(B, S, 3 * H)
             ctx = A.attention(q3[..., :H], q3[..., H:2 * H], q3[..., 2 * H:], cfg.heads, kv_lens=lengths)
@@ -249,12 +249,32 @@ class BertModel:
         return N.pool_norm(h, lengths, self.cfg.pooling, True)
 
     def score(self, ids, lengths=None, type_ids=None) -> torch.Tensor:
-        """Cross-encoder relevance logits fp32 [B]."""
+        """Cross-encoder relevance logits fp32 [B] on padded ``[B, S]`` batches.  The last encoder layer computes keys /
+        values for every token but the query, attention output, out-projection, LayerNorms and FFN only for the <s>
+        rows the classifier reads (same logits; see :meth:`_cls_last_layer`)."""
+        from infomesh_b200.ops import attention as A
+        from infomesh_b200.ops import gemm as G
         from infomesh_b200.ops import nn as N
 
         assert self.cfg.classifier
-        h = self.hidden_states(ids, lengths, type_ids)
-        return classifier_head(h, self.w)
+        cfg, w, H = self.cfg, self.w, self.cfg.hidden
+        B, S = ids.shape
+        if cfg.head_dim not in (32, 64) or len(w.layers) < 1:
+            return classifier_head(self.hidden_states(ids, lengths, type_ids), w)
+        x = self.hidden_states(ids, lengths, type_ids, skip_last=True)               # [B, S, H]
+        lay = w.layers[-1]
+        kv = G.linear(x.view(B * S, H), lay["wqkv"][H:], lay["bqkv"][H:]).view(B, S, 2 * H)
+        x_cls = x[:, 0, :]                                                           # strided rows, no copy
+        q_cls = G.linear(x_cls, lay["wqkv"][:H], lay["bqkv"][:H])
+        kv_len = lengths if lengths is not None else S
+        ctx = A.attention_decode(q_cls, kv[..., :H], kv[..., H:], cfg.heads, kv_len)
+        y = G.linear(ctx, lay["wo"], lay["bo"], residual=x_cls)
+        x1 = N.layernorm(y, lay["ln1_g"], lay["ln1_b"], cfg.eps)
+        h = G.linear(x1, lay["w1"], lay["b1"], act="gelu")
+        y2 = G.linear(h, lay["w2"], lay["b2"], residual=x1)
+        cls = N.layernorm(y2, lay["ln2_g"], lay["ln2_b"], cfg.eps)
+        hcls = G.linear(cls, w.cls_w1, w.cls_b1, act="tanh")
+        return G.linear(hcls, w.cls_w2p, w.cls_b2p, out_dtype=torch.float32)[:, 0].contiguous()
 
     # ------------------------------------------------------------------ references
     def _torch_forward(self, ids, lengths, type_ids, dtype):
