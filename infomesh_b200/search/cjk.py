@@ -4,12 +4,12 @@ from __future__ import annotations
 
 import re
 
-_CJK = re.compile(r"[一-鿿㐀-䶿豈-﫿]")
-_HANGUL = re.compile(r"[가-힯ᄀ-ᇿ㄰-㆏]")
-_KANA = re.compile(r"[぀-ゟ゠-ヿ]")
-_THAI = re.compile(r"[฀-๿]")
-_ARABIC = re.compile(r"[؀-ۿ]")
-_DEVANAGARI = re.compile(r"[ऀ-ॿ]")
+_CJK = re.compile("[\\u4e00-\\u9fff\\u3400-\\u4dbf\\uf900-\\ufaff]")          # ideographs (+ ext. A, compatibility)
+_HANGUL = re.compile("[\\uac00-\\ud7af\\u1100-\\u11ff\\u3130-\\u318f]")       # syllables, jamo, compatibility jamo
+_KANA = re.compile("[\\u3040-\\u309f\\u30a0-\\u30ff]")
+_THAI = re.compile("[\\u0e00-\\u0e7f]")
+_ARABIC = re.compile("[\\u0600-\\u06ff]")
+_DEVANAGARI = re.compile("[\\u0900-\\u097f]")
 _NGRAM_SCRIPTS = (_CJK, _HANGUL, _KANA, _THAI)
 
 
