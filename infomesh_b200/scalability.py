@@ -11,6 +11,7 @@ from contextlib import contextmanager
 from dataclasses import dataclass, field
 from typing import Any
 
+from infomesh_b200.hashing import content_hash
 from infomesh_b200.utils.log import get_logger
 
 logger = get_logger(__name__)
@@ -75,8 +76,12 @@ def batch_ingest(store: Any, documents: list[dict[str, str]], *, batch_size: int
     ok, errors = 0, []
     for doc in documents:
         try:
-            store.add_document(url=doc["url"], title=doc.get("title", ""), text=doc.get("content", doc.get("text", "")),
-                               raw_html_hash=doc.get("content_hash", ""), text_hash=doc.get("text_hash", ""),
+            text = doc.get("content", doc.get("text", ""))
+            # hashes default to the text's own digest: an empty text_hash would make the store's duplicate check
+            # collapse every record of the batch into the first one
+            text_hash = doc.get("text_hash") or content_hash(text)
+            store.add_document(url=doc["url"], title=doc.get("title", ""), text=text,
+                               raw_html_hash=doc.get("content_hash") or text_hash, text_hash=text_hash,
                                language=doc.get("language"))
             ok += 1
         except Exception as exc:  # noqa: BLE001
