@@ -139,7 +139,7 @@ class LocalStore:
             try:
                 fn(event, payload)
             except Exception as exc:  # noqa: BLE001 — a mirror failure must never lose a document
-                logger.warning("store_listener_failed", event=event, error=str(exc))
+                logger.warning("store_listener_failed", store_event=event, error=str(exc))
 
     # ------------------------------------------------------------------ writes
     def add_document(self, url: str, title: str, text: str, raw_html_hash: str, text_hash: str, *,

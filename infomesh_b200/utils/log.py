@@ -33,24 +33,24 @@ class _KVLogger:
         tail = " ".join(f"{k}={v!r}" if isinstance(v, str) and " " in v else f"{k}={v}" for k, v in fields.items())
         self._log.log(level, f"{event} {tail}".rstrip(), exc_info=exc_info)
 
-    def debug(self, event: str, **kw: Any) -> None:
+    def debug(self, event: str, /, **kw: Any) -> None:
         self._emit(logging.DEBUG, event, kw)
 
-    def info(self, event: str, **kw: Any) -> None:
+    def info(self, event: str, /, **kw: Any) -> None:
         self._emit(logging.INFO, event, kw)
 
-    def warning(self, event: str, **kw: Any) -> None:
+    def warning(self, event: str, /, **kw: Any) -> None:
         self._emit(logging.WARNING, event, kw)
 
     warn = warning
 
-    def error(self, event: str, **kw: Any) -> None:
+    def error(self, event: str, /, **kw: Any) -> None:
         self._emit(logging.ERROR, event, kw)
 
-    def critical(self, event: str, **kw: Any) -> None:
+    def critical(self, event: str, /, **kw: Any) -> None:
         self._emit(logging.CRITICAL, event, kw)
 
-    def exception(self, event: str, **kw: Any) -> None:
+    def exception(self, event: str, /, **kw: Any) -> None:
         kw.setdefault("exc_info", True)
         self._emit(logging.ERROR, event, kw)
 
