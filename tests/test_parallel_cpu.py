@@ -61,3 +61,37 @@ def test_context_parallel_single_process_degenerates_to_plain_attention():
     ref = attention_ref(q, k, v, 2)
     assert (ulysses_attention(q, k, v, 2) - ref).abs().max() < 1e-5
     assert (allpairs_attention(q, k, v, 2) - ref).abs().max() < 1e-5
+
+
+# ------------------------------------------------------------------ flag-protocol model (parallel/sim.py)
+def test_flag_protocol_model_survives_random_and_adversarial_schedules():
+    from infomesh_b200.parallel import sim
+
+    for world, ctas in ((2, 1), (2, 3), (4, 2), (8, 2)):
+        for seed in range(25):
+            log = sim.run(world, 6, ctas=ctas, seed=seed)
+            assert len(log) == world * 6 and {u for _, u in log} == set(range(6))
+        for fast in range(world):
+            sim.run(world, 6, ctas=ctas, seed=fast, pick=sim.favour(fast))
+
+
+def test_flag_protocol_model_bounds_how_far_a_rank_can_run_ahead():
+    from infomesh_b200.parallel import sim
+
+    log = sim.run(4, 8, ctas=2, seed=3, pick=sim.favour(0, weight=1000))
+    done: dict[int, int] = {}
+    for rank, use in log:                      # a rank completes use u only after every rank has pushed use u,
+        done[rank] = use                       # i.e. after every rank completed use u - 1: the lead is at most 1
+        assert max(done.values()) - min(done.get(r, -1) for r in range(4)) <= 2
+
+
+def test_checker_catches_the_overwrite_when_double_buffering_is_removed():
+    from infomesh_b200.parallel import sim
+
+    hits = 0
+    for seed in range(40):
+        try:
+            sim.run(2, 6, ctas=1, buffers=1, seed=seed, pick=sim.favour(0))
+        except sim.Violation:
+            hits += 1
+    assert hits > 0, "single-buffered slots must be observably unsafe, otherwise the model proves nothing"
