@@ -16,7 +16,7 @@ def keys_export() -> None:
     """Print the public key (PEM) and peer id."""
     from infomesh_b200.p2p.keys import ensure_keys, export_public_key
 
-    d = load_config().node.data_dir / "keys"
+    d = load_config().node.data_dir
     kp = ensure_keys(d)
     click.echo(f"Peer ID: {kp.peer_id}")
     click.echo(export_public_key(d))
@@ -28,6 +28,6 @@ def keys_rotate() -> None:
     """Generate a new key pair; the old key signs a revocation record that peers can verify."""
     from infomesh_b200.p2p.keys import rotate_keys
 
-    old, new, rec = rotate_keys(load_config().node.data_dir / "keys")
+    old, new, rec = rotate_keys(load_config().node.data_dir)
     click.secho("✔ Key rotated", fg="green")
     click.echo(f"  old peer id: {old.peer_id}\n  new peer id: {new.peer_id}\n  revocation record signed by both keys ({rec.reason})")

@@ -88,7 +88,7 @@ def start(seeds: str | None, background: bool, no_dashboard: bool, role: str | N
             return
         from infomesh_b200.p2p.keys import ensure_keys
 
-        keys = ensure_keys(config.node.data_dir / "keys")
+        keys = ensure_keys(config.node.data_dir)
         click.echo(f"InfoMesh v{__version__} starting...\n  Peer ID: {keys.peer_id}\n  Data dir: {config.node.data_dir}")
         from infomesh_b200.version_check import check_pypi_update, format_update_banner
 
@@ -227,7 +227,7 @@ def _make_credit_sync(config: Config):
         email = resolve_github_email(config) or ""
         if not email:
             return None
-        kp = ensure_keys(config.node.data_dir / "keys")
+        kp = ensure_keys(config.node.data_dir)
         return CreditSyncManager(CreditLedger(config.node.data_dir / "credits.db", owner_email=email),
                                  CreditSyncStore(config.node.data_dir / "credit_sync.db"), email, key_pair=kp, local_peer_id=kp.peer_id)
     except Exception:  # noqa: BLE001

@@ -2,6 +2,7 @@
 key rotation with a dual-signed revocation record (reference infomesh/p2p/keys.py:41-416)."""
 from __future__ import annotations
 
+import contextlib
 import hashlib
 import os
 import shutil
@@ -82,6 +83,12 @@ def peer_id_from_public_key(public_key: bytes) -> str:
 
 def ensure_keys(data_dir: Path) -> KeyPair:
     keys_dir = Path(data_dir) / "keys"
+    nested = keys_dir / "keys"                    # early builds passed <data_dir>/keys here; pull that pair up one level
+    if not (keys_dir / "private.pem").exists() and (nested / "private.pem").exists():
+        for f in nested.iterdir():
+            f.rename(keys_dir / f.name)
+        with contextlib.suppress(OSError):
+            nested.rmdir()
     if (keys_dir / "private.pem").exists():
         return KeyPair.load(keys_dir)
     logger.info("first_run_keygen", keys_dir=str(keys_dir))

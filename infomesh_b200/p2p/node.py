@@ -204,7 +204,7 @@ class InfoMeshNode:
 
     def _prepare_identity(self) -> None:
         data_dir = Path(self._config.node.data_dir)
-        self._key_pair = ensure_keys(data_dir / "keys")
+        self._key_pair = ensure_keys(data_dir)
         self._peer_id = self._key_pair.peer_id
         pub = self._key_pair.public_key_bytes()
         cache = data_dir / "keys" / "pow.bin"

@@ -181,7 +181,7 @@ class AppContext:
                                 compression_enabled=c.storage.compression_enabled, compression_level=c.storage.compression_level)
         self.key_pair = None
         try:
-            self.key_pair = ensure_keys(c.node.data_dir / "keys")
+            self.key_pair = ensure_keys(c.node.data_dir)
         except Exception as exc:  # noqa: BLE001
             logger.warning("key_init_failed", error=str(exc))
 
