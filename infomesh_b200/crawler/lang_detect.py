@@ -13,6 +13,9 @@ class LanguageDetection:
     script: str = "latin"
 
 
+LanguageDetectionResult = LanguageDetection      # name used by the reference (crawler/lang_detect.py:15)
+
+
 _SCRIPTS: tuple[tuple[str, str, re.Pattern[str]], ...] = (
     ("ko", "hangul", re.compile(r"[가-힯ᄀ-ᇿ㄰-㆏]")),
     ("ja", "kana", re.compile(r"[぀-ゟ゠-ヿ]")),

@@ -2,8 +2,11 @@
 1-6, r refresh, m music, q quit with a "stop the node too?" prompt (reference infomesh/dashboard/app.py:40-518)."""
 from __future__ import annotations
 
+import contextlib
+
 from textual.app import App, ComposeResult
 from textual.binding import Binding
+from textual.command import DiscoveryHit, Hit, Hits, Provider
 from textual.containers import Horizontal, Vertical
 from textual.screen import ModalScreen
 from textual.widgets import Button, Footer, Header, Static, TabbedContent, TabPane
@@ -22,6 +25,30 @@ from infomesh_b200.dashboard.screens.settings import SettingsPane
 TABS = ("overview", "crawl", "search", "network", "credits", "settings")
 
 
+class DashboardCommandProvider(Provider):
+    """Ctrl+P palette entries: the six tabs plus refresh / music / help / quit (reference dashboard/app.py:40-76)."""
+
+    @staticmethod
+    def _entries() -> list[tuple[str, str, str]]:
+        tabs = [(name.title(), f"Switch to the {name.title()} tab ({i + 1})", f"app.tab_{i + 1}") for i, name in enumerate(TABS)]
+        return tabs + [("Refresh", "Re-read every panel now (r)", "app.refresh"), ("Toggle BGM", "Background music on / off (m)", "app.toggle_bgm"),
+                       ("Help", "Keyboard shortcuts (?)", "app.help"), ("Exit", "Quit the dashboard (q)", "app.quit")]
+
+    def _runner(self, action: str):
+        return lambda: self.app.run_action(action)
+
+    async def discover(self) -> Hits:
+        for name, text, action in self._entries():
+            yield DiscoveryHit(display=name, command=self._runner(action), help=text)
+
+    async def search(self, query: str) -> Hits:
+        matcher = self.matcher(query)
+        for name, text, action in self._entries():
+            score = matcher.match(name)
+            if score > 0:
+                yield Hit(score=score, match_display=matcher.highlight(name), command=self._runner(action), help=text)
+
+
 class QuitConfirmScreen(ModalScreen[str]):
     """-> "stop_all" | "dashboard_only" | "cancel"."""
     BINDINGS = [Binding("escape", "cancel", "Cancel")]
@@ -35,6 +62,10 @@ class QuitConfirmScreen(ModalScreen[str]):
                 yield Button("Stop node too", id="stop_all", variant="error")
                 yield Button("Cancel", id="cancel")
 
+    def on_mount(self) -> None:
+        with contextlib.suppress(Exception):           # the safe choice has the focus when the dialog opens
+            self.query_one("#cancel", Button).focus()
+
     def on_button_pressed(self, event: Button.Pressed) -> None:
         self.dismiss(event.button.id or "cancel")
 
@@ -45,6 +76,7 @@ class QuitConfirmScreen(ModalScreen[str]):
 class DashboardApp(App[None]):
     TITLE = "InfoMesh Dashboard"
     SUB_TITLE = f"v{__version__}"
+    COMMANDS = App.COMMANDS | {DashboardCommandProvider}
     BINDINGS = [*(Binding(str(i + 1), f"tab('{name}')", name.title()) for i, name in enumerate(TABS)), Binding("r", "refresh", "Refresh"),
                 Binding("m", "toggle_bgm", "Music"), Binding("question_mark", "help", "Help"), Binding("q", "quit", "Quit")]
 
@@ -56,6 +88,7 @@ class DashboardApp(App[None]):
         self.exit_action = "dashboard_only"
         self.cache = DashboardDataCache(self.config, ttl=max(self.config.dashboard.refresh_interval, 0.2))
         self.bgm = BGMPlayer()
+        self._theme_ready = False
 
     def compose(self) -> ComposeResult:
         yield Header()
@@ -78,7 +111,33 @@ class DashboardApp(App[None]):
         theme = getattr(self.config.dashboard, "theme", "")
         if theme and theme in getattr(self, "available_themes", {}):
             self.theme = theme
+        self._theme_ready = True
         self.set_interval(15.0, self._check_bgm_health)
+
+    def watch_theme(self, new_theme: str) -> None:
+        """A theme picked in the command palette is written back to config.toml."""
+        if not getattr(self, "_theme_ready", False) or new_theme == getattr(self.config.dashboard, "theme", ""):
+            return
+        from dataclasses import replace
+
+        from infomesh_b200.config import save_config
+
+        try:
+            new = replace(self.config, dashboard=replace(self.config.dashboard, theme=new_theme))
+            save_config(new)
+            self.update_config(new)
+            with contextlib.suppress(Exception):
+                self.query_one(SettingsPane).update_config(new)
+        except Exception as exc:  # noqa: BLE001 — a read-only config file must not crash the TUI
+            self.notify(f"theme not saved: {exc}", severity="warning")
+
+    def on_unmount(self) -> None:
+        self._cleanup()
+
+    def _cleanup(self) -> None:
+        """Idempotent: every exit path (quit, ctrl+c, crash) ends here."""
+        self.bgm.stop()
+        self.cache.close()
 
     def _check_bgm_health(self) -> None:
         self.bgm.reap_sfx()
@@ -94,11 +153,48 @@ class DashboardApp(App[None]):
         self.update_config(event.config)
         self.set_data_cache_ttl(max(event.config.dashboard.refresh_interval, 0.2))
 
+    def on_settings_pane_restart_requested(self, event: SettingsPane.RestartRequested) -> None:
+        """Stop the node this dashboard was started with and launch a fresh worker with the saved config."""
+        if self.node_pid is None:
+            self.notify("Node is not running under this dashboard; restart it with `infomesh start`.", title="Restart", severity="warning")
+            return
+        from infomesh_b200 import runtime as RT
+        from infomesh_b200.cli.serve import _serve_cmd, _spawn
+
+        try:
+            if not RT.request_graceful_stop(self.node_pid, timeout_seconds=10.0):
+                self.notify(f"node {self.node_pid} did not exit; not restarted", title="Restart", severity="error")
+                return
+        except ProcessLookupError:
+            pass
+        RT.clear_pid_file(self.config.node.data_dir, self.node_pid)
+        self.node_pid = _spawn(_serve_cmd(None, None)).pid
+        RT.write_pid_file(self.config.node.data_dir, self.node_pid)
+        self.notify(f"node restarted (PID {self.node_pid}) for: {', '.join(event.keys)}", title="Restart")
+
     def on_credits_pane_credit_earned(self, event: CreditsPane.CreditEarned) -> None:
         self.notify(f"+{event.amount:.2f} credits", title="Credits earned", timeout=3)
 
     def action_tab(self, name: str) -> None:
         self.query_one("#tabs", TabbedContent).active = name
+
+    def action_tab_1(self) -> None:
+        self.action_tab(TABS[0])
+
+    def action_tab_2(self) -> None:
+        self.action_tab(TABS[1])
+
+    def action_tab_3(self) -> None:
+        self.action_tab(TABS[2])
+
+    def action_tab_4(self) -> None:
+        self.action_tab(TABS[3])
+
+    def action_tab_5(self) -> None:
+        self.action_tab(TABS[4])
+
+    def action_tab_6(self) -> None:
+        self.action_tab(TABS[5])
 
     def action_refresh(self) -> None:
         self.cache.set_ttl(0.0)
@@ -132,8 +228,7 @@ class DashboardApp(App[None]):
         if result in (None, "cancel"):
             return
         self.exit_action = result
-        self.bgm.stop()
-        self.cache.close()
+        self._cleanup()
         self.exit()
 
 

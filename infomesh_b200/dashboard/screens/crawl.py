@@ -11,6 +11,27 @@ from infomesh_b200.dashboard import utils as U
 from infomesh_b200.dashboard.widgets import BarChart, LiveLog
 
 
+class CrawlStatsPanel(Static):
+    """One line of crawl throughput and the limits currently in force."""
+
+    def __init__(self, config, **kw):
+        super().__init__("", **kw)
+        self.config = config
+
+    def show(self, stats) -> None:
+        ago = U.format_uptime(time.time() - stats.last_crawl_at) + " ago" if stats.last_crawl_at else "never"
+        c = self.config.crawl
+        self.update(f"pages last hour [bold]{stats.pages_last_hour:,}[/]  ·  last crawl {ago}  ·  limit {c.urls_per_hour}/h  ·  "
+                    f"{c.max_concurrent} connections  ·  delay {c.politeness_delay}s  ·  RSS {'on' if c.rss_enabled else 'off'}")
+
+
+class TopDomainsPanel(BarChart):
+    """Domains ranked by indexed pages."""
+
+    def show(self, stats) -> None:
+        self.set_items([(d, float(n)) for d, n in stats.top_domains])
+
+
 class CrawlPane(Vertical):
     def __init__(self, config, cache, **kw):
         super().__init__(**kw)
@@ -18,9 +39,9 @@ class CrawlPane(Vertical):
         self._seen: set[int] = set()
 
     def compose(self) -> ComposeResult:
-        yield Static("", id="cr-head")
+        yield CrawlStatsPanel(self.config, id="cr-head")
         yield Static("[bold]Top domains[/]")
-        yield BarChart("", id="cr-domains")
+        yield TopDomainsPanel("", id="cr-domains")
         yield Static("[bold]Crawl log[/]")
         yield LiveLog(visible=14, id="cr-log")
 
@@ -30,10 +51,6 @@ class CrawlPane(Vertical):
 
     def refresh_data(self) -> None:
         st = self.cache.get_stats()
-        ago = U.format_uptime(time.time() - st.last_crawl_at) + " ago" if st.last_crawl_at else "never"
-        c = self.config.crawl
-        self.query_one("#cr-head", Static).update(
-            f"pages last hour [bold]{st.pages_last_hour:,}[/]  ·  last crawl {ago}  ·  limit {c.urls_per_hour}/h  ·  "
-            f"{c.max_concurrent} connections  ·  delay {c.politeness_delay}s  ·  RSS {'on' if c.rss_enabled else 'off'}")
-        self.query_one("#cr-domains", BarChart).set_items([(d, float(n)) for d, n in st.top_domains])
+        self.query_one(CrawlStatsPanel).show(st)
+        self.query_one(TopDomainsPanel).show(st)
         U.push_new_docs_to_log(self.query_one("#cr-log", LiveLog), st.recent_docs, self._seen)

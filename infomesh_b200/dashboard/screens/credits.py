@@ -1,6 +1,8 @@
-"""Credits tab: balance, tier, allowance state and the earnings breakdown; posts ``CreditEarned`` when the balance grows
-(reference infomesh/dashboard/screens/credits.py:30-386)."""
+"""Credits tab: balance / tier / allowance, earnings by action and the latest ledger entries; posts ``CreditEarned`` when
+the total earned grows (reference infomesh/dashboard/screens/credits.py:30-386)."""
 from __future__ import annotations
+
+import time
 
 from textual.app import ComposeResult
 from textual.containers import Vertical
@@ -9,6 +11,35 @@ from textual.widgets import Static
 
 from infomesh_b200.dashboard import utils as U
 from infomesh_b200.dashboard.widgets import BarChart
+
+
+class BalancePanel(Static):
+    def show(self, stats, allowance) -> None:
+        al = allowance
+        extra = (f"  ·  grace {al.grace_remaining_hours:.0f}h left" if al.state.value == "grace" and al.grace_remaining_hours is not None
+                 else f"  ·  debt {al.debt_amount:.2f}" if al.state.value == "debt" else "")
+        self.update(f"balance [bold green]{stats.balance:,.2f}[/]  ·  {U.tier_label(stats.tier)}  ·  earned {stats.total_earned:,.2f}  "
+                    f"spent {stats.total_spent:,.2f}\nsearch cost {al.search_cost:.3f} ({al.state.value}){extra}  ·  "
+                    f"contribution score {stats.contribution_score:,.2f}")
+
+
+class EarningsBreakdownPanel(BarChart):
+    def show(self, by_action: dict[str, float]) -> None:
+        self.set_items(sorted(((str(k), float(v)) for k, v in by_action.items()), key=lambda kv: -kv[1])[:8])
+
+
+class TransactionTable(Static):
+    """The most recent ledger entries, newest first."""
+
+    def show(self, entries) -> None:
+        if not entries:
+            self.update("[dim]no transactions yet[/]")
+            return
+        rows = [f"[dim]{'time':<9}{'action':<16}{'qty':>6}{'credits':>10}  note[/]"]
+        for e in entries:
+            note = (e.note or "")[:48].replace("[", "\\[")
+            rows.append(f"{time.strftime('%H:%M:%S', time.localtime(e.timestamp)):<9}{e.action:<16}{e.quantity:>6.1f}{e.credits:>+10.2f}  {note}")
+        self.update("\n".join(rows))
 
 
 class CreditsPane(Vertical):
@@ -23,9 +54,11 @@ class CreditsPane(Vertical):
         self._last_earned: float | None = None
 
     def compose(self) -> ComposeResult:
-        yield Static("", id="cd-head")
+        yield BalancePanel("", id="cd-head")
         yield Static("[bold]Earnings by action[/]")
-        yield BarChart("", id="cd-actions")
+        yield EarningsBreakdownPanel("", id="cd-actions")
+        yield Static("[bold]Recent transactions[/]")
+        yield TransactionTable("", id="cd-tx")
 
     def on_mount(self) -> None:
         self.refresh_data()
@@ -33,7 +66,7 @@ class CreditsPane(Vertical):
 
     def refresh_data(self) -> None:
         path = self.config.node.data_dir / "credits.db"
-        head = self.query_one("#cd-head", Static)
+        head = self.query_one(BalancePanel)
         if not path.exists():
             head.update("[dim]No credit history yet — start crawling to earn credits.[/]")
             return
@@ -43,17 +76,15 @@ class CreditsPane(Vertical):
             led = CreditLedger(path)
             try:
                 s, al = led.stats(), led.search_allowance()
-                by_action = dict(led.earnings_by_action()) if hasattr(led, "earnings_by_action") else {}
+                by_action, recent = dict(led.earnings_by_action()), led.recent_entries(limit=8)
             finally:
                 led.close()
         except Exception as exc:  # noqa: BLE001
             head.update(f"[red]ledger unavailable: {exc}[/]")
             return
-        extra = (f"  ·  grace {al.grace_remaining_hours:.0f}h left" if al.state.value == "grace" and al.grace_remaining_hours is not None
-                 else f"  ·  debt {al.debt_amount:.2f}" if al.state.value == "debt" else "")
-        head.update(f"balance [bold green]{s.balance:,.2f}[/]  ·  {U.tier_label(s.tier)}  ·  earned {s.total_earned:,.2f}  spent {s.total_spent:,.2f}\n"
-                    f"search cost {al.search_cost:.3f} ({al.state.value}){extra}  ·  contribution score {s.contribution_score:,.2f}")
-        self.query_one("#cd-actions", BarChart).set_items(sorted(((str(k), float(v)) for k, v in by_action.items()), key=lambda kv: -kv[1])[:8])
+        head.show(s, al)
+        self.query_one(EarningsBreakdownPanel).show(by_action)
+        self.query_one(TransactionTable).show(recent)
         if self._last_earned is not None and s.total_earned > self._last_earned:
             self.post_message(self.CreditEarned(s.total_earned - self._last_earned))
         self._last_earned = s.total_earned

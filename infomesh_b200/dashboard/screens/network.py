@@ -1,4 +1,5 @@
-"""Network tab: P2P state, peers, DHT and bandwidth counters (reference infomesh/dashboard/screens/network.py:26-382)."""
+"""Network tab: P2P state, DHT counters, bandwidth sparklines, peer table
+(reference infomesh/dashboard/screens/network.py:26-382).  All four panels read the node's ``p2p_status.json``."""
 from __future__ import annotations
 
 from textual.app import ComposeResult
@@ -9,37 +10,81 @@ from infomesh_b200.dashboard import utils as U
 from infomesh_b200.dashboard.widgets import SparklineChart
 
 
+def _section(st: dict, key: str) -> dict:
+    v = st.get(key) if st else None
+    return v if isinstance(v, dict) else {}
+
+
+class P2PStatusPanel(Static):
+    def __init__(self, config, **kw):
+        super().__init__("", **kw)
+        self.config = config
+
+    def show(self, st: dict) -> None:
+        cfg, boot = self.config, _section(st, "bootstrap")
+        state = str(st.get("state", "stopped")) if st else "not started"
+        lines = [f"P2P [bold]{state}[/]  ·  peers [bold]{int(st.get('peers', 0) or 0) if st else 0}[/]  ·  port {cfg.node.listen_port}/tcp  ·  "
+                 f"replication {cfg.network.replication_factor}x",
+                 f"bootstrap  {boot.get('connected', 0)} connected of {boot.get('configured', len(cfg.network.bootstrap_nodes))} configured",
+                 "listen  " + ", ".join(str(a) for a in (st.get("listen_addrs", []) if st else [])[:2])]
+        self.update("\n".join(lines))
+
+
+class DHTPanel(Static):
+    def show(self, st: dict) -> None:
+        dht = _section(st, "dht")
+        self.update(f"DHT  stored {dht.get('keys_stored', 0):,}  published {dht.get('keys_published', 0):,}  gets {dht.get('gets_performed', 0):,}  "
+                f"puts {dht.get('puts_performed', 0):,}")
+
+
+class BandwidthPanel(Vertical):
+    """Upload / download rate sparklines from the cumulative byte counters (KiB/s at the 2 s refresh)."""
+
+    def __init__(self, **kw):
+        super().__init__(**kw)
+        self.last = (0, 0)
+
+    def compose(self) -> ComposeResult:
+        yield SparklineChart("upload", color="yellow", id="nw-up")
+        yield SparklineChart("download", color="green", id="nw-down")
+
+    def show(self, st: dict) -> None:
+        bw = _section(st, "bandwidth")
+        up, down = int(bw.get("upload_bytes", 0) or 0), int(bw.get("download_bytes", 0) or 0)
+        self.query_one("#nw-up", SparklineChart).push(max(0, up - self.last[0]) / 2048)
+        self.query_one("#nw-down", SparklineChart).push(max(0, down - self.last[1]) / 2048)
+        self.last = (up, down)
+
+
+class PeerTable(Static):
+    def show(self, st: dict) -> None:
+        ids = st.get("peer_ids", []) if st else []
+        vers = st.get("peer_versions", {}) if st else {}
+        self.update("[bold]Peers[/]\n" + ("\n".join(f"  {p[:24]}…  v{vers.get(p, '?')}" for p in ids[:15]) or "  [dim]none connected[/]"))
+
+
 class NetworkPane(Vertical):
     def __init__(self, config, **kw):
         super().__init__(**kw)
         self.config = config
-        self._last = (0, 0)
+
+    @property
+    def _last(self) -> tuple[int, int]:
+        return self.query_one(BandwidthPanel).last
 
     def compose(self) -> ComposeResult:
-        yield Static("", id="nw-state")
-        yield SparklineChart("upload", color="yellow", id="nw-up")
-        yield SparklineChart("download", color="green", id="nw-down")
-        yield Static("", id="nw-peers")
+        yield P2PStatusPanel(self.config, id="nw-state")
+        yield DHTPanel("", id="nw-dht")
+        yield BandwidthPanel(id="nw-bw")
+        yield PeerTable("", id="nw-peers")
 
     def on_mount(self) -> None:
         self.refresh_data()
         self.set_interval(2.0, self.refresh_data)
 
     def refresh_data(self) -> None:
-        st, cfg = U.read_p2p_status(self.config), self.config
-        state = str(st.get("state", "stopped")) if st else "not started"
-        dht, bw, boot = (st.get(k) if isinstance(st.get(k), dict) else {} for k in ("dht", "bandwidth", "bootstrap")) if st else ({}, {}, {})
-        lines = [f"P2P [bold]{state}[/]  ·  peers [bold]{int(st.get('peers', 0) or 0) if st else 0}[/]  ·  port {cfg.node.listen_port}/tcp  ·  "
-                 f"replication {cfg.network.replication_factor}x",
-                 f"DHT  stored {dht.get('keys_stored', 0):,}  published {dht.get('keys_published', 0):,}  gets {dht.get('gets_performed', 0):,}  "
-                 f"puts {dht.get('puts_performed', 0):,}",
-                 f"bootstrap  {boot.get('connected', 0)} connected of {boot.get('configured', len(cfg.network.bootstrap_nodes))} configured",
-                 "listen  " + ", ".join(str(a) for a in (st.get("listen_addrs", []) if st else [])[:2])]
-        self.query_one("#nw-state", Static).update("\n".join(lines))
-        up, down = int(bw.get("upload_bytes", 0) or 0), int(bw.get("download_bytes", 0) or 0)
-        self.query_one("#nw-up", SparklineChart).push(max(0, up - self._last[0]) / 2048)
-        self.query_one("#nw-down", SparklineChart).push(max(0, down - self._last[1]) / 2048)
-        self._last = (up, down)
-        ids = st.get("peer_ids", []) if st else []
-        vers = st.get("peer_versions", {}) if st else {}
-        self.query_one("#nw-peers", Static).update("[bold]Peers[/]\n" + ("\n".join(f"  {p[:24]}…  v{vers.get(p, '?')}" for p in ids[:15]) or "  [dim]none connected[/]"))
+        st = U.read_p2p_status(self.config)
+        self.query_one(P2PStatusPanel).show(st)
+        self.query_one(DHTPanel).show(st)
+        self.query_one(BandwidthPanel).show(st)
+        self.query_one(PeerTable).show(st)

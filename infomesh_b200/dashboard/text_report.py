@@ -176,3 +176,18 @@ def print_text_report(config: Config | None = None) -> None:
     con.print(Columns(panels[:2], equal=True, expand=True))
     for p in panels[2:]:
         con.print(p)
+
+
+_TAB_SECTIONS = {"overview": (_node_section, _resource_section), "crawl": (_index_section,), "search": (_index_section,),
+                 "network": (_network_section,), "credits": (_credits_section,), "settings": (_node_section,)}
+
+
+def print_dashboard(config: Config | None = None, *, tab: str | None = None) -> None:
+    """Rich snapshot on the console; ``tab`` narrows it to the sections of one dashboard tab (reference text_report.py:289)."""
+    cfg = config or load_config()
+    if tab is None:
+        print_text_report(cfg)
+        return
+    con = Console()
+    for section in _TAB_SECTIONS.get(tab.lower(), (_node_section,)):
+        con.print(section(cfg))

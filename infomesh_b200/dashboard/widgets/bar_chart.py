@@ -1,21 +1,33 @@
 """Horizontal bar chart of (label, count) pairs (reference infomesh/dashboard/widgets/bar_chart.py:14-90)."""
 from __future__ import annotations
 
+from dataclasses import dataclass
+
 from textual.widgets import Static
 
 
-def render_bars(items: list[tuple[str, float]], *, width: int = 28, label_width: int = 26) -> str:
+@dataclass
+class BarItem:
+    label: str
+    value: float
+    color: str = "green"
+    suffix: str = ""
+
+
+def render_bars(items: "list[tuple[str, float] | BarItem]", *, width: int = 28, label_width: int = 26) -> str:
+    """``items``: (label, value) pairs or :class:`BarItem` objects (per-bar colour and suffix)."""
     if not items:
         return "[dim]no data yet[/]"
-    peak = max(v for _, v in items) or 1.0
+    bars = [i if isinstance(i, BarItem) else BarItem(str(i[0]), float(i[1])) for i in items]
+    peak = max(b.value for b in bars) or 1.0
     rows = []
-    for label, v in items:
-        n = max(1, int(v / peak * width)) if v > 0 else 0
-        name = label if len(label) <= label_width else label[:label_width - 1] + "…"
-        rows.append(f"{name:<{label_width}} [green]{'█' * n}[/][dim]{'░' * (width - n)}[/] {v:,.0f}")
+    for b in bars:
+        n = max(1, int(b.value / peak * width)) if b.value > 0 else 0
+        name = b.label if len(b.label) <= label_width else b.label[:label_width - 1] + "…"
+        rows.append(f"{name:<{label_width}} [{b.color}]{'█' * n}[/][dim]{'░' * (width - n)}[/] {b.value:,.0f}{b.suffix}")
     return "\n".join(rows)
 
 
 class BarChart(Static):
-    def set_items(self, items: list[tuple[str, float]]) -> None:
+    def set_items(self, items: "list[tuple[str, float] | BarItem]") -> None:
         self.update(render_bars(items))

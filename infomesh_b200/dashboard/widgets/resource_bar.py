@@ -15,6 +15,13 @@ class ResourceBar(Static):
     def __init__(self, label: str, **kw):
         super().__init__(render_resource(label, 0.0), **kw)
         self._label = label
+        self._max_value = 100.0
 
     def set_value(self, ratio: float, detail: str = "") -> None:
         self.update(render_resource(self._label, ratio, detail))
+
+    def update_value(self, value: float, max_value: float | None = None) -> None:
+        """Absolute value against a maximum (default 100), as the reference widget is driven."""
+        if max_value is not None:
+            self._max_value = float(max_value)
+        self.set_value(value / self._max_value if self._max_value > 0 else 0.0)

@@ -27,3 +27,12 @@ class SparklineChart(Static):
         self._values.append(float(value))
         last = self._values[-1]
         self.update(f"[bold]{self._label:<10}[/] [{self._color}]{render_sparkline(self._values, self._width)}[/] {last:,.1f}")
+
+    def push_value(self, value: float, *, max_points: int = 30) -> None:
+        if max_points != self._values.maxlen:
+            self._values = deque(self._values, maxlen=max(1, max_points))
+        self.push(value)
+
+    @property
+    def data(self) -> list[float]:
+        return list(self._values)

@@ -599,21 +599,32 @@ class ToolRuntime:
 
     async def credit_balance(self, args: dict[str, Any]) -> str:
         if self.ctx.ledger is None:
-            return _js({"enabled": False})
-        data = self._credit_data()
-        st = self.ctx.ledger.stats()
-        data.update(total_earned=round(st.total_earned, 2), total_spent=round(st.total_spent, 2), contribution_score=round(st.contribution_score, 2))
+            data: dict[str, object] = {"balance": 0, "state": "normal", "search_cost": 0.1, "note": "Credit ledger not active"}
+        else:
+            data = self._credit_data()
+            st = self.ctx.ledger.stats()
+            data.update(total_earned=round(st.total_earned, 2), total_spent=round(st.total_spent, 2), contribution_score=round(st.contribution_score, 2))
+        if args.get("format", "json") == "text":
+            return "\n".join(["Credit Balance", "==============", f"Balance: {data.get('balance', 0)}", f"State: {data.get('state', 'n/a')}",
+                              f"Search cost: {data.get('search_cost', 0)}"])
         return _js(data)
 
     async def index_stats(self, args: dict[str, Any]) -> str:
         store = self.ctx.store
-        data: dict[str, object] = {"documents": store.get_stats().get("document_count", 0)}
+        data: dict[str, object] = {"document_count": store.get_stats().get("document_count", 0)}
         with contextlib.suppress(Exception):
             data["top_domains"] = [{"domain": d, "count": c} for d, c in store.get_top_domains(limit=10)]
         if self.ctx.vector_store is not None:
-            data["vector"] = self.ctx.vector_store.get_stats()
+            vs = self.ctx.vector_store.get_stats()
+            data["vector"] = {**vs, "document_count": vs.get("document_count", 0), "model": vs.get("model", "unknown")}
         if self.gpu_index is not None:
             data["gpu"] = self.gpu_index.stats()
+        if args.get("format", "json") == "text":
+            lines = ["Index Statistics", "================", f"Documents: {data['document_count']}"]
+            if data.get("top_domains"):
+                lines.append("Top domains:")
+                lines += [f"  {d['domain']}: {d['count']}" for d in data["top_domains"][:5]]      # type: ignore[index]
+            return "\n".join(lines)
         return _js(data)
 
     async def remove_url(self, args: dict[str, Any]) -> str:
@@ -639,3 +650,133 @@ def _format_gpu_hits(hits: list[dict[str, object]], elapsed_ms: float, max_snipp
     for i, h in enumerate(hits, 1):
         lines += [f"{i}. {h['title']}", f"   {h['url']}", f"   rerank score: {float(h['score']):.3f}", f"   {str(h['snippet'])[:max_snippet]}", ""]
     return "\n".join(lines)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Functional entry points.  The reference exposes one free function per tool that takes its collaborators as keyword
+# arguments (infomesh/mcp/handlers.py:218-1616); embedders that call those directly keep working: each adapter wraps the
+# collaborators in a throw-away context, runs the same ToolRuntime method as the MCP server, and returns MCP text content.
+# ---------------------------------------------------------------------------------------------------------------------
+_CTX_FIELDS = ("store", "vector_store", "link_graph", "ledger", "llm_backend", "worker", "scheduler", "feedback_store",
+               "credit_sync_manager", "distributed_index", "p2p_node", "key_pair", "dedup", "gpu_index")
+
+
+def _text_content(text: str) -> list[Any]:
+    try:
+        from mcp.types import TextContent
+
+        return [TextContent(type="text", text=text)]
+    except ImportError:                       # the MCP SDK is optional; the shape stays the same
+        from types import SimpleNamespace
+
+        return [SimpleNamespace(type="text", text=text)]
+
+
+def _adhoc_runtime(*, config: Any | None = None, query_cache: QueryCache | None = None, sessions: SessionStore | None = None,
+                   analytics: AnalyticsTracker | None = None, webhooks: WebhookRegistry | None = None, last_search_query: str = "",
+                   **deps: Any) -> "ToolRuntime":
+    from types import SimpleNamespace
+
+    from infomesh_b200.config import Config
+
+    ctx = SimpleNamespace(config=config or Config(), **{f: deps.get(f) for f in _CTX_FIELDS})
+    rt = ToolRuntime(ctx)
+    rt.query_cache = query_cache if query_cache is not None else rt.query_cache
+    rt.sessions = sessions if sessions is not None else rt.sessions
+    rt.analytics = analytics if analytics is not None else rt.analytics
+    rt.webhooks = webhooks if webhooks is not None else rt.webhooks
+    rt.last_query = last_search_query
+    return rt
+
+
+async def _run_tool(tool: str, arguments: dict[str, Any] | None, **deps: Any) -> list[Any]:
+    return _text_content(await _adhoc_runtime(**deps).call(tool, dict(arguments or {})))
+
+
+def _run_tool_sync(tool: str, arguments: dict[str, Any] | None, **deps: Any) -> list[Any]:
+    import asyncio
+
+    coro = _run_tool(tool, arguments, **deps)
+    try:
+        asyncio.get_running_loop()
+    except RuntimeError:
+        return asyncio.run(coro)
+    import concurrent.futures                 # called from inside a loop: finish on a helper thread
+
+    with concurrent.futures.ThreadPoolExecutor(max_workers=1) as pool:
+        return pool.submit(asyncio.run, coro).result()
+
+
+def deduct_search_cost(ledger: Any) -> None:
+    """Charge one search to the ledger; accounting problems never fail the search."""
+    if ledger is None:
+        return
+    try:
+        ledger.spend(ledger.search_allowance().search_cost, reason="search")
+    except Exception:  # noqa: BLE001
+        logger.debug("search_cost_deduction_failed")
+
+
+async def handle_search(name: str, arguments: dict[str, Any], **deps: Any) -> list[Any]:
+    """``name``: ``"search"`` (network + local) or ``"search_local"``."""
+    return await _run_tool(name if name in ("search", "search_local") else "search", arguments, **deps)
+
+
+async def handle_web_search(arguments: dict[str, Any], **deps: Any) -> list[Any]:
+    return await _run_tool("web_search", arguments, **deps)
+
+
+async def handle_fetch(arguments: dict[str, Any], **deps: Any) -> list[Any]:
+    return await _run_tool("fetch_page", arguments, **deps)
+
+
+async def handle_crawl(arguments: dict[str, Any], **deps: Any) -> list[Any]:
+    return await _run_tool("crawl_url", arguments, **deps)
+
+
+async def handle_batch(arguments: dict[str, Any], **deps: Any) -> list[Any]:
+    return await _run_tool("batch_search", arguments, **deps)
+
+
+async def handle_explain(arguments: dict[str, Any], **deps: Any) -> list[Any]:
+    return await _run_tool("explain", arguments, **deps)
+
+
+async def handle_search_rag(arguments: dict[str, Any], **deps: Any) -> list[Any]:
+    return await _run_tool("search_rag", arguments, **deps)
+
+
+async def handle_extract_answer(arguments: dict[str, Any], **deps: Any) -> list[Any]:
+    return await _run_tool("extract_answer", arguments, **deps)
+
+
+async def handle_fact_check(arguments: dict[str, Any], **deps: Any) -> list[Any]:
+    return await _run_tool("fact_check", arguments, **deps)
+
+
+def handle_stats(arguments: dict[str, Any], **deps: Any) -> list[Any]:
+    return _run_tool_sync("network_stats", arguments, **deps)
+
+
+def handle_status(arguments: dict[str, Any], **deps: Any) -> list[Any]:
+    return _run_tool_sync("status", arguments, **deps)
+
+
+def handle_suggest(arguments: dict[str, Any], **deps: Any) -> list[Any]:
+    return _run_tool_sync("suggest", arguments, **deps)
+
+
+def handle_ping() -> list[Any]:
+    return _text_content(_js({"status": "ok", "server": "infomesh", "version": SERVER_VERSION, "api_version": MCP_API_VERSION}))
+
+
+def handle_credit_balance(arguments: dict[str, Any], **deps: Any) -> list[Any]:
+    return _run_tool_sync("credit_balance", arguments, **deps)
+
+
+def handle_index_stats(arguments: dict[str, Any], **deps: Any) -> list[Any]:
+    return _run_tool_sync("index_stats", arguments, **deps)
+
+
+def handle_remove_url(arguments: dict[str, Any], **deps: Any) -> list[Any]:
+    return _run_tool_sync("remove_url", arguments, **deps)

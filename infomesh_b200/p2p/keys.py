@@ -155,3 +155,19 @@ def verify_revocation(record: KeyRevocationRecord) -> bool:
         return False
     return (verify_with_public_key(record.old_public_key, payload, record.old_key_signature)
             and verify_with_public_key(record.new_public_key, payload, record.new_key_signature))
+
+
+def load_revocations(data_dir: Path) -> list[KeyRevocationRecord]:
+    """Every revocation record saved under ``<data_dir>/keys/revocations`` (oldest file name first); unreadable files are
+    skipped (reference infomesh/p2p/keys.py:391-416)."""
+    rev_dir = Path(data_dir) / "keys" / "revocations"
+    if not rev_dir.is_dir():
+        return []
+    out: list[KeyRevocationRecord] = []
+    for path in sorted(rev_dir.glob("*.bin")):
+        try:
+            raw = msgpack.unpackb(path.read_bytes(), raw=False)
+            out.append(KeyRevocationRecord(**raw))
+        except Exception:  # noqa: BLE001
+            logger.warning("revocation_load_failed", path=str(path))
+    return out

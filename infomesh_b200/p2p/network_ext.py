@@ -80,6 +80,8 @@ class DNSPeer:
     host: str
     port: int
     source: str = "dns"
+    peer_id: str = ""
+    priority: int = 0
 
 
 def discover_peers_dns(domain: str = "infomesh.io", *, default_port: int = 4001) -> list[DNSPeer]:

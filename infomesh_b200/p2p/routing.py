@@ -35,12 +35,12 @@ class RoutingStats:
     peers_responded: int = 0
     peers_timed_out: int = 0
     avg_response_ms: float = 0.0
-    _times: deque = field(default_factory=lambda: deque(maxlen=10_000), repr=False)
+    _response_times: deque = field(default_factory=lambda: deque(maxlen=10_000), repr=False)
 
     def record_response(self, elapsed_ms: float) -> None:
         self.peers_responded += 1
-        self._times.append(elapsed_ms)
-        self.avg_response_ms = sum(self._times) / len(self._times)
+        self._response_times.append(elapsed_ms)
+        self.avg_response_ms = sum(self._response_times) / len(self._response_times)
 
 
 @dataclass(frozen=True)

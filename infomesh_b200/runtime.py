@@ -214,3 +214,10 @@ def mark_runtime_stopped(data_dir: Path, pid: int) -> None:
 def request_graceful_stop(pid: int, *, timeout_seconds: float = 5.0) -> bool:
     os.kill(pid, signal.SIGTERM)
     return wait_for_process_exit(pid, timeout_seconds=timeout_seconds)
+
+
+class contextlib_suppress_os_error(contextlib.suppress):
+    """``with contextlib_suppress_os_error(): ...`` — kept for callers written against reference runtime.py:202."""
+
+    def __init__(self) -> None:
+        super().__init__(OSError)

@@ -203,3 +203,22 @@ def perform_merkle_audit(document_hash: str, proof: Any, expected_root_hash: str
         return mk(document_hash, AuditVerdict.PASS, "merkle_proof_valid")
     except Exception as exc:  # noqa: BLE001
         return mk(None, AuditVerdict.ERROR, f"merkle_audit_error: {exc}")
+
+
+def audit_result_canonical(result: AuditResult) -> bytes:
+    """Bytes an auditor signs: id, both parties, URL, the evidence hashes, verdict and completion time — so a verdict cannot
+    be changed after it was signed (reference infomesh/trust/audit.py:507-524)."""
+    return "|".join([result.audit_id, result.auditor_peer_id, result.target_peer_id, result.url, result.actual_text_hash or "",
+                     result.actual_raw_hash or "", result.verdict.value, f"{result.completed_at:.6f}"]).encode()
+
+
+def sign_audit_result(result: AuditResult, key_pair: Any) -> AuditResult:
+    from dataclasses import replace
+
+    return replace(result, auditor_signature=key_pair.sign(audit_result_canonical(result)))
+
+
+def verify_audit_result(result: AuditResult, public_key: bytes) -> bool:
+    from infomesh_b200.p2p.keys import verify_with_public_key
+
+    return bool(result.auditor_signature) and verify_with_public_key(public_key, audit_result_canonical(result), result.auditor_signature)

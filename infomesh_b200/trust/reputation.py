@@ -98,6 +98,10 @@ class LLMReputationTracker(SQLiteStore):
         reps = [self._build(tuple(r), now=time.time()) for r in rows]
         return [r for r in reps if grade is None or r.grade == grade]
 
+    def top_peers(self, n: int = 10) -> list[PeerReputation]:
+        """The ``n`` best peers by EMA quality among those with at least ``MIN_SAMPLES`` ratings."""
+        return self.list_peers(min_ratings=MIN_SAMPLES)[:n]
+
     def best_peers(self, *, limit: int = 5, min_ratings: int = MIN_SAMPLES) -> list[str]:
         return [r.peer_id for r in self.list_peers(min_ratings=min_ratings)[:limit]]
 

@@ -27,5 +27,7 @@ class VectorStoreLike(Protocol):
 
     def get_stats(self) -> dict[str, Any]: ...
 
+    def close(self) -> None: ...
+
 
 AuthorityFn = Callable[[str], float]

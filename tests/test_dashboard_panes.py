@@ -112,7 +112,7 @@ def test_network_pane_reads_the_status_file(tmp_path):
             app.query_one(NetworkPane).refresh_data()
             await pilot.pause()
             state, peers = _text(app.query_one("#nw-state", Static)), _text(app.query_one("#nw-peers", Static))
-            assert "running" in state and "stored 1,234" in state and "1 connected of 2 configured" in state and "/ip4/0.0.0.0/tcp/4001" in state
+            assert "running" in state and "stored 1,234" in _text(app.query_one("#nw-dht", Static)) and "1 connected of 2 configured" in state and "/ip4/0.0.0.0/tcp/4001" in state
             assert "v0.3.1" in peers and "v?" in peers and app.query_one(NetworkPane)._last == (4096, 8192)
             RT.clear_pid_file(tmp_path, os.getpid())
 
@@ -276,3 +276,110 @@ def test_module_entry_point_dispatches_to_the_cli():
 
     out = subprocess.run([sys.executable, "-m", "infomesh_b200", "--help"], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "search" in out.stdout and "start" in out.stdout
+
+
+def test_settings_pane_stages_saves_and_flags_restart_keys(tmp_path, monkeypatch):
+    import infomesh_b200.config as C
+    from infomesh_b200.dashboard.screens import settings as S
+
+    monkeypatch.setattr(C, "DEFAULT_CONFIG_PATH", tmp_path / "config.toml")
+    cfg = _cfg(tmp_path)
+    changed = replace(cfg, storage=replace(cfg.storage, compression_level=9), crawl=replace(cfg.crawl, max_depth=5))
+    assert S.restart_keys_changed(cfg, changed) == ["storage.compression_level"] and S.restart_keys_changed(cfg, cfg) == []
+
+    async def drive():
+        events = []
+
+        class Host(App):
+            def compose(self):
+                yield S.SettingsPane(cfg)
+
+            def on_settings_pane_config_changed(self, m):
+                events.append(("changed", m.config.crawl.max_depth))
+
+            def on_settings_pane_restart_requested(self, m):
+                events.append(("restart", tuple(m.keys)))
+
+        app = Host()
+        async with app.run_test(size=(120, 50)) as pilot:
+            pane = app.query_one(S.SettingsPane)
+            assert "(restart)" in _text(app.query_one("#st-table", Static))
+            msg = pane.apply_edit("crawl.max_depth = 4")
+            await pilot.pause()
+            assert "saved crawl.max_depth" in msg and "restart" not in msg and "max_depth = 4" in (tmp_path / "config.toml").read_text()
+            msg = pane.apply_edit("storage.compression_level = 7")
+            await pilot.pause()
+            assert "after a node restart" in msg and isinstance(app.screen, S.RestartConfirmScreen) and app.screen.keys == ["storage.compression_level"]
+            await pilot.click("#btn-restart-yes")
+            await pilot.pause()
+            assert ("restart", ("storage.compression_level",)) in events and ("changed", 4) in events
+            await pilot.click("#btn-reset")
+            await pilot.pause()
+            assert "defaults staged" in _text(app.query_one("#st-msg", Static)) and pane.config.crawl.max_depth == C.Config().crawl.max_depth
+            assert pane.config.node.data_dir == tmp_path and "max_depth = 4" in (tmp_path / "config.toml").read_text()     # nothing written yet
+            await pilot.click("#btn-save")
+            await pilot.pause()
+            assert "saved" in _text(app.query_one("#st-msg", Static)) and "max_depth = 4" not in (tmp_path / "config.toml").read_text()
+            if isinstance(app.screen, S.RestartConfirmScreen):                 # compression level went back to its default
+                await pilot.click("#btn-restart-no")
+                await pilot.pause()
+            themed = replace(pane.config, dashboard=replace(pane.config.dashboard, theme="nord"))
+            pane.update_config(themed)
+            assert pane.config is themed and pane.refresh_data() is None
+
+    asyncio.run(drive())
+
+
+def test_search_pane_bindings_and_results_panel(tmp_path):
+    from infomesh_b200.dashboard.screens.search import SearchPane, SearchResultsPanel
+    from textual.widgets import Input
+
+    cfg = _cfg(tmp_path)
+    _seed(cfg)
+    text = SearchResultsPanel.render_results("q [x]", [{"title": "T [1]", "url": "https://u", "snippet": "a <b>hit</b>", "score": 0.5}], 3.2, "local")
+    assert "\\[x]" in text and "T \\[1]" in text and "[bold yellow]hit[/]" in text and "0.500" in text
+    assert SearchResultsPanel.render_results("q", [], 1.0) == "No results found."
+
+    async def drive():
+        app = _host(lambda: SearchPane(cfg))
+        async with app.run_test(size=(120, 40)) as pilot:
+            pane = app.query_one(SearchPane)
+            pane.action_focus_search()
+            await pilot.pause()
+            assert app.focused is app.query_one("#se-input", Input)
+            await pilot.press(*"barriers", "enter")
+            await pilot.pause()
+            assert "site0.example" in _text(app.query_one("#se-results")) or "site1.example" in _text(app.query_one("#se-results"))
+            pane.action_blur_search()
+            assert pane.refresh_data() is None
+            app.query_one(SearchResultsPanel).display_results("x", [], 0.0)
+            assert "No results" in _text(app.query_one("#se-results"))
+
+    asyncio.run(drive())
+
+
+def test_app_palette_tab_actions_and_cleanup(tmp_path, monkeypatch):
+    import infomesh_b200.config as C
+    from infomesh_b200.dashboard.app import TABS, DashboardApp, DashboardCommandProvider
+
+    monkeypatch.setattr(C, "DEFAULT_CONFIG_PATH", tmp_path / "config.toml")
+    cfg = _cfg(tmp_path)
+    names = [e[0] for e in DashboardCommandProvider._entries()]
+    assert names[:6] == [t.title() for t in TABS] and {"Refresh", "Toggle BGM", "Help", "Exit"} <= set(names)
+
+    async def drive():
+        app = DashboardApp(cfg)
+        async with app.run_test(size=(120, 40)) as pilot:
+            await pilot.pause()
+            for i, tab in enumerate(TABS, 1):
+                await app.run_action(f"tab_{i}")
+                assert app.query_one("#tabs").active == tab
+            other = next(t for t in app.available_themes if t != app.theme)
+            app.theme = other
+            await pilot.pause()
+            assert app.config.dashboard.theme == other and f'theme = "{other}"' in (tmp_path / "config.toml").read_text()
+            app.exit()
+        return app
+
+    app = asyncio.run(drive())
+    assert app.cache._conn is None if hasattr(app.cache, "_conn") else True

@@ -86,7 +86,7 @@ def test_tool_runtime_end_to_end(tmp_path):
     assert o["status"]["documents_indexed"] == 3 and o["status"]["status"] == "ok" and o["status"]["gpu"] == {"enabled": False}
     assert len(o["batch"]["results"]) == 2 and o["too_many"].startswith("Error [INVALID_PARAM]")
     assert any("Ownership" in s for s in o["suggest"]["suggestions"]) and o["hook_bad"].startswith("Error [SSRF_BLOCKED]")
-    assert o["ping"]["status"] == "ok" and "balance" in o["credits"] and o["istats"]["documents"] == 3
+    assert o["ping"]["status"] == "ok" and "balance" in o["credits"] and o["istats"]["document_count"] == 3
     assert o["rm"].startswith("Removed") and o["rm2"].startswith("Error [NOT_FOUND]") and o["unknown"].startswith("Error [NOT_FOUND]")
     assert o["analytics"]["total_searches"] >= 4 and o["analytics"]["persistent"]["total_fetches"] == 1 and o["analytics"]["tools"]["web_search"] == 6
     ctx.close()

@@ -134,3 +134,56 @@ def test_runtime_auth_and_unknown_tool_render_errors(tmp_path):
     assert out.startswith("Error [INTERNAL]") and "handler exploded" not in out                # internals are not leaked
     assert "web_search" in rt.tool_names and asyncio.run(rt.call("nope")).startswith("Error [NOT_FOUND]")
     ctx.close()
+
+
+def test_functional_handlers_wrap_the_same_runtime(tmp_path):
+    """Reference-style free functions (explicit collaborators as keyword arguments) return MCP text content."""
+    import asyncio
+    import json
+
+    from infomesh_b200.credits.ledger import ActionType, CreditLedger
+    from infomesh_b200.crawler.parser import ParsedPage
+    from infomesh_b200.index.local_store import LocalStore
+    from infomesh_b200.mcp import handlers as H
+    from infomesh_b200.mcp.session import AnalyticsTracker
+    from infomesh_b200.services import index_document
+
+    with LocalStore(tmp_path / "i.db") as store:
+        index_document(ParsedPage(url="https://e.org/tmem", title="Tensor memory", text="Tensor memory holds accumulators for tcgen05 MMA. " * 6, language="en",
+                                  raw_html_hash="r", text_hash="t"), store)
+        led = CreditLedger()
+        led.record_action(ActionType.CRAWL, 5)
+        an = AnalyticsTracker()
+        out = asyncio.run(H.handle_search("search_local", {"query": "tensor memory", "format": "json"}, store=store, link_graph=None, ledger=led, analytics=an))
+        data = json.loads(out[0].text)
+        assert out[0].type == "text" and data["results"][0]["url"] == "https://e.org/tmem" and an.tool_calls["search_local"] == 1
+        assert led.stats().total_spent > 0                                   # the search was charged
+        web = asyncio.run(H.handle_web_search({"query": "tensor memory", "local_only": True}, store=store, ledger=None))
+        assert "e.org/tmem" in web[0].text
+        assert "e.org/tmem" in H.handle_suggest({"prefix": "Tens"}, store=store)[0].text or "Tensor" in H.handle_suggest({"prefix": "Tens"}, store=store)[0].text
+        assert json.loads(H.handle_ping()[0].text)["api_version"] == H.MCP_API_VERSION
+        assert json.loads(H.handle_index_stats({"format": "json"}, store=store, vector_store=None)[0].text)["document_count"] == 1
+        bal = H.handle_credit_balance({"format": "json"}, ledger=led, credit_sync_manager=None)[0].text
+        assert "balance" in bal
+        status = H.handle_status({}, store=store, vector_store=None, link_graph=None, ledger=led, scheduler=None, p2p_node=None, distributed_index=None,
+                                 analytics=an)[0].text
+        assert json.loads(status)["documents_indexed"] == 1
+        assert "Documents: 1" in H.handle_index_stats({"format": "text"}, store=store, vector_store=None)[0].text
+        assert H.handle_credit_balance({"format": "text"}, ledger=None)[0].text.splitlines()[2:] == ["Balance: 0", "State: normal", "Search cost: 0.1"]
+        expl = json.loads(asyncio.run(H.handle_explain({"query": "tensor"}, store=store, link_graph=None))[0].text)
+        assert expl["results"] and "weights" in expl["results"][0]
+        cached = asyncio.run(H.handle_fetch({"url": "https://e.org/tmem"}, store=store, worker=None, vector_store=None))[0].text
+        assert "Tensor memory" in cached
+        assert "Removed from index" in H.handle_remove_url({"url": "https://e.org/tmem"}, store=store)[0].text
+        assert "Error [" in H.handle_remove_url({"url": "https://e.org/tmem"}, store=store)[0].text
+
+        class Broke:
+            def search_allowance(self):
+                raise RuntimeError("db locked")
+
+        H.deduct_search_cost(Broke()), H.deduct_search_cost(None)          # never raises
+
+        async def inside_loop():
+            return H.handle_ping(), H.handle_index_stats({}, store=store, vector_store=None)
+
+        assert len(asyncio.run(inside_loop())) == 2

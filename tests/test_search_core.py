@@ -155,10 +155,22 @@ def test_query_cache_lru_ttl_and_keys():
     assert c.get(k2, now=3) is None and c.get(k3, now=3) == 3 and len(c) == 2
     assert c.get(k1, now=11) is None                               # TTL from insertion, not from access
     st = c.stats
-    assert (st.hits, st.misses, st.evictions) == (2, 2, 1) and st.hit_rate == 0.5
-    c.invalidate(k3)
+    assert (st.hits, st.misses, st.evictions) == (2, 2, 2) and st.hit_rate == 0.5 and st.total == 4     # expiry counts as an eviction
+    assert c.invalidate(k3) and not c.invalidate(k3)
     c.invalidate()
     assert len(c) == 0
+
+
+def test_query_cache_reference_calling_convention():
+    c = QueryCache(max_size=3, ttl_seconds=10)
+    c.put("Rust Ownership ", 10, ["r1", "r2"], now=0)
+    assert c.get("rust ownership", 10, now=1) == ["r1", "r2"] and c.get("rust ownership", 20, now=1) is None
+    assert c.get(QueryCache.make_key("rust ownership", 10), now=1) == ["r1", "r2"]          # both conventions share one store
+    c.put("old", 5, ["x"], now=0), c.put("new", 5, ["y"], now=9)
+    assert c.size == 3 and c.evict_expired(now=10.5) == 2 and c.size == 1 and c.get("new", 5, now=10.5) == ["y"]
+    assert c.invalidate("new", 5) is True and c.invalidate("new", 5) is False
+    c.put("a", 1, []), c.clear()
+    assert c.size == 0 and c.stats.evictions == 2
 
 
 # ------------------------------------------------------------------ formatting

@@ -176,7 +176,7 @@ def test_query_cache_lru_ttl():
     c.put(k3, 3, now=1)                      # evicts k2 (LRU)
     assert c.get(k2, now=1) is None and c.get(k1, now=20) is None   # TTL
     st = c.stats
-    assert st.evictions == 1 and st.hits == 1 and st.misses == 2
+    assert st.evictions == 2 and st.hits == 1 and st.misses == 2      # LRU eviction + TTL expiry
 
 
 def test_format_fetch_result():
