@@ -8,24 +8,24 @@ from dataclasses import dataclass
 
 @dataclass(frozen=True)
 class LanguageDetection:
-    language: str          # ISO 639-1, "und" when undetermined
-    confidence: float      # 0..1
-    script: str = "latin"
+    language: str          # ISO 639-1; "en" with confidence 0.0 when undetermined (the reference's contract)
+    confidence: float      # 0..0.95
+    script: str = "Latin"  # Latin | Hangul | Kana | CJK | Cyrillic | Arabic | Devanagari | Thai | Greek | Hebrew | Unknown
 
 
 LanguageDetectionResult = LanguageDetection      # name used by the reference (crawler/lang_detect.py:15)
 
 
 _SCRIPTS: tuple[tuple[str, str, re.Pattern[str]], ...] = (
-    ("ko", "hangul", re.compile(r"[가-힯ᄀ-ᇿ㄰-㆏]")),
-    ("ja", "kana", re.compile(r"[぀-ゟ゠-ヿ]")),
-    ("zh", "han", re.compile(r"[一-鿿㐀-䶿]")),
-    ("th", "thai", re.compile(r"[฀-๿]")),
-    ("ar", "arabic", re.compile(r"[؀-ۿݐ-ݿ]")),
-    ("hi", "devanagari", re.compile(r"[ऀ-ॿ]")),
-    ("ru", "cyrillic", re.compile(r"[Ѐ-ӿ]")),
-    ("el", "greek", re.compile(r"[Ͱ-Ͽ]")),
-    ("he", "hebrew", re.compile(r"[֐-׿]")),
+    ("ko", "Hangul", re.compile(r"[가-힯ᄀ-ᇿ㄰-㆏]")),
+    ("ja", "Kana", re.compile(r"[぀-ゟ゠-ヿ]")),
+    ("zh", "CJK", re.compile(r"[一-鿿㐀-䶿]")),
+    ("th", "Thai", re.compile(r"[฀-๿]")),
+    ("ar", "Arabic", re.compile(r"[؀-ۿݐ-ݿ]")),
+    ("hi", "Devanagari", re.compile(r"[ऀ-ॿ]")),
+    ("ru", "Cyrillic", re.compile(r"[Ѐ-ӿ]")),
+    ("el", "Greek", re.compile(r"[Ͱ-Ͽ]")),
+    ("he", "Hebrew", re.compile(r"[֐-׿]")),
 )
 _WORD = re.compile(r"[^\W\d_]+", re.UNICODE)
 
@@ -58,33 +58,37 @@ _COMMON: dict[str, frozenset[str]] = {
 _CYRILLIC = ("ru", "uk")
 
 
-def detect_language(text: str) -> LanguageDetection:
-    if not text or not text.strip():
-        return LanguageDetection("und", 0.0, "unknown")
+_UNDETERMINED = LanguageDetection("en", 0.0, "Unknown")
+MAX_CONFIDENCE = 0.95
+
+
+def detect_language(text: str, *, min_text_length: int = 20) -> LanguageDetection:
+    """Texts shorter than ``min_text_length`` are not judged at all (reference crawler/lang_detect.py:346-362)."""
+    if not text or len(text) < min_text_length or not text.strip():
+        return _UNDETERMINED
     sample = text[:5000]
     letters = sum(1 for ch in sample if ch.isalpha())
     if letters == 0:
-        return LanguageDetection("und", 0.0, "unknown")
+        return _UNDETERMINED
     shares = {lang: (script, len(rx.findall(sample)) / letters) for lang, script, rx in _SCRIPTS}
     # Japanese text mixes kana with han: any meaningful kana share wins over "zh"
     if shares["ja"][1] >= 0.05:
-        return LanguageDetection("ja", min(1.0, 0.6 + shares["ja"][1] + shares["zh"][1]), "kana")
+        return LanguageDetection("ja", min(MAX_CONFIDENCE, 0.6 + shares["ja"][1] + shares["zh"][1]), "Kana")
     best_lang, (best_script, best_share) = max(shares.items(), key=lambda kv: kv[1][1])
     if best_share >= 0.3 and best_lang != "ru":
-        return LanguageDetection(best_lang, min(1.0, 0.5 + best_share / 2), best_script)
+        return LanguageDetection(best_lang, min(MAX_CONFIDENCE, 0.5 + best_share / 2), best_script)
     words = [w.lower() for w in _WORD.findall(sample)]
     if not words:
-        return LanguageDetection("und", 0.0, "unknown")
+        return _UNDETERMINED
     cyrillic = best_lang == "ru" and best_share >= 0.3
     pool = _CYRILLIC if cyrillic else [k for k in _COMMON if k not in _CYRILLIC]
     hits = {lang: sum(1 for w in words if w in _COMMON[lang]) for lang in pool}
     lang = max(hits, key=lambda k: hits[k])
     total = hits[lang]
     if total == 0:
-        return LanguageDetection("ru" if cyrillic else "und", 0.35 if cyrillic else 0.0,
-                                 "cyrillic" if cyrillic else "latin")
+        return LanguageDetection("ru", 0.35, "Cyrillic") if cyrillic else LanguageDetection("en", 0.1, "Latin")
     ranked = sorted(hits.values(), reverse=True)
     margin = (ranked[0] - ranked[1]) / ranked[0] if len(ranked) > 1 else 1.0
     density = min(1.0, total / max(len(words), 1) * 4)
-    return LanguageDetection(lang, round(min(1.0, 0.25 + 0.45 * density + 0.3 * margin), 3),
-                             "cyrillic" if cyrillic else "latin")
+    return LanguageDetection(lang, round(min(MAX_CONFIDENCE, 0.25 + 0.45 * density + 0.3 * margin), 3),
+                             "Cyrillic" if cyrillic else "Latin")

@@ -18,18 +18,46 @@ class CrawlStatsPanel(Static):
         super().__init__("", **kw)
         self.config = config
 
+    def on_mount(self) -> None:
+        self.update("[dim]waiting for crawl statistics…[/]")
+
     def show(self, stats) -> None:
-        ago = U.format_uptime(time.time() - stats.last_crawl_at) + " ago" if stats.last_crawl_at else "never"
+        self.update_stats(pages_per_hour=stats.pages_last_hour, last_crawl_at=stats.last_crawl_at)
+
+    def update_stats(self, total_pages: int = 0, pages_per_hour: int = 0, domain_count: int = 0, last_crawl_at: float = 0.0,
+                     countdown: int = 0) -> None:
+        """Push-style update for callers that already hold the numbers (reference screens/crawl.py:60)."""
+        self._values = (total_pages, pages_per_hour, domain_count, last_crawl_at)
+        self._countdown = countdown
+        self._render_line()
+
+    def update_countdown(self, countdown: int) -> None:
+        self._countdown = countdown
+        self._render_line()
+
+    def _render_line(self) -> None:
+        total, per_hour, domains, last = getattr(self, "_values", (0, 0, 0, 0.0))
+        ago = U.format_uptime(time.time() - last) + " ago" if last else "never"
         c = self.config.crawl
-        self.update(f"pages last hour [bold]{stats.pages_last_hour:,}[/]  ·  last crawl {ago}  ·  limit {c.urls_per_hour}/h  ·  "
-                    f"{c.max_concurrent} connections  ·  delay {c.politeness_delay}s  ·  RSS {'on' if c.rss_enabled else 'off'}")
+        extra = (f"{total:,} pages · {domains:,} domains  ·  " if total or domains else "")
+        tick = f"  ·  refresh in {self._countdown}s" if getattr(self, "_countdown", 0) > 0 else ""
+        self.update(f"{extra}pages last hour [bold]{per_hour:,}[/]  ·  last crawl {ago}  ·  limit {c.urls_per_hour}/h  ·  "
+                    f"{c.max_concurrent} connections  ·  delay {c.politeness_delay}s  ·  RSS {'on' if c.rss_enabled else 'off'}{tick}")
 
 
 class TopDomainsPanel(BarChart):
     """Domains ranked by indexed pages."""
 
+    def __init__(self, *a, cache=None, **kw):
+        super().__init__(*a, **kw)
+        self.cache = cache
+
     def show(self, stats) -> None:
         self.set_items([(d, float(n)) for d, n in stats.top_domains])
+
+    def refresh_data(self) -> None:
+        if self.cache is not None:
+            self.show(self.cache.get_stats())
 
 
 class CrawlPane(Vertical):
@@ -41,7 +69,7 @@ class CrawlPane(Vertical):
     def compose(self) -> ComposeResult:
         yield CrawlStatsPanel(self.config, id="cr-head")
         yield Static("[bold]Top domains[/]")
-        yield TopDomainsPanel("", id="cr-domains")
+        yield TopDomainsPanel("", cache=self.cache, id="cr-domains")
         yield Static("[bold]Crawl log[/]")
         yield LiveLog(visible=14, id="cr-log")
 

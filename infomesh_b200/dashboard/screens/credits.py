@@ -13,7 +13,43 @@ from infomesh_b200.dashboard import utils as U
 from infomesh_b200.dashboard.widgets import BarChart
 
 
-class BalancePanel(Static):
+def _read_ledger(config):
+    """(stats, allowance, earnings by action, recent entries), or None when there is no ledger yet."""
+    path = config.node.data_dir / "credits.db"
+    if not path.exists():
+        return None
+    from infomesh_b200.credits.ledger import CreditLedger
+
+    led = CreditLedger(path)
+    try:
+        return led.stats(), led.search_allowance(), dict(led.earnings_by_action()), led.recent_entries(limit=8)
+    finally:
+        led.close()
+
+
+class _LedgerPanel:
+    """Mixin: a panel that can also refresh itself straight from the ledger file when given a config."""
+    config = None
+
+    def on_mount(self) -> None:
+        if self.config is not None:
+            self.refresh_data()
+
+    def refresh_data(self) -> None:
+        if self.config is None:
+            return
+        try:
+            data = _read_ledger(self.config)
+        except Exception:  # noqa: BLE001
+            data = None
+        if data is not None:
+            self._show_ledger(*data)
+
+
+class BalancePanel(_LedgerPanel, Static):
+    def _show_ledger(self, stats, allowance, by_action, recent) -> None:
+        self.show(stats, allowance)
+
     def show(self, stats, allowance) -> None:
         al = allowance
         extra = (f"  ·  grace {al.grace_remaining_hours:.0f}h left" if al.state.value == "grace" and al.grace_remaining_hours is not None
@@ -23,13 +59,19 @@ class BalancePanel(Static):
                     f"contribution score {stats.contribution_score:,.2f}")
 
 
-class EarningsBreakdownPanel(BarChart):
+class EarningsBreakdownPanel(_LedgerPanel, BarChart):
+    def _show_ledger(self, stats, allowance, by_action, recent) -> None:
+        self.show(by_action)
+
     def show(self, by_action: dict[str, float]) -> None:
         self.set_items(sorted(((str(k), float(v)) for k, v in by_action.items()), key=lambda kv: -kv[1])[:8])
 
 
-class TransactionTable(Static):
+class TransactionTable(_LedgerPanel, Static):
     """The most recent ledger entries, newest first."""
+
+    def _show_ledger(self, stats, allowance, by_action, recent) -> None:
+        self.show(recent)
 
     def show(self, entries) -> None:
         if not entries:
@@ -65,23 +107,16 @@ class CreditsPane(Vertical):
         self.set_interval(3.0, self.refresh_data)
 
     def refresh_data(self) -> None:
-        path = self.config.node.data_dir / "credits.db"
         head = self.query_one(BalancePanel)
-        if not path.exists():
-            head.update("[dim]No credit history yet — start crawling to earn credits.[/]")
-            return
         try:
-            from infomesh_b200.credits.ledger import CreditLedger
-
-            led = CreditLedger(path)
-            try:
-                s, al = led.stats(), led.search_allowance()
-                by_action, recent = dict(led.earnings_by_action()), led.recent_entries(limit=8)
-            finally:
-                led.close()
+            data = _read_ledger(self.config)
         except Exception as exc:  # noqa: BLE001
             head.update(f"[red]ledger unavailable: {exc}[/]")
             return
+        if data is None:
+            head.update("[dim]No credit history yet — start crawling to earn credits.[/]")
+            return
+        s, al, by_action, recent = data
         head.show(s, al)
         self.query_one(EarningsBreakdownPanel).show(by_action)
         self.query_one(TransactionTable).show(recent)

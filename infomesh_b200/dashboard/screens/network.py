@@ -20,6 +20,12 @@ class P2PStatusPanel(Static):
         super().__init__("", **kw)
         self.config = config
 
+    def on_mount(self) -> None:
+        self.show({})
+
+    def update_status(self, data: dict[str, object], countdown: int = 0) -> None:
+        self.show(dict(data or {}))
+
     def show(self, st: dict) -> None:
         cfg, boot = self.config, _section(st, "bootstrap")
         state = str(st.get("state", "stopped")) if st else "not started"
@@ -31,6 +37,12 @@ class P2PStatusPanel(Static):
 
 
 class DHTPanel(Static):
+    def on_mount(self) -> None:
+        self.show({})
+
+    def update_data(self, dht_data: dict[str, int], *, p2p_state: str = "stopped") -> None:
+        self.show({"dht": dict(dht_data or {}), "state": p2p_state})
+
     def show(self, st: dict) -> None:
         dht = _section(st, "dht")
         self.update(f"DHT  stored {dht.get('keys_stored', 0):,}  published {dht.get('keys_published', 0):,}  gets {dht.get('gets_performed', 0):,}  "
@@ -48,6 +60,9 @@ class BandwidthPanel(Vertical):
         yield SparklineChart("upload", color="yellow", id="nw-up")
         yield SparklineChart("download", color="green", id="nw-down")
 
+    def update_from_status(self, bw_data: dict[str, int]) -> None:
+        self.show({"bandwidth": dict(bw_data or {})})
+
     def show(self, st: dict) -> None:
         bw = _section(st, "bandwidth")
         up, down = int(bw.get("upload_bytes", 0) or 0), int(bw.get("download_bytes", 0) or 0)
@@ -57,6 +72,9 @@ class BandwidthPanel(Vertical):
 
 
 class PeerTable(Static):
+    def set_peers(self, peer_ids: list[str], versions: dict[str, str] | None = None) -> None:
+        self.show({"peer_ids": list(peer_ids), "peer_versions": dict(versions or {})})
+
     def show(self, st: dict) -> None:
         ids = st.get("peer_ids", []) if st else []
         vers = st.get("peer_versions", {}) if st else {}

@@ -20,6 +20,9 @@ class NodeInfoPanel(Static):
         super().__init__("", **kw)
         self.config, self.cache = config, cache
 
+    def on_mount(self) -> None:
+        self.refresh_data()
+
     def refresh_data(self) -> None:
         cfg = self.config
         running, up = U.is_node_running_with_uptime(cfg)
@@ -84,6 +87,16 @@ class ActivityPanel(Vertical):
         yield SparklineChart("cpu %", color="cyan", id="ov-cpuspark")
         yield Static("[bold]Recently indexed[/]")
         yield LiveLog(id="ov-log")
+
+    # push-style updates for callers that count events themselves (reference screens/overview.py:253-276)
+    def update_crawl(self, count: int) -> None:
+        self.query_one("#ov-rate", SparklineChart).push(float(count))
+
+    def update_index(self, count: int) -> None:
+        self._last_count = int(count)
+
+    def update_search(self, count: int) -> None:
+        self.query_one("#ov-log", LiveLog).log_event(f"{count} queries served", style="dim")
 
     def refresh_data(self, cpu: float | None = None) -> None:
         st = self.cache.get_stats()

@@ -31,6 +31,12 @@ class SearchResultsPanel(Static):
                         f"   {r.get('url', '')}\n   {snip}")
         return "\n".join(rows)
 
+    def on_mount(self) -> None:
+        self.update("[dim]Type a query above and press Enter to search the local index[/]")
+
+    def display_error(self, message: str) -> None:
+        self.update(f"[bold red]Error:[/] {_markup(message)}")
+
     def display_results(self, query: str, results: list[dict[str, object]], elapsed_ms: float, source: str = "local") -> None:
         self.update(self.render_results(query, results, elapsed_ms, source))
 
@@ -75,4 +81,4 @@ class SearchPane(Vertical):
             try:
                 panel.update(self.run_query(q))
             except Exception as exc:  # noqa: BLE001
-                panel.update(f"[red]search failed: {exc}[/]")
+                panel.display_error(f"search failed: {exc}")

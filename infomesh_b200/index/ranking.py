@@ -70,10 +70,11 @@ def freshness_score(crawled_at: float, *, now: float | None = None,
     return max(MIN_FRESHNESS, math.pow(2.0, -age / half_life))
 
 
-def normalize_bm25(score: float, *, max_score: float) -> float:
-    if score <= 0 or max_score <= 0:
+def normalize_bm25(score: float, *, max_score: float = 1.0) -> float:
+    """Saturation ``s / (s + k)`` with ``k = max_score`` (a score equal to it maps to 0.5)."""
+    if score <= 0:
         return 0.0
-    return score / (score + max_score)
+    return score / (score + max(max_score, 0.0))
 
 
 def combined_score(bm25: float, freshness: float, trust: float, authority: float = 0.0, *, title_match: float = 0.0,

@@ -33,7 +33,9 @@ def _install_stubs() -> None:
             return self
 
     class _Stub(types.ModuleType):
-        def __getattr__(self, _n):
+        def __getattr__(self, n):
+            if n.startswith("__"):            # inspect / importlib probe modules for __file__, __path__, ...
+                raise AttributeError(n)
             return _Any()
 
     sys.modules.setdefault("structlog", _Stub("structlog"))
@@ -140,9 +142,11 @@ def behaviour(ref_root: Path) -> int:
         for args, kwargs in calls:
             total += 1
             out = []
-            for f in (rf, of):
-                try:
-                    out.append(("ok", _norm(f(*args, **kwargs))))
+            for f, pkg in ((rf, "infomesh"), (of, "infomesh_b200")):
+                try:        # callables among the arguments build package-specific objects (dataclasses of that side)
+                    a = [x(pkg) if callable(x) else x for x in args]
+                    k = {n: (x(pkg) if callable(x) else x) for n, x in kwargs.items()}
+                    out.append(("ok", _norm(f(*a, **k))))
                 except Exception as exc:  # noqa: BLE001
                     out.append(("raise", type(exc).__name__))
             if out[0] != out[1]:

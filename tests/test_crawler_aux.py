@@ -19,7 +19,7 @@ from infomesh_b200.crawler.lang_detect import detect_language
     ("Le renard brun rapide saute par dessus le chien paresseux et ce n'est pas ce que nous avons dit", "fr"),
     ("분산 검색 엔진은 여러 노드가 협력하여 색인을 만든다", "ko"),
     ("分散型検索エンジンはノードが協力してインデックスを作ります", "ja"),
-    ("分布式搜索引擎由多个节点协作建立索引", "zh"),
+    ("分布式搜索引擎由多个节点协作建立索引，每个节点负责一部分文档。", "zh"),
     ("Быстрая коричневая лиса прыгает через ленивую собаку и это не то что он сказал", "ru"),
     ("ภาษาไทยเป็นภาษาที่มีวรรณยุกต์", "th"),
     ("محرك بحث موزع يعمل عبر عدة عقد", "ar"),
@@ -30,13 +30,16 @@ def test_detect_language(text, lang):
 
 
 def test_detect_language_undetermined_inputs():
-    assert detect_language("").language == "und" and detect_language("   ").confidence == 0.0
-    assert detect_language("12345 !!! 67890").language == "und"
+    empty = detect_language("")
+    assert (empty.language, empty.confidence, empty.script) == ("en", 0.0, "Unknown") and detect_language("   ").confidence == 0.0
+    assert detect_language("12345 !!! 67890 12345 !!! 67890").confidence == 0.0
+    assert detect_language("too short").confidence == 0.0 and detect_language("too short", min_text_length=3).script == "Latin"
 
 
 def test_detect_language_scripts_do_not_bleed_into_each_other():
-    assert detect_language("한국어 문장입니다").script == "hangul"
-    assert detect_language("これは日本語です").script == "kana"
+    assert detect_language("한국어 문장입니다. 두 번째 문장도 있습니다.").script == "Hangul"
+    assert detect_language("これは日本語です。二つ目の文もあります。").script == "Kana"
+    assert all(detect_language(t).confidence <= 0.95 for t in ("한국어 문장입니다. 두 번째 문장도 있습니다.", "the cat and the dog are in the house with it"))
 
 
 # ------------------------------------------------------------------ freshness tiers / recrawl queue

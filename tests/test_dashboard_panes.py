@@ -383,3 +383,42 @@ def test_app_palette_tab_actions_and_cleanup(tmp_path, monkeypatch):
 
     app = asyncio.run(drive())
     assert app.cache._conn is None if hasattr(app.cache, "_conn") else True
+
+
+def test_panels_accept_push_style_updates(tmp_path):
+    from infomesh_b200.dashboard.screens.crawl import CrawlStatsPanel
+    from infomesh_b200.dashboard.screens.network import BandwidthPanel, DHTPanel, P2PStatusPanel, PeerTable
+    from infomesh_b200.dashboard.screens.search import SearchResultsPanel
+    from textual.containers import Vertical
+
+    cfg = _cfg(tmp_path)
+
+    class Box(Vertical):
+        def compose(self):
+            yield CrawlStatsPanel(cfg, id="a")
+            yield P2PStatusPanel(cfg, id="b")
+            yield DHTPanel("", id="c")
+            yield BandwidthPanel(id="d")
+            yield PeerTable("", id="e")
+            yield SearchResultsPanel(cfg, id="f")
+
+    async def drive():
+        app = _host(Box)
+        async with app.run_test(size=(140, 50)) as pilot:
+            await pilot.pause()
+            q = app.query_one
+            assert "waiting" in _text(q("#a")) and "not started" in _text(q("#b")) and "stored 0" in _text(q("#c"))
+            q("#a", CrawlStatsPanel).update_stats(total_pages=1200, pages_per_hour=40, domain_count=7, last_crawl_at=time.time() - 30, countdown=4)
+            assert "1,200 pages · 7 domains" in _text(q("#a")) and "refresh in 4s" in _text(q("#a"))
+            q("#a", CrawlStatsPanel).update_countdown(0)
+            assert "refresh in" not in _text(q("#a"))
+            q("#b", P2PStatusPanel).update_status({"state": "running", "peers": 3})
+            q("#c", DHTPanel).update_data({"keys_stored": 42}, p2p_state="running")
+            q("#d", BandwidthPanel).update_from_status({"upload_bytes": 2048, "download_bytes": 4096})
+            q("#e", PeerTable).set_peers(["p" * 40], {"p" * 40: "1.2.3"})
+            q("#f", SearchResultsPanel).display_error("index [locked]")
+            await pilot.pause()
+            assert "peers 3" in _text(q("#b")).replace("[bold]", "") and "stored 42" in _text(q("#c")) and q("#d", BandwidthPanel).last == (2048, 4096)
+            assert "v1.2.3" in _text(q("#e")) and "Error:" in _text(q("#f")) and "[locked]" in _text(q("#f"))
+
+    asyncio.run(drive())
