@@ -126,7 +126,7 @@ def test_freshness_decay_half_life_floor_and_future():
 
 
 def test_bm25_saturation_normalisation():
-    assert R.normalize_bm25(5.0, max_score=5.0) == 0.5 and R.normalize_bm25(0, max_score=5) == 0.0 and R.normalize_bm25(3, max_score=0) == 0.0
+    assert R.normalize_bm25(5.0, max_score=5.0) == 0.5 and R.normalize_bm25(0, max_score=5) == 0.0 and R.normalize_bm25(3, max_score=0) == 1.0     # k = 0 saturates immediately (reference ranking.py:99-101)
     assert R.normalize_bm25(10, max_score=5) > R.normalize_bm25(5, max_score=5)
 
 
