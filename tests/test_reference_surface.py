@@ -28,3 +28,10 @@ def test_pure_functions_agree_with_the_reference_except_for_documented_cases(tmp
     allowed = {"hashing.short_hash", "crawler.lang_detect.detect_language", "crawler.rss.parse_feed_xml", "api.extensions.get_completion_commands"}
     assert set(diffs) <= allowed, out.stdout[-4000:]
     assert "calls compared" in out.stdout
+
+
+@pytest.mark.skipif(not (REF / "infomesh").is_dir(), reason="no reference checkout on this machine")
+def test_wire_bytes_hashes_ledger_maths_and_search_output_match_the_reference(tmp_path):
+    out = subprocess.run([sys.executable, str(ROOT / "scripts" / "diff_vs_reference.py"), "interop", str(REF)], capture_output=True, text=True,
+                         timeout=900, cwd=tmp_path)
+    assert out.returncode == 0 and "0 differences" in out.stdout, out.stdout[-4000:] + out.stderr[-2000:]
