@@ -142,6 +142,120 @@ def seeds(M):
     return {c:len(S.load_seeds(c)) for c in S.CATEGORIES} if hasattr(S,"CATEGORIES") else None
 
 
+# ---- stateful scenarios: the same script drives both implementations through the reference's method names ----
+@case
+def feedback_store(M):
+    F = M("search.feedback").FeedbackStore()
+    for _ in range(3):
+        F.record_fetch("tensor memory", "https://a.org/1", 1)
+    F.record_skip("tensor memory", ["https://b.org/2", "https://b.org/3"])
+    F.record_citation("tensor memory", "https://a.org/1")
+    F.record_reformulation("tensor memory")
+    st = F.get_url_stats("https://a.org/1")
+    out = [round(F.get_boost("https://a.org/1"), 6), round(F.get_boost("https://b.org/2"), 6), F.get_boost("https://none/"), F.signal_count(),
+           [(u.url, round(u.boost_score, 6), u.fetch_count, u.skip_count, u.cite_count) for u in F.top_boosted_urls(5)],
+           (st.fetch_count, st.skip_count, st.cite_count) if st else None, len(F.hash_query("Tensor Memory ")), F.hash_query("a") == F.hash_query("A ")]
+    F.close()
+    return out
+
+
+@case
+def subnet_limiter_and_profiles(M):
+    S = M("p2p.sybil").SubnetLimiter()
+    res = [S.can_add("10.1.2.3", 0), S.add("10.1.2.3", "p1", 0), S.add("10.1.2.4", "p2", 0), S.add("10.1.2.5", "p3", 0), S.can_add("10.1.2.6", 0),
+           S.add("10.1.2.6", "p4", 0), S.can_add("10.1.2.6", 1), S.get_subnet_counts(0), S.total_nodes]
+    S.remove("10.1.2.3", "p1", 0)
+    res.append(S.can_add("10.1.2.6", 0))
+    T = M("p2p.peer_profile").PeerProfileTracker()
+    for ms in (100, 300, 200):
+        T.record("a", ms)
+    T.record("b", 2000, success=False)
+    T.record("c", 50)
+    pa = T.get("a")
+    res += [round(pa.avg_latency_ms, 4), round(T.adaptive_timeout("a", base_ms=5000), 3), T.adaptive_timeout("zz"), T.known_peers,
+            T.rank_by_latency(["a", "b", "c"], diversity=False), round(T.get("b").success_rate, 3)]
+    return res
+
+
+@case
+def simhash_index_and_dedup(M):
+    SH = M("crawler.simhash")
+    idx = SH.SimHashIndex(max_entries=3)
+    fp = SH.simhash("the quick brown fox jumps over the lazy dog near the river bank today")
+    idx.add(1, fp), idx.add(2, fp ^ 0b101), idx.add(3, fp ^ (2 ** 40 - 1))
+    res = [sorted(idx.find_near_duplicates(fp)), sorted(idx.find_near_duplicates(fp, threshold=0)), idx.size]
+    idx.add(4, 12345)                                   # over capacity: the oldest entry leaves
+    res += [idx.size, sorted(idx.find_near_duplicates(fp))]
+    DD = M("crawler.dedup").DeduplicatorDB()
+    text = "Thread block clusters let several CTAs share distributed shared memory and multicast TMA loads across the cluster. " * 3
+    res += [DD.is_url_seen("https://e.org/a?utm_source=x"), DD.is_content_seen("h1"), DD.is_near_duplicate(text)]
+    DD.mark_seen("https://e.org/a", "h1", text)
+    res += [DD.is_url_seen("https://E.org/a/?utm_source=x#frag"), DD.is_content_seen("h1"), DD.is_near_duplicate(text + " extra"), DD.is_near_duplicate("completely different words about cooking pasta with tomato sauce and basil leaves")]
+    DD.close()
+    return res
+
+
+@case
+def bloom_sessions_webhooks(M):
+    B = M("scalability").BloomFilter(capacity=1000, fp_rate=0.01)
+    for i in range(200):
+        B.add(f"url-{i}")
+    res = [all(f"url-{i}" in B for i in range(200)), sum(f"other-{i}" in B for i in range(500)) < 25, B.size_bytes]
+    X = M("mcp.session")
+    st = X.SessionStore(max_size=2)
+    a = st.get_or_create("s1")
+    st.get_or_create("s2"), st.get_or_create("s3")
+    res.append(st.get_or_create("s1") is a)             # s1 was evicted by the size cap
+    an = X.AnalyticsTracker()
+    an.record_search(10.0), an.record_search(30.0), an.record_crawl(), an.record_fetch()
+    d = an.to_dict()
+    res.append({k: d[k] for k in ("total_searches", "total_crawls", "total_fetches", "avg_latency_ms") if k in d})
+    wh = X.WebhookRegistry(max_registrations=2)
+    res += [wh.register("https://hooks.example.org/a"), wh.register("http://127.0.0.1/x"), wh.register("https://hooks.example.org/a"),
+            wh.register("https://hooks.example.org/b"), wh.register("https://hooks.example.org/c"), wh.unregister("https://hooks.example.org/a"), sorted(wh.urls)]
+    return res
+
+
+@case
+def quality_and_related(M):
+    Qm = M("search.quality")
+    ab = Qm.ABTest("rerank")
+    ab.compare("q1", [3, 2, 0], [0, 2, 3]), ab.compare("q2", [1, 0], [1, 0]), ab.compare("q3", [0, 1], [1, 0])
+    c = Qm.QueryIntentClassifier()
+    res = [D._norm(ab.summary()), [c.classify(q) for q in ("how to install cuda", "facebook login", "buy rtx 5090", "latest ai news today", "python")],
+           D._norm(c.classify_with_confidence("how do I write a kernel"))]
+    R = M("search.nlp").RelatedSearchTracker()
+    for q in ("python asyncio", "python threading", "python asyncio tutorial", "rust ownership"):
+        R.record(q)
+    res.append(R.related("python asyncio", limit=3))
+    return res
+
+
+@case
+def reputation_and_farming(M):
+    T = M("trust.reputation").LLMReputationTracker()
+    for q in (0.9, 0.8, 1.0, 0.7, 0.9, 0.95):
+        T.record_quality("good", q)
+    for q in (0.1, 0.2, 0.1, 0.3, 0.2):
+        T.record_quality("bad", q)
+    T.record_quality("new", 0.9)
+    g, b = T.get_reputation("good"), T.get_reputation("bad")
+    res = [round(g.ema_quality, 4), str(getattr(g.grade, "value", g.grade)), round(b.ema_quality, 4), str(getattr(b.grade, "value", b.grade)),
+           round(T.get_quality_score("nobody"), 4), [p.peer_id for p in T.top_peers(5)], [p.peer_id for p in T.list_peers()]]
+    F = M("credits.farming").FarmingDetector()
+    t0 = 1_000_000.0
+    F.register_node("n1", now=t0)
+    res += [F.is_on_probation("n1", now=t0 + 3600), F.is_on_probation("n1", now=t0 + 25 * 3600), round(F.probation_remaining("n1", now=t0 + 3600), 1)]
+    for i in range(40):
+        F.log_action("n1", "crawl", now=t0 + 30 * 3600 + i * 60.0)          # metronome-regular: a bot signature
+    now = t0 + 30 * 3600 + 40 * 60
+    res += [F.actions_in_last_hour("n1", "crawl", now=now), F.detect_regular_intervals("n1", "crawl", now=now), F.detect_burst("n1", "crawl", now=now),
+            F.is_rate_limited("n1", "crawl", now=now), F.is_blocked("n1")]
+    v = F.check("n1", "crawl", now=now)
+    res.append(D._norm(v))
+    return res
+
+
 def superset(ref, ours) -> bool:
     """True when ``ours`` contains everything ``ref`` has (this build adds GPU-specific entries in a few catalogues)."""
     if isinstance(ref, dict) and isinstance(ours, dict):
