@@ -15,7 +15,8 @@ import os
 import threading
 from pathlib import Path
 
-_LIB_PATH = Path(__file__).resolve().parent / "_native" / "libinfomesh_b200.so"
+# INFOMESH_B200_NATIVE_LIB points the bridge at another build of the library (the sanitizer build of the host runtime)
+_LIB_PATH = Path(os.environ.get("INFOMESH_B200_NATIVE_LIB") or Path(__file__).resolve().parent / "_native" / "libinfomesh_b200.so")
 _lock = threading.Lock()
 _lib: ctypes.CDLL | None = None
 _load_error: str | None = None
@@ -55,7 +56,8 @@ def lib(build_if_missing: bool = True) -> ctypes.CDLL:
         except OSError as exc:
             _load_error = str(exc)
             raise NativeUnavailable(_load_error) from exc
-        handle.im_last_error.restype = ctypes.c_char_p
+        if hasattr(handle, "im_last_error"):          # absent from host-only builds
+            handle.im_last_error.restype = ctypes.c_char_p
         _lib = handle
         return handle
 

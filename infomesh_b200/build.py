@@ -95,6 +95,42 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB_PATH
 
 
+HOST_ASAN_LIB = OUT_DIR / "libinfomesh_b200_host_asan.so"
+
+
+def build_host_sanitized() -> Path:
+    """The C++ host runtime alone (tokeniser / index builder / MD5 / SimHash / Hamming scan) under AddressSanitizer and
+    UndefinedBehaviorSanitizer.  Load it with ``INFOMESH_B200_NATIVE_LIB=<path>`` and
+    ``LD_PRELOAD=$(g++ -print-file-name=libasan.so)``; ``tests/test_native_cpu.py`` does exactly that in a subprocess."""
+    srcs = sorted(CSRC.rglob("*.cpp"))
+    OUT_DIR.mkdir(parents=True, exist_ok=True)
+    errors = []
+    for cxx in dict.fromkeys(c for c in (os.environ.get("CXX"), shutil.which("g++"), "/usr/bin/g++", shutil.which("clang++")) if c):
+        cmd = [cxx, "-std=c++17", "-O1", "-g", "-fno-omit-frame-pointer", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
+               "-fPIC", "-shared", "-DIM_BUILD", *map(str, srcs), "-o", str(HOST_ASAN_LIB)]
+        p = subprocess.run(cmd, capture_output=True, text=True)
+        if p.returncode == 0:                     # not every toolchain ships the sanitizer runtimes
+            return HOST_ASAN_LIB
+        errors.append(f"{cxx}: {(p.stdout + p.stderr).strip()[-300:]}")
+    raise RuntimeError("sanitized host build failed:\n" + "\n".join(errors))
+
+
+def sanitizer_runtime() -> str | None:
+    """Path of libasan for LD_PRELOAD (python itself is not instrumented), or None when no compiler provides one."""
+    for cxx in dict.fromkeys(c for c in (os.environ.get("CXX"), shutil.which("g++"), "/usr/bin/g++") if c):
+        out = subprocess.run([cxx, "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+        if out and Path(out).exists():
+            return str(Path(out).resolve())
+    return None
+
+
+def main() -> int:
+    if "--sanitize-host" in sys.argv:
+        print(build_host_sanitized())
+        return 0
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    return 0
+
+
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
-    print(path)
+    raise SystemExit(main())

@@ -127,7 +127,7 @@ struct Md5 {
     for (; off + 64 <= len; off += 64) block(st, data + off);
     uint8_t tail[128] = {0};
     const int64_t rem = len - off;
-    std::memcpy(tail, data + off, static_cast<size_t>(rem));
+    if (rem > 0) std::memcpy(tail, data + off, static_cast<size_t>(rem));
     tail[rem] = 0x80;
     const int64_t tl = rem + 9 <= 64 ? 64 : 128;
     const uint64_t bits = static_cast<uint64_t>(len) * 8ull;
@@ -161,7 +161,7 @@ IM_API long long im_ib_tokenize(void* h, const char* text, long long len, int ad
   std::vector<int32_t> ids;
   b->tokenize(text, len, ids, add != 0);
   const long long n = static_cast<long long>(ids.size()) < cap ? static_cast<long long>(ids.size()) : cap;
-  std::memcpy(out, ids.data(), static_cast<size_t>(n) * sizeof(int32_t));
+  if (n > 0) std::memcpy(out, ids.data(), static_cast<size_t>(n) * sizeof(int32_t));   // data() may be null when empty
   return static_cast<long long>(ids.size());
 }
 IM_API int im_ib_lookup(void* h, const char* term, long long len) {
@@ -186,7 +186,7 @@ IM_API long long im_ib_term_bytes(void* h, int id, char* out, long long cap) {
   if (id < 0 || static_cast<size_t>(id) >= b->terms.size()) return -1;
   const std::string& t = b->terms[id];
   const long long n = static_cast<long long>(t.size()) < cap ? static_cast<long long>(t.size()) : cap;
-  std::memcpy(out, t.data(), static_cast<size_t>(n));
+  if (n > 0) std::memcpy(out, t.data(), static_cast<size_t>(n));
   return static_cast<long long>(t.size());
 }
 // Export CSR: off[V+1], doc[nnz], tf[nnz], doc_len[n_docs], df[V]
@@ -204,7 +204,7 @@ IM_API int im_ib_export(void* h, long long* off, int* doc, unsigned char* tf, in
     if (df) df[t] = static_cast<int>(b->postings[t].size());
   }
   off[V] = pos;
-  std::memcpy(doc_len, b->doc_len.data(), b->doc_len.size() * sizeof(int32_t));
+  if (!b->doc_len.empty()) std::memcpy(doc_len, b->doc_len.data(), b->doc_len.size() * sizeof(int32_t));
   return 0;
 }
 

@@ -117,3 +117,67 @@ def test_graft_build_entry():
 
     g.build()
     assert _native.lib_path().exists()
+
+
+_ASAN_SCENARIO = r"""
+import ctypes, hashlib, random
+import numpy as np
+from infomesh_b200 import _native
+from infomesh_b200.ops import bm25 as BM, dedup as DD
+
+L = _native.lib()
+L.im_md5_first8_be.restype = ctypes.c_ulonglong
+for n in (0, 1, 55, 56, 57, 63, 64, 65, 119, 120, 1000, 4097):             # every MD5 padding boundary
+    s = bytes(random.Random(n).randrange(256) for _ in range(n))
+    assert L.im_md5_first8_be(s, ctypes.c_longlong(n)) == int.from_bytes(hashlib.md5(s).digest()[:8], "big")
+
+b = BM.HostIndexBuilder()
+rng = random.Random(7)
+words = ["tensor", "memory", "Ünïcödé", "한국어", "x" * 300, "a", "", "tab\tsep", "new\nline", "\x00nul", "emoji😀", "mixed-CASE_42"]
+for i in range(400):
+    b.add_text(" ".join(rng.choice(words) for _ in range(rng.randrange(0, 40))))
+b.add_text(""), b.add_text(" \t\n "), b.add_text("word " * 20000)
+b.add_terms([0, 1, 2, 2, 2]), b.add_terms([])
+assert b.lookup("TENSOR") >= 0 and b.lookup("") == -1 and b.lookup("z" * 5000) == -1
+assert len(b.tokenize("tensor unknownword memory", add=False)) >= 2 and len(b.tokenize("", add=True)) == 0
+for t in range(0, 5):
+    assert isinstance(b.term(t), str)
+csr = b.export()
+assert csr["off"][-1] == len(csr["doc"]) == len(csr["tf"]) and len(csr["doc_len"]) == b.n_docs
+b.close()
+
+texts = ["", "one", "one two", "one two three", "The quick brown fox " * 500, "Ünïcödé wörds hérè", "a" * 10000, "한국어 문장 입니다"]
+got = DD.simhash_cpu(texts)
+assert (got == np.asarray([DD.simhash_py(t) for t in texts], dtype=np.uint64)).all()
+table = np.asarray([rng.getrandbits(64) for _ in range(1000)] + [int(got[4])], dtype=np.uint64)
+L.im_hamming_find_cpu.restype = ctypes.c_longlong
+hit = L.im_hamming_find_cpu(table.ctypes.data_as(ctypes.c_void_p), ctypes.c_longlong(len(table)), ctypes.c_ulonglong(int(got[4]) ^ 0b11), ctypes.c_int(3))
+assert hit == 1000, hit
+assert L.im_hamming_find_cpu(table.ctypes.data_as(ctypes.c_void_p), ctypes.c_longlong(0), ctypes.c_ulonglong(1), ctypes.c_int(3)) == -1
+print("ASAN_SCENARIO_OK")
+"""
+
+
+def test_host_runtime_is_clean_under_address_and_ub_sanitizers(tmp_path):
+    """the C++ host library (tokeniser, index builder, MD5, SimHash, Hamming scan) built with
+    -fsanitize=address,undefined and driven through the normal Python wrappers in a subprocess."""
+    import os
+    import subprocess
+    import sys
+
+    from infomesh_b200 import build as B
+
+    runtime = B.sanitizer_runtime()
+    if runtime is None:
+        pytest.skip("no compiler with the sanitizer runtimes on this machine")
+    try:
+        lib = B.build_host_sanitized()
+    except RuntimeError as exc:
+        pytest.skip(f"sanitizer build unavailable: {exc}")
+    env = dict(os.environ, INFOMESH_B200_NATIVE_LIB=str(lib), LD_PRELOAD=runtime, ASAN_OPTIONS="detect_leaks=0:abort_on_error=0:exitcode=66",
+               UBSAN_OPTIONS="print_stacktrace=1:halt_on_error=1", CUDA_VISIBLE_DEVICES="")
+    out = subprocess.run([sys.executable, "-c", _ASAN_SCENARIO], capture_output=True, text=True, env=env, timeout=600,
+                         cwd=str(B.ROOT.parent))
+    report = out.stdout[-2000:] + out.stderr[-6000:]
+    assert out.returncode == 0 and "ASAN_SCENARIO_OK" in out.stdout, report
+    assert "AddressSanitizer" not in out.stderr and "runtime error:" not in out.stderr, report
