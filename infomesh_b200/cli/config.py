@@ -31,7 +31,8 @@ def config_set(key: str, value: str) -> None:
         raise click.ClickException(str(exc)) from None
     save_config(new)
     section, _, name = key.partition(".")
-    click.secho(f"✔ {key} = {getattr(getattr(new, section), name)}  ({DEFAULT_CONFIG_PATH})", fg="green")
+    click.secho(f"Set {key} = {getattr(getattr(new, section), name)}", fg="green")
+    click.echo(f"  saved to {DEFAULT_CONFIG_PATH}")
 
 
 @config_group.command("github")

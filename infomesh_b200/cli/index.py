@@ -28,9 +28,13 @@ def index_stats() -> None:
     cfg = load_config()
     with _store(cfg) as st:
         n = st.get_stats().get("document_count", 0)
-        click.echo(f"Documents: {n}")
+        click.echo(f"Index Statistics\n{'=' * 30}")                       # field labels as in reference cli/index.py:32-44
+        click.echo(f"Database:        {cfg.index.db_path}")
+        click.echo(f"Documents:       {n}")
+        click.echo(f"Tokenizer:       {cfg.index.fts_tokenizer}")
+        click.echo(f"Compression:     {'on' if cfg.storage.compression_enabled else 'off'}")
         if cfg.index.db_path.exists():
-            click.echo(f"DB size:   {cfg.index.db_path.stat().st_size / 2 ** 20:.1f} MB ({cfg.index.db_path})")
+            click.echo(f"DB size:         {cfg.index.db_path.stat().st_size / 2 ** 20:.2f} MB")
         top = st.get_top_domains(limit=7)
         if top:
             click.echo("Top domains:")

@@ -45,6 +45,7 @@ async def _wait_for_peer(node, timeout: float = 8.0) -> bool:
 def search(query: str, limit: int, local_only: bool, vector: bool, gpu: bool) -> None:
     """Search the index (network search first, local fallback)."""
     from infomesh_b200.index.local_store import LocalStore
+    from infomesh_b200.search import formatter as F      # the same renderers the MCP tools use (reference cli/search.py:33-136)
     from infomesh_b200.search import query as Q
 
     cfg = load_config()
@@ -68,7 +69,7 @@ def search(query: str, limit: int, local_only: bool, vector: bool, gpu: bool) ->
                 res = Q.search_hybrid(store, vs, query, limit=limit)
             finally:
                 vs.close()
-            _print_ranked(res.results, res.elapsed_ms, "hybrid")
+            click.echo(F.format_hybrid_results(res))
             return
         if not local_only:
             from infomesh_b200.services import bootstrap_p2p, create_local_search_fn
@@ -81,12 +82,11 @@ def search(query: str, limit: int, local_only: bool, vector: bool, gpu: bool) ->
                         return await Q.search_distributed(store, dist_index, query, limit=limit, network_search_fn=node.search_network)
 
                     res = asyncio.run(go())
-                    _print_ranked(res.results, res.elapsed_ms, f"distributed: {res.local_count} local + {res.remote_count} remote")
+                    click.echo(F.format_distributed_results(res))
                     return
                 finally:
                     node.stop()
-        res = Q.search_local(store, query, limit=limit)
-        _print_ranked(res.results, res.elapsed_ms, "local")
+        click.echo(F.format_fts_results(Q.search_local(store, query, limit=limit)))
     finally:
         store.close()
 
@@ -107,12 +107,14 @@ def feedback_stats() -> None:
     """Signal counts and the strongest boosts."""
     fb = _feedback_store()
     try:
-        click.echo(f"Signals recorded: {fb.signal_count()}")
-        top = fb.top_boosted_urls(5)
+        count, top = fb.signal_count(), fb.top_boosted_urls(5)
+        click.echo(f"Total signals: {count}")
+        click.echo(f"Boosted URLs:  {len(top)}")
         if top:
-            click.echo("Top boosted URLs:")
+            click.echo(f"\n{'URL':<60} {'Boost':>8} {'Fetch':>6} {'Skip':>6} {'Cite':>6}")
+            click.echo("─" * 90)
             for u in top:
-                click.echo(f"  {u.boost_score:+.2f}  fetch {u.fetch_count} · skip {u.skip_count} · cite {u.cite_count}  {u.url}")
+                click.echo(f"{u.url[:60]:<60} {u.boost_score:>+8.2f} {u.fetch_count:>6} {u.skip_count:>6} {u.cite_count:>6}")
     finally:
         fb.close()
 

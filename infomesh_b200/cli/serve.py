@@ -336,7 +336,7 @@ def _render_p2p_status(config: Config, running: bool) -> None:
     try:
         st = json.loads((config.node.data_dir / "p2p_status.json").read_text())
     except (OSError, ValueError):
-        click.echo("P2P:             (no status yet)")
+        click.echo("P2P:             stopped")
         return
     fresh = time.time() - float(st.get("timestamp", 0)) < 30
     state = st.get("state", "unknown") if (fresh and running) else "stopped"
@@ -351,10 +351,22 @@ def _render_p2p_status(config: Config, running: bool) -> None:
 
 
 def _render_credit_status(ledger) -> None:
+    """Credits / Tier / (state) / GitHub lines, labelled as in reference cli/serve.py:876-901."""
     if ledger is None:
+        click.echo("Credits:         N/A (ledger unavailable)")
         return
-    al = ledger.search_allowance()
-    click.echo(f"Credits:         {ledger.balance():.2f} ({al.state.value}, search cost {al.search_cost:.3f}, {ledger.tier().name})")
+    ls = ledger.stats()
+    click.echo(f"Credits:         {ls.balance:.1f} (earned {ls.total_earned:.1f} / spent {ls.total_spent:.1f})")
+    click.echo(f"Tier:            {ls.tier.value} (score {ls.contribution_score:.1f}, search cost {ls.search_cost:.3f})")
+    if ls.credit_state.value != "normal":
+        extra = (f" ({ls.grace_remaining_hours:.0f} h of grace left)" if ls.credit_state.value == "grace" and ls.grace_remaining_hours is not None
+                 else f" (debt {ls.debt_amount:.2f})" if ls.credit_state.value == "debt" else "")
+        click.echo(f"Credit state:    {ls.credit_state.value}{extra}")
+    if ls.owner_email:
+        click.echo(f"GitHub:          {ls.owner_email}\n                 Credits linked across all nodes.")
+    else:
+        click.echo("GitHub:          " + click.style("not connected", fg="yellow"))
+        click.echo("                 Run 'infomesh config github your@email.com' to link.")
 
 
 @click.command()

@@ -39,7 +39,7 @@ def test_cli_commands(node_env):
     assert out.exit_code == 0 and "asyncio — Asynchronous I/O" in out.output and "docs.python.org" in out.output
     assert "No results found." in run(cli, ["search", "--local", "zzzqqq"]).output
     st = run(cli, ["index", "stats"])
-    assert st.exit_code == 0 and "Documents: 2" in st.output and "docs.python.org" in st.output
+    assert st.exit_code == 0 and "Documents:       2" in st.output and "Tokenizer:       unicode61" in st.output and "docs.python.org" in st.output
     snap = str(node_env / "out.infomesh-snapshot")
     assert "Exported 2 documents" in run(cli, ["index", "export", snap]).output
     assert "Imported 0 of 2" in run(cli, ["index", "import", snap]).output
@@ -63,7 +63,7 @@ def test_cli_commands(node_env):
     (node_env / "feeds.opml").write_text('<opml><body><outline text="a" xmlUrl="https://a.example/feed.xml"/></body></opml>')
     assert "1 new feeds" in run(cli, ["feeds", "import", str(node_env / "feeds.opml")]).output
     assert "https://a.example/feed.xml" in run(cli, ["feeds", "list"]).output
-    assert "Signals recorded: 0" in run(cli, ["feedback", "stats"]).output and run(cli, ["feedback", "top-urls"]).exit_code == 0
+    assert "Total signals: 0" in run(cli, ["feedback", "stats"]).output and run(cli, ["feedback", "top-urls"]).exit_code == 0
     doc = run(cli, ["doctor"])
     assert doc.exit_code == 0 and "InfoMesh Doctor" in doc.output and "Summary:" in doc.output
     bench = run(cli, ["bench", "-n", "3"])
