@@ -494,27 +494,41 @@ class ToolRuntime:
         return "\n".join(lines)
 
     async def batch_search(self, args: dict[str, Any]) -> str:
+        """Up to 10 queries (extra ones are ignored, as in reference mcp/handlers.py:906-977).  ``format="text"`` (default) renders
+        each query with the standard result formatter; ``format="json"`` returns ``{"api_version", "batch_results": [...]}``."""
+        from infomesh_b200.search.formatter import format_fts_results, format_fts_results_json
+        from infomesh_b200.search.query import search_local
+
         queries = args.get("queries", [])
         if not isinstance(queries, list) or not queries:
-            raise ToolError(ErrorCode.INVALID_PARAM, "queries must be a non-empty list")
-        if len(queries) > 10:
-            raise ToolError(ErrorCode.INVALID_PARAM, "Batch search exceeds maximum queries (10)")
-        limit = _int(args, "limit", 5, 1, 20)
+            raise ToolError(ErrorCode.INVALID_PARAM, "queries must be a non-empty array")
+        if len(queries) > 50:
+            raise ToolError(ErrorCode.INVALID_PARAM, "Batch search exceeds maximum queries (50)")
+        queries, limit, fmt = queries[:10], _int(args, "limit", 5, 1, 50), args.get("format", "text")
         gi = self.gpu_index
-        if gi is not None and gi.engine is not None:          # one device pass for the whole batch
+        if gi is not None and gi.engine is not None and fmt == "json":          # one device pass for the whole batch
             import asyncio
 
             rows = await asyncio.to_thread(gi.search_many, [str(q) for q in queries], limit)
-            return _js({"api_version": MCP_API_VERSION, "source": "gpu_hybrid",
-                        "results": [{"query": q, "results": r} for q, r in zip(queries, rows)]})
-        out = []
-        for q in queries:
-            txt = await self._search({"query": str(q), "limit": limit, "format": "json"}, network=False)
-            try:
-                out.append({"query": q, **json.loads(txt)})
-            except ValueError:
-                out.append({"query": q, "error": txt})
-        return _js({"api_version": MCP_API_VERSION, "results": out})
+            batch = [{"query": q, "source": "gpu_hybrid", "total": len(r), "results": r} for q, r in zip(queries, rows)]
+            return _js({"api_version": MCP_API_VERSION, "batch_results": batch, "results": batch})
+        batch, parts = [], []
+        for i, q in enumerate(queries, 1):
+            if not isinstance(q, str) or not q.strip():
+                batch.append({"query": str(q), "error": "invalid"})
+                parts.append(f"--- Query {i}: (invalid) ---\n")
+                continue
+            self._deduct()
+            t0 = time.monotonic()
+            res = search_local(self.ctx.store, q, limit=limit, authority_fn=self._authority_fn())
+            await self.analytics.record_search((time.monotonic() - t0) * 1000)
+            if fmt == "json":
+                batch.append({**json.loads(format_fts_results_json(res)), "query": q})
+            else:
+                parts.append(f"--- Query {i}: {q} ---\n{format_fts_results(res)}\n")
+        if fmt == "json":
+            return _js({"api_version": MCP_API_VERSION, "batch_results": batch, "results": batch})
+        return "\n".join(parts)
 
     async def suggest(self, args: dict[str, Any]) -> str:
         prefix = args.get("prefix", "")
@@ -556,7 +570,13 @@ class ToolRuntime:
         if not isinstance(query, str) or not query.strip():
             raise ToolError(ErrorCode.INVALID_PARAM, "query must be a non-empty string")
         res = search_local(self.ctx.store, query, limit=_int(args, "limit", 5, 1, 50), authority_fn=self._authority_fn(), **extract_filters(args))
-        return _js({"api_version": MCP_API_VERSION, **explain_query(query, _sanitize_fts_query(query), res.results, res.elapsed_ms).to_dict()})
+        ex = explain_query(query, _sanitize_fts_query(query), res.results, res.elapsed_ms)
+        if args.get("format", "json") == "text":
+            lines = [f"Query: {ex.query}", f"Results: {ex.total_results}", f"Elapsed: {ex.elapsed_ms:.1f}ms", ""]
+            for e in ex.results:
+                lines += [f"  {e.url}", f"    Score: {e.combined_score:.4f}", *(f"    {k}: {v:.4f}" for k, v in e.weighted.items()), ""]
+            return "\n".join(lines)
+        return _js({"api_version": MCP_API_VERSION, **ex.to_dict()})
 
     async def search_history(self, args: dict[str, Any]) -> str:
         if self.pstore is None:
@@ -577,7 +597,11 @@ class ToolRuntime:
         res = search_local(self.ctx.store, query, limit=_int(args, "limit", 5, 1, 50), authority_fn=self._authority_fn(), **extract_filters(args))
         await self.analytics.record_search((time.monotonic() - t0) * 1000)
         out = format_rag_output(query, res.results, chunk_size=_int(args, "chunk_size", 500, 50, 8000), max_chunks=_int(args, "max_chunks", 10, 1, 50))
-        return _js({"api_version": MCP_API_VERSION, **out.to_dict()})
+        data = out.to_dict()
+        # key names of the reference's tool output (mcp/handlers.py search_rag) next to the richer chunk records
+        data["context_chunks"] = [{"url": c["url"], "title": c["title"], "text": c["text"], "relevance_score": round(float(c["score"]), 4)}
+                                  for c in data.get("chunks", [])]
+        return _js({"api_version": MCP_API_VERSION, **data})
 
     async def extract_answer(self, args: dict[str, Any]) -> str:
         from infomesh_b200.search.query import search_local

@@ -27,8 +27,11 @@ class ScoreExplanation:
 
     def to_dict(self) -> dict[str, object]:
         r4 = lambda d: {k: round(v, 4) for k, v in d.items()}  # noqa: E731
+        base = ("bm25", "freshness", "trust", "authority")       # the four signals the reference's tool output breaks a score into
         return {"url": self.url, "title": self.title, "combined_score": round(self.combined_score, 4), "components": r4(self.components),
-                "weights": r4(self.weights), "weighted_contributions": r4(self.weighted), "notes": self.notes}
+                "weights": r4(self.weights), "weighted_contributions": r4(self.weighted), "notes": self.notes,
+                "breakdown": {k: round(self.weighted.get(k, 0.0), 4) for k in base},
+                "dominant_factor": max(self.weighted, key=lambda k: self.weighted.get(k, 0.0)) if self.weighted else ""}
 
 
 @dataclass

@@ -4,6 +4,7 @@
     python scripts/diff_vs_reference.py surface   [/root/reference]     # public names the reference exports that we lack
     python scripts/diff_vs_reference.py behaviour [/root/reference]     # same inputs through both, outputs compared
     python scripts/diff_vs_reference.py interop   [/root/reference]     # wire bytes, hashes, ledger/trust maths, search output
+    python scripts/diff_vs_reference.py mcp       [/root/reference]     # text returned by every MCP tool handler
 
 The reference is imported read-only with tiny stand-ins for the logging / compression wheels that are not installed
 here; nothing from it is copied.  Exit code 1 when differences are found."""
@@ -169,6 +170,11 @@ def main() -> int:
         import os
 
         os.environ.setdefault("INFOMESH_NODE_DATA_DIR", tmp)
+        if mode == "mcp":
+            sys.path.insert(0, str(ref_root))
+            import diff_mcp
+
+            return diff_mcp.run()
         if mode == "interop":
             sys.path.insert(0, str(ref_root))
             import diff_interop

@@ -61,8 +61,10 @@ def test_tool_runtime_end_to_end(tmp_path):
         out["fetch"] = await rt.call("fetch_page", {"url": "https://example.org/python-history"})
         out["ssrf"] = await rt.call("fetch_page", {"url": "http://169.254.169.254/latest"})
         out["status"] = json.loads(await rt.call("status", {}))
-        out["batch"] = json.loads(await rt.call("batch_search", {"queries": ["asyncio", "ownership"], "limit": 2}))
-        out["too_many"] = await rt.call("batch_search", {"queries": [str(i) for i in range(11)]})
+        out["batch"] = json.loads(await rt.call("batch_search", {"queries": ["asyncio", "ownership", ""], "limit": 2, "format": "json"}))
+        out["batch_text"] = await rt.call("batch_search", {"queries": ["asyncio", "ownership"], "limit": 2})
+        out["eleven"] = await rt.call("batch_search", {"queries": ["asyncio"] * 11})
+        out["too_many"] = await rt.call("batch_search", {"queries": []})
         out["suggest"] = json.loads(await rt.call("suggest", {"prefix": "own"}))
         out["hook_bad"] = await rt.call("register_webhook", {"url": "http://127.0.0.1/x"})
         out["ping"] = json.loads(await rt.call("ping", {}))
@@ -84,7 +86,10 @@ def test_tool_runtime_end_to_end(tmp_path):
     assert o["fact"]["verdict"] == "supported" and o["fact"]["supporting"] >= 1
     assert "History of Python" in o["fetch"] and "COPYRIGHT NOTICE" in o["fetch"] and o["ssrf"].startswith("Error [SSRF_BLOCKED]")
     assert o["status"]["documents_indexed"] == 3 and o["status"]["status"] == "ok" and o["status"]["gpu"] == {"enabled": False}
-    assert len(o["batch"]["results"]) == 2 and o["too_many"].startswith("Error [INVALID_PARAM]")
+    assert len(o["batch"]["batch_results"]) == 3 and o["batch"]["batch_results"][2] == {"query": "", "error": "invalid"}
+    assert o["batch"]["batch_results"][0]["query"] == "asyncio" and o["too_many"].startswith("Error [INVALID_PARAM]")
+    assert o["batch_text"].startswith("--- Query 1: asyncio ---\nFound ") and "--- Query 2: ownership ---" in o["batch_text"]
+    assert o["eleven"].count("--- Query ") == 10                                   # extra queries are ignored, not an error
     assert any("Ownership" in s for s in o["suggest"]["suggestions"]) and o["hook_bad"].startswith("Error [SSRF_BLOCKED]")
     assert o["ping"]["status"] == "ok" and "balance" in o["credits"] and o["istats"]["document_count"] == 3
     assert o["rm"].startswith("Removed") and o["rm2"].startswith("Error [NOT_FOUND]") and o["unknown"].startswith("Error [NOT_FOUND]")
