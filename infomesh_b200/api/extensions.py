@@ -47,6 +47,19 @@ def generate_openapi_spec() -> dict[str, Any]:
         tools = {t["name"]: t["inputSchema"] for t in tool_schemas()}
     except Exception:  # noqa: BLE001
         tools = {}
+    # the MCP endpoint and the two generic schemas that clients generated from the reference's spec expect
+    paths["/mcp"] = {"post": {"summary": "MCP endpoint (streamable HTTP transport, port 8081)",
+                              "requestBody": {"required": True, "content": {"application/json": {"schema": {"type": "object"}}}},
+                              "responses": {"200": {"description": "MCP response"}}}}
+    tools = {**tools,
+             "SearchRequest": {"type": "object", "required": ["query"],
+                               "properties": {"query": {"type": "string", "description": "Search query"},
+                                              "limit": {"type": "integer", "default": 10, "maximum": 50},
+                                              "format": {"type": "string", "enum": ["text", "json"], "default": "text"},
+                                              "language": {"type": "string", "description": "ISO 639-1 code"}}},
+             "SearchResult": {"type": "object",
+                              "properties": {"url": {"type": "string"}, "title": {"type": "string"}, "snippet": {"type": "string"},
+                                             "score": {"type": "number"}, "domain": {"type": "string"}, "crawled_at": {"type": "number"}}}}
     return {"openapi": "3.1.0",
             "info": {"title": "InfoMesh API", "version": __version__, "description": "Local admin API and MCP tool schemas of an InfoMesh node."},
             "servers": [{"url": "http://127.0.0.1:8080", "description": "admin API"}, {"url": "http://127.0.0.1:8081", "description": "MCP streamable HTTP (/mcp)"}],

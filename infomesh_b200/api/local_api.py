@@ -32,6 +32,9 @@ except ImportError:  # pragma: no cover — create_admin_app() raises a clear er
 logger = get_logger(__name__)
 
 _LOCAL_ADMIN_HOSTS = frozenset({"127.0.0.1", "::1", "localhost", "testclient"})
+# never leave the box (filesystem layout, peer addresses) — same four keys as reference api/local_api.py:39-46 ...
+_ALWAYS_REDACTED = frozenset({"data_dir", "db_path", "bootstrap_nodes", "persist_dir"})
+# ... plus credentials and identity, masked when set
 _SENSITIVE_KEYS = frozenset({"api_key", "secret", "password", "token", "private_key", "github_email"})
 _RATE_LIMIT_PER_SECOND = 10
 _RATE_MAX_CLIENTS = 10_000
@@ -72,7 +75,9 @@ def _format_duration(seconds: float) -> str:
 
 def _redact_paths(cfg: dict[str, Any]) -> None:
     for k, v in list(cfg.items()):
-        if k in _SENSITIVE_KEYS:
+        if k in _ALWAYS_REDACTED:
+            cfg[k] = "***REDACTED***"
+        elif k in _SENSITIVE_KEYS:
             cfg[k] = "***REDACTED***" if v else v
         elif isinstance(v, Path):
             cfg[k] = str(v)

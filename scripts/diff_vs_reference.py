@@ -5,6 +5,7 @@
     python scripts/diff_vs_reference.py behaviour [/root/reference]     # same inputs through both, outputs compared
     python scripts/diff_vs_reference.py interop   [/root/reference]     # wire bytes, hashes, ledger/trust maths, search output
     python scripts/diff_vs_reference.py mcp       [/root/reference]     # text returned by every MCP tool handler
+    python scripts/diff_vs_reference.py http      [/root/reference]     # every route of the local admin API
 
 The reference is imported read-only with tiny stand-ins for the logging / compression wheels that are not installed
 here; nothing from it is copied.  Exit code 1 when differences are found."""
@@ -170,6 +171,11 @@ def main() -> int:
         import os
 
         os.environ.setdefault("INFOMESH_NODE_DATA_DIR", tmp)
+        if mode == "http":
+            sys.path.insert(0, str(ref_root))
+            import diff_http
+
+            return diff_http.run()
         if mode == "mcp":
             sys.path.insert(0, str(ref_root))
             import diff_mcp

@@ -99,9 +99,11 @@ def test_config_endpoint_redacts_secrets_and_reload_failure_is_a_500(tmp_path, m
     from infomesh_b200.api import local_api
     from infomesh_b200.api.local_api import _redact_paths, create_admin_app
 
-    d = {"node": {"data_dir": Path("/x"), "github_email": "me@example.org"}, "llm": {"api_key": "sk-1", "token": ""}, "n": 3}
+    d = {"node": {"data_dir": Path("/x"), "log_dir": Path("/var/log"), "github_email": "me@example.org"}, "llm": {"api_key": "sk-1", "token": ""},
+         "network": {"bootstrap_nodes": ["/ip4/1.2.3.4/tcp/4001"]}, "n": 3}
     _redact_paths(d)
-    assert d == {"node": {"data_dir": "/x", "github_email": "***REDACTED***"}, "llm": {"api_key": "***REDACTED***", "token": ""}, "n": 3}
+    assert d == {"node": {"data_dir": "***REDACTED***", "log_dir": "/var/log", "github_email": "***REDACTED***"},
+                 "llm": {"api_key": "***REDACTED***", "token": ""}, "network": {"bootstrap_nodes": "***REDACTED***"}, "n": 3}
     bad = tmp_path / "config.toml"
     bad.write_text("[node\nbroken")
     app = create_admin_app(_cfg(tmp_path), config_path=bad)

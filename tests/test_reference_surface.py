@@ -42,3 +42,11 @@ def test_mcp_tool_outputs_contain_everything_the_reference_returns(tmp_path):
     out = subprocess.run([sys.executable, str(ROOT / "scripts" / "diff_vs_reference.py"), "mcp", str(REF)], capture_output=True, text=True,
                          timeout=900, cwd=tmp_path)
     assert out.returncode == 0 and "0 unexpected differences" in out.stdout, out.stdout[-4000:] + out.stderr[-2000:]
+
+
+@pytest.mark.skipif(not (REF / "infomesh").is_dir(), reason="no reference checkout on this machine")
+def test_admin_api_responses_contain_everything_the_reference_returns(tmp_path):
+    pytest.importorskip("fastapi")
+    out = subprocess.run([sys.executable, str(ROOT / "scripts" / "diff_vs_reference.py"), "http", str(REF)], capture_output=True, text=True,
+                         timeout=900, cwd=tmp_path)
+    assert out.returncode == 0 and ", 0 differences" in out.stdout, out.stdout[-4000:] + out.stderr[-2000:]
