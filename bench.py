@@ -14,8 +14,8 @@ weights are random-initialised (no network for datasets / checkpoints).
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
-``--impl reference`` must run the unmodified reference from baseline/_ref; it cannot be installed in this
-image (hatchling build backend, structlog and zstandard are absent) so that arm reports ``unavailable``.
+``--impl reference`` runs the unmodified reference from baseline/_ref (installed by baseline/install_ref.py) through
+its own ``search_hybrid`` on the same synthetic corpus generator -- see baseline/reference_arm.py for what differs.
 ``--impl torch`` is the PyTorch (cuBLAS / SDPA / NCCL) build of the same pipeline, used for A/B.
 """
 from __future__ import annotations
@@ -31,22 +31,12 @@ import time
 
 
 def _reference_arm(args) -> int:
-    ref_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "baseline", "_ref")
-    why = None
-    if not os.path.isdir(os.path.join(ref_dir, "infomesh")):
-        why = ("reference not installable offline: pip needs the 'hatchling' build backend (absent from "
-               "/opt/wheelhouse) and the package imports structlog + zstandard, neither available")
-    else:
-        sys.path.insert(0, ref_dir)
-        try:
-            import infomesh.search.query  # noqa: F401
-        except Exception as exc:  # noqa: BLE001
-            why = f"reference import failed: {type(exc).__name__}: {exc}"
-    if why is None:
-        why = "reference has no GPU/hybrid path runnable here (chromadb + sentence-transformers missing)"
-    if int(os.environ.get("RANK", "0")) == 0:
-        print(json.dumps({"impl": "reference", "unavailable": why}))
-    return 0
+    """Run the unmodified reference (baseline/_ref) through its own search_hybrid(); see baseline/reference_arm.py."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "baseline"))
+    import reference_arm
+
+    return reference_arm.run(args, ClockSampler=ClockSampler)
 
 
 class ClockSampler:
@@ -129,6 +119,13 @@ def main() -> int:
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU candidate exchange: fused peer-memory kernels or NCCL all-gathers (baseline)")
     ap.add_argument("--latency-b1", action="store_true", help="also measure batch-1 p50 latency")
+    ap.add_argument("--ref-docs", type=int, default=1_000_000,
+                    help="reference arm: documents to index (its per-row INSERT+COMMIT build is time-boxed, see below)")
+    ap.add_argument("--ref-build-budget-s", type=float, default=150.0,
+                    help="reference arm: stop indexing after this many seconds and report the size reached")
+    ap.add_argument("--query-mix", choices=["rare", "common"], default="rare",
+                    help="rare: 2-3 selective terms per query; common: every other query also carries one of its "
+                         "document's most frequent terms (long posting lists)")
     args = ap.parse_args()
     if args.impl == "reference":
         return _reference_arm(args)
