@@ -30,6 +30,12 @@ struct AttnParams {
   const float* rel_bias;  // [nH, Sq + Sk - 1] additive bias indexed by (j - i) + (Sq - 1), or null (already * log2e)
   int alias_p;            // single-chunk, HD == 64: P overwrites the (dead) Q+K tiles -> 48 KB smem, 4 CTAs / SM
   const int* cu_seqlens;  // [B+1] packed (unpadded) batch: sequence b owns rows [cu[b], cu[b+1]) of q / k / v / out
+  // MXFP8 output (single-chunk kernel, head_dim 64): the normalised O row is quantised in the epilogue -- each thread
+  // owns exactly one 32-column block -- and written as e4m3 bytes + ue8m0 scales in the SFA chunk layout of the
+  // out-projection GEMM (csrc/gemm/gemm_mxf8.cu), so no bf16 context tensor and no quantiser kernel exist on that path.
+  uint8_t* out_q;         // [rows, ld_outq] e4m3 bytes or null
+  uint8_t* out_sf;        // [ceil(rows/128)][n_kb][512] scale chunks
+  int ld_outq, n_kb;
 };
 
 constexpr int kAttnThreads = 128;
@@ -473,6 +479,41 @@ attn_fwd_1chunk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
     if constexpr (HD == 64) tmem_ld_32x32b_x32(tmem_base + lane_base + half * kCols, v);
     else tmem_ld_32x32b_x16(tmem_base + lane_base + half * kCols, v);
     tmem_ld_wait();
+    if constexpr (HD == 64) {
+      if (p.out_q != nullptr) {
+        // ---- MXFP8 epilogue: this thread's 32 columns are one scale block of the out-projection's K dimension ----
+        float amax = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) amax = fmaxf(amax, fabsf(__uint_as_float(v[i])));
+        float sinv;
+        const uint32_t e = ue8m0_from_amax(amax * inv, sinv);
+        sinv *= inv;
+        if (row < q_len) {
+          const int grow = q_row0 + row;
+          const int col = head * HD + static_cast<int>(half) * 32;
+          uint4* dst = reinterpret_cast<uint4*>(p.out_q + static_cast<size_t>(grow) * p.ld_outq + col);
+          uint4 q0, q1;
+#define IM_F(i) (__uint_as_float(v[i]) * sinv)
+          q0.x = pack_e4m3x4(IM_F(0), IM_F(1), IM_F(2), IM_F(3));
+          q0.y = pack_e4m3x4(IM_F(4), IM_F(5), IM_F(6), IM_F(7));
+          q0.z = pack_e4m3x4(IM_F(8), IM_F(9), IM_F(10), IM_F(11));
+          q0.w = pack_e4m3x4(IM_F(12), IM_F(13), IM_F(14), IM_F(15));
+          q1.x = pack_e4m3x4(IM_F(16), IM_F(17), IM_F(18), IM_F(19));
+          q1.y = pack_e4m3x4(IM_F(20), IM_F(21), IM_F(22), IM_F(23));
+          q1.z = pack_e4m3x4(IM_F(24), IM_F(25), IM_F(26), IM_F(27));
+          q1.w = pack_e4m3x4(IM_F(28), IM_F(29), IM_F(30), IM_F(31));
+#undef IM_F
+          dst[0] = q0;
+          dst[1] = q1;
+          p.out_sf[(static_cast<size_t>(grow >> 7) * p.n_kb + (col >> 7)) * 512 + (grow & 31) * 16 + ((grow & 127) >> 5) * 4 +
+                   ((col & 127) >> 5)] = static_cast<uint8_t>(e);
+        }
+        tc_fence_before();
+        __syncthreads();
+        if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+        return;
+      }
+    }
     uint4 q[kCols / 8];
 #pragma unroll
     for (int j = 0; j < kCols / 8; ++j) {
@@ -629,11 +670,14 @@ kv_append_kernel(const __nv_bfloat16* __restrict__ qkv, int ld_qkv, int inner, _
 
 }  // namespace im
 
-// q: [B*Sq, ldq] with head h at column h*HD (pass base pointer already offset to the Q block); k, v likewise.
-IM_API int im_attn_fwd(const void* q, const void* k, const void* v, void* out, int B, int n_heads, int head_dim, int Sq,
-                       int Sk, int ldq, int ldk, int ldv, int ldo, const int* kv_lens, int causal, int causal_offset,
-                       float scale, const float* rel_bias_log2, void* stream, const int* cu_seqlens) {
+static int attn_fwd_impl(const void* q, const void* k, const void* v, void* out, int B, int n_heads, int head_dim, int Sq,
+                         int Sk, int ldq, int ldk, int ldv, int ldo, const int* kv_lens, int causal, int causal_offset,
+                         float scale, const float* rel_bias_log2, void* stream, const int* cu_seqlens, void* out_q,
+                         int ld_outq, void* out_sf, int n_kb) {
   using namespace im;
+  if (out_q != nullptr && !(head_dim == 64 && Sk <= kAttnBKV && Sq <= kAttnBQ && rel_bias_log2 == nullptr && scale > 0.f &&
+                            (ld_outq % 16) == 0))
+    return set_error("im_attn_fwd_mx", "MXFP8 output: single-chunk path only (head_dim 64, S <= 128, no bias)");
   if (B <= 0 || Sq <= 0 || Sk <= 0) return 0;
   if (cu_seqlens != nullptr && !(Sq == Sk && Sk <= kAttnBKV && rel_bias_log2 == nullptr && !causal && scale > 0.f))
     return set_error("im_attn_fwd", "packed (cu_seqlens) attention: self-attention, max_seqlen <= 128, no bias");
@@ -660,12 +704,16 @@ IM_API int im_attn_fwd(const void* q, const void* k, const void* v, void* out, i
   p.rel_bias = rel_bias_log2;
   p.alias_p = (head_dim == 64 && Sk <= kAttnBKV) ? 1 : 0;
   p.cu_seqlens = cu_seqlens;
+  p.out_q = reinterpret_cast<uint8_t*>(out_q);
+  p.out_sf = reinterpret_cast<uint8_t*>(out_sf);
+  p.ld_outq = ld_outq;
+  p.n_kb = n_kb;
   const int bias_bytes = rel_bias_log2 ? (Sq + Sk) * 4 : 0;
   dim3 grid((Sq + kAttnBQ - 1) / kAttnBQ, n_heads, B);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (Sk <= kAttnBKV && Sq <= kAttnBQ && rel_bias_log2 == nullptr && scale > 0.f) {
     // single-chunk fast path; head_dim 64: O goes out through TMA when a 128-row box cannot spill into the next sequence
-    const int tma_out = (head_dim == 64 && Sq == kAttnBQ && cu_seqlens == nullptr) ? 1 : 0;
+    const int tma_out = (head_dim == 64 && Sq == kAttnBQ && cu_seqlens == nullptr && out_q == nullptr) ? 1 : 0;
     CUtensorMap to = tq;
     if (tma_out &&
         get_tmap_2d(&to, out, static_cast<uint64_t>(B) * Sq, cols, static_cast<uint64_t>(ldo) * 2, kAttnBQ, head_dim, 2, sw))
@@ -700,6 +748,21 @@ IM_API int im_attn_fwd(const void* q, const void* k, const void* v, void* out, i
   }
   IM_LAUNCH_OK("attn_fwd_kernel");
   return 0;
+}
+
+// q: [B*Sq, ldq] with head h at column h*HD (pass base pointer already offset to the Q block); k, v likewise.
+IM_API int im_attn_fwd(const void* q, const void* k, const void* v, void* out, int B, int n_heads, int head_dim, int Sq,
+                       int Sk, int ldq, int ldk, int ldv, int ldo, const int* kv_lens, int causal, int causal_offset,
+                       float scale, const float* rel_bias_log2, void* stream, const int* cu_seqlens) {
+  return attn_fwd_impl(q, k, v, out, B, n_heads, head_dim, Sq, Sk, ldq, ldk, ldv, ldo, kv_lens, causal, causal_offset, scale,
+                       rel_bias_log2, stream, cu_seqlens, nullptr, 0, nullptr, 0);
+}
+// Same, with the context written as MXFP8 (e4m3 bytes [rows, ld_outq] + SFA scale chunks with n_kb k-blocks per row block).
+IM_API int im_attn_fwd_mx(const void* q, const void* k, const void* v, void* out_q, int ld_outq, void* out_sf, int n_kb, int B,
+                          int n_heads, int head_dim, int Sq, int Sk, int ldq, int ldk, int ldv, const int* kv_lens, float scale,
+                          void* stream, const int* cu_seqlens) {
+  return attn_fwd_impl(q, k, v, nullptr, B, n_heads, head_dim, Sq, Sk, ldq, ldk, ldv, 8, kv_lens, 0, 0, scale, nullptr, stream,
+                       cu_seqlens, out_q, ld_outq, out_sf, n_kb);
 }
 
 IM_API int im_attn_decode(const void* q, int ldq, const void* kc, const void* vc, int ld_kv, int s_max,

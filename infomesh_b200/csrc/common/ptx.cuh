@@ -368,6 +368,97 @@ __host__ __device__ constexpr uint32_t umma_idesc_f8(uint32_t M, uint32_t N, uin
   return (1u << 4) | (afmt << 7) | (bfmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+
+// ---------------------------------------------------------------------------------
+// Block-scaled fp8 (MX): kind::mxf8f6f4.block_scale — e4m3 operands with one ue8m0 scale per 32 K-elements per row.
+// Scale factors live in TMEM: for 128 rows x (4 scale bytes = one 128-element K block), lane (r % 32) of EVERY lane
+// quadrant holds, in column (r / 32), the 32-bit word {sf(k0), sf(k1), sf(k2), sf(k3)} of row r.  That is exactly what
+// `tcgen05.cp.32x128b.warpx4` produces from a 512-byte shared-memory chunk laid out as 32 rows x 16 bytes
+// (byte offset (r % 32) * 16 + (r / 32) * 4 + k): each row's 16 bytes become 4 TMEM columns, broadcast to the 4
+// quadrants.  The MMA picks byte k of the word through the a_sf_id / b_sf_id fields of the instruction descriptor
+// (mirrored in bits 31:30 of the TMEM address operand, as CUTLASS' make_runtime_instr_desc_block_scaled does).
+// ---------------------------------------------------------------------------------
+// 1-D bulk copy global -> shared, completion on an mbarrier (bytes: multiple of 16; both addresses 16-byte aligned)
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// shared-memory descriptor of one 512-byte scale chunk (32 rows x 16 bytes, no swizzle: 8-row core matrices 128 B apart)
+__device__ __forceinline__ uint64_t umma_desc_sf_chunk(uint32_t saddr) { return umma_smem_desc(saddr, 0, 128, kSwizzleNone); }
+
+// kind::mxf8f6f4.block_scale instruction descriptor (no c_format field: the accumulator is always fp32).
+// scale_format bit 23 = 1 (ue8m0); a/b format 0 = e4m3; sf ids are OR-ed in per MMA: a_sf_id << 29 | b_sf_id << 4.
+__host__ __device__ constexpr uint32_t umma_idesc_mxf8(uint32_t M, uint32_t N, uint32_t afmt = 0, uint32_t bfmt = 0) {
+  return (afmt << 7) | (bfmt << 10) | ((N >> 3) << 17) | (1u << 23) | ((M >> 4) << 24);
+}
+
+// One 128-element K block of a block-scaled GEMM, as ONE asm statement executed by all 32 lanes of the converged MMA
+// warp (see umma_bf16_kblock64_warp for why): three scale-chunk copies smem -> TMEM (SFA, and the two chunks covering a
+// 192-row B tile), then 4 x (K = 32) MMAs with sf id 0..3, then the commit that frees the smem stage.  tcgen05.cp and
+// tcgen05.mma execute in issue order, so the copies of the NEXT k-block cannot overtake these MMAs and one TMEM scale
+// buffer is enough.
+__device__ __forceinline__ void umma_mxf8_kblock128_warp(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                         uint32_t tmem_sfa, uint32_t tmem_sfb_cp, uint32_t tmem_sfb,
+                                                         uint64_t sfa_desc, uint64_t sfb_desc, uint32_t accumulate_first,
+                                                         uint64_t* commit_bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q, pe;\n"
+      ".reg .b64 a1, a2, a3, b1, b2, b3, sfb1;\n"
+      ".reg .b32 i1, i2, i3, fa1, fa2, fa3, fb1, fb2, fb3, cpb1;\n"
+      "setp.ne.b32 p, %9, 0;\n"
+      "setp.eq.b32 q, %9, %9;\n"
+      "add.s64 a1, %1, 2;\n"
+      "add.s64 b1, %2, 2;\n"
+      "add.s64 a2, %1, 4;\n"
+      "add.s64 b2, %2, 4;\n"
+      "add.s64 a3, %1, 6;\n"
+      "add.s64 b3, %2, 6;\n"
+      "add.s64 sfb1, %8, 32;\n"               // second 512-byte chunk of the B scales (address field is in 16-byte units)
+      "add.u32 cpb1, %5, 4;\n"
+      "or.b32 i1, %3, 0x20000010;\n"          // a_sf_id = b_sf_id = 1
+      "or.b32 i2, %3, 0x40000020;\n"          // 2
+      "or.b32 i3, %3, 0x60000030;\n"          // 3
+      "or.b32 fa1, %4, 0x40000000;\n"
+      "or.b32 fa2, %4, 0x80000000;\n"
+      "or.b32 fa3, %4, 0xC0000000;\n"
+      "or.b32 fb1, %6, 0x40000000;\n"
+      "or.b32 fb2, %6, 0x80000000;\n"
+      "or.b32 fb3, %6, 0xC0000000;\n"
+      "elect.sync _|pe, 0xffffffff;\n"
+      "@pe tcgen05.cp.cta_group::1.32x128b.warpx4 [%4], %7;\n"
+      "@pe tcgen05.cp.cta_group::1.32x128b.warpx4 [%5], %8;\n"
+      "@pe tcgen05.cp.cta_group::1.32x128b.warpx4 [cpb1], sfb1;\n"
+      "@pe tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%4], [%6], p;\n"
+      "@pe tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale [%0], a1, b1, i1, [fa1], [fb1], q;\n"
+      "@pe tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale [%0], a2, b2, i2, [fa2], [fb2], q;\n"
+      "@pe tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale [%0], a3, b3, i3, [fa3], [fb3], q;\n"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%10];\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(tmem_sfa), "r"(tmem_sfb_cp), "r"(tmem_sfb), "l"(sfa_desc), "l"(sfb_desc),
+      "r"(accumulate_first), "r"(smem_u32(commit_bar))
+      : "memory");
+}
+
+// ue8m0 block scale for an absolute maximum: the smallest power of two s with amax / s <= 448 (e4m3 max), as the biased
+// exponent byte, and 1/s as a float.  amax == 0 maps to exponent 1 (any finite scale works for an all-zero block).
+__device__ __forceinline__ uint32_t ue8m0_from_amax(float amax, float& inv_scale) {
+  const float t = amax * (1.0f / 448.0f);
+  uint32_t e = (__float_as_uint(t) + 0x7FFFFFu) >> 23;   // ceil to the next power of two
+  e = e < 1u ? 1u : (e > 253u ? 253u : e);
+  inv_scale = __uint_as_float((254u - e) << 23);          // 2^(127 - e)
+  return e;
+}
+// four floats -> four e4m3 bytes (little-endian: f0 in the low byte), round-to-nearest, saturating
+__device__ __forceinline__ uint32_t pack_e4m3x4(float f0, float f1, float f2, float f3) {
+  uint16_t lo, hi;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(lo) : "f"(f1), "f"(f0));
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(hi) : "f"(f3), "f"(f2));
+  return static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16);
+}
+
 // ---------------------------------------------------------------------------------
 // small numeric helpers
 // ---------------------------------------------------------------------------------

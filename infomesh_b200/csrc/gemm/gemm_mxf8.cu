@@ -1,0 +1,360 @@
+// K6 (block-scaled) — persistent warp-specialised MXFP8 GEMM for sm_100a.
+//
+//   C[M,N] = epilogue( (A ⊙ SFA)[M,K] · (B ⊙ SFB)[N,K]^T )
+//
+// A, B: e4m3 bytes, K contiguous.  SFA / SFB: one ue8m0 scale per 32 K-elements per row, stored in 512-byte chunks that
+// are already in the shape `tcgen05.cp.32x128b.warpx4` wants (see ptx.cuh): chunk (rb, kb) covers rows [128 rb, +128) and
+// K elements [128 kb, +128); byte (r % 32) * 16 + (r / 32) * 4 + (k / 32) % 4.  SFA is [ceil(M/128)][K/128] chunks,
+// SFB is [K/128][ceil(N/128) (+1 pad)] chunks (k-block major so the two chunks a 192-row tile straddles are contiguous).
+//
+// The MMAs are `tcgen05.mma.kind::mxf8f6f4.block_scale` 128 x 192 x 32 with fp32 accumulators in TMEM; scale chunks
+// travel global -> smem with `cp.async.bulk` on the same mbarrier as the TMA operand tiles and smem -> TMEM with
+// `tcgen05.cp` issued by the MMA thread right in front of the four MMAs of the k-block.  BN = 192 because two 256-column
+// accumulators would fill all 512 TMEM columns and leave none for the scales: 2 x 192 + 4 (SFA) + 8 (SFB) = 396.
+// On odd N tiles the 192 rows start 64 rows into a 128-row scale chunk, so the SFB operand address is shifted by two
+// TMEM columns (the same trick CUTLASS' sm100 block-scaled collective uses for CtaN = 192).
+//
+// Epilogues (8 warps, TMEM -> registers -> swizzled smem -> TMA store):
+//   out_mx = 0: bf16  C = act(acc + bias) + residual
+//   out_mx = 1: MXFP8 C = quantise(act(acc + bias)): per row and 32 columns amax -> ue8m0 -> e4m3, scales written in the
+//               SFA chunk layout of the NEXT GEMM (so FFN-up -> GELU -> FFN-down never materialises bf16 activations and
+//               no standalone quantiser kernel runs).
+// Replaces the fp32/cuBLAS linear layers behind infomesh/index/vector_store.py:104-125 and the external LLM reranker
+// (infomesh/search/reranker.py:124-159).
+#include "../common/host.h"
+#include "../common/ptx.cuh"
+#include "../common/tmap_cache.h"
+
+namespace im {
+
+struct MxEpilogue {
+  const float* bias;        // [N] or null
+  uint8_t* c_sf;            // out_mx: scale chunks of the output, [ceil(M/128)][N/128][512]
+  const uint8_t* sfa;       // [ceil(M/128)][K/128][512]
+  const uint8_t* sfb;       // [K/128][n_chunks_b][512]
+  int n_chunks_b;           // chunks per k-block in sfb (>= ceil(N/128) + 1 so an odd last tile may over-read one chunk)
+  int act;                  // 0 none, 1 gelu(erf), 2 relu, 3 gelu(tanh), 4 tanh
+  int out_mx;
+  int has_res;
+  const int* m_dev;         // optional device-side row count (varlen batches under CUDA graphs)
+};
+
+constexpr int kMxBM = 128;
+constexpr int kMxBN = 192;
+constexpr int kMxBK = 128;                 // fp8 elements (= bytes) per k-block
+constexpr int kMxStages = 4;
+constexpr int kMxEpiWarps = 8;
+constexpr int kMxThreads = 64 + 32 * kMxEpiWarps;
+constexpr int kMxABBytes = (kMxBM + kMxBN) * kMxBK;           // 40960: multiple of 1024 (swizzle-128 alignment)
+constexpr int kMxSfBytes = 512 + 1024;                        // SFA chunk + two SFB chunks
+constexpr int kMxStoreTile = 2048;                            // [32 rows x 32 bf16] or [32 rows x 32 B] staging tile
+constexpr int kMxStoreBytes = kMxEpiWarps * 3 * kMxStoreTile; // three 32-column chunks per warp and tile
+constexpr int kMxTmemCols = 512;
+constexpr int kMxSfaCol = 2 * kMxBN;                          // 384
+constexpr int kMxSfbCol = kMxSfaCol + 4;                      // 388
+constexpr int kMxSmemBytes = kMxStages * (kMxABBytes + kMxSfBytes) + kMxStoreBytes + 1024 + 256;
+
+__device__ __forceinline__ void mx_act32(float (&f)[32], int act) {
+  switch (act) {
+    case 1: {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const uint64_t g = gelu_erf2(pk2(f[2 * i], f[2 * i + 1]));
+        upk2(g, f[2 * i], f[2 * i + 1]);
+      }
+    } break;
+    case 2:
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.0f);
+      break;
+    case 3:
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = gelu_tanh(f[i]);
+      break;
+    case 4:
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = tanh_approx(f[i]);
+      break;
+    default:
+      break;
+  }
+}
+
+__global__ void __launch_bounds__(kMxThreads, 1)
+gemm_mxf8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r,
+                 const MxEpilogue ep, int M, int N, int K) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* smem_sf = smem + kMxStages * kMxABBytes;                 // [stage][SFA 512 | SFB 1024]
+  uint8_t* smem_store = smem_sf + kMxStages * kMxSfBytes;           // 1024-aligned: 4 * 1536 = 6144
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_store + kMxStoreBytes);
+  uint64_t* empty_bar = full_bar + kMxStages;
+  uint64_t* tmem_full = empty_bar + kMxStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint64_t* res_bar = tmem_empty + 2;      // [8] residual tiles of one epilogue warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + kMxEpiWarps);
+
+  const uint32_t warp = warp_id();
+  const uint32_t lane = lane_id();
+  pdl_trigger();
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_c);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kMxStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], kMxEpiWarps);
+    }
+    for (int i = 0; i < kMxEpiWarps; ++i) mbar_init(&res_bar[i], 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, kMxTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  pdl_wait();
+  if (ep.m_dev != nullptr) M = min(M, max(0, *ep.m_dev));
+  const int num_m = (M + kMxBM - 1) / kMxBM;
+  const int num_n = (N + kMxBN - 1) / kMxBN;
+  const int num_k = K / kMxBK;
+  const int num_tiles = num_m * num_n;
+
+  if (warp == 0) {
+    // ------------------------------- producer: TMA tiles + bulk scale chunks -------------------------------
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m_blk = t / num_n, n_blk = t % num_n;
+        const int chunk_b = (n_blk * kMxBN) >> 7;     // first 128-row scale chunk the tile touches
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * kMxABBytes;
+          uint8_t* sb = sa + kMxBM * kMxBK;
+          uint8_t* ssf = smem_sf + stage * kMxSfBytes;
+          mbar_expect_tx(&full_bar[stage], kMxABBytes + kMxSfBytes);
+          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kMxBK, m_blk * kMxBM);
+          tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * kMxBK, n_blk * kMxBN);
+          bulk_load(ssf, ep.sfa + (static_cast<size_t>(m_blk) * num_k + kb) * 512, 512, &full_bar[stage]);
+          bulk_load(ssf + 512, ep.sfb + (static_cast<size_t>(kb) * ep.n_chunks_b + chunk_b) * 512, 1024, &full_bar[stage]);
+          if (++stage == kMxStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer (whole warp, one elected lane issues) ----------------------
+    const uint32_t idesc = umma_idesc_mxf8(kMxBM, kMxBN);
+    const uint64_t a_desc0 = umma_desc_k_sw128(smem_u32(smem));
+    const uint64_t b_desc0 = umma_desc_k_sw128(smem_u32(smem) + kMxBM * kMxBK);
+    const uint64_t sfa_desc0 = umma_desc_sf_chunk(smem_u32(smem_sf));
+    const uint64_t sfb_desc0 = umma_desc_sf_chunk(smem_u32(smem_sf) + 512);
+    const uint32_t t_sfa = tmem_base + kMxSfaCol;
+    const uint32_t t_sfb_cp = tmem_base + kMxSfbCol;
+    uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int n_blk = t % num_n;
+      // odd tiles start 64 rows into their first scale chunk: skip two TMEM columns of SFB
+      const uint32_t t_sfb = t_sfb_cp + (((n_blk * kMxBN) & 127) >> 5);
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * kMxBN;
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint64_t soff = static_cast<uint64_t>(stage * (kMxABBytes >> 4));
+        const uint64_t sfoff = static_cast<uint64_t>(stage * (kMxSfBytes >> 4));
+        umma_mxf8_kblock128_warp(d_tmem, a_desc0 + soff, b_desc0 + soff, idesc, t_sfa, t_sfb_cp, t_sfb, sfa_desc0 + sfoff,
+                                 sfb_desc0 + sfoff, kb != 0 ? 1u : 0u, &empty_bar[stage]);
+        if (++stage == kMxStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit_warp(&tmem_full[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------- epilogue warps --------------------------------------------------------
+    const uint32_t quad = warp & 3u;
+    const uint32_t ew = warp - 2;                              // 0..7
+    const int c_lo = static_cast<int>(ew >> 2) * (kMxBN / 2);  // this warp's 96 columns of the tile
+    uint8_t* my_store = smem_store + ew * 3 * kMxStoreTile;
+    const uint32_t row_in_tile = quad * 32u + lane;
+    const int n_kb_out = N >> 7;                               // k-blocks of the NEXT GEMM (out_mx)
+    uint32_t acc = 0, acc_phase = 0, tile_cnt = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tile_cnt) {
+      const int m_blk = t / num_n, n_blk = t % num_n;
+      const int tile_row0 = m_blk * kMxBM + static_cast<int>(quad * 32u);
+      const int col_base = n_blk * kMxBN + c_lo;
+      // the staging tiles are free once the previous tile's stores have been read out of smem
+      if (lane == 0) tma_store_wait_read<0>();
+      __syncwarp();
+      if (ep.has_res && lane == 0) {
+        mbar_expect_tx(&res_bar[ew], 3 * kMxStoreTile);
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+          tma_load_2d(my_store + j * kMxStoreTile, &tmap_r, &res_bar[ew], col_base + 32 * j, tile_row0);
+      }
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      if (ep.has_res) mbar_wait(&res_bar[ew], tile_cnt & 1u);
+#pragma unroll 1
+      for (int j = 0; j < 3; ++j) {
+        const int col0 = col_base + 32 * j;
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + ((quad * 32u) << 16) + acc * kMxBN + c_lo + 32 * j, v);
+        tmem_ld_wait();
+        if (col0 >= N) continue;
+        float f[32];
+        if (ep.bias != nullptr) {
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0) + q4);
+            f[4 * q4 + 0] = __uint_as_float(v[4 * q4 + 0]) + b4.x;
+            f[4 * q4 + 1] = __uint_as_float(v[4 * q4 + 1]) + b4.y;
+            f[4 * q4 + 2] = __uint_as_float(v[4 * q4 + 2]) + b4.z;
+            f[4 * q4 + 3] = __uint_as_float(v[4 * q4 + 3]) + b4.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+        }
+        mx_act32(f, ep.act);
+        uint8_t* tile = my_store + j * kMxStoreTile;
+        if (ep.out_mx) {
+          float amax = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) amax = fmaxf(amax, fabsf(f[i]));
+          float inv;
+          const uint32_t e = ue8m0_from_amax(amax, inv);
+          uint4 q0, q1;
+          q0.x = pack_e4m3x4(f[0] * inv, f[1] * inv, f[2] * inv, f[3] * inv);
+          q0.y = pack_e4m3x4(f[4] * inv, f[5] * inv, f[6] * inv, f[7] * inv);
+          q0.z = pack_e4m3x4(f[8] * inv, f[9] * inv, f[10] * inv, f[11] * inv);
+          q0.w = pack_e4m3x4(f[12] * inv, f[13] * inv, f[14] * inv, f[15] * inv);
+          q1.x = pack_e4m3x4(f[16] * inv, f[17] * inv, f[18] * inv, f[19] * inv);
+          q1.y = pack_e4m3x4(f[20] * inv, f[21] * inv, f[22] * inv, f[23] * inv);
+          q1.z = pack_e4m3x4(f[24] * inv, f[25] * inv, f[26] * inv, f[27] * inv);
+          q1.w = pack_e4m3x4(f[28] * inv, f[29] * inv, f[30] * inv, f[31] * inv);
+          // 32-byte rows; the two halves of lanes l and l^... land in different 16-byte bank groups via the XOR
+          const uint32_t x = (lane >> 2) & 1u;
+          *reinterpret_cast<uint4*>(tile + lane * 32 + ((0u ^ x) << 4)) = x ? q1 : q0;
+          *reinterpret_cast<uint4*>(tile + lane * 32 + ((1u ^ x) << 4)) = x ? q0 : q1;
+          // scale byte of (row, 32-column block) in the consumer GEMM's SFA chunk layout
+          if (tile_row0 + static_cast<int>(lane) < M) {
+            uint8_t* sf = ep.c_sf + (static_cast<size_t>(m_blk) * n_kb_out + (col0 >> 7)) * 512 + lane * 16 + quad * 4 +
+                          ((col0 & 127) >> 5);
+            *sf = static_cast<uint8_t>(e);
+          }
+        } else {
+          // bf16 tile: 64-byte rows, TMA SWIZZLE_64B (16-byte chunk index ^= (row >> 1) & 3)
+          const uint32_t sw = (lane >> 1) & 3u;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            uint4* slot = reinterpret_cast<uint4*>(tile + lane * 64 + ((static_cast<uint32_t>(q4) ^ sw) << 4));
+            if (ep.has_res) {
+              const uint4 rq = *slot;
+              const float2 a = unpack_bf16x2(rq.x), b = unpack_bf16x2(rq.y), cc = unpack_bf16x2(rq.z), d = unpack_bf16x2(rq.w);
+              f[8 * q4 + 0] += a.x; f[8 * q4 + 1] += a.y; f[8 * q4 + 2] += b.x; f[8 * q4 + 3] += b.y;
+              f[8 * q4 + 4] += cc.x; f[8 * q4 + 5] += cc.y; f[8 * q4 + 6] += d.x; f[8 * q4 + 7] += d.y;
+            }
+            uint4 q;
+            q.x = pack_bf16x2(f[8 * q4 + 0], f[8 * q4 + 1]);
+            q.y = pack_bf16x2(f[8 * q4 + 2], f[8 * q4 + 3]);
+            q.z = pack_bf16x2(f[8 * q4 + 4], f[8 * q4 + 5]);
+            q.w = pack_bf16x2(f[8 * q4 + 6], f[8 * q4 + 7]);
+            *slot = q;
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) tma_store_2d(&tmap_c, tile, col0, tile_row0);
+      }
+      // accumulator stage drained -> back to the MMA warp; one bulk group per tile
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_commit();
+        mbar_arrive(&tmem_empty[acc]);
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, kMxTmemCols);
+}
+
+}  // namespace im
+
+// C = act(A·B^T + bias) (+ residual) with MXFP8 operands; out_mx selects bf16 or MXFP8 output (see file header).
+IM_API int im_gemm_mxf8(const void* A, const void* SFA, const void* B, const void* SFB, int n_chunks_b, void* C, void* C_sf,
+                        const float* bias, const void* residual, int M, int N, int K, int lda, int ldb, int ldc, int ldr,
+                        int act, int out_mx, const int* m_dev, int max_ctas, void* stream) {
+  using namespace im;
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if (K % kMxBK) return set_error("im_gemm_mxf8", "K must be a multiple of 128");
+  if (N % 32) return set_error("im_gemm_mxf8", "N must be a multiple of 32");
+  if ((lda % 16) || (ldb % 16)) return set_error("im_gemm_mxf8", "operand row pitches must be multiples of 16 bytes");
+  if (out_mx && (N % 128)) return set_error("im_gemm_mxf8", "MXFP8 output needs N % 128 == 0");
+  if (out_mx && residual != nullptr) return set_error("im_gemm_mxf8", "residual is only fused into the bf16 epilogue");
+  if (n_chunks_b < ((N + kMxBN - 1) / kMxBN * kMxBN + 127) / 128)
+    return set_error("im_gemm_mxf8", "SFB needs ceil(round_up(N,192)/128) chunks per k-block");
+  static bool configured = false;
+  if (!configured) {
+    IM_CUDA_OK(cudaFuncSetAttribute(gemm_mxf8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMxSmemBytes));
+    configured = true;
+  }
+  CUtensorMap ta, tb, tc, tr;
+  if (get_tmap_2d(&ta, A, M, K, static_cast<uint64_t>(lda), kMxBM, kMxBK, 1, TMAP_SW_128)) return -1;
+  if (get_tmap_2d(&tb, B, N, K, static_cast<uint64_t>(ldb), kMxBN, kMxBK, 1, TMAP_SW_128)) return -1;
+  if (out_mx) {
+    if (get_tmap_2d(&tc, C, M, N, static_cast<uint64_t>(ldc), 32, 32, 1, TMAP_SW_NONE)) return -1;
+  } else {
+    if (get_tmap_2d(&tc, C, M, N, static_cast<uint64_t>(ldc) * 2, 32, 32, 2, TMAP_SW_64)) return -1;
+  }
+  tr = tc;
+  if (residual != nullptr && get_tmap_2d(&tr, residual, M, N, static_cast<uint64_t>(ldr) * 2, 32, 32, 2, TMAP_SW_64)) return -1;
+  MxEpilogue ep;
+  ep.bias = bias;
+  ep.c_sf = reinterpret_cast<uint8_t*>(C_sf);
+  ep.sfa = reinterpret_cast<const uint8_t*>(SFA);
+  ep.sfb = reinterpret_cast<const uint8_t*>(SFB);
+  ep.n_chunks_b = n_chunks_b;
+  ep.act = act;
+  ep.out_mx = out_mx;
+  ep.has_res = residual != nullptr ? 1 : 0;
+  ep.m_dev = m_dev;
+  const int tiles = ((M + kMxBM - 1) / kMxBM) * ((N + kMxBN - 1) / kMxBN);
+  int grid = tiles < sm_count() ? tiles : sm_count();
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+  if (grid < 1) grid = 1;
+  IM_CUDA_OK(launch_pdl(gemm_mxf8_kernel, dim3(grid), dim3(kMxThreads), kMxSmemBytes, reinterpret_cast<cudaStream_t>(stream),
+                        ta, tb, tc, tr, ep, M, N, K));
+  IM_LAUNCH_OK("gemm_mxf8_kernel");
+  return 0;
+}

@@ -96,12 +96,59 @@ __device__ __forceinline__ void store_row(__nv_bfloat16* __restrict__ row, int l
   }
 }
 
+
+// MXFP8 twin of store_row: the normalised row as e4m3 bytes + one ue8m0 scale per 32 columns, written in the SFA chunk
+// layout of the consuming block-scaled GEMM (csrc/gemm/gemm_mxf8.cu).  A 32-column scale block is 4 lanes (16-byte
+// layout) or 8 lanes (8-byte layout) of the warp, so its amax is two or three xor-shuffles.
+struct MxRowOut {
+  uint8_t* q;      // [rows, ld] e4m3 bytes (null: no MX output)
+  uint8_t* sf;     // [ceil(rows/128)][H/128][512] scale chunks
+  int ld;
+};
+template <int VEC>
+__device__ __forceinline__ void store_row_mx(const MxRowOut& mx, int grow, int lane, const float (&o)[VEC][4]) {
+  constexpr int n_kb = VEC;  // H / 128
+  uint8_t* qrow = mx.q + static_cast<size_t>(grow) * mx.ld;
+  uint8_t* sfrow = mx.sf + static_cast<size_t>(grow >> 7) * n_kb * 512 + (grow & 31) * 16 + ((grow & 127) >> 5) * 4;
+  if constexpr (VEC % 2 == 0) {
+#pragma unroll
+    for (int c = 0; c < VEC / 2; ++c) {
+      float amax = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) amax = fmaxf(amax, fmaxf(fabsf(o[2 * c][j]), fabsf(o[2 * c + 1][j])));
+      amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+      amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+      float inv;
+      const uint32_t e = ue8m0_from_amax(amax, inv);
+      uint2 u;
+      u.x = pack_e4m3x4(o[2 * c][0] * inv, o[2 * c][1] * inv, o[2 * c][2] * inv, o[2 * c][3] * inv);
+      u.y = pack_e4m3x4(o[2 * c + 1][0] * inv, o[2 * c + 1][1] * inv, o[2 * c + 1][2] * inv, o[2 * c + 1][3] * inv);
+      const int col = c * 256 + lane * 8;
+      *reinterpret_cast<uint2*>(qrow + col) = u;
+      if ((lane & 3) == 0) sfrow[(col >> 7) * 512 + ((col & 127) >> 5)] = static_cast<uint8_t>(e);
+    }
+  } else {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      float amax = fmaxf(fmaxf(fabsf(o[v][0]), fabsf(o[v][1])), fmaxf(fabsf(o[v][2]), fabsf(o[v][3])));
+      amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+      amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+      amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
+      float inv;
+      const uint32_t e = ue8m0_from_amax(amax, inv);
+      const int col = v * 128 + lane * 4;
+      *reinterpret_cast<uint32_t*>(qrow + col) = pack_e4m3x4(o[v][0] * inv, o[v][1] * inv, o[v][2] * inv, o[v][3] * inv);
+      if ((lane & 7) == 0) sfrow[v * 512 + (lane >> 3)] = static_cast<uint8_t>(e);
+    }
+  }
+}
+
 // H must be a multiple of 128 and <= 1024 (VEC = H / 128 groups of 4 per lane)
 template <int VEC>
 __device__ __forceinline__ void ln_finish(float (&x)[VEC][4], const float* gamma, const float* beta, float eps,
                                           __nv_bfloat16* out_row, int lane, bool rms_only,
                                           __nv_bfloat16* const* peer_rows = nullptr, size_t peer_off = 0, int n_peer = 0,
-                                          int skip_peer = -1) {
+                                          int skip_peer = -1, const MxRowOut* mx = nullptr, int grow = 0) {
   constexpr int H = VEC * 128;
   float s = 0.f;
 #pragma unroll
@@ -130,6 +177,7 @@ __device__ __forceinline__ void ln_finish(float (&x)[VEC][4], const float* gamma
     x[v][3] = (x[v][3] - mean) * rstd * g.w + b.w;
   }
   if (out_row != nullptr) store_row<VEC>(out_row, lane, x);
+  if (mx != nullptr && mx->q != nullptr) store_row_mx<VEC>(*mx, grow, lane, x);
   // fused all-gather: the normalised row also lands in every peer's full-sequence buffer (NVLink stores)
   for (int p = 0; p < n_peer; ++p)
     if (p != skip_peer) store_row<VEC>(peer_rows[p] + peer_off, lane, x);
@@ -141,7 +189,7 @@ embed_ln_kernel(const int* __restrict__ ids, const int* __restrict__ pos_ids, co
                 const __nv_bfloat16* __restrict__ word, const __nv_bfloat16* __restrict__ pos,
                 const __nv_bfloat16* __restrict__ type, const float* __restrict__ gamma, const float* __restrict__ beta,
                 float eps, int n_tokens, int seq_len, int pos_offset, int vocab, int max_pos,
-                __nv_bfloat16* __restrict__ out, const int* __restrict__ n_rows_dev) {
+                __nv_bfloat16* __restrict__ out, const int* __restrict__ n_rows_dev, const MxRowOut mx) {
   constexpr int H = VEC * 128;
   const int row = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -161,7 +209,7 @@ embed_ln_kernel(const int* __restrict__ ids, const int* __restrict__ pos_ids, co
     store_row<VEC>(out + static_cast<size_t>(row) * H, lane, x);
     return;
   }
-  ln_finish<VEC>(x, gamma, beta, eps, out + static_cast<size_t>(row) * H, lane, false);
+  ln_finish<VEC>(x, gamma, beta, eps, out + static_cast<size_t>(row) * H, lane, false, nullptr, 0, 0, -1, &mx, row);
 }
 
 // out[row] = LN( sum_{p<P} in[p][row] + residual[row] );  in_stride_p = elements between partial p and p+1
@@ -184,6 +232,7 @@ struct SumLnComm {
   int world;
   int rank;
   const int* n_rows_dev;  // optional device-side row count (unpadded batches): rows >= *n_rows_dev are skipped
+  MxRowOut mx;            // optional MXFP8 copy of the normalised rows (feeds the block-scaled GEMMs)
 };
 
 template <int VEC>
@@ -223,10 +272,10 @@ sum_ln_kernel(const __nv_bfloat16* in, size_t in_stride_p, int P,  // in / resid
     if (residual != nullptr) load_row<VEC, true>(residual + static_cast<size_t>(row) * H, lane, x);
     if (sum_out != nullptr)  // pre-norm architectures keep the un-normalised residual stream
       store_row<VEC>(sum_out + static_cast<size_t>(row) * H, lane, x);
-    if (out != nullptr || cm.peer_out != nullptr) {
+    if (out != nullptr || cm.peer_out != nullptr || cm.mx.q != nullptr) {
       const size_t grow = static_cast<size_t>(cm.out_row_offset) + row;
       ln_finish<VEC>(x, gamma, beta, eps, out != nullptr ? out + static_cast<size_t>(row) * H : nullptr, lane, rms_only != 0,
-                     cm.peer_out, grow * H, cm.peer_out != nullptr ? cm.world : 0);
+                     cm.peer_out, grow * H, cm.peer_out != nullptr ? cm.world : 0, -1, &cm.mx, row);
     }
   }
   if (cm.peer_out_flags != nullptr) {
@@ -467,28 +516,49 @@ quantize_rows_fp8_kernel(const __nv_bfloat16* __restrict__ x, int ld, int K, int
     default: return im::set_error("hidden size", "H must be 128*{1,2,3,4,6,8}"); \
   }
 
-IM_API int im_embed_ln(const int* ids, const int* pos_ids, const int* type_ids, const void* word, const void* pos,
-                       const void* type, const float* gamma, const float* beta, float eps, int n_tokens, int seq_len,
-                       int pos_offset, int vocab, int max_pos, int H, void* out, void* stream, const int* n_rows_dev) {
+static int embed_ln_impl(const int* ids, const int* pos_ids, const int* type_ids, const void* word, const void* pos,
+                         const void* type, const float* gamma, const float* beta, float eps, int n_tokens, int seq_len,
+                         int pos_offset, int vocab, int max_pos, int H, void* out, void* stream, const int* n_rows_dev,
+                         void* mx_q, int mx_ld, void* mx_sf) {
   using namespace im;
   if (n_tokens <= 0) return 0;
   if (H % 128) return set_error("im_embed_ln", "H must be a multiple of 128");
+  if (mx_q != nullptr && (gamma == nullptr || (mx_ld % 16))) return set_error("im_embed_ln", "MX output needs a LayerNorm and a 16-byte row pitch");
+  MxRowOut mx;
+  mx.q = reinterpret_cast<uint8_t*>(mx_q);
+  mx.sf = reinterpret_cast<uint8_t*>(mx_sf);
+  mx.ld = mx_ld;
   const int grid = (n_tokens + kRowsPerBlock - 1) / kRowsPerBlock;
   auto s = reinterpret_cast<cudaStream_t>(stream);
   IM_DISPATCH_VEC(H, IM_CUDA_OK(launch_pdl(embed_ln_kernel<VEC>, dim3(grid), dim3(kRowsPerBlock * 32), 0, s, ids, pos_ids,
                                            type_ids, (const __nv_bfloat16*)word, (const __nv_bfloat16*)pos,
                                            (const __nv_bfloat16*)type, gamma, beta, eps, n_tokens, seq_len, pos_offset,
-                                           vocab, max_pos, (__nv_bfloat16*)out, n_rows_dev)));
+                                           vocab, max_pos, (__nv_bfloat16*)out, n_rows_dev, mx)));
   IM_LAUNCH_OK("embed_ln_kernel");
   return 0;
 }
+IM_API int im_embed_ln(const int* ids, const int* pos_ids, const int* type_ids, const void* word, const void* pos,
+                       const void* type, const float* gamma, const float* beta, float eps, int n_tokens, int seq_len,
+                       int pos_offset, int vocab, int max_pos, int H, void* out, void* stream, const int* n_rows_dev) {
+  return embed_ln_impl(ids, pos_ids, type_ids, word, pos, type, gamma, beta, eps, n_tokens, seq_len, pos_offset, vocab, max_pos,
+                       H, out, stream, n_rows_dev, nullptr, 0, nullptr);
+}
+// embed + LayerNorm that also emits the MXFP8 copy (e4m3 [rows, mx_ld] + SFA scale chunks) the first QKV GEMM consumes
+IM_API int im_embed_ln_mx(const int* ids, const int* pos_ids, const int* type_ids, const void* word, const void* pos,
+                          const void* type, const float* gamma, const float* beta, float eps, int n_tokens, int seq_len,
+                          int pos_offset, int vocab, int max_pos, int H, void* out, void* stream, const int* n_rows_dev,
+                          void* mx_q, int mx_ld, void* mx_sf) {
+  return embed_ln_impl(ids, pos_ids, type_ids, word, pos, type, gamma, beta, eps, n_tokens, seq_len, pos_offset, vocab, max_pos,
+                       H, out, stream, n_rows_dev, mx_q, mx_ld, mx_sf);
+}
 
-IM_API int im_sum_ln(const void* in, long long in_stride_p, int P, const void* residual, const float* gamma,
+static int sum_ln_impl(const void* in, long long in_stride_p, int P, const void* residual, const float* gamma,
                      const float* beta, float eps, int rms_only, int n_rows, int H, void* out, void* sum_out,
                      const uint32_t* arrive_flags, uint32_t* arrive_state, unsigned arrivals_per_block, int blocks_per_src,
                      void* const* peer_out, uint32_t* const* peer_out_flags, int out_row_offset, int world, int rank,
-                     void* stream, const int* n_rows_dev) {
+                     void* stream, const int* n_rows_dev, void* mx_q, int mx_ld, void* mx_sf) {
   using namespace im;
+  if (mx_q != nullptr && ((mx_ld % 16) || out_row_offset != 0)) return set_error("im_sum_ln", "MX output: 16-byte row pitch, no row offset");
   if (n_rows <= 0) return 0;
   if (H % 128) return set_error("im_sum_ln", "H must be a multiple of 128");
   if (arrive_flags != nullptr && P > 32) return set_error("im_sum_ln", "at most 32 partial sources");
@@ -503,6 +573,9 @@ IM_API int im_sum_ln(const void* in, long long in_stride_p, int P, const void* r
   cm.world = world;
   cm.rank = rank;
   cm.n_rows_dev = n_rows_dev;
+  cm.mx.q = reinterpret_cast<uint8_t*>(mx_q);
+  cm.mx.sf = reinterpret_cast<uint8_t*>(mx_sf);
+  cm.mx.ld = mx_ld;
   const int grid = (n_rows + kRowsPerBlock - 1) / kRowsPerBlock;
   auto s = reinterpret_cast<cudaStream_t>(stream);
   IM_DISPATCH_VEC(H, IM_CUDA_OK(launch_pdl(sum_ln_kernel<VEC>, dim3(grid), dim3(kRowsPerBlock * 32), 0, s,
@@ -511,6 +584,21 @@ IM_API int im_sum_ln(const void* in, long long in_stride_p, int P, const void* r
                                            (__nv_bfloat16*)out, (__nv_bfloat16*)sum_out, cm)));
   IM_LAUNCH_OK("sum_ln_kernel");
   return 0;
+}
+IM_API int im_sum_ln(const void* in, long long in_stride_p, int P, const void* residual, const float* gamma,
+                     const float* beta, float eps, int rms_only, int n_rows, int H, void* out, void* sum_out,
+                     const uint32_t* arrive_flags, uint32_t* arrive_state, unsigned arrivals_per_block, int blocks_per_src,
+                     void* const* peer_out, uint32_t* const* peer_out_flags, int out_row_offset, int world, int rank,
+                     void* stream, const int* n_rows_dev) {
+  return sum_ln_impl(in, in_stride_p, P, residual, gamma, beta, eps, rms_only, n_rows, H, out, sum_out, arrive_flags,
+                     arrive_state, arrivals_per_block, blocks_per_src, peer_out, peer_out_flags, out_row_offset, world, rank,
+                     stream, n_rows_dev, nullptr, 0, nullptr);
+}
+// LayerNorm / RMSNorm that also emits the MXFP8 copy of the normalised rows (the next block-scaled GEMM's A operand)
+IM_API int im_sum_ln_mx(const void* in, const void* residual, const float* gamma, const float* beta, float eps, int rms_only,
+                        int n_rows, int H, void* out, void* stream, const int* n_rows_dev, void* mx_q, int mx_ld, void* mx_sf) {
+  return sum_ln_impl(in, 0, 1, residual, gamma, beta, eps, rms_only, n_rows, H, out, nullptr, nullptr, nullptr, 0, 0, nullptr,
+                     nullptr, 0, 1, 0, stream, n_rows_dev, mx_q, mx_ld, mx_sf);
 }
 
 IM_API int im_pool_norm(const void* h, const int* lengths, int batch, int seq_len, int H, int mode, int normalize,

@@ -1,0 +1,42 @@
+"""MXFP8 helpers (ops/mx.py): quantiser oracle, scale-chunk packing round trips."""
+import torch
+
+from infomesh_b200.ops import mx as MX
+
+
+def test_quantize_ref_bounds_and_roundtrip():
+    torch.manual_seed(0)
+    x = torch.randn(70, 256) * torch.logspace(-3, 3, 70)[:, None]
+    q, e = MX.quantize_ref(x)
+    assert q.shape == (70, 256) and e.shape == (70, 8) and q.dtype == torch.uint8
+    back = MX.dequantize(q, e)
+    blk = x.reshape(70, 8, 32)
+    amax = blk.abs().amax(-1, keepdim=True)
+    # e4m3 keeps 3 mantissa bits: error <= 2^-4 of the block maximum's power-of-two ceiling
+    assert ((back.reshape(70, 8, 32) - blk).abs() <= amax * 2 ** -3 + 1e-12).all()
+    scale = (e.int() << 23).view(torch.float32)
+    assert (amax.squeeze(-1) / scale <= 448.0).all()          # never saturates
+    assert (amax.squeeze(-1) / scale > 448.0 / 2 - 1e-3).all()  # and the scale is the smallest such power of two
+
+
+def test_zero_block_is_finite():
+    q, e = MX.quantize_ref(torch.zeros(4, 64))
+    assert torch.isfinite(MX.dequantize(q, e)).all() and (q == 0).all()
+
+
+def test_sfa_pack_roundtrip_and_layout():
+    e = torch.arange(300 * 8, dtype=torch.int64).reshape(300, 8).remainder(251).to(torch.uint8)
+    ch = MX.pack_sfa(e)
+    assert ch.shape == (3, 2, 512)
+    assert torch.equal(MX.unpack_sfa(ch, 300), e)
+    r, s = 128 + 37 + 64, 5                         # row 229 -> block 1, m1 = 3, m0 = 5;  s = 5 -> kb 1, byte 1
+    assert ch[1, 1, 5 * 16 + 3 * 4 + 1] == e[r, s]
+
+
+def test_sfb_pack_layout():
+    e = torch.arange(768 * 24).reshape(768, 24).remainder(241).to(torch.uint8)
+    ch = MX.pack_sfb(e)
+    assert ch.shape == (6, MX.sfb_chunks(768), 512) and MX.sfb_chunks(768) == 6
+    n, s = 5 * 128 + 2 * 32 + 9, 13                 # chunk 5, m1 = 2, m0 = 9; kb 3, byte 1
+    assert ch[3, 5, 9 * 16 + 2 * 4 + 1] == e[n, s]
+    assert MX.sfb_chunks(384) == 3 and MX.sfb_chunks(2304) == 18 and MX.sfb_chunks(1152) == 9
