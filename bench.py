@@ -97,27 +97,44 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def _peaks() -> dict:
+    """Roofline denominators: the driver-measured MEASURED_PEAKS.json when present, else the profiling guide's fallback."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    try:
+        with open(os.path.join(here, "MEASURED_PEAKS.json")) as fh:
+            p = json.load(fh)
+        return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_tflops": float(p["bf16_tflops"]),
+                "bf16_tflops_sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "source": "measured"}
+    except Exception:  # noqa: BLE001
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
 def main() -> int:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="fused", choices=["fused", "torch", "reference"])
+    ap.add_argument("--config", default="hybrid", choices=["hybrid", "dense_b1", "rag", "index_build"],
+                    help="BASELINE.json config: hybrid = #3 (headline); dense_b1 = #2; rag = #4; index_build = #5")
     ap.add_argument("--docs", type=int, default=10_000_000, help="total documents in the index (all ranks)")
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--pair-seq", type=int, default=128)
     ap.add_argument("--no-rerank", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-varlen", action="store_true", help="run the cross-encoder on padded [pairs, seq_len] batches")
-    ap.add_argument("--no-padded-arm", action="store_true", help="skip the extra padded-cross-encoder measurement")
-    ap.add_argument("--precision", choices=["bf16", "fp8"], default="bf16",
-                    help="fp8: cross-encoder projections as e4m3 GEMMs (reported as dtype fp8; NOT the headline config)")
+    ap.add_argument("--quick", action="store_true", help="headline numbers only (skip the sustained loop, stage table and A/B arms)")
+    ap.add_argument("--precision", choices=["mxfp8", "bf16", "fp8"], default=os.environ.get("INFOMESH_B200_BENCH_PRECISION", "mxfp8"),
+                    help="cross-encoder GEMM precision.  mxfp8 (default): block-scaled e4m3 x e4m3 with ue8m0 scales per 32 "
+                         "(tcgen05 kind::mxf8f6f4.block_scale), fp32 accumulation, quantisers fused into LayerNorm / attention "
+                         "/ GELU epilogues; bf16: round-1 configuration")
     ap.add_argument("--rerank-chunks", type=int, default=1, help="cross-encoder sub-batches per step (L2 residency)")
-    ap.add_argument("--pipeline", choices=["auto", "on", "off"], default="auto",
-                    help="keep two batches in flight (retrieval of batch i+1 overlaps the cross-encoder of batch i); "
-                         "auto = on when a rank's cross-encoder share is small enough to be latency-bound")
+    ap.add_argument("--pipeline", choices=["on", "off"], default="on",
+                    help="on: `value` keeps two batches in flight (retrieval of batch i+1 overlaps the cross-encoder of "
+                         "batch i) at EVERY N, and one_batch_in_flight is reported beside it; off: `value` is one batch in flight")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU candidate exchange: fused peer-memory kernels or NCCL all-gathers (baseline)")
+    ap.add_argument("--sustain-s", type=float, default=5.0, help="length of the sustained-throughput loop")
     ap.add_argument("--latency-b1", action="store_true", help="also measure batch-1 p50 latency")
     ap.add_argument("--ref-docs", type=int, default=1_000_000,
                     help="reference arm: documents to index (its per-row INSERT+COMMIT build is time-boxed, see below)")
@@ -129,6 +146,12 @@ def main() -> int:
     args = ap.parse_args()
     if args.impl == "reference":
         return _reference_arm(args)
+    if args.config != "hybrid":
+        here = os.path.dirname(os.path.abspath(__file__))
+        sys.path.insert(0, os.path.join(here, "scripts"))
+        import bench_configs
+
+        return bench_configs.run(args, ClockSampler=ClockSampler, peaks=_peaks())
 
     import torch
 
@@ -146,6 +169,7 @@ def main() -> int:
     if world != args.gpus and rank == 0:
         print(f"[bench] note: WORLD_SIZE={world} but --gpus {args.gpus}; using WORLD_SIZE", file=sys.stderr)
     assert args.warmup >= 3 or args.steps <= 2, "timing rules: at least 3 warm-up steps"
+    peaks = _peaks()
 
     n_global = args.docs
     per = (n_global + world - 1) // world
@@ -158,15 +182,18 @@ def main() -> int:
     torch.cuda.synchronize()
     build_s = time.time() - t0
 
+    precision = args.precision if args.impl == "fused" else "bf16"
     hcfg = HybridConfig(nq=args.batch, pair_seq=args.pair_seq, rerank=not args.no_rerank, backend=args.impl,
-                        use_graph=not args.no_graph, exchange=args.exchange, varlen=not args.no_varlen, rerank_chunks=args.rerank_chunks, precision=args.precision)
-    eng = HybridEngine(shard, hcfg, docs_per_shard=(n_global if world > 1 else n_local))
+                        use_graph=not args.no_graph, exchange=args.exchange, varlen=not args.no_varlen,
+                        rerank_chunks=args.rerank_chunks, precision=precision, strict_graph=True)
+    dps = n_global if world > 1 else n_local
+    eng = HybridEngine(shard, hcfg, docs_per_shard=dps)
 
     # ---- query batches on pinned host memory (distinct per step so nothing is cached between iterations) ----
     n_batches = args.steps + args.warmup
     qcfg = SynthConfig(n_docs=n_global, n_docs_global=n_global)
     q_terms, q_tok, q_len, _ = make_queries(qcfg, n_batches * args.batch, max_terms=hcfg.max_terms,
-                                            max_q_tokens=hcfg.max_q_tokens, device=dev)
+                                            max_q_tokens=hcfg.max_q_tokens, device=dev, mix=args.query_mix)
     enc_ids = torch.zeros((n_batches * args.batch, hcfg.enc_seq), dtype=torch.int32)
     span = eng.encoder.cfg.vocab_size - 1000
     qt = (1000 + (q_tok.long() * 40503 % span)).to(torch.int32)
@@ -191,7 +218,7 @@ def main() -> int:
     d2h_bytes = out_s_host.numel() * 4 + out_i_host.numel() * 8
     dev_batches = [tuple(x.to(dev) for x in b) for b in batches]
 
-    def timed(run_step, n_warm, n_steps, offset=0):
+    def timed(run_step, n_warm, n_steps):
         for i in range(n_warm):
             run_step(i)
         D.barrier()
@@ -207,17 +234,19 @@ def main() -> int:
         total = evs[0].elapsed_time(evs[-1])
         return D.all_reduce_max(total), per_step
 
-    # ---- (a) device-timed pipeline, inputs already resident (kernel-level number) ----
-    def step_dev(i):
-        eng.load_inputs(*dev_batches[i % n_batches])
-        eng.run()
+    def dev_step(e):
+        def f(i):
+            e.load_inputs(*dev_batches[i % n_batches])
+            e.run()
+        return f
 
-    # ---- (b) end to end through the public API: pinned H2D every step + D2H of the result ----
-    def step_e2e(i):
-        eng.search_batch(*batches[i % n_batches], out_scores_host=out_s_host, out_ids_host=out_i_host)
+    def e2e_step(e):
+        def f(i):
+            e.search_batch(*batches[i % n_batches], out_scores_host=out_s_host, out_ids_host=out_i_host)
+        return f
 
-    # ---- pipelined serving (the engine's throughput mode): retrieval of batch i+1 overlaps the cross-encoder of
-    #      batch i on a second stream; every batch still goes through every kernel inside the timed region ----
+    # pipelined serving (the engine's throughput mode): retrieval of batch i+1 overlaps the cross-encoder of batch i on a
+    # second stream; every batch still goes through every kernel inside the timed region
     def timed_pipe(e, src, host_out, n_warm, n_steps):
         for i in range(n_warm):
             e.submit(*src[i % n_batches], out_scores_host=host_out[0], out_ids_host=host_out[1])
@@ -236,66 +265,137 @@ def main() -> int:
         per = [evs[i].elapsed_time(evs[i + 1]) for i in range(n_steps)]
         return D.all_reduce_max(evs[0].elapsed_time(evs[-1])), per
 
+    def qps(ms, steps):
+        return round(B * steps / (ms / 1e3), 2)
+
+    def summary(ms, per, steps, **extra):
+        return dict({"value": qps(ms, steps), "unit": "queries/s", "ms_per_step": round(ms / steps, 4),
+                     "p50_step_ms": round(statistics.median(per), 4)}, **extra)
+
+    K, W = args.steps, args.warmup
     sampler = ClockSampler(ctx.local_rank)
     launches = eng.launches_per_step()
-    # measured: +13 % at <= 160 pairs/rank (latency-bound kernels interleave), -2 % at >= 640 pairs/rank (persistent GEMMs own the SMs)
-    want_pipe = args.pipeline == "on" or (args.pipeline == "auto" and eng.nq_local * hcfg.n_rerank <= 400)
-    pipelined = want_pipe and eng.pipeline_supported()
-    unpipelined = None
+    pipelined = args.pipeline == "on" and eng.pipeline_supported()
+    # ---- (a) one batch in flight, device-timed (per-batch latency; the same methodology at every N) ----
+    if not pipelined:
+        sampler.start()
+    lat_ms, lat_steps = timed(dev_step(eng), W, K)
+    if not pipelined:
+        clocks = sampler.stop()
+    one_in_flight = summary(lat_ms, lat_steps, K, note="one batch in flight: per-batch latency, device-timed")
+    # ---- (b) two batches in flight (throughput mode), device-timed: the headline `value` at every N ----
     if pipelined:
-        # per-batch latency: one batch at a time through the single-graph path
-        lat_ms, lat_steps = timed(step_dev, args.warmup, args.steps)
-        unpipelined = {"value": round(args.batch * args.steps / (lat_ms / 1e3), 2), "unit": "queries/s",
-                       "ms_per_step": round(lat_ms / args.steps, 4), "p50_step_ms": round(statistics.median(lat_steps), 4),
-                       "note": "one batch in flight (per-batch latency); `value` keeps two batches in flight"}
         sampler.start()
-        total_ms, per_step = timed_pipe(eng, dev_batches, (None, None), args.warmup, args.steps)
+        total_ms, per_step = timed_pipe(eng, dev_batches, (None, None), W, K)
         clocks = sampler.stop()
-        e2e_ms, e2e_steps = timed_pipe(eng, batches, (out_s_host, out_i_host), args.warmup, args.steps)
+        e2e_ms, e2e_steps = timed_pipe(eng, batches, (out_s_host, out_i_host), W, K)
     else:
-        sampler.start()
-        total_ms, per_step = timed(step_dev, args.warmup, args.steps)
-        clocks = sampler.stop()
-        e2e_ms, e2e_steps = timed(step_e2e, args.warmup, args.steps)
-    # sanity: results are real document ids
+        total_ms, per_step = lat_ms, lat_steps
+        e2e_ms, e2e_steps = timed(e2e_step(eng), W, K)
     ids_ok = bool((out_i_host[:, 0] >= 0).float().mean() > 0.5)
 
-    # ---- (c) the same pipeline with the cross-encoder forced onto padded [pairs, seq_len] batches, for transparency:
-    #          `value` is the product (unpadded); this is what the step costs when every pair is computed at seq_len
-    padded = None
-    if hcfg.rerank and hcfg.varlen and args.impl == "fused" and not args.no_padded_arm:
-        from dataclasses import replace as _replace
-
-        eng_p = HybridEngine(shard, _replace(hcfg, varlen=False), encoder=eng.encoder, reranker=eng.reranker,
-                             docs_per_shard=(n_global if world > 1 else n_local))
-
-        def step_pad(i):
-            eng_p.load_inputs(*dev_batches[i % n_batches])
-            eng_p.run()
-
+    extras = {}
+    if not args.quick:
+        # ---- (c) sustained: the same end-to-end loop for >= sustain_s seconds (power / thermal steady state) ----
+        est_ms = max(e2e_ms / K, 1e-3)
+        n_sus = max(K, int(args.sustain_s * 1e3 / est_ms))
+        sus_sampler = ClockSampler(ctx.local_rank)
+        sus_sampler.start()
         if pipelined:
-            pad_ms, _ = timed_pipe(eng_p, dev_batches, (None, None), args.warmup, args.steps)
+            sus_ms, sus_per = timed_pipe(eng, batches, (out_s_host, out_i_host), 3, n_sus)
         else:
-            pad_ms, _ = timed(step_pad, args.warmup, args.steps)
-        padded = {"value": round(B * args.steps / (pad_ms / 1e3), 2), "unit": "queries/s",
-                  "ms_per_step": round(pad_ms / args.steps, 4),
-                  "note": f"cross-encoder on padded [{B * hcfg.n_rerank // world} x {args.pair_seq}] batches per rank"}
-        del eng_p
+            sus_ms, sus_per = timed(e2e_step(eng), 3, n_sus)
+        sus_clocks = sus_sampler.stop()
+        sp = sorted(sus_per)
+        extras["sustained"] = {"value": qps(sus_ms, n_sus), "unit": "queries/s", "seconds": round(sus_ms / 1e3, 2), "steps": n_sus,
+                               "ms_per_step": round(sus_ms / n_sus, 4), "p50_step_ms": round(sp[len(sp) // 2], 4),
+                               "p99_step_ms": round(sp[min(len(sp) - 1, int(0.99 * len(sp)))], 4), "clocks": sus_clocks,
+                               "note": "end-to-end (pinned H2D + D2H every step), same engine and mode as `e2e`"}
+        # ---- (d) per-stage device time + roofline fractions (eager launches with events between the stages) ----
+        eng.load_inputs(*dev_batches[0])
+        st = eng.stage_times()
+        roof = {}
+        vec_bytes = shard.vectors.numel() * shard.vectors.element_size()
+        if st["dense_local"] > 0:
+            gbs = vec_bytes / (st["dense_local"] * 1e-3) / 1e9
+            roof["dense_local"] = {"bytes": vec_bytes, "achieved_gbs": round(gbs, 1), "frac_of_hbm": round(gbs / peaks["hbm_gbs"], 3)}
+        if hcfg.rerank and getattr(eng, "last_pair_lens", None) is not None:
+            lens = eng.last_pair_lens.float()
+            toks = float(lens.sum().item()) if hcfg.varlen and args.impl == "fused" else float(lens.numel() * args.pair_seq)
+            mean_len = float(lens.mean().item())
+            fl = toks * eng.reranker.flops_per_token(int(mean_len))
+            tf = fl / (st["cross_encoder"] * 1e-3) / 1e12
+            roof["cross_encoder"] = {"flops": fl, "achieved_tflops": round(tf, 1),
+                                     "frac_of_bf16_sustained": round(tf / peaks["bf16_tflops_sustained"], 3),
+                                     "frac_of_bf16_burst": round(tf / peaks["bf16_tflops"], 3),
+                                     "note": "fractions are against the MEASURED cuBLAS bf16 peaks; an fp8 kernel may exceed 1.0 "
+                                             "(nominal dense fp8 peak 4500 TFLOP/s)"}
+        enc_fl = B * hcfg.enc_seq * eng.encoder.flops_per_token(hcfg.enc_seq)
+        roof["encode"] = {"flops": enc_fl, "achieved_tflops": round(enc_fl / (st["encode"] * 1e-3) / 1e12, 2),
+                          "note": "12 tiny layers on 64 x 32 tokens: launch-latency bound, not a roofline kernel"}
+        extras["stages_ms"] = st
+        extras["roofline"] = dict(roof, peaks=peaks)
+        # ---- (e) retrieval only (no reranker): the like-for-like number against the reference arm, which has none ----
+        if hcfg.rerank:
+            from dataclasses import replace as _replace
+
+            eng_r = HybridEngine(shard, _replace(hcfg, rerank=False), encoder=eng.encoder, docs_per_shard=dps)
+            r_ms, r_per = timed(dev_step(eng_r), W, K)
+            r2_ms, r2_per = timed(e2e_step(eng_r), W, K)
+            extras["retrieval_only"] = summary(r_ms, r_per, K, e2e_value=qps(r2_ms, K),
+                                               note="encode + dense + BM25 + exchange + RRF top-10, no cross-encoder")
+            eng_r._graph = None
+            del eng_r
+        # ---- (f) A/B arms on the same shard: the PyTorch (cuBLAS/SDPA/NCCL) build, and bf16 when the headline is fp8 ----
+        if args.impl == "fused":
+            from dataclasses import replace as _replace
+
+            if hcfg.rerank and precision != "bf16":
+                eng_b = HybridEngine(shard, _replace(hcfg, precision="bf16"), encoder=eng.encoder, reranker=eng.reranker,
+                                     docs_per_shard=dps)
+                b_ms, b_per = timed(dev_step(eng_b), W, K)
+                extras["bf16_arm"] = summary(b_ms, b_per, K, note="same pipeline, cross-encoder GEMMs in bf16 (round-1 config), one batch in flight")
+                eng_b._graph = None
+                del eng_b
+            try:
+                eng_t = HybridEngine(shard, _replace(hcfg, backend="torch", exchange="nccl", use_graph=False, precision="bf16"),
+                                     encoder=eng.encoder, reranker=eng.reranker, docs_per_shard=dps)
+                n_t = max(3, min(K, 5))
+                t_ms, t_per = timed(dev_step(eng_t), 3, n_t)
+                extras["torch_arm"] = summary(t_ms, t_per, n_t, steps=n_t,
+                                              note="this repo's PyTorch build of the same pipeline on the same shard: cuBLAS bf16 "
+                                                   "matmuls, SDPA, torch.topk, NCCL collectives (padded pairs); BM25 / RRF / pair "
+                                                   "assembly have no PyTorch equivalent and use the kernels in both arms")
+                del eng_t
+            except Exception as exc:  # noqa: BLE001 -- e.g. out of memory for the materialised score matrix
+                extras["torch_arm"] = {"unavailable": f"{type(exc).__name__}: {str(exc)[:120]}"}
+            torch.cuda.empty_cache()
+        # ---- (g) padded cross-encoder, for transparency ----
+        if hcfg.rerank and hcfg.varlen and args.impl == "fused":
+            from dataclasses import replace as _replace
+
+            eng_p = HybridEngine(shard, _replace(hcfg, varlen=False, precision="bf16"), encoder=eng.encoder, reranker=eng.reranker,
+                                 docs_per_shard=dps)
+            pad_ms, pad_per = timed(dev_step(eng_p), W, K)
+            extras["padded_cross_encoder"] = summary(pad_ms, pad_per, K,
+                                                     note=f"bf16 cross-encoder on padded [{B * hcfg.n_rerank // world} x {args.pair_seq}] batches per rank, one batch in flight")
+            eng_p._graph = None
+            del eng_p
 
     lat_b1 = None
     if args.latency_b1:
         cfg1 = HybridConfig(nq=world, pair_seq=args.pair_seq, rerank=not args.no_rerank, backend=args.impl,
-                            use_graph=not args.no_graph, exchange=args.exchange)
-        eng1 = HybridEngine(shard, cfg1, encoder=eng.encoder, reranker=eng.reranker,
-                            docs_per_shard=(n_global if world > 1 else n_local))
+                            use_graph=not args.no_graph, exchange=args.exchange, precision=precision)
+        eng1 = HybridEngine(shard, cfg1, encoder=eng.encoder, reranker=eng.reranker, docs_per_shard=dps)
         b1 = [tuple(x[:world] for x in b) for b in dev_batches]
 
         def step_b1(i):
             eng1.load_inputs(*b1[i % n_batches])
             eng1.run()
 
-        _, s1 = timed(step_b1, args.warmup, max(args.steps, 10))
+        _, s1 = timed(step_b1, W, max(K, 10))
         lat_b1 = statistics.median(s1)
+        eng1._graph = None
 
     pad_note = "padded [pairs, seq_len] cross-encoder batches"
     if hcfg.rerank and getattr(eng, "last_pair_lens", None) is not None:
@@ -306,59 +406,63 @@ def main() -> int:
                         "layer evaluates its query / FFN rows only for the <s> token the classifier reads (same logits)")
         else:
             pad_note += f" (mean real pair length {mean_len:.1f})"
+    dtype = {"bf16": "bf16",
+             "mxfp8": "mxfp8 cross-encoder GEMMs (e4m3 x e4m3, ue8m0 block scales per 32, fp32 accumulate); bf16 encoder, "
+                      "attention, norms, residual stream and dense index",
+             "fp8": "fp8-e4m3 per-row-scaled projections in the cross-encoder (fp32 accumulate), bf16 elsewhere"}[precision]
     if rank == 0:
-        qps = B * args.steps / (total_ms / 1e3)
-        qps_e2e = B * args.steps / (e2e_ms / 1e3)
+        torch_v = extras.get("torch_arm", {}).get("value")
         result = {
             "metric": "queries/sec, hybrid BM25+dense top-10 with cross-encoder rerank over a 10M-doc index",
-            "value": round(qps, 2),
+            "value": qps(total_ms, K),
             "unit": "queries/s",
             "n_gpus": world,
-            "steps": args.steps,
-            "warmup": args.warmup,
-            "ms_per_step": round(total_ms / args.steps, 4),
+            "steps": K,
+            "warmup": W,
+            "ms_per_step": round(total_ms / K, 4),
             "p50_step_ms": round(statistics.median(per_step), 4),
             "higher_is_better": True,
             "scaling": "strong",
-            "vs_baseline": None,
-            "dtype": "bf16" if args.precision == "bf16" else "fp8-e4m3 projections in the cross-encoder (fp32 accumulate), bf16 elsewhere",
+            "vs_baseline": round(qps(total_ms, K) / torch_v, 3) if torch_v else None,
+            "vs_baseline_note": "BASELINE.md publishes no number; its comparison target is this repo's own PyTorch "
+                                "(cuBLAS + NCCL) build of the pipeline on the same box = `torch_arm` in this line",
+            "dtype": dtype,
             "data": "synthetic (Zipfian 10M-doc corpus, random unit vectors, random-init weights)",
             "impl": args.impl,
             "config": {
                 "model": "bge-small-en encoder + bge-reranker-base cross-encoder (random-init)",
                 "index_docs": n_global, "dim": 384, "global_batch": B, "seq_len": args.pair_seq,
                 "query_tokens": hcfg.enc_seq, "candidates_per_query": hcfg.n_rerank, "top_k": hcfg.k_out,
-                "rerank": hcfg.rerank,
+                "rerank": hcfg.rerank, "query_mix": args.query_mix,
                 "parallelism": f"doc-sharded index x{world} + data-parallel reranker x{world}",
                 "l2_policy": "inputs larger than L2: every step streams this rank's dense shard "
-                             f"({shard.vectors.numel() * 2 / 1e9:.2f} GB/rank) plus the query terms' postings, and uses "
-                             "a distinct query batch",
+                             f"({shard.vectors.numel() * shard.vectors.element_size() / 1e9:.2f} GB/rank) plus the query terms' "
+                             "postings, and uses a distinct query batch",
                 "padding": pad_note,
-                "cuda_graph": bool(eng._graph is not None),
+                "cuda_graph": bool(eng._graph is not None or getattr(eng, "_ga", None) is not None),
                 "exchange": ("none" if world == 1 else ("p2p-fused" if eng.heap is not None else "nccl")),
                 "index_build_s": round(build_s, 1),
+                "pipelined": bool(pipelined),
+                "methodology": "`value` = two batches in flight (retrieval of batch i+1 overlaps the cross-encoder of batch i) "
+                               "at every N; `one_batch_in_flight` = the same K steps with one batch in flight, at every N",
             },
-            "e2e": {"value": round(qps_e2e, 2), "unit": "queries/s", "ms_per_step": round(e2e_ms / args.steps, 4),
+            "e2e": {"value": qps(e2e_ms, K), "unit": "queries/s", "ms_per_step": round(e2e_ms / K, 4),
                     "p50_step_ms": round(statistics.median(e2e_steps), 4),
-                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
-            "gpu_launches": launches * args.steps,
+                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "api": "HybridEngine.submit()/drain() (pipelined) or search_batch(): pinned-host token ids + term ids in, "
+                           "top-10 ids + scores out"},
+            "gpu_launches": launches * K,
             "gpu_launches_per_step": launches,
             "clocks": clocks,
             "results_valid": ids_ok,
+            "one_batch_in_flight": one_in_flight,
         }
-        result["config"]["pipelined"] = bool(pipelined)
-        if unpipelined is not None:
-            result["one_batch_in_flight"] = unpipelined
-        if padded is not None:
-            result["padded_cross_encoder"] = padded
+        result.update(extras)
         if lat_b1 is not None:
             result["latency_batch1_p50_ms"] = round(lat_b1, 4)
         print(json.dumps(result), flush=True)
     # graphs hold references to the NCCL communicator: drop them before tearing the group down
     eng._graph = None
-    eng_p = None
-    if lat_b1 is not None:
-        eng1._graph = None
     D.shutdown()
     return 0
 

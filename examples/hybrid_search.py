@@ -18,7 +18,9 @@ with tempfile.TemporaryDirectory() as d:
     for i in range(600):
         t = TOPICS[i % len(TOPICS)]
         store.add_document(url=f"https://example.org/{i}", title=f"{t.title()} #{i}", text=f"{t} — note {i}. " * 8, raw_html_hash=f"r{i}", text_hash=f"t{i}", language="en")
-    index = GpuSearchIndex(store, query_batch=16)
+    # allow_untrained: this demo ships no checkpoints, so the (random-init) encoder / reranker are allowed to rank; a real
+    # deployment passes encoder_path= / reranker_path= instead and leaves the flag off
+    index = GpuSearchIndex(store, query_batch=16, allow_untrained=True)
     print("resident documents:", index.rebuild(), index.stats())
     queries = ["kademlia buckets", "merkle audit proofs", "bandwidth throttling", "duplicate detection"]
     index.search_many(queries)                       # warm-up (captures the CUDA graph)

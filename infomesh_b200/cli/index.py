@@ -131,10 +131,11 @@ def index_import_urls(url_file: str, max_urls: int) -> None:
 @click.option("--save", "save_dir", default=None, help="Also write the device segments + manifest to this directory")
 def index_gpu_build(no_rerank: bool, save_dir: str | None) -> None:
     """Build the HBM-resident mirror of the index on cuda:0 and report its footprint."""
-    from infomesh_b200.engine.gpu_index import GpuSearchIndex
+    from infomesh_b200.engine.gpu_index import GpuSearchIndex, gpu_index_kwargs
 
-    with _store(load_config()) as st:
-        gi = GpuSearchIndex(st, rerank=not no_rerank)
+    cfg = load_config()
+    with _store(cfg) as st:
+        gi = GpuSearchIndex(st, rerank=not no_rerank, **gpu_index_kwargs(getattr(cfg, "gpu", None)))
         n = gi.rebuild()
         info = gi.stats()
         if save_dir and n:

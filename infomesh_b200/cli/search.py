@@ -53,9 +53,9 @@ def search(query: str, limit: int, local_only: bool, vector: bool, gpu: bool) ->
                        compression_level=cfg.storage.compression_level)
     try:
         if gpu:
-            from infomesh_b200.engine.gpu_index import GpuSearchIndex
+            from infomesh_b200.engine.gpu_index import GpuSearchIndex, gpu_index_kwargs
 
-            gi = GpuSearchIndex(store, query_batch=8)
+            gi = GpuSearchIndex(store, query_batch=8, **gpu_index_kwargs(getattr(cfg, "gpu", None)))
             gi.rebuild()
             t0 = time.monotonic()
             hits = gi.search(query, limit)

@@ -154,6 +154,9 @@ class GpuConfig:
     device: int = 0                  # CUDA ordinal used by the single-process serving path
     query_batch: int = 64            # queries packed into one device pass by the store-backed GPU index
     rerank: bool = True              # cross-encoder second stage on the device
+    encoder_path: str = ""           # HF-style checkpoint dir (config.json + model.safetensors + vocab.txt) for the encoder
+    reranker_path: str = ""          # same for the cross-encoder; without checkpoints the device path serves BM25 order only
+    allow_untrained_models: bool = False   # let random-init models rank (benchmarks / demos only)
 
 
 @dataclass(frozen=True)

@@ -11,9 +11,20 @@ store once and produces, on the GPU:
 Queries are answered in batches: ``search_many`` tokenises on the host, copies three small int tensors from pinned
 memory, replays the captured CUDA graph and maps the winning doc rows back to URLs / titles / snippets through SQLite.
 Deleted documents are masked with the ``alive`` byte map until the next rebuild.
+
+Two guards for serving:
+
+* **No ranking by untrained models.**  The dense leg is used only when the encoder carries checkpoint weights
+  (``BertModel.pretrained``, set by :mod:`infomesh_b200.models.loader`) and the cross-encoder second stage only when the
+  reranker does; otherwise the device path answers with BM25 order (GPU postings) alone.  Benchmarks and kernel tests
+  pass ``allow_untrained=True``.
+* **Thread safety.**  MCP / HTTP call ``search_many`` from worker threads while the crawl loop may ``rebuild``: one
+  re-entrant lock serialises device passes over the shared pinned staging buffers, and a rebuild prepares everything
+  off to the side and publishes engine + row maps + staging in one step under that lock.
 """
 from __future__ import annotations
 
+import threading
 import time
 from dataclasses import dataclass
 from typing import Any
@@ -52,14 +63,34 @@ class _StoreShard:
 class GpuSearchIndex:
     def __init__(self, store: Any, *, device: str | torch.device = "cuda:0", encoder: BertModel | None = None,
                  reranker: BertModel | None = None, rerank: bool = True, query_batch: int = 64, passage_len: int = 96,
-                 enc_doc_tokens: int = 128, embed_batch: int = 256, use_graph: bool = True, seed: int = 0):
+                 enc_doc_tokens: int = 128, embed_batch: int = 256, use_graph: bool = True, seed: int = 0,
+                 encoder_path: str | None = None, reranker_path: str | None = None, allow_untrained: bool = False):
         self.store = store
         self.device = torch.device(device)
+        self.enc_tok = self.rr_tok = None
+        if encoder is None and encoder_path:
+            from infomesh_b200.models.loader import load_bert, load_tokenizer
+
+            encoder = load_bert(encoder_path, device=self.device)
+            self.enc_tok = load_tokenizer(encoder_path, encoder.cfg.vocab_size)
+        if reranker is None and reranker_path and rerank:
+            from infomesh_b200.models.loader import load_bert, load_tokenizer
+
+            reranker = load_bert(reranker_path, device=self.device)
+            self.rr_tok = load_tokenizer(reranker_path, reranker.cfg.vocab_size)
         self.encoder = encoder or BertModel(BGE_SMALL, device=self.device, seed=seed + 1)
-        self.reranker = (reranker or BertModel(BGE_RERANKER_BASE, device=self.device, seed=seed + 2)) if rerank else None
-        self.enc_tok = HashTokenizer(self.encoder.cfg.vocab_size, BERT_SPECIALS)
-        self.rr_tok = HashTokenizer(BGE_RERANKER_BASE.vocab_size, XLMR_SPECIALS)
-        self.rerank, self.nq, self.passage_len = rerank, query_batch, passage_len
+        self.allow_untrained = bool(allow_untrained)
+        # ranking policy: a model without checkpoint weights may not influence results (see module docstring)
+        self.use_dense = self.allow_untrained or bool(getattr(self.encoder, "pretrained", False))
+        want_rr = rerank and (self.allow_untrained or bool(getattr(reranker, "pretrained", False)))
+        self.reranker = (reranker or BertModel(BGE_RERANKER_BASE, device=self.device, seed=seed + 2)) if want_rr else None
+        if rerank and not want_rr:
+            logger.warning("gpu_rerank_disabled", reason="reranker has no checkpoint weights (random init); BM25/RRF order is kept")
+        if not self.use_dense:
+            logger.warning("gpu_dense_disabled", reason="encoder has no checkpoint weights (random init); BM25-only retrieval")
+        self.enc_tok = self.enc_tok or HashTokenizer(self.encoder.cfg.vocab_size, BERT_SPECIALS)
+        self.rr_tok = self.rr_tok or HashTokenizer(BGE_RERANKER_BASE.vocab_size, XLMR_SPECIALS)
+        self.rerank, self.nq, self.passage_len = want_rr, query_batch, passage_len
         self.enc_doc_tokens, self.embed_batch, self.use_graph = enc_doc_tokens, embed_batch, use_graph
         self.builder: HostIndexBuilder | None = None
         self.engine: HybridEngine | None = None
@@ -68,6 +99,7 @@ class GpuSearchIndex:
         self._pending = 0
         self.built_at = 0.0
         self.build_seconds = 0.0
+        self._lock = threading.RLock()
 
     # ------------------------------------------------------------------ build
     @property
@@ -100,11 +132,10 @@ class GpuSearchIndex:
                 flush()
         flush()
         n = len(ids)
-        self.doc_ids = np.asarray(ids, dtype=np.int64)
-        self._row_of = {d: i for i, d in enumerate(ids)}
-        self._pending = 0
         if n == 0:
-            self.engine, self.builder = None, builder
+            with self._lock:
+                self.doc_ids, self._row_of, self._pending = np.zeros(0, dtype=np.int64), {}, 0
+                self.engine, self.builder = None, builder
             return 0
         csr = builder.export()
         vectors = torch.cat(vec_chunks).contiguous()
@@ -114,7 +145,8 @@ class GpuSearchIndex:
             if row:
                 ptok[i, :len(row)] = torch.tensor(row, dtype=torch.int32)
             plen[i] = max(len(row), 1)
-        self._install(builder, csr, vectors, ptok.to(dev), plen.to(dev), torch.ones((n,), dtype=torch.uint8, device=dev))
+        self._install(builder, csr, vectors, ptok.to(dev), plen.to(dev), torch.ones((n,), dtype=torch.uint8, device=dev),
+                      np.asarray(ids, dtype=np.int64))
         shard = self.engine.shard
         self.built_at, self.build_seconds = time.time(), time.time() - t0
         logger.info("gpu_index_built", docs=n, seconds=round(self.build_seconds, 2), hbm_mb=round(shard.nbytes() / 2 ** 20, 1))
@@ -190,8 +222,7 @@ class GpuSearchIndex:
         ptok = torch.from_numpy(read("passage_tok.bin", np.int32)).view(n, man["passage_len"]).to(dev)
         plen = torch.from_numpy(read("passage_len.bin", np.int32)).to(dev)
         alive = torch.from_numpy(read("alive.bin", np.uint8)).to(dev)
-        self.doc_ids = read("doc_ids.bin", np.int64)
-        self._row_of = {int(x): i for i, x in enumerate(self.doc_ids)}
+        doc_ids = read("doc_ids.bin", np.int64)
         builder = HostIndexBuilder()
         terms = (d / "vocab.txt").read_text(encoding="utf-8")
         if terms:
@@ -199,39 +230,43 @@ class GpuSearchIndex:
         if builder.vocab != man["vocab"]:
             raise ValueError("vocabulary does not round-trip")
         self.passage_len = man["passage_len"]
-        self._install(builder, csr, vectors, ptok, plen, alive)
+        self._install(builder, csr, vectors, ptok, plen, alive, doc_ids)
         self.built_at, self.build_seconds = time.time(), time.time() - t0
         return n
 
-    def _install(self, builder, csr, vectors, ptok, plen, alive) -> None:
-        """Adopt device structures (fresh build or loaded segments) and (re)create the engine + pinned staging."""
+    def _install(self, builder, csr, vectors, ptok, plen, alive, doc_ids) -> None:
+        """Adopt device structures (fresh build or loaded segments): the engine, row maps and pinned staging are built
+        into locals and published together under the lock, so a concurrent search sees either the old or the new index."""
         dev = self.device
-        self._csr = csr
         shard = _StoreShard(dev, vectors, Bm25Index(csr, device=dev), ptok, plen, alive)
         cfg = HybridConfig(nq=self.nq, rerank=self.rerank, k_fetch=20, n_rerank=20, k_out=10, pair_seq=min(128, 32 + self.passage_len),
-                           use_graph=self.use_graph)
-        self.engine = HybridEngine(shard, cfg, encoder=self.encoder, reranker=self.reranker)
-        self.builder = builder
+                           use_graph=self.use_graph, dense=self.use_dense)
+        engine = HybridEngine(shard, cfg, encoder=self.encoder, reranker=self.reranker)
         pin = torch.cuda.is_available()
 
         def mk(*shape, fill=0):
             t = torch.full(shape, fill, dtype=torch.int32)
             return t.pin_memory() if pin else t
 
-        self._h_enc, self._h_enc_len = mk(cfg.nq, cfg.enc_seq), mk(cfg.nq, fill=1)
-        self._h_qtok, self._h_qlen = mk(cfg.nq, cfg.max_q_tokens, fill=self.rr_tok.sp.pad), mk(cfg.nq, fill=1)
-        self._h_terms = mk(cfg.nq, cfg.max_terms, fill=-1)
-        self._h_scores = torch.empty((cfg.nq, cfg.k_out), dtype=torch.float32)
-        self._h_ids = torch.empty((cfg.nq, cfg.k_out), dtype=torch.int64)
+        h_scores = torch.empty((cfg.nq, cfg.k_out), dtype=torch.float32)
+        h_ids = torch.empty((cfg.nq, cfg.k_out), dtype=torch.int64)
         if pin:
-            self._h_scores, self._h_ids = self._h_scores.pin_memory(), self._h_ids.pin_memory()
+            h_scores, h_ids = h_scores.pin_memory(), h_ids.pin_memory()
+        staging = (mk(cfg.nq, cfg.enc_seq), mk(cfg.nq, fill=1), mk(cfg.nq, cfg.max_q_tokens, fill=self.rr_tok.sp.pad),
+                   mk(cfg.nq, fill=1), mk(cfg.nq, cfg.max_terms, fill=-1), h_scores, h_ids)
+        row_of = {int(x): i for i, x in enumerate(doc_ids)}
+        with self._lock:
+            self._csr, self.engine, self.builder = csr, engine, builder
+            self.doc_ids, self._row_of, self._pending = doc_ids, row_of, 0
+            (self._h_enc, self._h_enc_len, self._h_qtok, self._h_qlen, self._h_terms, self._h_scores, self._h_ids) = staging
 
     def mark_deleted(self, doc_id: int) -> bool:
-        row = self._row_of.get(int(doc_id))
-        if row is None or self.engine is None:
-            return False
-        self.engine.shard.alive[row] = 0
-        return True
+        with self._lock:
+            row = self._row_of.get(int(doc_id))
+            if row is None or self.engine is None:
+                return False
+            self.engine.shard.alive[row] = 0
+            return True
 
     def note_added(self, n: int = 1) -> None:
         """New documents become searchable on the GPU at the next rebuild; callers rebuild past a threshold."""
@@ -271,16 +306,21 @@ class GpuSearchIndex:
         nq = self.engine.cfg.nq
         for a in range(0, len(queries), nq):
             chunk = queries[a:a + nq]
-            self._stage(chunk)
-            self.engine.search_batch(self._h_enc, self._h_enc_len, self._h_qtok, self._h_qlen, self._h_terms, self._h_scores, self._h_ids)
-            torch.cuda.current_stream(self.device).synchronize()
-            scores, rows = self._h_scores.numpy(), self._h_ids.numpy()
+            with self._lock:      # staging buffers, graph-static device buffers and the row map are shared state
+                if self.engine is None:
+                    out.extend([] for _ in chunk)
+                    continue
+                self._stage(chunk)
+                self.engine.search_batch(self._h_enc, self._h_enc_len, self._h_qtok, self._h_qlen, self._h_terms, self._h_scores, self._h_ids)
+                torch.cuda.current_stream(self.device).synchronize()
+                scores, rows = self._h_scores.numpy().copy(), self._h_ids.numpy().copy()
+                doc_ids = self.doc_ids
             for i, q in enumerate(chunk):
                 hits = []
                 for s, r in zip(scores[i], rows[i]):
-                    if r < 0 or r >= self.n_docs or len(hits) >= k:
+                    if r < 0 or r >= doc_ids.size or len(hits) >= k:
                         continue
-                    doc = self.store.get_document(int(self.doc_ids[r]))
+                    doc = self.store.get_document(int(doc_ids[r]))
                     if doc is None:
                         continue
                     hits.append({"doc_id": doc.doc_id, "url": doc.url, "title": doc.title, "snippet": _snippet(doc.text, q),
@@ -295,7 +335,23 @@ class GpuSearchIndex:
         sh = self.engine.shard if self.engine else None
         return {"documents": self.n_docs, "pending": self._pending, "built_at": self.built_at, "build_seconds": round(self.build_seconds, 2),
                 "hbm_bytes": sh.nbytes() if sh else 0, "vocab": self.builder.vocab if self.builder else 0,
-                "query_batch": self.nq, "rerank": self.rerank, "cuda_graph": bool(self.engine and self.engine._graph is not None)}
+                "query_batch": self.nq, "rerank": self.rerank, "dense": self.use_dense,
+                "encoder": getattr(self.encoder, "source", "random-init"),
+                "reranker": getattr(self.reranker, "source", "random-init") if self.reranker is not None else "off",
+                "cuda_graph": bool(self.engine and self.engine._graph is not None)}
+
+
+def gpu_index_kwargs(gcfg) -> dict:
+    """``[gpu]`` config section -> keyword arguments of :class:`GpuSearchIndex` (checkpoint paths + ranking policy)."""
+    kw = {}
+    if gcfg is None:
+        return kw
+    if getattr(gcfg, "encoder_path", ""):
+        kw["encoder_path"] = gcfg.encoder_path
+    if getattr(gcfg, "reranker_path", ""):
+        kw["reranker_path"] = gcfg.reranker_path
+    kw["allow_untrained"] = bool(getattr(gcfg, "allow_untrained_models", False))
+    return kw
 
 
 def _snippet(text: str, query: str, width: int = 200) -> str:

@@ -34,13 +34,16 @@ class HybridConfig:
     n_rerank: int = 20        # reference reranks <= 20 candidates (reranker.py:20)
     k_out: int = 10
     varlen: bool = True       # cross-encoder runs on the unpadded token stream (padding never reaches a kernel)
-    precision: str = "bf16"   # "fp8": cross-encoder projections as e4m3 GEMMs (opt-in; never the benchmark default)
+    precision: str = "bf16"   # cross-encoder GEMMs: "bf16" | "mxfp8" (block-scaled e4m3, quantisers fused into the
+                              # producers) | "fp8" (round-1 per-row e4m3 with a standalone quantiser; kept for A/B)
     rerank_chunks: int = 1    # split the rank's pairs into this many sub-batches so activations stay L2-resident
     pair_seq: int = 128       # <s> q </s></s> passage </s>
     rerank: bool = True
+    dense: bool = True        # False: BM25-only retrieval (serving with an encoder that has no checkpoint weights)
     backend: str = "fused"    # "fused" | "torch"
     use_graph: bool = True
     exchange: str = "p2p"     # multi-GPU list exchange: "p2p" (fused peer-memory kernels) | "nccl" (baseline collectives)
+    strict_graph: bool = False  # CUDA-graph capture failure is an error (benchmarks) instead of a warning + eager fallback
     degraded_ok: bool = False  # p2p exchange: drop a silent shard after ``wait_limit`` polls instead of trapping
     wait_limit: int = 0        # 0 = library default (~1 s)
 
@@ -183,12 +186,17 @@ class HybridEngine:
     # ------------------------------------------------------------------ one batch
     def _forward(self):
         cfg = self.cfg
-        q_emb = self._encode()
-        de_s, de_i = self._dense_local(q_emb)
+        if cfg.dense:
+            q_emb = self._encode()
+            de_s, de_i = self._dense_local(q_emb)
         bm_s, bm_i = self._bm25_local()
-        de_s, de_i = self._exchange(de_s, de_i, getattr(self, "ch_dense", None))
+        if cfg.dense:
+            de_s, de_i = self._exchange(de_s, de_i, getattr(self, "ch_dense", None))
         bm_s, bm_i = self._exchange(bm_s, bm_i, getattr(self, "ch_bm25", None))
-        fu_s, fu_i = self._fuse(bm_i, de_i)
+        if cfg.dense:
+            fu_s, fu_i = self._fuse(bm_i, de_i)
+        else:       # BM25 order is the fused order
+            fu_s, fu_i = bm_s[:, :cfg.n_rerank].contiguous(), bm_i[:, :cfg.n_rerank].contiguous()
         if cfg.rerank:
             logits = self._rerank(fu_i)
             F.rerank_select(logits.float().contiguous(), fu_i.contiguous(), cfg.k_out, self.out_scores, self.out_ids)
@@ -229,6 +237,8 @@ class HybridEngine:
                 self._forward()
             self._graph = g
         except Exception as exc:  # noqa: BLE001 — fall back to eager launches, loudly
+            if self.cfg.strict_graph:
+                raise RuntimeError(f"CUDA graph capture failed (strict_graph): {exc!r}") from exc
             import warnings
 
             warnings.warn(f"CUDA graph capture failed, running eagerly: {exc!r}")
@@ -264,7 +274,7 @@ class HybridEngine:
     # pipeline (one communicator, two streams).
     def pipeline_supported(self) -> bool:
         cfg = self.cfg
-        return (cfg.backend == "fused" and cfg.rerank and cfg.use_graph and not self._graph_failed
+        return (cfg.backend == "fused" and cfg.rerank and cfg.dense and cfg.use_graph and not self._graph_failed
                 and (not self.ctx.is_dist or self.heap is not None))
 
     def _local_logits(self, pair_ids, pair_lens):
@@ -396,6 +406,42 @@ class HybridEngine:
         if self.heap is None:
             return []
         return sorted(set(self.ch_dense.dead_ranks()) | set(self.ch_bm25.dead_ranks()))
+
+    def stage_times(self, iters: int = 5) -> dict:
+        """Median device time (ms) of every pipeline stage, measured eagerly with CUDA events between the stages (so
+        the sum exceeds a CUDA-graph replay of the whole step by the launch gaps).  Names the limiter at each N."""
+        cfg = self.cfg
+        names = ["encode", "dense_local", "bm25_local", "exchange_merge", "fuse_pairs", "cross_encoder", "select"]
+        acc = {n: [] for n in names}
+        for _ in range(iters + 1):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+            ev[0].record()
+            q_emb = self._encode()
+            ev[1].record()
+            de_s, de_i = self._dense_local(q_emb)
+            ev[2].record()
+            bm_s, bm_i = self._bm25_local()
+            ev[3].record()
+            de_s, de_i = self._exchange(de_s, de_i, getattr(self, "ch_dense", None))
+            bm_s, bm_i = self._exchange(bm_s, bm_i, getattr(self, "ch_bm25", None))
+            ev[4].record()
+            fu_s, fu_i = self._fuse(bm_i, de_i)
+            pairs = self._pairs(fu_i) if cfg.rerank else None
+            ev[5].record()
+            if cfg.rerank:
+                logits = self._score(*pairs)
+            ev[6].record()
+            if cfg.rerank:
+                F.rerank_select(logits.float().contiguous(), fu_i.contiguous(), cfg.k_out, self.out_scores, self.out_ids)
+            ev[7].record()
+            torch.cuda.synchronize()
+            for j, n in enumerate(names):
+                acc[n].append(ev[j].elapsed_time(ev[j + 1]))
+        out = {}
+        for n in names:
+            v = sorted(acc[n][1:])
+            out[n] = round(v[len(v) // 2], 4)
+        return out
 
     def launches_per_step(self) -> int:
         from infomesh_b200 import _native

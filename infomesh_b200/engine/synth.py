@@ -190,10 +190,13 @@ class SynthShard:
 
 
 def make_queries(cfg: SynthConfig, n_queries: int, max_terms: int = 8, max_q_tokens: int = 32, seed: int = 99,
-                 df_global: torch.Tensor | None = None, device="cpu", n_terms=(2, 3)):
+                 df_global: torch.Tensor | None = None, device="cpu", n_terms=(2, 3), mix: str = "rare"):
     """Queries as (term ids [nq, max_terms] -1 padded, model tokens [nq, max_q_tokens], token lens [nq]).
 
-    Each query takes the rarest terms of a random (global) document so AND-BM25 has at least one hit.
+    Each query takes 2-3 terms of a random (global) document so AND-BM25 has at least one hit.  ``mix="rare"``: the
+    terms sit in the 45-90 % rarity quantiles of that document (short posting lists); ``mix="common"``: every other
+    query additionally carries the document's MOST frequent term (posting lists of ~10-40 % of the corpus), which is
+    what stresses list intersection.
     Generated on ``device`` deterministically; identical on every rank.
     """
     dev = torch.device(device)
@@ -214,6 +217,8 @@ def make_queries(cfg: SynthConfig, n_queries: int, max_terms: int = 8, max_q_tok
         kt = min(int(k_terms[i]), terms.numel())
         # spread the picks over the 45%..90% rarity quantiles: selective but not unique terms
         pos = [int(round((terms.numel() - 1) * (0.45 + 0.45 * j / max(kt - 1, 1)))) for j in range(kt)]
+        if mix == "common" and i % 2 == 1:
+            pos[0] = 0
         pick = terms[torch.tensor(sorted(set(pos)), dtype=torch.long)]
         q_terms[i, :pick.numel()] = pick.to(torch.int32)
         toks = term_to_token(pick.to(torch.int32), cfg)

@@ -56,10 +56,10 @@ def attach_gpu_index(ctx: AppContext) -> Any | None:
 
         if not torch.cuda.is_available() or not _native.available():
             return None
-        from infomesh_b200.engine.gpu_index import GpuSearchIndex
+        from infomesh_b200.engine.gpu_index import GpuSearchIndex, gpu_index_kwargs
 
         gi = GpuSearchIndex(ctx.store, device=f"cuda:{getattr(gcfg, 'device', 0)}", rerank=getattr(gcfg, "rerank", True),
-                            query_batch=getattr(gcfg, "query_batch", 64))
+                            query_batch=getattr(gcfg, "query_batch", 64), **gpu_index_kwargs(gcfg))
         gi.rebuild()
         ctx.gpu_index = gi
     except Exception as exc:  # noqa: BLE001

@@ -125,6 +125,10 @@ class BertModel:
         self.cfg = cfg
         self.device = torch.device(device)
         self.w = weights if weights is not None else BertWeights(cfg, device=device, seed=seed)
+        # True only when the weights came from a checkpoint (models/loader.py).  Serving code must not let a random-init
+        # model influence ranking; benchmarks / tests opt in explicitly.
+        self.pretrained = False
+        self.source = "random-init"
 
     # ------------------------------------------------------------------ native path
     def hidden_states(self, ids: torch.Tensor, lengths: torch.Tensor | None = None,
@@ -166,11 +170,53 @@ class BertModel:
         H = cfg.hidden
         assert S <= 128 and cfg.head_dim == 64, "packed path: max_seqlen <= 128, head_dim 64"
         pk_ids, pk_pos, cu, total = N.seq_pack(ids.contiguous(), lengths, cfg.pos_offset)
-        x = N.embed_ln(pk_ids, w.word, w.pos, w.type, w.emb_g, w.emb_b, cfg.eps, S, pos_ids=pk_pos, n_rows_dev=total)
         layers = w.layers[:-1] if cls_only_last else w.layers
+        if precision == "mxfp8":
+            from infomesh_b200.ops import mx as MX
+
+            xq = MX.alloc_act(B * S, H, ids.device)
+            x = N.embed_ln(pk_ids, w.word, w.pos, w.type, w.emb_g, w.emb_b, cfg.eps, S, pos_ids=pk_pos, n_rows_dev=total,
+                           mx_out=xq)
+            for lay in layers:
+                x, xq = self._packed_layer_mx(x, xq, lay, B, S, cu, total)
+            return x, cu, total
+        x = N.embed_ln(pk_ids, w.word, w.pos, w.type, w.emb_g, w.emb_b, cfg.eps, S, pos_ids=pk_pos, n_rows_dev=total)
         for lay in layers:
             x = self._packed_layer(x, lay, B, S, cu, total, fp8=(precision == "fp8"))
         return x, cu, total
+
+    def _mx_weights(self, lay):
+        """MXFP8 copies of a layer's four GEMM weights (e4m3 + ue8m0 per 32, packed once on first use)."""
+        from infomesh_b200.ops import mx as MX
+
+        if "wqkv_mx" not in lay:
+            for name in ("wqkv", "wo", "w1", "w2"):
+                lay[name + "_mx"] = MX.quantize_weight(lay[name])
+        return lay
+
+    def _packed_layer_mx(self, x, xq, lay, B, S, cu, total):
+        """One encoder layer on block-scaled fp8 GEMMs.  Every GEMM input arrives already quantised by the kernel that
+        produced it: LayerNorm (x -> QKV, x1 -> FFN-up), the attention epilogue (context -> out-proj) and the GELU
+        epilogue of FFN-up (h -> FFN-down); bf16 survives only on the residual stream and as Q/K/V for attention."""
+        from infomesh_b200.ops import attention as A
+        from infomesh_b200.ops import mx as MX
+        from infomesh_b200.ops import nn as N
+
+        cfg, H = self.cfg, self.cfg.hidden
+        self._mx_weights(lay)
+        dev = x.device
+        qkv = MX.linear_mx(xq, lay["wqkv_mx"], lay["bqkv"], m_dev=total)
+        q3 = qkv.view(B, S, 3 * H)
+        ctx = MX.alloc_act(B * S, H, dev)
+        A.attention_mx(q3[..., :H], q3[..., H:2 * H], q3[..., 2 * H:], cfg.heads, ctx, cu_seqlens=cu)
+        y = MX.linear_mx(ctx, lay["wo_mx"], lay["bo"], residual=x, m_dev=total)
+        x1q = MX.alloc_act(B * S, H, dev)
+        x1 = N.layernorm_mx(y, lay["ln1_g"], lay["ln1_b"], cfg.eps, x1q, n_rows_dev=total)
+        h = MX.linear_mx(x1q, lay["w1_mx"], lay["b1"], act="gelu", out_mx=True, m_dev=total)
+        y2 = MX.linear_mx(h, lay["w2_mx"], lay["b2"], residual=x1, m_dev=total)
+        x2q = MX.alloc_act(B * S, H, dev)
+        x2 = N.layernorm_mx(y2, lay["ln2_g"], lay["ln2_b"], cfg.eps, x2q, n_rows_dev=total)
+        return x2, x2q
 
     def _fp8_weights(self, lay):
         """Per-tensor e4m3 copies of a layer's four GEMM weights (made once, on first use of the fp8 path)."""

@@ -77,6 +77,28 @@ def attention(q, k, v, n_heads, kv_lens=None, causal=False, causal_offset=0, sca
     return out
 
 
+def attention_mx(q, k, v, n_heads, mx_out, kv_lens=None, scale=None, cu_seqlens=None):
+    """Single-chunk (S <= 128, head_dim 64) attention whose context is written as MXFP8 into ``mx_out`` (an
+    :class:`infomesh_b200.ops.mx.MxTensor` over the flattened ``[B*S, nH*hd]`` rows): the quantiser of the
+    out-projection's input is the attention epilogue."""
+    assert q.is_cuda and q.dtype == torch.bfloat16 and k.dtype == torch.bfloat16 and v.dtype == torch.bfloat16
+    B, Sq, HH = q.shape
+    Sk = k.shape[1]
+    hd = HH // n_heads
+    assert hd == 64 and Sq <= 128 and Sk <= 128 and mx_out.q.shape == (B * Sq, HH)
+    assert q.stride(2) == 1 and k.stride(2) == 1 and v.stride(2) == 1
+    scale = (1.0 / math.sqrt(hd)) if scale is None else scale
+    L = _native.require()
+    rc = L.im_attn_fwd_mx(_native.ptr(q), _native.ptr(k), _native.ptr(v), _native.ptr(mx_out.q),
+                          ctypes.c_int(mx_out.q.stride(0)), _native.ptr(mx_out.sf), ctypes.c_int(HH // 128), ctypes.c_int(B),
+                          ctypes.c_int(n_heads), ctypes.c_int(hd), ctypes.c_int(Sq), ctypes.c_int(Sk),
+                          ctypes.c_int(q.stride(1)), ctypes.c_int(k.stride(1)), ctypes.c_int(v.stride(1)),
+                          _native.ptr(kv_lens), ctypes.c_float(scale), _native.stream_ptr(), _native.ptr(cu_seqlens))
+    _native.check(rc, "im_attn_fwd_mx")
+    _native.count_launch()
+    return mx_out
+
+
 def attention_decode(q, k_cache, v_cache, n_heads, kv_len, scale=None, rel_bias_log2=None, q_pos=0, out=None,
                      seq_start=None, step_dev=None):
     """One query token per sequence against a KV cache ``[B, S_max, nH*hd]``; ``kv_len`` int or int32 tensor.

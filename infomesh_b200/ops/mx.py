@@ -123,8 +123,13 @@ def quantize_act_ref(x: torch.Tensor) -> MxTensor:
     return MxTensor(q, pack_sfa(e))
 
 
-def alloc_act(m: int, k: int, device) -> MxTensor:
-    """Uninitialised MX activation buffer (scale chunks start as exponent 127 so untouched rows dequantise finitely)."""
+def alloc_act(m: int, k: int, device, init: bool = False) -> MxTensor:
+    """MX activation buffer for a fused producer to fill.  ``init=False`` (hot path): no fill kernels -- rows the
+    producer skips (beyond a varlen batch's token count) hold garbage that only ever reaches their own, equally
+    ignored, output rows.  ``init=True`` zeroes the data and sets every scale to 1.0 (tests, dequantising whole buffers)."""
+    if not init:
+        return MxTensor(torch.empty((m, k), device=device, dtype=torch.uint8),
+                        torch.empty(((m + 127) // 128, k // 128, 512), device=device, dtype=torch.uint8))
     q = torch.zeros((m, k), device=device, dtype=torch.uint8)
     sf = torch.full(((m + 127) // 128, k // 128, 512), 127, device=device, dtype=torch.uint8)
     return MxTensor(q, sf)

@@ -45,19 +45,48 @@ def pool_norm_ref(h, lengths, mode="cls", normalize=True):
 
 # ----------------------------------------------------------------------------- kernels
 def embed_ln(ids, word, pos, type_emb, gamma, beta, eps, seq_len, pos_ids=None, type_ids=None, pos_offset=0, out=None,
-             n_rows_dev=None):
+             n_rows_dev=None, mx_out=None):
+    """``mx_out``: an :class:`infomesh_b200.ops.mx.MxTensor` that also receives the normalised rows as MXFP8."""
     n = ids.numel()
     H = word.shape[1]
     assert ids.dtype == torch.int32 and word.dtype == torch.bfloat16
     if out is None:
         out = torch.empty((n, H), device=word.device, dtype=torch.bfloat16)
     L = _native.require()
+    if mx_out is not None:
+        assert mx_out.q.shape == (n, H) and mx_out.sf.shape[1] == H // 128
+        rc = L.im_embed_ln_mx(_native.ptr(ids), _native.ptr(pos_ids), _native.ptr(type_ids), _native.ptr(word),
+                              _native.ptr(pos), _native.ptr(type_emb), _native.ptr(gamma), _native.ptr(beta),
+                              ctypes.c_float(eps), ctypes.c_int(n), ctypes.c_int(seq_len), ctypes.c_int(pos_offset),
+                              ctypes.c_int(word.shape[0]), ctypes.c_int(pos.shape[0] if pos is not None else 1),
+                              ctypes.c_int(H), _native.ptr(out), _native.stream_ptr(), _native.ptr(n_rows_dev),
+                              _native.ptr(mx_out.q), ctypes.c_int(mx_out.q.stride(0)), _native.ptr(mx_out.sf))
+        _native.check(rc, "im_embed_ln_mx")
+        _native.count_launch()
+        return out
     rc = L.im_embed_ln(_native.ptr(ids), _native.ptr(pos_ids), _native.ptr(type_ids), _native.ptr(word),
                        _native.ptr(pos), _native.ptr(type_emb), _native.ptr(gamma), _native.ptr(beta),
                        ctypes.c_float(eps), ctypes.c_int(n), ctypes.c_int(seq_len), ctypes.c_int(pos_offset),
                        ctypes.c_int(word.shape[0]), ctypes.c_int(pos.shape[0] if pos is not None else 1),
                        ctypes.c_int(H), _native.ptr(out), _native.stream_ptr(), _native.ptr(n_rows_dev))
     _native.check(rc, "im_embed_ln")
+    _native.count_launch()
+    return out
+
+
+def layernorm_mx(x, gamma, beta, eps, mx_out, residual=None, rms_only=False, out=None, want_bf16=True, n_rows_dev=None):
+    """``LN(x + residual)`` written twice by ONE kernel: bf16 (the residual stream) and MXFP8 into ``mx_out`` (the A
+    operand of the next block-scaled GEMM) -- the quantiser is fused into its producer."""
+    n, H = x.shape
+    assert x.dtype == torch.bfloat16 and x.stride(1) == 1 and mx_out.q.shape == (n, H)
+    if out is None and want_bf16:
+        out = torch.empty((n, H), device=x.device, dtype=torch.bfloat16)
+    L = _native.require()
+    rc = L.im_sum_ln_mx(_native.ptr(x), _native.ptr(residual), _native.ptr(gamma), _native.ptr(beta), ctypes.c_float(eps),
+                        ctypes.c_int(1 if rms_only else 0), ctypes.c_int(n), ctypes.c_int(H),
+                        _native.ptr(out if want_bf16 else None), _native.stream_ptr(), _native.ptr(n_rows_dev),
+                        _native.ptr(mx_out.q), ctypes.c_int(mx_out.q.stride(0)), _native.ptr(mx_out.sf))
+    _native.check(rc, "im_sum_ln_mx")
     _native.count_launch()
     return out
 

@@ -63,9 +63,9 @@ class InfoMeshClient:
         self._data_dir.mkdir(parents=True, exist_ok=True)
         self._ctx = AppContext(cfg)
         if self._gpu:
-            from infomesh_b200.engine.gpu_index import GpuSearchIndex
+            from infomesh_b200.engine.gpu_index import GpuSearchIndex, gpu_index_kwargs
 
-            self._gpu_index = GpuSearchIndex(self._ctx.store)
+            self._gpu_index = GpuSearchIndex(self._ctx.store, **gpu_index_kwargs(getattr(cfg, "gpu", None)))
             self._gpu_index.rebuild()
 
     def close(self) -> None:

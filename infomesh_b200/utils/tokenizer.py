@@ -132,3 +132,85 @@ def load_tokenizer(name_or_dir: str, vocab_size: int = 32128) -> Seq2SeqTokenize
     p = Path(name_or_dir)
     model_file = str(p / "spiece.model") if p.is_dir() else None
     return Seq2SeqTokenizer(vocab_size, model_file)
+
+
+class WordPieceTokenizer(HashTokenizer):
+    """BERT WordPiece from a ``vocab.txt``: lower-case, split on whitespace and punctuation, then greedy
+    longest-match-first with ``##`` continuation pieces; words that cannot be segmented map to ``[UNK]``.
+    Same interface as :class:`HashTokenizer` (``encode`` / ``encode_plain`` / ``encode_batch``)."""
+
+    _SPLIT = re.compile(r"\w+|[^\w\s]", re.UNICODE)
+
+    def __init__(self, vocab_file, max_chars_per_word: int = 100):
+        lines = Path(vocab_file).read_text("utf-8").splitlines()
+        self.vocab = {w: i for i, w in enumerate(lines)}
+        self.vocab_size = len(lines)
+        g = self.vocab.get
+        self.sp = SpecialTokens(cls=g("[CLS]", 101), sep=g("[SEP]", 102), pad=g("[PAD]", 0), unk=g("[UNK]", 100), first_regular=0)
+        self.max_chars = max_chars_per_word
+
+    def pieces(self, word: str) -> list[int]:
+        if len(word) > self.max_chars:
+            return [self.sp.unk]
+        out, start = [], 0
+        while start < len(word):
+            end, cur = len(word), None
+            while start < end:
+                sub = word[start:end] if start == 0 else "##" + word[start:end]
+                if sub in self.vocab:
+                    cur = self.vocab[sub]
+                    break
+                end -= 1
+            if cur is None:
+                return [self.sp.unk]
+            out.append(cur)
+            start = end
+        return out
+
+    def _ids(self, text: str) -> list[int]:
+        ids: list[int] = []
+        for w in self._SPLIT.findall(text.lower()):
+            ids.extend(self.pieces(w))
+        return ids
+
+    def word_id(self, word: str) -> int:
+        p = self.pieces(word.lower())
+        return p[0] if p else self.sp.unk
+
+    def encode(self, text: str, max_len: int = 512, add_special: bool = True) -> list[int]:
+        ids = self._ids(text)
+        if add_special:
+            ids = [self.sp.cls] + ids[:max_len - 2] + [self.sp.sep]
+        return ids[:max_len]
+
+    def encode_plain(self, text: str, max_len: int) -> list[int]:
+        return self._ids(text)[:max_len]
+
+
+class SentencePieceTokenizer(HashTokenizer):
+    """XLM-R SentencePiece (``sentencepiece.bpe.model``) with fairseq's id shift (<s>=0, <pad>=1, </s>=2, <unk>=3, piece
+    ids + 1)."""
+
+    def __init__(self, model_file, vocab_size: int):
+        import sentencepiece as spm
+
+        self.proc = spm.SentencePieceProcessor(model_file=str(model_file))
+        self.vocab_size = vocab_size
+        self.vocab = None
+        self.sp = XLMR_SPECIALS
+
+    def _ids(self, text: str) -> list[int]:
+        return [i + 1 if i > 0 else self.sp.unk for i in self.proc.encode(text)]
+
+    def word_id(self, word: str) -> int:
+        ids = self._ids(word)
+        return ids[0] if ids else self.sp.unk
+
+    def encode(self, text: str, max_len: int = 512, add_special: bool = True) -> list[int]:
+        ids = self._ids(text)
+        if add_special:
+            ids = [self.sp.cls] + ids[:max_len - 2] + [self.sp.sep]
+        return ids[:max_len]
+
+    def encode_plain(self, text: str, max_len: int) -> list[int]:
+        return self._ids(text)[:max_len]

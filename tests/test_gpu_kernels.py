@@ -334,7 +334,7 @@ def test_gpu_search_index_over_local_store(tmp_path):
     small = BertConfig(name="tiny-enc", vocab_size=30522, hidden=384, layers=2, heads=12, ffn=1536, max_pos=512)
     rr = BertConfig(name="tiny-rr", vocab_size=250002, hidden=768, layers=2, heads=12, ffn=3072, max_pos=514, pos_offset=2,
                     type_vocab=1, classifier=True)
-    gi = GpuSearchIndex(store, device=dev, encoder=BertModel(small, device=dev, seed=1), reranker=BertModel(rr, device=dev, seed=2),
+    gi = GpuSearchIndex(store, device=dev, encoder=BertModel(small, device=dev, seed=1), reranker=BertModel(rr, device=dev, seed=2), allow_untrained=True,
                         query_batch=8)
     assert gi.rebuild() == 60
     res = gi.search_many(["kademlia buckets", "merkle audit proofs", "zzzunknownterm kademlia"], k=5)
@@ -346,7 +346,7 @@ def test_gpu_search_index_over_local_store(tmp_path):
     # segments round-trip: a second index loads them (no re-encoding) and answers identically
     man = gi.save(tmp_path / "segments")
     assert man["n_docs"] == 60 and set(man["files"]) == set(GpuSearchIndex._FILES)
-    gi2 = GpuSearchIndex(store, device=dev, encoder=gi.encoder, reranker=gi.reranker, query_batch=8)
+    gi2 = GpuSearchIndex(store, device=dev, encoder=gi.encoder, reranker=gi.reranker, query_batch=8, allow_untrained=True)
     assert gi2.load(tmp_path / "segments") == 60
     again2 = gi2.search_many(["kademlia buckets", "merkle audit proofs"], k=5)
     assert [h["doc_id"] for h in again2[0]] == [h["doc_id"] for h in res[0]]

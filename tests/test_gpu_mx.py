@@ -1,0 +1,177 @@
+"""GPU numerics of the MXFP8 (block-scaled fp8) path: the tcgen05 kind::mxf8f6f4.block_scale GEMM and the fused
+quantisers in its producers, each against a plain PyTorch fp32 oracle of the same op, plus an accuracy gate for the
+whole cross-encoder (logit error vs the fp32 model)."""
+from __future__ import annotations
+
+from dataclasses import replace
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _native_required():
+    from infomesh_b200 import _native
+
+    _native.require()
+    torch.manual_seed(0)
+
+
+@pytest.mark.parametrize("m,n,k,bias,act,resid", [
+    (256, 384, 256, False, None, False), (1000, 768, 768, True, None, True), (777, 2304, 768, True, None, False),
+    (300, 3072, 768, True, "gelu", False), (520, 768, 3072, True, None, True), (130, 1152, 384, True, None, False),
+    (4096, 1536, 384, True, "gelu", False), (64, 192, 128, False, "relu", False),
+])
+def test_mx_gemm_matches_dequantised_fp32_reference(m, n, k, bias, act, resid):
+    from infomesh_b200.ops import mx as MX
+
+    a = MX.quantize_act_ref(torch.randn(m, k, device=DEV) * torch.logspace(-2, 2, m, device=DEV)[:, None])
+    w = MX.quantize_weight(torch.randn(n, k, device=DEV) * 0.05)
+    b = torch.randn(n, device=DEV) if bias else None
+    r = torch.randn(m, n, device=DEV).bfloat16() if resid else None
+    out = MX.linear_mx(a, w, b, r, act)
+    ref = MX.linear_mx_ref(a, w, b, r, act)
+    # row-wise: the rows span four orders of magnitude
+    err = (out.float() - ref).abs().amax(1)
+    assert (err <= 0.01 * ref.abs().amax(1) + 0.02).all(), (err / ref.abs().amax(1)).max().item()
+
+
+def test_mx_gemm_device_row_count_and_mx_output():
+    from infomesh_b200.ops import mx as MX
+
+    m, n, k, rows = 1024, 3072, 768, 777
+    a = MX.quantize_act_ref(torch.randn(m, k, device=DEV))
+    w = MX.quantize_weight(torch.randn(n, k, device=DEV) * 0.05)
+    b = torch.randn(n, device=DEV) * 0.1
+    m_dev = torch.tensor([rows], device=DEV, dtype=torch.int32)
+    out = MX.linear_mx(a, w, b, act="gelu", out_mx=True, m_dev=m_dev, out=MX.alloc_act(m, n, DEV, init=True))
+    ref = MX.linear_mx_ref(a, w, b, act="gelu", rows=rows)
+    got = out.float(rows)
+    # one e4m3 rounding (2^-4 relative to the block's power-of-two ceiling) on top of the GEMM error
+    blk = ref.reshape(rows, n // 32, 32).abs().amax(-1, keepdim=True).expand(-1, -1, 32).reshape(rows, n)
+    assert ((got - ref).abs() <= blk * 2 ** -3 + 1e-3).all()
+    e_ref = MX.quantize_ref(ref)[1].int()
+    e_got = MX.unpack_sfa(out.sf, rows).int()
+    assert (e_ref - e_got).abs().max().item() <= 1 and ((e_ref != e_got).float().mean().item() < 0.01)
+    # rows beyond the device-side count were not computed: their scales are still the initial 1.0 in untouched row blocks
+    assert (MX.unpack_sfa(out.sf, m)[896:] == 127).all()
+
+
+@pytest.mark.parametrize("h", [768, 384])
+def test_layernorm_mx_matches_oracle(h):
+    from infomesh_b200.ops import mx as MX
+    from infomesh_b200.ops import nn as N
+
+    n = 1000
+    x = (torch.randn(n, h, device=DEV) * 3).bfloat16()
+    r = torch.randn(n, h, device=DEV).bfloat16()
+    g = torch.rand(h, device=DEV) + 0.5
+    b = torch.randn(h, device=DEV) * 0.1
+    mxo = MX.alloc_act(n, h, DEV, init=True)
+    out = N.layernorm_mx(x, g, b, 1e-5, mxo, residual=r)
+    ref = N.layernorm_ref(x, g, b, 1e-5, residual=r)
+    assert (out.float() - ref).abs().max().item() < 0.03
+    q_ref, e_ref = MX.quantize_ref(ref)
+    e_got = MX.unpack_sfa(mxo.sf, n)
+    assert (e_ref.int() - e_got.int()).abs().max().item() <= 1
+    assert (e_ref != e_got).float().mean().item() < 0.01          # fp32 rounding at a power-of-two boundary only
+    blk = ref.reshape(n, h // 32, 32).abs().amax(-1, keepdim=True).expand(-1, -1, 32).reshape(n, h)
+    assert ((mxo.float() - ref).abs() <= blk * 2 ** -3 + 1e-4).all()
+
+
+def test_attention_mx_matches_attention_then_quantise():
+    from infomesh_b200.ops import attention as A
+    from infomesh_b200.ops import mx as MX
+
+    B, S, nH, hd = 9, 128, 12, 64
+    H = nH * hd
+    qkv = (torch.randn(B, S, 3 * H, device=DEV) * 0.7).bfloat16()
+    lens = torch.tensor([128, 1, 77, 128, 33, 100, 5, 64, 127], device=DEV, dtype=torch.int32)
+    ctx = MX.alloc_act(B * S, H, DEV, init=True)
+    A.attention_mx(qkv[..., :H], qkv[..., H:2 * H], qkv[..., 2 * H:], nH, ctx, kv_lens=lens)
+    ref = A.attention_ref(qkv[..., :H], qkv[..., H:2 * H], qkv[..., 2 * H:], nH, kv_lens=lens).reshape(B * S, H)
+    got = ctx.float()
+    blk = ref.reshape(B * S, H // 32, 32).abs().amax(-1, keepdim=True).expand(-1, -1, 32).reshape(B * S, H)
+    assert ((got - ref).abs() <= blk * 2 ** -3 + 0.02).all()      # every query row is valid in the padded layout
+
+
+def test_cross_encoder_mxfp8_accuracy_gate():
+    """Logits of the MXFP8 cross-encoder vs the fp32 PyTorch oracle of the same (random-init) model; the bf16 kernels'
+    own error is measured alongside so the gate is relative to what bf16 already costs."""
+    from infomesh_b200.models.bert import BGE_RERANKER_BASE, BertModel
+
+    m = BertModel(replace(BGE_RERANKER_BASE, layers=4), device=DEV, seed=5)
+    B, S = 40, 128
+    g = torch.Generator(device="cpu").manual_seed(4)
+    ids = torch.randint(5, 5000, (B, S), generator=g, dtype=torch.int32).to(DEV)
+    lens = torch.randint(20, S + 1, (B,), generator=g, dtype=torch.int32).to(DEV)
+    ref = m.score_ref(ids, lens)
+    bf = m.score_packed(ids, lens)
+    mx = m.score_packed(ids, lens, precision="mxfp8")
+    assert torch.isfinite(mx).all()
+    spread = (ref.max() - ref.min()).item()
+    e_bf = (bf - ref).abs().max().item()
+    e_mx = (mx - ref).abs().max().item()
+    assert e_mx < max(0.15 * spread, 4 * e_bf + 0.02), (e_mx, e_bf, spread)
+    # ranking agreement: the ordering of the candidates by logit is what the reranker consumes
+    top_ref = set(torch.topk(ref, 10).indices.tolist())
+    top_mx = set(torch.topk(mx, 10).indices.tolist())
+    assert len(top_ref & top_mx) >= 7
+
+
+def test_gpu_index_untrained_models_keep_bm25_order_and_survive_concurrent_rebuild(tmp_path):
+    """Serving policy: without checkpoint weights neither the encoder nor the reranker may influence ranking -- the
+    device path returns exactly the BM25 (FTS5-formula) order; and searches racing a rebuild never see a torn index."""
+    import threading
+
+    from infomesh_b200.engine.gpu_index import GpuSearchIndex
+    from infomesh_b200.index.local_store import LocalStore
+    from infomesh_b200.models.bert import BertConfig, BertModel
+
+    store = LocalStore(tmp_path / "idx.db")
+    topics = ["tensor memory accumulators", "kademlia routing buckets", "sqlite full text ranking", "merkle audit proofs"]
+    for i in range(80):
+        t = topics[i % len(topics)]
+        reps = 1 + (i // len(topics)) % 5                      # different term frequencies -> distinct BM25 scores
+        store.add_document(url=f"https://example.org/{i}", title=f"Doc {i}", text=(f"{t} " * reps + f"filler text number {i} " * 3),
+                           raw_html_hash=f"r{i}", text_hash=f"t{i}", language="en")
+    dev = torch.device("cuda:0")
+    small = BertConfig(name="tiny-enc", vocab_size=30522, hidden=384, layers=2, heads=12, ffn=1536, max_pos=512)
+    gi = GpuSearchIndex(store, device=dev, encoder=BertModel(small, device=dev, seed=1), query_batch=8)
+    assert gi.use_dense is False and gi.rerank is False and gi.reranker is None
+    gi.rebuild()
+    got = [h["doc_id"] for h in gi.search("kademlia routing buckets", k=5)]
+    want = [r.doc_id for r in store.search("kademlia routing buckets", limit=5)]
+    assert got == want, (got, want)
+    assert gi.stats()["dense"] is False and gi.stats()["encoder"] == "random-init"
+
+    errors: list[Exception] = []
+    stop = threading.Event()
+
+    def searcher():
+        try:
+            while not stop.is_set():
+                hits = gi.search_many(["merkle audit proofs", "sqlite ranking"], k=5)
+                assert len(hits) == 2
+                for hs in hits:
+                    for h in hs:
+                        assert h["url"].startswith("https://example.org/")
+        except Exception as exc:  # noqa: BLE001
+            errors.append(exc)
+
+    ths = [threading.Thread(target=searcher) for _ in range(3)]
+    for t in ths:
+        t.start()
+    for j in range(3):
+        store.add_document(url=f"https://example.org/new{j}", title=f"New {j}", text=f"merkle audit proofs fresh document {j} " * 4,
+                           raw_html_hash=f"rn{j}", text_hash=f"tn{j}", language="en")
+        gi.rebuild()
+    stop.set()
+    for t in ths:
+        t.join()
+    assert not errors, errors[:1]
+    assert gi.n_docs == 83
+    store.close()

@@ -34,11 +34,12 @@ def test_query_terms_match_engine_queries():
     from infomesh_b200.engine import synth
 
     cfg = synth.SynthConfig(n_docs=1000, n_docs_global=1000)
-    qt, _, _, docs = synth.make_queries(cfg, 12)
-    mine, docs2 = R.query_terms(1000, 12, R._zipf_cdf())
-    assert torch.equal(docs, docs2)
-    for i, terms in enumerate(mine):
-        assert terms == [int(t) for t in qt[i] if int(t) >= 0]
+    for mix in ("rare", "common"):
+        qt, _, _, docs = synth.make_queries(cfg, 12, mix=mix)
+        mine, docs2 = R.query_terms(1000, 12, R._zipf_cdf(), mix=mix)
+        assert torch.equal(docs, docs2)
+        for i, terms in enumerate(mine):
+            assert terms == [int(t) for t in qt[i] if int(t) >= 0]
 
 
 def test_zstandard_stand_in_round_trip():
