@@ -362,7 +362,7 @@ def main() -> int:
                                      encoder=eng.encoder, reranker=eng.reranker, docs_per_shard=dps)
                 n_t = max(3, min(K, 5))
                 t_ms, t_per = timed(dev_step(eng_t), 3, n_t)
-                extras["torch_arm"] = summary(t_ms, t_per, n_t, steps=n_t,
+                extras["torch_arm"] = summary(t_ms, t_per, n_t, timed_steps=n_t,
                                               note="this repo's PyTorch build of the same pipeline on the same shard: cuBLAS bf16 "
                                                    "matmuls, SDPA, torch.topk, NCCL collectives (padded pairs); BM25 / RRF / pair "
                                                    "assembly have no PyTorch equivalent and use the kernels in both arms")

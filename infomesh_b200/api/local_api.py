@@ -149,7 +149,7 @@ def create_admin_app(config: Config | None = None, config_path: Path | None = No
         resp = await call_next(request)
         resp.headers["X-Content-Type-Options"] = "nosniff"
         resp.headers["X-Frame-Options"] = "DENY"
-        resp.headers["Content-Security-Policy"] = "default-src 'self'; script-src 'unsafe-inline'; style-src 'unsafe-inline'"
+        resp.headers["Content-Security-Policy"] = "default-src 'self'; script-src 'self'; style-src 'unsafe-inline'; object-src 'none'; base-uri 'none'"
         return resp
 
     def st(request: Request) -> AdminState:
@@ -338,6 +338,12 @@ def create_admin_app(config: Config | None = None, config_path: Path | None = No
     async def dashboard_page():
         return HTMLResponse(content=_DASHBOARD_HTML)
 
+    @app.get("/dashboard.js")
+    async def dashboard_js():
+        from starlette.responses import Response
+
+        return Response(content=_DASHBOARD_JS, media_type="application/javascript")
+
     return app
 
 
@@ -353,14 +359,31 @@ _DASHBOARD_HTML = """<!doctype html><html><head><meta charset="utf-8"><title>Inf
 <style>body{font:14px system-ui;margin:2rem;background:#111;color:#ddd}h1{font-size:1.3rem}.c{display:inline-block;min-width:11rem;
 margin:.4rem;padding:.8rem 1rem;background:#1c1c1c;border-radius:.5rem}.c b{display:block;font-size:1.4rem;color:#7fd}input{padding:.4rem;width:22rem}
 li{margin:.5rem 0}a{color:#8bf}</style></head><body><h1>InfoMesh node</h1><div id="cards"></div>
-<p><input id="q" placeholder="search the local index"> <button onclick="go()">Search</button></p><ol id="res"></ol>
-<script>
+<p><input id="q" placeholder="search the local index"> <button id="go">Search</button></p><ol id="res"></ol>
+<script src="/dashboard.js"></script></body></html>"""
+
+# Served as a same-origin file so the CSP can be `script-src 'self'` (no inline script, no inline event handlers).
+# Everything that originates from crawled pages (title, snippet, url) is inserted with textContent / createElement only:
+# the snippet's <b>…</b> highlight marks are re-created as elements, any other markup stays inert text, and links are
+# kept only for http(s) URLs.
+_DASHBOARD_JS = """'use strict';
 async function j(u){return (await fetch(u)).json()}
+function el(tag,text){const e=document.createElement(tag);if(text!==undefined)e.textContent=String(text);return e}
+function safeUrl(u){try{const p=new URL(u);return (p.protocol==='http:'||p.protocol==='https:')?p.href:null}catch(e){return null}}
+function snippetNodes(parent,s){const parts=String(s||'').split(/(<b>|<\\/b>)/);let bold=false;
+for(const p of parts){if(p==='<b>'){bold=true;continue}if(p==='</b>'){bold=false;continue}if(!p)continue;
+parent.appendChild(bold?el('b',p):document.createTextNode(p))}}
 async function refresh(){const s=await j('/status'),a=await j('/analytics'),p=await j('/network/peers'),g=await j('/gpu/stats');
 const cards=[['Documents',s.index.document_count],['DB size (MB)',s.index.db_size_mb],['Uptime',s.uptime_human],['Searches',a.total_searches],
 ['Avg latency (ms)',a.avg_latency_ms],['Peers',p.connected],['GPU docs',g.documents??'off']];
-document.getElementById('cards').innerHTML=cards.map(c=>`<div class="c">${c[0]}<b>${c[1]}</b></div>`).join('')}
+const box=document.getElementById('cards');box.replaceChildren();
+for(const c of cards){const d=el('div');d.className='c';d.appendChild(document.createTextNode(c[0]));d.appendChild(el('b',c[1]));box.appendChild(d)}}
 async function go(){const q=document.getElementById('q').value;const r=await j('/search?q='+encodeURIComponent(q)+'&limit=10');
-document.getElementById('res').innerHTML=(r.results||[]).map(x=>`<li><a href="${x.url}">${x.title||x.url}</a> <small>${x.score}</small><br>${x.snippet}</li>`).join('')}
-refresh();setInterval(refresh,5000)
-</script></body></html>"""
+const ol=document.getElementById('res');ol.replaceChildren();
+for(const x of (r.results||[])){const li=el('li');const href=safeUrl(x.url);const head=href?el('a',x.title||x.url):el('span',x.title||x.url);
+if(href){head.href=href;head.rel='noopener noreferrer'}li.appendChild(head);li.appendChild(document.createTextNode(' '));
+li.appendChild(el('small',x.score));li.appendChild(el('br'));snippetNodes(li,x.snippet);ol.appendChild(li)}}
+document.getElementById('go').addEventListener('click',go);
+document.getElementById('q').addEventListener('keydown',e=>{if(e.key==='Enter')go()});
+refresh();setInterval(refresh,5000);
+"""

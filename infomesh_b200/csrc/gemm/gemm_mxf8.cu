@@ -14,7 +14,9 @@
 // On odd N tiles the 192 rows start 64 rows into a 128-row scale chunk, so the SFB operand address is shifted by two
 // TMEM columns (the same trick CUTLASS' sm100 block-scaled collective uses for CtaN = 192).
 //
-// Epilogues (8 warps, TMEM -> registers -> swizzled smem -> TMA store):
+// Epilogues (12 warps = 3 per TMEM lane quadrant, 64 columns each; both 32-column TMEM loads of a warp are issued before
+// the first is consumed -- at K = 768 a tile is only 6 k-blocks (~2300 tensor cycles), so the epilogue's latency chain,
+// not its instruction count, decides whether the tensor pipe stays busy; TMEM -> registers -> swizzled smem -> TMA store):
 //   out_mx = 0: bf16  C = act(acc + bias) + residual
 //   out_mx = 1: MXFP8 C = quantise(act(acc + bias)): per row and 32 columns amax -> ue8m0 -> e4m3, scales written in the
 //               SFA chunk layout of the NEXT GEMM (so FFN-up -> GELU -> FFN-down never materialises bf16 activations and
@@ -43,12 +45,13 @@ constexpr int kMxBM = 128;
 constexpr int kMxBN = 192;
 constexpr int kMxBK = 128;                 // fp8 elements (= bytes) per k-block
 constexpr int kMxStages = 4;
-constexpr int kMxEpiWarps = 8;
+constexpr int kMxEpiWarps = 12;
 constexpr int kMxThreads = 64 + 32 * kMxEpiWarps;
 constexpr int kMxABBytes = (kMxBM + kMxBN) * kMxBK;           // 40960: multiple of 1024 (swizzle-128 alignment)
 constexpr int kMxSfBytes = 512 + 1024;                        // SFA chunk + two SFB chunks
 constexpr int kMxStoreTile = 2048;                            // [32 rows x 32 bf16] or [32 rows x 32 B] staging tile
-constexpr int kMxStoreBytes = kMxEpiWarps * 3 * kMxStoreTile; // three 32-column chunks per warp and tile
+constexpr int kMxChunks = 2;                                  // 32-column chunks per epilogue warp and tile (3 warps x 64 = 192)
+constexpr int kMxStoreBytes = kMxEpiWarps * kMxChunks * kMxStoreTile;
 constexpr int kMxTmemCols = 512;
 constexpr int kMxSfaCol = 2 * kMxBN;                          // 384
 constexpr int kMxSfbCol = kMxSfaCol + 4;                      // 388
@@ -195,10 +198,9 @@ gemm_mxf8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else {
     // ------------------------------- epilogue warps --------------------------------------------------------
     const uint32_t quad = warp & 3u;
-    const uint32_t ew = warp - 2;                              // 0..7
-    const int c_lo = static_cast<int>(ew >> 2) * (kMxBN / 2);  // this warp's 96 columns of the tile
-    uint8_t* my_store = smem_store + ew * 3 * kMxStoreTile;
-    const uint32_t row_in_tile = quad * 32u + lane;
+    const uint32_t ew = warp - 2;                              // 0..11
+    const int c_lo = static_cast<int>(ew >> 2) * (32 * kMxChunks);  // this warp's 64 columns of the tile
+    uint8_t* my_store = smem_store + ew * kMxChunks * kMxStoreTile;
     const int n_kb_out = N >> 7;                               // k-blocks of the NEXT GEMM (out_mx)
     uint32_t acc = 0, acc_phase = 0, tile_cnt = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tile_cnt) {
@@ -209,34 +211,41 @@ gemm_mxf8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       if (lane == 0) tma_store_wait_read<0>();
       __syncwarp();
       if (ep.has_res && lane == 0) {
-        mbar_expect_tx(&res_bar[ew], 3 * kMxStoreTile);
+        mbar_expect_tx(&res_bar[ew], kMxChunks * kMxStoreTile);
 #pragma unroll
-        for (int j = 0; j < 3; ++j)
+        for (int j = 0; j < kMxChunks; ++j)
           tma_load_2d(my_store + j * kMxStoreTile, &tmap_r, &res_bar[ew], col_base + 32 * j, tile_row0);
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
+      // both accumulator chunks in flight before either is touched
+      uint32_t v[kMxChunks][32];
+#pragma unroll
+      for (int j = 0; j < kMxChunks; ++j)
+        tmem_ld_32x32b_x32(tmem_base + ((quad * 32u) << 16) + acc * kMxBN + c_lo + 32 * j, v[j]);
+      tmem_ld_wait();
+      // TMEM reads done -> the MMA warp may start the tile after next on this accumulator stage
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (ep.has_res) mbar_wait(&res_bar[ew], tile_cnt & 1u);
-#pragma unroll 1
-      for (int j = 0; j < 3; ++j) {
+#pragma unroll
+      for (int j = 0; j < kMxChunks; ++j) {
         const int col0 = col_base + 32 * j;
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_base + ((quad * 32u) << 16) + acc * kMxBN + c_lo + 32 * j, v);
-        tmem_ld_wait();
         if (col0 >= N) continue;
         float f[32];
         if (ep.bias != nullptr) {
 #pragma unroll
           for (int q4 = 0; q4 < 8; ++q4) {
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + col0) + q4);
-            f[4 * q4 + 0] = __uint_as_float(v[4 * q4 + 0]) + b4.x;
-            f[4 * q4 + 1] = __uint_as_float(v[4 * q4 + 1]) + b4.y;
-            f[4 * q4 + 2] = __uint_as_float(v[4 * q4 + 2]) + b4.z;
-            f[4 * q4 + 3] = __uint_as_float(v[4 * q4 + 3]) + b4.w;
+            f[4 * q4 + 0] = __uint_as_float(v[j][4 * q4 + 0]) + b4.x;
+            f[4 * q4 + 1] = __uint_as_float(v[j][4 * q4 + 1]) + b4.y;
+            f[4 * q4 + 2] = __uint_as_float(v[j][4 * q4 + 2]) + b4.z;
+            f[4 * q4 + 3] = __uint_as_float(v[j][4 * q4 + 3]) + b4.w;
           }
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[j][i]);
         }
         mx_act32(f, ep.act);
         uint8_t* tile = my_store + j * kMxStoreTile;
@@ -246,16 +255,19 @@ gemm_mxf8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           for (int i = 0; i < 32; ++i) amax = fmaxf(amax, fabsf(f[i]));
           float inv;
           const uint32_t e = ue8m0_from_amax(amax, inv);
-          uint4 q0, q1;
-          q0.x = pack_e4m3x4(f[0] * inv, f[1] * inv, f[2] * inv, f[3] * inv);
-          q0.y = pack_e4m3x4(f[4] * inv, f[5] * inv, f[6] * inv, f[7] * inv);
-          q0.z = pack_e4m3x4(f[8] * inv, f[9] * inv, f[10] * inv, f[11] * inv);
-          q0.w = pack_e4m3x4(f[12] * inv, f[13] * inv, f[14] * inv, f[15] * inv);
-          q1.x = pack_e4m3x4(f[16] * inv, f[17] * inv, f[18] * inv, f[19] * inv);
-          q1.y = pack_e4m3x4(f[20] * inv, f[21] * inv, f[22] * inv, f[23] * inv);
-          q1.z = pack_e4m3x4(f[24] * inv, f[25] * inv, f[26] * inv, f[27] * inv);
-          q1.w = pack_e4m3x4(f[28] * inv, f[29] * inv, f[30] * inv, f[31] * inv);
-          // 32-byte rows; the two halves of lanes l and l^... land in different 16-byte bank groups via the XOR
+          const uint64_t inv2 = pk2(inv, inv);
+          uint32_t w8[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float a0, a1, a2, a3;
+            upk2(mul2(pk2(f[4 * i], f[4 * i + 1]), inv2), a0, a1);
+            upk2(mul2(pk2(f[4 * i + 2], f[4 * i + 3]), inv2), a2, a3);
+            w8[i] = pack_e4m3x4(a0, a1, a2, a3);
+          }
+          const uint4 q0 = make_uint4(w8[0], w8[1], w8[2], w8[3]), q1 = make_uint4(w8[4], w8[5], w8[6], w8[7]);
+          // 32-byte rows: swap the two 16-byte halves on every other group of four lanes so a quarter-warp's stores spread
+          // over all eight 16-byte bank groups ... the TMA store below expects plain rows, so the swap is undone by
+          // construction: (half ^ x) selects the slot, x ? the other vector : this one selects the data
           const uint32_t x = (lane >> 2) & 1u;
           *reinterpret_cast<uint4*>(tile + lane * 32 + ((0u ^ x) << 4)) = x ? q1 : q0;
           *reinterpret_cast<uint4*>(tile + lane * 32 + ((1u ^ x) << 4)) = x ? q0 : q1;
@@ -289,13 +301,7 @@ gemm_mxf8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         __syncwarp();
         if (lane == 0) tma_store_2d(&tmap_c, tile, col0, tile_row0);
       }
-      // accumulator stage drained -> back to the MMA warp; one bulk group per tile
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        tma_store_commit();
-        mbar_arrive(&tmem_empty[acc]);
-      }
+      if (lane == 0) tma_store_commit();   // one bulk group per tile
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;

@@ -94,6 +94,10 @@ class IndexSubmitReceiver:
         self._keys = key_registry
         self._received = self._rejected = self._indexed = 0
 
+    def bind_key_registry(self, key_registry) -> None:
+        """Called by the P2P node once its transport exists: submissions are then checked against the verified keys."""
+        self._keys = key_registry
+
     @property
     def stats(self) -> dict[str, int]:
         return {"received": self._received, "rejected": self._rejected, "indexed": self._indexed}
@@ -105,28 +109,43 @@ class IndexSubmitReceiver:
         return IndexSubmitAck(url=url, doc_id=doc_id, success=ok, error=error,
                               peer_id=self._key_pair.peer_id if self._key_pair else "")
 
-    def handle_submit(self, payload: dict[str, Any]) -> IndexSubmitAck:
+    def _reject(self, url: str, pid: str, reason: str) -> IndexSubmitAck:
+        self._rejected += 1
+        logger.warning("index_submit_rejected", peer_id=pid, url=url, reason=reason)
+        return self._ack(url, ok=False, error=reason)
+
+    def handle_submit(self, payload: dict[str, Any], sender: str | None = None) -> IndexSubmitAck:
+        """``sender``: peer id the transport VERIFIED for the enclosing envelope ("" = unsigned frame, ``None`` = the
+        caller has no transport identity, e.g. the localhost HTTP bridge).
+
+        Checks, in order: the text really hashes to ``text_hash`` (a captured signature cannot be replayed with other
+        text); with a ``peer_acl`` in force the claimed ``peer_id`` must be in it, must equal the transport-verified
+        sender, and the Ed25519 signature over ``url:text_hash:raw_html_hash`` must verify under that peer's known key.
+        In open mode a signature is still checked whenever the key is known."""
         from infomesh_b200.crawler.parser import ParsedPage
+        from infomesh_b200.hashing import content_hash
         from infomesh_b200.p2p.keys import verify_with_public_key
         from infomesh_b200.services import index_document
 
         self._received += 1
         pid, url = str(payload.get("peer_id", "")), str(payload.get("url", ""))
-        if not self.is_peer_allowed(pid):
-            self._rejected += 1
-            logger.warning("index_submit_rejected", peer_id=pid, url=url, reason="peer_not_in_acl")
-            return self._ack(url, ok=False, error="peer_not_allowed")
         text_hash, raw_hash = str(payload.get("text_hash", "")), str(payload.get("raw_html_hash", ""))
-        # with an ACL in force a verifiable signature is mandatory; in open mode it is checked when the key is known
+        if content_hash(str(payload.get("text", ""))) != text_hash:
+            return self._reject(url, pid, "text_hash_mismatch")
+        if not self.is_peer_allowed(pid):
+            return self._reject(url, pid, "peer_not_allowed")
+        if sender is not None and pid and sender and sender != pid:
+            return self._reject(url, pid, "peer_id_mismatch")
         pub = self._keys.get(pid) if self._keys is not None and pid else None
         sig = payload.get("signature") or b""
-        if pub is not None:
-            if not verify_with_public_key(pub, _sign_blob(url, text_hash, raw_hash), bytes(sig)):
-                self._rejected += 1
-                return self._ack(url, ok=False, error="bad_signature")
-        elif self._acl and self._keys is not None:
-            self._rejected += 1
-            return self._ack(url, ok=False, error="unknown_key")
+        if self._acl:
+            # an ACL only means something if the claimed identity is proven end to end
+            if sender is not None and sender != pid:
+                return self._reject(url, pid, "unsigned_sender")
+            if pub is None:
+                return self._reject(url, pid, "unknown_key")
+        if pub is not None and not verify_with_public_key(pub, _sign_blob(url, text_hash, raw_hash), bytes(sig)):
+            return self._reject(url, pid, "bad_signature")
         page = ParsedPage(url=url, title=str(payload.get("title", "")), text=str(payload.get("text", "")),
                           raw_html_hash=raw_hash, text_hash=text_hash, language=str(payload.get("language", "")))
         try:

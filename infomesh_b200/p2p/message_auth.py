@@ -62,18 +62,40 @@ def envelope_from_dict(d: dict[str, Any]) -> SignedEnvelope:
     return SignedEnvelope(d["payload"], d["peer_id"], d["signature"], d["nonce"], d["timestamp"])
 
 
-class PeerKeyRegistry:
-    def __init__(self):
-        self._keys: dict[str, bytes] = {}
+MAX_KNOWN_KEYS = 10_000          # LRU bound of the trust-on-first-use key table
+NONCE_WINDOW = 1024              # how far behind the highest nonce an unseen nonce is still accepted
 
-    def register(self, peer_id: str, public_key: bytes) -> None:
+
+class PeerKeyRegistry:
+    """peer id -> Ed25519 public key, least-recently-used eviction past ``capacity`` so a flood of fresh identities cannot
+    grow the table without bound (pinned entries -- operator-configured peers -- are never evicted)."""
+
+    def __init__(self, capacity: int = MAX_KNOWN_KEYS):
+        self._keys: OrderedDict[str, bytes] = OrderedDict()
+        self._pinned: set[str] = set()
+        self._cap = max(1, int(capacity))
+
+    def register(self, peer_id: str, public_key: bytes, *, pinned: bool = False) -> None:
         self._keys[peer_id] = public_key
+        self._keys.move_to_end(peer_id)
+        if pinned:
+            self._pinned.add(peer_id)
+        if len(self._keys) > self._cap:
+            for victim in list(self._keys):
+                if len(self._keys) <= self._cap:
+                    break
+                if victim not in self._pinned and victim != peer_id:
+                    del self._keys[victim]
 
     def get(self, peer_id: str) -> bytes | None:
-        return self._keys.get(peer_id)
+        pub = self._keys.get(peer_id)
+        if pub is not None:
+            self._keys.move_to_end(peer_id)
+        return pub
 
     def remove(self, peer_id: str) -> None:
         self._keys.pop(peer_id, None)
+        self._pinned.discard(peer_id)
 
     def __contains__(self, peer_id: str) -> bool:
         return peer_id in self._keys
@@ -83,18 +105,38 @@ class PeerKeyRegistry:
 
 
 class NonceTracker:
-    """Highest nonce per sender; LRU-evicts beyond MAX_NONCE_HISTORY senders."""
+    """Replay filter per sender: a sliding window below the highest nonce seen.
 
-    def __init__(self):
+    A strictly increasing rule rejects honest traffic when frames of one sender arrive out of order (each request uses
+    its own TCP connection here, so a large REPLICATE can land after a later PING).  A nonce is accepted iff it has not
+    been seen and is not older than ``NONCE_WINDOW`` below the sender's highest; senders are LRU-evicted beyond
+    MAX_NONCE_HISTORY."""
+
+    def __init__(self, window: int = NONCE_WINDOW):
         self._highest: OrderedDict[str, int] = OrderedDict()
+        self._seen: dict[str, set[int]] = {}
+        self._window = max(0, int(window))
+
+    def acceptable(self, peer_id: str, nonce: int) -> bool:
+        hi = self._highest.get(peer_id, 0)
+        if nonce > hi:
+            return True
+        return nonce > hi - self._window and nonce > 0 and nonce not in self._seen.get(peer_id, ())
 
     def check_and_record(self, peer_id: str, nonce: int) -> bool:
-        if nonce <= self._highest.get(peer_id, 0):
+        if not self.acceptable(peer_id, nonce):
             return False
-        self._highest[peer_id] = nonce
+        hi = max(self._highest.get(peer_id, 0), nonce)
+        self._highest[peer_id] = hi
         self._highest.move_to_end(peer_id)
+        seen = self._seen.setdefault(peer_id, set())
+        seen.add(nonce)
+        if len(seen) > 2 * self._window + 2:
+            floor = hi - self._window
+            self._seen[peer_id] = {n for n in seen if n > floor}
         while len(self._highest) > MAX_NONCE_HISTORY:
-            self._highest.popitem(last=False)
+            old, _ = self._highest.popitem(last=False)
+            self._seen.pop(old, None)
         return True
 
     def highest(self, peer_id: str) -> int:
@@ -126,7 +168,7 @@ def verify_envelope(envelope: SignedEnvelope, key_registry: PeerKeyRegistry, non
     age = abs(ts - envelope.timestamp)
     if age > max_age:
         raise VerificationError(f"message too old ({age:.0f}s > {max_age:.0f}s)")
-    if envelope.nonce <= nonce_tracker.highest(pid):
+    if not nonce_tracker.acceptable(pid, envelope.nonce):
         raise VerificationError(f"replayed nonce {envelope.nonce} from {pid[:16]}")
     if not _verify_raw(pub, _canonical_bytes(pid, envelope.nonce, envelope.timestamp, envelope.payload),
                        envelope.signature):

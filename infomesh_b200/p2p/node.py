@@ -219,6 +219,8 @@ class InfoMeshNode:
         self._stop_async = asyncio.Event()
         self._prepare_identity()
         self._transport = Transport(self._key_pair, throttle=self._throttle, is_isolated_fn=self._is_isolated)
+        if self._index_submit_receiver is not None and hasattr(self._index_submit_receiver, "bind_key_registry"):
+            self._index_submit_receiver.bind_key_registry(self._transport.keys)
         await self._transport.listen(cfg.node.listen_address, cfg.node.listen_port)
         self._kad = KadDHT(self._transport, subnet_limiter=self._subnet_limiter)
         self._dht = InfoMeshDHT(self._kad, self._peer_id)
@@ -306,7 +308,8 @@ class InfoMeshNode:
             if peer.peer_id and payload.get("peer_id") and payload["peer_id"] != peer.peer_id:
                 return MessageType.INDEX_SUBMIT_ACK, {"url": payload.get("url", ""), "success": False,
                                                        "error": "peer_id_mismatch", "doc_id": 0, "peer_id": self._peer_id}
-            ack = await asyncio.get_running_loop().run_in_executor(None, self._index_submit_receiver.handle_submit, payload)
+            ack = await asyncio.get_running_loop().run_in_executor(None, self._index_submit_receiver.handle_submit, payload,
+                                                                   peer.peer_id)
             return MessageType.INDEX_SUBMIT_ACK, asdict(ack)
 
         async def on_pex(payload, peer: PeerInfo):

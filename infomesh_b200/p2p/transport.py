@@ -66,6 +66,12 @@ async def read_frame(reader: asyncio.StreamReader, *, max_bytes: int = MAX_MESSA
     return prefix + await reader.readexactly(n)
 
 
+# message types that change a node's state: an unsigned frame of these kinds is refused even when the transport otherwise
+# accepts unsigned traffic (read-only requests from anonymous peers)
+WRITE_TYPES = frozenset({MessageType.INDEX_SUBMIT, MessageType.REPLICATE_REQUEST, MessageType.DHT_STORE, MessageType.INDEX_PUBLISH,
+                         MessageType.KEY_REVOCATION, MessageType.ATTESTATION_PUBLISH})
+
+
 class Transport:
     def __init__(self, key_pair: Any | None = None, *, throttle: BandwidthThrottle | None = None,
                  is_isolated_fn: Callable[[str], bool] | None = None, require_signed: bool = False):
@@ -114,18 +120,23 @@ class Transport:
         """-> (type, payload, verified sender id or "")."""
         kind, payload = decode_message(frame)
         if kind != MessageType.SIGNED_ENVELOPE:
-            if self._require_signed:
+            if self._require_signed or kind in WRITE_TYPES:
                 raise MA.VerificationError("unsigned message refused")
             return kind, payload, ""
         pid, pub = str(payload.get("peer_id", "")), payload.get("public_key")
-        if isinstance(pub, bytes | bytearray) and pid and pid not in self.keys:
+        registry = self.keys
+        first_use = isinstance(pub, bytes | bytearray) and bool(pid) and pid not in self.keys
+        if first_use:
             from infomesh_b200.p2p.keys import peer_id_from_public_key
 
             if peer_id_from_public_key(bytes(pub)) != pid:      # trust-on-first-use, bound to the id derivation
                 raise MA.VerificationError("public key does not match peer id")
-            self.keys.register(pid, bytes(pub))
-        inner = MA.verify_envelope(MA.envelope_from_dict(payload), self.keys, self._nonces_in,
+            registry = MA.PeerKeyRegistry(1)                     # candidate key: verify FIRST, remember only on success
+            registry.register(pid, bytes(pub))
+        inner = MA.verify_envelope(MA.envelope_from_dict(payload), registry, self._nonces_in,
                                    is_isolated_fn=self._isolated)
+        if first_use:
+            self.keys.register(pid, bytes(pub))
         kind, body = decode_message(inner)
         return kind, body, pid
 
@@ -168,7 +179,10 @@ class Transport:
 
     # ------------------------------------------------------------------ client side
     async def request(self, addr: str | tuple[str, int], msg_type: MessageType, payload: dict[str, Any], *,
-                      timeout: float = 5.0, expect_reply: bool = True) -> tuple[MessageType, dict[str, Any]] | None:
+                      timeout: float = 5.0, expect_reply: bool = True,
+                      expect_peer: str | None = None) -> tuple[MessageType, dict[str, Any]] | None:
+        """One request / reply exchange.  ``expect_peer``: the peer id that was dialled -- a reply signed by anyone else
+        (an on-path host answering with its own self-signed envelope) or not signed at all is rejected."""
         host, port = addr if isinstance(addr, tuple) else parse_multiaddr(addr)[:2]
 
         async def _go():
@@ -181,7 +195,9 @@ class Transport:
                 self.bytes_in += len(frame)
                 if self.throttle:
                     await self.throttle.acquire_download(len(frame))
-                kind, body, _ = self._unwrap(frame)
+                kind, body, sender = self._unwrap(frame)
+                if expect_peer and sender != expect_peer:
+                    raise MA.VerificationError(f"reply signed by {sender[:16] or 'nobody'}, expected {expect_peer[:16]}")
                 return kind, body
             finally:
                 writer.close()

@@ -22,7 +22,11 @@ def _cfg(tmp_path, **net):
 
 
 def _page(i=0, text="Blackwell tensor cores keep accumulators in tensor memory. " * 5):
-    return ParsedPage(url=f"https://example.org/p{i}", title=f"Page {i}", text=text, language="en", raw_html_hash=f"raw{i}", text_hash=f"txt{i}")
+    from infomesh_b200.hashing import content_hash
+
+    text = f"{text}#{i}"
+    return ParsedPage(url=f"https://example.org/p{i}", title=f"Page {i}", text=text, language="en", raw_html_hash=f"raw{i}",
+                      text_hash=content_hash(text))
 
 
 def _store(cfg):
@@ -156,13 +160,19 @@ def test_submit_roundtrip_with_acl_and_signature(tmp_path):
     k2, a2 = decode_message(recv.build_ack_message(ack))
     assert k2 == MessageType.INDEX_SUBMIT_ACK and a2["url"] == "https://example.org/p1"
 
-    forged = dict(payload, text_hash="other")                          # signature no longer covers the payload
+    forged = dict(payload, url="https://example.org/elsewhere")         # signature no longer covers the payload
     assert recv.handle_submit(forged).error == "bad_signature"
+    swapped = dict(payload, text="attacker text under a captured signature")
+    assert recv.handle_submit(swapped).error == "text_hash_mismatch"    # a sniffed signature cannot carry other text
     _, outsider = decode_message(IndexSubmitSender(cfg, key_pair=stranger).build_submit_message(_page(2)))
     assert recv.handle_submit(outsider).error == "peer_not_allowed"
+    # transport-verified sender must be the claimed peer; an unsigned frame cannot claim an ACL'd identity
+    assert recv.handle_submit(payload, sender=stranger.peer_id).error == "peer_id_mismatch"
+    assert recv.handle_submit(payload, sender="").error == "unsigned_sender"
+    assert recv.handle_submit(payload, sender=crawler.peer_id).error == ""          # duplicate url -> indexed as no-op
     reg.remove(crawler.peer_id)
     assert recv.handle_submit(payload).error == "unknown_key"          # ACL in force => a verifiable key is mandatory
-    assert recv.stats == {"received": 4, "rejected": 3, "indexed": 1}
+    assert recv.stats["rejected"] == 6 and recv.stats["indexed"] == 2
     st.close()
 
 
@@ -177,7 +187,8 @@ def test_open_mode_accepts_unsigned_submissions_and_reports_index_errors(tmp_pat
     assert payload["peer_id"] == "" and payload["signature"] == b""
     assert recv.handle_submit(payload).success
     st.close()                                                         # a closed store makes indexing raise
-    bad = recv.handle_submit(dict(payload, url="https://example.org/other", text_hash="zz"))
+    _, other = decode_message(IndexSubmitSender(cfg).build_submit_message(_page(4)))
+    bad = recv.handle_submit(other)
     assert not bad.success and bad.error and recv.stats["indexed"] == 1
 
 

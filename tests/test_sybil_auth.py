@@ -82,10 +82,20 @@ def test_replay_and_stale_messages_rejected():
     e1 = MA.sign_envelope(b"a", kp, ctr, now=1000.0)
     e2 = MA.sign_envelope(b"b", kp, ctr, now=1000.0)
     assert MA.verify_envelope(e2, reg, trk, now=1000.0) == b"b"
+    # frames of one sender may overtake each other (one TCP connection per request): an UNSEEN lower nonce inside the
+    # sliding window is accepted once ...
+    assert MA.verify_envelope(e1, reg, trk, now=1000.0) == b"a"
+    # ... but every exact replay is refused, and so is anything older than the window
+    for env in (e1, e2):
+        with pytest.raises(MA.VerificationError, match="replayed"):
+            MA.verify_envelope(env, reg, trk, now=1000.0)
+    far = MA.NonceCounter(10 * MA.NONCE_WINDOW)
+    ehi = MA.sign_envelope(b"hi", kp, far, now=1000.0)
+    assert MA.verify_envelope(ehi, reg, trk, now=1000.0) == b"hi"
+    stale = MA.sign_envelope(b"old", kp, MA.NonceCounter(5), now=1000.0)
     with pytest.raises(MA.VerificationError, match="replayed"):
-        MA.verify_envelope(e1, reg, trk, now=1000.0)                    # lower nonce after a higher one
-    with pytest.raises(MA.VerificationError, match="replayed"):
-        MA.verify_envelope(e2, reg, trk, now=1000.0)
+        MA.verify_envelope(stale, reg, trk, now=1000.0)
+    ctr = MA.NonceCounter(20 * MA.NONCE_WINDOW)
     e3 = MA.sign_envelope(b"c", kp, ctr, now=1000.0)
     with pytest.raises(MA.VerificationError, match="too old"):
         MA.verify_envelope(e3, reg, trk, now=1000.0 + 10_000)
