@@ -14,6 +14,13 @@
 // On odd N tiles the 192 rows start 64 rows into a 128-row scale chunk, so the SFB operand address is shifted by two
 // TMEM columns (the same trick CUTLASS' sm100 block-scaled collective uses for CtaN = 192).
 //
+// A-resident variant (ARES, K <= 768): at K = 768 a 128 x 192 tile needs 240 KB of operands for ~2300 tensor cycles, and
+// 148 SMs asking for that saturate the ~12 TB/s the L2 can deliver to TMA before the tensor pipes are busy.  The
+// activation block [128 rows x K] (<= 96 KB) is therefore loaded ONCE per work unit and stays in shared memory while
+// the unit's G consecutive N tiles stream only their weight tiles through a 3-stage ring (-27..37 % operand traffic).
+// Each A k-block has its own full / empty barrier pair, so the next unit's A[kb] is fetched as soon as the last N tile
+// of the current unit has consumed A[kb] -- no bubble between units.
+//
 // Epilogues (12 warps = 3 per TMEM lane quadrant, 64 columns each; both 32-column TMEM loads of a warp are issued before
 // the first is consumed -- at K = 768 a tile is only 6 k-blocks (~2300 tensor cycles), so the epilogue's latency chain,
 // not its instruction count, decides whether the tensor pipe stays busy; TMEM -> registers -> swizzled smem -> TMA store):
@@ -39,6 +46,7 @@ struct MxEpilogue {
   int out_mx;
   int has_res;
   const int* m_dev;         // optional device-side row count (varlen batches under CUDA graphs)
+  int n_per_unit;           // G: consecutive N tiles per work unit (1 unless the A-resident variant is used)
 };
 
 constexpr int kMxBM = 128;
@@ -55,7 +63,15 @@ constexpr int kMxStoreBytes = kMxEpiWarps * kMxChunks * kMxStoreTile;
 constexpr int kMxTmemCols = 512;
 constexpr int kMxSfaCol = 2 * kMxBN;                          // 384
 constexpr int kMxSfbCol = kMxSfaCol + 4;                      // 388
-constexpr int kMxSmemBytes = kMxStages * (kMxABBytes + kMxSfBytes) + kMxStoreBytes + 1024 + 256;
+constexpr int kMxBarBytes = 512;
+constexpr int kMxSmemBytes = kMxStages * (kMxABBytes + kMxSfBytes) + kMxStoreBytes + 1024 + kMxBarBytes;
+// A-resident variant
+constexpr int kAresMaxKb = 6;                                 // K <= 768
+constexpr int kAresBStages = 3;
+constexpr int kAresABytes = kMxBM * kMxBK;                    // 16384 per k-block
+constexpr int kAresBBytes = kMxBN * kMxBK;                    // 24576 per stage
+constexpr int kAresSmemBytes = kAresMaxKb * (kAresABytes + 512) + kAresBStages * (kAresBBytes + 1024) + kMxStoreBytes + 1024 +
+                               kMxBarBytes;
 
 __device__ __forceinline__ void mx_act32(float (&f)[32], int act) {
   switch (act) {
@@ -83,6 +99,7 @@ __device__ __forceinline__ void mx_act32(float (&f)[32], int act) {
   }
 }
 
+template <bool ARES>
 __global__ void __launch_bounds__(kMxThreads, 1)
 gemm_mxf8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r,
@@ -90,14 +107,25 @@ gemm_mxf8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint8_t* smem_sf = smem + kMxStages * kMxABBytes;                 // [stage][SFA 512 | SFB 1024]
-  uint8_t* smem_store = smem_sf + kMxStages * kMxSfBytes;           // 1024-aligned: 4 * 1536 = 6144
+  // ring layout: [stage][A 16K | B 24K] ... [stage][SFA 512 | SFB 1024];  A-resident: A[kb] x6, B[stage] x3, SFA[kb] x6, SFB[stage] x3
+  uint8_t* sA = smem;
+  uint8_t* sB = ARES ? smem + kAresMaxKb * kAresABytes : smem + kMxBM * kMxBK;
+  uint8_t* sSFA = ARES ? sB + kAresBStages * kAresBBytes : smem + kMxStages * kMxABBytes;
+  uint8_t* sSFB = ARES ? sSFA + kAresMaxKb * 512 : sSFA + 512;
+  uint8_t* smem_store = ARES ? sSFB + kAresBStages * 1024 : sSFA + kMxStages * kMxSfBytes;   // 1024-aligned in both layouts
+  constexpr uint32_t kAStride = ARES ? kAresABytes : kMxABBytes;      // bytes between consecutive A slots
+  constexpr uint32_t kBStride = ARES ? kAresBBytes : kMxABBytes;
+  constexpr uint32_t kSfaStride = ARES ? 512 : kMxSfBytes;
+  constexpr uint32_t kSfbStride = ARES ? 1024 : kMxSfBytes;
+  constexpr uint32_t kBStages = ARES ? kAresBStages : kMxStages;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_store + kMxStoreBytes);
   uint64_t* empty_bar = full_bar + kMxStages;
   uint64_t* tmem_full = empty_bar + kMxStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* res_bar = tmem_empty + 2;      // [8] residual tiles of one epilogue warp
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + kMxEpiWarps);
+  uint64_t* res_bar = tmem_empty + 2;      // [12] residual tiles of one epilogue warp
+  uint64_t* a_full = res_bar + kMxEpiWarps;   // [6] A-resident: k-block kb of the unit's activation block has landed
+  uint64_t* a_empty = a_full + kAresMaxKb;    // [6] ... and has been consumed by the unit's last N tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + kAresMaxKb);
 
   const uint32_t warp = warp_id();
   const uint32_t lane = lane_id();
@@ -118,6 +146,10 @@ gemm_mxf8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_init(&tmem_empty[i], kMxEpiWarps);
     }
     for (int i = 0; i < kMxEpiWarps; ++i) mbar_init(&res_bar[i], 1);
+    for (int i = 0; i < kAresMaxKb; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -134,28 +166,41 @@ gemm_mxf8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int num_m = (M + kMxBM - 1) / kMxBM;
   const int num_n = (N + kMxBN - 1) / kMxBN;
   const int num_k = K / kMxBK;
-  const int num_tiles = num_m * num_n;
+  // work units: (m block, group of G consecutive N tiles); G = 1 makes a unit one tile in row-major tile order
+  const int G = ARES ? max(1, ep.n_per_unit) : 1;
+  const int n_groups = (num_n + G - 1) / G;
+  const int num_units = num_m * n_groups;
 
   if (warp == 0) {
     // ------------------------------- producer: TMA tiles + bulk scale chunks -------------------------------
     if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int m_blk = t / num_n, n_blk = t % num_n;
-        const int chunk_b = (n_blk * kMxBN) >> 7;     // first 128-row scale chunk the tile touches
-        for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * kMxABBytes;
-          uint8_t* sb = sa + kMxBM * kMxBK;
-          uint8_t* ssf = smem_sf + stage * kMxSfBytes;
-          mbar_expect_tx(&full_bar[stage], kMxABBytes + kMxSfBytes);
-          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kMxBK, m_blk * kMxBM);
-          tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * kMxBK, n_blk * kMxBN);
-          bulk_load(ssf, ep.sfa + (static_cast<size_t>(m_blk) * num_k + kb) * 512, 512, &full_bar[stage]);
-          bulk_load(ssf + 512, ep.sfb + (static_cast<size_t>(kb) * ep.n_chunks_b + chunk_b) * 512, 1024, &full_bar[stage]);
-          if (++stage == kMxStages) {
-            stage = 0;
-            phase ^= 1;
+      uint32_t stage = 0, phase = 0, unit_i = 0;
+      for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++unit_i) {
+        const int m_blk = u / n_groups, n0 = (u % n_groups) * G, n1 = min(num_n, n0 + G);
+        for (int n_blk = n0; n_blk < n1; ++n_blk) {
+          const int chunk_b = (n_blk * kMxBN) >> 7;     // first 128-row scale chunk the tile touches
+          for (int kb = 0; kb < num_k; ++kb) {
+            if constexpr (ARES) {
+              if (n_blk == n0) {    // the unit's activation k-block: once, into its own slot
+                mbar_wait(&a_empty[kb], (unit_i & 1u) ^ 1u);
+                mbar_expect_tx(&a_full[kb], kAresABytes + 512);
+                tma_load_2d(sA + kb * kAStride, &tmap_a, &a_full[kb], kb * kMxBK, m_blk * kMxBM);
+                bulk_load(sSFA + kb * kSfaStride, ep.sfa + (static_cast<size_t>(m_blk) * num_k + kb) * 512, 512, &a_full[kb]);
+              }
+            }
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_expect_tx(&full_bar[stage], ARES ? kAresBBytes + 1024 : kMxABBytes + kMxSfBytes);
+            if constexpr (!ARES) {
+              tma_load_2d(sA + stage * kAStride, &tmap_a, &full_bar[stage], kb * kMxBK, m_blk * kMxBM);
+              bulk_load(sSFA + stage * kSfaStride, ep.sfa + (static_cast<size_t>(m_blk) * num_k + kb) * 512, 512, &full_bar[stage]);
+            }
+            tma_load_2d(sB + stage * kBStride, &tmap_b, &full_bar[stage], kb * kMxBK, n_blk * kMxBN);
+            bulk_load(sSFB + stage * kSfbStride, ep.sfb + (static_cast<size_t>(kb) * ep.n_chunks_b + chunk_b) * 512, 1024,
+                      &full_bar[stage]);
+            if (++stage == kBStages) {
+              stage = 0;
+              phase ^= 1;
+            }
           }
         }
       }
@@ -163,36 +208,45 @@ gemm_mxf8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else if (warp == 1) {
     // ------------------------------- MMA issuer (whole warp, one elected lane issues) ----------------------
     const uint32_t idesc = umma_idesc_mxf8(kMxBM, kMxBN);
-    const uint64_t a_desc0 = umma_desc_k_sw128(smem_u32(smem));
-    const uint64_t b_desc0 = umma_desc_k_sw128(smem_u32(smem) + kMxBM * kMxBK);
-    const uint64_t sfa_desc0 = umma_desc_sf_chunk(smem_u32(smem_sf));
-    const uint64_t sfb_desc0 = umma_desc_sf_chunk(smem_u32(smem_sf) + 512);
+    const uint64_t a_desc0 = umma_desc_k_sw128(smem_u32(sA));
+    const uint64_t b_desc0 = umma_desc_k_sw128(smem_u32(sB));
+    const uint64_t sfa_desc0 = umma_desc_sf_chunk(smem_u32(sSFA));
+    const uint64_t sfb_desc0 = umma_desc_sf_chunk(smem_u32(sSFB));
     const uint32_t t_sfa = tmem_base + kMxSfaCol;
     const uint32_t t_sfb_cp = tmem_base + kMxSfbCol;
-    uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int n_blk = t % num_n;
-      // odd tiles start 64 rows into their first scale chunk: skip two TMEM columns of SFB
-      const uint32_t t_sfb = t_sfb_cp + (((n_blk * kMxBN) & 127) >> 5);
-      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * kMxBN;
-      for (int kb = 0; kb < num_k; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+    uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, unit_i = 0;
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x, ++unit_i) {
+      const int n0 = (u % n_groups) * G, n1 = min(num_n, n0 + G);
+      for (int n_blk = n0; n_blk < n1; ++n_blk) {
+        // odd tiles start 64 rows into their first scale chunk: skip two TMEM columns of SFB
+        const uint32_t t_sfb = t_sfb_cp + (((n_blk * kMxBN) & 127) >> 5);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint64_t soff = static_cast<uint64_t>(stage * (kMxABBytes >> 4));
-        const uint64_t sfoff = static_cast<uint64_t>(stage * (kMxSfBytes >> 4));
-        umma_mxf8_kblock128_warp(d_tmem, a_desc0 + soff, b_desc0 + soff, idesc, t_sfa, t_sfb_cp, t_sfb, sfa_desc0 + sfoff,
-                                 sfb_desc0 + sfoff, kb != 0 ? 1u : 0u, &empty_bar[stage]);
-        if (++stage == kMxStages) {
-          stage = 0;
-          phase ^= 1;
+        const uint32_t d_tmem = tmem_base + acc * kMxBN;
+        for (int kb = 0; kb < num_k; ++kb) {
+          if constexpr (ARES) {
+            if (n_blk == n0) mbar_wait(&a_full[kb], unit_i & 1u);
+          }
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_slot = ARES ? static_cast<uint32_t>(kb) : stage;
+          umma_mxf8_kblock128_warp(d_tmem, a_desc0 + static_cast<uint64_t>(a_slot * (kAStride >> 4)),
+                                   b_desc0 + static_cast<uint64_t>(stage * (kBStride >> 4)), idesc, t_sfa, t_sfb_cp, t_sfb,
+                                   sfa_desc0 + static_cast<uint64_t>(a_slot * (kSfaStride >> 4)),
+                                   sfb_desc0 + static_cast<uint64_t>(stage * (kSfbStride >> 4)), kb != 0 ? 1u : 0u, &empty_bar[stage]);
+          if constexpr (ARES) {
+            if (n_blk == n1 - 1) umma_commit_warp(&a_empty[kb]);   // last N tile of the unit: A[kb] may be overwritten
+          }
+          if (++stage == kBStages) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
-      }
-      umma_commit_warp(&tmem_full[acc]);
-      if (++acc == 2) {
-        acc = 0;
-        acc_phase ^= 1;
+        umma_commit_warp(&tmem_full[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
       }
     }
   } else {
@@ -203,8 +257,8 @@ gemm_mxf8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint8_t* my_store = smem_store + ew * kMxChunks * kMxStoreTile;
     const int n_kb_out = N >> 7;                               // k-blocks of the NEXT GEMM (out_mx)
     uint32_t acc = 0, acc_phase = 0, tile_cnt = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tile_cnt) {
-      const int m_blk = t / num_n, n_blk = t % num_n;
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x)
+    for (int m_blk = u / n_groups, n_blk = (u % n_groups) * G, n_end = min(num_n, n_blk + G); n_blk < n_end; ++n_blk, ++tile_cnt) {
       const int tile_row0 = m_blk * kMxBM + static_cast<int>(quad * 32u);
       const int col_base = n_blk * kMxBN + c_lo;
       // the staging tiles are free once the previous tile's stores have been read out of smem
@@ -320,7 +374,9 @@ gemm_mxf8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 // C = act(A·B^T + bias) (+ residual) with MXFP8 operands; out_mx selects bf16 or MXFP8 output (see file header).
 IM_API int im_gemm_mxf8(const void* A, const void* SFA, const void* B, const void* SFB, int n_chunks_b, void* C, void* C_sf,
                         const float* bias, const void* residual, int M, int N, int K, int lda, int ldb, int ldc, int ldr,
-                        int act, int out_mx, const int* m_dev, int max_ctas, void* stream) {
+                        int act, int out_mx, const int* m_dev, int max_ctas, void* stream, int mode) {
+  // mode: 0 = pick the variant (A-resident when K <= 768 and it pays), 1 = always the operand-ring kernel, 2 = force the
+  // A-resident kernel (tests / A-B timing).  Returns < 0 on error, else the N-tile group size used (0 = ring kernel).
   using namespace im;
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if (K % kMxBK) return set_error("im_gemm_mxf8", "K must be a multiple of 128");
@@ -332,7 +388,8 @@ IM_API int im_gemm_mxf8(const void* A, const void* SFA, const void* B, const voi
     return set_error("im_gemm_mxf8", "SFB needs ceil(round_up(N,192)/128) chunks per k-block");
   static bool configured = false;
   if (!configured) {
-    IM_CUDA_OK(cudaFuncSetAttribute(gemm_mxf8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMxSmemBytes));
+    IM_CUDA_OK(cudaFuncSetAttribute(gemm_mxf8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMxSmemBytes));
+    IM_CUDA_OK(cudaFuncSetAttribute(gemm_mxf8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAresSmemBytes));
     configured = true;
   }
   CUtensorMap ta, tb, tc, tr;
@@ -355,12 +412,31 @@ IM_API int im_gemm_mxf8(const void* A, const void* SFA, const void* B, const voi
   ep.out_mx = out_mx;
   ep.has_res = residual != nullptr ? 1 : 0;
   ep.m_dev = m_dev;
-  const int tiles = ((M + kMxBM - 1) / kMxBM) * ((N + kMxBN - 1) / kMxBN);
-  int grid = tiles < sm_count() ? tiles : sm_count();
+  const int num_m = (M + kMxBM - 1) / kMxBM, num_n = (N + kMxBN - 1) / kMxBN;
+  // A-resident variant when the activation block fits (K <= 768) and there is enough parallelism left after grouping N
+  // tiles: halve the group until the units cover the SMs at least twice (G = 1 degenerates to the ring kernel's order)
+  int G = 1;
+  // Measured on B200 (profiles/mx_gemm_check_r2c.log): the kernel is bound by shared-memory bandwidth (TMA fill + UMMA
+  // operand reads + epilogue staging ~ 576 KB per 128x192x768 tile against 128 B/clk), and with only 3 B stages left the
+  // A-resident variant loses more to L2 latency than it saves in fill traffic (QKV 200 vs 174 us, FFN-up 230 vs 242 us).
+  // It therefore runs only on request (mode 2); the operand ring is the default.
+  bool ares = (K / kMxBK) <= kAresMaxKb && num_n > 1 && mode == 2;
+  if (ares) {
+    G = num_n;
+    while (G > 1 && static_cast<long long>(num_m) * ((num_n + G - 1) / G) < 2LL * sm_count()) G = (G + 1) / 2;
+    if (G <= 1 && mode != 2) ares = false;
+    if (G < 1) G = 1;
+  }
+  ep.n_per_unit = G;
+  const long long units = static_cast<long long>(num_m) * (ares ? (num_n + G - 1) / G : num_n);
+  int grid = units < sm_count() ? static_cast<int>(units) : sm_count();
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   if (grid < 1) grid = 1;
-  IM_CUDA_OK(launch_pdl(gemm_mxf8_kernel, dim3(grid), dim3(kMxThreads), kMxSmemBytes, reinterpret_cast<cudaStream_t>(stream),
-                        ta, tb, tc, tr, ep, M, N, K));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (ares)
+    IM_CUDA_OK(launch_pdl(gemm_mxf8_kernel<true>, dim3(grid), dim3(kMxThreads), kAresSmemBytes, st, ta, tb, tc, tr, ep, M, N, K));
+  else
+    IM_CUDA_OK(launch_pdl(gemm_mxf8_kernel<false>, dim3(grid), dim3(kMxThreads), kMxSmemBytes, st, ta, tb, tc, tr, ep, M, N, K));
   IM_LAUNCH_OK("gemm_mxf8_kernel");
-  return 0;
+  return ares ? G : 0;
 }

@@ -142,11 +142,11 @@ def linear_mx_ref(a: MxTensor, w: MxWeight, bias=None, residual=None, act=None, 
 
 # ----------------------------------------------------------------------------- kernel
 def linear_mx(a: MxTensor, w: MxWeight, bias=None, residual=None, act=None, out=None, out_mx: bool = False, m_dev=None,
-              max_ctas: int = 0):
+              max_ctas: int = 0, mode: int = 0):
     """``a @ w^T`` on ``tcgen05.mma.kind::mxf8f6f4.block_scale`` with fused bias / activation / residual.
 
     ``out_mx=False`` -> bf16 ``[M, N]``;  ``out_mx=True`` -> :class:`MxTensor` ``[M, N]`` quantised in the epilogue (the next
-    GEMM's A operand)."""
+    GEMM's A operand).  ``mode``: 0 auto, 1 operand-ring kernel, 2 A-resident kernel (K <= 768)."""
     m, k = a.q.shape
     n = w.q.shape[0]
     assert a.q.is_cuda and a.q.dtype == torch.uint8 and w.q.dtype == torch.uint8 and w.q.shape[1] == k and k % 128 == 0
@@ -174,7 +174,8 @@ def linear_mx(a: MxTensor, w: MxWeight, bias=None, residual=None, act=None, out=
                         ctypes.c_int(w.q.stride(0)), ctypes.c_int(ldc),
                         ctypes.c_int(residual.stride(0) if residual is not None else 0),
                         ctypes.c_int(ACT[act] if not isinstance(act, int) else act), ctypes.c_int(1 if out_mx else 0),
-                        _native.ptr(m_dev), ctypes.c_int(max_ctas), _native.stream_ptr())
-    _native.check(rc, "im_gemm_mxf8")
+                        _native.ptr(m_dev), ctypes.c_int(max_ctas), _native.stream_ptr(), ctypes.c_int(mode))
+    if rc < 0:
+        _native.check(rc, "im_gemm_mxf8")
     _native.count_launch()
     return out

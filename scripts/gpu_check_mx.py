@@ -18,12 +18,12 @@ def rand_e4m3(r, k, amp=1.0):
     return x.to(torch.float8_e4m3fn).view(torch.uint8)
 
 
-def run_case(name, M, N, K, ea, eb, **kw):
+def run_case(name, M, N, K, ea, eb, mode=0, **kw):
     aq, bq = rand_e4m3(M, K), rand_e4m3(N, K)
     a = MX.MxTensor(aq, MX.pack_sfa(ea))
     w = MX.MxWeight(bq, MX.pack_sfb(eb), eb)
     ref = MX.linear_mx_ref(a, w, **kw)
-    out = MX.linear_mx(a, w, **kw)
+    out = MX.linear_mx(a, w, mode=mode, **kw)
     torch.cuda.synchronize()
     err = (out.float() - ref).abs().max().item()
     mag = ref.abs().max().item()
@@ -69,6 +69,13 @@ for (m, n, k) in [(1000, 768, 768), (777, 2304, 768), (300, 3072, 768), (520, 76
     allok &= run_case("reranker shape", m, n, k, torch.randint(120, 130, (m, s), device=dev, generator=g).to(torch.uint8),
                       torch.randint(120, 130, (n, s), device=dev, generator=g).to(torch.uint8))
 
+# A-resident kernel (forced): many m blocks so CTAs run several units back to back (A slot reuse, barrier phases)
+for (m, n, k) in [(1000, 768, 768), (40000, 2304, 768), (33000, 768, 768), (5000, 3072, 768), (3000, 1152, 384), (700, 384, 256)]:
+    s_ = k // 32
+    allok &= run_case("A-resident kernel", m, n, k, torch.randint(120, 130, (m, s_), device=dev, generator=g).to(torch.uint8),
+                      torch.randint(120, 130, (n, s_), device=dev, generator=g).to(torch.uint8), mode=2,
+                      bias=torch.randn(n, device=dev), residual=torch.randn(m, n, device=dev).to(torch.bfloat16))
+
 # ---- real quantised data + MX output epilogue ----
 M, N, K = 640, 3072, 768
 x = torch.randn(M, K, device=dev)
@@ -101,15 +108,16 @@ print(f"[{'ok' if (y.float() - yref).abs().max().item() < 0.02 * yref.abs().max(
 # ---- throughput (burst, L2-cold between shapes; same M as the reranker's packed batch) ----
 from infomesh_b200.ops import gemm as G  # noqa: E402
 
-for (m, n, k, kw) in [(90112, 2304, 768, {}), (90112, 768, 768, {}), (90112, 3072, 768, dict(act="gelu")),
-                      (90112, 3072, 768, dict(act="gelu", out_mx=True)), (90112, 768, 3072, {})]:
+for (m, n, k, kw) in [(90112, 2304, 768, {}), (90112, 768, 768, {}), (90112, 3072, 768, dict(act="gelu", out_mx=True)),
+                      (90112, 768, 3072, {}), (11264, 2304, 768, {}), (11264, 3072, 768, dict(act="gelu", out_mx=True))]:
     a = MX.MxTensor(rand_e4m3(m, k), MX.pack_sfa(torch.randint(120, 130, (m, k // 32), device=dev).to(torch.uint8)))
     w = MX.quantize_weight(torch.randn(n, k, device=dev) * 0.05)
     bias = torch.randn(n, device=dev)
     xb = torch.randn(m, k, device=dev).to(torch.bfloat16)
     wb = torch.randn(n, k, device=dev).to(torch.bfloat16)
     outb = None
-    for label, fn in (("mxf8", lambda: MX.linear_mx(a, w, bias=bias, **kw)),
+    for label, fn in (("mxf8 ring", lambda: MX.linear_mx(a, w, bias=bias, mode=1, **kw)),
+                      ("mxf8 A-resident" if k <= 768 else "mxf8 auto", lambda: MX.linear_mx(a, w, bias=bias, mode=0, **kw)),
                       ("bf16", lambda: G.linear(xb, wb, bias, act=kw.get("act")))):
         for _ in range(3):
             fn()
