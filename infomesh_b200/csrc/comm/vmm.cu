@@ -101,31 +101,6 @@ static CUmemAllocationProp alloc_prop(int dev) {
 // ---------------------------------------------------------------------------------------------------------------
 // multimem kernels
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void multimem_st_v4(void* mc_addr, const uint4& v) {
-  asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
-               : "memory");
-}
-__device__ __forceinline__ void multimem_red_add_release(uint32_t* mc_addr, uint32_t v) {
-  asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(mc_addr), "r"(v) : "memory");
-}
-// 8 bf16 sums (fp32 accumulation inside the switch) of the same 16 bytes on every GPU of the multicast group
-__device__ __forceinline__ uint4 multimem_ld_reduce_bf16x8(const void* mc_addr) {
-  uint4 r;
-  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-               : "l"(mc_addr)
-               : "memory");
-  return r;
-}
-__device__ __forceinline__ float4 multimem_ld_reduce_f32x4(const void* mc_addr) {
-  float4 r;
-  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
-               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
-               : "l"(mc_addr)
-               : "memory");
-  return r;
-}
-
 __device__ __forceinline__ void mc_flag_wait(const uint32_t* flag, uint32_t target, const char* what) {
   uint32_t spins = 0;
   while (static_cast<int32_t>(ld_acquire_sys(flag) - target) < 0) {
@@ -179,43 +154,64 @@ mc_allgather_kernel(const uint8_t* __restrict__ src, size_t bytes, uint8_t* mc_b
 }
 
 // Reduce-scatter (all_reduce = 0) or all-reduce (= 1) of a symmetric bf16 / fp32 buffer through the switch.
-// Every rank has written its partial into the same symmetric offset (unicast) and then arrives on the barrier counters
-// (multimem.red): after the wait, rank r reduces elements [r * n / world, (r + 1) * n / world) with multimem.ld_reduce and
-// stores them to `out` (local, reduce-scatter) or back through multimem.st (all-reduce; a second barrier publishes them).
+// Every rank has written its partial into the same symmetric offset (unicast).  Barrier protocol (two counter bumps per
+// rank and use, so late-wave CTAs never deadlock against peers):
+//   entry: CTA 0 arrives once (the kernel is stream-ordered after the producer, so a running CTA means the partial is
+//          complete); every CTA waits for all ranks' entry arrivals, then reduces its slice with multimem.ld_reduce
+//          (4 independent 16-byte reductions in flight per thread);
+//   exit:  the last CTA out arrives and waits for every rank's exit arrival before the kernel may complete, so a fast
+//          rank cannot overwrite its partial (next use) while a slower peer is still pulling it through the switch.
 __global__ void __launch_bounds__(256)
 mc_reduce_kernel(const uint8_t* mc_in, uint8_t* mc_out, uint8_t* __restrict__ out, size_t n16_total, int is_f32, uint32_t* mc_flag,
                  const uint32_t* local_flag, uint32_t* state, int world, int rank, int all_reduce) {
   const uint32_t step = *reinterpret_cast<volatile uint32_t*>(state);
-  // ---- entry barrier: my partial (written by the previous kernel on this stream) is complete
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) multimem_red_add_release(mc_flag + rank, 1u);
-  // two counter bumps per CTA and use in BOTH modes: the exit barrier also keeps a fast rank from overwriting its partial
-  // (next use) while a slower peer is still pulling it through the switch
-  const uint32_t target = (step * 2u + 1u) * gridDim.x;
-  if (threadIdx.x < static_cast<unsigned>(world)) mc_flag_wait(local_flag + threadIdx.x, target, "mc_reduce(enter)");
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    __threadfence_system();
+    multimem_red_add_release(mc_flag + rank, 1u);
+  }
+  if (threadIdx.x < static_cast<unsigned>(world)) mc_flag_wait(local_flag + threadIdx.x, step * 2u + 1u, "mc_reduce(enter)");
   __syncthreads();
   const size_t per_rank = (n16_total + world - 1) / world;
   const size_t r_lo = min(n16_total, static_cast<size_t>(rank) * per_rank), r_hi = min(n16_total, r_lo + per_rank);
-  const size_t n_mine = r_hi - r_lo;
-  const size_t per_cta = (n_mine + gridDim.x - 1) / gridDim.x;
-  const size_t lo = r_lo + blockIdx.x * per_cta, hi = min(r_hi, lo + per_cta);
-  for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    uint4 v;
-    if (is_f32) {
-      const float4 f = multimem_ld_reduce_f32x4(mc_in + i * 16);
-      v = make_uint4(__float_as_uint(f.x), __float_as_uint(f.y), __float_as_uint(f.z), __float_as_uint(f.w));
-    } else {
-      v = multimem_ld_reduce_bf16x8(mc_in + i * 16);
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i0 = r_lo + static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i0 < r_hi; i0 += 4 * stride) {
+    uint4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const size_t i = i0 + j * stride;
+      if (i < r_hi) {
+        if (is_f32) {
+          const float4 f = multimem_ld_reduce_f32x4(mc_in + i * 16);
+          v[j] = make_uint4(__float_as_uint(f.x), __float_as_uint(f.y), __float_as_uint(f.z), __float_as_uint(f.w));
+        } else {
+          v[j] = multimem_ld_reduce_bf16x8(mc_in + i * 16);
+        }
+      }
     }
-    if (all_reduce) multimem_st_v4(mc_out + i * 16, v);
-    else reinterpret_cast<uint4*>(out)[i - r_lo] = v;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const size_t i = i0 + j * stride;
+      if (i < r_hi) {
+        if (all_reduce) multimem_st_v4(mc_out + i * 16, v[j]);
+        else reinterpret_cast<uint4*>(out)[i - r_lo] = v[j];
+      }
+    }
   }
   __threadfence_system();
   __syncthreads();
-  if (threadIdx.x == 0) multimem_red_add_release(mc_flag + rank, 1u);
-  if (threadIdx.x < static_cast<unsigned>(world)) mc_flag_wait(local_flag + threadIdx.x, (step * 2u + 2u) * gridDim.x, "mc_reduce(exit)");
-  mc_channel_advance(state);
+  __shared__ int is_last;
+  if (threadIdx.x == 0) is_last = (atomicAdd(state + 1, 1u) == gridDim.x - 1u) ? 1 : 0;
+  __syncthreads();
+  if (is_last) {
+    if (threadIdx.x == 0) multimem_red_add_release(mc_flag + rank, 1u);
+    if (threadIdx.x < static_cast<unsigned>(world)) mc_flag_wait(local_flag + threadIdx.x, step * 2u + 2u, "mc_reduce(exit)");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      state[1] = 0u;
+      state[0] = step + 1u;
+      __threadfence();
+    }
+  }
 }
 
 }  // namespace im
@@ -381,8 +377,8 @@ IM_API int im_mc_reduce(const void* mc_in, void* mc_out, void* out, size_t bytes
                         const uint32_t* local_flag, uint32_t* state, int world, int rank, int all_reduce, int ctas, void* stream) {
   if (bytes == 0 || (bytes % 16) != 0) return set_error("im_mc_reduce", "buffer size must be a non-zero multiple of 16 bytes");
   const size_t n16 = bytes / 16;
-  int grid = ctas > 0 ? ctas : static_cast<int>((n16 / world + 2047) / 2048);
-  grid = grid < 1 ? 1 : (grid > 64 ? 64 : grid);    // every CTA spins on peers: keep all of them co-resident
+  int grid = ctas > 0 ? ctas : static_cast<int>((n16 / world + 1023) / 1024);
+  grid = grid < 1 ? 1 : (grid > 2 * sm_count() ? 2 * sm_count() : grid);
   mc_reduce_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint8_t*>(mc_in), static_cast<uint8_t*>(mc_out), static_cast<uint8_t*>(out), n16, is_f32, mc_flag, local_flag,
       state, world, rank, all_reduce);

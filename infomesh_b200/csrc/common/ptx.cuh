@@ -562,6 +562,33 @@ __device__ __forceinline__ float gelu_tanh(float x) {
   return 0.5f * x * (1.0f + tanh_approx(k0 * fmaf(k1 * x * x, x, x)));
 }
 
+// ---- NVLS multicast (multimem.*) on addresses of a cuMulticast mapping: one instruction acts on every GPU's copy
+__device__ __forceinline__ void multimem_st_v4(void* mc_addr, const uint4& v) {
+  asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void multimem_red_add_release(uint32_t* mc_addr, uint32_t v) {
+  asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(mc_addr), "r"(v) : "memory");
+}
+// 8 bf16 sums (fp32 accumulation inside the switch) of the same 16 bytes on every GPU of the multicast group
+__device__ __forceinline__ uint4 multimem_ld_reduce_bf16x8(const void* mc_addr) {
+  uint4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(mc_addr)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ float4 multimem_ld_reduce_f32x4(const void* mc_addr) {
+  float4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(mc_addr)
+               : "memory");
+  return r;
+}
+
+
 // system-scope release / acquire on flags living in (possibly peer) global memory
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");

@@ -301,6 +301,152 @@ sum_ln_kernel(const __nv_bfloat16* in, size_t in_stride_p, int P,  // in / resid
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Tensor-parallel all-reduce fused with residual add + LayerNorm / RMSNorm (TP without sequence sharding: T5 decode
+// steps and prefill, K8/K9).  Every rank's row-parallel GEMM has written its partial product [rows, H] into the same
+// symmetric buffer; this kernel
+//   1. arrives on a cross-rank barrier (ONE arrival per rank and use: the kernel is stream-ordered after the GEMM, so
+//      any CTA running means the partial is complete; every CTA then waits for all ranks' arrivals),
+//   2. reads the row either through the NVLS multicast address with multimem.ld_reduce (the switch returns the sum over
+//      all GPUs: one load instead of `world`) or, without multicast, with `world` unicast peer loads,
+//   3. adds the residual, writes the new residual stream and its normalised copy.
+// Call sites alternate between two channels, which makes the entry barrier sufficient (see parallel/tp_t5.py).
+struct TpAllReduce {
+  const __nv_bfloat16* const* peer_in;   // [world] unicast pointers to every rank's partial (P2P mode), or null
+  const __nv_bfloat16* mc_in;            // multicast pointer (NVLS mode), or null
+  uint32_t* const* peer_flag;            // [world] -> each rank's counter array [world]   (P2P arrivals)
+  uint32_t* mc_flag;                     // multicast view of the counter array            (NVLS arrival)
+  const uint32_t* local_flag;            // this rank's counter array [world]
+  uint32_t* state;                       // {use, done}
+  int world, rank;
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(kRowsPerBlock * 32)
+tp_allreduce_norm_kernel(const TpAllReduce ar, const __nv_bfloat16* __restrict__ residual, const float* __restrict__ gamma,
+                         const float* __restrict__ beta, float eps, int rms_only, int n_rows, __nv_bfloat16* __restrict__ sum_out,
+                         __nv_bfloat16* __restrict__ norm_out) {
+  constexpr int H = VEC * 128;
+  const int row = blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  pdl_trigger();
+  pdl_wait();
+  const uint32_t use = *reinterpret_cast<volatile uint32_t*>(ar.state);
+  if (blockIdx.x == 0) {
+    __threadfence_system();
+    if (ar.mc_flag != nullptr) {
+      if (threadIdx.x == 0) multimem_red_add_release(ar.mc_flag + ar.rank, 1u);
+    } else if (threadIdx.x < static_cast<unsigned>(ar.world)) {
+      uint32_t* f = ar.peer_flag[threadIdx.x] + ar.rank;
+      asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(f) : "memory");
+    }
+  }
+  if (threadIdx.x < static_cast<unsigned>(ar.world)) {
+    uint32_t spins = 0;
+    while (static_cast<int32_t>(ld_acquire_sys(ar.local_flag + threadIdx.x) - (use + 1u)) < 0) {
+      if (++spins > IM_WAIT_LIMIT) {
+        printf("[infomesh_b200] tp_allreduce_norm barrier timeout (peer %d)\n", static_cast<int>(threadIdx.x));
+        __trap();
+      }
+      __nanosleep(20);
+    }
+  }
+  __syncthreads();
+  if (row < n_rows) {
+    float x[VEC][4];
+    const size_t off = static_cast<size_t>(row) * H;
+    if (ar.mc_in != nullptr) {
+      // one switch-side reduction per 16 bytes
+      if constexpr (VEC % 2 == 0) {
+#pragma unroll
+        for (int c = 0; c < VEC / 2; ++c) {
+          const uint4 u = multimem_ld_reduce_bf16x8(ar.mc_in + off + c * 256 + lane * 8);
+          unpack4(u.x, u.y, x[2 * c]);
+          unpack4(u.z, u.w, x[2 * c + 1]);
+        }
+      } else {
+        // 8-byte layout: two lanes share one 16-byte reduction
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          const uint4 u = multimem_ld_reduce_bf16x8(ar.mc_in + off + v * 128 + (lane >> 1) * 8);
+          if (lane & 1) unpack4(u.z, u.w, x[v]);
+          else unpack4(u.x, u.y, x[v]);
+        }
+      }
+    } else {
+      load_row<VEC, false>(ar.peer_in[ar.rank] + off, lane, x);
+      for (int pp = 1; pp < ar.world; ++pp) load_row<VEC, true>(ar.peer_in[(ar.rank + pp) % ar.world] + off, lane, x);
+    }
+    if (residual != nullptr) load_row<VEC, true>(residual + off, lane, x);
+    if (sum_out != nullptr) store_row<VEC>(sum_out + off, lane, x);
+    if (norm_out != nullptr) ln_finish<VEC>(x, gamma, beta, eps, norm_out + off, lane, rms_only != 0);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {   // last CTA out advances the channel
+    __threadfence();
+    if (atomicAdd(ar.state + 1, 1u) == gridDim.x - 1u) {
+      ar.state[1] = 0u;
+      ar.state[0] += 1u;
+      __threadfence();
+    }
+  }
+}
+
+// Cross-GPU arg-max for a vocab-parallel LM head (K9): every rank holds (max, arg) of its vocabulary shard per row;
+// each pushes its pairs into slot[rank] of every peer (8-byte packed stores), arrives, waits, and picks the winner
+// (largest value, ties -> smallest token id, so all ranks agree bit-for-bit).  One CTA; rows <= 1024.
+__global__ void __launch_bounds__(256)
+tp_argmax_exchange_kernel(const float* __restrict__ val, const int* __restrict__ idx, int n_rows, uint2* const* peer_slots,
+                          uint32_t* const* peer_flag, const uint32_t* local_flag, uint32_t* state, int world, int rank,
+                          int* __restrict__ out_idx, float* __restrict__ out_val) {
+  const uint32_t use = *reinterpret_cast<volatile uint32_t*>(state);
+  const size_t par = static_cast<size_t>(use & 1u) * world * n_rows;
+  for (int r = threadIdx.x; r < n_rows; r += blockDim.x) {
+    const uint2 pk = make_uint2(__float_as_uint(val[r]), static_cast<uint32_t>(idx[r]));
+    for (int pp = 0; pp < world; ++pp) {
+      const int p = (rank + pp) % world;
+      peer_slots[p][par + static_cast<size_t>(rank) * n_rows + r] = pk;
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < static_cast<unsigned>(world)) {
+    uint32_t* f = peer_flag[threadIdx.x] + rank;
+    asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(f) : "memory");
+    uint32_t spins = 0;
+    while (static_cast<int32_t>(ld_acquire_sys(local_flag + threadIdx.x) - (use + 1u)) < 0) {
+      if (++spins > IM_WAIT_LIMIT) {
+        printf("[infomesh_b200] tp_argmax_exchange timeout (peer %d)\n", static_cast<int>(threadIdx.x));
+        __trap();
+      }
+      __nanosleep(20);
+    }
+  }
+  __syncthreads();
+  const uint2* mine = peer_slots[rank] + par;
+  for (int r = threadIdx.x; r < n_rows; r += blockDim.x) {
+    float best = -CUDART_INF_F;
+    int arg = 0x7fffffff;
+    for (int p = 0; p < world; ++p) {
+      const volatile uint32_t* pk = reinterpret_cast<const volatile uint32_t*>(mine + static_cast<size_t>(p) * n_rows + r);
+      const float v = __uint_as_float(pk[0]);
+      const int a = static_cast<int>(pk[1]);
+      if (v > best || (v == best && a < arg)) {
+        best = v;
+        arg = a;
+      }
+    }
+    out_idx[r] = arg;
+    if (out_val != nullptr) out_val[r] = best;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    state[0] = use + 1u;
+  }
+}
+
 // sentence embedding: mode 0 = CLS token, 1 = mean over valid tokens; L2 normalised; one block per sequence
 __global__ void __launch_bounds__(256)
 pool_norm_kernel(const __nv_bfloat16* __restrict__ h, const int* __restrict__ lengths, int seq_len, int H, int mode,
@@ -599,6 +745,46 @@ IM_API int im_sum_ln_mx(const void* in, const void* residual, const float* gamma
                         int n_rows, int H, void* out, void* stream, const int* n_rows_dev, void* mx_q, int mx_ld, void* mx_sf) {
   return sum_ln_impl(in, 0, 1, residual, gamma, beta, eps, rms_only, n_rows, H, out, nullptr, nullptr, nullptr, 0, 0, nullptr,
                      nullptr, 0, 1, 0, stream, n_rows_dev, mx_q, mx_ld, mx_sf);
+}
+
+
+IM_API int im_tp_allreduce_norm(void* const* peer_in, const void* mc_in, uint32_t* const* peer_flag, uint32_t* mc_flag,
+                                const uint32_t* local_flag, uint32_t* state, int world, int rank, const void* residual,
+                                const float* gamma, const float* beta, float eps, int rms_only, int n_rows, int H, void* sum_out,
+                                void* norm_out, void* stream) {
+  using namespace im;
+  if (n_rows <= 0) return 0;
+  if (H % 128) return set_error("im_tp_allreduce_norm", "H must be a multiple of 128");
+  if (world < 1 || world > 32) return set_error("im_tp_allreduce_norm", "world must be 1..32");
+  if (peer_in == nullptr && mc_in == nullptr) return set_error("im_tp_allreduce_norm", "need peer pointers or a multicast pointer");
+  TpAllReduce ar;
+  ar.peer_in = reinterpret_cast<const __nv_bfloat16* const*>(peer_in);
+  ar.mc_in = reinterpret_cast<const __nv_bfloat16*>(mc_in);
+  ar.peer_flag = peer_flag;
+  ar.mc_flag = mc_flag;
+  ar.local_flag = local_flag;
+  ar.state = state;
+  ar.world = world;
+  ar.rank = rank;
+  const int grid = (n_rows + kRowsPerBlock - 1) / kRowsPerBlock;
+  auto s = reinterpret_cast<cudaStream_t>(stream);
+  IM_DISPATCH_VEC(H, IM_CUDA_OK(launch_pdl(tp_allreduce_norm_kernel<VEC>, dim3(grid), dim3(kRowsPerBlock * 32), 0, s, ar,
+                                           (const __nv_bfloat16*)residual, gamma, beta, eps, rms_only, n_rows,
+                                           (__nv_bfloat16*)sum_out, (__nv_bfloat16*)norm_out)));
+  IM_LAUNCH_OK("tp_allreduce_norm_kernel");
+  return 0;
+}
+
+IM_API int im_tp_argmax_exchange(const float* val, const int* idx, int n_rows, void* const* peer_slots, uint32_t* const* peer_flag,
+                                 const uint32_t* local_flag, uint32_t* state, int world, int rank, int* out_idx, float* out_val,
+                                 void* stream) {
+  using namespace im;
+  if (n_rows <= 0) return 0;
+  if (world < 1 || world > 32) return set_error("im_tp_argmax_exchange", "world must be 1..32");
+  tp_argmax_exchange_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      val, idx, n_rows, reinterpret_cast<uint2* const*>(peer_slots), peer_flag, local_flag, state, world, rank, out_idx, out_val);
+  IM_LAUNCH_OK("tp_argmax_exchange_kernel");
+  return 0;
 }
 
 IM_API int im_pool_norm(const void* h, const int* lengths, int batch, int seq_len, int H, int mode, int normalize,
