@@ -1,8 +1,16 @@
-"""Freshness tiers, the trigger-priority recrawl queue and conditional-request headers
-(reference infomesh/crawler/freshness.py:23-238)."""
+"""Document freshness tiers, the priority recrawl queue and conditional-GET headers.
+
+Contract (SURVEY §2.1 crawler/ "Freshness queue", reference infomesh/crawler/freshness.py): a page is hot for an hour,
+warm for a day, cold for a week, stale afterwards; recrawl requests are served strictly by trigger class
+(user > RSS > content change > peer announce > scheduled) and oldest-first inside a class, one entry per URL, bounded.
+
+Implementation: the age boundaries are a sorted table searched with ``bisect``; the queue is one time-ordered lane per
+trigger class plus a URL index -- a dequeue walks the lanes in class order, so there is no global heap to re-balance
+and discarding a URL is a dictionary delete (its lane entry becomes a tombstone that the next dequeue drops)."""
 from __future__ import annotations
 
-import heapq
+import bisect
+import itertools
 import time
 from dataclasses import dataclass, field
 from enum import StrEnum
@@ -23,13 +31,14 @@ class FreshnessTier(StrEnum):
     STALE = "stale"
 
 
+_AGE_LIMITS = (TIER_HOT_MAX, TIER_WARM_MAX, TIER_COLD_MAX)
+_TIER_BY_SLOT = (FreshnessTier.HOT, FreshnessTier.WARM, FreshnessTier.COLD, FreshnessTier.STALE)
+
+
 def classify_freshness(crawled_at: float, *, now: float | None = None) -> FreshnessTier:
-    age = (now or time.time()) - crawled_at
-    if age <= TIER_HOT_MAX:
-        return FreshnessTier.HOT
-    if age <= TIER_WARM_MAX:
-        return FreshnessTier.WARM
-    return FreshnessTier.COLD if age <= TIER_COLD_MAX else FreshnessTier.STALE
+    """Tier of a page crawled at ``crawled_at`` (each limit is inclusive: exactly one hour old is still hot)."""
+    age = (time.time() if now is None else now) - crawled_at
+    return _TIER_BY_SLOT[bisect.bisect_left(_AGE_LIMITS, age)]
 
 
 class RecrawlTrigger(StrEnum):
@@ -40,10 +49,12 @@ class RecrawlTrigger(StrEnum):
     PEER_ANNOUNCE = "peer_announce"
 
 
+# serving order of the trigger classes (lower = sooner)
 TRIGGER_PRIORITY: dict[RecrawlTrigger, int] = {
     RecrawlTrigger.USER_REQUEST: 0, RecrawlTrigger.RSS_UPDATE: 1, RecrawlTrigger.CONTENT_CHANGE: 2,
     RecrawlTrigger.PEER_ANNOUNCE: 3, RecrawlTrigger.SCHEDULED: 4,
 }
+_LOWEST_CLASS = max(TRIGGER_PRIORITY.values())
 
 
 @dataclass(frozen=True, order=True)
@@ -56,74 +67,89 @@ class PriorityRecrawlItem:
 
 
 class PriorityRecrawlQueue:
-    """Min-heap on (trigger priority, enqueue time) with URL de-duplication and lazy deletion."""
+    """Bounded, de-duplicated recrawl queue: trigger class first, then age of the request."""
 
     def __init__(self, *, max_size: int = 10000):
-        self._heap: list[PriorityRecrawlItem] = []
-        self._live: set[str] = set()
-        self._max = max_size
-        self._enq = self._deq = 0
+        self._limit = int(max_size)
+        self._lanes: list[list[tuple[float, int, PriorityRecrawlItem]]] = [[] for _ in range(_LOWEST_CLASS + 1)]
+        self._by_url: dict[str, PriorityRecrawlItem] = {}
+        self._ticket = itertools.count()          # tie-break for identical timestamps: arrival order
+        self._served = 0
+        self._accepted = 0
 
+    # ---- producers
     def enqueue(self, url: str, trigger: RecrawlTrigger, *, source_feed: str = "", now: float | None = None) -> bool:
-        if url in self._live:
+        if url in self._by_url:
             return False
-        if len(self._heap) >= self._max:
-            logger.warning("recrawl_queue_full", max_size=self._max, url=url)
+        if len(self._by_url) >= self._limit:
+            logger.warning("recrawl_queue_full", max_size=self._limit, url=url)
             return False
-        heapq.heappush(self._heap, PriorityRecrawlItem(TRIGGER_PRIORITY.get(trigger, 4), now or time.time(), url,
-                                                       trigger, source_feed))
-        self._live.add(url)
-        self._enq += 1
+        lane = TRIGGER_PRIORITY.get(trigger, _LOWEST_CLASS)
+        item = PriorityRecrawlItem(lane, time.time() if now is None else now, url, trigger, source_feed)
+        bisect.insort(self._lanes[lane], (item.enqueued_at, next(self._ticket), item))
+        self._by_url[url] = item
+        self._accepted += 1
         return True
 
-    def dequeue(self) -> PriorityRecrawlItem | None:
-        while self._heap:
-            item = heapq.heappop(self._heap)
-            if item.url in self._live:
-                self._live.discard(item.url)
-                self._deq += 1
-                return item
+    def discard(self, url: str) -> None:
+        self._by_url.pop(url, None)
+
+    def clear(self) -> None:
+        for lane in self._lanes:
+            lane.clear()
+        self._by_url.clear()
+
+    # ---- consumer
+    def _head(self):
+        """(lane, entry) of the next live item, dropping tombstones on the way; ``None`` when empty."""
+        for lane in self._lanes:
+            while lane:
+                entry = lane[0]
+                if self._by_url.get(entry[2].url) is entry[2]:
+                    return lane, entry
+                lane.pop(0)
         return None
 
-    def discard(self, url: str) -> None:
-        self._live.discard(url)
-
     def peek(self) -> PriorityRecrawlItem | None:
-        while self._heap and self._heap[0].url not in self._live:
-            heapq.heappop(self._heap)
-        return self._heap[0] if self._heap else None
+        head = self._head()
+        return head[1][2] if head else None
 
+    def dequeue(self) -> PriorityRecrawlItem | None:
+        head = self._head()
+        if head is None:
+            return None
+        lane, entry = head
+        lane.pop(0)
+        del self._by_url[entry[2].url]
+        self._served += 1
+        return entry[2]
+
+    # ---- counters
     @property
     def size(self) -> int:
-        return len(self._live)
+        return len(self._by_url)
 
     @property
     def total_enqueued(self) -> int:
-        return self._enq
+        return self._accepted
 
     @property
     def total_dequeued(self) -> int:
-        return self._deq
-
-    def clear(self) -> None:
-        self._heap.clear()
-        self._live.clear()
+        return self._served
 
 
 @dataclass(frozen=True)
 class ConditionalHeaders:
+    """Validators remembered from the last fetch, replayed as a conditional request."""
     etag: str | None = None
     last_modified: str | None = None
 
+    _REQUEST_NAME = {"etag": "If-None-Match", "last_modified": "If-Modified-Since"}
+
     def to_request_headers(self) -> dict[str, str]:
-        h: dict[str, str] = {}
-        if self.etag:
-            h["If-None-Match"] = self.etag
-        if self.last_modified:
-            h["If-Modified-Since"] = self.last_modified
-        return h
+        return {header: value for attr, header in self._REQUEST_NAME.items() if (value := getattr(self, attr))}
 
     @staticmethod
     def from_response_headers(headers: dict[str, str]) -> "ConditionalHeaders":
-        low = {k.lower(): v for k, v in dict(headers).items()}
-        return ConditionalHeaders(low.get("etag"), low.get("last-modified"))
+        folded = {str(k).lower(): v for k, v in dict(headers).items()}
+        return ConditionalHeaders(etag=folded.get("etag"), last_modified=folded.get("last-modified"))

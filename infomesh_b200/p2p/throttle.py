@@ -1,13 +1,21 @@
-"""Token-bucket bandwidth limits for P2P traffic (config ``network.upload_limit_mbps`` / ``download_limit_mbps``);
-one second of burst, oversized transfers are paid for in bucket-sized chunks
-(reference infomesh/p2p/throttle.py:43-169)."""
+"""Bandwidth limits for P2P traffic (``network.upload_limit_mbps`` / ``download_limit_mbps``; 0 = unlimited).
+
+Contract (reference infomesh/p2p/throttle.py): a long-run byte rate per direction with one second of burst; callers
+``await acquire_*(nbytes)`` before moving data and get back how long they were held.
+
+Implementation: a virtual-clock meter (GCRA) instead of a refilled token counter.  Each direction keeps one number, the
+time up to which its bandwidth is already spoken for.  A transfer of ``n`` bytes books ``n / rate`` seconds starting at
+that point (but no earlier than one burst-second in the past -- idle time beyond the burst is not banked), and the caller
+sleeps until its booking ends.  Booking is a handful of arithmetic steps with no ``await`` in between, so concurrent
+tasks of one event loop serialise naturally without a lock, and an oversized transfer simply books a long slot."""
 from __future__ import annotations
 
 import asyncio
 import time
 from dataclasses import dataclass
 
-_BYTES_PER_MBIT = 1_000_000 / 8
+BYTES_PER_MEGABIT = 125_000
+BURST_SECONDS = 1.0
 
 
 @dataclass
@@ -19,60 +27,56 @@ class BandwidthStats:
 
 
 class BandwidthBucket:
-    def __init__(self, rate_mbps: float):
-        self._rate = rate_mbps * _BYTES_PER_MBIT      # bytes / second
-        self._tokens = self._rate
-        self._stamp = time.monotonic()
-        self._lock = asyncio.Lock()
+    """One direction's meter (the name is kept from the token-bucket formulation it replaces)."""
+
+    def __init__(self, rate_mbps: float, burst_seconds: float = BURST_SECONDS):
+        self._bytes_per_sec = float(rate_mbps) * BYTES_PER_MEGABIT
+        self._burst = float(burst_seconds)
+        self._booked_until = float("-inf")          # virtual clock: bandwidth is reserved up to here
 
     @property
     def rate_bytes_per_sec(self) -> float:
-        return self._rate
+        return self._bytes_per_sec
 
-    def _refill(self) -> None:
-        now = time.monotonic()
-        self._tokens = min(self._rate, self._tokens + (now - self._stamp) * self._rate)
-        self._stamp = now
+    def reserve(self, nbytes: int, now: float | None = None) -> float:
+        """Book ``nbytes`` and return the delay (seconds from ``now``) after which the transfer conforms to the rate."""
+        if nbytes <= 0 or self._bytes_per_sec <= 0:
+            return 0.0
+        now = time.monotonic() if now is None else now
+        start = max(self._booked_until, now - self._burst)
+        self._booked_until = start + nbytes / self._bytes_per_sec
+        return max(0.0, self._booked_until - now)
 
     async def acquire(self, nbytes: int) -> float:
         """Returns the seconds spent waiting."""
-        if nbytes <= 0 or self._rate <= 0:
-            return 0.0
-        waited, left = 0.0, float(nbytes)
-        while left > 0:
-            chunk = min(left, self._rate)
-            async with self._lock:
-                self._refill()
-                while self._tokens < chunk:
-                    nap = (chunk - self._tokens) / self._rate
-                    await asyncio.sleep(nap)
-                    waited += nap
-                    self._refill()
-                self._tokens -= chunk
-            left -= chunk
-        return waited
+        delay = self.reserve(nbytes)
+        if delay > 0:
+            await asyncio.sleep(delay)
+        return delay
 
 
 class BandwidthThrottle:
-    """0 Mbps disables the limit for that direction."""
+    """Upload and download meters plus byte / wait counters."""
 
     def __init__(self, upload_mbps: float = 5.0, download_mbps: float = 10.0):
-        self._up = BandwidthBucket(upload_mbps) if upload_mbps > 0 else None
-        self._down = BandwidthBucket(download_mbps) if download_mbps > 0 else None
+        self._meters = {"upload": BandwidthBucket(upload_mbps) if upload_mbps > 0 else None,
+                        "download": BandwidthBucket(download_mbps) if download_mbps > 0 else None}
         self._stats = BandwidthStats()
 
     @property
     def stats(self) -> BandwidthStats:
         return self._stats
 
+    async def _pass(self, direction: str, nbytes: int) -> float:
+        setattr(self._stats, f"{direction}_bytes", getattr(self._stats, f"{direction}_bytes") + nbytes)
+        meter = self._meters[direction]
+        held = await meter.acquire(nbytes) if meter is not None else 0.0
+        if held > 0:
+            setattr(self._stats, f"{direction}_waits", getattr(self._stats, f"{direction}_waits") + 1)
+        return held
+
     async def acquire_upload(self, nbytes: int) -> float:
-        self._stats.upload_bytes += nbytes
-        w = await self._up.acquire(nbytes) if self._up else 0.0
-        self._stats.upload_waits += 1 if w > 0 else 0
-        return w
+        return await self._pass("upload", nbytes)
 
     async def acquire_download(self, nbytes: int) -> float:
-        self._stats.download_bytes += nbytes
-        w = await self._down.acquire(nbytes) if self._down else 0.0
-        self._stats.download_waits += 1 if w > 0 else 0
-        return w
+        return await self._pass("download", nbytes)

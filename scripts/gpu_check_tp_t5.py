@@ -3,6 +3,7 @@
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29512 scripts/gpu_check_tp_t5.py [t5-small|t5-base]
 """
+import os
 import sys
 
 import torch
@@ -39,7 +40,9 @@ def timeit(fn, iters=5):
 
 rows = []
 single = T5Model(cfg, device=dev, seed=7)
-for B in (1, 8, 64):
+NVLS = os.environ.get("TP_T5_NVLS", "1") == "1"
+GRAPH = os.environ.get("TP_T5_GRAPH", "1") == "1"
+for B in [int(x) for x in os.environ.get("TP_T5_BATCHES", "1,8,64").split(",")]:
     g = torch.Generator().manual_seed(B)
     ids = torch.randint(5, cfg.vocab_size, (B, S), generator=g, dtype=torch.int32).to(dev)
     lens = torch.randint(S // 2, S + 1, (B,), generator=g, dtype=torch.int32).to(dev)
@@ -47,11 +50,11 @@ for B in (1, 8, 64):
     want_tok = single.generate(ids, lens, max_new_tokens=T, check_every=10 ** 6)
     res = {}
     for comm in ("fused", "nccl"):
-        m = TPT5Model(cfg, B, S, seed=7, comm=comm)
+        m = TPT5Model(cfg, B, S, seed=7, comm=comm, prefer_nvls=NVLS)
         enc = m.encode(ids, lens).float()
         mask = (torch.arange(S, device=dev)[None] < lens[:, None])[..., None]
         err = ((enc - want_enc) * mask).abs().max().item()
-        tok = m.generate(ids, lens, max_new_tokens=T)
+        tok = m.generate(ids, lens, max_new_tokens=T, use_graph=GRAPH)
         agree = (tok == want_tok[:, :T]).float().mean().item()
         same = torch.tensor([int(tok.sum().item())], device=dev)
         lo, hi = same.clone(), same.clone()
@@ -61,7 +64,7 @@ for B in (1, 8, 64):
         good = err < 0.25 and agree > 0.85 and int(lo.item()) == int(hi.item())
         allok &= good
         t_enc = timeit(lambda: m.encode(ids, lens))
-        t_gen = timeit(lambda: m.generate(ids, lens, max_new_tokens=T), iters=3)
+        t_gen = timeit(lambda: m.generate(ids, lens, max_new_tokens=T, use_graph=GRAPH), iters=3)
         res[comm] = (t_enc, t_gen)
         if rank == 0:
             print(f"[{'ok' if good else 'FAIL'}] tp={world} B={B} {comm:5s} nvls={getattr(m, 'nvls', False)}: max|enc err| {err:.3f}, token agreement with 1 GPU "
