@@ -12,6 +12,8 @@
 // hamming_scan: every probe fingerprint against the whole fingerprint table (reference SimHashIndex.find_near,
 // infomesh/crawler/simhash.py:186-205 is a linear Python scan): 128-bit loads, __popcll, per-probe packed
 // atomicMin of (distance << 32 | index).
+#include <cuda_bf16.h>
+
 #include "../common/host.h"
 #include "../common/ptx.cuh"
 
@@ -137,8 +139,9 @@ constexpr int kScanProbes = 256;  // probes staged in smem per launch chunk
 __global__ void __launch_bounds__(256)
 hamming_scan_kernel(const unsigned long long* __restrict__ table, long long n_table, long long table_index_base,
                     const unsigned long long* __restrict__ probes, int n_probes, int threshold,
-                    unsigned long long* __restrict__ best) {
+                    unsigned long long* __restrict__ best, const long long* __restrict__ n_table_dev) {
   __shared__ unsigned long long sp[kScanProbes];
+  if (n_table_dev != nullptr) n_table = min(n_table, *n_table_dev);   // shard fill level kept on the device (no host sync per batch)
   const int p0 = blockIdx.y * kScanProbes;
   const int np = min(kScanProbes, n_probes - p0);
   for (int i = threadIdx.x; i < np; i += blockDim.x) sp[i] = probes[p0 + i];
@@ -170,6 +173,83 @@ hamming_scan_kernel(const unsigned long long* __restrict__ table, long long n_ta
   }
 }
 
+// Resolve one index-build batch without touching the host (K1, BASELINE config 5):
+//   keep[j] = no rank found an already-indexed near-duplicate of passage j   (min over the gathered per-rank scan results)
+//             AND no EARLIER passage i < j of this batch is within `threshold` bits (all pairs, smem-tiled popcounts).
+// all_fp: [n] fingerprints of the whole batch in global order; best_parts: [P][n] packed scan results (all-ones = none).
+__global__ void __launch_bounds__(256)
+dedup_resolve_kernel(const unsigned long long* __restrict__ all_fp, const unsigned long long* __restrict__ best_parts, int P, int n,
+                     int threshold, uint8_t* __restrict__ keep) {
+  __shared__ unsigned long long tile[256];
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned long long mine = j < n ? all_fp[j] : 0ull;
+  bool dup = false;
+  if (j < n)
+    for (int p = 0; p < P; ++p) dup |= best_parts[static_cast<size_t>(p) * n + j] != ~0ull;
+  const int j_max = min(n, (blockIdx.x + 1) * static_cast<int>(blockDim.x));   // only passages before this block's last row matter
+  for (int base = 0; base < j_max; base += 256) {
+    const int i = base + threadIdx.x;
+    tile[threadIdx.x] = i < n ? all_fp[i] : 0ull;
+    __syncthreads();
+    const int lim = min(256, j - base);          // i < j
+    for (int t = 0; t < lim; ++t) dup |= __popcll(mine ^ tile[t]) <= threshold;
+    __syncthreads();
+  }
+  if (j < n) keep[j] = dup ? 0 : 1;
+}
+
+// Append this rank's surviving passages to its shard: exclusive scan of keep[slice] (one block), rows written at the
+// device-side fill level, which is then advanced.  Rows that would overflow the shard are dropped and counted.
+__global__ void __launch_bounds__(1024)
+dedup_append_kernel(const uint8_t* __restrict__ keep, int bpr, const __nv_bfloat16* __restrict__ emb, int H,
+                    const unsigned long long* __restrict__ fp, long long first_id, __nv_bfloat16* __restrict__ vectors,
+                    unsigned long long* __restrict__ fingerprints, long long* __restrict__ doc_ids, long long* __restrict__ n_dev,
+                    long long capacity, long long* __restrict__ counters /* {seen, dups, overflow} */) {
+  __shared__ int warp_tot[32];
+  __shared__ int pos_of[8192];
+  __shared__ long long base_s;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  int run = 0;   // rows kept in earlier 1024-row chunks
+  for (int c0 = 0; c0 < bpr; c0 += 1024) {
+    const int r = c0 + tid;
+    const int k = (r < bpr && keep[r]) ? 1 : 0;
+    const uint32_t bal = __ballot_sync(0xffffffffu, k);
+    const int in_warp = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) warp_tot[wid] = __popc(bal);
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int w = 0; w < 32; ++w) {
+      if (w < wid) before += warp_tot[w];
+      total += warp_tot[w];
+    }
+    if (r < bpr) pos_of[r] = k ? run + before + in_warp : -1;
+    run += total;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    base_s = *n_dev;
+    const long long room = capacity - base_s;
+    const long long take = run < room ? run : (room > 0 ? room : 0);
+    *n_dev = base_s + take;
+    counters[0] += bpr;
+    counters[1] += bpr - run;
+    counters[2] += run - take;
+  }
+  __syncthreads();
+  const long long base = base_s;
+  for (int r = wid; r < bpr; r += 32) {
+    const int pos = pos_of[r];
+    if (pos < 0 || base + pos >= capacity) continue;
+    const uint4* src = reinterpret_cast<const uint4*>(emb + static_cast<size_t>(r) * H);
+    uint4* dst = reinterpret_cast<uint4*>(vectors + static_cast<size_t>(base + pos) * H);
+    for (int c = lane; c < H / 8; c += 32) dst[c] = src[c];
+    if (lane == 0) {
+      fingerprints[base + pos] = fp[r];
+      doc_ids[base + pos] = first_id + r;
+    }
+  }
+}
+
 }  // namespace im
 
 IM_API int im_simhash(const uint8_t* text, const long long* word_start, const long long* word_end,
@@ -182,9 +262,9 @@ IM_API int im_simhash(const uint8_t* text, const long long* word_start, const lo
   return 0;
 }
 
-IM_API int im_hamming_scan(const unsigned long long* table, long long n_table, long long table_index_base,
-                           const unsigned long long* probes, int n_probes, int threshold, unsigned long long* best,
-                           void* stream) {
+static int hamming_scan_impl(const unsigned long long* table, long long n_table, long long table_index_base,
+                             const unsigned long long* probes, int n_probes, int threshold, unsigned long long* best,
+                             void* stream, const long long* n_table_dev) {
   using namespace im;
   if (n_table <= 0 || n_probes <= 0) return 0;
   long long blocks = (n_table / 2 + 255) / 256;
@@ -193,7 +273,41 @@ IM_API int im_hamming_scan(const unsigned long long* table, long long n_table, l
   if (blocks < 1) blocks = 1;
   dim3 grid(static_cast<unsigned>(blocks), (n_probes + kScanProbes - 1) / kScanProbes);
   hamming_scan_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(table, n_table, table_index_base,
-                                                                                probes, n_probes, threshold, best);
+                                                                                probes, n_probes, threshold, best, n_table_dev);
   IM_LAUNCH_OK("hamming_scan_kernel");
+  return 0;
+}
+IM_API int im_hamming_scan(const unsigned long long* table, long long n_table, long long table_index_base,
+                           const unsigned long long* probes, int n_probes, int threshold, unsigned long long* best,
+                           void* stream) {
+  return hamming_scan_impl(table, n_table, table_index_base, probes, n_probes, threshold, best, stream, nullptr);
+}
+// Same, scanning only the first min(n_table, *n_table_dev) entries (the shard's fill level lives on the device).
+IM_API int im_hamming_scan_dev(const unsigned long long* table, long long n_table, long long table_index_base,
+                               const unsigned long long* probes, int n_probes, int threshold, unsigned long long* best,
+                               const long long* n_table_dev, void* stream) {
+  return hamming_scan_impl(table, n_table, table_index_base, probes, n_probes, threshold, best, stream, n_table_dev);
+}
+
+IM_API int im_dedup_resolve(const unsigned long long* all_fp, const unsigned long long* best_parts, int P, int n, int threshold,
+                            uint8_t* keep, void* stream) {
+  using namespace im;
+  if (n <= 0) return 0;
+  dedup_resolve_kernel<<<(n + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(all_fp, best_parts, P, n, threshold, keep);
+  IM_LAUNCH_OK("dedup_resolve_kernel");
+  return 0;
+}
+
+IM_API int im_dedup_append(const uint8_t* keep, int bpr, const void* emb, int H, const unsigned long long* fp, long long first_id,
+                           void* vectors, unsigned long long* fingerprints, long long* doc_ids, long long* n_dev, long long capacity,
+                           long long* counters, void* stream) {
+  using namespace im;
+  if (bpr <= 0) return 0;
+  if (bpr > 8192) return set_error("im_dedup_append", "at most 8192 passages per rank and batch");
+  if (H % 8) return set_error("im_dedup_append", "H must be a multiple of 8");
+  dedup_append_kernel<<<1, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      keep, bpr, reinterpret_cast<const __nv_bfloat16*>(emb), H, fp, first_id, reinterpret_cast<__nv_bfloat16*>(vectors), fingerprints,
+      doc_ids, n_dev, capacity, counters);
+  IM_LAUNCH_OK("dedup_append_kernel");
   return 0;
 }

@@ -139,7 +139,7 @@ def simhash_from_arrays(text, word_start, word_end, doc_word_off, width: int = S
     return out
 
 
-def hamming_scan(table, probes, threshold: int = HAMMING_THRESHOLD, index_base: int = 0, best=None):
+def hamming_scan(table, probes, threshold: int = HAMMING_THRESHOLD, index_base: int = 0, best=None, n_table_dev=None):
     """For every probe: ``(distance, index)`` of the nearest table entry within ``threshold`` (else (-1,-1)).
 
     ``table`` / ``probes``: int64 CUDA tensors holding uint64 bit patterns.  ``best`` may be passed to
@@ -152,12 +152,60 @@ def hamming_scan(table, probes, threshold: int = HAMMING_THRESHOLD, index_base: 
         best = torch.full((probes.numel(),), -1, device=probes.device, dtype=torch.int64)  # 0xFFFF... pattern
     if table.numel() and probes.numel():
         L = _native.require()
-        rc = L.im_hamming_scan(_native.ptr(table), ctypes.c_longlong(table.numel()), ctypes.c_longlong(index_base),
-                               _native.ptr(probes), ctypes.c_int(probes.numel()), ctypes.c_int(threshold),
-                               _native.ptr(best), _native.stream_ptr())
+        if n_table_dev is not None:     # fill level read on the device: the scan covers table[:min(len, *n_table_dev)]
+            rc = L.im_hamming_scan_dev(_native.ptr(table), ctypes.c_longlong(table.numel()), ctypes.c_longlong(index_base),
+                                       _native.ptr(probes), ctypes.c_int(probes.numel()), ctypes.c_int(threshold),
+                                       _native.ptr(best), _native.ptr(n_table_dev), _native.stream_ptr())
+        else:
+            rc = L.im_hamming_scan(_native.ptr(table), ctypes.c_longlong(table.numel()), ctypes.c_longlong(index_base),
+                                   _native.ptr(probes), ctypes.c_int(probes.numel()), ctypes.c_int(threshold),
+                                   _native.ptr(best), _native.stream_ptr())
         _native.check(rc, "im_hamming_scan")
         _native.count_launch()
     return best
+
+
+def dedup_resolve(all_fp, best_parts, threshold: int = HAMMING_THRESHOLD):
+    """keep-mask uint8 ``[n]`` of a batch: no rank reported an indexed near-duplicate (``best_parts`` ``[P, n]`` packed scan
+    results) and no earlier passage of the batch is within ``threshold`` bits.  One kernel, no host sync."""
+    import torch
+
+    n = all_fp.numel()
+    bp = best_parts.reshape(-1, n).contiguous()
+    keep = torch.empty((n,), device=all_fp.device, dtype=torch.uint8)
+    L = _native.require()
+    rc = L.im_dedup_resolve(_native.ptr(all_fp), _native.ptr(bp), ctypes.c_int(bp.shape[0]), ctypes.c_int(n), ctypes.c_int(threshold),
+                            _native.ptr(keep), _native.stream_ptr())
+    _native.check(rc, "im_dedup_resolve")
+    _native.count_launch()
+    return keep
+
+
+def dedup_resolve_ref(all_fp, best_parts, threshold: int = HAMMING_THRESHOLD):
+    """NumPy oracle of :func:`dedup_resolve`."""
+    fp = all_fp.cpu().numpy().astype(np.uint64)
+    bp = best_parts.reshape(-1, fp.size).cpu().numpy()
+    keep = np.ones(fp.size, dtype=np.uint8)
+    for j in range(fp.size):
+        if (bp[:, j] != -1).any():
+            keep[j] = 0
+            continue
+        x = fp[:j] ^ fp[j]
+        if j and min(bin(int(v)).count("1") for v in x) <= threshold:
+            keep[j] = 0
+    return keep
+
+
+def dedup_append(keep_slice, emb, fp, first_id: int, vectors, fingerprints, doc_ids, n_dev, counters):
+    """Append the kept rows of this rank's slice to its shard at the device-side fill level ``n_dev`` (int64 ``[1]``);
+    ``counters`` (int64 ``[3]``) accumulates seen / duplicates / overflow."""
+    L = _native.require()
+    bpr, H = emb.shape
+    rc = L.im_dedup_append(_native.ptr(keep_slice), ctypes.c_int(bpr), _native.ptr(emb), ctypes.c_int(H), _native.ptr(fp),
+                           ctypes.c_longlong(first_id), _native.ptr(vectors), _native.ptr(fingerprints), _native.ptr(doc_ids),
+                           _native.ptr(n_dev), ctypes.c_longlong(vectors.shape[0]), _native.ptr(counters), _native.stream_ptr())
+    _native.check(rc, "im_dedup_append")
+    _native.count_launch()
 
 
 def unpack_best(best):

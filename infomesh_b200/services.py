@@ -38,45 +38,81 @@ def index_document(page: ParsedPage, store: LocalStore, vector_store: Any | None
     return doc_id
 
 
+class _NetworkPublisher:
+    """Adapter over whatever can announce documents to the mesh: a running P2P node (preferred) or a bare
+    ``DistributedIndex``.  Resolves the callables once; every call is best-effort and reports keywords published."""
+
+    def __init__(self, p2p_node: Any | None, distributed_index: Any | None):
+        self._one = self._many = None
+        self._one_takes_kwargs = False
+        node_one = getattr(p2p_node, "publish_document_to_network", None)
+        if callable(node_one):
+            self._one = node_one
+        else:
+            index_one = getattr(distributed_index, "publish_document", None)
+            if callable(index_one):
+                self._one, self._one_takes_kwargs = index_one, True
+        for owner, name in ((p2p_node, "publish_documents_to_network"), (distributed_index, "publish_batch")):
+            fn = getattr(owner, name, None)
+            if callable(fn):
+                self._many = fn
+                break
+        self.available = p2p_node is not None or distributed_index is not None
+
+    @staticmethod
+    def _count(value: Any) -> int:
+        return value if isinstance(value, int) else 0
+
+    async def one(self, page: ParsedPage, doc_id: int) -> int:
+        if self._one is None:
+            return 0
+        if self._one_takes_kwargs:
+            return self._count(await self._one(doc_id=doc_id, url=page.url, title=page.title, text=page.text))
+        return self._count(await self._one(doc_id, page.url, page.title, page.text))
+
+    async def many(self, docs: list[Any]) -> int:
+        return self._count(await self._many(docs)) if self._many is not None else 0
+
+
 async def publish_document_to_network(page: ParsedPage, doc_id: int | None, *, p2p_node: Any | None = None,
                                       distributed_index: Any | None = None) -> int:
+    """Announce one freshly indexed page; duplicates (``doc_id is None``) are never announced.  Never raises."""
     if doc_id is None:
         return 0
     try:
-        fn = getattr(p2p_node, "publish_document_to_network", None)
-        if callable(fn):
-            n = await fn(doc_id, page.url, page.title, page.text)
-            return n if isinstance(n, int) else 0
-        fn = getattr(distributed_index, "publish_document", None)
-        if callable(fn):
-            n = await fn(doc_id=doc_id, url=page.url, title=page.title, text=page.text)
-            return n if isinstance(n, int) else 0
+        return await _NetworkPublisher(p2p_node, distributed_index).one(page, doc_id)
     except Exception as exc:  # noqa: BLE001
         logger.warning("distributed_publish_failed", url=page.url, error=str(exc))
-    return 0
+        return 0
+
+
+def _publish_windows(store: LocalStore, batch_size: int, limit: int | None):
+    """Yield ``(offset_after, docs)`` windows over the store until it is exhausted or ``limit`` documents were read."""
+    seen = 0
+    while limit is None or seen < limit:
+        want = batch_size if limit is None else min(batch_size, limit - seen)
+        docs = store.get_documents_for_publish(limit=want, offset=seen)
+        if not docs:
+            return
+        seen += len(docs)
+        yield seen, docs
 
 
 async def republish_local_index(store: LocalStore, *, p2p_node: Any | None = None, distributed_index: Any | None = None,
                                 batch_size: int = 250, limit: int | None = None) -> int:
-    if p2p_node is None and distributed_index is None:
+    """Walk the local index in windows of ``batch_size`` (clamped to 1..1000) and re-announce every document, e.g. after
+    a restart.  A failing window is logged and skipped.  Returns the keywords published."""
+    publisher = _NetworkPublisher(p2p_node, distributed_index)
+    if not publisher.available:
         return 0
-    batch_size = max(1, min(batch_size, 1000))
-    publish = getattr(p2p_node, "publish_documents_to_network", None) or getattr(distributed_index, "publish_batch", None)
-    offset = total = 0
-    while limit is None or offset < limit:
-        take = batch_size if limit is None else min(batch_size, limit - offset)
-        docs = store.get_documents_for_publish(limit=take, offset=offset)
-        if not docs:
-            break
-        offset += len(docs)
-        if callable(publish):
-            try:
-                n = await publish(docs)
-                total += n if isinstance(n, int) else 0
-            except Exception as exc:  # noqa: BLE001
-                logger.warning("distributed_republish_batch_failed", offset=offset, error=str(exc))
-    logger.info("distributed_index_republished", documents_scanned=offset, keywords_published=total)
-    return total
+    scanned = published = 0
+    for scanned, docs in _publish_windows(store, max(1, min(batch_size, 1000)), limit):
+        try:
+            published += await publisher.many(docs)
+        except Exception as exc:  # noqa: BLE001
+            logger.warning("distributed_republish_batch_failed", offset=scanned, error=str(exc))
+    logger.info("distributed_index_republished", documents_scanned=scanned, keywords_published=published)
+    return published
 
 
 @dataclass(frozen=True)
@@ -92,36 +128,58 @@ class FetchPageResult:
     error: str | None = None
 
 
+class _PageFetcher:
+    """cache -> (optionally) crawl -> classify, with the size cap and staleness rule in one place."""
+
+    _PAYWALL_STATUS = frozenset({"http_402", "http_403"})
+
+    def __init__(self, store: LocalStore, vector_store: Any | None, max_size_bytes: int, cache_ttl_seconds: int):
+        self.store, self.vector_store = store, vector_store
+        self.cap, self.ttl = max_size_bytes, cache_ttl_seconds
+
+    def failure(self, url: str, error: str | None, **flags: Any) -> FetchPageResult:
+        return FetchPageResult(False, url=url, error=error, **flags)
+
+    def from_cache(self, url: str) -> FetchPageResult:
+        try:
+            validate_url(url)
+        except SSRFError as exc:
+            return self.failure(url, f"blocked: {exc}")
+        doc = self.store.get_document_by_url(url)
+        if doc is None:
+            return self.failure(url, "not_cached")
+        age = time.time() - doc.crawled_at
+        return FetchPageResult(True, title=doc.title, url=doc.url, text=_truncate_to_bytes(doc.text, self.cap), is_cached=True,
+                               is_stale=age > self.ttl, crawled_at=doc.crawled_at)
+
+    async def from_network(self, url: str, worker: Any) -> FetchPageResult:
+        if worker is None:
+            return self.failure(url, "crawler_unavailable")
+        outcome = await worker.crawl_url(url)
+        page = outcome.page if outcome.success else None
+        if page:
+            index_document(page, self.store, self.vector_store, js_required=outcome.js_required)
+            return FetchPageResult(True, title=page.title, url=url, text=_truncate_to_bytes(page.text, self.cap),
+                                   is_paywall=is_paywall_content(page.text), crawled_at=time.time())
+        if outcome.error in self._PAYWALL_STATUS:
+            return self.failure(url, f"paywall:{outcome.error}", is_paywall=True)
+        return self.failure(url, outcome.error)
+
+
 def fetch_page(url: str, *, store: LocalStore, worker: Any = None, vector_store: Any | None = None,
                max_size_bytes: int = 102_400, cache_ttl_seconds: int = 604_800) -> FetchPageResult:
     """Cache-only lookup (sync).  ``error="not_cached"`` tells the caller to crawl."""
-    try:
-        validate_url(url)
-    except SSRFError as exc:
-        return FetchPageResult(False, url=url, error=f"blocked: {exc}")
-    doc = store.get_document_by_url(url)
-    if doc is None:
-        return FetchPageResult(False, url=url, error="not_cached")
-    return FetchPageResult(True, doc.title, doc.url, _truncate_to_bytes(doc.text, max_size_bytes), True,
-                           time.time() - doc.crawled_at > cache_ttl_seconds, crawled_at=doc.crawled_at)
+    return _PageFetcher(store, vector_store, max_size_bytes, cache_ttl_seconds).from_cache(url)
 
 
 async def fetch_page_async(url: str, *, store: LocalStore, worker: Any, vector_store: Any | None = None,
                            max_size_bytes: int = 102_400, cache_ttl_seconds: int = 604_800) -> FetchPageResult:
-    cached = fetch_page(url, store=store, worker=worker, vector_store=vector_store, max_size_bytes=max_size_bytes,
-                        cache_ttl_seconds=cache_ttl_seconds)
+    """Cached copy if there is one (even a stale one, flagged), else crawl + index + return; SSRF refusals are final."""
+    fetcher = _PageFetcher(store, vector_store, max_size_bytes, cache_ttl_seconds)
+    cached = fetcher.from_cache(url)
     if cached.success or (cached.error or "").startswith("blocked"):
         return cached
-    if worker is None:
-        return FetchPageResult(False, url=url, error="crawler_unavailable")
-    res = await worker.crawl_url(url)
-    if res.success and res.page:
-        index_document(res.page, store, vector_store, js_required=res.js_required)
-        return FetchPageResult(True, res.page.title, url, _truncate_to_bytes(res.page.text, max_size_bytes), False, False,
-                               is_paywall_content(res.page.text), time.time())
-    if res.error in ("http_402", "http_403"):
-        return FetchPageResult(False, url=url, error=f"paywall:{res.error}", is_paywall=True)
-    return FetchPageResult(False, url=url, error=res.error)
+    return await fetcher.from_network(url, worker)
 
 
 @dataclass(frozen=True)

@@ -542,3 +542,28 @@ def test_index_builder_dedups_within_and_across_batches():
         first += n
     st = ib.stats()
     assert st["indexed"] == len(kept_fp) and st["duplicates"] == st["seen"] - st["indexed"] and st["duplicates"] >= 4
+
+
+def test_dedup_resolve_and_device_fill_level():
+    """In-batch all-pairs dedup + min over ranks' scan results in one kernel, against the NumPy oracle; the Hamming scan
+    honours a device-side table length."""
+    from infomesh_b200.ops import dedup as DD
+
+    g = torch.Generator().manual_seed(5)
+    n = 700
+    fp = torch.randint(-2 ** 62, 2 ** 62, (n,), generator=g, dtype=torch.int64)
+    fp[100] = fp[7] ^ 0b101          # 2 bits away from an earlier passage -> dropped
+    fp[650] = fp[300]                # exact repeat
+    fp[5] = fp[600] ^ 1              # near a LATER passage: the later one is the duplicate
+    best = torch.full((3, n), -1, dtype=torch.int64)
+    best[1, 42] = (2 << 32) | 17     # rank 1 found passage 42 in its shard
+    fp_d, best_d = fp.to(DEV), best.to(DEV)
+    keep = DD.dedup_resolve(fp_d, best_d)
+    ref = DD.dedup_resolve_ref(fp_d, best_d)
+    assert keep.cpu().numpy().tolist() == ref.tolist()
+    assert keep[100] == 0 and keep[650] == 0 and keep[42] == 0 and keep[5] == 1 and keep[600] == 0 and int(keep.sum()) == n - 4
+    table = torch.randint(-2 ** 62, 2 ** 62, (5000,), generator=g, dtype=torch.int64).to(DEV)
+    probes = table[[10, 4000]].clone()
+    full = DD.unpack_best(DD.hamming_scan(table, probes))[1].tolist()
+    part = DD.unpack_best(DD.hamming_scan(table, probes, n_table_dev=torch.tensor([1000], device=DEV)))[1].tolist()
+    assert full == [10, 4000] and part == [10, -1]
