@@ -135,6 +135,9 @@ def main() -> int:
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU candidate exchange: fused peer-memory kernels or NCCL all-gathers (baseline)")
     ap.add_argument("--sustain-s", type=float, default=5.0, help="length of the sustained-throughput loop")
+    ap.add_argument("--passages", choices=["sharded", "replicated"], default="sharded",
+                    help="multi-GPU passage-token store: sharded = each rank holds its own documents, peers read them over "
+                         "NVLink through pointer tables; replicated = every rank holds all 10M passages (round-1 layout)")
     ap.add_argument("--latency-b1", action="store_true", help="also measure batch-1 p50 latency")
     ap.add_argument("--ref-docs", type=int, default=1_000_000,
                     help="reference arm: documents to index (its per-row INSERT+COMMIT build is time-boxed, see below)")
@@ -177,8 +180,27 @@ def main() -> int:
     n_local = max(0, min(per, n_global - base))
     scfg = SynthConfig(n_docs=n_local, n_docs_global=n_global, doc_base=base)
     t0 = time.time()
-    shard = SynthShard(scfg, device=dev, df_allreduce=(D.all_reduce_sum_ if world > 1 else None),
-                       passages="global" if world > 1 else "local")
+    # multi-GPU: every rank keeps only ITS documents' passage tokens, placed in a symmetric heap; the pair-assembly kernel
+    # reads a winning passage from the owning GPU's HBM through the peer pointer tables (P2P loads over NVLink)
+    pheap = ptabs = None
+    if world > 1 and args.impl == "fused" and args.passages == "sharded":
+        from infomesh_b200.parallel import symm
+
+        pheap = symm.SymmetricHeap(per * (scfg.passage_len + 1) * 4 + (4 << 20), ctx)
+        offs = []
+
+        def palloc(shape, dtype):
+            full = (per,) + tuple(shape[1:])          # symmetric: every rank reserves the same `per` rows
+            view, off = pheap.alloc(full, dtype)
+            offs.append(off)
+            return view[:shape[0]]
+
+        shard = SynthShard(scfg, device=dev, df_allreduce=D.all_reduce_sum_, passages="local", alloc=palloc)
+        ptabs = (pheap.peer_table(offs[0]), pheap.peer_table(offs[1]))
+        pheap.barrier()
+    else:
+        shard = SynthShard(scfg, device=dev, df_allreduce=(D.all_reduce_sum_ if world > 1 else None),
+                           passages="global" if world > 1 else "local")
     torch.cuda.synchronize()
     build_s = time.time() - t0
 
@@ -186,8 +208,9 @@ def main() -> int:
     hcfg = HybridConfig(nq=args.batch, pair_seq=args.pair_seq, rerank=not args.no_rerank, backend=args.impl,
                         use_graph=not args.no_graph, exchange=args.exchange, varlen=not args.no_varlen,
                         rerank_chunks=args.rerank_chunks, precision=precision, strict_graph=True)
-    dps = n_global if world > 1 else n_local
-    eng = HybridEngine(shard, hcfg, docs_per_shard=dps)
+    dps = per if ptabs is not None else (n_global if world > 1 else n_local)
+    ekw = dict(docs_per_shard=dps, passage_tables=ptabs, passage_len=scfg.passage_len) if ptabs is not None else dict(docs_per_shard=dps)
+    eng = HybridEngine(shard, hcfg, **ekw)
 
     # ---- query batches on pinned host memory (distinct per step so nothing is cached between iterations) ----
     n_batches = args.steps + args.warmup
@@ -339,7 +362,7 @@ def main() -> int:
         if hcfg.rerank:
             from dataclasses import replace as _replace
 
-            eng_r = HybridEngine(shard, _replace(hcfg, rerank=False), encoder=eng.encoder, docs_per_shard=dps)
+            eng_r = HybridEngine(shard, _replace(hcfg, rerank=False), encoder=eng.encoder, **ekw)
             r_ms, r_per = timed(dev_step(eng_r), W, K)
             r2_ms, r2_per = timed(e2e_step(eng_r), W, K)
             extras["retrieval_only"] = summary(r_ms, r_per, K, e2e_value=qps(r2_ms, K),
@@ -351,15 +374,14 @@ def main() -> int:
             from dataclasses import replace as _replace
 
             if hcfg.rerank and precision != "bf16":
-                eng_b = HybridEngine(shard, _replace(hcfg, precision="bf16"), encoder=eng.encoder, reranker=eng.reranker,
-                                     docs_per_shard=dps)
+                eng_b = HybridEngine(shard, _replace(hcfg, precision="bf16"), encoder=eng.encoder, reranker=eng.reranker, **ekw)
                 b_ms, b_per = timed(dev_step(eng_b), W, K)
                 extras["bf16_arm"] = summary(b_ms, b_per, K, note="same pipeline, cross-encoder GEMMs in bf16 (round-1 config), one batch in flight")
                 eng_b._graph = None
                 del eng_b
             try:
                 eng_t = HybridEngine(shard, _replace(hcfg, backend="torch", exchange="nccl", use_graph=False, precision="bf16"),
-                                     encoder=eng.encoder, reranker=eng.reranker, docs_per_shard=dps)
+                                     encoder=eng.encoder, reranker=eng.reranker, **ekw)
                 n_t = max(3, min(K, 5))
                 t_ms, t_per = timed(dev_step(eng_t), 3, n_t)
                 extras["torch_arm"] = summary(t_ms, t_per, n_t, timed_steps=n_t,
@@ -374,8 +396,7 @@ def main() -> int:
         if hcfg.rerank and hcfg.varlen and args.impl == "fused":
             from dataclasses import replace as _replace
 
-            eng_p = HybridEngine(shard, _replace(hcfg, varlen=False, precision="bf16"), encoder=eng.encoder, reranker=eng.reranker,
-                                 docs_per_shard=dps)
+            eng_p = HybridEngine(shard, _replace(hcfg, varlen=False, precision="bf16"), encoder=eng.encoder, reranker=eng.reranker, **ekw)
             pad_ms, pad_per = timed(dev_step(eng_p), W, K)
             extras["padded_cross_encoder"] = summary(pad_ms, pad_per, K,
                                                      note=f"bf16 cross-encoder on padded [{B * hcfg.n_rerank // world} x {args.pair_seq}] batches per rank, one batch in flight")
@@ -386,7 +407,7 @@ def main() -> int:
     if args.latency_b1:
         cfg1 = HybridConfig(nq=world, pair_seq=args.pair_seq, rerank=not args.no_rerank, backend=args.impl,
                             use_graph=not args.no_graph, exchange=args.exchange, precision=precision)
-        eng1 = HybridEngine(shard, cfg1, encoder=eng.encoder, reranker=eng.reranker, docs_per_shard=dps)
+        eng1 = HybridEngine(shard, cfg1, encoder=eng.encoder, reranker=eng.reranker, **ekw)
         b1 = [tuple(x[:world] for x in b) for b in dev_batches]
 
         def step_b1(i):
@@ -434,7 +455,10 @@ def main() -> int:
                 "index_docs": n_global, "dim": 384, "global_batch": B, "seq_len": args.pair_seq,
                 "query_tokens": hcfg.enc_seq, "candidates_per_query": hcfg.n_rerank, "top_k": hcfg.k_out,
                 "rerank": hcfg.rerank, "query_mix": args.query_mix,
-                "parallelism": f"doc-sharded index x{world} + data-parallel reranker x{world}",
+                "parallelism": f"doc-sharded index x{world} (dense vectors, postings"
+                               + (", passage tokens read from the owning GPU over NVLink" if ptabs is not None else
+                                  (", passages replicated" if world > 1 else ", passages"))
+                               + f") + data-parallel reranker x{world}",
                 "l2_policy": "inputs larger than L2: every step streams this rank's dense shard "
                              f"({shard.vectors.numel() * shard.vectors.element_size() / 1e9:.2f} GB/rank) plus the query terms' "
                              "postings, and uses a distinct query batch",
@@ -463,6 +487,9 @@ def main() -> int:
         print(json.dumps(result), flush=True)
     # graphs hold references to the NCCL communicator: drop them before tearing the group down
     eng._graph = None
+    if pheap is not None:
+        torch.cuda.synchronize()
+        pheap.close()
     D.shutdown()
     return 0
 

@@ -134,6 +134,59 @@ rerank_select_kernel(const float* __restrict__ logits, const int64_t* __restrict
   }
 }
 
+
+// K12 — six-signal rank fuse (reference infomesh/index/ranking.py:104-148,171-238): one warp per query, one candidate
+// per lane (<= 32).  score = w0 * bm25 / (bm25 + max_bm25_of_query) + w1 * max(0.05, 2^(-age / half_life)) + w2 * trust
+//                          + w3 * authority + w4 * title_match + w5 * url_path; candidates come out sorted by score
+// (ties keep retrieval order).  Per-document signals (crawl time, trust, authority) are gathered by document row;
+// the query-dependent bonuses are optional per-pair arrays.
+__global__ void __launch_bounds__(128)
+rank_fuse_kernel(const float* __restrict__ bm25, const int64_t* __restrict__ rows, int n_cand, int nq, int64_t row_base,
+                 const float* __restrict__ crawled_at, const float* __restrict__ trust, const float* __restrict__ authority,
+                 const float* __restrict__ title_match, const float* __restrict__ url_path, float now, float half_life,
+                 float min_fresh, float default_trust, const float* __restrict__ w, int k_out, float* __restrict__ out_scores,
+                 int64_t* __restrict__ out_rows, float* __restrict__ out_signals) {
+  const int q = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const uint32_t lane = threadIdx.x & 31;
+  if (q >= nq) return;
+  const bool has = static_cast<int>(lane) < n_cand;
+  const size_t at = static_cast<size_t>(q) * n_cand + lane;
+  const int64_t row = has ? rows[at] : -1;
+  const bool live = has && row >= 0;
+  const float raw = live ? bm25[at] : 0.f;
+  float top = raw;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) top = fmaxf(top, __shfl_xor_sync(0xffffffffu, top, o));
+  if (!(top > 0.f)) top = 1.f;
+  const int64_t local = row - row_base;
+  const float sb = raw > 0.f ? raw / (raw + top) : 0.f;
+  const float age = live && crawled_at != nullptr ? fmaxf(0.f, now - crawled_at[local]) : 0.f;
+  const float sf = fmaxf(min_fresh, exp2f(-age / half_life));
+  const float st = live && trust != nullptr ? trust[local] : default_trust;
+  const float sa = live && authority != nullptr ? authority[local] : 0.f;
+  const float stt = live && title_match != nullptr ? title_match[at] : 0.f;
+  const float su = live && url_path != nullptr ? url_path[at] : 0.f;
+  float s = w[0] * sb + w[1] * sf + w[2] * st + w[3] * sa + w[4] * stt + w[5] * su;
+  if (!live) s = -CUDART_INF_F;
+  int rank = 0;
+  for (int j = 0; j < 32; ++j) {
+    const float o = __shfl_sync(0xffffffffu, s, j);
+    rank += (o > s || (o == s && j < static_cast<int>(lane))) ? 1 : 0;
+  }
+  if (has && rank < k_out) {
+    out_scores[static_cast<size_t>(q) * k_out + rank] = s;
+    out_rows[static_cast<size_t>(q) * k_out + rank] = live ? row : -1;
+    if (out_signals != nullptr) {
+      float* o = out_signals + (static_cast<size_t>(q) * k_out + rank) * 6;
+      o[0] = sb; o[1] = sf; o[2] = st; o[3] = sa; o[4] = stt; o[5] = su;
+    }
+  }
+  for (int r = n_cand + lane; r < k_out; r += 32) {
+    out_scores[static_cast<size_t>(q) * k_out + r] = -CUDART_INF_F;
+    out_rows[static_cast<size_t>(q) * k_out + r] = -1;
+  }
+}
+
 }  // namespace im
 
 IM_API int im_rrf_fuse(const int64_t* ids_a, const int64_t* ids_b, int ka, int kb, int nq, float rrf_k, float wa,
@@ -168,5 +221,19 @@ IM_API int im_rerank_select(const float* logits, const int64_t* cand_ids, int n_
   rerank_select_kernel<<<(nq + 3) / 4, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(logits, cand_ids, n_cand, nq,
                                                                                         k_out, out_scores, out_ids);
   IM_LAUNCH_OK("rerank_select_kernel");
+  return 0;
+}
+
+IM_API int im_rank_fuse(const float* bm25, const int64_t* rows, int n_cand, int nq, long long row_base, const float* crawled_at,
+                        const float* trust, const float* authority, const float* title_match, const float* url_path, float now,
+                        float half_life, float min_fresh, float default_trust, const float* weights, int k_out, float* out_scores,
+                        int64_t* out_rows, float* out_signals, void* stream) {
+  using namespace im;
+  if (nq <= 0) return 0;
+  if (n_cand > 32 || k_out > 32) return set_error("im_rank_fuse", "at most 32 candidates per query");
+  rank_fuse_kernel<<<(nq + 3) / 4, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      bm25, rows, n_cand, nq, row_base, crawled_at, trust, authority, title_match, url_path, now, half_life, min_fresh, default_trust,
+      weights, k_out, out_scores, out_rows, out_signals);
+  IM_LAUNCH_OK("rank_fuse_kernel");
   return 0;
 }

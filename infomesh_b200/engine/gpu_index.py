@@ -6,7 +6,11 @@ store once and produces, on the GPU:
 
 * dense vectors  — encoder forward over ``title + text`` in batches (replaces ChromaDB/hnswlib, N2/N3);
 * BM25 postings  — C++ ``IndexBuilder`` tokenises on the host, CSR arrays are uploaded once (replaces FTS5 scoring, N1);
-* passage tokens — the leading ``passage_len`` reranker tokens of every document for pair assembly.
+* passage tokens — the leading ``passage_len`` reranker tokens of every document for pair assembly;
+* passage terms  — every document split into passages (paragraph / sentence rules of ``search.passage.split_passages``)
+  and each passage's BM25 term ids, so the best passage of every hit is chosen ON THE DEVICE by ``passage_score``
+  (K11: coverage + 0.1 x density, the reference's ``select_best_passage``, infomesh/search/passage.py:143-227) and only
+  its character span is cut out of the document on the host.
 
 Queries are answered in batches: ``search_many`` tokenises on the host, copies three small int tensors from pinned
 memory, replays the captured CUDA graph and maps the winning doc rows back to URLs / titles / snippets through SQLite.
@@ -115,6 +119,7 @@ class GpuSearchIndex:
         vec_chunks: list[torch.Tensor] = []
         pt_rows: list[list[int]] = []
         batch_text: list[str] = []
+        docs_text: list[str] = []
 
         def flush():
             if batch_text:
@@ -127,6 +132,7 @@ class GpuSearchIndex:
             builder.add_text(body)
             ids.append(int(doc.doc_id))
             pt_rows.append(self.rr_tok.encode_plain(body, self.passage_len))
+            docs_text.append(doc.text)
             batch_text.append(body[:2000])                   # the reference embeds the first 2000 chars (vector_store.py:156)
             if len(batch_text) >= self.embed_batch:
                 flush()
@@ -138,6 +144,8 @@ class GpuSearchIndex:
                 self.engine, self.builder = None, builder
             return 0
         csr = builder.export()
+        passages = _passage_arrays(builder, docs_text)          # after every term is registered
+        del docs_text
         vectors = torch.cat(vec_chunks).contiguous()
         ptok = torch.full((n, self.passage_len), self.rr_tok.sp.pad, dtype=torch.int32)
         plen = torch.zeros((n,), dtype=torch.int32)
@@ -146,7 +154,7 @@ class GpuSearchIndex:
                 ptok[i, :len(row)] = torch.tensor(row, dtype=torch.int32)
             plen[i] = max(len(row), 1)
         self._install(builder, csr, vectors, ptok.to(dev), plen.to(dev), torch.ones((n,), dtype=torch.uint8, device=dev),
-                      np.asarray(ids, dtype=np.int64))
+                      np.asarray(ids, dtype=np.int64), passages)
         shard = self.engine.shard
         self.built_at, self.build_seconds = time.time(), time.time() - t0
         logger.info("gpu_index_built", docs=n, seconds=round(self.build_seconds, 2), hbm_mb=round(shard.nbytes() / 2 ** 20, 1))
@@ -154,7 +162,8 @@ class GpuSearchIndex:
 
     # ------------------------------------------------------------------ persistence
     _FILES = ("vectors.bin", "csr_off.bin", "csr_doc.bin", "csr_tf.bin", "doc_len.bin", "df.bin", "passage_tok.bin",
-              "passage_len.bin", "doc_ids.bin", "alive.bin", "vocab.txt")
+              "passage_len.bin", "doc_ids.bin", "alive.bin", "vocab.txt", "pass_terms.bin", "pass_off.bin", "doc_pass_off.bin",
+              "pass_span.bin")
 
     def _model_tag(self) -> str:
         """Identifies the encoder whose vectors are stored: config + a checksum of its first projection matrix."""
@@ -179,7 +188,8 @@ class GpuSearchIndex:
         arrays = {"vectors.bin": sh.vectors.view(torch.int16).cpu().numpy(), "csr_off.bin": csr["off"], "csr_doc.bin": csr["doc"],
                   "csr_tf.bin": csr["tf"], "doc_len.bin": csr["doc_len"], "df.bin": csr["df"],
                   "passage_tok.bin": sh.passage_tok.cpu().numpy(), "passage_len.bin": sh.passage_len.cpu().numpy(),
-                  "doc_ids.bin": self.doc_ids, "alive.bin": sh.alive.cpu().numpy()}
+                  "doc_ids.bin": self.doc_ids, "alive.bin": sh.alive.cpu().numpy(), "pass_terms.bin": self._pass["terms"],
+                  "pass_off.bin": self._pass["off"], "doc_pass_off.bin": self._pass["doc_off"], "pass_span.bin": self._pass["span"]}
         files = {}
         for name, arr in arrays.items():
             arr = np.ascontiguousarray(arr)
@@ -223,6 +233,8 @@ class GpuSearchIndex:
         plen = torch.from_numpy(read("passage_len.bin", np.int32)).to(dev)
         alive = torch.from_numpy(read("alive.bin", np.uint8)).to(dev)
         doc_ids = read("doc_ids.bin", np.int64)
+        passages = {"terms": read("pass_terms.bin", np.int32), "off": read("pass_off.bin", np.int64),
+                    "doc_off": read("doc_pass_off.bin", np.int64), "span": read("pass_span.bin", np.int32).reshape(-1, 2)}
         builder = HostIndexBuilder()
         terms = (d / "vocab.txt").read_text(encoding="utf-8")
         if terms:
@@ -230,11 +242,11 @@ class GpuSearchIndex:
         if builder.vocab != man["vocab"]:
             raise ValueError("vocabulary does not round-trip")
         self.passage_len = man["passage_len"]
-        self._install(builder, csr, vectors, ptok, plen, alive, doc_ids)
+        self._install(builder, csr, vectors, ptok, plen, alive, doc_ids, passages)
         self.built_at, self.build_seconds = time.time(), time.time() - t0
         return n
 
-    def _install(self, builder, csr, vectors, ptok, plen, alive, doc_ids) -> None:
+    def _install(self, builder, csr, vectors, ptok, plen, alive, doc_ids, passages) -> None:
         """Adopt device structures (fresh build or loaded segments): the engine, row maps and pinned staging are built
         into locals and published together under the lock, so a concurrent search sees either the old or the new index."""
         dev = self.device
@@ -255,7 +267,9 @@ class GpuSearchIndex:
         staging = (mk(cfg.nq, cfg.enc_seq), mk(cfg.nq, fill=1), mk(cfg.nq, cfg.max_q_tokens, fill=self.rr_tok.sp.pad),
                    mk(cfg.nq, fill=1), mk(cfg.nq, cfg.max_terms, fill=-1), h_scores, h_ids)
         row_of = {int(x): i for i, x in enumerate(doc_ids)}
+        pass_dev = {k: torch.from_numpy(np.ascontiguousarray(passages[k])).to(dev) for k in ("terms", "off", "doc_off")}
         with self._lock:
+            self._pass, self._pass_dev = passages, pass_dev
             self._csr, self.engine, self.builder = csr, engine, builder
             self.doc_ids, self._row_of, self._pending = doc_ids, row_of, 0
             (self._h_enc, self._h_enc_len, self._h_qtok, self._h_qlen, self._h_terms, self._h_scores, self._h_ids) = staging
@@ -312,21 +326,42 @@ class GpuSearchIndex:
                     continue
                 self._stage(chunk)
                 self.engine.search_batch(self._h_enc, self._h_enc_len, self._h_qtok, self._h_qlen, self._h_terms, self._h_scores, self._h_ids)
+                # K11 on the device: best passage (coverage + 0.1 x density) of every returned (query, document) pair
+                best_pass = self._best_passages()
                 torch.cuda.current_stream(self.device).synchronize()
                 scores, rows = self._h_scores.numpy().copy(), self._h_ids.numpy().copy()
-                doc_ids = self.doc_ids
+                best_pass = best_pass.cpu().numpy().reshape(rows.shape)
+                doc_ids, spans, doc_off = self.doc_ids, self._pass["span"], self._pass["doc_off"]
             for i, q in enumerate(chunk):
                 hits = []
-                for s, r in zip(scores[i], rows[i]):
+                for j, (s, r) in enumerate(zip(scores[i], rows[i])):
                     if r < 0 or r >= doc_ids.size or len(hits) >= k:
                         continue
                     doc = self.store.get_document(int(doc_ids[r]))
                     if doc is None:
                         continue
-                    hits.append({"doc_id": doc.doc_id, "url": doc.url, "title": doc.title, "snippet": _snippet(doc.text, q),
-                                 "score": float(s), "crawled_at": doc.crawled_at})
+                    bp = int(best_pass[i, j])
+                    if bp >= 0 and doc_off[r] + bp < doc_off[r + 1]:
+                        a, b = spans[doc_off[r] + bp]
+                        snippet = doc.text[a:b][:300]
+                    else:
+                        snippet = _snippet(doc.text, q)
+                    hits.append({"doc_id": doc.doc_id, "url": doc.url, "title": doc.title, "snippet": snippet,
+                                 "score": float(s), "crawled_at": doc.crawled_at, "passage": bp})
                 out.append(hits)
         return out
+
+    def _best_passages(self) -> torch.Tensor:
+        """int32 ``[nq * k_out]``: index of the best passage inside each returned document (-1: none / no query terms)."""
+        from infomesh_b200.ops.bm25 import passage_score
+
+        eng = self.engine
+        nq, k_out = eng.out_ids.shape
+        pair_doc = eng.out_ids.reshape(-1).clamp(min=-1).to(torch.int32)
+        pair_query = torch.arange(nq, device=self.device, dtype=torch.int32).repeat_interleave(k_out)
+        pd = self._pass_dev
+        _s, best = passage_score(pd["terms"], pd["off"], pd["doc_off"], pair_doc, pair_query, eng.in_terms)
+        return best
 
     def search(self, query: str, k: int = 10) -> list[dict[str, object]]:
         return self.search_many([query], k)[0]
@@ -339,6 +374,35 @@ class GpuSearchIndex:
                 "encoder": getattr(self.encoder, "source", "random-init"),
                 "reranker": getattr(self.reranker, "source", "random-init") if self.reranker is not None else "off",
                 "cuda_graph": bool(self.engine and self.engine._graph is not None)}
+
+
+def _passage_arrays(builder: HostIndexBuilder, texts: list[str]) -> dict:
+    """Split every document into passages and tokenise them into BM25 term ids.
+
+    -> ``terms`` int32 (all passages back to back), ``off`` int64 ``[n_pass + 1]`` token offsets, ``doc_off`` int64
+    ``[n_docs + 1]`` first passage of each document, ``span`` int32 ``[n_pass, 2]`` character range of the passage in the
+    document text (what the host cuts out once the device has picked the passage)."""
+    from infomesh_b200.search.passage import split_passages
+
+    terms: list[np.ndarray] = []
+    off, doc_off, span = [0], [0], []
+    for text in texts:
+        cursor = 0
+        for p in split_passages(text):
+            head = p[:40]
+            at = text.find(head, cursor)
+            if at < 0:
+                at = cursor
+            end = min(len(text), at + len(p))
+            cursor = max(cursor, end - 1)
+            t = builder.tokenize(text[at:end])
+            t = t[t >= 0]
+            terms.append(t.astype(np.int32))
+            off.append(off[-1] + int(t.size))
+            span.append((at, end))
+        doc_off.append(len(span))
+    return {"terms": np.concatenate(terms) if terms else np.zeros(1, np.int32), "off": np.asarray(off, np.int64),
+            "doc_off": np.asarray(doc_off, np.int64), "span": np.asarray(span, np.int32).reshape(-1, 2)}
 
 
 def gpu_index_kwargs(gcfg) -> dict:

@@ -50,7 +50,7 @@ class HybridConfig:
 
 class HybridEngine:
     def __init__(self, shard, cfg: HybridConfig, encoder: BertModel | None = None, reranker: BertModel | None = None,
-                 passage_tables=None, docs_per_shard: int | None = None, seed: int = 0):
+                 passage_tables=None, docs_per_shard: int | None = None, seed: int = 0, passage_len: int | None = None):
         self.cfg = cfg
         self.ctx = D.ctx()
         self.shard = shard
@@ -63,14 +63,21 @@ class HybridEngine:
         self.nq_local = cfg.nq // w
         # passage-token tables: one (tok, len) pointer pair per shard.  Default: this rank's own shard holds the
         # tokens of every document it may need (replicated store); a symmetric heap supplies peer pointers.
+        # A (tok_ptrs, len_ptrs) pair of int64 device tensors is a ready-made PEER table: entry p points at rank p's
+        # passage shard in the symmetric heap, so pair assembly pulls the winning passages straight out of the owning
+        # GPU's HBM over NVLink (no replicated passage store).
         if passage_tables is None:
             passage_tables = ([shard.passage_tok], [shard.passage_len])
             docs_per_shard = shard.passage_tok.shape[0]
-        self.tok_ptrs = F.ptr_table(passage_tables[0], dev)
-        self.len_ptrs = F.ptr_table(passage_tables[1], dev)
+        if isinstance(passage_tables[0], torch.Tensor):
+            self.tok_ptrs, self.len_ptrs = passage_tables[0], passage_tables[1]
+            self.passage_len = int(passage_len if passage_len is not None else shard.passage_tok.shape[1])
+        else:
+            self.tok_ptrs = F.ptr_table(passage_tables[0], dev)
+            self.len_ptrs = F.ptr_table(passage_tables[1], dev)
+            self.passage_len = passage_tables[0][0].shape[1]
         self._keep = passage_tables
         self.docs_per_shard = int(docs_per_shard)
-        self.passage_len = passage_tables[0][0].shape[1]
         # static I/O buffers (CUDA-graph friendly)
         i32 = dict(device=dev, dtype=torch.int32)
         self.in_enc_ids = torch.zeros((cfg.nq, cfg.enc_seq), **i32)

@@ -108,9 +108,11 @@ class SynthShard:
     """Everything one rank holds for the synthetic benchmark."""
 
     def __init__(self, cfg: SynthConfig, device="cuda", df_allreduce=None, build_chunk: int = 2_000_000,
-                 passages: str = "local"):
-        """``passages``: "local" keeps passage tokens of this shard's documents only; "global" replicates the
-        token store of every document (used until peer-mapped tables are wired for the multi-GPU reranker)."""
+                 passages: str = "local", alloc=None):
+        """``passages``: "local" keeps passage tokens of this shard's documents only (multi-GPU engines read peers'
+        passages through pointer tables into the symmetric heap); "global" replicates the token store of every document
+        (round-1 layout, kept for A/B).  ``alloc(shape, dtype) -> tensor`` places the passage arrays (e.g. in a symmetric
+        heap so peers can map them); default ``torch.empty`` on ``device``."""
         self.cfg = cfg
         dev = torch.device(device)
         self.device = dev
@@ -122,8 +124,10 @@ class SynthShard:
         df = torch.zeros(cfg.vocab_terms, device=dev, dtype=torch.int64)
         n_pass = n if passages == "local" else cfg.n_docs_global
         self.passages_global = passages != "local"
-        self.passage_tok = torch.empty((n_pass, cfg.passage_len), device=dev, dtype=torch.int32)
-        self.passage_len = torch.full((n_pass,), min(cfg.passage_len, cfg.doc_len), device=dev, dtype=torch.int32)
+        mk = alloc or (lambda shape, dtype: torch.empty(shape, device=dev, dtype=dtype))
+        self.passage_tok = mk((n_pass, cfg.passage_len), torch.int32)
+        self.passage_len = mk((n_pass,), torch.int32)
+        self.passage_len.fill_(min(cfg.passage_len, cfg.doc_len))
         p_off = cfg.doc_base if self.passages_global else 0
         for a in range(0, n, build_chunk):
             b = min(n, a + build_chunk)

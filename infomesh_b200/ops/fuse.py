@@ -102,3 +102,30 @@ def rerank_select(logits, cand_ids, k_out, out_scores=None, out_ids=None):
     _native.check(rc, "im_rerank_select")
     _native.count_launch()
     return out_scores, out_ids
+
+
+def rank_fuse(bm25, rows, k_out, *, crawled_at=None, trust=None, authority=None, title_match=None, url_path=None, now=None,
+              weights=None, row_base: int = 0, want_signals: bool = False):
+    """K12 on the device: the reference's six-signal ``combined_score`` + sort (infomesh/index/ranking.py:104-148,171-238).
+
+    ``bm25`` fp32 / ``rows`` int64 ``[nq, n <= 32]`` are a retrieval list (rows < 0 = empty); ``crawled_at`` / ``trust`` /
+    ``authority`` are per-DOCUMENT fp32 arrays indexed by ``row - row_base`` (``crawled_at`` holds seconds relative to the
+    same epoch as ``now`` -- pass ages as ``now=0, crawled_at=-age`` to stay inside fp32); ``title_match`` / ``url_path`` are
+    optional per-pair bonuses.  Returns (scores ``[nq, k_out]``, rows ``[nq, k_out]``[, signals ``[nq, k_out, 6]``])."""
+    from infomesh_b200.index import ranking as R
+
+    nq, n = rows.shape
+    dev = rows.device
+    w = torch.tensor(R.weight_vector(weights), dtype=torch.float32, device=dev)
+    out_s = torch.empty((nq, k_out), device=dev, dtype=torch.float32)
+    out_r = torch.empty((nq, k_out), device=dev, dtype=torch.int64)
+    sig = torch.zeros((nq, k_out, 6), device=dev, dtype=torch.float32) if want_signals else None
+    L = _native.require()
+    rc = L.im_rank_fuse(_native.ptr(bm25), _native.ptr(rows), ctypes.c_int(n), ctypes.c_int(nq), ctypes.c_longlong(row_base),
+                        _native.ptr(crawled_at), _native.ptr(trust), _native.ptr(authority), _native.ptr(title_match),
+                        _native.ptr(url_path), ctypes.c_float(0.0 if now is None else now),
+                        ctypes.c_float(R.FRESHNESS_HALF_LIFE_SECONDS), ctypes.c_float(R.MIN_FRESHNESS), ctypes.c_float(R.DEFAULT_TRUST),
+                        _native.ptr(w), ctypes.c_int(k_out), _native.ptr(out_s), _native.ptr(out_r), _native.ptr(sig), _native.stream_ptr())
+    _native.check(rc, "im_rank_fuse")
+    _native.count_launch()
+    return (out_s, out_r, sig) if want_signals else (out_s, out_r)

@@ -194,17 +194,31 @@ class TPT5Model:
         assert B == self.B, "the arg-max exchange slots are sized for the configured batch"
         dev, T, hs, d = ids.device, max_new_tokens, self.hs, cfg.d_model
         alpha = d ** -0.5
-        lens = lengths if lengths is not None else torch.full((B,), S, dtype=torch.int32, device=dev)
+        # decode state (static buffers + the captured step graph) is cached per shape, like T5Model.generate
+        cache = self.__dict__.setdefault("_dec_states", {})
+        st = cache.get((B, S, T))
+        if st is None:
+            st = SimpleNamespace(
+                lens=torch.empty((B,), dtype=torch.int32, device=dev),
+                xk=[torch.empty((B * S, 2 * hs), device=dev, dtype=torch.bfloat16) for _ in self.dec],
+                kc=[torch.zeros((B, T, hs), device=dev, dtype=torch.bfloat16) for _ in self.dec],
+                vc=[torch.zeros((B, T, hs), device=dev, dtype=torch.bfloat16) for _ in self.dec],
+                bias=self._ref._dec_bias_table(T)[self._h[0]:self._h[1]].contiguous(),
+                tok=torch.empty((B,), dtype=torch.long, device=dev), done=torch.empty((B,), dtype=torch.bool, device=dev),
+                out=torch.empty((B, T), dtype=torch.int32, device=dev), step=torch.zeros((1,), dtype=torch.int32, device=dev),
+                col=torch.arange(T, device=dev, dtype=torch.int32)[None, :], pad=torch.full((B,), cfg.pad_id, dtype=torch.int32, device=dev),
+                nxt=torch.zeros((B,), dtype=torch.int32, device=dev), graph=None)
+            cache[(B, S, T)] = st
+        lens = st.lens
+        lens.copy_(lengths if lengths is not None else torch.full((B,), S, dtype=torch.int32, device=dev))
         enc = self.encode(ids, lens).view(B * S, d)
-        st = SimpleNamespace(
-            xk=[G.linear(enc, lay["wkv_x"]).view(B, S, 2 * hs) for lay in self.dec],
-            kc=[torch.zeros((B, T, hs), device=dev, dtype=torch.bfloat16) for _ in self.dec],
-            vc=[torch.zeros((B, T, hs), device=dev, dtype=torch.bfloat16) for _ in self.dec],
-            bias=self._ref._dec_bias_table(T)[self._h[0]:self._h[1]].contiguous(),
-            tok=torch.full((B,), cfg.decoder_start_id, dtype=torch.long, device=dev), done=torch.zeros((B,), dtype=torch.bool, device=dev),
-            out=torch.full((B, T), cfg.pad_id, dtype=torch.int32, device=dev), step=torch.zeros((1,), dtype=torch.int32, device=dev),
-            col=torch.arange(T, device=dev, dtype=torch.int32)[None, :], pad=torch.full((B,), cfg.pad_id, dtype=torch.int32, device=dev),
-            nxt=torch.zeros((B,), dtype=torch.int32, device=dev))
+        for li, lay in enumerate(self.dec):
+            G.linear(enc, lay["wkv_x"], out=st.xk[li])
+        xk = [x.view(B, S, 2 * hs) for x in st.xk]
+        st.tok.fill_(cfg.decoder_start_id)
+        st.done.fill_(False)
+        st.out.fill_(cfg.pad_id)
+        st.step.zero_()
 
         def one_step():
             x = self.full.emb[st.tok]
@@ -216,7 +230,7 @@ class TPT5Model:
                                          step_dev=st.step)
                 x, nx = self._row_parallel(ctx, lay["wo"], x, lay["ln_x"], B)
                 qx = G.linear(nx, lay["wq_x"])
-                cx = A.attention_decode(qx, st.xk[li][..., :hs], st.xk[li][..., hs:], self.heads_local, lens, scale=1.0)
+                cx = A.attention_decode(qx, xk[li][..., :hs], xk[li][..., hs:], self.heads_local, lens, scale=1.0)
                 x, n2 = self._row_parallel(cx, lay["wo_x"], x, lay["ln2"], B)
                 h = G.linear(n2, lay["wi"], act="relu")
                 nxt_g = self.dec[li + 1]["ln1"] if li + 1 < len(self.dec) else self.full.dec_final
@@ -238,18 +252,20 @@ class TPT5Model:
             st.tok.copy_(nxt)
             st.step.add_(1)
 
-        graph = None
         t0 = 0
-        if use_graph and T > 2 and self.comm == "fused":
+        if use_graph and T > 2 and self.comm == "fused" and st.graph is None:
+            # 18 all-reduce sites per step (even), so the two channels keep alternating across replays
             one_step()
             t0 = 1
             torch.cuda.synchronize()
             s = torch.cuda.Stream(device=dev)
             s.wait_stream(torch.cuda.current_stream())
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, stream=s):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=s):
                 one_step()
             torch.cuda.current_stream().wait_stream(s)
+            st.graph = g
+        graph = st.graph if (use_graph and self.comm == "fused") else None
         for _t in range(t0, T):
             if graph is not None:
                 graph.replay()

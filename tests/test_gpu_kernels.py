@@ -567,3 +567,31 @@ def test_dedup_resolve_and_device_fill_level():
     full = DD.unpack_best(DD.hamming_scan(table, probes))[1].tolist()
     part = DD.unpack_best(DD.hamming_scan(table, probes, n_table_dev=torch.tensor([1000], device=DEV)))[1].tolist()
     assert full == [10, 4000] and part == [10, -1]
+
+
+def test_rank_fuse_matches_cpu_ranking():
+    """K12: the device six-signal fuse orders candidates exactly like index.ranking.rank_results."""
+    from infomesh_b200.index import ranking as R
+    from infomesh_b200.ops.fuse import rank_fuse
+
+    g = torch.Generator().manual_seed(2)
+    nq, n, n_docs = 5, 20, 300
+    rows = torch.stack([torch.randperm(n_docs, generator=g)[:n] for _ in range(nq)]).to(torch.int64)
+    rows[1, 15:] = -1
+    bm = torch.rand(nq, n, generator=g) * 12
+    age = torch.rand(n_docs, generator=g) * 30 * 86400
+    trust = torch.rand(n_docs, generator=g)
+    auth = torch.rand(n_docs, generator=g)
+    title = torch.rand(nq, n, generator=g)
+    url = torch.rand(nq, n, generator=g)
+    s, r, sig = rank_fuse(bm.to(DEV), rows.to(DEV), 10, crawled_at=(-age).to(DEV), trust=trust.to(DEV), authority=auth.to(DEV),
+                          title_match=title.to(DEV), url_path=url.to(DEV), now=0.0, want_signals=True)
+    for q in range(nq):
+        cands = [R.RawCandidate(doc_id=int(rows[q, j]), url="", title="", snippet="", bm25_raw=float(bm[q, j]), crawled_at=-float(age[rows[q, j]]),
+                                trust=float(trust[rows[q, j]]), authority=float(auth[rows[q, j]]), title_match=float(title[q, j]),
+                                url_path=float(url[q, j])) for j in range(n) if rows[q, j] >= 0]
+        want = R.rank_results(cands, limit=10, now=1e-9)
+        got_ids = [int(x) for x in r[q].cpu().tolist() if x >= 0]
+        assert got_ids == [w.doc_id for w in want]
+        assert abs(float(s[q, 0]) - want[0].combined_score) < 2e-4
+        assert abs(float(sig[q, 0, 1]) - want[0].freshness_score) < 2e-4

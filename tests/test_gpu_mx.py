@@ -138,6 +138,9 @@ def test_gpu_index_untrained_models_keep_bm25_order_and_survive_concurrent_rebui
         reps = 1 + (i // len(topics)) % 5                      # different term frequencies -> distinct BM25 scores
         store.add_document(url=f"https://example.org/{i}", title=f"Doc {i}", text=(f"{t} " * reps + f"filler text number {i} " * 3),
                            raw_html_hash=f"r{i}", text_hash=f"t{i}", language="en")
+    two_part = ("An opening paragraph about unrelated gardening matters, tomatoes and watering schedules in dry summers. " * 2
+                + "\n\n" + "The zeppelin hangar in friedrichshafen stores the restored airship hull for visitors all year round. " * 2)
+    store.add_document(url="https://example.org/zep", title="Airships", text=two_part, raw_html_hash="rz", text_hash="tz", language="en")
     dev = torch.device("cuda:0")
     small = BertConfig(name="tiny-enc", vocab_size=30522, hidden=384, layers=2, heads=12, ffn=1536, max_pos=512)
     gi = GpuSearchIndex(store, device=dev, encoder=BertModel(small, device=dev, seed=1), query_batch=8)
@@ -147,6 +150,9 @@ def test_gpu_index_untrained_models_keep_bm25_order_and_survive_concurrent_rebui
     want = [r.doc_id for r in store.search("kademlia routing buckets", limit=5)]
     assert got == want, (got, want)
     assert gi.stats()["dense"] is False and gi.stats()["encoder"] == "random-init"
+    # K11: the snippet is the passage the DEVICE scored best (second paragraph), not the head of the document
+    zep = gi.search("zeppelin hangar friedrichshafen", k=3)[0]
+    assert zep["url"].endswith("/zep") and zep["passage"] == 1 and zep["snippet"].startswith("The zeppelin hangar") and "gardening" not in zep["snippet"]
 
     errors: list[Exception] = []
     stop = threading.Event()
@@ -173,5 +179,5 @@ def test_gpu_index_untrained_models_keep_bm25_order_and_survive_concurrent_rebui
     for t in ths:
         t.join()
     assert not errors, errors[:1]
-    assert gi.n_docs == 83
+    assert gi.n_docs == 84
     store.close()
