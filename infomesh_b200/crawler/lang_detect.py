@@ -50,6 +50,22 @@ _COMMON: dict[str, frozenset[str]] = {
                     "tại bởi vì nên nhưng hoặc nếu thì mà cũng rất".split()),
     "id": frozenset("yang dan di ke dari untuk pada dengan ini itu adalah tidak akan atau juga oleh sebagai dalam "
                     "ada saya kami kita anda dia mereka telah sudah bisa dapat harus karena".split()),
+    "pl": frozenset("w i z na nie się do że to jest o jak a po co ale od za przez dla ich tak był być może tylko "
+                    "który która które tym tego już jeszcze czy gdy bardzo także oraz przy nad pod".split()),
+    "sv": frozenset("och i att det som en på är av för med till den har de inte om ett han men var sig från vi så "
+                    "kan när hon skulle också eller efter vid nu än över under mycket hade här".split()),
+    "da": frozenset("og i at det en den til er som på de med han af for ikke der var mig sig men et har om vi min "
+                    "havde ham hun nu over da fra du ud sin dem os op man hans hvor eller hvad skal selv".split()),
+    "no": frozenset("og i det er på en som til for av at med har de ikke den om et var fra men han seg vi kan så "
+                    "ble hun eller også etter ved nå skal over under mye hadde være blir bare noe".split()),
+    "fi": frozenset("ja on ei se että oli hän mutta joka kun niin myös kuin tai ovat olla tämä sen mitä vain jos "
+                    "hänen sitä vielä nyt sekä jo minä sinä me te he ole kanssa mukaan jälkeen".split()),
+    "cs": frozenset("a v se na je že to s z do o i pro ale jako za po by od tak jsou jeho být nebo jsem když už "
+                    "který která které jen má byl byla bylo při pod nad před také velmi".split()),
+    "ro": frozenset("și de în la a că cu pe nu este un o se din pentru care mai al ce sau dar au fost prin după "
+                    "lui ale sunt fi această acest foarte când între până fără către deja".split()),
+    "hu": frozenset("a az és hogy nem is egy ez volt van de meg csak mint már még vagy ha ki mi el be fel le én te "
+                    "ő mert nagyon után között alatt által szerint amely amikor lehet kell".split()),
     "ru": frozenset("и в не на я что он с как а то все она так его но да ты к у же вы за бы по только ее мне "
                     "было вот от меня еще нет о из ему".split()),
     "uk": frozenset("і в не на я що він з як а то все вона так його але та ти до у ж ви за би по тільки її мені "

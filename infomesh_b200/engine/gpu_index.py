@@ -58,6 +58,7 @@ class _StoreShard:
     def __init__(self, device, vectors, bm25, passage_tok, passage_len, alive):
         self.device, self.vectors, self.bm25 = device, vectors, bm25
         self.passage_tok, self.passage_len, self.alive = passage_tok, passage_len, alive
+        self.neg_age = self.authority = None
         self.cfg = _ShardCfg(0)
 
     def nbytes(self) -> int:
@@ -68,7 +69,8 @@ class GpuSearchIndex:
     def __init__(self, store: Any, *, device: str | torch.device = "cuda:0", encoder: BertModel | None = None,
                  reranker: BertModel | None = None, rerank: bool = True, query_batch: int = 64, passage_len: int = 96,
                  enc_doc_tokens: int = 128, embed_batch: int = 256, use_graph: bool = True, seed: int = 0,
-                 encoder_path: str | None = None, reranker_path: str | None = None, allow_untrained: bool = False):
+                 encoder_path: str | None = None, reranker_path: str | None = None, allow_untrained: bool = False,
+                 rank_signals: bool = False, authority_fn=None):
         self.store = store
         self.device = torch.device(device)
         self.enc_tok = self.rr_tok = None
@@ -84,6 +86,8 @@ class GpuSearchIndex:
             self.rr_tok = load_tokenizer(reranker_path, reranker.cfg.vocab_size)
         self.encoder = encoder or BertModel(BGE_SMALL, device=self.device, seed=seed + 1)
         self.allow_untrained = bool(allow_untrained)
+        # BM25-only answers ordered like the reference's search_local (freshness / trust / authority fused on the device)
+        self.rank_signals, self.authority_fn = bool(rank_signals), authority_fn
         # ranking policy: a model without checkpoint weights may not influence results (see module docstring)
         self.use_dense = self.allow_untrained or bool(getattr(self.encoder, "pretrained", False))
         want_rr = rerank and (self.allow_untrained or bool(getattr(reranker, "pretrained", False)))
@@ -120,6 +124,8 @@ class GpuSearchIndex:
         pt_rows: list[list[int]] = []
         batch_text: list[str] = []
         docs_text: list[str] = []
+        crawled: list[float] = []
+        auth: list[float] = []
 
         def flush():
             if batch_text:
@@ -133,6 +139,12 @@ class GpuSearchIndex:
             ids.append(int(doc.doc_id))
             pt_rows.append(self.rr_tok.encode_plain(body, self.passage_len))
             docs_text.append(doc.text)
+            crawled.append(float(doc.crawled_at or 0.0))
+            if self.authority_fn is not None:
+                try:
+                    auth.append(float(self.authority_fn(doc.url)))
+                except Exception:  # noqa: BLE001
+                    auth.append(0.0)
             batch_text.append(body[:2000])                   # the reference embeds the first 2000 chars (vector_store.py:156)
             if len(batch_text) >= self.embed_batch:
                 flush()
@@ -145,6 +157,8 @@ class GpuSearchIndex:
             return 0
         csr = builder.export()
         passages = _passage_arrays(builder, docs_text)          # after every term is registered
+        passages["neg_age"] = np.asarray(crawled, dtype=np.float64) - t0      # seconds before this build (<= 0), fp32-safe
+        passages["authority"] = np.asarray(auth, dtype=np.float32) if auth else None
         del docs_text
         vectors = torch.cat(vec_chunks).contiguous()
         ptok = torch.full((n, self.passage_len), self.rr_tok.sp.pad, dtype=torch.int32)
@@ -251,8 +265,11 @@ class GpuSearchIndex:
         into locals and published together under the lock, so a concurrent search sees either the old or the new index."""
         dev = self.device
         shard = _StoreShard(dev, vectors, Bm25Index(csr, device=dev), ptok, plen, alive)
+        if passages.get("neg_age") is not None:
+            shard.neg_age = torch.from_numpy(np.minimum(passages["neg_age"], 0.0).astype(np.float32)).to(dev)
+            shard.authority = torch.from_numpy(passages["authority"]).to(dev) if passages.get("authority") is not None else None
         cfg = HybridConfig(nq=self.nq, rerank=self.rerank, k_fetch=20, n_rerank=20, k_out=10, pair_seq=min(128, 32 + self.passage_len),
-                           use_graph=self.use_graph, dense=self.use_dense)
+                           use_graph=self.use_graph, dense=self.use_dense, rank_signals=self.rank_signals)
         engine = HybridEngine(shard, cfg, encoder=self.encoder, reranker=self.reranker)
         pin = torch.cuda.is_available()
 
@@ -414,6 +431,7 @@ def gpu_index_kwargs(gcfg) -> dict:
         kw["encoder_path"] = gcfg.encoder_path
     if getattr(gcfg, "reranker_path", ""):
         kw["reranker_path"] = gcfg.reranker_path
+    kw["rank_signals"] = True            # serving surfaces answer like search_local: ranking signals fused on the device
     kw["allow_untrained"] = bool(getattr(gcfg, "allow_untrained_models", False))
     return kw
 

@@ -40,6 +40,7 @@ class HybridConfig:
     pair_seq: int = 128       # <s> q </s></s> passage </s>
     rerank: bool = True
     dense: bool = True        # False: BM25-only retrieval (serving with an encoder that has no checkpoint weights)
+    rank_signals: bool = False  # BM25-only mode: order candidates with the six-signal rank fuse (K12) instead of raw BM25
     backend: str = "fused"    # "fused" | "torch"
     use_graph: bool = True
     exchange: str = "p2p"     # multi-GPU list exchange: "p2p" (fused peer-memory kernels) | "nccl" (baseline collectives)
@@ -202,6 +203,10 @@ class HybridEngine:
         bm_s, bm_i = self._exchange(bm_s, bm_i, getattr(self, "ch_bm25", None))
         if cfg.dense:
             fu_s, fu_i = self._fuse(bm_i, de_i)
+        elif cfg.rank_signals and getattr(self.shard, "neg_age", None) is not None:
+            # reference search_local semantics: BM25 squash + freshness + trust + authority, fused and sorted on the device
+            fu_s, fu_i = F.rank_fuse(bm_s.contiguous(), bm_i.contiguous(), cfg.n_rerank, crawled_at=self.shard.neg_age,
+                                     authority=getattr(self.shard, "authority", None), now=0.0, row_base=self.shard.cfg.doc_base)
         else:       # BM25 order is the fused order
             fu_s, fu_i = bm_s[:, :cfg.n_rerank].contiguous(), bm_i[:, :cfg.n_rerank].contiguous()
         if cfg.rerank:
