@@ -120,7 +120,7 @@ def test_trust_score_component_weights():
     failed = TS.compute_trust_score(uptime_hours=0, contribution_raw=0, audit_total=4, audit_passed=0, summary_avg=0.0)
     assert passed - failed == pytest.approx(0.40)            # the audit component carries 40 %
     rated = TS.compute_trust_score(uptime_hours=0, contribution_raw=0, audit_total=4, audit_passed=0, summary_avg=1.0)
-    assert rated - failed == pytest.approx(0.20)             # summary quality 20 %
+    assert rated - failed == pytest.approx(0.10)             # summary quality 20 %, measured from its neutral 0.5 default
 
 
 # ------------------------------------------------------------------ governor ladder
