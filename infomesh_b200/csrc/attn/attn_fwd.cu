@@ -33,9 +33,19 @@ struct AttnParams {
   // MXFP8 output (single-chunk kernel, head_dim 64): the normalised O row is quantised in the epilogue -- each thread
   // owns exactly one 32-column block -- and written as e4m3 bytes + ue8m0 scales in the SFA chunk layout of the
   // out-projection GEMM (csrc/gemm/gemm_mxf8.cu), so no bf16 context tensor and no quantiser kernel exist on that path.
+  // Context parallelism (multi-chunk kernel): the key / value sequence is sharded over `cp_world` ranks (cp_sk_local keys
+  // per rank and sequence, a multiple of 128); this rank's queries sit at global positions [cp_q_pos0, +Sq).  The kernel
+  // pulls every rank's K / V tiles itself -- TMA loads through tensor maps over the peers' symmetric-heap buffers -- in
+  // an all-pairs schedule that starts with its own shard (NVSwitch makes every peer one hop, so no ring is needed).
+  int cp_world, cp_rank, cp_sk_local, cp_q_pos0;
   uint8_t* out_q;         // [rows, ld_outq] e4m3 bytes or null
   uint8_t* out_sf;        // [ceil(rows/128)][n_kb][512] scale chunks
   int ld_outq, n_kb;
+};
+
+struct CpMaps {           // K / V tensor maps of every context-parallel rank (unused slots repeat slot 0)
+  CUtensorMap k[8];
+  CUtensorMap v[8];
 };
 
 constexpr int kAttnThreads = 128;
@@ -61,10 +71,10 @@ __device__ __forceinline__ uint64_t desc_mn_major(uint32_t saddr) {
   return HD == 64 ? umma_desc_mn_sw128(saddr, 16) : umma_desc_mn_sw64(saddr, 16);
 }
 
-template <int HD>
+template <int HD, bool CP>
 __global__ void __launch_bounds__(kAttnThreads)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+                const __grid_constant__ CUtensorMap tmap_v, const AttnParams p, const __grid_constant__ CpMaps cpm) {
   using Cfg = AttnCfg<HD>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -89,11 +99,27 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   pdl_wait();  // (kv_lens / rel_bias are read right below: no prologue to overlap in this kernel, only launch latency)
   const int q_row0 = b * p.Sq + qb * kAttnBQ;  // first query row of this tile in the q buffer
   const int kv_row0 = b * p.Sk;
-  const int q_idx = qb * kAttnBQ + tid;        // position of this thread's query within its sequence
+  const int q_loc = qb * kAttnBQ + tid;         // query row inside this rank's [Sq] shard (store guard)
+  const int q_idx = q_loc + (CP ? p.cp_q_pos0 : 0);   // position of this thread's query within the whole sequence
+  const int cpr = CP ? p.cp_sk_local / kAttnBKV : 0;   // key chunks per context-parallel rank
 
   int kv_limit = p.kv_lens ? min(p.kv_lens[b], p.Sk) : p.Sk;
   if (p.causal) kv_limit = min(kv_limit, qb * kAttnBQ + kAttnBQ + p.causal_offset);
   const int num_chunks = max(0, (kv_limit + kAttnBKV - 1) / kAttnBKV);
+  // iteration c works on global key chunk cg(c): context parallelism rotates the order so every rank starts on its own
+  // shard and the ranks never all pull from the same peer at once
+  const int rot = (CP && num_chunks > 0) ? (p.cp_rank * cpr) % num_chunks : 0;
+  auto chunk_of = [&](int c) { return CP ? (c + rot) % num_chunks : c; };
+  auto load_k = [&](int c) {
+    const int cg = chunk_of(c);
+    if constexpr (CP) tma_load_2d(sK, &cpm.k[cg / cpr], k_bar, head * HD, b * p.cp_sk_local + (cg % cpr) * kAttnBKV);
+    else tma_load_2d(sK, &tmap_k, k_bar, head * HD, kv_row0 + cg * kAttnBKV);
+  };
+  auto load_v = [&](int c) {
+    const int cg = chunk_of(c);
+    if constexpr (CP) tma_load_2d(sV, &cpm.v[cg / cpr], v_bar, head * HD, b * p.cp_sk_local + (cg % cpr) * kAttnBKV);
+    else tma_load_2d(sV, &tmap_v, v_bar, head * HD, kv_row0 + cg * kAttnBKV);
+  };
 
   if (tid == 0) {
     tma_prefetch_desc(&tmap_q);
@@ -111,7 +137,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     tmem_relinquish();
   }
   if (p.rel_bias != nullptr) {
-    const int nb = p.Sq + p.Sk - 1;
+    const int nb = (CP ? p.Sk : p.Sq) + p.Sk - 1;
     for (int i = tid; i < nb; i += kAttnThreads) s_bias[i] = p.rel_bias[static_cast<size_t>(head) * nb + i];
   }
   tc_fence_before();
@@ -126,9 +152,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     mbar_expect_tx(q_bar, Cfg::kTileBytes);
     tma_load_2d(sQ, &tmap_q, q_bar, head * HD, q_row0);
     mbar_expect_tx(k_bar, Cfg::kTileBytes);
-    tma_load_2d(sK, &tmap_k, k_bar, head * HD, kv_row0);
+    load_k(0);
     mbar_expect_tx(v_bar, Cfg::kTileBytes);
-    tma_load_2d(sV, &tmap_v, v_bar, head * HD, kv_row0);
+    load_v(0);
   }
 
   float o_acc[HD];
@@ -156,15 +182,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     tc_fence_after();
     if (tid == 0 && c + 1 < num_chunks) {  // K buffer is free: prefetch the next chunk under the softmax
       mbar_expect_tx(k_bar, Cfg::kTileBytes);
-      tma_load_2d(sK, &tmap_k, k_bar, head * HD, kv_row0 + (c + 1) * kAttnBKV);
+      load_k(c + 1);
     }
     __syncwarp();
 
     // ---------------- softmax over this thread's row ----------------
-    const int key0 = c * kAttnBKV;
+    const int key0 = chunk_of(c) * kAttnBKV;
     int vis_end = kv_len;  // keys [0, vis_end) visible
     if (p.causal) vis_end = min(vis_end, q_idx + p.causal_offset + 1);
-    const float* bias_row = p.rel_bias ? s_bias + (p.Sq - 1 - min(q_idx, p.Sq - 1)) : nullptr;  // index by key j
+    // bias table index = (j - i) + (S_q_total - 1); with context parallelism the table spans the WHOLE sequence (Sk == S)
+    const int sq_tot = CP ? p.Sk : p.Sq;
+    const float* bias_row = p.rel_bias ? s_bias + (sq_tot - 1 - min(q_idx, sq_tot - 1)) : nullptr;  // index by key j
     float m_c = kNegBig;
 #pragma unroll 1
     for (int cc = 0; cc < kAttnBKV; cc += 32) {
@@ -236,7 +264,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     tc_fence_after();
     if (tid == 0 && c + 1 < num_chunks) {  // V buffer is free
       mbar_expect_tx(v_bar, Cfg::kTileBytes);
-      tma_load_2d(sV, &tmap_v, v_bar, head * HD, kv_row0 + (c + 1) * kAttnBKV);
+      load_v(c + 1);
     }
     __syncwarp();
 
@@ -259,7 +287,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   }
 
   // ---------------- normalise + store ----------------
-  if (q_idx < p.Sq) {
+  if (q_loc < p.Sq) {
     const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
     __nv_bfloat16* orow = p.out + static_cast<size_t>(q_row0 + tid) * p.ldo + head * HD;
 #pragma unroll
@@ -704,6 +732,10 @@ static int attn_fwd_impl(const void* q, const void* k, const void* v, void* out,
   p.rel_bias = rel_bias_log2;
   p.alias_p = (head_dim == 64 && Sk <= kAttnBKV) ? 1 : 0;
   p.cu_seqlens = cu_seqlens;
+  p.cp_world = 1;
+  p.cp_rank = p.cp_sk_local = p.cp_q_pos0 = 0;
+  CpMaps no_cp;
+  for (int i = 0; i < 8; ++i) no_cp.k[i] = no_cp.v[i] = tk;
   p.out_q = reinterpret_cast<uint8_t*>(out_q);
   p.out_sf = reinterpret_cast<uint8_t*>(out_sf);
   p.ld_outq = ld_outq;
@@ -739,12 +771,12 @@ static int attn_fwd_impl(const void* q, const void* k, const void* v, void* out,
     }
   } else if (head_dim == 64) {
     const int smem = 3 * AttnCfg<64>::kTileBytes + (p.alias_p ? 0 : AttnCfg<64>::kPBytes) + 1024 + 64 + bias_bytes;
-    IM_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    IM_CUDA_OK(launch_pdl(attn_fwd_kernel<64>, grid, dim3(kAttnThreads), smem, s, tq, tk, tv, p));
+    IM_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    IM_CUDA_OK(launch_pdl(attn_fwd_kernel<64, false>, grid, dim3(kAttnThreads), smem, s, tq, tk, tv, p, no_cp));
   } else {
     const int smem = 3 * AttnCfg<32>::kTileBytes + AttnCfg<32>::kPBytes + 1024 + 64 + bias_bytes;
-    IM_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    IM_CUDA_OK(launch_pdl(attn_fwd_kernel<32>, grid, dim3(kAttnThreads), smem, s, tq, tk, tv, p));
+    IM_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    IM_CUDA_OK(launch_pdl(attn_fwd_kernel<32, false>, grid, dim3(kAttnThreads), smem, s, tq, tk, tv, p, no_cp));
   }
   IM_LAUNCH_OK("attn_fwd_kernel");
   return 0;
@@ -763,6 +795,66 @@ IM_API int im_attn_fwd_mx(const void* q, const void* k, const void* v, void* out
                           void* stream, const int* cu_seqlens) {
   return attn_fwd_impl(q, k, v, nullptr, B, n_heads, head_dim, Sq, Sk, ldq, ldk, ldv, 8, kv_lens, 0, 0, scale, nullptr, stream,
                        cu_seqlens, out_q, ld_outq, out_sf, n_kb);
+}
+
+// Context-parallel attention: this rank's queries q [B * Sq_local, ldq] against the keys / values of ALL ranks.  k_ptrs /
+// v_ptrs: host arrays of `world` device pointers to every rank's K / V buffer ([B * sk_local, ldk], peer-mapped through
+// the symmetric heap).  The kernel pulls the tiles itself (TMA over NVLink); the caller only has to make sure every
+// rank's K / V are complete (one heap barrier after the QKV projection).  kv_lens are GLOBAL key counts per sequence;
+// rel_bias_log2 is the [heads, 2 * S_total - 1] table of the whole sequence.
+IM_API int im_attn_fwd_cp(const void* q, const void* const* k_ptrs, const void* const* v_ptrs, void* out, int B, int n_heads,
+                          int head_dim, int sq_local, int sk_local, int world, int rank, int ldq, int ldk, int ldv, int ldo,
+                          const int* kv_lens, float scale, const float* rel_bias_log2, void* stream) {
+  using namespace im;
+  if (B <= 0 || sq_local <= 0 || sk_local <= 0) return 0;
+  if (world < 1 || world > 8) return set_error("im_attn_fwd_cp", "context-parallel world must be 1..8");
+  if (sk_local % kAttnBKV) return set_error("im_attn_fwd_cp", "keys per rank must be a multiple of 128");
+  if (head_dim != 64 && head_dim != 32) return set_error("im_attn_fwd_cp", "head_dim must be 32 or 64");
+  if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 8)) return set_error("im_attn_fwd_cp", "row pitches must be multiples of 8");
+  const TmapSwizzle sw = head_dim == 64 ? TMAP_SW_128 : TMAP_SW_64;
+  const uint64_t cols = static_cast<uint64_t>(n_heads) * head_dim;
+  CUtensorMap tq;
+  if (get_tmap_2d(&tq, q, static_cast<uint64_t>(B) * sq_local, cols, static_cast<uint64_t>(ldq) * 2, kAttnBQ, head_dim, 2, sw)) return -1;
+  CpMaps cpm;
+  for (int r = 0; r < 8; ++r) {
+    const int src = r < world ? r : 0;
+    if (get_tmap_2d(&cpm.k[r], k_ptrs[src], static_cast<uint64_t>(B) * sk_local, cols, static_cast<uint64_t>(ldk) * 2, kAttnBKV, head_dim, 2, sw)) return -1;
+    if (get_tmap_2d(&cpm.v[r], v_ptrs[src], static_cast<uint64_t>(B) * sk_local, cols, static_cast<uint64_t>(ldv) * 2, kAttnBKV, head_dim, 2, sw)) return -1;
+  }
+  const int sk_total = sk_local * world;
+  AttnParams p;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.ldo = ldo;
+  p.Sq = sq_local;
+  p.Sk = sk_total;
+  p.kv_lens = kv_lens;
+  p.causal = 0;
+  p.causal_offset = 0;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.rel_bias = rel_bias_log2;
+  p.alias_p = 0;
+  p.cu_seqlens = nullptr;
+  p.cp_world = world;
+  p.cp_rank = rank;
+  p.cp_sk_local = sk_local;
+  p.cp_q_pos0 = rank * sq_local;
+  p.out_q = nullptr;
+  p.out_sf = nullptr;
+  p.ld_outq = p.n_kb = 0;
+  const int bias_bytes = rel_bias_log2 ? 2 * sk_total * 4 : 0;
+  dim3 grid((sq_local + kAttnBQ - 1) / kAttnBQ, n_heads, B);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (head_dim == 64) {
+    const int smem = 3 * AttnCfg<64>::kTileBytes + AttnCfg<64>::kPBytes + 1024 + 64 + bias_bytes;
+    IM_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    IM_CUDA_OK(launch_pdl(attn_fwd_kernel<64, true>, grid, dim3(kAttnThreads), smem, s, tq, cpm.k[0], cpm.v[0], p, cpm));
+  } else {
+    const int smem = 3 * AttnCfg<32>::kTileBytes + AttnCfg<32>::kPBytes + 1024 + 64 + bias_bytes;
+    IM_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    IM_CUDA_OK(launch_pdl(attn_fwd_kernel<32, true>, grid, dim3(kAttnThreads), smem, s, tq, cpm.k[0], cpm.v[0], p, cpm));
+  }
+  IM_LAUNCH_OK("attn_fwd_kernel<cp>");
+  return 0;
 }
 
 IM_API int im_attn_decode(const void* q, int ldq, const void* kc, const void* vc, int ld_kv, int s_max,

@@ -95,3 +95,105 @@ def allpairs_attention(q, k, v, n_heads: int, group=None, scale: float | None = 
             acc = acc * torch.exp(lse_run - new)[..., None] + o * torch.exp(lse - new)[..., None]
             lse_run = new
     return acc.transpose(1, 2).reshape(B, s_loc, HH).to(q.dtype)
+
+
+# =====================================================================================================================
+# In-kernel context parallelism (the product path; the functions above are the torch.distributed baseline / CPU oracle)
+# =====================================================================================================================
+class CpQkvBuffers:
+    """Double-buffered ``[B * S_local, 3 * inner]`` QKV activations in the symmetric heap.
+
+    The QKV projection of layer ``l`` writes buffer ``l % 2``; after ONE heap barrier every rank's attention kernel pulls
+    the K / V tiles of all ranks straight out of those buffers (``attn_fwd_kernel<.., CP>``: TMA loads through tensor
+    maps over the peers' mapped memory, all-pairs order starting with the own shard).  Alternating the buffer makes that
+    single barrier sufficient: a rank reaches the barrier of layer ``l + 1`` only after its layer-``l`` attention has
+    finished reading, so nobody overwrites buffer ``l % 2`` (layer ``l + 2``) while a peer still reads it."""
+
+    def __init__(self, heap, batch: int, s_local: int, inner: int):
+        import ctypes
+
+        self.heap, self.B, self.s_local, self.inner = heap, batch, s_local, inner
+        c = heap.ctx
+        self.world, self.rank = c.world, c.rank
+        self.bufs, self._k_ptrs, self._v_ptrs = [], [], []
+        for _ in range(2):
+            view, off = heap.alloc((batch * s_local, 3 * inner), torch.bfloat16)
+            self.bufs.append(view)
+            self._k_ptrs.append((ctypes.c_void_p * c.world)(*[b + off + inner * 2 for b in heap.bases]))
+            self._v_ptrs.append((ctypes.c_void_p * c.world)(*[b + off + 2 * inner * 2 for b in heap.bases]))
+
+
+def cp_attention(bufs: CpQkvBuffers, parity: int, n_heads: int, *, kv_lens=None, scale: float | None = None, rel_bias=None, out=None):
+    """Attention of this rank's queries (``bufs.bufs[parity][:, :inner]``) over the keys / values of every rank.
+
+    ``kv_lens`` int32 ``[B]``: GLOBAL valid key counts; ``rel_bias`` fp32 ``[heads, 2 * S_total - 1]`` natural-log table of
+    the whole sequence (T5).  The caller must have issued ``heap.barrier()`` after the projection that filled the buffer."""
+    import ctypes
+
+    from infomesh_b200 import _native
+    from infomesh_b200.ops.attention import LOG2E
+
+    qkv = bufs.bufs[parity]
+    inner, B, s_loc = bufs.inner, bufs.B, bufs.s_local
+    hd = inner // n_heads
+    scale = (1.0 / math.sqrt(hd)) if scale is None else scale
+    if out is None:
+        out = torch.empty((B * s_loc, inner), device=qkv.device, dtype=torch.bfloat16)
+    bias_dev = (rel_bias.float() * LOG2E).contiguous() if rel_bias is not None else None
+    if bias_dev is not None:
+        assert bias_dev.shape == (n_heads, 2 * s_loc * bufs.world - 1)
+    L = _native.require()
+    rc = L.im_attn_fwd_cp(_native.ptr(qkv), bufs._k_ptrs[parity], bufs._v_ptrs[parity], _native.ptr(out), ctypes.c_int(B),
+                          ctypes.c_int(n_heads), ctypes.c_int(hd), ctypes.c_int(s_loc), ctypes.c_int(s_loc), ctypes.c_int(bufs.world),
+                          ctypes.c_int(bufs.rank), ctypes.c_int(3 * inner), ctypes.c_int(3 * inner), ctypes.c_int(3 * inner),
+                          ctypes.c_int(out.stride(0)), _native.ptr(kv_lens), ctypes.c_float(scale), _native.ptr(bias_dev),
+                          _native.stream_ptr())
+    _native.check(rc, "im_attn_fwd_cp")
+    _native.count_launch()
+    bufs._keep_bias = bias_dev
+    return out
+
+
+class CPT5Encoder:
+    """T5 encoder over a sequence sharded across the ranks (rank ``r`` holds positions ``[r * S/W, (r + 1) * S/W)`` of every
+    sequence): embeddings, norms, projections and the FFN are row-local with replicated weights; only attention crosses
+    ranks, and it does so INSIDE the attention kernel (:func:`cp_attention`).  Lets the summariser read a full ~100 KB
+    page (the reference truncates at 8000 characters, infomesh/summarizer/engine.py:382,396)."""
+
+    def __init__(self, model, batch: int, s_total: int, heap=None):
+        from infomesh_b200.parallel import dist as D
+        from infomesh_b200.parallel import symm
+
+        self.model, self.ctx = model, D.ctx()
+        W = self.ctx.world
+        assert s_total % (128 * W) == 0, "sequence length must split into 128-key chunks per rank"
+        self.B, self.S, self.s_local = batch, s_total, s_total // W
+        cfg = model.cfg
+        need = 2 * batch * self.s_local * 3 * cfg.inner * 2 + (1 << 20)
+        self.heap = heap or symm.SymmetricHeap(need + (4 << 20), self.ctx)
+        self.bufs = CpQkvBuffers(self.heap, batch, self.s_local, cfg.inner)
+        self.heap.barrier()
+
+    def encode_local(self, ids_local: torch.Tensor, lengths: torch.Tensor | None = None) -> torch.Tensor:
+        """``ids_local`` int32 ``[B, S/W]`` (this rank's slice) -> this rank's encoder states bf16 ``[B, S/W, d_model]``."""
+        from infomesh_b200.ops import gemm as G
+        from infomesh_b200.ops import nn as N
+
+        m, cfg, w = self.model, self.model.cfg, self.model.w
+        B, s_loc, inner = self.B, self.s_local, cfg.inner
+        x = w.emb[ids_local.reshape(-1).long()]
+        bias = m._enc_bias_table(self.S)
+        for li, lay in enumerate(w.enc):
+            par = li & 1
+            n1 = N.layernorm(x, lay["ln1"], None, cfg.eps, rms_only=True)
+            G.linear(n1, lay["wqkv"], out=self.bufs.bufs[par])
+            self.heap.barrier()                                   # every rank's K / V of this layer are in place
+            ctx = cp_attention(self.bufs, par, cfg.heads, kv_lens=lengths, scale=1.0, rel_bias=bias)
+            x = G.linear(ctx, lay["wo"], residual=x)
+            n2 = N.layernorm(x, lay["ln2"], None, cfg.eps, rms_only=True)
+            h = G.linear(n2, lay["wi"], act="relu")
+            x = G.linear(h, lay["wo2"], residual=x)
+        return N.layernorm(x, w.enc_final, None, cfg.eps, rms_only=True).view(B, s_loc, cfg.d_model)
+
+    def close(self):
+        self.heap.close()

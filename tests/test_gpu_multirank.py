@@ -48,3 +48,8 @@ def test_fused_topk_exchange_two_ranks():
 def test_fused_tp_encoder_two_ranks():
     text = _run("gpu_check_tp.py", port=29614)
     assert "ALL OK" in text and "MISMATCH" not in text, text[-3000:]
+
+
+def test_context_parallel_attention_in_kernel_two_ranks():
+    text = _run("gpu_check_cp.py", port=29615)
+    assert "ALL OK" in text, text[-3000:]
