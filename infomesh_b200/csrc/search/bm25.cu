@@ -7,6 +7,11 @@
 // Layout (per shard): post_off[V+1] (int64), post_doc[nnz] (int32, ascending inside a term), post_tf[nnz] (uint8),
 // doc_norm[n_docs] = k1 * (1 - b + b * len / avg_len)  (fp32, pre-computed), idf[V] (fp32, global statistics).
 //
+// Dense terms (document frequency >= n_docs / 32, a few hundred under Zipf) additionally get a DIRECT MAP: one tf byte per
+// document (`dense_tf[slot][doc]`, 0 = absent), so probing them during an intersection is a single load instead of a
+// ~22-step binary search through a multi-million-entry list -- this is what keeps queries that contain common words
+// (the reference's FTS5 handles them with its doclist index) from degenerating.
+//
 // One query per blockIdx.y.  The shortest posting list drives; each lane takes one driver posting, gallops
 // (binary search) through the other lists, and survivors are pushed into a WARP-DISTRIBUTED sorted top-32
 // (lane i holds entry i: insertion = ballot + shuffle, no shared memory).  Per-warp lists are merged by
@@ -63,7 +68,8 @@ bm25_and_topk_kernel(const long long* __restrict__ post_off, const int* __restri
                      const uint8_t* __restrict__ post_tf, const float* __restrict__ doc_norm,
                      const float* __restrict__ idf, const uint8_t* __restrict__ alive,
                      const int* __restrict__ q_terms, int max_terms, int vocab, float* __restrict__ out_scores,
-                     int* __restrict__ out_ids, int* __restrict__ out_counts) {
+                     int* __restrict__ out_ids, int* __restrict__ out_counts, const int* __restrict__ dense_slot,
+                     const uint8_t* __restrict__ dense_tf, long long n_docs) {
   const int q = blockIdx.y;
   const uint32_t lane = threadIdx.x & 31;
   const int warp_in_q = blockIdx.x * (kBm25Threads / 32) + (threadIdx.x >> 5);
@@ -71,6 +77,7 @@ bm25_and_topk_kernel(const long long* __restrict__ post_off, const int* __restri
 
   // query terms: -1 padded; any out-of-vocabulary term makes the AND empty
   int terms[kBm25MaxTerms];
+  const uint8_t* t_map[kBm25MaxTerms];   // direct tf map of a dense term, else null
   long long t_lo[kBm25MaxTerms], t_hi[kBm25MaxTerms];
   int nt = 0;
   bool empty = false;
@@ -87,6 +94,8 @@ bm25_and_topk_kernel(const long long* __restrict__ post_off, const int* __restri
     terms[nt] = t;
     t_lo[nt] = post_off[t];
     t_hi[nt] = post_off[t + 1];
+    const int slot = dense_slot != nullptr ? dense_slot[t] : -1;
+    t_map[nt] = slot >= 0 ? dense_tf + static_cast<size_t>(slot) * n_docs : nullptr;
     if (t_hi[nt] == t_lo[nt]) empty = true;
     ++nt;
   }
@@ -118,13 +127,15 @@ bm25_and_topk_kernel(const long long* __restrict__ post_off, const int* __restri
       for (int i = 0; i < nt; ++i) {
         if (i == drv) continue;
         if (hit) {
-          const long long pos = find_doc(post_doc, t_lo[i], t_hi[i], doc);
-          if (pos < t_hi[i] && __ldg(post_doc + pos) == doc) {
-            const float tf = static_cast<float>(__ldg(post_tf + pos));
-            score += idf[terms[i]] * tf * (kBm25K1 + 1.0f) / (tf + norm);
+          float tf = 0.f;
+          if (t_map[i] != nullptr) {
+            tf = static_cast<float>(__ldg(t_map[i] + doc));          // dense term: one byte, 0 = absent
           } else {
-            hit = false;
+            const long long pos = find_doc(post_doc, t_lo[i], t_hi[i], doc);
+            if (pos < t_hi[i] && __ldg(post_doc + pos) == doc) tf = static_cast<float>(__ldg(post_tf + pos));
           }
+          if (tf > 0.f) score += idf[terms[i]] * tf * (kBm25K1 + 1.0f) / (tf + norm);
+          else hit = false;
         }
       }
       matched += hit ? 1 : 0;
@@ -221,18 +232,34 @@ passage_score_kernel(const int* __restrict__ tok, const long long* __restrict__ 
 }  // namespace im
 
 // out lists: [P][nq][32] with P = blocks_per_query * 4 warps; returns P or <0
-IM_API int im_bm25_topk(const long long* post_off, const int* post_doc, const uint8_t* post_tf, const float* doc_norm,
-                        const float* idf, const uint8_t* alive, const int* q_terms, int nq, int max_terms, int vocab,
-                        int blocks_per_query, float* out_scores, int* out_ids, int* out_counts, void* stream) {
+static int bm25_topk_impl(const long long* post_off, const int* post_doc, const uint8_t* post_tf, const float* doc_norm,
+                          const float* idf, const uint8_t* alive, const int* q_terms, int nq, int max_terms, int vocab,
+                          int blocks_per_query, float* out_scores, int* out_ids, int* out_counts, void* stream,
+                          const int* dense_slot, const uint8_t* dense_tf, long long n_docs) {
   using namespace im;
   if (nq <= 0) return 0;
   if (max_terms > kBm25MaxTerms) return set_error("im_bm25_topk", "at most 16 query terms");
   if (blocks_per_query < 1) blocks_per_query = 1;
   dim3 grid(blocks_per_query, nq);
   bm25_and_topk_kernel<<<grid, kBm25Threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      post_off, post_doc, post_tf, doc_norm, idf, alive, q_terms, max_terms, vocab, out_scores, out_ids, out_counts);
+      post_off, post_doc, post_tf, doc_norm, idf, alive, q_terms, max_terms, vocab, out_scores, out_ids, out_counts, dense_slot,
+      dense_tf, n_docs);
   IM_LAUNCH_OK("bm25_and_topk_kernel");
   return blocks_per_query * (kBm25Threads / 32);
+}
+IM_API int im_bm25_topk(const long long* post_off, const int* post_doc, const uint8_t* post_tf, const float* doc_norm,
+                        const float* idf, const uint8_t* alive, const int* q_terms, int nq, int max_terms, int vocab,
+                        int blocks_per_query, float* out_scores, int* out_ids, int* out_counts, void* stream) {
+  return bm25_topk_impl(post_off, post_doc, post_tf, doc_norm, idf, alive, q_terms, nq, max_terms, vocab, blocks_per_query,
+                        out_scores, out_ids, out_counts, stream, nullptr, nullptr, 0);
+}
+// Same with direct tf maps for dense terms: dense_slot[vocab] (-1 = sparse), dense_tf[n_slots][n_docs].
+IM_API int im_bm25_topk_dense(const long long* post_off, const int* post_doc, const uint8_t* post_tf, const float* doc_norm,
+                              const float* idf, const uint8_t* alive, const int* q_terms, int nq, int max_terms, int vocab,
+                              int blocks_per_query, float* out_scores, int* out_ids, int* out_counts, const int* dense_slot,
+                              const uint8_t* dense_tf, long long n_docs, void* stream) {
+  return bm25_topk_impl(post_off, post_doc, post_tf, doc_norm, idf, alive, q_terms, nq, max_terms, vocab, blocks_per_query,
+                        out_scores, out_ids, out_counts, stream, dense_slot, dense_tf, n_docs);
 }
 
 IM_API int im_passage_score(const int* tok, const long long* pass_off, const long long* doc_pass_off,

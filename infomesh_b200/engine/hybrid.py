@@ -125,10 +125,9 @@ class HybridEngine:
 
     def _bm25_local(self):
         sh = self.shard
-        s, i = sh.bm25.search(self.in_terms, k=self.cfg.k_fetch, alive=sh.alive, id_offset=sh.cfg.doc_base)
-        if self.heap is not None and not self._inject_drop:      # 1-list "merge" whose epilogue pushes the shard's list to every peer
-            S.topk_merge(s.unsqueeze(0), i.unsqueeze(0), self.cfg.k_fetch, push=self.ch_bm25)
-        return s, i
+        # the kernel that merges the per-warp lists also pushes the shard's list to every peer (fused exchange)
+        push = self.ch_bm25 if (self.heap is not None and not self._inject_drop) else None
+        return sh.bm25.search(self.in_terms, k=self.cfg.k_fetch, alive=sh.alive, id_offset=sh.cfg.doc_base, push=push)
 
     def _exchange(self, scores, ids, chan=None):
         """per-shard top-k lists [nq, k] -> global top-k on every rank.

@@ -155,6 +155,33 @@ class Bm25Index:
         self.tf = t(csr["tf"] if len(csr["tf"]) else np.zeros(1, np.uint8), torch.uint8)
         self.norm = t(K1 * (1 - B + B * dl.astype(np.float32) / max(self.avg_len, 1e-9)), torch.float32)
         self.idf = t(idf_fts5(N, df), torch.float32)
+        self.dense_slot = self.dense_tf = None
+        self.build_dense_maps()
+
+    def build_dense_maps(self, min_df: int | None = None, max_bytes: int = 8 << 30) -> int:
+        """Direct tf maps for terms whose posting list covers >= 1/32 of the shard (at least 4096 documents): probing them
+        in an intersection becomes one byte load.  Returns the number of dense terms (0 = none, kernel takes the plain path)."""
+        import torch
+
+        n, V = self.n_docs, self.vocab
+        if n == 0 or V == 0:
+            return 0
+        min_df = max(4096, n // 32) if min_df is None else min_df
+        df_local = (self.off[1:] - self.off[:-1])
+        dense = torch.nonzero(df_local >= min_df).flatten()
+        if dense.numel() == 0 or dense.numel() * n > max_bytes:
+            dense = dense[torch.argsort(df_local[dense], descending=True)][:max(0, max_bytes // max(n, 1))]
+        if dense.numel() == 0:
+            self.dense_slot = self.dense_tf = None
+            return 0
+        slot = torch.full((V,), -1, dtype=torch.int32, device=self.device)
+        slot[dense] = torch.arange(dense.numel(), dtype=torch.int32, device=self.device)
+        tfmap = torch.zeros((dense.numel(), n), dtype=torch.uint8, device=self.device)
+        for s_i, t_id in enumerate(dense.tolist()):
+            a, b = int(self.off[t_id]), int(self.off[t_id + 1])
+            tfmap[s_i, self.doc[a:b].long()] = self.tf[a:b].clamp(min=1)
+        self.dense_slot, self.dense_tf = slot, tfmap
+        return int(dense.numel())
 
     @classmethod
     def from_device_csr(cls, off, doc, tf, norm, idf, avg_len):
@@ -165,10 +192,13 @@ class Bm25Index:
         self.n_docs = norm.numel()
         self.vocab = off.numel() - 1
         self.avg_len = float(avg_len)
+        self.dense_slot = self.dense_tf = None
+        self.build_dense_maps()
         return self
 
     def nbytes(self) -> int:
-        return sum(x.numel() * x.element_size() for x in (self.off, self.doc, self.tf, self.norm, self.idf))
+        base = sum(x.numel() * x.element_size() for x in (self.off, self.doc, self.tf, self.norm, self.idf))
+        return base + (self.dense_tf.numel() + self.dense_slot.numel() * 4 if self.dense_tf is not None else 0)
 
     def search_partials(self, q_terms, alive=None, blocks_per_query=0, counts=None):
         """q_terms: int32 [nq, T<=16] (-1 padded) on device -> per-warp lists (scores[P,nq,32], ids[P,nq,32])."""
@@ -178,25 +208,35 @@ class Bm25Index:
         assert q_terms.dtype == torch.int32 and T <= MAX_TERMS and q_terms.is_contiguous()
         L = _native.require()
         if blocks_per_query <= 0:
-            blocks_per_query = max(1, min(64, (2 * L.im_sm_count()) // max(nq, 1)))
+            # 16 CTAs (64 warps) per query: a query whose driving list has millions of postings is spread over enough
+            # warps, and the warps of a selective query find their slice empty and exit at once
+            blocks_per_query = max(1, min(64, max(16, (2 * L.im_sm_count()) // max(nq, 1))))
         P = blocks_per_query * 4
         out_s = torch.empty((P, nq, 32), device=self.device, dtype=torch.float32)
         out_i = torch.empty((P, nq, 32), device=self.device, dtype=torch.int32)
-        rc = L.im_bm25_topk(_native.ptr(self.off), _native.ptr(self.doc), _native.ptr(self.tf), _native.ptr(self.norm),
-                            _native.ptr(self.idf), _native.ptr(alive), _native.ptr(q_terms), ctypes.c_int(nq),
-                            ctypes.c_int(T), ctypes.c_int(self.vocab), ctypes.c_int(blocks_per_query),
-                            _native.ptr(out_s), _native.ptr(out_i), _native.ptr(counts), _native.stream_ptr())
+        if self.dense_tf is not None:
+            rc = L.im_bm25_topk_dense(_native.ptr(self.off), _native.ptr(self.doc), _native.ptr(self.tf), _native.ptr(self.norm),
+                                      _native.ptr(self.idf), _native.ptr(alive), _native.ptr(q_terms), ctypes.c_int(nq),
+                                      ctypes.c_int(T), ctypes.c_int(self.vocab), ctypes.c_int(blocks_per_query),
+                                      _native.ptr(out_s), _native.ptr(out_i), _native.ptr(counts), _native.ptr(self.dense_slot),
+                                      _native.ptr(self.dense_tf), ctypes.c_longlong(self.n_docs), _native.stream_ptr())
+        else:
+            rc = L.im_bm25_topk(_native.ptr(self.off), _native.ptr(self.doc), _native.ptr(self.tf), _native.ptr(self.norm),
+                                _native.ptr(self.idf), _native.ptr(alive), _native.ptr(q_terms), ctypes.c_int(nq),
+                                ctypes.c_int(T), ctypes.c_int(self.vocab), ctypes.c_int(blocks_per_query),
+                                _native.ptr(out_s), _native.ptr(out_i), _native.ptr(counts), _native.stream_ptr())
         if rc < 0:
             _native.check(rc, "im_bm25_topk")
         _native.count_launch()
         return out_s, out_i
 
-    def search(self, q_terms, k=20, alive=None, id_offset=0):
+    def search(self, q_terms, k=20, alive=None, id_offset=0, push=None):
+        """``push``: a ``TopkChannel`` -- the merge kernel also stores the shard's list into every peer's receive area."""
         from infomesh_b200.ops.search import topk_merge
 
         assert k <= 32
         ps, pi = self.search_partials(q_terms, alive)
-        return topk_merge(ps, pi, k, id_offset=id_offset)
+        return topk_merge(ps, pi, k, id_offset=id_offset, push=push)
 
 
 def passage_score_ref(tokens, pass_bounds, q_terms):

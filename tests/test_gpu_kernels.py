@@ -595,3 +595,32 @@ def test_rank_fuse_matches_cpu_ranking():
         assert got_ids == [w.doc_id for w in want]
         assert abs(float(s[q, 0]) - want[0].combined_score) < 2e-4
         assert abs(float(sig[q, 0, 1]) - want[0].freshness_score) < 2e-4
+
+
+def test_bm25_dense_term_maps_match_plain_path_and_oracle():
+    """Queries that contain very common terms: the direct tf maps of dense terms give exactly the plain (binary-search)
+    result and the NumPy/FTS5-formula oracle's ordering, including two-common-term queries whose driving list is long."""
+    from infomesh_b200.engine.synth import SynthConfig, SynthShard, make_queries
+    from infomesh_b200.ops.bm25 import bm25_ref
+
+    cfg = SynthConfig(n_docs=200_000, n_docs_global=200_000, vocab_terms=20_000, doc_len=48)
+    shard = SynthShard(cfg, device=DEV)
+    bm = shard.bm25
+    n_dense = int((bm.dense_slot >= 0).sum().item()) if bm.dense_slot is not None else 0
+    assert n_dense >= 5                                             # Zipf head terms cover > 1/32 of the corpus
+    qt, _, _, _ = make_queries(cfg, 24, mix="common")
+    qt = qt.to(DEV)
+    qt[0, :3] = torch.tensor([0, 1, -1], dtype=torch.int32)          # the two MOST common terms: a ~100k-entry driving list
+    qt[1, :3] = torch.tensor([2, 5, 7], dtype=torch.int32)
+    s_dense, i_dense = bm.search(qt, k=20)
+    keep = (bm.dense_slot, bm.dense_tf)
+    bm.dense_slot = bm.dense_tf = None
+    s_plain, i_plain = bm.search(qt, k=20)
+    bm.dense_slot, bm.dense_tf = keep
+    assert torch.equal(i_dense, i_plain) and torch.allclose(s_dense, s_plain)
+    csr = {"off": bm.off.cpu().numpy(), "doc": bm.doc.cpu().numpy(), "tf": bm.tf.cpu().numpy(),
+           "doc_len": np.full(cfg.n_docs, cfg.doc_len, np.int32), "df": (bm.off[1:] - bm.off[:-1]).cpu().numpy().astype(np.int32)}
+    for q in (0, 1, 5):
+        ref = bm25_ref(csr, qt[q].cpu().numpy(), k=20)
+        got = [(round(float(s), 3), int(i)) for s, i in zip(s_dense[q].tolist(), i_dense[q].tolist()) if i >= 0]
+        assert [i for _, i in got] == [i for _, i in ref] or [s for s, _ in got] == [round(s, 3) for s, _ in ref]
