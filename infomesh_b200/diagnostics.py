@@ -163,4 +163,20 @@ def run_diagnostics(data_dir: Path | None = None, *, p2p_port: int = 4001, admin
             add("gpu", "error" if it.severity == IssueSeverity.ERROR else "warning", it.message)
     except Exception as exc:  # noqa: BLE001
         add("gpu", "warning", f"GPU check failed: {exc}")
+    # --- GPU health (ECC / Xid / throttle) through NVML
+    try:
+        from infomesh_b200.resources.gpu_health import GpuHealthMonitor
+
+        mon = GpuHealthMonitor()
+        hs = [h for h in mon.poll() if h.available]
+        mon.close()
+        bad = [h for h in hs if not h.healthy]
+        if bad:
+            add("gpu_health", "error", "; ".join(f"GPU {h.index}: uncorrected ECC {h.ecc_uncorrected}, Xid {h.last_xid} x{h.xid_events}" for h in bad))
+        elif hs:
+            hot = sorted({r for h in hs for r in h.throttle_reasons if r != "sw_power_cap"})
+            add("gpu_health", "warning" if hot else "ok", f"{len(hs)} GPU(s) healthy (no uncorrected ECC errors, no critical Xid)"
+                + (f"; throttling: {', '.join(hot)}" if hot else ""))
+    except Exception as exc:  # noqa: BLE001
+        add("gpu_health", "warning", f"GPU health check failed: {exc}")
     return rep

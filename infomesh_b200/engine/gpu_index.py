@@ -383,9 +383,18 @@ class GpuSearchIndex:
     def search(self, query: str, k: int = 10) -> list[dict[str, object]]:
         return self.search_many([query], k)[0]
 
+    def health(self) -> dict:
+        """NVML view of the serving device(s): ECC / Xid / throttle state (resources/gpu_health.py); cached monitor."""
+        from infomesh_b200.resources.gpu_health import GpuHealthMonitor
+
+        mon = self.__dict__.get("_health_mon")
+        if mon is None:
+            mon = self.__dict__["_health_mon"] = GpuHealthMonitor([self.device.index or 0] if self.device.type == "cuda" else None)
+        return mon.summary()
+
     def stats(self) -> dict[str, object]:
         sh = self.engine.shard if self.engine else None
-        return {"documents": self.n_docs, "pending": self._pending, "built_at": self.built_at, "build_seconds": round(self.build_seconds, 2),
+        return {"health": self.health(),"documents": self.n_docs, "pending": self._pending, "built_at": self.built_at, "build_seconds": round(self.build_seconds, 2),
                 "hbm_bytes": sh.nbytes() if sh else 0, "vocab": self.builder.vocab if self.builder else 0,
                 "query_batch": self.nq, "rerank": self.rerank, "dense": self.use_dense,
                 "encoder": getattr(self.encoder, "source", "random-init"),
