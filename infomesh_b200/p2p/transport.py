@@ -2,9 +2,12 @@
 
 The reference rides on py-libp2p (trio) streams (infomesh/p2p/node.py:535-598, 771-981).  Neither libp2p nor trio is
 a dependency here: peers speak the same ``[u32 BE length][msgpack {type, payload}]`` frames
-(infomesh/p2p/protocol.py:303-378) over plain asyncio TCP, one short-lived connection per request like a libp2p
-stream.  Every request frame is wrapped in a :class:`SignedEnvelope` when the node has a key pair, bandwidth is
-charged to the token buckets, and handlers are registered per :class:`MessageType`.
+(infomesh/p2p/protocol.py:303-378) over asyncio TCP, one short-lived connection per request like a libp2p stream.
+When the node has a key pair a connection starts with the ``IMN1`` handshake of :mod:`infomesh_b200.p2p.secure_channel`
+(ephemeral X25519 + Ed25519 identities, ChaCha20-Poly1305 records -- the role Noise plays under libp2p,
+infomesh/p2p/node.py:550-552): frames are encrypted and the channel itself authenticates the sender.  Peers that do
+not speak it are still served in plaintext with every frame wrapped in a :class:`SignedEnvelope` (unless
+``require_encrypted``).  Bandwidth is charged to the token buckets; handlers are registered per :class:`MessageType`.
 
 Multiaddrs are the ``/ip4/<host>/tcp/<port>/p2p/<peer_id>`` subset.
 """
@@ -16,6 +19,7 @@ from dataclasses import dataclass
 from typing import Any, Awaitable, Callable
 
 from infomesh_b200.p2p import message_auth as MA
+from infomesh_b200.p2p import secure_channel as SC
 from infomesh_b200.p2p.protocol import (MAX_MESSAGE_SIZE, MessageType, decode_message, encode_message,
                                         encode_signed_envelope, read_frame_length, safe_unpackb)
 from infomesh_b200.p2p.throttle import BandwidthThrottle
@@ -74,8 +78,13 @@ WRITE_TYPES = frozenset({MessageType.INDEX_SUBMIT, MessageType.REPLICATE_REQUEST
 
 class Transport:
     def __init__(self, key_pair: Any | None = None, *, throttle: BandwidthThrottle | None = None,
-                 is_isolated_fn: Callable[[str], bool] | None = None, require_signed: bool = False):
+                 is_isolated_fn: Callable[[str], bool] | None = None, require_signed: bool = False, encrypt: bool = True,
+                 require_encrypted: bool = False):
         self.key_pair = key_pair
+        self.encrypt = bool(encrypt and key_pair is not None)          # offer / accept the IMN1 encrypted channel
+        self.require_encrypted = bool(require_encrypted)               # refuse plaintext peers altogether
+        self._plain_peers: set[tuple[str, int]] = set()                # peers that turned the handshake down
+        self.encrypted_in = self.encrypted_out = 0
         self.peer_id = key_pair.peer_id if key_pair is not None else ""
         self.throttle = throttle
         self.keys = MA.PeerKeyRegistry()
@@ -116,10 +125,13 @@ class Transport:
         d["public_key"] = self.key_pair.public_key_bytes()
         return encode_signed_envelope(d)
 
-    def _unwrap(self, frame: bytes) -> tuple[MessageType, dict[str, Any], str]:
-        """-> (type, payload, verified sender id or "")."""
+    def _unwrap(self, frame: bytes, channel_sender: str = "") -> tuple[MessageType, dict[str, Any], str]:
+        """-> (type, payload, verified sender id or "").  ``channel_sender``: the peer id the encrypted channel already
+        authenticated; a bare frame inside such a channel counts as signed by that peer."""
         kind, payload = decode_message(frame)
         if kind != MessageType.SIGNED_ENVELOPE:
+            if channel_sender:
+                return kind, payload, channel_sender
             if self._require_signed or kind in WRITE_TYPES:
                 raise MA.VerificationError("unsigned message refused")
             return kind, payload, ""
@@ -142,24 +154,52 @@ class Transport:
 
     async def _serve_conn(self, reader: asyncio.StreamReader, writer: asyncio.StreamWriter) -> None:
         peer = writer.get_extra_info("peername") or ("?", 0)
+        session: SC.SecureSession | None = None
         try:
-            frame = await asyncio.wait_for(read_frame(reader), timeout=30.0)
+            prefix = await asyncio.wait_for(reader.readexactly(4), timeout=30.0)
+            if prefix == SC.MAGIC:
+                if not self.encrypt:
+                    return                                                  # no identity to answer with: drop the connection
+                session = await SC.server_handshake(reader, writer, self.key_pair)
+                if self._isolated is not None and self._isolated(session.remote_peer_id):
+                    return
+                self.keys.register(session.remote_peer_id, session.remote_public_key)      # proven by the handshake
+                frame = await asyncio.wait_for(session.recv(reader), timeout=30.0)
+                self.encrypted_in += 1
+            else:
+                if self.require_encrypted:
+                    await self._send(writer, encode_message(MessageType.ERROR, {"error": "encrypted channel required"}))
+                    return
+                n = read_frame_length(prefix)
+                if n > MAX_MESSAGE_SIZE:
+                    raise ValueError(f"frame too large: {n}")
+                frame = prefix + await asyncio.wait_for(reader.readexactly(n), timeout=30.0)
             self.bytes_in += len(frame)
             if self.throttle:
                 await self.throttle.acquire_download(len(frame))
+
+            async def answer(data: bytes) -> None:
+                if session is not None:
+                    if self.throttle:
+                        await self.throttle.acquire_upload(len(data))
+                    self.bytes_out += await session.send(writer, data)
+                else:
+                    await self._send(writer, data)
+
             try:
-                kind, payload, sender = self._unwrap(frame)
+                kind, payload, sender = self._unwrap(frame, channel_sender=session.remote_peer_id if session else "")
             except (MA.VerificationError, ValueError) as exc:
-                await self._send(writer, encode_message(MessageType.ERROR, {"error": str(exc)}))
+                await answer(encode_message(MessageType.ERROR, {"error": str(exc)}))
                 return
             handler = self._handlers.get(kind)
             if handler is None:
-                await self._send(writer, encode_message(MessageType.ERROR, {"error": f"unsupported type {int(kind)}"}))
+                await answer(encode_message(MessageType.ERROR, {"error": f"unsupported type {int(kind)}"}))
                 return
             reply = await handler(payload, PeerInfo(sender, peer[0], peer[1]))
             if reply is not None:
-                await self._send(writer, self._wrap(encode_message(*reply)))
-        except (asyncio.IncompleteReadError, asyncio.TimeoutError, ConnectionError, ValueError) as exc:
+                # inside an authenticated channel the reply needs no envelope of its own
+                await answer(encode_message(*reply) if session is not None else self._wrap(encode_message(*reply)))
+        except (asyncio.IncompleteReadError, asyncio.TimeoutError, ConnectionError, ValueError, SC.HandshakeError) as exc:
             logger.debug("transport_conn_error", error=str(exc))
         except Exception:  # noqa: BLE001 — a handler bug must not kill the listener
             logger.exception("transport_handler_failed")
@@ -184,8 +224,31 @@ class Transport:
         """One request / reply exchange.  ``expect_peer``: the peer id that was dialled -- a reply signed by anyone else
         (an on-path host answering with its own self-signed envelope) or not signed at all is rejected."""
         host, port = addr if isinstance(addr, tuple) else parse_multiaddr(addr)[:2]
+        if expect_peer is None and not isinstance(addr, tuple):
+            expect_peer = parse_multiaddr(addr)[2] or None             # /p2p/<peer_id> in the multiaddr pins the identity
 
-        async def _go():
+        async def _secure():
+            reader, writer = await asyncio.open_connection(host, port)
+            try:
+                session = await SC.client_handshake(reader, writer, self.key_pair, expect_peer=expect_peer)
+                self.keys.register(session.remote_peer_id, session.remote_public_key)
+                data = encode_message(msg_type, payload)
+                if self.throttle:
+                    await self.throttle.acquire_upload(len(data))
+                self.bytes_out += await session.send(writer, data)
+                self.encrypted_out += 1
+                if not expect_reply:
+                    return None
+                frame = await session.recv(reader)
+                self.bytes_in += len(frame)
+                if self.throttle:
+                    await self.throttle.acquire_download(len(frame))
+                kind, body, _sender = self._unwrap(frame, channel_sender=session.remote_peer_id)
+                return kind, body
+            finally:
+                writer.close()
+
+        async def _plain():
             reader, writer = await asyncio.open_connection(host, port)
             try:
                 await self._send(writer, self._wrap(encode_message(msg_type, payload)))
@@ -201,6 +264,22 @@ class Transport:
                 return kind, body
             finally:
                 writer.close()
+
+        async def _go():
+            if self.encrypt and (host, port) not in self._plain_peers:
+                try:
+                    return await _secure()
+                except (asyncio.IncompleteReadError, ConnectionError, SC.HandshakeError) as exc:
+                    # an identity mismatch is final; a peer that merely does not speak IMN1 (it closes the connection or
+                    # answers with a plaintext ERROR frame) is remembered and served the legacy way
+                    if isinstance(exc, SC.HandshakeError) and "expected" in str(exc):
+                        raise MA.VerificationError(str(exc)) from exc
+                    if self.require_encrypted:
+                        raise
+                    self._plain_peers.add((host, port))
+            elif self.require_encrypted:
+                raise ConnectionError("peer does not support the encrypted channel")
+            return await _plain()
 
         return await asyncio.wait_for(_go(), timeout=timeout)
 
