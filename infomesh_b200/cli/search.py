@@ -53,13 +53,17 @@ def search(query: str, limit: int, local_only: bool, vector: bool, gpu: bool) ->
                        compression_level=cfg.storage.compression_level)
     try:
         if gpu:
-            from infomesh_b200.engine.gpu_index import GpuSearchIndex, gpu_index_kwargs
+            from infomesh_b200.engine.multigpu import make_index
 
-            gi = GpuSearchIndex(store, query_batch=8, **gpu_index_kwargs(getattr(cfg, "gpu", None)))
-            gi.rebuild()
-            t0 = time.monotonic()
-            hits = gi.search(query, limit)
-            _print_ranked(hits, (time.monotonic() - t0) * 1000, "gpu hybrid")
+            gi = make_index(store, getattr(cfg, "gpu", None), query_batch=8)
+            try:
+                gi.rebuild()
+                t0 = time.monotonic()
+                hits = gi.search(query, limit)
+                label = f"gpu hybrid x{gi.world}" if hasattr(gi, "world") else "gpu hybrid"
+                _print_ranked(hits, (time.monotonic() - t0) * 1000, label)
+            finally:
+                gi.close()
             return
         if vector:
             from infomesh_b200.index.vector_store import VectorStore

@@ -70,7 +70,7 @@ class GpuSearchIndex:
                  reranker: BertModel | None = None, rerank: bool = True, query_batch: int = 64, passage_len: int = 96,
                  enc_doc_tokens: int = 128, embed_batch: int = 256, use_graph: bool = True, seed: int = 0,
                  encoder_path: str | None = None, reranker_path: str | None = None, allow_untrained: bool = False,
-                 rank_signals: bool = False, authority_fn=None):
+                 rank_signals: bool = False, authority_fn=None, shard: tuple[int, int] | None = None):
         self.store = store
         self.device = torch.device(device)
         self.enc_tok = self.rr_tok = None
@@ -88,6 +88,11 @@ class GpuSearchIndex:
         self.allow_untrained = bool(allow_untrained)
         # BM25-only answers ordered like the reference's search_local (freshness / trust / authority fused on the device)
         self.rank_signals, self.authority_fn = bool(rank_signals), authority_fn
+        # (rank, world) of a document-sharded deployment (engine/multigpu.py): this process indexes documents
+        # [rank * per, (rank + 1) * per) of the store on its GPU; vocabulary / df / idf stay global
+        self.shard_rank, self.shard_world = shard if shard is not None else (0, 1)
+        self.row_base = 0
+        self._pheap = None
         # ranking policy: a model without checkpoint weights may not influence results (see module docstring)
         self.use_dense = self.allow_untrained or bool(getattr(self.encoder, "pretrained", False))
         want_rr = rerank and (self.allow_untrained or bool(getattr(reranker, "pretrained", False)))
@@ -133,18 +138,27 @@ class GpuSearchIndex:
                 vec_chunks.append(self.encoder.embed(tok.to(dev, non_blocking=True), lens.to(dev, non_blocking=True)))
                 batch_text.clear()
 
+        n_total = int(self.store.get_stats().get("document_count", 0)) if self.shard_world > 1 else 0
+        per = (n_total + self.shard_world - 1) // self.shard_world if self.shard_world > 1 else 0
+        lo, hi = (self.shard_rank * per, min(n_total, (self.shard_rank + 1) * per)) if self.shard_world > 1 else (0, 1 << 62)
+        seen = -1
         for doc in self.store.iter_documents():
             body = f"{doc.title}\n{doc.text}"
-            builder.add_text(body)
-            ids.append(int(doc.doc_id))
-            pt_rows.append(self.rr_tok.encode_plain(body, self.passage_len))
-            docs_text.append(doc.text)
+            builder.add_text(body)                            # EVERY rank tokenises the whole store: global vocabulary and df
+            seen += 1
+            # ranking signals are per-document scalars: kept for EVERY document on every rank (8 B / doc), because the
+            # rank fuse runs after the exchange, on candidate rows of any shard
             crawled.append(float(doc.crawled_at or 0.0))
             if self.authority_fn is not None:
                 try:
                     auth.append(float(self.authority_fn(doc.url)))
                 except Exception:  # noqa: BLE001
                     auth.append(0.0)
+            if not (lo <= seen < hi):
+                continue
+            ids.append(int(doc.doc_id))
+            pt_rows.append(self.rr_tok.encode_plain(body, self.passage_len))
+            docs_text.append(doc.text)
             batch_text.append(body[:2000])                   # the reference embeds the first 2000 chars (vector_store.py:156)
             if len(batch_text) >= self.embed_batch:
                 flush()
@@ -156,6 +170,10 @@ class GpuSearchIndex:
                 self.engine, self.builder = None, builder
             return 0
         csr = builder.export()
+        if self.shard_world > 1:
+            csr = _slice_csr(csr, lo, hi)                       # this rank's postings, global df / avg_len kept alongside
+            csr["per_rank"] = per
+            self.row_base = lo
         passages = _passage_arrays(builder, docs_text)          # after every term is registered
         passages["neg_age"] = np.asarray(crawled, dtype=np.float64) - t0      # seconds before this build (<= 0), fp32-safe
         passages["authority"] = np.asarray(auth, dtype=np.float32) if auth else None
@@ -264,13 +282,35 @@ class GpuSearchIndex:
         """Adopt device structures (fresh build or loaded segments): the engine, row maps and pinned staging are built
         into locals and published together under the lock, so a concurrent search sees either the old or the new index."""
         dev = self.device
-        shard = _StoreShard(dev, vectors, Bm25Index(csr, device=dev), ptok, plen, alive)
+        bm = Bm25Index(csr, device=dev, n_docs_global=csr.get("n_docs_global"), avg_len=csr.get("avg_len_global"),
+                       df_global=csr.get("df_global"))
+        ptabs, ekw = None, {}
+        if self.shard_world > 1:
+            # passage tokens live in a symmetric heap so pair assembly on any rank can read this shard's passages over NVLink
+            from infomesh_b200.parallel import dist as D
+            from infomesh_b200.parallel import symm
+
+            per = int(csr["per_rank"])
+            if self._pheap is not None:
+                self._pheap.close()
+            self._pheap = symm.SymmetricHeap(per * (self.passage_len + 1) * 4 + (4 << 20), D.ctx())
+            tok_v, tok_off = self._pheap.alloc((per, self.passage_len), torch.int32)
+            len_v, len_off = self._pheap.alloc((per,), torch.int32)
+            tok_v[:ptok.shape[0]].copy_(ptok)
+            len_v[:plen.shape[0]].copy_(plen)
+            ptok, plen = tok_v[:ptok.shape[0]], len_v[:plen.shape[0]]
+            ptabs = (self._pheap.peer_table(tok_off), self._pheap.peer_table(len_off))
+            self._pheap.barrier()
+            ekw = dict(passage_tables=ptabs, docs_per_shard=per, passage_len=self.passage_len)
+        shard = _StoreShard(dev, vectors, bm, ptok, plen, alive)
+        shard.cfg = _ShardCfg(self.row_base)
         if passages.get("neg_age") is not None:
             shard.neg_age = torch.from_numpy(np.minimum(passages["neg_age"], 0.0).astype(np.float32)).to(dev)
             shard.authority = torch.from_numpy(passages["authority"]).to(dev) if passages.get("authority") is not None else None
+            shard.signal_base = 0 if self.shard_world > 1 else self.row_base     # sharded: the signal arrays cover every document
         cfg = HybridConfig(nq=self.nq, rerank=self.rerank, k_fetch=20, n_rerank=20, k_out=10, pair_seq=min(128, 32 + self.passage_len),
                            use_graph=self.use_graph, dense=self.use_dense, rank_signals=self.rank_signals)
-        engine = HybridEngine(shard, cfg, encoder=self.encoder, reranker=self.reranker)
+        engine = HybridEngine(shard, cfg, encoder=self.encoder, reranker=self.reranker, **ekw)
         pin = torch.cuda.is_available()
 
         def mk(*shape, fill=0):
@@ -329,6 +369,32 @@ class GpuSearchIndex:
             e = [self.enc_tok.sp.cls, self.enc_tok.sp.sep]
             self._h_enc[i, :2] = torch.tensor(e, dtype=torch.int32)
 
+    def search_arrays(self, chunk: list[str]) -> dict[str, np.ndarray]:
+        """One device pass over up to ``query_batch`` queries -> host arrays ``[nq, k_out]``: ``scores``, global ``rows``,
+        and for the rows THIS process owns ``doc_ids`` (else -1) and the best passage ``pass`` / its character ``span``.
+        In a sharded deployment every rank runs this collectively on the same queries (engine/multigpu.py merges)."""
+        with self._lock:      # staging buffers, graph-static device buffers and the row map are shared state
+            if self.engine is None:
+                return {}
+            self._stage(chunk)
+            self.engine.search_batch(self._h_enc, self._h_enc_len, self._h_qtok, self._h_qlen, self._h_terms, self._h_scores, self._h_ids)
+            # K11 on the device: best passage (coverage + 0.1 x density) of every returned (query, document) pair
+            best_pass = self._best_passages()
+            torch.cuda.current_stream(self.device).synchronize()
+            scores, rows = self._h_scores.numpy().copy(), self._h_ids.numpy().copy()
+            best_pass = best_pass.cpu().numpy().reshape(rows.shape)
+            doc_ids, spans, doc_off = self.doc_ids, self._pass["span"], self._pass["doc_off"]
+        local = rows - self.row_base
+        own = (local >= 0) & (local < doc_ids.size)
+        lr = np.where(own, local, 0)
+        ids = np.where(own, doc_ids[lr] if doc_ids.size else -1, -1)
+        pidx = doc_off[lr] + np.maximum(best_pass, 0)
+        has = own & (best_pass >= 0) & (pidx < doc_off[np.minimum(lr + 1, doc_off.size - 1)])
+        span = np.full(rows.shape + (2,), -1, np.int64)
+        if spans.shape[0]:
+            span[has] = spans[pidx[has]]
+        return {"scores": scores, "rows": rows, "doc_ids": ids.astype(np.int64), "pass": np.where(has, best_pass, -1), "span": span}
+
     def search_many(self, queries: list[str], k: int = 10) -> list[list[dict[str, object]]]:
         """One device pass per ``query_batch`` queries.  Each hit: doc_id, url, title, snippet, score."""
         if self.engine is None or not queries:
@@ -337,35 +403,8 @@ class GpuSearchIndex:
         nq = self.engine.cfg.nq
         for a in range(0, len(queries), nq):
             chunk = queries[a:a + nq]
-            with self._lock:      # staging buffers, graph-static device buffers and the row map are shared state
-                if self.engine is None:
-                    out.extend([] for _ in chunk)
-                    continue
-                self._stage(chunk)
-                self.engine.search_batch(self._h_enc, self._h_enc_len, self._h_qtok, self._h_qlen, self._h_terms, self._h_scores, self._h_ids)
-                # K11 on the device: best passage (coverage + 0.1 x density) of every returned (query, document) pair
-                best_pass = self._best_passages()
-                torch.cuda.current_stream(self.device).synchronize()
-                scores, rows = self._h_scores.numpy().copy(), self._h_ids.numpy().copy()
-                best_pass = best_pass.cpu().numpy().reshape(rows.shape)
-                doc_ids, spans, doc_off = self.doc_ids, self._pass["span"], self._pass["doc_off"]
-            for i, q in enumerate(chunk):
-                hits = []
-                for j, (s, r) in enumerate(zip(scores[i], rows[i])):
-                    if r < 0 or r >= doc_ids.size or len(hits) >= k:
-                        continue
-                    doc = self.store.get_document(int(doc_ids[r]))
-                    if doc is None:
-                        continue
-                    bp = int(best_pass[i, j])
-                    if bp >= 0 and doc_off[r] + bp < doc_off[r + 1]:
-                        a, b = spans[doc_off[r] + bp]
-                        snippet = doc.text[a:b][:300]
-                    else:
-                        snippet = _snippet(doc.text, q)
-                    hits.append({"doc_id": doc.doc_id, "url": doc.url, "title": doc.title, "snippet": snippet,
-                                 "score": float(s), "crawled_at": doc.crawled_at, "passage": bp})
-                out.append(hits)
+            arr = self.search_arrays(chunk)
+            out.extend(format_hits(self.store, chunk, k, arr) if arr else [[] for _ in chunk])
         return out
 
     def _best_passages(self) -> torch.Tensor:
@@ -374,7 +413,8 @@ class GpuSearchIndex:
 
         eng = self.engine
         nq, k_out = eng.out_ids.shape
-        pair_doc = eng.out_ids.reshape(-1).clamp(min=-1).to(torch.int32)
+        pair_doc = eng.out_ids.reshape(-1) - self.row_base          # rows of other shards are not scored here
+        pair_doc = torch.where((pair_doc >= 0) & (pair_doc < self.doc_ids.size), pair_doc, -1).to(torch.int32)
         pair_query = torch.arange(nq, device=self.device, dtype=torch.int32).repeat_interleave(k_out)
         pd = self._pass_dev
         _s, best = passage_score(pd["terms"], pd["off"], pd["doc_off"], pair_doc, pair_query, eng.in_terms)
@@ -382,6 +422,16 @@ class GpuSearchIndex:
 
     def search(self, query: str, k: int = 10) -> list[dict[str, object]]:
         return self.search_many([query], k)[0]
+
+    def close(self) -> None:
+        """Drop the device structures (and, sharded, leave the symmetric heaps: peers must do the same collectively)."""
+        with self._lock:
+            eng, self.engine = self.engine, None
+            if eng is not None and getattr(eng, "heap", None) is not None:
+                eng.heap.close()
+            if self._pheap is not None:
+                self._pheap.close()
+                self._pheap = None
 
     def health(self) -> dict:
         """NVML view of the serving device(s): ECC / Xid / throttle state (resources/gpu_health.py); cached monitor."""
@@ -400,6 +450,57 @@ class GpuSearchIndex:
                 "encoder": getattr(self.encoder, "source", "random-init"),
                 "reranker": getattr(self.reranker, "source", "random-init") if self.reranker is not None else "off",
                 "cuda_graph": bool(self.engine and self.engine._graph is not None)}
+
+
+def format_hits(store, chunk: list[str], k: int, arr: dict[str, np.ndarray]) -> list[list[dict[str, object]]]:
+    """Host-side tail of a search: document rows from the store, snippet = the device-chosen passage (K11) or a window
+    around the first query term.  ``arr`` is :meth:`GpuSearchIndex.search_arrays` output (merged over shards)."""
+    out = []
+    for i, q in enumerate(chunk):
+        hits: list[dict[str, object]] = []
+        for j in range(arr["scores"].shape[1]):
+            did = int(arr["doc_ids"][i, j])
+            if did < 0 or len(hits) >= k:
+                continue
+            doc = store.get_document(did)
+            if doc is None:
+                continue
+            a, b = (int(x) for x in arr["span"][i, j])
+            snippet = doc.text[a:b][:300] if a >= 0 else _snippet(doc.text, q)
+            hits.append({"doc_id": doc.doc_id, "url": doc.url, "title": doc.title, "snippet": snippet,
+                         "score": float(arr["scores"][i, j]), "crawled_at": doc.crawled_at, "passage": int(arr["pass"][i, j])})
+        out.append(hits)
+    return out
+
+
+def merge_shard_arrays(parts: list[dict[str, np.ndarray]]) -> dict[str, np.ndarray]:
+    """Combine the per-rank views of ONE collective search: scores / rows are identical on every rank (the final
+    selection runs everywhere), ``doc_ids`` / ``pass`` / ``span`` are filled only by the rank that owns the row."""
+    out = {key: np.array(val, copy=True) for key, val in parts[0].items()}
+    for part in parts[1:]:
+        fill = (out["doc_ids"] < 0) & (part["doc_ids"] >= 0)
+        for key in ("doc_ids", "pass"):
+            out[key][fill] = part[key][fill]
+        out["span"][fill] = part["span"][fill]
+    return out
+
+
+def _slice_csr(csr: dict, lo: int, hi: int) -> dict:
+    """Postings of documents ``[lo, hi)`` out of a global CSR, re-based to local rows, with the GLOBAL statistics BM25
+    needs (document count, average length, document frequencies) carried along."""
+    off, doc, tf, dl, df = csr["off"], csr["doc"], csr["tf"], csr["doc_len"], csr["df"]
+    V = len(off) - 1
+    nnz = int(off[-1])
+    term_of = np.repeat(np.arange(V, dtype=np.int64), np.diff(off))
+    d = doc[:nnz]
+    sel = (d >= lo) & (d < hi)
+    counts = np.bincount(term_of[sel], minlength=V)
+    new_off = np.zeros(V + 1, np.int64)
+    new_off[1:] = np.cumsum(counts)
+    n_all = len(dl)
+    return {"off": new_off, "doc": (d[sel] - lo).astype(np.int32), "tf": tf[:nnz][sel], "doc_len": dl[lo:hi], "df": df,
+            "df_global": df, "n_docs_global": n_all, "avg_len_global": float(dl.sum() / max(n_all, 1)),
+            "per_rank": 0}
 
 
 def _passage_arrays(builder: HostIndexBuilder, texts: list[str]) -> dict:

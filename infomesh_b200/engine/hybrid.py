@@ -205,7 +205,7 @@ class HybridEngine:
         elif cfg.rank_signals and getattr(self.shard, "neg_age", None) is not None:
             # reference search_local semantics: BM25 squash + freshness + trust + authority, fused and sorted on the device
             fu_s, fu_i = F.rank_fuse(bm_s.contiguous(), bm_i.contiguous(), cfg.n_rerank, crawled_at=self.shard.neg_age,
-                                     authority=getattr(self.shard, "authority", None), now=0.0, row_base=self.shard.cfg.doc_base)
+                                     authority=getattr(self.shard, "authority", None), now=0.0, row_base=getattr(self.shard, "signal_base", self.shard.cfg.doc_base))
         else:       # BM25 order is the fused order
             fu_s, fu_i = bm_s[:, :cfg.n_rerank].contiguous(), bm_i[:, :cfg.n_rerank].contiguous()
         if cfg.rerank:

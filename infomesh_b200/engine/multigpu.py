@@ -1,0 +1,280 @@
+"""Document-sharded serving over every GPU of a node: ``[gpu] devices = N`` (SURVEY §5 "scale-up inside a node").
+
+The reference serves one process per node and scales by adding peers (infomesh/services.py:70-140 builds one store, one
+vector index); a B200 node has 8 GPUs behind one NVSwitch, so the product path here is ONE front object with the
+``GpuSearchIndex`` interface and one worker process per GPU:
+
+* every worker opens the same ``LocalStore`` read-only, tokenises the WHOLE store once (global vocabulary, document
+  frequencies and average length -- BM25 scores are then identical to a single-GPU index), keeps the postings, vectors
+  and passages of its own contiguous document range ``[rank * per, (rank + 1) * per)`` in HBM, and joins an NCCL group
+  for the bootstrap of the symmetric heaps;
+* a search is a collective: the front hands the same query batch to every worker, each runs the fused pipeline
+  (local BM25 + dense top-k pushed into every peer's heap, merge, RRF, passages pulled from the owning GPU, data-parallel
+  cross-encoder, logit all-gather, final selection) and returns host arrays; rank 0's scores/rows are the answer, every
+  rank contributes doc ids and K11 passage spans for the rows it owns;
+* the front formats hits through its own store handle (``gpu_index.format_hits``).
+
+Control plane: one duplex pipe per worker (``multiprocessing`` spawn context -- CUDA-safe); requests are fanned out before
+any reply is read so the ranks enter the collective together; a worker that dies or misses its deadline marks the front
+unhealthy and searches return empty until ``rebuild()`` respawns the group (the caller -- services / MCP -- falls back to
+the CPU store exactly as it does when no GPU index exists).
+
+``index_factory`` ("package.module:callable") replaces ``GpuSearchIndex`` inside the workers; the CPU test-suite uses it
+to exercise the process plumbing and the merge without a GPU."""
+from __future__ import annotations
+
+import importlib
+import multiprocessing as mp
+import os
+import socket
+import threading
+import time
+from typing import Any
+
+import numpy as np
+
+from infomesh_b200.utils.log import get_logger
+
+logger = get_logger(__name__)
+
+READY_TIMEOUT_S = 1800.0
+CALL_TIMEOUT_S = 120.0
+AUTO_DOCS_PER_GPU = 250_000
+
+
+def _free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _resolve(path: str):
+    mod, _, name = path.partition(":")
+    return getattr(importlib.import_module(mod), name)
+
+
+def _default_factory(store_path: str, rank: int, world: int, kwargs: dict):
+    from infomesh_b200.engine.gpu_index import GpuSearchIndex
+    from infomesh_b200.index.local_store import LocalStore
+    from infomesh_b200.parallel import dist as D
+
+    D.init()
+    store = LocalStore(store_path)
+    return GpuSearchIndex(store, device=f"cuda:{rank}", shard=(rank, world), **kwargs)
+
+
+def _worker_main(rank: int, world: int, port: int, conn, store_path: str, kwargs: dict, factory: str | None) -> None:
+    """Entry point of one per-GPU worker process."""
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    try:
+        make = _resolve(factory) if factory else _default_factory
+        index = make(store_path, rank, world, dict(kwargs))
+        n = index.rebuild()
+        conn.send(("ready", {"rank": rank, "documents": int(n), "stats": _plain(index.stats())}))
+    except Exception as exc:  # noqa: BLE001 -- the front must learn why the worker never became ready
+        conn.send(("failed", f"{type(exc).__name__}: {exc}"))
+        return
+    while True:
+        try:
+            op, arg = conn.recv()
+        except (EOFError, OSError):
+            break
+        try:
+            if op == "search":
+                conn.send(("ok", index.search_arrays(arg)))
+            elif op == "rebuild":
+                conn.send(("ok", int(index.rebuild())))
+            elif op == "stats":
+                conn.send(("ok", _plain(index.stats())))
+            elif op == "close":
+                conn.send(("ok", None))
+                break
+            else:
+                conn.send(("error", f"unknown op {op!r}"))
+        except Exception as exc:  # noqa: BLE001
+            conn.send(("error", f"{type(exc).__name__}: {exc}"))
+    closer = getattr(index, "close", None)
+    if closer:
+        closer()
+    try:
+        from infomesh_b200.parallel import dist as D
+
+        D.shutdown()
+    except Exception:  # noqa: BLE001
+        pass
+
+
+def _plain(obj: Any) -> Any:
+    """Stats dictionaries cross a pipe: keep them to builtin types."""
+    if isinstance(obj, dict):
+        return {str(k): _plain(v) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return [_plain(v) for v in obj]
+    if isinstance(obj, (np.integer,)):
+        return int(obj)
+    if isinstance(obj, (np.floating,)):
+        return float(obj)
+    return obj if isinstance(obj, (str, int, float, bool, type(None))) else str(obj)
+
+
+class MultiGpuSearchIndex:
+    """``GpuSearchIndex`` interface (``rebuild`` / ``search`` / ``search_many`` / ``stats`` / ``close``) over N worker
+    processes, one per GPU."""
+
+    def __init__(self, store: Any, *, devices: int, store_path: str | None = None, query_batch: int = 64,
+                 index_factory: str | None = None, call_timeout: float = CALL_TIMEOUT_S, ready_timeout: float = READY_TIMEOUT_S,
+                 **index_kwargs):
+        if devices < 2:
+            raise ValueError("MultiGpuSearchIndex needs devices >= 2 (use GpuSearchIndex for one GPU)")
+        if query_batch % devices:
+            raise ValueError(f"query_batch {query_batch} must be a multiple of devices {devices} (data-parallel reranker)")
+        self.store, self.world, self.nq = store, int(devices), int(query_batch)
+        self.store_path = str(store_path or getattr(store, "path", None) or getattr(store, "db_path", ""))
+        self._factory, self._kwargs = index_factory, dict(index_kwargs, query_batch=query_batch)
+        self._call_timeout, self._ready_timeout = float(call_timeout), float(ready_timeout)
+        self._procs: list[mp.Process] = []
+        self._conns: list[Any] = []
+        self._lock = threading.Lock()           # one collective in flight: the pipes are not multiplexed
+        self._worker_stats: list[dict] = []
+        self.healthy = False
+        self.built_at = 0.0
+        self.build_seconds = 0.0
+
+    # ------------------------------------------------------------------ lifecycle
+    def _spawn(self) -> None:
+        ctx = mp.get_context("spawn")
+        port = _free_port()
+        for rank in range(self.world):
+            parent, child = ctx.Pipe(duplex=True)
+            p = ctx.Process(target=_worker_main, name=f"infomesh-gpu{rank}", daemon=True,
+                            args=(rank, self.world, port, child, self.store_path, self._kwargs, self._factory))
+            p.start()
+            child.close()
+            self._procs.append(p)
+            self._conns.append(parent)
+
+    def _collect(self, timeout: float) -> list[Any]:
+        """One reply per worker, in rank order, all within ``timeout`` seconds of now."""
+        deadline = time.monotonic() + timeout
+        out = []
+        for rank, conn in enumerate(self._conns):
+            left = deadline - time.monotonic()
+            if left <= 0 or not conn.poll(left):
+                alive = self._procs[rank].is_alive()
+                raise TimeoutError(f"GPU worker {rank} {'did not answer in time' if alive else 'exited'}")
+            tag, payload = conn.recv()
+            if tag in ("failed", "error"):
+                raise RuntimeError(f"GPU worker {rank}: {payload}")
+            out.append(payload)
+        return out
+
+    def rebuild(self) -> int:
+        """(Re)spawn the worker group if needed and rebuild every shard.  Returns the total document count."""
+        t0 = time.time()
+        with self._lock:
+            try:
+                if self.healthy:
+                    for conn in self._conns:
+                        conn.send(("rebuild", None))
+                    counts = self._collect(self._ready_timeout)
+                    n = int(sum(counts))
+                else:
+                    self._teardown()
+                    self._spawn()
+                    ready = self._collect(self._ready_timeout)
+                    self._worker_stats = [r["stats"] for r in ready]
+                    n = int(sum(r["documents"] for r in ready))
+                self.healthy = True
+            except Exception as exc:  # noqa: BLE001
+                logger.error("multigpu_rebuild_failed", error=str(exc))
+                self._teardown()
+                raise
+        self.n_docs = n
+        self.built_at, self.build_seconds = time.time(), time.time() - t0
+        logger.info("multigpu_index_built", docs=n, gpus=self.world, seconds=round(self.build_seconds, 2))
+        return n
+
+    def _teardown(self) -> None:
+        for conn in self._conns:
+            try:
+                conn.send(("close", None))
+            except Exception:  # noqa: BLE001
+                pass
+        for p in self._procs:
+            p.join(timeout=10)
+            if p.is_alive():
+                p.terminate()       # exact child handle, never a pattern
+                p.join(timeout=5)
+        for conn in self._conns:
+            conn.close()
+        self._procs, self._conns, self.healthy = [], [], False
+
+    def close(self) -> None:
+        with self._lock:
+            self._teardown()
+
+    # ------------------------------------------------------------------ queries
+    def search_many(self, queries: list[str], k: int = 10) -> list[list[dict[str, object]]]:
+        from infomesh_b200.engine.gpu_index import format_hits, merge_shard_arrays
+
+        if not self.healthy or not queries:
+            return [[] for _ in queries]
+        out: list[list[dict[str, object]]] = []
+        for a in range(0, len(queries), self.nq):
+            chunk = queries[a:a + self.nq]
+            with self._lock:
+                if not self.healthy:
+                    out.extend([] for _ in chunk)
+                    continue
+                try:
+                    for conn in self._conns:          # fan out first: the ranks meet inside the fused exchange
+                        conn.send(("search", chunk))
+                    parts = self._collect(self._call_timeout)
+                except Exception as exc:  # noqa: BLE001
+                    logger.error("multigpu_search_failed", error=str(exc))
+                    self._teardown()                  # a rank is gone: peers would spin on its flags forever
+                    out.extend([] for _ in chunk)
+                    continue
+            out.extend(format_hits(self.store, chunk, k, merge_shard_arrays(parts)) if parts and parts[0] else [[] for _ in chunk])
+        return out
+
+    def search(self, query: str, k: int = 10) -> list[dict[str, object]]:
+        return self.search_many([query], k)[0]
+
+    def stats(self) -> dict[str, object]:
+        per_rank = self._worker_stats
+        if self.healthy:
+            with self._lock:
+                try:
+                    for conn in self._conns:
+                        conn.send(("stats", None))
+                    per_rank = self._worker_stats = self._collect(min(self._call_timeout, 10.0))
+                except Exception as exc:  # noqa: BLE001
+                    logger.warning("multigpu_stats_failed", error=str(exc))
+        return {"gpus": self.world, "healthy": self.healthy, "documents": getattr(self, "n_docs", 0), "built_at": self.built_at,
+                "build_seconds": round(self.build_seconds, 2), "query_batch": self.nq,
+                "hbm_bytes": int(sum(int(s.get("hbm_bytes", 0)) for s in per_rank)), "per_rank": per_rank}
+
+
+def make_index(store: Any, gcfg: Any = None, **overrides):
+    """The serving surfaces' single entry point: ``[gpu] devices`` > 1 (or 0 = all visible, when more than one GPU is
+    visible and the store is large enough to shard) -> :class:`MultiGpuSearchIndex`, else ``GpuSearchIndex``."""
+    from infomesh_b200.engine.gpu_index import GpuSearchIndex, gpu_index_kwargs
+
+    kw = dict(gpu_index_kwargs(gcfg), **overrides)
+    want = int(getattr(gcfg, "devices", 1) or 0) if gcfg is not None else 1
+    if want != 1:
+        import torch
+
+        visible = torch.cuda.device_count() if torch.cuda.is_available() else 0
+        n_docs = int(store.get_stats().get("document_count", 0)) if hasattr(store, "get_stats") else 0
+        # auto (0): one GPU per AUTO_DOCS_PER_GPU documents -- a small store gains nothing from 8 copies of the models
+        n = min(visible, max(1, n_docs // AUTO_DOCS_PER_GPU)) if want == 0 else min(want, visible)
+        nq = int(kw.get("query_batch", getattr(gcfg, "query_batch", 64)))
+        while n > 1 and (nq % n or n_docs < 2 * n):
+            n -= 1
+        if n > 1:
+            kw.setdefault("query_batch", nq)
+            return MultiGpuSearchIndex(store, devices=n, **kw)
+    dev = int(getattr(gcfg, "device", 0)) if gcfg is not None else 0
+    return GpuSearchIndex(store, device=f"cuda:{dev}", **kw)

@@ -56,10 +56,10 @@ def attach_gpu_index(ctx: AppContext) -> Any | None:
 
         if not torch.cuda.is_available() or not _native.available():
             return None
-        from infomesh_b200.engine.gpu_index import GpuSearchIndex, gpu_index_kwargs
+        from infomesh_b200.engine.multigpu import make_index
 
-        gi = GpuSearchIndex(ctx.store, device=f"cuda:{getattr(gcfg, 'device', 0)}", rerank=getattr(gcfg, "rerank", True),
-                            query_batch=getattr(gcfg, "query_batch", 64), **gpu_index_kwargs(gcfg))
+        # [gpu] devices > 1 (or 0 = all visible): one worker process per GPU behind the same interface
+        gi = make_index(ctx.store, gcfg, rerank=getattr(gcfg, "rerank", True), query_batch=getattr(gcfg, "query_batch", 64))
         gi.rebuild()
         ctx.gpu_index = gi
     except Exception as exc:  # noqa: BLE001

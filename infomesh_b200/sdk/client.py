@@ -63,15 +63,17 @@ class InfoMeshClient:
         self._data_dir.mkdir(parents=True, exist_ok=True)
         self._ctx = AppContext(cfg)
         if self._gpu:
-            from infomesh_b200.engine.gpu_index import GpuSearchIndex, gpu_index_kwargs
+            from infomesh_b200.engine.multigpu import make_index
 
-            self._gpu_index = GpuSearchIndex(self._ctx.store, **gpu_index_kwargs(getattr(cfg, "gpu", None)))
+            self._gpu_index = make_index(self._ctx.store, getattr(cfg, "gpu", None))
             self._gpu_index.rebuild()
 
     def close(self) -> None:
         if self._ctx is not None:
             self._ctx.close()
             self._ctx = None
+        if self._gpu_index is not None and hasattr(self._gpu_index, "close"):
+            self._gpu_index.close()
         self._gpu_index = None
 
     def __enter__(self) -> "InfoMeshClient":

@@ -53,3 +53,14 @@ def test_fused_tp_encoder_two_ranks():
 def test_context_parallel_attention_in_kernel_two_ranks():
     text = _run("gpu_check_cp.py", port=29615)
     assert "ALL OK" in text, text[-3000:]
+
+
+def test_multigpu_product_serving_matches_single_gpu():
+    """[gpu] devices = 2: worker-per-GPU serving returns the single-GPU hit lists (scripts/gpu_check_multigpu_serving.py)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = subprocess.run([sys.executable, str(ROOT / "scripts" / "gpu_check_multigpu_serving.py"), "--gpus", "2", "--docs", "6000",
+                          "--queries", "128", "--full"], capture_output=True, text=True, timeout=600, cwd=str(ROOT),
+                         env=dict(os.environ, PYTHONPATH=str(ROOT)))
+    text = out.stdout + out.stderr
+    assert out.returncode == 0 and "ALL OK" in text, text[-3000:]
