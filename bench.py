@@ -128,6 +128,10 @@ def main() -> int:
                     help="cross-encoder GEMM precision.  mxfp8 (default): block-scaled e4m3 x e4m3 with ue8m0 scales per 32 "
                          "(tcgen05 kind::mxf8f6f4.block_scale), fp32 accumulation, quantisers fused into LayerNorm / attention "
                          "/ GELU epilogues; bf16: round-1 configuration")
+    ap.add_argument("--dense", choices=["bf16", "fp8"], default=os.environ.get("INFOMESH_B200_BENCH_DENSE", "bf16"),
+                    help="dense shard storage streamed by the similarity search.  fp8: e4m3 rows + per-row scale (half the HBM "
+                         "bytes), 32-wide over-fetch re-scored exactly against the bf16 rows; `dense_recall_vs_bf16` reports "
+                         "the agreement with the bf16 search on the timed batches")
     ap.add_argument("--rerank-chunks", type=int, default=1, help="cross-encoder sub-batches per step (L2 residency)")
     ap.add_argument("--pipeline", choices=["on", "off"], default="on",
                     help="on: `value` keeps two batches in flight (retrieval of batch i+1 overlaps the cross-encoder of "
@@ -207,7 +211,8 @@ def main() -> int:
     precision = args.precision if args.impl == "fused" else "bf16"
     hcfg = HybridConfig(nq=args.batch, pair_seq=args.pair_seq, rerank=not args.no_rerank, backend=args.impl,
                         use_graph=not args.no_graph, exchange=args.exchange, varlen=not args.no_varlen,
-                        rerank_chunks=args.rerank_chunks, precision=precision, strict_graph=True)
+                        rerank_chunks=args.rerank_chunks, precision=precision, strict_graph=True,
+                        dense_dtype=args.dense if args.impl == "fused" else "bf16")
     dps = per if ptabs is not None else (n_global if world > 1 else n_local)
     ekw = dict(docs_per_shard=dps, passage_tables=ptabs, passage_len=scfg.passage_len) if ptabs is not None else dict(docs_per_shard=dps)
     eng = HybridEngine(shard, hcfg, **ekw)
@@ -339,6 +344,19 @@ def main() -> int:
         st = eng.stage_times()
         roof = {}
         vec_bytes = shard.vectors.numel() * shard.vectors.element_size()
+        if hcfg.dense_dtype == "fp8":
+            vec_bytes = shard.vectors_f8.numel() + shard.vec_scale.numel() * 4
+            # agreement of the fp8 (over-fetch + exact re-score) search with the exact bf16 search, same queries
+            from infomesh_b200.ops import search as S_
+
+            q_emb = eng._encode()
+            f_s, f_i = eng._dense_local(q_emb)
+            b_s, b_i = S_.sim_topk(q_emb, shard.vectors, hcfg.k_fetch, alive=shard.alive, id_offset=shard.cfg.doc_base)
+            torch.cuda.synchronize()
+            fi, bi = f_i.cpu(), b_i.cpu()
+            rec = [len(set(x[:10].tolist()) & set(y[:10].tolist())) / 10.0 for x, y in zip(fi, bi)]
+            extras["dense_recall_vs_bf16"] = {"recall_at_10": round(sum(rec) / len(rec), 4), "top1_equal": round(float((fi[:, 0] == bi[:, 0]).float().mean()), 4),
+                                              "k_fetch_fp8": 32, "note": "this rank's shard; fp8 pass over-fetches 32 and re-scores against bf16 rows"}
         if st["dense_local"] > 0:
             gbs = vec_bytes / (st["dense_local"] * 1e-3) / 1e9
             roof["dense_local"] = {"bytes": vec_bytes, "achieved_gbs": round(gbs, 1), "frac_of_hbm": round(gbs / peaks["hbm_gbs"], 3)}
@@ -429,7 +447,8 @@ def main() -> int:
             pad_note += f" (mean real pair length {mean_len:.1f})"
     dtype = {"bf16": "bf16",
              "mxfp8": "mxfp8 cross-encoder GEMMs (e4m3 x e4m3, ue8m0 block scales per 32, fp32 accumulate); bf16 encoder, "
-                      "attention, norms, residual stream and dense index",
+                      "attention, norms, residual stream" + (" and dense index" if args.dense == "bf16" else "; dense index e4m3 + per-row "
+                      "scale with exact bf16 re-scoring of a 32-wide over-fetch"),
              "fp8": "fp8-e4m3 per-row-scaled projections in the cross-encoder (fp32 accumulate), bf16 elsewhere"}[precision]
     if rank == 0:
         torch_v = extras.get("torch_arm", {}).get("value")
@@ -454,7 +473,7 @@ def main() -> int:
                 "model": "bge-small-en encoder + bge-reranker-base cross-encoder (random-init)",
                 "index_docs": n_global, "dim": 384, "global_batch": B, "seq_len": args.pair_seq,
                 "query_tokens": hcfg.enc_seq, "candidates_per_query": hcfg.n_rerank, "top_k": hcfg.k_out,
-                "rerank": hcfg.rerank, "query_mix": args.query_mix,
+                "rerank": hcfg.rerank, "query_mix": args.query_mix, "dense_shard": hcfg.dense_dtype,
                 "parallelism": f"doc-sharded index x{world} (dense vectors, postings"
                                + (", passage tokens read from the owning GPU over NVLink" if ptabs is not None else
                                   (", passages replicated" if world > 1 else ", passages"))

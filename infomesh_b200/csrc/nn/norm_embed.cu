@@ -450,13 +450,15 @@ tp_argmax_exchange_kernel(const float* __restrict__ val, const int* __restrict__
 // sentence embedding: mode 0 = CLS token, 1 = mean over valid tokens; L2 normalised; one block per sequence
 __global__ void __launch_bounds__(256)
 pool_norm_kernel(const __nv_bfloat16* __restrict__ h, const int* __restrict__ lengths, int seq_len, int H, int mode,
-                 int normalize, __nv_bfloat16* __restrict__ out, float* __restrict__ out_f32) {
+                 int normalize, __nv_bfloat16* __restrict__ out, float* __restrict__ out_f32, uint8_t* __restrict__ out_q8,
+                 float* __restrict__ out_qscale) {
   extern __shared__ float pooled[];
   __shared__ float red[8];
+  __shared__ float redm[8];
   const int b = blockIdx.x;
   const int len = lengths ? max(1, min(lengths[b], seq_len)) : seq_len;
   const __nv_bfloat16* base = h + static_cast<size_t>(b) * seq_len * H;
-  float sq = 0.f;
+  float sq = 0.f, amax = 0.f;
   for (int c = threadIdx.x; c < H; c += blockDim.x) {
     float acc;
     if (mode == 0) {
@@ -468,17 +470,40 @@ pool_norm_kernel(const __nv_bfloat16* __restrict__ h, const int* __restrict__ le
     }
     pooled[c] = acc;
     sq += acc * acc;
+    amax = fmaxf(amax, fabsf(acc));
   }
   sq = warp_sum(sq);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  if ((threadIdx.x & 31) == 0) {
+    red[threadIdx.x >> 5] = sq;
+    redm[threadIdx.x >> 5] = amax;
+  }
   __syncthreads();
-  float tot = 0.f;
-  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i];
+  float tot = 0.f, mx = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) {
+    tot += red[i];
+    mx = fmaxf(mx, redm[i]);
+  }
   const float inv = normalize ? rsqrtf(fmaxf(tot, 1e-24f)) : 1.0f;
+  // e4m3 copy for the fp8 similarity search: power-of-two row scale s (amax / s <= 448), value = q8 * s
+  float q_inv = 1.0f;
+  if (out_q8 != nullptr) {
+    const uint32_t e = ue8m0_from_amax(mx * inv, q_inv);
+    if (threadIdx.x == 0) out_qscale[b] = __uint_as_float(e << 23);
+  }
   for (int c = threadIdx.x; c < H; c += blockDim.x) {
     const float v = pooled[c] * inv;
     if (out) out[static_cast<size_t>(b) * H + c] = __float2bfloat16(v);
     if (out_f32) out_f32[static_cast<size_t>(b) * H + c] = v;
+  }
+  if (out_q8 != nullptr) {
+    for (int c = threadIdx.x * 4; c < H; c += blockDim.x * 4) {   // H % 4 == 0 (checked on the host)
+      // quantise what the bf16 copy holds, so both representations describe the same vector
+      const float v0 = __bfloat162float(__float2bfloat16(pooled[c] * inv)), v1 = __bfloat162float(__float2bfloat16(pooled[c + 1] * inv));
+      const float v2 = __bfloat162float(__float2bfloat16(pooled[c + 2] * inv)), v3 = __bfloat162float(__float2bfloat16(pooled[c + 3] * inv));
+      *reinterpret_cast<uint32_t*>(out_q8 + static_cast<size_t>(b) * H + c) = pack_e4m3x4(v0 * q_inv, v1 * q_inv, v2 * q_inv, v3 * q_inv);
+    }
   }
 }
 
@@ -788,11 +813,12 @@ IM_API int im_tp_argmax_exchange(const float* val, const int* idx, int n_rows, v
 }
 
 IM_API int im_pool_norm(const void* h, const int* lengths, int batch, int seq_len, int H, int mode, int normalize,
-                        void* out_bf16, float* out_f32, void* stream) {
+                        void* out_bf16, float* out_f32, void* stream, void* out_q8, float* out_qscale) {
   using namespace im;
   if (batch <= 0) return 0;
+  if (out_q8 != nullptr && (H % 4 != 0 || out_qscale == nullptr)) return set_error("im_pool_norm", "fp8 output needs H % 4 == 0 and a scale buffer");
   pool_norm_kernel<<<batch, 256, H * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>(
-      (const __nv_bfloat16*)h, lengths, seq_len, H, mode, normalize, (__nv_bfloat16*)out_bf16, out_f32);
+      (const __nv_bfloat16*)h, lengths, seq_len, H, mode, normalize, (__nv_bfloat16*)out_bf16, out_f32, (uint8_t*)out_q8, out_qscale);
   IM_LAUNCH_OK("pool_norm_kernel");
   return 0;
 }

@@ -59,16 +59,23 @@ __device__ __forceinline__ void list_insert(volatile float* lv, volatile int* li
 
 // NPAD = queries padded to the MMA N granule (16); documents are the MMA M dimension so that every epilogue
 // thread owns ONE document row and compares its NPAD scores against per-query thresholds held in smem.
-template <int NPAD>
+//
+// F8: the shard is e4m3 with one fp32 scale per document row (half the HBM bytes of bf16 -- the pass is HBM-bound, so
+// about twice the documents per second); queries arrive as e4m3 + one scale each (emitted by pool_norm).  A k-block is
+// still 128 bytes of K (128 elements instead of 64), the MMA is kind::f8f6f4 (K = 32 per instruction, same 32-byte
+// descriptor step), and the epilogue turns the raw accumulator into the true score acc * d_scale[doc] * q_scale[j]
+// before the threshold filter, so lists, thresholds and the merge are unchanged.
+template <int NPAD, bool F8>
 __global__ void __launch_bounds__(kSimThreads, 1)
 sim_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_d, int nq,
                 int n_docs, int dim, int stages, int ktop, const uint8_t* __restrict__ alive,
                 float* __restrict__ out_scores, int* __restrict__ out_ids, const float* __restrict__ thr_init,
-                int thr_stride) {
+                int thr_stride, const float* __restrict__ d_scale, const float* __restrict__ q_scale) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  const int num_kb = dim / kSimBK;
+  constexpr int kBKe = F8 ? 2 * kSimBK : kSimBK;   // K elements per 128-byte k-block
+  const int num_kb = dim / kBKe;
   constexpr int kQTileBytes = NPAD * kSimBK * 2;
   uint8_t* smem_q = smem;                          // num_kb tiles of [NPAD x 64] bf16 (resident)
   uint8_t* smem_d = smem + num_kb * kQTileBytes;   // ring of [128 docs x 64] tiles; NPAD*128 B keeps 1024 alignment
@@ -79,7 +86,8 @@ sim_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float* thr = reinterpret_cast<float*>(tmem_slot + 2);   // [NPAD] CTA-wide lower bound of the K-th best per query
-  float* list_v = reinterpret_cast<float*>(thr + NPAD);     // [4 warps][nq][ktop]
+  float* qsc = thr + NPAD;                                  // [NPAD] per-query dequantisation scale (F8)
+  float* list_v = reinterpret_cast<float*>(qsc + NPAD);     // [4 warps][nq][ktop]
   int* list_i = reinterpret_cast<int*>(list_v + 4 * nq * ktop);
 
   constexpr uint32_t kTmemCols = (2 * NPAD) < 32 ? 32 : (2 * NPAD);
@@ -115,6 +123,7 @@ sim_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       if (b > -CUDART_INF_F && b == b) t0 = __uint_as_float(b > 0.f ? __float_as_uint(b) - 1u : (b < 0.f ? __float_as_uint(b) + 1u : 0x80000001u));
     }
     thr[i] = t0;
+    qsc[i] = (F8 && i < nq) ? q_scale[i] : 1.0f;
   }
   for (int i = threadIdx.x; i < 4 * nq * ktop; i += kSimThreads) {
     list_v[i] = -CUDART_INF_F;
@@ -128,14 +137,14 @@ sim_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   if (warp == 0) {
     if (lane == 0) {
       mbar_expect_tx(q_bar, num_kb * kQTileBytes);
-      for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(smem_q + kb * kQTileBytes, &tmap_q, q_bar, kb * kSimBK, 0);
+      for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(smem_q + kb * kQTileBytes, &tmap_q, q_bar, kb * kBKe, 0);
       const uint64_t pol = l2_policy_evict_first();  // the shard is streamed exactly once
       uint32_t stage = 0, phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], kSimTileBytes);
-          tma_load_2d_hint(smem_d + stage * kSimTileBytes, &tmap_d, &full_bar[stage], kb * kSimBK, t * kSimBM, pol);
+          tma_load_2d_hint(smem_d + stage * kSimTileBytes, &tmap_d, &full_bar[stage], kb * kBKe, t * kSimBM, pol);
           if (++stage == (uint32_t)stages) {
             stage = 0;
             phase ^= 1;
@@ -145,7 +154,7 @@ sim_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(kSimBM, NPAD);
+      constexpr uint32_t idesc = F8 ? umma_idesc_f8(kSimBM, NPAD) : umma_idesc_f16(kSimBM, NPAD);
       mbar_wait(q_bar, 0);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       const uint32_t q0 = smem_u32(smem_q);
@@ -159,9 +168,12 @@ sim_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           const uint32_t a0 = smem_u32(smem_d + stage * kSimTileBytes);  // documents: A operand
           const uint32_t b0 = q0 + kb * kQTileBytes;                      // queries:   B operand
 #pragma unroll
-          for (int k = 0; k < kSimBK / 16; ++k)
-            umma_bf16(d_tmem, umma_desc_k_sw128(a0 + k * 32), umma_desc_k_sw128(b0 + k * 32), idesc,
-                      (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < kSimBK / 16; ++k) {   // 4 x 32 bytes of K: 16 bf16 or 32 e4m3 elements per MMA
+            if constexpr (F8)
+              umma_f8(d_tmem, umma_desc_k_sw128(a0 + k * 32), umma_desc_k_sw128(b0 + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+            else
+              umma_bf16(d_tmem, umma_desc_k_sw128(a0 + k * 32), umma_desc_k_sw128(b0 + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
           umma_commit(&empty_bar[stage]);
           if (++stage == (uint32_t)stages) {
             stage = 0;
@@ -191,6 +203,7 @@ sim_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const int doc = t * kSimBM + static_cast<int>(quad * 32u + lane);
       bool doc_ok = doc < n_docs;
       if (doc_ok && alive != nullptr) doc_ok = alive[doc] != 0;
+      const float ds = (F8 && doc < n_docs) ? d_scale[doc] : 1.0f;
 #pragma unroll
       for (int c = 0; c < NPAD; c += kChunk) {
         uint32_t v[kChunk];
@@ -199,7 +212,11 @@ sim_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         tmem_ld_wait();
         if (doc_ok) {
 #pragma unroll
-          for (int i = 0; i < kChunk; ++i) rmax[c + i] = fmaxf(rmax[c + i], __uint_as_float(v[i]));
+          for (int i = 0; i < kChunk; ++i) {
+            float x = __uint_as_float(v[i]);
+            if constexpr (F8) x *= ds * qsc[c + i];
+            rmax[c + i] = fmaxf(rmax[c + i], x);
+          }
         }
       }
       tc_fence_before();
@@ -234,12 +251,23 @@ sim_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const int doc = t * kSimBM + static_cast<int>(quad * 32u + lane);
       bool doc_ok = doc < n_docs;
       if (doc_ok && alive != nullptr) doc_ok = alive[doc] != 0;
+      const float ds = (F8 && doc < n_docs) ? d_scale[doc] : 1.0f;
 #pragma unroll 1
       for (int c = 0; c < NPAD; c += kChunk) {
         uint32_t v[kChunk];
         if constexpr (kChunk == 32) tmem_ld_32x32b_x32(tmem_base + ((quad * 32u) << 16) + acc * NPAD + c, v);
         else tmem_ld_32x32b_x16(tmem_base + ((quad * 32u) << 16) + acc * NPAD + c, v);
         tmem_ld_wait();
+        if constexpr (F8) {   // raw accumulator -> true score
+#pragma unroll
+          for (int i = 0; i < kChunk; i += 4) {
+            const float4 qs4 = *reinterpret_cast<const float4*>(qsc + c + i);
+            v[i] = __float_as_uint(__uint_as_float(v[i]) * ds * qs4.x);
+            v[i + 1] = __float_as_uint(__uint_as_float(v[i + 1]) * ds * qs4.y);
+            v[i + 2] = __float_as_uint(__uint_as_float(v[i + 2]) * ds * qs4.z);
+            v[i + 3] = __float_as_uint(__uint_as_float(v[i + 3]) * ds * qs4.w);
+          }
+        }
 #pragma unroll
         for (int g = 0; g < kChunk; g += 8) {
           if (c + g >= nq) break;  // warp-uniform: padded query columns
@@ -468,14 +496,16 @@ topk_merge_kernel(const float* __restrict__ cand_scores, const int64_t* __restri
 }  // namespace im
 
 // Per-CTA candidate lists: out_scores/out_ids are [grid, nq, ktop]; returns grid (CTA count) or <0.
-template <int NPAD>
+template <int NPAD, bool F8 = false>
 static int launch_sim(const void* Q, const void* D, int nq, int n_docs, int dim, int ldq, int ldd, int ktop,
                       const uint8_t* alive, float* out_scores, int* out_ids, int max_ctas, const float* thr_init,
-                      int thr_stride, cudaStream_t s) {
+                      int thr_stride, cudaStream_t s, const float* d_scale = nullptr, const float* q_scale = nullptr) {
   using namespace im;
-  const int num_kb = dim / kSimBK;
+  constexpr int kEB = F8 ? 1 : 2;                  // bytes per element
+  constexpr int kBKe = 128 / kEB;                  // elements per 128-byte k-block
+  const int num_kb = dim / kBKe;
   const int q_bytes = num_kb * NPAD * kSimBK * 2;
-  const int misc = 1024 /*align*/ + 512 /*barriers*/ + NPAD * 4 + 4 * nq * ktop * 8;
+  const int misc = 1024 /*align*/ + 512 /*barriers*/ + NPAD * 8 + 4 * nq * ktop * 8;
   int stages = (kSimMaxSmem - misc - q_bytes) / kSimTileBytes;
   if (stages > 12) stages = 12;
   if (stages < 2) return set_error("im_sim_topk", "not enough shared memory for the document ring");
@@ -485,11 +515,11 @@ static int launch_sim(const void* Q, const void* D, int nq, int n_docs, int dim,
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   if (grid < 1) grid = 1;
   CUtensorMap tq, td;
-  if (get_tmap_2d(&tq, Q, nq, dim, static_cast<uint64_t>(ldq) * 2, NPAD, kSimBK, 2, TMAP_SW_128)) return -1;
-  if (get_tmap_2d(&td, D, n_docs, dim, static_cast<uint64_t>(ldd) * 2, kSimBM, kSimBK, 2, TMAP_SW_128)) return -1;
-  IM_CUDA_OK(cudaFuncSetAttribute(sim_topk_kernel<NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-  sim_topk_kernel<NPAD><<<grid, kSimThreads, smem_bytes, s>>>(tq, td, nq, n_docs, dim, stages, ktop, alive, out_scores,
-                                                               out_ids, thr_init, thr_stride);
+  if (get_tmap_2d(&tq, Q, nq, dim, static_cast<uint64_t>(ldq) * kEB, NPAD, kBKe, kEB, TMAP_SW_128)) return -1;
+  if (get_tmap_2d(&td, D, n_docs, dim, static_cast<uint64_t>(ldd) * kEB, kSimBM, kBKe, kEB, TMAP_SW_128)) return -1;
+  IM_CUDA_OK(cudaFuncSetAttribute(sim_topk_kernel<NPAD, F8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  sim_topk_kernel<NPAD, F8><<<grid, kSimThreads, smem_bytes, s>>>(tq, td, nq, n_docs, dim, stages, ktop, alive, out_scores,
+                                                                   out_ids, thr_init, thr_stride, d_scale, q_scale);
   IM_LAUNCH_OK("sim_topk_kernel");
   return grid;
 }
@@ -506,6 +536,100 @@ IM_API int im_sim_topk(const void* Q, const void* D, int nq, int n_docs, int dim
   if (nq <= 32) return launch_sim<32>(Q, D, nq, n_docs, dim, ldq, ldd, ktop, alive, out_scores, out_ids, max_ctas, thr_init, thr_stride, s);
   if (nq <= 64) return launch_sim<64>(Q, D, nq, n_docs, dim, ldq, ldd, ktop, alive, out_scores, out_ids, max_ctas, thr_init, thr_stride, s);
   return launch_sim<128>(Q, D, nq, n_docs, dim, ldq, ldd, ktop, alive, out_scores, out_ids, max_ctas, thr_init, thr_stride, s);
+}
+
+// e4m3 shard + per-row scales (see the F8 note above the kernel).  Q8 / D8: row-major e4m3 bytes, ld in elements.
+IM_API int im_sim_topk_f8(const void* Q8, const float* q_scale, const void* D8, const float* d_scale, int nq, int n_docs,
+                          int dim, int ldq, int ldd, int ktop, const uint8_t* alive, float* out_scores, int* out_ids,
+                          int max_ctas, const float* thr_init, int thr_stride, void* stream) {
+  using namespace im;
+  if (nq < 1 || nq > 128) return set_error("im_sim_topk_f8", "nq must be in [1,128]");
+  if (dim % 128 != 0 || dim > 1024) return set_error("im_sim_topk_f8", "dim must be a multiple of 128 and <= 1024");
+  if (ldq % 16 != 0 || ldd % 16 != 0) return set_error("im_sim_topk_f8", "row strides must be multiples of 16 bytes");
+  if (ktop < 0 || ktop > 32) return set_error("im_sim_topk_f8", "ktop must be in [0,32]");
+  if (q_scale == nullptr || d_scale == nullptr) return set_error("im_sim_topk_f8", "scales are required");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+#define IM_SIM_F8(NP) launch_sim<NP, true>(Q8, D8, nq, n_docs, dim, ldq, ldd, ktop, alive, out_scores, out_ids, max_ctas, thr_init, thr_stride, s, d_scale, q_scale)
+  if (nq <= 16) return IM_SIM_F8(16);
+  if (nq <= 32) return IM_SIM_F8(32);
+  if (nq <= 64) return IM_SIM_F8(64);
+  return IM_SIM_F8(128);
+#undef IM_SIM_F8
+}
+
+// Exact re-scoring of a candidate list against the bf16 rows (fp8 retrieval over-fetches, this restores the fp32-accurate
+// order): one CTA per query, warp w scores candidate w (<= 32 candidates), warp 0 then ranks them (score desc, id asc)
+// and writes the best k_out.  cand ids are LOCAL rows (int64, -1 = empty); out ids = row + id_offset.
+namespace im {
+__global__ void __launch_bounds__(1024)
+rescore_topk_kernel(const __nv_bfloat16* __restrict__ Q, int ldq, const __nv_bfloat16* __restrict__ D, int ldd, int dim,
+                    const int64_t* __restrict__ cand, int n_cand, int k_out, int64_t id_offset,
+                    float* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
+  __shared__ float sc[32];
+  __shared__ long long id[32];
+  const int q = blockIdx.x;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (static_cast<int>(warp) < n_cand) {
+    const int64_t row = cand[static_cast<size_t>(q) * n_cand + warp];
+    float acc = 0.f;
+    if (row >= 0) {
+      const uint4* qv = reinterpret_cast<const uint4*>(Q + static_cast<size_t>(q) * ldq);
+      const uint4* dv = reinterpret_cast<const uint4*>(D + static_cast<size_t>(row) * ldd);
+      for (int c = lane; c < dim / 8; c += 32) {
+        const uint4 a = qv[c], b = dv[c];
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 x = unpack_bf16x2(aw[i]), y = unpack_bf16x2(bw[i]);
+          acc = fmaf(x.x, y.x, acc);
+          acc = fmaf(x.y, y.y, acc);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    }
+    if (lane == 0) {
+      sc[warp] = row >= 0 ? acc : -CUDART_INF_F;
+      id[warp] = row;
+    }
+  } else if (warp < 32 && lane == 0) {
+    sc[warp] = -CUDART_INF_F;
+    id[warp] = -1;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const float s = sc[lane];
+    const long long d = id[lane];
+    int rank = 0;
+    for (int j = 0; j < 32; ++j) {
+      const float o = sc[j];
+      const long long od = id[j];
+      rank += (od >= 0 && (o > s || (o == s && (od < d || (od == d && j < static_cast<int>(lane)))))) ? 1 : 0;
+    }
+    if (d < 0) rank = 32;   // empties go last (and are rewritten below)
+    if (rank < k_out) {
+      out_scores[static_cast<size_t>(q) * k_out + rank] = s;
+      out_ids[static_cast<size_t>(q) * k_out + rank] = d + id_offset;
+    }
+    const int live = __popc(__ballot_sync(0xffffffffu, d >= 0));
+    for (int r = live + static_cast<int>(lane); r < k_out; r += 32) {
+      out_scores[static_cast<size_t>(q) * k_out + r] = -CUDART_INF_F;
+      out_ids[static_cast<size_t>(q) * k_out + r] = -1;
+    }
+  }
+}
+}  // namespace im
+
+IM_API int im_rescore_topk(const void* Q, int ldq, const void* D, int ldd, int dim, const int64_t* cand, int nq, int n_cand,
+                           int k_out, int64_t id_offset, float* out_scores, int64_t* out_ids, void* stream) {
+  using namespace im;
+  if (nq <= 0) return 0;
+  if (n_cand < 1 || n_cand > 32 || k_out < 1 || k_out > 32) return set_error("im_rescore_topk", "at most 32 candidates");
+  if (dim % 8 != 0 || ldq % 8 != 0 || ldd % 8 != 0) return set_error("im_rescore_topk", "rows must be 16-byte aligned");
+  rescore_topk_kernel<<<nq, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      (const __nv_bfloat16*)Q, ldq, (const __nv_bfloat16*)D, ldd, dim, cand, n_cand, k_out, id_offset, out_scores, out_ids);
+  IM_LAUNCH_OK("rescore_topk_kernel");
+  return 0;
 }
 
 IM_API int im_topk_merge(const float* cand_scores, const int64_t* cand_ids64, const int* cand_ids32, int P, int nq,

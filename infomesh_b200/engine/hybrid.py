@@ -40,6 +40,7 @@ class HybridConfig:
     pair_seq: int = 128       # <s> q </s></s> passage </s>
     rerank: bool = True
     dense: bool = True        # False: BM25-only retrieval (serving with an encoder that has no checkpoint weights)
+    dense_dtype: str = "bf16"  # "fp8": e4m3 shard + row scales, 32-wide over-fetch re-scored against the bf16 rows (K3)
     rank_signals: bool = False  # BM25-only mode: order candidates with the six-signal rank fuse (K12) instead of raw BM25
     backend: str = "fused"    # "fused" | "torch"
     use_graph: bool = True
@@ -88,6 +89,14 @@ class HybridEngine:
         self.in_terms = torch.full((cfg.nq, cfg.max_terms), -1, **i32)
         self.out_scores = torch.zeros((cfg.nq, cfg.k_out), device=dev, dtype=torch.float32)
         self.out_ids = torch.full((cfg.nq, cfg.k_out), -1, device=dev, dtype=torch.int64)
+        self._f8 = cfg.dense and cfg.dense_dtype == "fp8" and cfg.backend == "fused"
+        if self._f8:
+            if getattr(shard, "vectors_f8", None) is None:
+                from infomesh_b200.ops import nn as N
+
+                shard.vectors_f8, shard.vec_scale = N.quantize_rows_e4m3(shard.vectors)
+            self.q8 = torch.zeros((cfg.nq, shard.vectors.shape[1]), device=dev, dtype=torch.uint8)
+            self.q8_scale = torch.ones((cfg.nq,), device=dev, dtype=torch.float32)
         self._graph = None
         self._graph_failed = False
         self.heap = None
@@ -112,6 +121,8 @@ class HybridEngine:
     def _encode(self):
         if self.cfg.backend == "torch":
             return self.encoder.embed_torch(self.in_enc_ids, self.in_enc_len)
+        if self._f8:
+            return self.encoder.embed(self.in_enc_ids, self.in_enc_len, out_q8=self.q8, out_qscale=self.q8_scale)
         return self.encoder.embed(self.in_enc_ids, self.in_enc_len)
 
     def _dense_local(self, q_emb):
@@ -121,6 +132,10 @@ class HybridEngine:
             v, i = torch.topk(sc.float(), min(cfg.k_fetch, sh.vectors.shape[0]), dim=1)
             return v, i.long() + sh.cfg.doc_base
         push = self.ch_dense if (self.heap is not None and not self._inject_drop) else None
+        if self._f8:
+            # half the HBM bytes per document; q8 / q8_scale were written by the encoder's pooling kernel
+            return S.sim_topk_f8(self.q8, self.q8_scale, sh.vectors_f8, sh.vec_scale, cfg.k_fetch, alive=sh.alive,
+                                 id_offset=sh.cfg.doc_base, push=push, rescore=(q_emb, sh.vectors), k_fetch=32)
         return S.sim_topk(q_emb, sh.vectors, cfg.k_fetch, alive=sh.alive, id_offset=sh.cfg.doc_base, push=push)
 
     def _bm25_local(self):

@@ -287,12 +287,13 @@ class BertModel:
         hcls = G.linear(cls, w.cls_w1, w.cls_b1, act="tanh")
         return G.linear(hcls, w.cls_w2p, w.cls_b2p, out_dtype=torch.float32)[:, 0].contiguous()
 
-    def embed(self, ids, lengths=None) -> torch.Tensor:
-        """Sentence embeddings, L2-normalised bf16 [B, H]."""
+    def embed(self, ids, lengths=None, out_q8=None, out_qscale=None) -> torch.Tensor:
+        """Sentence embeddings, L2-normalised bf16 [B, H].  ``out_q8`` / ``out_qscale``: also emit the e4m3 copy + row
+        scale the fp8 dense search consumes (same pooling kernel, no extra pass)."""
         from infomesh_b200.ops import nn as N
 
         h = self.hidden_states(ids, lengths)
-        return N.pool_norm(h, lengths, self.cfg.pooling, True)
+        return N.pool_norm(h, lengths, self.cfg.pooling, True, out_q8=out_q8, out_qscale=out_qscale)
 
     def score(self, ids, lengths=None, type_ids=None) -> torch.Tensor:
         """Cross-encoder relevance logits fp32 [B] on padded ``[B, S]`` batches.  The last encoder layer computes keys /

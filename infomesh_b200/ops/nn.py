@@ -153,18 +153,47 @@ def gather_rows(x, idx, n):
     return out
 
 
-def pool_norm(h, lengths=None, mode="cls", normalize=True, out=None, out_f32=None):
+def pool_norm(h, lengths=None, mode="cls", normalize=True, out=None, out_f32=None, out_q8=None, out_qscale=None):
+    """Pooled (CLS / mean) and L2-normalised sentence vectors, bf16 ``[B, H]``.  ``out_q8`` (uint8 ``[B, H]``, e4m3 bytes)
+    + ``out_qscale`` (fp32 ``[B]``, power of two): the same vectors quantised for the fp8 similarity search
+    (``ops.search.sim_topk_f8``), emitted by the same kernel -- no separate quantisation pass."""
     B, S, H = h.shape
     assert h.is_contiguous() and h.dtype == torch.bfloat16
     if out is None:
         out = torch.empty((B, H), device=h.device, dtype=torch.bfloat16)
+    if out_q8 is not None:
+        assert out_q8.dtype == torch.uint8 and out_q8.is_contiguous() and out_q8.shape == (B, H)
+        assert out_qscale is not None and out_qscale.dtype == torch.float32 and out_qscale.numel() >= B
     L = _native.require()
     rc = L.im_pool_norm(_native.ptr(h), _native.ptr(lengths), ctypes.c_int(B), ctypes.c_int(S), ctypes.c_int(H),
                         ctypes.c_int(0 if mode == "cls" else 1), ctypes.c_int(1 if normalize else 0),
-                        _native.ptr(out), _native.ptr(out_f32), _native.stream_ptr())
+                        _native.ptr(out), _native.ptr(out_f32), _native.stream_ptr(), _native.ptr(out_q8), _native.ptr(out_qscale))
     _native.check(rc, "im_pool_norm")
     _native.count_launch()
     return out
+
+
+def quantize_rows_e4m3(x, normalize=False, chunk=1 << 20):
+    """bf16 ``[n, H]`` -> (uint8 ``[n, H]`` e4m3 bytes, fp32 ``[n]`` power-of-two row scales) with the pooling kernel
+    (sequence length 1): the index-build side of the fp8 dense shard.  ``value = e4m3 * scale``."""
+    n, H = x.shape
+    q8 = torch.empty((n, H), device=x.device, dtype=torch.uint8)
+    sc = torch.empty((n,), device=x.device, dtype=torch.float32)
+    scratch = torch.empty((min(n, chunk), H), device=x.device, dtype=torch.bfloat16)
+    for a in range(0, n, chunk):
+        b = min(n, a + chunk)
+        pool_norm(x[a:b].contiguous().view(b - a, 1, H), None, "cls", normalize, out=scratch[:b - a], out_q8=q8[a:b], out_qscale=sc[a:b])
+    return q8, sc
+
+
+def quantize_rows_e4m3_ref(x):
+    """PyTorch oracle of :func:`quantize_rows_e4m3` (no normalisation): same power-of-two scale rule as the kernel."""
+    xf = x.float()
+    amax = xf.abs().amax(dim=1).clamp_min(1e-30)
+    e = torch.ceil(torch.log2(amax / 448.0)).clamp(-126, 126)
+    scale = torch.exp2(e)
+    q = (xf / scale[:, None]).to(torch.float8_e4m3fn)
+    return q.view(torch.uint8), scale
 
 
 def cls_head(h, w1, b1, w2, b2, out=None):

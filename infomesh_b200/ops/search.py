@@ -55,6 +55,81 @@ def sim_topk_partials(q, docs, ktop=16, alive=None, max_ctas=0, thr_init=None):
     return out_s, out_i
 
 
+def sim_topk_partials_f8(q8, q_scale, d8, d_scale, ktop=16, alive=None, max_ctas=0, thr_init=None):
+    """fp8 twin of :func:`sim_topk_partials`: ``q8`` / ``d8`` uint8 e4m3 rows, ``q_scale`` / ``d_scale`` fp32 per row;
+    scores in the lists are true dot products (``acc * d_scale * q_scale``)."""
+    assert q8.is_cuda and d8.is_cuda and q8.dtype == torch.uint8 and d8.dtype == torch.uint8
+    assert q8.stride(1) == 1 and d8.stride(1) == 1 and q8.shape[1] == d8.shape[1] and q8.shape[1] % 128 == 0
+    assert q_scale.dtype == torch.float32 and d_scale.dtype == torch.float32 and d_scale.numel() >= d8.shape[0]
+    nq, dim = q8.shape
+    n_docs = d8.shape[0]
+    L = _native.require()
+    sms = L.im_sm_count()
+    tiles = (n_docs + 127) // 128
+    grid = max(1, min(tiles, sms if max_ctas <= 0 else min(sms, max_ctas)))
+    lists, width = (grid * 4, 1) if ktop == 0 else (grid, ktop)
+    out_s = torch.empty((lists, nq, width), device=q8.device, dtype=torch.float32)
+    out_i = torch.empty((lists, nq, width), device=q8.device, dtype=torch.int32)
+    rc = L.im_sim_topk_f8(_native.ptr(q8), _native.ptr(q_scale), _native.ptr(d8), _native.ptr(d_scale), ctypes.c_int(nq),
+                          ctypes.c_int(n_docs), ctypes.c_int(dim), ctypes.c_int(q8.stride(0)), ctypes.c_int(d8.stride(0)),
+                          ctypes.c_int(ktop), _native.ptr(alive), _native.ptr(out_s), _native.ptr(out_i), ctypes.c_int(max_ctas),
+                          _native.ptr(thr_init), ctypes.c_int(thr_init.stride(0) if thr_init is not None else 0), _native.stream_ptr())
+    if rc < 0:
+        _native.check(rc, "im_sim_topk_f8")
+    assert rc == grid, (rc, grid)
+    _native.count_launch()
+    return out_s, out_i
+
+
+def rescore_topk(q, docs, cand_rows, k_out, id_offset=0, out_scores=None, out_ids=None):
+    """Exact bf16 re-scoring of ``cand_rows`` int64 ``[nq, n <= 32]`` (local rows, -1 = empty) -> best ``k_out`` by
+    true dot product (score desc, id asc), ids shifted by ``id_offset``."""
+    nq, n = cand_rows.shape
+    assert q.dtype == torch.bfloat16 and docs.dtype == torch.bfloat16 and cand_rows.dtype == torch.int64 and cand_rows.is_contiguous()
+    if out_scores is None:
+        out_scores = torch.empty((nq, k_out), device=q.device, dtype=torch.float32)
+    if out_ids is None:
+        out_ids = torch.empty((nq, k_out), device=q.device, dtype=torch.int64)
+    L = _native.require()
+    rc = L.im_rescore_topk(_native.ptr(q), ctypes.c_int(q.stride(0)), _native.ptr(docs), ctypes.c_int(docs.stride(0)),
+                           ctypes.c_int(q.shape[1]), _native.ptr(cand_rows), ctypes.c_int(nq), ctypes.c_int(n), ctypes.c_int(k_out),
+                           ctypes.c_int64(id_offset), _native.ptr(out_scores), _native.ptr(out_ids), _native.stream_ptr())
+    _native.check(rc, "im_rescore_topk")
+    _native.count_launch()
+    return out_scores, out_ids
+
+
+def sim_topk_f8(q8, q_scale, d8, d_scale, k=10, alive=None, id_offset=0, push=None, rescore=None, k_fetch=None):
+    """Top-``k`` over an e4m3 shard.  ``rescore=(q_bf16, docs_bf16)``: fetch ``k_fetch`` (default ``min(32, 2k)``)
+    candidates from the fp8 pass and re-rank them exactly against the bf16 rows, so quantisation noise can only cost a
+    document that was outside the over-fetched list (measured recall: tests/test_gpu_kernels.py)."""
+    kf = k if rescore is None else min(32, k_fetch or 2 * k)
+    assert 1 <= k <= kf <= 32
+    thr = sample_threshold_f8(q8, q_scale, d8, d_scale, kf, alive)
+    ps, pi = sim_topk_partials_f8(q8, q_scale, d8, d_scale, ktop=kf, alive=alive, thr_init=thr)
+    if rescore is None:
+        return topk_merge(ps, pi, k, id_offset=id_offset, push=push)
+    _s, rows = topk_merge(ps, pi, kf)
+    rs, ri = rescore_topk(rescore[0], rescore[1], rows, k, id_offset=id_offset)
+    if push is None:
+        return rs, ri
+    # the fused exchange lives in the merge kernel: a 1-list merge of the re-scored (already global) list pushes it
+    return topk_merge(rs.unsqueeze(0), ri.unsqueeze(0), k, push=push)
+
+
+def sample_threshold_f8(q8, q_scale, d8, d_scale, k, alive=None):
+    """:func:`sample_threshold` for the fp8 shard."""
+    n = d8.shape[0]
+    n_s = max(SAMPLE_MIN_DOCS, n // SAMPLE_FRACTION)
+    if n < 2 * n_s or k > 32:
+        return None
+    ps, pi = sim_topk_partials_f8(q8, q_scale, d8[:n_s], d_scale, ktop=0, alive=alive)
+    if ps.shape[0] < k:
+        return None
+    ms, _ = topk_merge(ps, pi, k)
+    return ms[:, k - 1]
+
+
 def topk_merge(cand_scores, cand_ids, k_out, id_offset=0, out_scores=None, out_ids=None, push=None, wait=None):
     """Merge ``[P, nq, k_in]`` candidate lists into ``[nq, k_out]`` (score desc, id asc).
 

@@ -60,6 +60,68 @@ def test_sim_topk_exact(nq, n, dim, k, alive):
     assert (i[:, :kk] == ri + 1000).float().mean().item() > 0.98
 
 
+def test_quantize_rows_e4m3_matches_oracle():
+    from infomesh_b200.ops.nn import quantize_rows_e4m3, quantize_rows_e4m3_ref
+
+    x = (torch.randn(777, 384, device=DEV) * torch.rand(777, 1, device=DEV) * 3).bfloat16()
+    x[5] = 0
+    q8, sc = quantize_rows_e4m3(x)
+    r8, rsc = quantize_rows_e4m3_ref(x)
+    assert torch.equal(sc, rsc)
+    deq = q8.view(torch.float8_e4m3fn).float() * sc[:, None]
+    ref = r8.view(torch.float8_e4m3fn).float() * rsc[:, None]
+    assert (deq - ref).abs().max().item() <= 1e-6 + 0.07 * x.float().abs().max().item()   # at most one e4m3 ulp apart
+    assert (q8 != r8).float().mean().item() < 0.01                                          # ties in rounding only
+    assert (deq - x.float()).abs().max().item() <= x.float().abs().amax(dim=1).max().item() / 14   # half an ulp of 3 mantissa bits
+
+
+@pytest.mark.parametrize("nq,n,dim,k,alive", [(64, 300_000, 384, 20, None), (8, 50_000, 384, 10, 0.9), (128, 20_000, 512, 16, None),
+                                               (1, 5000, 128, 10, None)])
+def test_sim_topk_f8_scores_and_rescored_recall(nq, n, dim, k, alive):
+    """fp8 shard: list scores are the dot products of the DEQUANTISED vectors; with bf16 re-scoring of a 32-wide
+    over-fetch the result matches the exact bf16 search (recall@k vs the fp32 oracle >= 0.99)."""
+    from infomesh_b200.ops.nn import quantize_rows_e4m3
+    from infomesh_b200.ops.search import sim_topk_f8, sim_topk_ref
+
+    q = torch.nn.functional.normalize(torch.randn(nq, dim, device=DEV), dim=1).bfloat16()
+    d = torch.nn.functional.normalize(torch.randn(n, dim, device=DEV), dim=1).bfloat16()
+    mask = (torch.rand(n, device=DEV) < alive).to(torch.uint8) if alive is not None else None
+    q8, qs = quantize_rows_e4m3(q)
+    d8, ds = quantize_rows_e4m3(d)
+    # (1) raw fp8 search against the oracle over the dequantised operands
+    s, i = sim_topk_f8(q8, qs, d8, ds, k, alive=mask, id_offset=7)
+    qd = q8.view(torch.float8_e4m3fn).float() * qs[:, None]
+    dd = d8.view(torch.float8_e4m3fn).float() * ds[:, None]
+    rs, ri = sim_topk_ref(qd, dd, k, alive=mask)
+    assert (s - rs).abs().max().item() < 1e-4
+    assert (i == ri + 7).float().mean().item() > 0.98
+    # (2) over-fetch + exact re-scoring vs the fp32 oracle on the bf16 vectors
+    s2, i2 = sim_topk_f8(q8, qs, d8, ds, k, alive=mask, id_offset=7, rescore=(q, d), k_fetch=32)
+    es, ei = sim_topk_ref(q, d, k, alive=mask)
+    recall = sum(len(set(a.tolist()) & set((b + 7).tolist())) for a, b in zip(i2, ei)) / ei.numel()
+    assert recall >= 0.99, recall
+    hit = i2 == ei + 7
+    assert (s2 - es).abs()[hit].max().item() < 2e-3
+    assert (s2[:, :-1] >= s2[:, 1:]).all()
+
+
+def test_rescore_topk_orders_and_pads():
+    from infomesh_b200.ops.search import rescore_topk
+
+    q = torch.nn.functional.normalize(torch.randn(3, 384, device=DEV), dim=1).bfloat16()
+    d = torch.nn.functional.normalize(torch.randn(100, 384, device=DEV), dim=1).bfloat16()
+    cand = torch.tensor([[5, 9, -1, 70, 9], [1, 2, 3, 4, 5], [-1, -1, -1, -1, -1]], device=DEV, dtype=torch.int64)
+    s, i = rescore_topk(q, d, cand, 4, id_offset=100)
+    full = q.float() @ d.float().t()
+    for r in range(2):
+        rows = [x for x in cand[r].tolist() if x >= 0]
+        order = sorted(set(rows), key=lambda x: (-full[r, x].item(), x))
+        got = [x - 100 for x in i[r].tolist() if x >= 0]
+        assert got[0] == order[0] and set(got) <= set(rows)
+        assert abs(s[r, 0].item() - full[r, order[0]].item()) < 2e-3
+    assert i[2].tolist() == [-1, -1, -1, -1]
+
+
 def test_topk_merge_dedup_and_order():
     from infomesh_b200.ops.search import topk_merge
 
