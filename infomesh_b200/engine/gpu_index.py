@@ -311,6 +311,7 @@ class GpuSearchIndex:
         cfg = HybridConfig(nq=self.nq, rerank=self.rerank, k_fetch=20, n_rerank=20, k_out=10, pair_seq=min(128, 32 + self.passage_len),
                            use_graph=self.use_graph, dense=self.use_dense, rank_signals=self.rank_signals)
         engine = HybridEngine(shard, cfg, encoder=self.encoder, reranker=self.reranker, **ekw)
+        engine.warm()           # graph capture belongs to the build, not to the first query (and never to a serving thread)
         pin = torch.cuda.is_available()
 
         def mk(*shape, fill=0):

@@ -238,6 +238,11 @@ class HybridEngine:
         self.in_q_len.copy_(q_len, non_blocking=True)
         self.in_terms.copy_(terms, non_blocking=True)
 
+    def warm(self):
+        """Capture the step graph now (index build time) instead of inside the first query."""
+        if self.cfg.use_graph and not self._graph_failed and self.cfg.backend == "fused" and self._graph is None:
+            self._capture()
+
     def run(self):
         """Execute the pipeline on the currently loaded inputs (CUDA graph replay when enabled)."""
         if self.cfg.use_graph and not self._graph_failed and self.cfg.backend == "fused":
@@ -259,7 +264,9 @@ class HybridEngine:
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            # thread_local: other host threads (an index rebuild allocating memory, another engine replaying its graph)
+            # may keep issuing CUDA calls while this thread captures
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 self._forward()
             self._graph = g
         except Exception as exc:  # noqa: BLE001 — fall back to eager launches, loudly
@@ -365,7 +372,7 @@ class HybridEngine:
             out = []
             for b in self._pbuf:
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=stream):
+                with torch.cuda.graph(g, stream=stream, capture_error_mode="thread_local"):
                     fn(b)
                 out.append(g)
             torch.cuda.synchronize()

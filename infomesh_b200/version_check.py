@@ -1,12 +1,19 @@
-"""Update detection: the package index (24 h on-disk cache, 5 s timeout) and version gossip from PING/PONG exchanges
-(reference infomesh/version_check.py:27-280).  Comparison keeps only the numeric prefix of each dotted segment."""
+"""Is a newer release out?  Two sources: the package index (asked at most once a day, answer memoised on disk, 5 s
+network budget) and the versions peers announce in PING/PONG.
+
+Contract (SURVEY §2.1 "version check"; reference infomesh/version_check.py): versions compare by the leading integer of each
+dotted segment (``1.2.3rc1`` -> ``(1, 2, 3)``, nothing numeric -> ``(0,)``); every failure (offline, bad JSON, unwritable
+cache) degrades to "no update known", never to an exception; peer-reported versions longer than 32 characters are ignored;
+when both sources know an update the higher version wins.
+
+Implementation: versions are turned into sort keys by one function used everywhere; the on-disk memo is a tiny record
+class with ``load`` / ``store``; ``check_for_update`` gathers candidate announcements and takes the maximum."""
 from __future__ import annotations
 
-import contextlib
 import json
-import re
 import time
 from dataclasses import dataclass
+from itertools import takewhile
 from pathlib import Path
 
 from infomesh_b200 import __version__
@@ -15,7 +22,8 @@ _PYPI_URL = "https://pypi.org/pypi/infomesh/json"
 _CACHE_TTL_SECONDS = 86400
 _CACHE_FILE_NAME = "version_cache.json"
 _REQUEST_TIMEOUT = 5.0
-_LEADING_INT = re.compile(r"\d+")
+_MAX_PEER_VERSION_LEN = 32
+_SOURCE_LABEL = {"pypi": "PyPI", "peer": "P2P peer"}
 
 
 @dataclass(frozen=True)
@@ -25,90 +33,110 @@ class UpdateInfo:
     source: str      # "pypi" | "peer"
 
 
-def _parse_version(v: str) -> tuple[int, ...]:
-    nums = []
-    for seg in v.split("."):
-        m = _LEADING_INT.match(seg)
-        if m:
-            nums.append(int(m.group()))
-    return tuple(nums) or (0,)
+# ----------------------------------------------------------------------------- ordering
+def _parse_version(text: str) -> tuple[int, ...]:
+    """Sort key: leading digits of every dotted segment; segments without any are skipped."""
+    key = tuple(int(digits) for part in text.split(".") if (digits := "".join(takewhile(str.isdigit, part))))
+    return key or (0,)
 
 
 def is_newer(candidate: str, current: str | None = None) -> bool:
-    return _parse_version(candidate) > _parse_version(current or __version__)
+    return _parse_version(candidate) > _parse_version(__version__ if not current else current)
+
+
+def _clean(value: object) -> str | None:
+    return value if isinstance(value, str) and value else None
+
+
+# ----------------------------------------------------------------------------- package index, memoised on disk
+class _Memo:
+    """``{"version": ..., "ts": ...}`` next to the node's other state files."""
+
+    def __init__(self, data_dir: Path):
+        self.file = Path(data_dir) / _CACHE_FILE_NAME
+
+    def load(self) -> str | None:
+        try:
+            rec = json.loads(self.file.read_text(encoding="utf-8"))
+            fresh = time.time() - float(rec.get("ts", 0)) <= _CACHE_TTL_SECONDS
+            return _clean(rec.get("version", "")) if fresh else None
+        except Exception:  # noqa: BLE001 -- missing / corrupt memo == no memo
+            return None
+
+    def store(self, version: str) -> None:
+        try:
+            self.file.write_text(json.dumps({"version": version, "ts": time.time()}), encoding="utf-8")
+        except OSError:
+            pass
 
 
 def _read_cache(data_dir: Path) -> str | None:
-    try:
-        raw = json.loads((Path(data_dir) / _CACHE_FILE_NAME).read_text(encoding="utf-8"))
-        if time.time() - float(raw.get("ts", 0)) > _CACHE_TTL_SECONDS:
-            return None
-        ver = raw.get("version", "")
-        return ver if isinstance(ver, str) and ver else None
-    except Exception:  # noqa: BLE001
-        return None
+    return _Memo(data_dir).load()
 
 
 def _write_cache(data_dir: Path, version: str) -> None:
-    with contextlib.suppress(OSError):
-        (Path(data_dir) / _CACHE_FILE_NAME).write_text(json.dumps({"version": version, "ts": time.time()}), encoding="utf-8")
+    _Memo(data_dir).store(version)
 
 
 def _fetch_latest_from_pypi() -> str | None:
     try:
-        import urllib.request
+        from urllib.request import urlopen
 
-        with urllib.request.urlopen(_PYPI_URL, timeout=_REQUEST_TIMEOUT) as resp:  # noqa: S310 — constant https URL
-            if resp.status != 200:
+        with urlopen(_PYPI_URL, timeout=_REQUEST_TIMEOUT) as reply:  # noqa: S310 -- constant https URL
+            if reply.status != 200:
                 return None
-            ver = json.loads(resp.read(1 << 22)).get("info", {}).get("version", "")
-        return ver if isinstance(ver, str) and ver else None
+            body = json.loads(reply.read(4 << 20))
+        return _clean(body.get("info", {}).get("version", ""))
     except Exception:  # noqa: BLE001
         return None
 
 
 def check_pypi_update(data_dir: Path) -> UpdateInfo | None:
-    latest = _read_cache(data_dir)
-    if latest is None:
-        latest = _fetch_latest_from_pypi()
-        if latest is None:
+    published = _read_cache(data_dir)
+    if published is None:
+        published = _fetch_latest_from_pypi()
+        if published is None:
             return None
-        _write_cache(data_dir, latest)
-    return UpdateInfo(__version__, latest, "pypi") if is_newer(latest) else None
+        _write_cache(data_dir, published)
+    return UpdateInfo(__version__, published, "pypi") if is_newer(published) else None
 
 
+# ----------------------------------------------------------------------------- peer gossip
 class PeerVersionTracker:
     def __init__(self):
-        self._peer_versions: dict[str, str] = {}
+        self._seen: dict[str, str] = {}
 
     def record(self, peer_id: str, version: str) -> None:
-        if version and isinstance(version, str) and len(version) <= 32:
-            self._peer_versions[peer_id] = version
-
-    def get_newest_peer_version(self) -> str | None:
-        return max(self._peer_versions.values(), key=_parse_version) if self._peer_versions else None
-
-    def check_peer_update(self) -> UpdateInfo | None:
-        newest = self.get_newest_peer_version()
-        return UpdateInfo(__version__, newest, "peer") if newest and is_newer(newest) else None
+        if _clean(version) and len(version) <= _MAX_PEER_VERSION_LEN:
+            self._seen[peer_id] = version
 
     @property
     def peer_versions(self) -> dict[str, str]:
-        return dict(self._peer_versions)
+        return dict(self._seen)
+
+    def get_newest_peer_version(self) -> str | None:
+        return max(self._seen.values(), key=_parse_version, default=None)
+
+    def check_peer_update(self) -> UpdateInfo | None:
+        top = self.get_newest_peer_version()
+        return UpdateInfo(__version__, top, "peer") if top is not None and is_newer(top) else None
 
 
+# ----------------------------------------------------------------------------- combined
 def check_for_update(data_dir: Path | None = None, peer_tracker: PeerVersionTracker | None = None) -> UpdateInfo | None:
-    best: UpdateInfo | None = None
+    found: list[UpdateInfo] = []
     if data_dir is not None:
-        with contextlib.suppress(Exception):
-            best = check_pypi_update(data_dir)
+        try:
+            found.append(check_pypi_update(data_dir))
+        except Exception:  # noqa: BLE001
+            pass
     if peer_tracker is not None:
-        peer = peer_tracker.check_peer_update()
-        if peer is not None and (best is None or is_newer(peer.latest, best.latest)):
-            best = peer
-    return best
+        found.append(peer_tracker.check_peer_update())
+    found = [f for f in found if f is not None]
+    # max() keeps the first of equal keys: the package index wins a tie, as it is the authoritative source
+    return max(found, key=lambda f: _parse_version(f.latest), default=None)
 
 
 def format_update_banner(info: UpdateInfo) -> str:
-    src = "PyPI" if info.source == "pypi" else "P2P peer"
-    return f"\n  ⬆ Update available ({src}): v{info.current} → v{info.latest}\n    Run: infomesh update\n"
+    where = _SOURCE_LABEL.get(info.source, _SOURCE_LABEL["peer"])
+    return f"\n  ⬆ Update available ({where}): v{info.current} → v{info.latest}\n    Run: infomesh update\n"
