@@ -1,11 +1,20 @@
-"""PDF text extraction through PyMuPDF when it is installed (reference infomesh/crawler/pdf.py:16-71)."""
+"""Text out of PDF bytes, when PyMuPDF (``fitz``) is importable.
+
+Contract (SURVEY §2.1 crawler/ "pdf"; reference infomesh/crawler/pdf.py): a URL is a PDF when its path ends in ``.pdf``
+(any case, trailing slash ignored) or it carries an ``application/pdf`` hint; extraction reads at most ``max_pages`` pages,
+joins them with blank lines, and yields ``None`` for an empty document, a parse failure, or a missing library -- never an
+exception.  Metadata values are stringified, empty ones dropped."""
 from __future__ import annotations
 
+from contextlib import closing
 from dataclasses import dataclass
+from importlib import import_module
 
 from infomesh_b200.utils.log import get_logger
 
 logger = get_logger(__name__)
+
+_PDF_HINTS = ("application/pdf",)
 
 
 @dataclass(frozen=True)
@@ -17,25 +26,31 @@ class PDFContent:
 
 
 def is_pdf_url(url: str) -> bool:
-    low = url.lower().rstrip("/")
-    return low.endswith(".pdf") or "application/pdf" in low
+    folded = url.casefold().rstrip("/")
+    return folded.endswith(".pdf") or any(hint in folded for hint in _PDF_HINTS)
 
 
-def extract_pdf_text(data: bytes, *, max_pages: int = 50) -> PDFContent | None:
+def _pymupdf():
     try:
-        import fitz  # type: ignore
+        return import_module("fitz")
     except ImportError:
         logger.debug("pymupdf_not_installed")
         return None
+
+
+def extract_pdf_text(data: bytes, *, max_pages: int = 50) -> PDFContent | None:
+    engine = _pymupdf()
+    if engine is None:
+        return None
     try:
-        doc = fitz.open(stream=data, filetype="pdf")
-        n = min(doc.page_count, max_pages)
-        text = "\n\n".join(doc[i].get_text() for i in range(n)).strip()
-        meta = doc.metadata or {}
-        doc.close()
-        if not text:
-            return None
-        return PDFContent(text, meta.get("title", "") or "", n, {k: str(v) for k, v in meta.items() if v})
-    except Exception:  # noqa: BLE001
+        with closing(engine.open(stream=data, filetype="pdf")) as document:
+            pages = min(max_pages, document.page_count)
+            body = "\n\n".join(document[number].get_text() for number in range(pages)).strip()
+            info = dict(document.metadata or {})
+    except Exception:  # noqa: BLE001 -- damaged or encrypted file
         logger.debug("pdf_extraction_failed")
         return None
+    if not body:
+        return None
+    return PDFContent(text=body, title=info.get("title") or "", page_count=pages,
+                      metadata={key: str(value) for key, value in info.items() if value})

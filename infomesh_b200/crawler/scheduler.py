@@ -1,21 +1,29 @@
-"""Crawl scheduler: bounded asyncio queue, per-domain politeness (robots Crawl-delay capped at 60 s), pending-per-domain
-cap, hourly budget, stale-domain pruning (reference infomesh/crawler/scheduler.py:27-208)."""
+"""Crawl frontier: which URL may be fetched next, and when.
+
+Contract (SURVEY §2.1 crawler/ "scheduler"; reference infomesh/crawler/scheduler.py): a bounded FIFO of ``(url, depth)``;
+at most ``pending_per_domain`` queued URLs per host; an optional depth limit; between two fetches of one host at least the
+politeness delay -- or the host's robots ``Crawl-delay``, capped at 60 s -- must pass; at most ``urls_per_hour`` fetches
+per rolling hour (0 = unlimited), a URL that hits the cap goes back to the queue while the caller sleeps out the hour;
+bookkeeping for hosts that are idle for an hour is dropped once the table grows large.
+
+Implementation: three small collaborators instead of one class doing everything -- ``_HostBook`` (per-host counters and
+pruning), ``_HourlyAllowance`` (the rolling budget) and the queue; ``Scheduler`` only sequences them."""
 from __future__ import annotations
 
 import asyncio
 import time
-from collections import defaultdict
 from dataclasses import dataclass
-from urllib.parse import urlparse
+from urllib.parse import urlsplit
 
 from infomesh_b200.utils.log import get_logger
 
 logger = get_logger(__name__)
 
 _MAX_TRACKED_DOMAINS = 50_000
-_DOMAIN_PRUNE_THRESHOLD = int(_MAX_TRACKED_DOMAINS * 0.8)
+_DOMAIN_PRUNE_THRESHOLD = _MAX_TRACKED_DOMAINS * 4 // 5
 _DOMAIN_STALE_SECONDS = 3600.0
 _QUEUE_SIZE = 10_000
+_HOUR = 3600.0
 MAX_CRAWL_DELAY = 60.0
 
 
@@ -26,85 +34,128 @@ class DomainState:
     error_count: int = 0
     crawl_delay: float | None = None
 
+    def idle_since(self, cutoff: float) -> bool:
+        return self.pending_count == 0 and self.last_request_at < cutoff
+
+
+def _host(url: str) -> str:
+    return urlsplit(url).netloc
+
+
+class _HostBook(dict):
+    """host -> :class:`DomainState`, created on first touch."""
+
+    def __missing__(self, host: str) -> DomainState:
+        state = self[host] = DomainState()
+        return state
+
+    def shrink_to(self, limit: int) -> None:
+        """Forget idle hosts when more than ``limit`` are tracked (hosts with queued URLs are never dropped)."""
+        if len(self) <= limit:
+            return
+        cutoff = time.monotonic() - _DOMAIN_STALE_SECONDS
+        for host in [h for h, st in self.items() if st.idle_since(cutoff)]:
+            del self[host]
+
+
+class _HourlyAllowance:
+    """Fetches granted in the current hour window; ``limit == 0`` disables the cap."""
+
+    def __init__(self, limit: int):
+        self.limit = int(limit)
+        self.used = 0
+        self.window_opened = time.monotonic()
+
+    def roll(self) -> bool:
+        """Open a new window when the hour is over.  True if it rolled."""
+        now = time.monotonic()
+        if now - self.window_opened < _HOUR:
+            return False
+        self.used, self.window_opened = 0, now
+        return True
+
+    def exhausted(self) -> bool:
+        return self.limit > 0 and self.used >= self.limit
+
+    def seconds_left(self) -> float:
+        return max(_HOUR - (time.monotonic() - self.window_opened), 1.0)
+
 
 class Scheduler:
-    def __init__(self, *, politeness_delay: float = 1.0, urls_per_hour: int = 60, pending_per_domain: int = 10,
-                 max_depth: int = 0):
-        self._delay = politeness_delay
-        self._per_hour = urls_per_hour
-        self._per_domain = pending_per_domain
-        self._max_depth = max_depth
-        self._domains: dict[str, DomainState] = defaultdict(DomainState)
+    def __init__(self, *, politeness_delay: float = 1.0, urls_per_hour: int = 60, pending_per_domain: int = 10, max_depth: int = 0):
+        self._politeness = politeness_delay
+        self._host_cap = pending_per_domain
+        self._depth_cap = max_depth
+        self._domains = _HostBook()
+        self._budget = _HourlyAllowance(urls_per_hour)
         self._queue: asyncio.Queue[tuple[str, int]] = asyncio.Queue(maxsize=_QUEUE_SIZE)
-        self._hour_count = 0
-        self._hour_start = time.monotonic()
 
-    async def add_url(self, url: str, depth: int = 0) -> bool:
-        if self._max_depth > 0 and depth > self._max_depth:
-            return False
-        if len(self._domains) > _DOMAIN_PRUNE_THRESHOLD:
-            self._prune(_DOMAIN_PRUNE_THRESHOLD)
-        st = self._domains[urlparse(url).netloc]
-        if st.pending_count >= self._per_domain or self._queue.full():
-            return False
-        st.pending_count += 1
-        await self._queue.put((url, depth))
-        return True
+    # ---- configuration
+    @property
+    def _per_hour(self) -> int:
+        return self._budget.limit
 
     def set_urls_per_hour(self, limit: int) -> None:
         """0 = unlimited."""
-        self._per_hour = limit
+        self._budget.limit = int(limit)
 
     def set_crawl_delay(self, domain: str, delay: float) -> None:
         self._domains[domain].crawl_delay = min(float(delay), MAX_CRAWL_DELAY)
 
-    async def get_url(self) -> tuple[str, int]:
-        while True:
-            url, depth = await self._queue.get()
-            st = self._domains[urlparse(url).netloc]
-            delay = st.crawl_delay if st.crawl_delay is not None else self._delay
-            wait = delay - (time.monotonic() - st.last_request_at)
-            if wait > 0:
-                await asyncio.sleep(wait)
-            if self._per_hour > 0:
-                self._roll_hour()
-                if self._hour_count >= self._per_hour:
-                    remaining = max(3600 - (time.monotonic() - self._hour_start), 1.0)
-                    logger.info("scheduler_hourly_limit", count=self._hour_count, wait_secs=round(remaining))
-                    await self._queue.put((url, depth))
-                    await asyncio.sleep(remaining)
-                    continue
-                self._hour_count += 1
-            st.last_request_at = time.monotonic()
-            return url, depth
+    # ---- producers
+    async def add_url(self, url: str, depth: int = 0) -> bool:
+        if 0 < self._depth_cap < depth:
+            return False
+        self._domains.shrink_to(_DOMAIN_PRUNE_THRESHOLD)
+        state = self._domains[_host(url)]
+        if state.pending_count >= self._host_cap or self._queue.full():
+            return False
+        state.pending_count += 1
+        await self._queue.put((url, depth))
+        return True
 
+    # ---- consumer
+    async def get_url(self) -> tuple[str, int]:
+        """Next ``(url, depth)``; returns only once the host's delay has passed and the hourly budget allows it."""
+        while True:
+            item = await self._queue.get()
+            state = self._domains[_host(item[0])]
+            gap = self._politeness if state.crawl_delay is None else state.crawl_delay
+            pause = state.last_request_at + gap - time.monotonic()
+            if pause > 0:
+                await asyncio.sleep(pause)
+            if self._budget.limit > 0:
+                if self._budget.roll():
+                    self._domains.shrink_to(_MAX_TRACKED_DOMAINS)
+                if self._budget.exhausted():
+                    nap = self._budget.seconds_left()
+                    logger.info("scheduler_hourly_limit", count=self._budget.used, wait_secs=round(nap))
+                    await self._queue.put(item)
+                    await asyncio.sleep(nap)
+                    continue
+                self._budget.used += 1
+            state.last_request_at = time.monotonic()
+            return item
+
+    # ---- completion
     def mark_done(self, url: str) -> None:
-        st = self._domains.get(urlparse(url).netloc)
-        if st is None:
+        state = self._domains.get(_host(url))
+        if state is None:
             return
-        st.pending_count = max(0, st.pending_count - 1)
-        if len(self._domains) > _DOMAIN_PRUNE_THRESHOLD:
-            self._prune(_DOMAIN_PRUNE_THRESHOLD)
+        state.pending_count = max(state.pending_count - 1, 0)
+        self._domains.shrink_to(_DOMAIN_PRUNE_THRESHOLD)
 
     def mark_error(self, url: str) -> None:
-        st = self._domains.get(urlparse(url).netloc)
-        if st is not None:
-            st.error_count += 1
-            self.mark_done(url)
-
-    def _roll_hour(self) -> None:
-        now = time.monotonic()
-        if now - self._hour_start >= 3600:
-            self._hour_count, self._hour_start = 0, now
-            self._prune(_MAX_TRACKED_DOMAINS)
+        state = self._domains.get(_host(url))
+        if state is None:
+            return
+        state.error_count += 1
+        self.mark_done(url)
 
     def _prune(self, threshold: int) -> None:
-        if len(self._domains) <= threshold:
-            return
-        cutoff = time.monotonic() - _DOMAIN_STALE_SECONDS
-        for d in [d for d, s in self._domains.items() if s.pending_count == 0 and s.last_request_at < cutoff]:
-            del self._domains[d]
+        self._domains.shrink_to(threshold)
 
+    # ---- introspection
     @property
     def pending_count(self) -> int:
         return self._queue.qsize()
