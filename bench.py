@@ -323,6 +323,20 @@ def main() -> int:
     ids_ok = bool((out_i_host[:, 0] >= 0).float().mean() > 0.5)
 
     extras = {}
+    if hcfg.dense_dtype == "fp8":
+        # agreement of the fp8 (over-fetch + exact re-score) search with the exact bf16 search, same queries
+        from infomesh_b200.ops import search as S_
+
+        eng.load_inputs(*dev_batches[0])
+        q_emb = eng._encode()
+        f_s, f_i = S_.sim_topk_f8(eng.q8, eng.q8_scale, shard.vectors_f8, shard.vec_scale, hcfg.k_fetch, alive=shard.alive,
+                                  id_offset=shard.cfg.doc_base, rescore=(q_emb, shard.vectors), k_fetch=32)    # no push: local check
+        b_s, b_i = S_.sim_topk(q_emb, shard.vectors, hcfg.k_fetch, alive=shard.alive, id_offset=shard.cfg.doc_base)
+        torch.cuda.synchronize()
+        fi, bi = f_i.cpu(), b_i.cpu()
+        rec = [len(set(x[:10].tolist()) & set(y[:10].tolist())) / 10.0 for x, y in zip(fi, bi)]
+        extras["dense_recall_vs_bf16"] = {"recall_at_10": round(sum(rec) / len(rec), 4), "top1_equal": round(float((fi[:, 0] == bi[:, 0]).float().mean()), 4),
+                                          "k_fetch_fp8": 32, "note": "this rank's shard; fp8 pass over-fetches 32 and re-scores against bf16 rows"}
     if not args.quick:
         # ---- (c) sustained: the same end-to-end loop for >= sustain_s seconds (power / thermal steady state) ----
         est_ms = max(e2e_ms / K, 1e-3)
@@ -346,17 +360,6 @@ def main() -> int:
         vec_bytes = shard.vectors.numel() * shard.vectors.element_size()
         if hcfg.dense_dtype == "fp8":
             vec_bytes = shard.vectors_f8.numel() + shard.vec_scale.numel() * 4
-            # agreement of the fp8 (over-fetch + exact re-score) search with the exact bf16 search, same queries
-            from infomesh_b200.ops import search as S_
-
-            q_emb = eng._encode()
-            f_s, f_i = eng._dense_local(q_emb)
-            b_s, b_i = S_.sim_topk(q_emb, shard.vectors, hcfg.k_fetch, alive=shard.alive, id_offset=shard.cfg.doc_base)
-            torch.cuda.synchronize()
-            fi, bi = f_i.cpu(), b_i.cpu()
-            rec = [len(set(x[:10].tolist()) & set(y[:10].tolist())) / 10.0 for x, y in zip(fi, bi)]
-            extras["dense_recall_vs_bf16"] = {"recall_at_10": round(sum(rec) / len(rec), 4), "top1_equal": round(float((fi[:, 0] == bi[:, 0]).float().mean()), 4),
-                                              "k_fetch_fp8": 32, "note": "this rank's shard; fp8 pass over-fetches 32 and re-scores against bf16 rows"}
         if st["dense_local"] > 0:
             gbs = vec_bytes / (st["dense_local"] * 1e-3) / 1e9
             roof["dense_local"] = {"bytes": vec_bytes, "achieved_gbs": round(gbs, 1), "frac_of_hbm": round(gbs / peaks["hbm_gbs"], 3)}

@@ -1,11 +1,20 @@
-"""Per-peer latency profiles: EMA (alpha 0.3) average, p95 over the last 100 samples, success rate, bandwidth class,
-latency ranking with 20 % slow-peer diversity, adaptive per-peer timeouts clamped to 500..5000 ms
-(reference infomesh/p2p/peer_profile.py:27-263)."""
+"""What this node has learned about how quickly each peer answers.
+
+Contract (SURVEY §2.1 p2p/ "peer profiles"; reference infomesh/p2p/peer_profile.py): per peer an exponentially weighted
+mean latency (alpha 0.3, seeded by the first sample), the 95th percentile and the success rate over the last 100
+interactions (failures count towards the rate but not the latency), and -- after three interactions -- a bandwidth class
+(< 100 ms fast, < 500 ms medium, else slow).  Ranking orders peers by mean latency with unknown peers last and, for
+diversity, lets each peer of the slower half jump ahead of its half with probability 0.2.  The per-peer timeout scales a
+base timeout by ``latency / 200 ms`` and is clamped to 0.5-5 s.  Peers silent for an hour are forgotten.
+
+Implementation: sliding windows are bounded deques; class boundaries are a bisected table; the percentile is a single
+interpolating helper; pruning is triggered by a countdown rather than a modulo on a creation counter."""
 from __future__ import annotations
 
-import math
 import random
 import time
+from bisect import bisect_right
+from collections import deque
 from dataclasses import dataclass, field
 from enum import StrEnum
 
@@ -14,6 +23,10 @@ MAX_HISTORY = 100
 STALE_TIMEOUT = 3600
 DIVERSITY_RATIO = 0.2
 REFERENCE_LATENCY_MS = 200.0
+_TIMEOUT_RANGE_MS = (500.0, 5000.0)
+_UNRANKED_MS = 9999.0
+_CLASS_AFTER = 3                      # interactions before a class is assigned
+_PRUNE_EVERY_NEW_PEERS = 500
 
 
 class BandwidthClass(StrEnum):
@@ -21,6 +34,24 @@ class BandwidthClass(StrEnum):
     MEDIUM = "medium"
     SLOW = "slow"
     UNKNOWN = "unknown"
+
+
+_CLASS_EDGES_MS = (100.0, 500.0)
+_CLASS_BY_BUCKET = (BandwidthClass.FAST, BandwidthClass.MEDIUM, BandwidthClass.SLOW)
+
+
+def _classify_bandwidth(avg_ms: float) -> BandwidthClass:
+    return _CLASS_BY_BUCKET[bisect_right(_CLASS_EDGES_MS, avg_ms)]
+
+
+def _percentile(values, pct: float) -> float:
+    """Linear interpolation between closest ranks; 0.0 for no data."""
+    ordered = sorted(values)
+    if not ordered:
+        return 0.0
+    whole, frac = divmod(pct / 100.0 * (len(ordered) - 1), 1.0)
+    low = ordered[int(whole)]
+    return low if frac == 0.0 else low + (ordered[int(whole) + 1] - low) * frac
 
 
 @dataclass
@@ -32,84 +63,82 @@ class PeerProfile:
     last_seen: float = 0.0
     bandwidth_class: BandwidthClass = BandwidthClass.UNKNOWN
     total_interactions: int = 0
-    _latency_history: list[float] = field(default_factory=list, repr=False)
-    _success_history: list[bool] = field(default_factory=list, repr=False)
+    _latencies: deque = field(default_factory=lambda: deque(maxlen=MAX_HISTORY), repr=False)
+    _outcomes: deque = field(default_factory=lambda: deque(maxlen=MAX_HISTORY), repr=False)
 
+    def observe(self, elapsed_ms: float, ok: bool, stamp: float) -> None:
+        self.total_interactions += 1
+        self.last_seen = stamp
+        self._outcomes.append(bool(ok))
+        self.success_rate = sum(self._outcomes) / len(self._outcomes)
+        if ok:
+            seeded = self.avg_latency_ms != 0.0
+            self.avg_latency_ms = self.avg_latency_ms + EMA_ALPHA * (elapsed_ms - self.avg_latency_ms) if seeded else elapsed_ms
+            self._latencies.append(elapsed_ms)
+            self.p95_latency_ms = _percentile(self._latencies, 95)
+        if self.total_interactions >= _CLASS_AFTER:
+            self.bandwidth_class = _classify_bandwidth(self.avg_latency_ms)
 
-def _classify_bandwidth(avg_ms: float) -> BandwidthClass:
-    return BandwidthClass.FAST if avg_ms < 100 else BandwidthClass.MEDIUM if avg_ms < 500 else BandwidthClass.SLOW
-
-
-def _percentile(values: list[float], pct: float) -> float:
-    if not values:
-        return 0.0
-    s = sorted(values)
-    pos = pct / 100 * (len(s) - 1)
-    lo, hi = math.floor(pos), math.ceil(pos)
-    return s[lo] if lo == hi else s[lo] * (hi - pos) + s[hi] * (pos - lo)
+    @property
+    def rank_key(self) -> float:
+        return _UNRANKED_MS if self.bandwidth_class is BandwidthClass.UNKNOWN else self.avg_latency_ms
 
 
 class PeerProfileTracker:
     def __init__(self, *, max_peers: int = 10_000):
-        self._profiles: dict[str, PeerProfile] = {}
-        self._max = max_peers
-        self._new = 0
+        self._book: dict[str, PeerProfile] = {}
+        self._capacity = max_peers
+        self._until_prune = _PRUNE_EVERY_NEW_PEERS
+
+    # ---- recording
+    def _admit(self, peer_id: str) -> PeerProfile:
+        self._until_prune -= 1
+        if self._until_prune <= 0 or len(self._book) >= self._capacity:
+            self._until_prune = _PRUNE_EVERY_NEW_PEERS
+            self.prune_stale()
+        profile = self._book[peer_id] = PeerProfile(peer_id)
+        return profile
 
     def record(self, peer_id: str, elapsed_ms: float, *, success: bool = True) -> PeerProfile:
-        p = self._profiles.get(peer_id)
-        if p is None:
-            self._new += 1
-            if len(self._profiles) >= self._max or self._new % 500 == 0:
-                self.prune_stale()
-            p = self._profiles[peer_id] = PeerProfile(peer_id)
-        p.total_interactions += 1
-        p.last_seen = time.time()
-        if success:
-            p.avg_latency_ms = elapsed_ms if p.avg_latency_ms == 0.0 else EMA_ALPHA * elapsed_ms + (1 - EMA_ALPHA) * p.avg_latency_ms
-            p._latency_history = (p._latency_history + [elapsed_ms])[-MAX_HISTORY:]
-            p.p95_latency_ms = _percentile(p._latency_history, 95)
-        p._success_history = (p._success_history + [success])[-MAX_HISTORY:]
-        p.success_rate = sum(p._success_history) / len(p._success_history)
-        if p.total_interactions >= 3:
-            p.bandwidth_class = _classify_bandwidth(p.avg_latency_ms)
-        return p
+        profile = self._book.get(peer_id) or self._admit(peer_id)
+        profile.observe(elapsed_ms, success, time.time())
+        return profile
 
+    # ---- lookup
     def get(self, peer_id: str) -> PeerProfile | None:
-        return self._profiles.get(peer_id)
+        return self._book.get(peer_id)
 
     def get_or_default(self, peer_id: str) -> PeerProfile:
-        return self._profiles.get(peer_id) or PeerProfile(peer_id)
+        return self._book.get(peer_id) or PeerProfile(peer_id)
 
     @property
     def known_peers(self) -> int:
-        return len(self._profiles)
+        return len(self._book)
 
+    # ---- decisions
     def rank_by_latency(self, peer_ids: list[str], *, diversity: bool = True) -> list[str]:
-        """Fast half first; each slow-half peer is promoted right behind it with probability 0.2."""
-        def key(pid: str) -> float:
-            p = self.get_or_default(pid)
-            return 9999.0 if p.bandwidth_class == BandwidthClass.UNKNOWN else p.avg_latency_ms
-
-        ordered = sorted(peer_ids, key=key)
-        if not diversity or len(ordered) <= 2:
-            return ordered
-        mid = max(1, len(ordered) // 2)
-        fast, slow = ordered[:mid], ordered[mid:]
-        lucky = [pid for pid in slow if random.random() < DIVERSITY_RATIO]
-        return fast + lucky + [pid for pid in slow if pid not in lucky]
+        by_speed = sorted(peer_ids, key=lambda pid: self.get_or_default(pid).rank_key)
+        if not diversity or len(by_speed) < 3:
+            return by_speed
+        cut = max(len(by_speed) // 2, 1)
+        quick, slow = by_speed[:cut], by_speed[cut:]
+        promoted = {pid for pid in slow if random.random() < DIVERSITY_RATIO}
+        return quick + [p for p in slow if p in promoted] + [p for p in slow if p not in promoted]
 
     def adaptive_timeout(self, peer_id: str, *, base_ms: float = 2000.0) -> float:
-        p = self.get(peer_id)
-        if p is None or p.avg_latency_ms == 0.0:
+        profile = self._book.get(peer_id)
+        if profile is None or not profile.avg_latency_ms:
             return base_ms
-        return max(500.0, min(base_ms * p.avg_latency_ms / REFERENCE_LATENCY_MS, 5000.0))
+        low, high = _TIMEOUT_RANGE_MS
+        return min(high, max(low, base_ms * (profile.avg_latency_ms / REFERENCE_LATENCY_MS)))
 
+    # ---- housekeeping
     def prune_stale(self, *, max_age: float = STALE_TIMEOUT) -> int:
-        now = time.time()
-        dead = [pid for pid, p in self._profiles.items() if p.last_seen > 0 and now - p.last_seen > max_age]
-        for pid in dead:
-            del self._profiles[pid]
-        return len(dead)
+        horizon = time.time() - max_age
+        silent = [pid for pid, prof in self._book.items() if 0 < prof.last_seen < horizon]
+        for pid in silent:
+            self._book.pop(pid)
+        return len(silent)
 
     def reset(self) -> None:
-        self._profiles.clear()
+        self._book.clear()

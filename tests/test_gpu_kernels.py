@@ -67,7 +67,9 @@ def test_quantize_rows_e4m3_matches_oracle():
     x[5] = 0
     q8, sc = quantize_rows_e4m3(x)
     r8, rsc = quantize_rows_e4m3_ref(x)
-    assert torch.equal(sc, rsc)
+    live = torch.ones(777, dtype=torch.bool, device=DEV)
+    live[5] = False                                  # an all-zero row may carry any finite scale
+    assert torch.equal(sc[live], rsc[live]) and torch.isfinite(sc).all() and (q8[5] == 0).all()
     deq = q8.view(torch.float8_e4m3fn).float() * sc[:, None]
     ref = r8.view(torch.float8_e4m3fn).float() * rsc[:, None]
     assert (deq - ref).abs().max().item() <= 1e-6 + 0.07 * x.float().abs().max().item()   # at most one e4m3 ulp apart
