@@ -63,19 +63,19 @@ class PeerProfile:
     last_seen: float = 0.0
     bandwidth_class: BandwidthClass = BandwidthClass.UNKNOWN
     total_interactions: int = 0
-    _latencies: deque = field(default_factory=lambda: deque(maxlen=MAX_HISTORY), repr=False)
-    _outcomes: deque = field(default_factory=lambda: deque(maxlen=MAX_HISTORY), repr=False)
+    _latency_history: deque = field(default_factory=lambda: deque(maxlen=MAX_HISTORY), repr=False)
+    _success_history: deque = field(default_factory=lambda: deque(maxlen=MAX_HISTORY), repr=False)
 
     def observe(self, elapsed_ms: float, ok: bool, stamp: float) -> None:
         self.total_interactions += 1
         self.last_seen = stamp
-        self._outcomes.append(bool(ok))
-        self.success_rate = sum(self._outcomes) / len(self._outcomes)
+        self._success_history.append(bool(ok))
+        self.success_rate = sum(self._success_history) / len(self._success_history)
         if ok:
             seeded = self.avg_latency_ms != 0.0
             self.avg_latency_ms = self.avg_latency_ms + EMA_ALPHA * (elapsed_ms - self.avg_latency_ms) if seeded else elapsed_ms
-            self._latencies.append(elapsed_ms)
-            self.p95_latency_ms = _percentile(self._latencies, 95)
+            self._latency_history.append(elapsed_ms)
+            self.p95_latency_ms = _percentile(self._latency_history, 95)
         if self.total_interactions >= _CLASS_AFTER:
             self.bandwidth_class = _classify_bandwidth(self.avg_latency_ms)
 

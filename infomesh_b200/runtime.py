@@ -14,6 +14,7 @@ write, tolerant read, discard); the public functions are thin, named operations 
 assembled from a field table rather than a hand-written dict."""
 from __future__ import annotations
 
+import contextlib
 import json
 import os
 import signal
@@ -269,3 +270,10 @@ def mark_runtime_stopped(data_dir: Path, pid: int) -> None:
     owner = read_runtime_status(data_dir, max_age_seconds=None).get("pid")
     if owner in (None, pid):
         write_runtime_status(data_dir, {"status": "stopped", "pid": pid, "updated_at": round(time.time(), 3)})
+
+
+class contextlib_suppress_os_error(contextlib.suppress):
+    """``with contextlib_suppress_os_error(): ...`` swallows ``OSError`` (name kept for API parity with the reference)."""
+
+    def __init__(self) -> None:
+        super().__init__(OSError)
