@@ -77,3 +77,30 @@ def test_reference_arm_runs_search_hybrid():
     assert line["same_config"] is False and line["gpu_launches"] == 0
     # the 2-3 AND-ed terms come from a real document, so FTS5 contributed to the fused top-10
     assert line["config"]["last_query_fts_hits_in_top10"] >= 1
+
+
+def test_merkle_roots_and_proofs_interoperate_with_the_reference():
+    """Proofs are wire format: a proof built by either implementation must verify in the other (scripts/diff_interop.py
+    covers the codec; this covers trust/merkle.py)."""
+    import hashlib
+    import sys
+
+    root = Path(__file__).resolve().parent.parent / "baseline"
+    if not (root / "_ref" / "infomesh" / "trust" / "merkle.py").exists():
+        pytest.skip("reference not installed")
+    sys.path[:0] = [str(root / "shims"), str(root / "_ref")]
+    try:
+        from infomesh.trust import merkle as R
+    finally:
+        del sys.path[:2]
+    from infomesh_b200.trust import merkle as M
+
+    for n in (1, 2, 3, 5, 8, 13, 64):
+        hs = [hashlib.sha256(str(i).encode()).hexdigest() for i in range(n)]
+        a, b = R.MerkleTree(), M.MerkleTree()
+        assert a.build(hs) == b.build(hs)
+        for i in range(n):
+            wire_theirs, wire_ours = R.serialize_proof(a.get_proof(i)), M.serialize_proof(b.get_proof(i))
+            assert [(h, str(s)) for h, s in wire_theirs["proof_path"]] == [(h, str(s)) for h, s in wire_ours["proof_path"]]
+            assert M.MerkleTree.verify_document(hs[i], M.deserialize_proof(wire_theirs))
+            assert R.MerkleTree.verify_document(hs[i], R.deserialize_proof(wire_ours))
