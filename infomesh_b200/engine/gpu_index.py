@@ -175,7 +175,14 @@ class GpuSearchIndex:
             csr["per_rank"] = per
             self.row_base = lo
         passages = _passage_arrays(builder, docs_text)          # after every term is registered
-        passages["neg_age"] = np.asarray(crawled, dtype=np.float64) - t0      # seconds before this build (<= 0), fp32-safe
+        t_ref = t0
+        if self.shard_world > 1:      # one reference instant for every rank: the fused scores must agree bit for bit
+            import torch.distributed as dist
+
+            box = torch.tensor([t0], dtype=torch.float64, device=dev)
+            dist.broadcast(box, src=0)
+            t_ref = float(box.item())
+        passages["neg_age"] = np.asarray(crawled, dtype=np.float64) - t_ref   # seconds before this build (<= 0), fp32-safe
         passages["authority"] = np.asarray(auth, dtype=np.float32) if auth else None
         del docs_text
         vectors = torch.cat(vec_chunks).contiguous()
@@ -475,14 +482,19 @@ def format_hits(store, chunk: list[str], k: int, arr: dict[str, np.ndarray]) -> 
 
 
 def merge_shard_arrays(parts: list[dict[str, np.ndarray]]) -> dict[str, np.ndarray]:
-    """Combine the per-rank views of ONE collective search: scores / rows are identical on every rank (the final
-    selection runs everywhere), ``doc_ids`` / ``pass`` / ``span`` are filled only by the rank that owns the row."""
+    """Combine the per-rank views of ONE collective search.  Rank 0's scores / rows are the answer; ``doc_ids`` / ``pass`` /
+    ``span`` of a row come from the rank that owns it, matched BY ROW VALUE inside the same query -- the final selection
+    runs on every rank and near-ties may land in a different slot there, so positions are not trusted."""
     out = {key: np.array(val, copy=True) for key, val in parts[0].items()}
+    want = out["rows"]                                                     # [nq, k]
     for part in parts[1:]:
-        fill = (out["doc_ids"] < 0) & (part["doc_ids"] >= 0)
-        for key in ("doc_ids", "pass"):
-            out[key][fill] = part[key][fill]
-        out["span"][fill] = part["span"][fill]
+        have = part["rows"]
+        same = (have[:, :, None] == want[:, None, :]) & (part["doc_ids"][:, :, None] >= 0) & (want[:, None, :] >= 0)   # [nq, k_src, k_dst]
+        src = same.argmax(axis=1)                                          # for each destination slot: source slot (if any)
+        hit = same.any(axis=1) & (out["doc_ids"] < 0)
+        q = np.broadcast_to(np.arange(want.shape[0])[:, None], want.shape)
+        for key in ("doc_ids", "pass", "span"):
+            out[key][hit] = part[key][q[hit], src[hit]]
     return out
 
 

@@ -104,6 +104,9 @@ def rerank_select(logits, cand_ids, k_out, out_scores=None, out_ids=None):
     return out_scores, out_ids
 
 
+_WEIGHT_CACHE: dict = {}
+
+
 def rank_fuse(bm25, rows, k_out, *, crawled_at=None, trust=None, authority=None, title_match=None, url_path=None, now=None,
               weights=None, row_base: int = 0, want_signals: bool = False):
     """K12 on the device: the reference's six-signal ``combined_score`` + sort (infomesh/index/ranking.py:104-148,171-238).
@@ -116,7 +119,10 @@ def rank_fuse(bm25, rows, k_out, *, crawled_at=None, trust=None, authority=None,
 
     nq, n = rows.shape
     dev = rows.device
-    w = torch.tensor(R.weight_vector(weights), dtype=torch.float32, device=dev)
+    key = (str(dev), tuple(sorted((weights or {}).items())))
+    w = _WEIGHT_CACHE.get(key)
+    if w is None:            # uploaded once per (device, override set): no H2D copy inside a captured step
+        w = _WEIGHT_CACHE[key] = torch.tensor(R.weight_vector(weights), dtype=torch.float32).to(dev)
     out_s = torch.empty((nq, k_out), device=dev, dtype=torch.float32)
     out_r = torch.empty((nq, k_out), device=dev, dtype=torch.int64)
     sig = torch.zeros((nq, k_out, 6), device=dev, dtype=torch.float32) if want_signals else None

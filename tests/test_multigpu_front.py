@@ -96,6 +96,11 @@ def test_merge_and_format():
     b = {"scores": a["scores"], "rows": a["rows"], "doc_ids": np.array([[-1, 55, -1]]), "pass": np.array([[-1, 1, -1]]),
          "span": np.array([[[-1, -1], [2, 6], [-1, -1]]])}
     m = merge_shard_arrays([a, b])
+    # the owning rank may hold the row in another slot (near-ties resolved differently): matched by row value
+    b2 = {"scores": a["scores"], "rows": np.array([[5, 0, 2]]), "doc_ids": np.array([[55, -1, -1]]), "pass": np.array([[1, -1, -1]]),
+          "span": np.array([[[2, 6], [-1, -1], [-1, -1]]])}
+    m2 = merge_shard_arrays([a, b2])
+    assert m2["doc_ids"].tolist() == [[10, 55, 12]] and m2["span"][0, 1].tolist() == [2, 6]
     assert m["doc_ids"].tolist() == [[10, 55, 12]] and m["pass"].tolist() == [[0, 1, -1]] and m["span"][0, 1].tolist() == [2, 6]
 
     class Doc:
