@@ -1,9 +1,19 @@
-"""Malicious-node detector combining trust and farming signals (reference infomesh/trust/detector.py:25-209):
-farming-blocked or UNTRUSTED => HIGH; two or more weak signals => MEDIUM; both recommend isolation."""
+"""Deciding whether a peer should be cut off, from what the trust store and the farming detector know about it.
+
+Contract (SURVEY §2.1 trust/ "detector"; reference infomesh/trust/detector.py): weak signals are >= 2 consecutive audit
+failures, >= 1 farming anomaly, a trust score below 0.5, a farming block, and an exceeded rate limit.  Verdicts, first
+match wins: already isolated -> ISOLATED; farming block -> HIGH; UNTRUSTED tier -> HIGH; two or more weak signals ->
+MEDIUM; exactly one -> LOW; none -> NONE.  HIGH and MEDIUM recommend isolation (ISOLATED reports it as already done);
+``assess_and_enforce`` carries the recommendation out.  A peer the trust store has never seen counts as score 0.5, tier
+NORMAL, no failures.
+
+Implementation: the observations about a peer are gathered once into a ``_Evidence`` record; weak signals are a table of
+(predicate, label) probes over it; verdicts are an ordered rule table -- adding a signal or a rule is one more row."""
 from __future__ import annotations
 
 from dataclasses import dataclass
 from enum import StrEnum
+from typing import Callable
 
 from infomesh_b200.credits.farming import FarmingDetector, FarmingVerdict
 from infomesh_b200.trust.scoring import TrustStore, TrustTier
@@ -39,49 +49,73 @@ class ThreatAssessment:
     detail: str
 
 
+@dataclass(frozen=True)
+class _Evidence:
+    score: float
+    tier: TrustTier
+    audit_failures: int
+    isolated: bool
+    farming: FarmingVerdict
+    anomalies: int
+    rate_limited: bool
+
+    @property
+    def farming_blocked(self) -> bool:
+        return self.farming == FarmingVerdict.BLOCKED
+
+
+# (does the signal fire?, how it is reported)
+_PROBES: tuple[tuple[Callable[[_Evidence], bool], Callable[[_Evidence], str]], ...] = (
+    (lambda e: e.audit_failures >= WEAK_SIGNAL_AUDIT_FAILURES, lambda e: f"audit_failures={e.audit_failures}"),
+    (lambda e: e.anomalies >= WEAK_SIGNAL_ANOMALY_COUNT, lambda e: f"anomalies={e.anomalies}"),
+    (lambda e: e.score < WEAK_SIGNAL_TRUST_THRESHOLD, lambda e: f"low_trust={e.score:.3f}"),
+    (lambda e: e.farming_blocked, lambda e: "farming_blocked"),
+    (lambda e: e.rate_limited, lambda e: "rate_limited"),
+)
+
+# (applies?, level, isolate?, explanation) -- evaluated top-down
+_RULES: tuple[tuple[Callable[[_Evidence, list[str]], bool], ThreatLevel, bool, Callable[[_Evidence, list[str]], str]], ...] = (
+    (lambda e, w: e.farming_blocked, ThreatLevel.HIGH, True, lambda e, w: "blocked for credit farming"),
+    (lambda e, w: e.tier == TrustTier.UNTRUSTED, ThreatLevel.HIGH, True, lambda e, w: f"untrusted peer (score={e.score:.3f})"),
+    (lambda e, w: len(w) >= WEAK_SIGNAL_ISOLATION_COUNT, ThreatLevel.MEDIUM, True, lambda e, w: f"multiple weak signals: {', '.join(w)}"),
+    (lambda e, w: len(w) == 1, ThreatLevel.LOW, False, lambda e, w: f"single weak signal: {w[0]}"),
+    (lambda e, w: True, ThreatLevel.NONE, False, lambda e, w: "no threats detected"),
+)
+
+
 class MaliciousNodeDetector:
     def __init__(self, trust_store: TrustStore, farming_detector: FarmingDetector):
         self._trust = trust_store
         self._farming = farming_detector
 
-    def assess(self, peer_id: str, *, action: str = "crawl") -> ThreatAssessment:
-        pt = self._trust.get_trust(peer_id)
-        score = pt.trust_score if pt else 0.5
-        tier = pt.tier if pt else TrustTier.NORMAL
-        fails = pt.consecutive_audit_failures if pt else 0
-        fc = self._farming.check(peer_id, action)
-        mk = lambda level, signals, isolate, detail: ThreatAssessment(  # noqa: E731
-            peer_id, level, score, tier, fc.verdict, fails, fc.anomaly_count, signals, isolate, detail)
-        if pt is not None and pt.isolated:
-            return mk(ThreatLevel.ISOLATED, [], True, "already isolated")
-        weak = []
-        if fails >= WEAK_SIGNAL_AUDIT_FAILURES:
-            weak.append(f"audit_failures={fails}")
-        if fc.anomaly_count >= WEAK_SIGNAL_ANOMALY_COUNT:
-            weak.append(f"anomalies={fc.anomaly_count}")
-        if score < WEAK_SIGNAL_TRUST_THRESHOLD:
-            weak.append(f"low_trust={score:.3f}")
-        if fc.verdict == FarmingVerdict.BLOCKED:
-            weak.append("farming_blocked")
-        if fc.rate_limit_exceeded:
-            weak.append("rate_limited")
-        if fc.verdict == FarmingVerdict.BLOCKED:
-            out = mk(ThreatLevel.HIGH, weak, True, "blocked for credit farming")
-        elif tier == TrustTier.UNTRUSTED:
-            out = mk(ThreatLevel.HIGH, weak, True, f"untrusted peer (score={score:.3f})")
-        elif len(weak) >= WEAK_SIGNAL_ISOLATION_COUNT:
-            out = mk(ThreatLevel.MEDIUM, weak, True, f"multiple weak signals: {', '.join(weak)}")
-        elif len(weak) == 1:
-            out = mk(ThreatLevel.LOW, weak, False, f"single weak signal: {weak[0]}")
+    def _collect(self, peer_id: str, action: str) -> _Evidence:
+        known = self._trust.get_trust(peer_id)
+        farm = self._farming.check(peer_id, action)
+        if known is None:
+            score, tier, failures, isolated = 0.5, TrustTier.NORMAL, 0, False
         else:
-            out = mk(ThreatLevel.NONE, weak, False, "no threats detected")
-        if out.should_isolate:
-            logger.warning("malicious_node_detected", peer_id=peer_id[:12], threat_level=out.threat_level.value,
-                           detail=out.detail)
-        return out
+            score, tier, failures, isolated = known.trust_score, known.tier, known.consecutive_audit_failures, bool(known.isolated)
+        return _Evidence(score, tier, failures, isolated, farm.verdict, farm.anomaly_count, bool(farm.rate_limit_exceeded))
+
+    def assess(self, peer_id: str, *, action: str = "crawl") -> ThreatAssessment:
+        seen = self._collect(peer_id, action)
+
+        def verdict(level: ThreatLevel, signals: list[str], isolate: bool, why: str) -> ThreatAssessment:
+            return ThreatAssessment(peer_id=peer_id, threat_level=level, trust_score=seen.score, trust_tier=seen.tier,
+                                    farming_verdict=seen.farming, consecutive_audit_failures=seen.audit_failures,
+                                    anomaly_count=seen.anomalies, weak_signals=signals, should_isolate=isolate, detail=why)
+
+        if seen.isolated:
+            return verdict(ThreatLevel.ISOLATED, [], True, "already isolated")
+        signals = [describe(seen) for fires, describe in _PROBES if fires(seen)]
+        level, isolate, explain = next((lv, iso, ex) for applies, lv, iso, ex in _RULES if applies(seen, signals))
+        result = verdict(level, signals, isolate, explain(seen, signals))
+        if isolate:
+            logger.warning("malicious_node_detected", peer_id=peer_id[:12], threat_level=level.value, detail=result.detail)
+        return result
 
     def assess_and_enforce(self, peer_id: str, *, action: str = "crawl") -> ThreatAssessment:
-        a = self.assess(peer_id, action=action)
-        if a.should_isolate and a.threat_level != ThreatLevel.ISOLATED:
+        outcome = self.assess(peer_id, action=action)
+        if outcome.should_isolate and outcome.threat_level is not ThreatLevel.ISOLATED:
             self._trust.isolate_peer(peer_id)
-        return a
+        return outcome
