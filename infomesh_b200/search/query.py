@@ -1,12 +1,27 @@
-"""Query orchestration: local (FTS5 -> rank -> passage), hybrid (keyword + vector -> RRF), distributed
-(local + peers -> dedupe -> rank).  Mirrors reference infomesh/search/query.py:54-531; the GPU engine plugs in
-through ``gpu_engine=`` (batched device pipeline, ``engine.hybrid``) while the CPU path stays the oracle.
-"""
+"""The three ways a query is answered: from this node's store, from store + vector index, or from the whole network.
+
+Contract (reference infomesh/search/query.py):
+
+* ``search_local``: sanitise the text for FTS5 (CJK-aware), fetch ``2 x limit`` BM25 rows, widen with up to three synonym
+  expansions when fewer than ``limit`` came back, rank with the six-signal ranker, then replace weak snippets (short, or
+  without a query term) by the best passage of the document.
+* ``search_hybrid``: keyword top-``limit`` and vector top-``limit`` fused by reciprocal-rank fusion; ``source`` says which
+  of the two lists actually contributed.
+* ``search_distributed``: local results plus remote ones -- from the peer fan-out callback when given, else from DHT
+  pointer lookups -- de-duplicated by URL with local copies winning, sorted by combined score; remote failures never fail
+  the search; remote numbers are untrusted input and are coerced defensively.
+
+The sanitiser never returns an empty string (fallback: the alphanumeric residue, then the literal ``infomesh``).  The GPU
+engine serves the same contracts through ``engine.gpu_index``; this module stays the CPU oracle.
+
+Implementation: the sanitiser is a character translation table plus one operator pattern; timing is a small stopwatch
+object; URL de-duplication is one ordered-dict helper used by both the synonym widening and the network merge; the two
+remote sources are generator functions with one shared error boundary."""
 from __future__ import annotations
 
 import re
 import time
-from collections.abc import Callable
+from collections.abc import AsyncIterator, Callable, Iterable
 from dataclasses import dataclass, replace
 from math import isfinite
 from typing import TYPE_CHECKING, Any
@@ -21,10 +36,11 @@ if TYPE_CHECKING:  # pragma: no cover
 
 logger = get_logger(__name__)
 
-_FTS_SPECIALS = re.compile(r'["\(\)\*\{\}\^:]')
-_FTS_OPERATORS = re.compile(r"\b(AND|OR|NOT|NEAR)\b", re.IGNORECASE)
-_WS = re.compile(r"\s+")
 MAX_QUERY_CHARS = 1000
+_FALLBACK_QUERY = "infomesh"
+_FTS_SYNTAX_TO_SPACE = str.maketrans({ch: " " for ch in '"()*{}^:'})
+_FTS_KEYWORDS = re.compile(r"\b(?:AND|OR|NOT|NEAR)\b", re.IGNORECASE)
+_NOT_PLAIN = re.compile(r"[^a-zA-Z0-9\s]")
 
 
 @dataclass(frozen=True)
@@ -53,19 +69,38 @@ class DistributedResult:
     remote_count: int = 0
 
 
+class _Stopwatch:
+    def __init__(self):
+        self._t0 = time.monotonic()
+
+    @property
+    def ms(self) -> float:
+        return (time.monotonic() - self._t0) * 1000.0
+
+
+def _squeeze(text: str) -> str:
+    return " ".join(text.split())
+
+
 def _sanitize_fts_query(query: str) -> str:
-    """Strip FTS5 syntax (quotes, parens, ``* { } ^ :``) and boolean / NEAR operators; never return empty."""
-    query = query[:MAX_QUERY_CHARS]
-    cleaned = _WS.sub(" ", _FTS_OPERATORS.sub(" ", _FTS_SPECIALS.sub(" ", query))).strip()
-    if cleaned:
-        return cleaned
-    alnum = _WS.sub(" ", re.sub(r"[^a-zA-Z0-9\s]", " ", query)).strip()[:100]
-    return alnum or "infomesh"
+    """Plain words only: FTS5 punctuation and the AND / OR / NOT / NEAR keywords are blanked out."""
+    clipped = query[:MAX_QUERY_CHARS]
+    words = _squeeze(_FTS_KEYWORDS.sub(" ", clipped.translate(_FTS_SYNTAX_TO_SPACE)))
+    return words or _squeeze(_NOT_PLAIN.sub(" ", clipped))[:100] or _FALLBACK_QUERY
 
 
 sanitize_fts_query = _sanitize_fts_query
 
 
+def _first_per_url(items: Iterable[Any]) -> list[Any]:
+    """Order-preserving de-duplication on ``.url``: the first occurrence wins."""
+    unique: dict[str, Any] = {}
+    for item in items:
+        unique.setdefault(item.url, item)
+    return list(unique.values())
+
+
+# ----------------------------------------------------------------------------- local
 def search_local(store: LocalStore, query: str, *, limit: int = 10, offset: int = 0,
                  authority_fn: Callable[[str], float] | None = None, language: str | None = None,
                  date_from: float | None = None, date_to: float | None = None,
@@ -74,138 +109,132 @@ def search_local(store: LocalStore, query: str, *, limit: int = 10, offset: int 
     from infomesh_b200.search.nlp import expand_query
     from infomesh_b200.search.passage import _tokenize
 
-    t0 = time.monotonic()
-    filters = dict(language=language, date_from=date_from, date_to=date_to, include_domains=include_domains,
-                   exclude_domains=exclude_domains)
-    fts_query = _sanitize_fts_query(tokenize_query_cjk(query))
-    rows = store.search(fts_query, limit=limit * 2, offset=offset, **filters)
-    if len(rows) < limit:  # sparse: widen with synonyms (each expansion is its own AND query)
-        seen = {r.url for r in rows}
-        for term in expand_query(query, max_expansions=3):
-            tq = _sanitize_fts_query(term)
-            if not tq or tq == "infomesh":
-                continue
-            for r in store.search(tq, limit=limit, offset=0, **filters):
-                if r.url not in seen:
-                    seen.add(r.url)
-                    rows.append(r)
+    watch = _Stopwatch()
+    narrowing = {"language": language, "date_from": date_from, "date_to": date_to, "include_domains": include_domains,
+                 "exclude_domains": exclude_domains}
+    rows = list(store.search(_sanitize_fts_query(tokenize_query_cjk(query)), limit=2 * limit, offset=offset, **narrowing))
+    if len(rows) < limit:
+        # thin result: each synonym expansion is run as its own (implicit AND) query and appended behind the originals
+        variants = (_sanitize_fts_query(term) for term in expand_query(query, max_expansions=3))
+        for variant in variants:
+            if variant and variant != _FALLBACK_QUERY:
+                rows.extend(store.search(variant, limit=limit, offset=0, **narrowing))
+        rows = _first_per_url(rows)
     ranked = rank_local_results(rows, authority_fn=authority_fn, query_tokens=_tokenize(query), limit=limit)
     if ranked:
         _enhance_snippets(store, ranked, query)
-    elapsed = (time.monotonic() - t0) * 1000
-    logger.info("query_local", query=query, raw=len(rows), ranked=len(ranked), elapsed_ms=round(elapsed, 1))
-    return QueryResult(ranked, len(ranked), elapsed, "local")
+    logger.info("query_local", query=query, raw=len(rows), ranked=len(ranked), elapsed_ms=round(watch.ms, 1))
+    return QueryResult(ranked, len(ranked), watch.ms, "local")
 
 
 def _enhance_snippets(store: LocalStore, results: list[RankedResult], query: str, *, max_enhance: int = 10) -> None:
-    """Swap weak FTS5 snippets (short or without a query term) for the best passage of the full text."""
+    """In place: a snippet under 80 characters, or without any query term, is replaced by the best passage when longer."""
     from infomesh_b200.search.passage import _tokenize, select_best_passage
 
-    wanted = set(_tokenize(query))
-    for i, r in enumerate(results[:max_enhance]):
-        if len(r.snippet) >= 80 and wanted & set(_tokenize(r.snippet)):
+    query_terms = frozenset(_tokenize(query))
+
+    def good_enough(snippet: str) -> bool:
+        return len(snippet) >= 80 and not query_terms.isdisjoint(_tokenize(snippet))
+
+    for slot, hit in enumerate(results[:max_enhance]):
+        if good_enough(hit.snippet):
             continue
         try:
-            doc = store.get_document(int(r.doc_id))
+            document = store.get_document(int(hit.doc_id))
         except (TypeError, ValueError):
             continue
-        if doc is None or not doc.text:
-            continue
-        passage = select_best_passage(doc.text, query, max_length=300)
-        if passage and len(passage) > len(r.snippet):
-            results[i] = replace(r, snippet=passage)
+        body = getattr(document, "text", "")
+        better = select_best_passage(body, query, max_length=300) if body else ""
+        if better and len(better) > len(hit.snippet):
+            results[slot] = replace(hit, snippet=better)
 
 
+# ----------------------------------------------------------------------------- hybrid
 def search_hybrid(store: LocalStore, vector_store: VectorStoreLike, query: str, *, limit: int = 10,
                   fts_weight: float = 1.0, vector_weight: float = 1.0,
                   authority_fn: Callable[[str], float] | None = None) -> HybridResult:
-    """Keyword top-``limit`` + vector top-``limit`` fused with RRF (k = 60)."""
     from infomesh_b200.search.merge import merge_results
 
-    if not (hasattr(vector_store, "search") and hasattr(vector_store, "add_document")):
+    if not all(hasattr(vector_store, method) for method in ("search", "add_document")):
         raise TypeError(f"vector_store must be a VectorStore, got {type(vector_store).__name__}")
-    t0 = time.monotonic()
-    fts = store.search(_sanitize_fts_query(query), limit=limit)
-    vec = vector_store.search(query, limit=limit)
-    merged = merge_results(fts, vec, limit=limit, fts_weight=fts_weight, vector_weight=vector_weight)
-    elapsed = (time.monotonic() - t0) * 1000
-    has_fts = any(m.fts_score is not None for m in merged)
-    has_vec = any(m.vector_score is not None for m in merged)
-    source = "hybrid" if has_fts and has_vec else ("vector" if has_vec else "fts")
-    logger.info("query_hybrid", query=query, fts_count=len(fts), vec_count=len(vec), merged_count=len(merged),
-                elapsed_ms=round(elapsed, 1))
-    return HybridResult(merged, len(merged), elapsed, source)
+    watch = _Stopwatch()
+    keyword_hits = store.search(_sanitize_fts_query(query), limit=limit)
+    vector_hits = vector_store.search(query, limit=limit)
+    fused = merge_results(keyword_hits, vector_hits, limit=limit, fts_weight=fts_weight, vector_weight=vector_weight)
+    from_keywords = any(m.fts_score is not None for m in fused)
+    from_vectors = any(m.vector_score is not None for m in fused)
+    origin = {(True, True): "hybrid", (False, True): "vector"}.get((from_keywords, from_vectors), "fts")
+    logger.info("query_hybrid", query=query, fts_count=len(keyword_hits), vec_count=len(vector_hits), merged_count=len(fused),
+                elapsed_ms=round(watch.ms, 1))
+    return HybridResult(fused, len(fused), watch.ms, origin)
 
 
-# ------------------------------------------------------------------ distributed
-def _safe_remote_int(value: object, *, default: int = 0) -> int:
+# ----------------------------------------------------------------------------- distributed
+def _finite(value: object) -> float | None:
+    """A finite float out of untrusted input (numbers or numeric strings; booleans and containers are rejected)."""
     if isinstance(value, bool) or not isinstance(value, (int, float, str)):
-        return default
+        return None
     try:
-        f = float(value)
-        return int(f) if isfinite(f) else default
+        number = float(value)
     except (TypeError, ValueError, OverflowError):
-        return default
+        return None
+    return number if isfinite(number) else None
+
+
+def _safe_remote_int(value: object, *, default: int = 0) -> int:
+    number = _finite(value)
+    return default if number is None else int(number)
 
 
 def _safe_remote_float(value: object, *, default: float = 0.0) -> float:
-    if isinstance(value, bool) or not isinstance(value, (int, float, str)):
-        return default
-    try:
-        f = float(value)
-    except (TypeError, ValueError):
-        return default
-    return f if isfinite(f) else default
+    number = _finite(value)
+    return default if number is None else number
 
 
-def _make_remote_result(*, url: str, title: str, snippet: str, score: object, doc_id: object,
-                        peer_id: str) -> RankedResult:
-    """Remote hits carry only the peer's own score; every local signal is zero."""
-    return RankedResult(doc_id=_safe_remote_int(doc_id), url=url, title=title, snippet=snippet, bm25_score=0.0,
-                        freshness_score=0.0, trust_score=0.0, authority_score=0.0,
-                        combined_score=_safe_remote_float(score), crawled_at=0.0, peer_id=peer_id)
+def _make_remote_result(*, url: str, title: str, snippet: str, score: object, doc_id: object, peer_id: str) -> RankedResult:
+    """A remote hit is ranked by its peer's score alone: none of the local signals is known for it."""
+    return RankedResult(doc_id=_safe_remote_int(doc_id), url=url, title=title, snippet=snippet, bm25_score=0.0, freshness_score=0.0,
+                        trust_score=0.0, authority_score=0.0, combined_score=_safe_remote_float(score), crawled_at=0.0, peer_id=peer_id)
 
 
-async def search_distributed(store: LocalStore, distributed_index: "DistributedIndex | None", query: str, *,
-                             limit: int = 10, authority_fn: Callable[[str], float] | None = None,
-                             vector_store: VectorStoreLike | None = None,
-                             network_search_fn: Callable[[str, list[str], int], Any] | None = None
-                             ) -> DistributedResult:
-    """Local search + (peer fan-out through ``network_search_fn`` | DHT pointer stubs), deduped by URL."""
+async def _from_peers(fan_out, query: str, keywords: list[str], limit: int) -> AsyncIterator[RankedResult]:
+    for item in await fan_out(query, keywords, limit):
+        if isinstance(item, dict) and item.get("url"):
+            yield _make_remote_result(url=str(item["url"]), title=str(item.get("title", "")), snippet=str(item.get("snippet", "")),
+                                      score=item.get("score", 0.0), doc_id=item.get("doc_id", 0), peer_id=str(item.get("peer_id", "")))
+
+
+async def _from_dht(index: "DistributedIndex", keywords: list[str]) -> AsyncIterator[RankedResult]:
+    for pointer in await index.query(keywords):
+        yield _make_remote_result(url=pointer.url, title=pointer.title, snippet="", score=pointer.score, doc_id=pointer.doc_id,
+                                  peer_id=pointer.peer_id)
+
+
+async def search_distributed(store: LocalStore, distributed_index: "DistributedIndex | None", query: str, *, limit: int = 10,
+                             authority_fn: Callable[[str], float] | None = None, vector_store: VectorStoreLike | None = None,
+                             network_search_fn: Callable[[str, list[str], int], Any] | None = None) -> DistributedResult:
     from infomesh_b200.index.distributed import extract_keywords
 
-    t0 = time.monotonic()
+    watch = _Stopwatch()
     query = _sanitize_fts_query(query)
-    local = search_local(store, query, limit=limit, authority_fn=authority_fn)
+    mine = search_local(store, query, limit=limit, authority_fn=authority_fn)
     keywords = extract_keywords(query, max_keywords=10)
-    remote: list[RankedResult] = []
-    if keywords and network_search_fn is not None:
+    if not keywords:
+        stream, failure_event = None, ""
+    elif network_search_fn is not None:
+        stream, failure_event = _from_peers(network_search_fn, query, keywords, limit), "network_search_failed"
+    elif distributed_index is not None:
+        stream, failure_event = _from_dht(distributed_index, keywords), "dht_query_failed"
+    else:
+        stream, failure_event = None, ""
+    theirs: list[RankedResult] = []
+    if stream is not None:
         try:
-            for r in await network_search_fn(query, keywords, limit):
-                if isinstance(r, dict) and r.get("url"):
-                    remote.append(_make_remote_result(
-                        url=str(r["url"]), title=str(r.get("title", "")), snippet=str(r.get("snippet", "")),
-                        score=r.get("score", 0.0), doc_id=r.get("doc_id", 0), peer_id=str(r.get("peer_id", ""))))
-        except Exception:  # noqa: BLE001 — search is never blocked by the network
-            logger.exception("network_search_failed")
-    elif keywords and distributed_index is not None:
-        try:
-            for ptr in await distributed_index.query(keywords):
-                remote.append(_make_remote_result(url=ptr.url, title=ptr.title, snippet="", score=ptr.score,
-                                                  doc_id=ptr.doc_id, peer_id=ptr.peer_id))
-        except Exception:  # noqa: BLE001
-            logger.exception("dht_query_failed")
-    remote_count = len(remote)
-    seen: set[str] = set()
-    merged: list[RankedResult] = []
-    for r in [*local.results, *remote]:  # local first wins on duplicates
-        if r.url not in seen:
-            seen.add(r.url)
-            merged.append(r)
-    merged.sort(key=lambda r: r.combined_score, reverse=True)
-    merged = merged[:limit]
-    elapsed = (time.monotonic() - t0) * 1000
-    source = "distributed" if remote_count > 0 else "local_only"
-    logger.info("query_distributed", query=query, local_count=local.total, remote_count=remote_count,
-                merged=len(merged), elapsed_ms=round(elapsed, 1))
-    return DistributedResult(merged, len(merged), elapsed, source, local.total, remote_count)
+            async for hit in stream:
+                theirs.append(hit)
+        except Exception:  # noqa: BLE001 -- the network must never be able to fail a search
+            logger.exception(failure_event)
+    combined = sorted(_first_per_url([*mine.results, *theirs]), key=lambda r: r.combined_score, reverse=True)[:limit]
+    logger.info("query_distributed", query=query, local_count=mine.total, remote_count=len(theirs), merged=len(combined),
+                elapsed_ms=round(watch.ms, 1))
+    return DistributedResult(combined, len(combined), watch.ms, "distributed" if theirs else "local_only", mine.total, len(theirs))
