@@ -132,6 +132,11 @@ def main() -> int:
                     help="dense shard storage streamed by the similarity search.  fp8: e4m3 rows + per-row scale (half the HBM "
                          "bytes), 32-wide over-fetch re-scored exactly against the bf16 rows; `dense_recall_vs_bf16` reports "
                          "the agreement with the bf16 search on the timed batches")
+    ap.add_argument("--retrieval-sms", type=int, default=int(os.environ.get("INFOMESH_B200_BENCH_RETRIEVAL_SMS", "0")),
+                    help="pipelined mode: SMs reserved for the HBM-bound index scan while the previous batch's cross-encoder GEMMs "
+                         "run on the rest (0 = the two streams time-share the whole GPU)")
+    ap.add_argument("--sweep-overlap", default="", help="comma list of retrieval-sms values to A/B after the main run "
+                                                        "(each with the bf16 and the fp8 dense shard) -> `overlap_sweep`")
     ap.add_argument("--rerank-chunks", type=int, default=1, help="cross-encoder sub-batches per step (L2 residency)")
     ap.add_argument("--pipeline", choices=["on", "off"], default="on",
                     help="on: `value` keeps two batches in flight (retrieval of batch i+1 overlaps the cross-encoder of "
@@ -212,7 +217,8 @@ def main() -> int:
     hcfg = HybridConfig(nq=args.batch, pair_seq=args.pair_seq, rerank=not args.no_rerank, backend=args.impl,
                         use_graph=not args.no_graph, exchange=args.exchange, varlen=not args.no_varlen,
                         rerank_chunks=args.rerank_chunks, precision=precision, strict_graph=True,
-                        dense_dtype=args.dense if args.impl == "fused" else "bf16")
+                        dense_dtype=args.dense if args.impl == "fused" else "bf16",
+                        retrieval_sms=args.retrieval_sms if args.impl == "fused" else 0)
     dps = per if ptabs is not None else (n_global if world > 1 else n_local)
     ekw = dict(docs_per_shard=dps, passage_tables=ptabs, passage_len=scfg.passage_len) if ptabs is not None else dict(docs_per_shard=dps)
     eng = HybridEngine(shard, hcfg, **ekw)
@@ -323,6 +329,16 @@ def main() -> int:
     ids_ok = bool((out_i_host[:, 0] >= 0).float().mean() > 0.5)
 
     extras = {}
+    if args.sweep_overlap and pipelined:
+        sweep = []
+        for dd in ("bf16", "fp8"):
+            for r in [int(x) for x in args.sweep_overlap.split(",")]:
+                e2 = HybridEngine(shard, _replace(hcfg, retrieval_sms=r, dense_dtype=dd), encoder=eng.encoder, reranker=eng.reranker, **ekw)
+                ms2, per2 = timed_pipe(e2, dev_batches, (None, None), W, K)
+                sweep.append({"dense": dd, "retrieval_sms": r, "value": qps(ms2, K), "ms_per_step": round(ms2 / K, 4)})
+                del e2
+                torch.cuda.empty_cache()
+        extras["overlap_sweep"] = sweep
     if hcfg.dense_dtype == "fp8":
         # agreement of the fp8 (over-fetch + exact re-score) search with the exact bf16 search, same queries
         from infomesh_b200.ops import search as S_
@@ -476,7 +492,7 @@ def main() -> int:
                 "model": "bge-small-en encoder + bge-reranker-base cross-encoder (random-init)",
                 "index_docs": n_global, "dim": 384, "global_batch": B, "seq_len": args.pair_seq,
                 "query_tokens": hcfg.enc_seq, "candidates_per_query": hcfg.n_rerank, "top_k": hcfg.k_out,
-                "rerank": hcfg.rerank, "query_mix": args.query_mix, "dense_shard": hcfg.dense_dtype,
+                "rerank": hcfg.rerank, "query_mix": args.query_mix, "dense_shard": hcfg.dense_dtype, "retrieval_sms": hcfg.retrieval_sms,
                 "parallelism": f"doc-sharded index x{world} (dense vectors, postings"
                                + (", passage tokens read from the owning GPU over NVLink" if ptabs is not None else
                                   (", passages replicated" if world > 1 else ", passages"))

@@ -115,3 +115,31 @@ def launch_count() -> int:
 def reset_launch_count() -> None:
     global _launch_count
     _launch_count = 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# SM budgets.  The persistent kernels (GEMMs, similarity scan) launch one CTA per SM by default.  The serving pipeline
+# overlaps an HBM-bound scan with tensor-core-bound GEMMs on two streams; both kinds need a whole SM's shared memory, so
+# they only run side by side if each is told to leave SMs free.  ``sm_budget(kind)`` is what a wrapper uses when its
+# caller passed ``max_ctas=0``; ``with sm_budgets(gemm=136, scan=12): ...`` scopes a setting (launch dimensions are frozen
+# into a CUDA graph at capture time, so the scope only has to cover warm-up + capture).
+SM_BUDGET = {"gemm": 0, "scan": 0}
+
+
+def sm_budget(kind: str) -> int:
+    return SM_BUDGET.get(kind, 0)
+
+
+class sm_budgets:
+    def __init__(self, **limits: int):
+        self._new, self._old = limits, {}
+
+    def __enter__(self):
+        for kind, n in self._new.items():
+            self._old[kind] = SM_BUDGET.get(kind, 0)
+            SM_BUDGET[kind] = int(n)
+        return self
+
+    def __exit__(self, *exc):
+        SM_BUDGET.update(self._old)
+        return False

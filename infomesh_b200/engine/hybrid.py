@@ -41,6 +41,8 @@ class HybridConfig:
     rerank: bool = True
     dense: bool = True        # False: BM25-only retrieval (serving with an encoder that has no checkpoint weights)
     dense_dtype: str = "bf16"  # "fp8": e4m3 shard + row scales, 32-wide over-fetch re-scored against the bf16 rows (K3)
+    retrieval_sms: int = 0     # pipelined serving: SMs left to the HBM-bound scan while the cross-encoder GEMMs of the previous
+                               # batch run on the others (0 = no partition: the two streams time-share the whole GPU)
     rank_signals: bool = False  # BM25-only mode: order candidates with the six-signal rank fuse (K12) instead of raw BM25
     backend: str = "fused"    # "fused" | "torch"
     use_graph: bool = True
@@ -331,7 +333,17 @@ class HybridEngine:
             out_scores=torch.zeros((cfg.nq, cfg.k_out), device=dev, dtype=torch.float32),
             out_ids=torch.full((cfg.nq, cfg.k_out), -1, device=dev, dtype=torch.int64),
             host=None, done=None) for _ in range(2)]
-        self._sa, self._sb = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        # SA (retrieval) outranks SB: its small latency-bound kernels and the scan CTAs take an SM as soon as one frees up
+        self._sa, self._sb = torch.cuda.Stream(device=dev, priority=-1), torch.cuda.Stream(device=dev)
+        from infomesh_b200 import _native
+
+        r_sms = int(cfg.retrieval_sms)
+        n_sms = _native.require().im_sm_count()
+        # Both the scan and the GEMMs are persistent kernels that need an SM's whole shared memory, so they overlap only if
+        # each leaves room: the scan gets r_sms CTAs, the cross-encoder GEMMs n_sms - r_sms.  Launch dimensions are frozen at
+        # capture, so the budgets only have to be in force while a stage is warmed up and captured.
+        budget_a = _native.sm_budgets(scan=r_sms) if r_sms > 0 else _native.sm_budgets()
+        budget_b = _native.sm_budgets(gemm=n_sms - r_sms) if r_sms > 0 else _native.sm_budgets()
         cur = torch.cuda.current_stream()
         self._sa.wait_stream(cur)
         self._sb.wait_stream(cur)
@@ -358,10 +370,10 @@ class HybridEngine:
 
         # warm every stage eagerly in pipeline order (identical on every rank), then capture one graph per stage / parity
         for b in self._pbuf:
-            with torch.cuda.stream(self._sa):
+            with torch.cuda.stream(self._sa), budget_a:
                 stage_a(b)
             self._sb.wait_stream(self._sa)
-            with torch.cuda.stream(self._sb):
+            with torch.cuda.stream(self._sb), budget_b:
                 stage_b(b)
             self._sa.wait_stream(self._sb)
             with torch.cuda.stream(self._sa):
@@ -378,7 +390,11 @@ class HybridEngine:
             torch.cuda.synchronize()
             return out
 
-        self._ga, self._gb, self._gc = cap(stage_a, self._sa), cap(stage_b, self._sb), cap(stage_c, self._sa)
+        with budget_a:
+            self._ga = cap(stage_a, self._sa)
+        with budget_b:
+            self._gb = cap(stage_b, self._sb)
+        self._gc = cap(stage_c, self._sa)
         self._ev_a = [torch.cuda.Event() for _ in range(2)]
         self._ev_b = [torch.cuda.Event() for _ in range(2)]
         self._tick = 0

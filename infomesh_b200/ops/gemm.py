@@ -78,7 +78,7 @@ def linear(a, w, bias=None, residual=None, act=None, alpha=1.0, out=None, out_dt
         ctypes.c_void_p(rs.peer_c_ptr if rs else 0), ctypes.c_void_p(rs.peer_flags_ptr if rs else 0),
         ctypes.c_int(rs.rank if rs else 0), ctypes.c_int(rs.rows_per_rank if rs else 0),
         ctypes.c_void_p(ag.flags_ptr if ag else 0), ctypes.c_void_p(ag.state_ptr if ag else 0),
-        ctypes.c_int(ag.m_rotate if ag else 0), ctypes.c_int(max_ctas), _native.stream_ptr(),
+        ctypes.c_int(ag.m_rotate if ag else 0), ctypes.c_int(max_ctas or _native.sm_budget("gemm")), _native.stream_ptr(),
         rs.peer_c_host if rs else ctypes.c_void_p(0), ctypes.c_int(rs.world if rs else 0),
         _native.ptr(m_dev), ctypes.c_int(1 if fp8 else 0), _native.ptr(row_scale))
     _native.check(rc, "im_gemm_bf16_tn")

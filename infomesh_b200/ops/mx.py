@@ -174,7 +174,7 @@ def linear_mx(a: MxTensor, w: MxWeight, bias=None, residual=None, act=None, out=
                         ctypes.c_int(w.q.stride(0)), ctypes.c_int(ldc),
                         ctypes.c_int(residual.stride(0) if residual is not None else 0),
                         ctypes.c_int(ACT[act] if not isinstance(act, int) else act), ctypes.c_int(1 if out_mx else 0),
-                        _native.ptr(m_dev), ctypes.c_int(max_ctas), _native.stream_ptr(), ctypes.c_int(mode))
+                        _native.ptr(m_dev), ctypes.c_int(max_ctas or _native.sm_budget("gemm")), _native.stream_ptr(), ctypes.c_int(mode))
     if rc < 0:
         _native.check(rc, "im_gemm_mxf8")
     _native.count_launch()

@@ -34,6 +34,7 @@ def sim_topk_partials(q, docs, ktop=16, alive=None, max_ctas=0, thr_init=None):
     nq, dim = q.shape
     n_docs = docs.shape[0]
     L = _native.require()
+    max_ctas = max_ctas or _native.sm_budget("scan")
     sms = L.im_sm_count()
     tiles = (n_docs + 127) // 128
     grid = max(1, min(tiles, sms if max_ctas <= 0 else min(sms, max_ctas)))
@@ -64,6 +65,7 @@ def sim_topk_partials_f8(q8, q_scale, d8, d_scale, ktop=16, alive=None, max_ctas
     nq, dim = q8.shape
     n_docs = d8.shape[0]
     L = _native.require()
+    max_ctas = max_ctas or _native.sm_budget("scan")
     sms = L.im_sm_count()
     tiles = (n_docs + 127) // 128
     grid = max(1, min(tiles, sms if max_ctas <= 0 else min(sms, max_ctas)))
