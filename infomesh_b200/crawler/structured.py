@@ -1,15 +1,21 @@
-"""Structured metadata embedded in pages: JSON-LD, OpenGraph, meta description / keywords
-(reference infomesh/crawler/structured.py:14-92)."""
+"""Machine-readable metadata a page carries about itself: JSON-LD blocks, OpenGraph properties, description, keywords.
+
+Contract (SURVEY §2.1 crawler/ "structured data"; reference infomesh/crawler/structured.py): every
+``<script type="application/ld+json">`` body that parses contributes its object (or the objects of its top-level list);
+``<meta property|name="og:*" content=...>`` fills the OpenGraph map (later duplicates win); the first
+``<meta name="description">`` is the description; the first ``<meta name="keywords">`` is split on commas.  Malformed
+JSON-LD is skipped, never fatal; an object with nothing in it is falsy.
+
+Implementation: one pass of ``html.parser`` -- attributes are read as a mapping, so their order, quoting and case do not
+matter (a pattern over raw markup needs ``property`` before ``content``)."""
 from __future__ import annotations
 
 import json
-import re
-from dataclasses import dataclass, field
+from dataclasses import asdict, dataclass, field
+from html.parser import HTMLParser
 
-_JSON_LD = re.compile(r'<script[^>]*type=["\']application/ld\+json["\'][^>]*>(.*?)</script>', re.S | re.I)
-_OG = re.compile(r'<meta\s+(?:property|name)=["\']og:([^"\']+)["\']\s+content=["\']([^"\']*)["\']', re.I)
-_DESC = re.compile(r'<meta\s+name=["\']description["\']\s+content=["\']([^"\']*)["\']', re.I)
-_KEYWORDS = re.compile(r'<meta\s+name=["\']keywords["\']\s+content=["\']([^"\']*)["\']', re.I)
+_LD_TYPE = "application/ld+json"
+_OG_PREFIX = "og:"
 
 
 @dataclass
@@ -20,30 +26,65 @@ class StructuredData:
     meta_keywords: list[str] = field(default_factory=list)
 
     def to_dict(self) -> dict[str, object]:
-        return {"json_ld": self.json_ld, "opengraph": self.opengraph, "meta_description": self.meta_description,
-                "meta_keywords": self.meta_keywords}
+        return asdict(self)
 
     def __bool__(self) -> bool:
-        return bool(self.json_ld or self.opengraph or self.meta_description or self.meta_keywords)
+        return any(asdict(self).values())
+
+
+class _MetadataReader(HTMLParser):
+    def __init__(self):
+        super().__init__(convert_charrefs=True)
+        self.found = StructuredData()
+        self._ld_buffer: list[str] | None = None      # not None while inside a JSON-LD <script>
+        self._have_description = self._have_keywords = False
+
+    # ---- <meta>
+    def _on_meta(self, attrs: dict[str, str]) -> None:
+        key = (attrs.get("property") or attrs.get("name") or "").strip()
+        if "content" not in attrs or not key:
+            return
+        value, folded = attrs["content"], key.lower()
+        if folded.startswith(_OG_PREFIX) and len(key) > len(_OG_PREFIX):
+            self.found.opengraph[key[len(_OG_PREFIX):]] = value
+        elif folded == "description" and "name" in attrs and not self._have_description:
+            self.found.meta_description, self._have_description = value.strip(), True
+        elif folded == "keywords" and "name" in attrs and not self._have_keywords:
+            self.found.meta_keywords = [word for word in (part.strip() for part in value.split(",")) if word]
+            self._have_keywords = True
+
+    # ---- <script type="application/ld+json">
+    def _close_ld(self) -> None:
+        raw, self._ld_buffer = "".join(self._ld_buffer or ()), None
+        try:
+            doc = json.loads(raw)
+        except ValueError:
+            return
+        self.found.json_ld.extend(item for item in (doc if isinstance(doc, list) else [doc]) if isinstance(item, dict))
+
+    def handle_starttag(self, tag, attrs):
+        mapping = {name: (value or "") for name, value in attrs}
+        if tag == "meta":
+            self._on_meta(mapping)
+        elif tag == "script" and mapping.get("type", "").strip().lower() == _LD_TYPE:
+            self._ld_buffer = []
+
+    handle_startendtag = handle_starttag
+
+    def handle_data(self, data):
+        if self._ld_buffer is not None:
+            self._ld_buffer.append(data)
+
+    def handle_endtag(self, tag):
+        if tag == "script" and self._ld_buffer is not None:
+            self._close_ld()
 
 
 def extract_structured_data(html: str) -> StructuredData:
-    out = StructuredData()
-    for m in _JSON_LD.finditer(html):
-        try:
-            data = json.loads(m.group(1))
-        except ValueError:
-            continue
-        if isinstance(data, list):
-            out.json_ld.extend(d for d in data if isinstance(d, dict))
-        elif isinstance(data, dict):
-            out.json_ld.append(data)
-    for m in _OG.finditer(html):
-        out.opengraph[m.group(1)] = m.group(2)
-    d = _DESC.search(html)
-    if d:
-        out.meta_description = d.group(1).strip()
-    k = _KEYWORDS.search(html)
-    if k:
-        out.meta_keywords = [w.strip() for w in k.group(1).split(",") if w.strip()]
-    return out
+    reader = _MetadataReader()
+    try:
+        reader.feed(html)
+        reader.close()
+    except Exception:  # noqa: BLE001 -- broken markup: keep what was read so far
+        pass
+    return reader.found
