@@ -109,6 +109,9 @@ def _peaks() -> dict:
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+from dataclasses import replace as _replace  # noqa: E402
+
+
 def main() -> int:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -397,7 +400,6 @@ def main() -> int:
         extras["roofline"] = dict(roof, peaks=peaks)
         # ---- (e) retrieval only (no reranker): the like-for-like number against the reference arm, which has none ----
         if hcfg.rerank:
-            from dataclasses import replace as _replace
 
             eng_r = HybridEngine(shard, _replace(hcfg, rerank=False), encoder=eng.encoder, **ekw)
             r_ms, r_per = timed(dev_step(eng_r), W, K)
@@ -408,7 +410,6 @@ def main() -> int:
             del eng_r
         # ---- (f) A/B arms on the same shard: the PyTorch (cuBLAS/SDPA/NCCL) build, and bf16 when the headline is fp8 ----
         if args.impl == "fused":
-            from dataclasses import replace as _replace
 
             if hcfg.rerank and precision != "bf16":
                 eng_b = HybridEngine(shard, _replace(hcfg, precision="bf16"), encoder=eng.encoder, reranker=eng.reranker, **ekw)
@@ -431,7 +432,6 @@ def main() -> int:
             torch.cuda.empty_cache()
         # ---- (g) padded cross-encoder, for transparency ----
         if hcfg.rerank and hcfg.varlen and args.impl == "fused":
-            from dataclasses import replace as _replace
 
             eng_p = HybridEngine(shard, _replace(hcfg, varlen=False, precision="bf16"), encoder=eng.encoder, reranker=eng.reranker, **ekw)
             pad_ms, pad_per = timed(dev_step(eng_p), W, K)
