@@ -48,7 +48,7 @@ async def _index_and_publish(ctx: Any, result: Any) -> None:
     if gi is not None and doc_id is not None:
         gi.note_added()
         if gi._pending >= GPU_REBUILD_PENDING:          # noqa: SLF001
-            await asyncio.to_thread(gi.rebuild)
+            await asyncio.to_thread(getattr(gi, "refresh", gi.rebuild))     # incremental append when the index supports it
 
 
 async def feed_poll_loop(ctx: Any) -> None:

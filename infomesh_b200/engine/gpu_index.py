@@ -182,6 +182,7 @@ class GpuSearchIndex:
             box = torch.tensor([t0], dtype=torch.float64, device=dev)
             dist.broadcast(box, src=0)
             t_ref = float(box.item())
+        self._t_ref = t_ref
         passages["neg_age"] = np.asarray(crawled, dtype=np.float64) - t_ref   # seconds before this build (<= 0), fp32-safe
         passages["authority"] = np.asarray(auth, dtype=np.float32) if auth else None
         del docs_text
@@ -198,6 +199,69 @@ class GpuSearchIndex:
         self.built_at, self.build_seconds = time.time(), time.time() - t0
         logger.info("gpu_index_built", docs=n, seconds=round(self.build_seconds, 2), hbm_mb=round(shard.nbytes() / 2 ** 20, 1))
         return n
+
+    def refresh(self) -> int:
+        """Incremental append: index the documents added to the store since the last build WITHOUT re-reading, re-tokenising
+        or re-encoding the ones already resident.  New rows are tokenised into the live posting builder, encoded, and
+        concatenated behind the resident vectors / passage tokens / passage tables; the CSR is re-exported from the builder
+        (a memcpy-class pass over the postings) and the device structures are swapped in atomically.  Cost is
+        O(new documents) model work + O(postings) copies, against O(corpus) model work for :meth:`rebuild`.
+        Returns the number of documents appended.  (A sharded index re-balances its ranges, so it rebuilds.)"""
+        if self.engine is None or self.builder is None or self.shard_world > 1 or self.doc_ids.size == 0:
+            before = self.n_docs
+            return max(0, self.rebuild() - before)
+        t0 = time.time()
+        dev = self.device
+        last = int(self.doc_ids.max())
+        new_ids, texts, bodies, pt_rows, crawled, auth = [], [], [], [], [], []
+        for doc in self.store.iter_documents(after=last):
+            body = f"{doc.title}\n{doc.text}"
+            self.builder.add_text(body)
+            new_ids.append(int(doc.doc_id))
+            texts.append(doc.text)
+            bodies.append(body[:2000])
+            pt_rows.append(self.rr_tok.encode_plain(body, self.passage_len))
+            crawled.append(float(doc.crawled_at or 0.0))
+            if self.authority_fn is not None:
+                try:
+                    auth.append(float(self.authority_fn(doc.url)))
+                except Exception:  # noqa: BLE001
+                    auth.append(0.0)
+        m = len(new_ids)
+        if m == 0:
+            self._pending = 0
+            return 0
+        old = self.engine.shard
+        vec_new = []
+        for a in range(0, m, self.embed_batch):
+            tok, lens = self.enc_tok.encode_batch(bodies[a:a + self.embed_batch], max_len=self.enc_doc_tokens)
+            vec_new.append(self.encoder.embed(tok.to(dev, non_blocking=True), lens.to(dev, non_blocking=True)))
+        vectors = torch.cat([old.vectors, *vec_new]).contiguous()
+        ptok_new = torch.full((m, self.passage_len), self.rr_tok.sp.pad, dtype=torch.int32)
+        plen_new = torch.zeros((m,), dtype=torch.int32)
+        for i, row in enumerate(pt_rows):
+            if row:
+                ptok_new[i, :len(row)] = torch.tensor(row, dtype=torch.int32)
+            plen_new[i] = max(len(row), 1)
+        ptok = torch.cat([old.passage_tok, ptok_new.to(dev)])
+        plen = torch.cat([old.passage_len, plen_new.to(dev)])
+        alive = torch.cat([old.alive, torch.ones((m,), dtype=torch.uint8, device=dev)])       # deletions survive an append
+        fresh = _passage_arrays(self.builder, texts)
+        prev = self._pass
+        n_tok_prev = int(prev["off"][-1])
+        passages = {"terms": np.concatenate([prev["terms"][:n_tok_prev], fresh["terms"]]),
+                    "off": np.concatenate([prev["off"], fresh["off"][1:] + n_tok_prev]),
+                    "doc_off": np.concatenate([prev["doc_off"], fresh["doc_off"][1:] + prev["doc_off"][-1]]),
+                    "span": np.concatenate([prev["span"].reshape(-1, 2), fresh["span"]])}
+        if prev.get("neg_age") is not None:
+            passages["neg_age"] = np.concatenate([prev["neg_age"], np.asarray(crawled, dtype=np.float64) - getattr(self, "_t_ref", t0)])
+            passages["authority"] = (np.concatenate([prev["authority"], np.asarray(auth, dtype=np.float32)])
+                                     if prev.get("authority") is not None and auth else prev.get("authority"))
+        csr = self.builder.export()
+        self._install(self.builder, csr, vectors, ptok, plen, alive, np.concatenate([self.doc_ids, np.asarray(new_ids, dtype=np.int64)]), passages)
+        self.built_at = time.time()
+        logger.info("gpu_index_appended", docs=m, total=self.n_docs, seconds=round(time.time() - t0, 2))
+        return m
 
     # ------------------------------------------------------------------ persistence (SURVEY §5.4)
     _FILES = ("vectors.bin", "csr_off.bin", "csr_doc.bin", "csr_tf.bin", "doc_len.bin", "df.bin", "passage_tok.bin",

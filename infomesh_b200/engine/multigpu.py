@@ -189,10 +189,18 @@ class MultiGpuSearchIndex:
                 logger.error("multigpu_rebuild_failed", error=str(exc))
                 self._teardown()
                 raise
-        self.n_docs = n
+        self.n_docs, self._pending = n, 0
         self.built_at, self.build_seconds = time.time(), time.time() - t0
         logger.info("multigpu_index_built", docs=n, gpus=self.world, seconds=round(self.build_seconds, 2))
         return n
+
+    def refresh(self) -> int:
+        """Sharded ranges are re-balanced on growth, so an append is a rebuild of every shard (in place, workers kept)."""
+        before = getattr(self, "n_docs", 0)
+        return max(0, self.rebuild() - before)
+
+    def note_added(self, n: int = 1) -> None:
+        self._pending = getattr(self, "_pending", 0) + n
 
     def _teardown(self) -> None:
         for conn in self._conns:

@@ -283,9 +283,9 @@ class LocalStore:
         row = self._conn.execute("SELECT * FROM documents WHERE url = ?", (url,)).fetchone()
         return self._to_document(row) if row else None
 
-    def iter_documents(self, batch: int = 1000):
-        """Stream every document in doc_id order (GPU shard rebuild, snapshot export)."""
-        last = 0
+    def iter_documents(self, batch: int = 1000, after: int = 0):
+        """Stream every document with ``doc_id > after`` in doc_id order (GPU shard build / incremental append, snapshots)."""
+        last = int(after)
         while True:
             rows = self._conn.execute("SELECT * FROM documents WHERE doc_id > ? ORDER BY doc_id LIMIT ?",
                                       (last, batch)).fetchall()

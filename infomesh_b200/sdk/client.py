@@ -150,9 +150,12 @@ class InfoMeshClient:
         return doc_id
 
     def refresh_gpu_index(self) -> int:
-        """Rebuild the HBM mirror so newly added documents become searchable on the device."""
+        """Make newly added documents searchable on the device: incremental append where the index supports it
+        (``GpuSearchIndex.refresh``), a rebuild otherwise.  Returns the number of documents appended / indexed."""
         self._ensure_init()
-        return self._gpu_index.rebuild() if self._gpu_index is not None else 0
+        if self._gpu_index is None:
+            return 0
+        return getattr(self._gpu_index, "refresh", self._gpu_index.rebuild)()
 
     # ------------------------------------------------------------------ misc
     def suggest(self, prefix: str, *, limit: int = 5) -> list[str]:

@@ -181,3 +181,40 @@ def test_gpu_index_untrained_models_keep_bm25_order_and_survive_concurrent_rebui
     assert not errors, errors[:1]
     assert gi.n_docs == 84
     store.close()
+
+
+def test_gpu_index_refresh_appends_without_rebuilding(tmp_path):
+    """refresh(): new store rows become searchable, old rows keep their vectors / ids, result lists equal a full rebuild."""
+    from infomesh_b200.engine.gpu_index import GpuSearchIndex
+    from infomesh_b200.index.local_store import LocalStore
+    from infomesh_b200.models.bert import BertConfig, BertModel
+
+    store = LocalStore(tmp_path / "i.db")
+    words = ["kademlia", "routing", "buckets", "merkle", "audit", "proofs", "sqlite", "ranking", "tensor", "memory", "barrier", "switch"]
+    def add(i):
+        body = " ".join(words[(i * 7 + j) % len(words)] for j in range(12 + i % 5)) + f". Second paragraph about unique{i} topic{i % 4}. " * 2
+        store.add_document(url=f"https://example.org/{i}", title=f"Doc {i} {words[i % len(words)]}", text=body, raw_html_hash=f"r{i}", text_hash=f"t{i}", language="en")
+    for i in range(60):
+        add(i)
+    dev = torch.device("cuda:0")
+    small = BertConfig(name="tiny-enc", vocab_size=30522, hidden=384, layers=2, heads=12, ffn=1536, max_pos=512)
+    gi = GpuSearchIndex(store, device=dev, encoder=BertModel(small, device=dev, seed=1), query_batch=8, rank_signals=True)
+    assert gi.rebuild() == 60
+    vec_before = gi.engine.shard.vectors[:60].clone()
+    gi.mark_deleted(int(gi.doc_ids[3]))
+    for i in range(60, 75):
+        add(i)
+    assert gi.search("unique70") == []
+    assert gi.refresh() == 15 and gi.n_docs == 75 and gi.refresh() == 0
+    assert torch.equal(gi.engine.shard.vectors[:60], vec_before)                # resident rows were not re-encoded
+    assert int(gi.engine.shard.alive[3]) == 0                                     # a deletion survives the append
+    hit = gi.search("unique70", k=3)
+    assert hit and hit[0]["url"] == "https://example.org/70" and "unique70" in hit[0]["snippet"]
+    queries = ["kademlia routing", "merkle audit proofs", "tensor memory", "unique12", "sqlite ranking barrier"]
+    appended = [[h["doc_id"] for h in hs] for hs in gi.search_many(queries, k=5)]
+    full = GpuSearchIndex(store, device=dev, encoder=gi.encoder, query_batch=8, rank_signals=True)
+    full.rebuild()
+    full.mark_deleted(int(full.doc_ids[3]))
+    rebuilt = [[h["doc_id"] for h in hs] for hs in full.search_many(queries, k=5)]
+    assert [set(a) for a in appended] == [set(b) for b in rebuilt]
+    store.close()
