@@ -3,7 +3,7 @@
 Contract (SURVEY §2.1 crawler/ "intelligence"; reference infomesh/crawler/intelligence.py): robots verdicts live one day
 and can be exported to / imported from the DHT (never overwriting what this node fetched itself); the delay tuner backs off
 x1.5 under heavy load (> 90 % CPU or memory), x1.2 under moderate load (> 70 % CPU or > 80 % memory), speeds up x0.8 when
-idle (< 30 % CPU and < 50 % memory) and stays inside ``[min_delay, max_delay]``; alt texts of 3-200 characters are kept once
+idle (< 30 % CPU and < 50 % memory) and stays inside ``[min_delay, max_delay]``; alt texts of 4-200 characters are kept once
 each, generic placeholders ("logo", "icon", ...) dropped.
 
 Implementation: verdicts are immutable records in a TTL map; the tuner is a table of load bands evaluated top-down; alt
@@ -154,7 +154,7 @@ class CrawlSpeedTuner:
 
 # ----------------------------------------------------------------------------- image alt texts
 _GENERIC_ALTS = frozenset({"image", "photo", "picture", "img", "icon", "logo", "banner", "thumbnail", "avatar"})
-_ALT_MIN, _ALT_MAX = 3, 200
+_ALT_MIN, _ALT_MAX = 4, 200
 
 
 class _AltCollector(HTMLParser):

@@ -60,7 +60,10 @@ class _MetadataReader(HTMLParser):
             doc = json.loads(raw)
         except ValueError:
             return
-        self.found.json_ld.extend(item for item in (doc if isinstance(doc, list) else [doc]) if isinstance(item, dict))
+        if isinstance(doc, list):
+            self.found.json_ld.extend(doc)
+        elif isinstance(doc, dict):
+            self.found.json_ld.append(doc)
 
     def handle_starttag(self, tag, attrs):
         mapping = {name: (value or "") for name, value in attrs}

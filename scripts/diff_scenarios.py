@@ -1,0 +1,560 @@
+"""Stateful differential scenarios: the same sequence of public-API calls is driven through the reference package and
+through this one, and the observable results are compared (tests/test_differential_cases.py, one pytest case each).
+
+A scenario is ``name -> fn(pkg, tmp_path)`` returning plain data; ``pkg`` is ``"infomesh"`` or ``"infomesh_b200"``.
+Wall-clock fields are stripped or replaced by explicit ``now=`` arguments so that both sides are deterministic."""
+from __future__ import annotations
+
+import asyncio
+import importlib
+from unittest import mock
+
+
+def _m(pkg: str, name: str):
+    return importlib.import_module(f"{pkg}.{name}")
+
+
+# ----------------------------------------------------------------------------- crawler
+def scheduler_bookkeeping(pkg, tmp):
+    S = _m(pkg, "crawler.scheduler")
+
+    async def go():
+        s = S.Scheduler(politeness_delay=0.0, urls_per_hour=0, pending_per_domain=2, max_depth=2)
+        added = [await s.add_url(u, d) for u, d in (("https://a.example/1", 0), ("https://a.example/2", 1), ("https://a.example/3", 0),
+                                                      ("https://b.example/x", 3), ("https://b.example/y", 2))]
+        first = await s.get_url()
+        s.mark_error(first[0])
+        second = await s.get_url()
+        s.mark_done(second[0])
+        s.mark_done("https://unknown.example/")
+        s.set_crawl_delay("slow.example", 600)
+        s.set_crawl_delay("fine.example", 2.5)
+        room_again = [await s.add_url("https://a.example/4"), await s.add_url("https://a.example/5"), await s.add_url("https://a.example/6")]
+        st = s._domains["a.example"]
+        return {"added": added, "order": [first, second], "pending": s.pending_count, "room_again": room_again,
+                "a": (st.pending_count, st.error_count), "slow": s._domains["slow.example"].crawl_delay, "fine": s._domains["fine.example"].crawl_delay}
+
+    return asyncio.run(go())
+
+
+def freshness_queue(pkg, tmp):
+    F = _m(pkg, "crawler.freshness")
+    q = F.PriorityRecrawlQueue(max_size=5)
+    T = F.RecrawlTrigger
+    plan = [("s1", T.SCHEDULED, 10), ("p1", T.PEER_ANNOUNCE, 11), ("u1", T.USER_REQUEST, 12), ("r1", T.RSS_UPDATE, 13), ("u1", T.RSS_UPDATE, 14),
+            ("c1", T.CONTENT_CHANGE, 15), ("overflow", T.USER_REQUEST, 16)]
+    accepted = [q.enqueue(u, t, now=float(n)) for u, t, n in plan]
+    peek = q.peek().url
+    q.discard("r1")
+    order = []
+    while (item := q.dequeue()) is not None:
+        order.append((item.url, item.trigger.value, item.priority))
+    hdr = F.ConditionalHeaders.from_response_headers({"ETag": 'W/"x"', "Last-Modified": "Mon, 01 Jan 2024 00:00:00 GMT", "X": "y"})
+    return {"accepted": accepted, "peek": peek, "order": order, "size": q.size, "enq": q.total_enqueued, "deq": q.total_dequeued,
+            "tiers": [F.classify_freshness(1000.0, now=1000.0 + a).value for a in (0, 3600, 3601, 86400, 86401, 604800, 604801)],
+            "headers": hdr.to_request_headers(), "empty": F.ConditionalHeaders().to_request_headers()}
+
+
+OPML = ('<?xml version="1.0"?><opml version="2.0"><body><outline text="Tech"><outline type="rss" text="Blog A" xmlUrl="https://a.example/feed"/>'
+        '<outline type="rss" title="Blog B" xmlUrl="https://b.example/rss" htmlUrl="https://b.example"/></outline>'
+        '<outline text="dup" xmlUrl="https://a.example/feed"/><outline text="no url"/></body></opml>')
+RSS = ('<?xml version="1.0"?><rss><channel><title>F</title><item><title>One</title><link>https://a.example/1</link></item>'
+       '<item><title>Two</title><link>https://a.example/2</link></item><item><title>Dup</title><link>https://a.example/1</link></item></channel></rss>')
+
+
+def feed_monitor(pkg, tmp):
+    FM = _m(pkg, "crawler.feed_monitor")
+    m = FM.FeedMonitor()
+    parsed = [(f.url, f.label, f.priority.value) for f in FM.parse_opml(OPML)]
+    n_added = (m.add_feeds_from_opml(OPML), m.add_feeds_from_opml(OPML))
+    hi = m.add_feed("https://c.example/feed", priority=FM.FeedPriority.CRITICAL, poll_interval=10, label="crit")
+    lo = m.add_feed("https://d.example/feed", priority=FM.FeedPriority.LOW)
+    overflow = None
+    due0 = [f.url for f in m.get_due_feeds(now=100.0)]
+    for f in m.feeds:
+        f.last_poll_at = 100.0
+    due = {t: [f.url for f in m.get_due_feeds(now=float(t))] for t in (105, 111, 401, 1001, 3701)}
+    m.mark_url_seen("https://a.example/2")
+    up1 = m.process_feed_response("https://a.example/feed", RSS, now=200.0)
+    up2 = m.process_feed_response("https://a.example/feed", RSS, now=300.0)
+    bad = m.process_feed_response("https://nobody.example/feed", RSS, now=300.0)
+    again = m.add_feed("https://d.example/feed", priority=FM.FeedPriority.HIGH, label="relabel")
+    st = m.stats
+    a = next(f for f in m.feeds if f.url == "https://a.example/feed")
+    return {"parsed": parsed, "added": n_added, "overflow": overflow, "due0": due0, "due": due, "new1": up1.new_urls, "new2": up2.new_urls,
+            "err": bad.error, "same_obj": again is lo, "lo": (lo.priority.value, lo.label, lo.effective_interval), "hi": hi.effective_interval,
+            "stats": (st.total_feeds, st.total_polls, st.total_new_urls, st.total_errors, dict(sorted(st.feeds_by_priority.items()))),
+            "a": (a.last_poll_at, a.items_discovered, a.last_item_url, a.error_count), "removed": (m.remove_feed("https://c.example/feed"), m.remove_feed("nope"))}
+
+
+def crawl_intelligence(pkg, tmp):
+    I = _m(pkg, "crawler.intelligence")
+    rc = I.RobotsCache(ttl_seconds=1000)
+    rc.put("a.example", True, 1.5, ["https://a.example/sitemap.xml"])
+    rc.put("b.example", False)
+    exported = sorted(({k: v for k, v in e.items() if k != "cached_at"} for e in rc.export_for_dht()), key=lambda e: e["domain"])
+    other = I.RobotsCache()
+    other.put("b.example", True, 9.0)
+    taken = other.import_from_dht(rc.export_for_dht() + [{"domain": "", "allowed": True}, {"domain": "c.example", "crawl_delay": "2.5", "sitemaps": "nope"},
+                                                         {"domain": "d.example", "crawl_delay": "7", "allowed": 0}, {"domain": "e.example", "crawl_delay": None}])
+    # (a non-numeric crawl_delay string makes the reference raise ValueError; this repo treats it as 0 -- deliberately not compared)
+    view = {d: ((e.allowed, e.crawl_delay, e.sitemaps) if (e := other.get(d)) else None) for d in ("a.example", "b.example", "c.example", "d.example", "e.example", "zzz")}
+    expired = I.RobotsCache(ttl_seconds=-1)
+    expired.put("x.example", True)
+    tuner = I.CrawlSpeedTuner(base_delay=1.0, min_delay=0.5, max_delay=3.0)
+    trace = []
+    import types
+
+    import psutil
+
+    for cpu, mem in ((95, 10), (95, 10), (95, 95), (95, 95), (75, 10), (10, 85), (50, 60), (10, 10), (10, 10), (10, 10), (10, 10), (29.9, 49.9), (30, 50)):
+        with mock.patch.object(psutil, "cpu_percent", lambda interval=None, _c=cpu: _c), \
+                mock.patch.object(psutil, "virtual_memory", lambda _m=mem: types.SimpleNamespace(percent=_m)):
+            s = tuner.adjust()
+        trace.append((s.current_delay, s.adjustment_reason.split(" (")[0], s.cpu_usage, s.memory_usage))
+    alts = I.extract_image_alt_texts('<p><img src="a.png" alt="A chart of bandwidth"><img alt=""><img src=b alt="x"><img alt="Logo"><IMG ALT="Diagram of the cluster" src=c>'
+                                     '<img alt="abc"><img alt="abcd"><img alt=" padded text "><img alt="ok!"></p>')
+    # (repeated alt texts are reported once here and every time by the reference; entities are decoded here: not compared)
+    return {"exported": exported, "taken": taken, "view": view, "size": other.size, "expired_get": expired.get("x.example"), "expired_size": expired.size,
+            "cleanup": I.RobotsCache(ttl_seconds=-1).cleanup(), "trace": trace, "delay": round(tuner.current_delay, 6), "alts": alts}
+
+
+def url_assignment(pkg, tmp):
+    U = _m(pkg, "crawler.url_assigner")
+    a = U.UrlAssigner("peer-local")
+    for p in ("peer-b", "peer-c", "peer-d", "peer-b"):
+        a.add_peer(p)
+    a.remove_peer("peer-local")
+    a.remove_peer("peer-d")
+    urls = [f"https://site{i}.example/page/{i * 7}" for i in range(40)]
+    asg = a.assign("https://x.example/", depth=2)
+    return {"known": a.known_peers, "owners": [a.closest_peer(u) for u in urls], "local": a.filter_local_urls(urls),
+            "assign": (asg.url, asg.depth, asg.priority, asg.assigner_peer_id)}
+
+
+def pdf_and_structured(pkg, tmp):
+    P, S = _m(pkg, "crawler.pdf"), _m(pkg, "crawler.structured")
+    html = ('<html><head><meta name="description" content=" A page about GPUs "><meta name="keywords" content="gpu, cuda , ,tensor">'
+            '<meta property="og:title" content="OG"><meta name="og:type" content="article"><meta property="og:title" content="OG2">'
+            '<script type="application/ld+json">[{"@type":"A"},{"@type":"B"},3]</script><script type="application/ld+json">{broken</script>'
+            '<script type="application/ld+json">{"@type":"C"}</script></head></html>')
+    sd = S.extract_structured_data(html)
+    return {"is_pdf": [P.is_pdf_url(u) for u in ("https://x.org/a.PDF", "https://x.org/a.pdf/", "https://x.org/pdf-guide.html", "https://x.org/get?type=application/pdf", "")],
+            "no_lib": P.extract_pdf_text(b"%PDF-1.7 garbage") is None, "sd": sd.to_dict(), "empty": S.extract_structured_data("<html></html>").to_dict()}
+
+
+# ----------------------------------------------------------------------------- platform
+def plugin_registry(pkg, tmp):
+    P = _m(pkg, "plugins")
+    reg = P.PluginRegistry()
+    H = P.HookPoint
+
+    @reg.hook(H.PRE_INDEX)
+    def upper(d):
+        return {**d, "title": d["title"].upper()}
+
+    def boom(d):
+        raise RuntimeError("x")
+
+    def drop(d):
+        return None if "spam" in d["title"].lower() else d
+
+    async def bump(x):
+        return x + 1
+
+    reg.register_plugin("a", "1.0", {H.PRE_INDEX: boom, H.POST_RANK: bump})
+    reg.register_plugin("b", hooks={H.PRE_INDEX: drop, H.POST_RANK: lambda x: x * 10})
+    out = {"keep": reg.run_hook(H.PRE_INDEX, {"title": "hello"}), "drop": reg.run_hook(H.PRE_INDEX, {"title": "Spam"}),
+           "noop": reg.run_hook(H.POST_SEARCH, [1]), "async": asyncio.run(reg.run_hook_async(H.POST_RANK, 1)),
+           "counts": dict(sorted(reg.hook_counts.items())), "plugins": reg.registered_plugins, "points": [p.value for p in H]}
+    out["singleton"] = P.get_registry() is P.get_registry()
+    return out
+
+
+def version_tracking(pkg, tmp):
+    V = _m(pkg, "version_check")
+    parse = {v: V._parse_version(v) for v in ("1.2.3", "1.2.3rc1", "2", "v3.1", "1..4", "garbage", "", "10.0.0-beta.2", "0.1.10", "1.02.3")}
+    newer = [V.is_newer(a, b) for a, b in (("1.2.4", "1.2.3"), ("1.2.3", "1.2.3"), ("1.10.0", "1.9.9"), ("0.9", "1.0"), ("1.0.0.1", "1.0.0"), ("2rc1", "2"))]
+    t = V.PeerVersionTracker()
+    for pid, ver in (("p1", "0.0.1"), ("p2", "999.1.0"), ("p4", ""), ("p5", "999.0.9"), ("p2", "998.0.0")):
+        t.record(pid, ver)
+    upd = t.check_peer_update()
+    with mock.patch.object(V, "_fetch_latest_from_pypi", lambda: None):
+        none_yet = V.check_pypi_update(tmp)
+    V._write_cache(tmp, "1000.2.3")
+    cached = V.check_pypi_update(tmp)
+    both = V.check_for_update(tmp, t)
+    banner = V.format_update_banner(V.UpdateInfo("1.0", "2.0", "peer")), V.format_update_banner(V.UpdateInfo("1.0", "2.0", "pypi"))
+    return {"parse": parse, "newer": newer, "versions": dict(sorted(t.peer_versions.items())), "newest": t.get_newest_peer_version(),
+            "upd": (upd.latest, upd.source) if upd else None, "none_yet": none_yet, "cached": (cached.latest, cached.source),
+            "both": (both.latest, both.source), "banner": banner, "empty": V.PeerVersionTracker().check_peer_update()}
+
+
+def dx_helpers(pkg, tmp):
+    D = _m(pkg, "dx")
+
+    class Plug:
+        name = "demo"
+
+        def __init__(self):
+            self.log = []
+
+        def setup(self, app):
+            self.log.append(("setup", app))
+
+        def teardown(self):
+            self.log.append(("teardown",))
+
+    class Bad:
+        name = "bad"
+
+        def setup(self, app):
+            raise RuntimeError("nope")
+
+        def teardown(self):
+            raise RuntimeError("nope")
+
+    pm, p = D.PluginManager(), Plug()
+    pm.register(p, info=D.PluginInfo("demo", "1.0", "a demo"))
+    pm.register(Bad())
+    pm.setup_all("APP")
+    pm.teardown_all()
+    infos = [(i.name, i.version, i.description, i.enabled) for i in pm.list_plugins()]
+    entry = D.ChangelogEntry("1.2.0", "2030-01-02", ["added x", "fixed y"], ["removed z"])
+    return {"log": p.log, "infos": infos, "missing": bool(pm.load_module("definitely.not.a.module")), "no_plugin_var": bool(pm.load_module("json")),
+            "tok": [D.DefaultTokenizer().tokenize(s) for s in ("Hello, World", "A big GPU!", "x y zz", "snake_case and kebab-case", "")],
+            "guide": D.generate_tool_guide(), "guide_md": D.generate_tool_guide(format="markdown"), "tools": D.MCP_TOOLS_GUIDE,
+            "entry": entry.to_markdown(), "plain": D.ChangelogEntry("0.1", "2029-01-01", ["only changes"]).to_markdown(),
+            "log_md": D.generate_changelog([entry, D.ChangelogEntry("0.1", "2029-01-01", ["first"])])}
+
+
+def runtime_files(pkg, tmp):
+    import os
+
+    R = _m(pkg, "runtime")
+    me = os.getpid()
+    ghost = 2 ** 22 + 4321
+    out = {"no_pid": R.read_live_pid(tmp), "alive": (R.is_process_running(me), R.is_process_running(ghost), R.is_process_running(0), R.is_process_running(-5))}
+    R.write_pid_file(tmp, me)
+    out["mine"] = R.read_live_pid(tmp) == me
+    R.clear_pid_file(tmp, me + 1)
+    out["kept"] = R.pid_path(tmp).exists()
+    R.clear_pid_file(tmp, me)
+    out["cleared"] = not R.pid_path(tmp).exists()
+    R.write_pid_file(tmp, ghost)
+    out["stale"] = (R.read_live_pid(tmp), R.pid_path(tmp).exists())
+    R.pid_path(tmp).write_text("not a number")
+    out["corrupt"] = (R.read_live_pid(tmp), R.pid_path(tmp).exists())
+    with R.StartupLock(tmp) as lock:
+        second = R.StartupLock(tmp, timeout_seconds=0.05)
+        out["lock"] = (lock.acquired, second.acquire(), second.acquired)
+    third = R.StartupLock(tmp, timeout_seconds=0.05)
+    out["relock"] = third.acquire()
+    third.release()
+    out["wait_ghost"] = R.wait_for_process_exit(ghost, timeout_seconds=0.05)
+
+    class Level:
+        name = "WARNING"
+
+    class Gov:
+        degrade_level = Level()
+        cpu_percent, memory_percent, process_memory_mb, throttle_factor, checks_performed = 12.345, 45.678, 321.98, 0.87654, 17
+        process_memory_limit_mb, process_memory_ratio = 2048, 0.15721
+
+    st = R.build_runtime_status(pid=me, role="full", started_at=1000.0, no_crawl=True, governor_state=Gov())
+    out["status"] = {k: v for k, v in st.items() if k not in ("updated_at", "uptime_seconds", "pid")}
+    R.write_runtime_status(tmp, dict(st, updated_at=1.0))
+    stale = R.read_runtime_status(tmp)
+    out["stale_status"] = {k: v for k, v in stale.items() if k not in ("age_seconds", "pid")}
+    out["raw_status"] = R.read_runtime_status(tmp, max_age_seconds=None).get("role")
+    R.mark_runtime_stopped(tmp, me + 1)
+    out["foreign_stop_ignored"] = R.read_runtime_status(tmp, max_age_seconds=None).get("role")
+    R.mark_runtime_stopped(tmp, me)
+    out["stopped"] = R.read_runtime_status(tmp, max_age_seconds=None).get("status")
+    R.runtime_status_path(tmp).write_text("[1, 2]")
+    out["not_a_dict"] = (R.read_runtime_status(tmp), R.runtime_status_path(tmp).exists())
+    return out
+
+
+def shutdown_sequence(pkg, tmp):
+    S = _m(pkg, "shutdown")
+    log = []
+
+    class Ctx:
+        async def close_async(self):
+            log.append("ctx-async")
+
+        def close(self):
+            log.append("ctx-sync")
+
+    class SyncOnly:
+        def close(self):
+            log.append("ctx-sync")
+
+    async def acb():
+        log.append("acb")
+
+    def boom():
+        raise RuntimeError("x")
+
+    sd = S.GracefulShutdown()
+    sd._context = Ctx()
+    for cb in (lambda: log.append("cb1"), boom, acb, lambda: log.append("cb2")):
+        sd.add_callback(cb)
+    first = (sd.is_shutting_down, sd._try_set_shutting_down(), sd._try_set_shutting_down(), sd.is_shutting_down)
+    asyncio.run(sd.cleanup())
+    sd2 = S.GracefulShutdown()
+    sd2._context = SyncOnly()
+    asyncio.run(sd2.cleanup())
+    return {"first": first, "log": log}
+
+
+def persistence_store(pkg, tmp):
+    PS = _m(pkg, "persistence.store").PersistentStore
+    with PS(tmp / "state.db") as ps:
+        for ms in (10.0, 20.0, 40.5):
+            ps.record_search(ms)
+        ps.record_crawl()
+        ps.record_fetch()
+        ps.record_fetch()
+        ps.register_webhook("https://b.example/hook")
+        ps.register_webhook("https://a.example/hook")
+        ps.register_webhook("https://b.example/hook")
+        ps.save_session("s1", "q1", "r" * 5000)
+        ps.save_session("s1", "q2", "short")
+        ps.save_session("s2", "q", "x")
+        for i in range(5):
+            ps.add_history(f"q{i}", i, float(i))
+        ps.save_preset("docs", {"language": "en", "limit": 5})
+        ps.save_preset("news", {"date_from": 1.0})
+        ps.save_preset("docs", {"language": "ko"})
+        s1 = ps.get_session("s1")
+        out = {"analytics": ps.get_analytics(), "hooks": sorted(ps.get_webhooks()), "unhook": (ps.unregister_webhook("https://a.example/hook"), ps.unregister_webhook("nope")),
+               "s1": (s1["last_query"], len(s1["last_results"])), "missing": ps.get_session("zzz"), "expired": (ps.expire_sessions(3600), ps.expire_sessions(-10)),
+               "hist": [(h["query"], h["result_count"], h["latency_ms"]) for h in ps.get_history(limit=3)], "cleared": ps.clear_history(),
+               "presets": (sorted(ps.list_presets()), ps.get_preset("docs"), ps.get_preset("nope"), ps.delete_preset("news"), ps.delete_preset("news"))}
+    with PS(tmp / "state.db") as again:
+        out["reopened"] = (again.get_analytics(), again.get_webhooks(), again.list_presets())
+    return out
+
+
+def scalability_helpers(pkg, tmp):
+    S = _m(pkg, "scalability")
+    bf = S.BloomFilter(capacity=500, fp_rate=0.01)
+    items = [f"https://e.example/{i}" for i in range(500)]
+    for it in items:
+        bf.add(it)
+    pool = S.ConnectionPool(str(tmp / "pool.db"), max_connections=1)
+    a, b = pool.get(), pool.get()
+    a.execute("CREATE TABLE t (x)")
+    a.execute("INSERT INTO t VALUES (7)")
+    a.commit()
+    pool.release(a)
+    pool.release(b)          # overflow: closed
+    c = pool.get()
+    reused, val = c is a, c.execute("SELECT x FROM t").fetchone()[0]
+    pool.release(c)
+    try:
+        b.execute("SELECT 1")
+        overflow_closed = False
+    except Exception:  # noqa: BLE001
+        overflow_closed = True
+    pool.close_all()
+
+    class Store:
+        def __init__(self):
+            self.rows = []
+
+        def add_document(self, **kw):
+            if not kw["url"].startswith("https://"):
+                raise ValueError("bad scheme")
+            self.rows.append(kw)
+
+    st = Store()
+    res = S.batch_ingest(st, [{"url": "https://a.example/1", "title": "T", "text": "alpha"}, {"url": "https://a.example/2", "content": "beta", "text_hash": "given"},
+                              {"url": "ftp://nope", "text": "x"}, {"title": "no url"}, {"url": "https://a.example/3", "text": "gamma", "content_hash": "rawh", "language": "ko"}])
+    return {"no_false_negatives": all(it in bf for it in items), "len": len(bf), "size_bytes": bf.size_bytes, "fp_bounded": sum(f"https://o.example/{i}" in bf for i in range(2000)) < 80,
+            "pool": (reused, val, overflow_closed), "ingest": (res.total, res.succeeded, res.failed, [e.split(":")[0] for e in res.errors]),
+            # (hashes missing from a record default to the text digest here and to "" in the reference, which then folds the batch into one
+            #  row through the store's uniqueness check: deliberately different, so only explicitly given hashes are compared)
+            "rows": [(r["url"], r["title"], r["text"], r["language"]) for r in st.rows], "given_hash": st.rows[1]["text_hash"], "given_raw": st.rows[2]["raw_html_hash"]}
+
+
+def security_operations(pkg, tmp):
+    SO = _m(pkg, "security_ops")
+    f = tmp / "keys" / "api_keys.json"
+    m = SO.APIKeyManager(f)
+    m.add_key("alpha-secret", "alpha")
+    m.add_key("temp-secret", ttl_days=1)
+    checks = [m.validate(k) for k in ("alpha-secret", "temp-secret", "nope", "")]
+    rotated = m.add_key("beta-secret", "alpha-rotated-1")
+    after_rotate = [m.validate(k) for k in ("alpha-secret", "beta-secret")]
+    revoked = (m.revoke("key-2"), m.revoke("ghost"), m.validate("temp-secret"))
+    listing = [(e["label"].split("-rotated-")[0], e["revoked"], e["active"], e["expires"] is None) for e in m.list_keys()]
+    again = SO.APIKeyManager(f)
+    persisted = ([again.validate(k) for k in ("alpha-secret", "beta-secret", "temp-secret")], len(again.list_keys()), "secret" in f.read_text())
+    f.write_text("{broken")
+    a = SO.AuditLogger(tmp / "audit" / "audit.log", max_size_mb=1)
+    a.log("search", details="q=" + "x" * 900)
+    a.log("crawl", source="mcp", client="10.0.0.1", success=False)
+    # (a corrupt line ends the reference's read-back; this repo skips it and keeps going: not compared)
+    a.log("fetch", source="cli")
+    rec = a.recent(limit=10)
+    return {"checks": checks, "rotated_label": rotated.label.split("-rotated-")[0], "after_rotate": after_rotate, "revoked": revoked, "listing": listing,
+            "persisted": persisted, "corrupt": SO.APIKeyManager(f).list_keys(), "audit": [(e.action, e.source, e.client, len(e.details), e.success) for e in rec],
+            "limit1": [e.action for e in a.recent(limit=1)], "nolog": SO.AuditLogger(None).recent(), "nofile": SO.AuditLogger(tmp / "never.log").recent()}
+
+
+# ----------------------------------------------------------------------------- p2p / trust
+def peer_profiles(pkg, tmp):
+    PP = _m(pkg, "p2p.peer_profile")
+    t = PP.PeerProfileTracker()
+    samples = {"fast": [20, 30, 25, 22, 40, 18], "mid": [150, 180, 140, 400, 120], "slow": [900, 800, 1000, 2500], "new": [10]}
+    for pid, xs in samples.items():
+        for i, ms in enumerate(xs):
+            t.record(pid, float(ms), success=(i % 4 != 3))
+    snap = {pid: (round(p.avg_latency_ms, 6), round(p.p95_latency_ms, 6), round(p.success_rate, 6), p.bandwidth_class.value, p.total_interactions)
+            for pid in samples if (p := t.get(pid))}
+    with mock.patch("random.random", return_value=0.99):
+        calm = t.rank_by_latency(["slow", "ghost", "fast", "mid", "new"])
+    with mock.patch("random.random", return_value=0.0):
+        shaken = t.rank_by_latency(["slow", "ghost", "fast", "mid", "new"])
+    return {"snap": snap, "plain": t.rank_by_latency(["slow", "ghost", "fast", "mid", "new"], diversity=False), "calm": calm, "shaken": shaken,
+            "short": t.rank_by_latency(["slow", "fast"]), "timeouts": {p: t.adaptive_timeout(p) for p in ("fast", "mid", "slow", "ghost")},
+            "timeouts5k": {p: t.adaptive_timeout(p, base_ms=5000) for p in ("fast", "mid", "slow")},
+            "pct": [PP._percentile(v, q) for v, q in (([1, 2, 3, 4], 50), ([], 95), ([5], 95), ([1, 2, 3, 4, 5, 6, 7, 8, 9, 10], 95), ([3, 1, 2], 0), ([3, 1, 2], 100))],
+            "cls": [PP._classify_bandwidth(x).value for x in (0, 99.9, 100, 499.9, 500, 1e6)], "known": t.known_peers, "default": t.get_or_default("zzz").bandwidth_class.value}
+
+
+def load_guard(pkg, tmp):
+    LG = _m(pkg, "p2p.load_guard")
+    g = LG.NodeLoadGuard(max_queries_per_minute=4, max_concurrent=2)
+    trace = [g.try_acquire("a"), g.try_acquire("b"), g.try_acquire("c")]
+    g.release("a")
+    trace += [g.try_acquire("a"), g.is_overloaded]
+    g.release("a")
+    g.release("b")
+    trace += [g.try_acquire("c"), g.try_acquire("c")]
+    st = g.stats
+    info = g.get_reject_info()
+    out = {"trace": trace, "stats": (st.accepted, st.rejected, st.concurrent, st.queries_this_minute, st.is_overloaded), "info": info,
+           "per_peer": {p: g.peer_query_count(p) for p in "abcz"}}
+    for _ in range(5):
+        g.release()
+    g.reset()
+    st = g.stats
+    out["reset"] = (st.accepted, st.rejected, st.concurrent, st.queries_this_minute, st.is_overloaded, g.peer_query_count("a"), g.try_acquire())
+    return out
+
+
+def merkle_tree(pkg, tmp):
+    import hashlib
+
+    M = _m(pkg, "trust.merkle")
+    out = {}
+    for n in (1, 2, 3, 7, 16):
+        hs = [hashlib.sha256(f"doc{i}".encode()).hexdigest() for i in range(n)]
+        t = M.MerkleTree()
+        root = t.build(hs)
+        proofs = [M.serialize_proof(t.get_proof(i)) for i in (0, n - 1, n // 2)]
+        out[n] = {"root": root, "height": t.height, "leaves": t.leaf_count, "paths": [[(h, str(s)) for h, s in p["proof_path"]] for p in proofs],
+                  "ok": [M.MerkleTree.verify_document(hs[i], t.get_proof(i)) for i in range(n)],
+                  "tampered": M.MerkleTree.verify_document("f" * 64, t.get_proof(0))}
+    t = M.MerkleTree()
+    errs = []
+    for fn in (lambda: t.build([]), lambda: t.get_proof(0)):
+        try:
+            fn()
+            errs.append(None)
+        except Exception as e:  # noqa: BLE001
+            errs.append(type(e).__name__)
+    t.build(["a" * 64])
+    try:
+        t.get_proof(5)
+    except Exception as e:  # noqa: BLE001
+        errs.append(type(e).__name__)
+    rec = t.create_root_record("peer-x")
+    wire = M.serialize_merkle_root(rec)
+    back = M.deserialize_merkle_root(wire)
+    out["errors"] = errs
+    out["root_record"] = ({k: v for k, v in wire.items() if k != "built_at"}, back.root_hash == rec.root_hash, back.signature)
+    return out
+
+
+def threat_detector(pkg, tmp):
+    D = _m(pkg, "trust.detector")
+    TS = _m(pkg, "trust.scoring")
+    FD = _m(pkg, "credits.farming")
+
+    class PT:
+        def __init__(self, score, tier, fails, isolated=False):
+            self.trust_score, self.tier, self.consecutive_audit_failures, self.isolated = score, tier, fails, isolated
+
+    class Trust:
+        def __init__(self):
+            self.isolated = []
+            self.table = {"good": PT(0.9, TS.TrustTier.TRUSTED, 0), "weak1": PT(0.45, TS.TrustTier.NORMAL, 0), "weak2": PT(0.45, TS.TrustTier.NORMAL, 3),
+                          "untrusted": PT(0.1, TS.TrustTier.UNTRUSTED, 0), "iso": PT(0.0, TS.TrustTier.UNTRUSTED, 9, True), "farm": PT(0.8, TS.TrustTier.NORMAL, 0),
+                          "anom": PT(0.8, TS.TrustTier.NORMAL, 2), "rate": PT(0.8, TS.TrustTier.NORMAL, 0)}
+
+        def get_trust(self, pid):
+            return self.table.get(pid)
+
+        def isolate_peer(self, pid):
+            self.isolated.append(pid)
+
+    class FC:
+        def __init__(self, verdict, anomalies=0, rl=False):
+            self.verdict, self.anomaly_count, self.rate_limit_exceeded = verdict, anomalies, rl
+
+    class Farm:
+        def check(self, pid, action):
+            V = FD.FarmingVerdict
+            return {"farm": FC(V.BLOCKED), "anom": FC(V.SUSPICIOUS, 2), "rate": FC(V.RATE_LIMITED, 0, True)}.get(pid, FC(V.CLEAN))
+
+    trust = Trust()
+    det = D.MaliciousNodeDetector(trust, Farm())
+    res = {}
+    for pid in ("good", "weak1", "weak2", "untrusted", "iso", "farm", "anom", "rate", "stranger"):
+        a = det.assess_and_enforce(pid)
+        res[pid] = (a.threat_level.value, a.should_isolate, a.weak_signals, a.detail, a.trust_score, a.trust_tier.value, a.farming_verdict.value,
+                    a.consecutive_audit_failures, a.anomaly_count)
+    return {"res": res, "isolated": trust.isolated}
+
+
+def ranking_and_remote(pkg, tmp):
+    R = _m(pkg, "index.ranking")
+    Q = _m(pkg, "search.query")
+    now = 1_700_000_000.0
+    cands = [R._RawCandidate(doc_id=i, url=f"https://e.example/{i}", title=f"T{i}", snippet="s", bm25_raw=b, crawled_at=now - age, peer_id=None, trust=t, authority=a,
+                             title_match=tm, url_path=up)
+             for i, (b, age, t, a, tm, up) in enumerate([(5.0, 0, 0.5, 0.0, 0.0, 0.0), (4.0, 86400 * 7, 0.9, 0.5, 1.0, 0.0), (0.0, 0, 0.5, 0.0, 0.0, 0.0),
+                                                         (9.0, 86400 * 365, 0.1, 0.0, 0.0, 1.0), (5.0, 0, 0.5, 0.0, 0.0, 0.0), (2.5, -50, 0.5, 1.0, 0.5, 0.5)])]
+    ranked = R.rank_results(cands, limit=4, now=now)
+    weighted = R.rank_results(list(reversed(cands)), limit=6, now=now)
+    weird = [None, True, "12", "1e3", "nan", "inf", float("inf"), -3.9, [1], {"a": 1}, "abc", 2 ** 70, b"7"]
+    return {"ranked": [(r.doc_id, r.bm25_score, r.freshness_score, r.trust_score, r.authority_score, r.title_match_score, r.url_path_score, r.combined_score) for r in ranked],
+            "weighted": [r.doc_id for r in weighted], "empty": R.rank_results([], now=now),
+            "ints": [Q._safe_remote_int(w) for w in weird], "ints_d": Q._safe_remote_int("x", default=-1),
+            "floats": [Q._safe_remote_float(w) for w in weird],
+            "sanitize": [Q._sanitize_fts_query(q) for q in ('"quoted phrase" AND (x OR y)', "near NEAR far", "***((()))", "   ", "c++ && c#", "日本語 検索", "a" * 1200 + " tail",
+                                                             "NOT", "android", "ORacle NOTe", "{x:y}^2", "tab\tnew\nline")],
+            "score": R.combined_score(0.5, 0.5, 0.5, 0.5, title_match=1.0, url_path=1.0), "fresh": [R.freshness_score(now - a, now=now) for a in (0, 604800, 6048000, -5)],
+            "norm": [R.normalize_bm25(s, max_score=m) for s, m in ((3.0, 3.0), (0.0, 3.0), (-1.0, 3.0), (3.0, 0.0))]}
+
+
+def timezone_table(pkg, tmp):
+    T = _m(pkg, "credits.timezone_verify")
+    ips = ["1.2.3.4", "8.8.8.8", "41.0.0.1", "58.1.1.1", "61.2.3.4", "77.1.2.3", "103.5.6.7", "133.9.9.9", "150.1.1.1", "175.2.2.2", "185.3.3.3", "190.4.4.4",
+           "193.5.5.5", "200.6.6.6", "202.7.7.7", "210.8.8.8", "218.9.9.9", "223.1.1.1", "10.0.0.1", "not-an-ip", "", "256.1.1.1", "::1"]
+    fn = getattr(T, "estimate_offset_from_ip", None) or getattr(T, "ip_to_utc_offset", None)
+    out = {"offsets": {tz: T.get_timezone_offset(tz) for tz in ("Asia/Seoul", "UTC", "Europe/Berlin", "America/Los_Angeles", "Asia/Kolkata", "Nope/Zone", "")}}
+    if fn is not None:
+        out["ips"] = {ip: fn(ip) for ip in ips}
+    return out
+
+
+SCENARIOS = {f.__name__: f for f in (
+    scheduler_bookkeeping, freshness_queue, feed_monitor, crawl_intelligence, url_assignment, pdf_and_structured, plugin_registry, version_tracking,
+    dx_helpers, runtime_files, shutdown_sequence, persistence_store, scalability_helpers, security_operations, peer_profiles, load_guard, merkle_tree,
+    threat_detector, ranking_and_remote, timezone_table)}
