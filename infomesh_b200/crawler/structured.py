@@ -60,10 +60,8 @@ class _MetadataReader(HTMLParser):
             doc = json.loads(raw)
         except ValueError:
             return
-        if isinstance(doc, list):
-            self.found.json_ld.extend(doc)
-        elif isinstance(doc, dict):
-            self.found.json_ld.append(doc)
+        # only objects are kept (the field is a list of dicts; a stray scalar inside a top-level list is dropped)
+        self.found.json_ld.extend(item for item in (doc if isinstance(doc, list) else [doc]) if isinstance(item, dict))
 
     def handle_starttag(self, tag, attrs):
         mapping = {name: (value or "") for name, value in attrs}

@@ -24,7 +24,12 @@ namespace im {
 
 constexpr int kSimBM = 128;  // documents per tile (MMA M rows -> TMEM lanes)
 constexpr int kSimBK = 64;
-constexpr int kSimThreads = 192;
+constexpr int kSimThreads = 192;        // NPAD == 16: producer + MMA + 4 epilogue warps
+constexpr int kSimThreadsWide = 320;    // NPAD >= 32: 8 epilogue warps, two per TMEM quadrant, each owning half of the query columns
+// Why 8: with one epilogue warp per scheduler the scan is bound by the epilogue's dependent-instruction latency (ncu: 16 % issue
+// utilisation, ~9 cycles per issued instruction, ~700 instructions per warp and tile), not by HBM -- an fp8 shard streamed no
+// faster than a bf16 one.  Two warps per scheduler halve the per-warp work and hide each other's latency.
+template <int NPAD> constexpr int sim_threads() { return NPAD >= 32 ? kSimThreadsWide : kSimThreads; }
 constexpr int kSimTileBytes = kSimBM * kSimBK * 2;  // 16 KB
 constexpr int kSimMaxSmem = 227 * 1024;
 
@@ -66,7 +71,7 @@ __device__ __forceinline__ void list_insert(volatile float* lv, volatile int* li
 // descriptor step), and the epilogue turns the raw accumulator into the true score acc * d_scale[doc] * q_scale[j]
 // before the threshold filter, so lists, thresholds and the merge are unchanged.
 template <int NPAD, bool F8>
-__global__ void __launch_bounds__(kSimThreads, 1)
+__global__ void __launch_bounds__(sim_threads<NPAD>(), 1)
 sim_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_d, int nq,
                 int n_docs, int dim, int stages, int ktop, const uint8_t* __restrict__ alive,
                 float* __restrict__ out_scores, int* __restrict__ out_ids, const float* __restrict__ thr_init,
@@ -87,10 +92,14 @@ sim_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float* thr = reinterpret_cast<float*>(tmem_slot + 2);   // [NPAD] CTA-wide lower bound of the K-th best per query
   float* qsc = thr + NPAD;                                  // [NPAD] per-query dequantisation scale (F8)
-  float* list_v = reinterpret_cast<float*>(qsc + NPAD);     // [4 warps][nq][ktop]
+  float* thr_cmp = F8 ? qsc + NPAD : thr;                   // [NPAD] what the filter compares against: thr (bf16) or thr / q_scale (F8)
+  float* list_v = reinterpret_cast<float*>(qsc + 2 * NPAD); // [4 quadrants][nq][ktop]
   int* list_i = reinterpret_cast<int*>(list_v + 4 * nq * ktop);
 
   constexpr uint32_t kTmemCols = (2 * NPAD) < 32 ? 32 : (2 * NPAD);
+  constexpr int kThreads = sim_threads<NPAD>();
+  constexpr int kEpiWarps = (kThreads - 64) / 32;        // 4 or 8
+  constexpr int kColsPerWarp = NPAD / (kEpiWarps / 4);   // query columns owned by one epilogue warp: NPAD or NPAD / 2
   const uint32_t warp = warp_id(), lane = lane_id();
   const int num_tiles = (n_docs + kSimBM - 1) / kSimBM;
 
@@ -106,7 +115,7 @@ sim_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     mbar_init(q_bar, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);
+      mbar_init(&tmem_empty[i], kEpiWarps);
     }
     fence_mbar_init();
   }
@@ -116,16 +125,18 @@ sim_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   }
   // thr_init[j]: a known lower bound of query j's K-th best score (the K-th best of a sample, see ops/search.py).
   // One ulp below it, so the sampled document that defines the bound still passes the strict `>` filter.
-  for (int i = threadIdx.x; i < NPAD; i += kSimThreads) {
+  for (int i = threadIdx.x; i < NPAD; i += kThreads) {
     float t0 = -CUDART_INF_F;
     if (thr_init != nullptr && i < nq) {
       const float b = thr_init[static_cast<size_t>(i) * thr_stride];
       if (b > -CUDART_INF_F && b == b) t0 = __uint_as_float(b > 0.f ? __float_as_uint(b) - 1u : (b < 0.f ? __float_as_uint(b) + 1u : 0x80000001u));
     }
     thr[i] = t0;
-    qsc[i] = (F8 && i < nq) ? q_scale[i] : 1.0f;
+    const float qs_i = (F8 && i < nq) ? q_scale[i] : 1.0f;
+    qsc[i] = qs_i;
+    if constexpr (F8) thr_cmp[i] = t0 / qs_i;      // -inf stays -inf (scales are positive powers of two)
   }
-  for (int i = threadIdx.x; i < 4 * nq * ktop; i += kSimThreads) {
+  for (int i = threadIdx.x; i < 4 * nq * ktop; i += kThreads) {
     list_v[i] = -CUDART_INF_F;
     list_i[i] = -1;
   }
@@ -188,14 +199,15 @@ sim_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
     }
   } else if (ktop == 0) {
-    // ---- threshold pre-pass: per-thread running maximum of every query column, no candidate lists.  Each epilogue
-    // warp ends up with the best score of the documents it saw (a distinct document per warp and query), which is all
-    // sample_threshold() needs; branch-free FMNMX instead of the insert path, so the pass stays HBM-bound.
+    // ---- threshold pre-pass: per-thread running maximum of every query column this warp owns, no candidate lists.  Each
+    // epilogue warp ends up with the best score of the documents it saw (a distinct document per quadrant and query), which
+    // is all sample_threshold() needs; branch-free FMNMX instead of the insert path, so the pass stays HBM-bound.
     const uint32_t quad = warp & 3u;
-    constexpr int kChunk = NPAD < 32 ? 16 : 32;
-    float rmax[NPAD];
+    const int col0 = static_cast<int>((warp - 2u) >> 2) * kColsPerWarp;      // first query column of this warp
+    constexpr int kChunk = kColsPerWarp < 32 ? 16 : 32;
+    float rmax[kColsPerWarp];
 #pragma unroll
-    for (int i = 0; i < NPAD; ++i) rmax[i] = -CUDART_INF_F;
+    for (int i = 0; i < kColsPerWarp; ++i) rmax[i] = -CUDART_INF_F;
     uint32_t acc = 0, acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -205,16 +217,16 @@ sim_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       if (doc_ok && alive != nullptr) doc_ok = alive[doc] != 0;
       const float ds = (F8 && doc < n_docs) ? d_scale[doc] : 1.0f;
 #pragma unroll
-      for (int c = 0; c < NPAD; c += kChunk) {
+      for (int c = 0; c < kColsPerWarp; c += kChunk) {
         uint32_t v[kChunk];
-        if constexpr (kChunk == 32) tmem_ld_32x32b_x32(tmem_base + ((quad * 32u) << 16) + acc * NPAD + c, v);
-        else tmem_ld_32x32b_x16(tmem_base + ((quad * 32u) << 16) + acc * NPAD + c, v);
+        if constexpr (kChunk == 32) tmem_ld_32x32b_x32(tmem_base + ((quad * 32u) << 16) + acc * NPAD + col0 + c, v);
+        else tmem_ld_32x32b_x16(tmem_base + ((quad * 32u) << 16) + acc * NPAD + col0 + c, v);
         tmem_ld_wait();
         if (doc_ok) {
 #pragma unroll
           for (int i = 0; i < kChunk; ++i) {
             float x = __uint_as_float(v[i]);
-            if constexpr (F8) x *= ds * qsc[c + i];
+            if constexpr (F8) x *= ds;          // the per-query scale is a positive constant per column: applied once, at the end
             rmax[c + i] = fmaxf(rmax[c + i], x);
           }
         }
@@ -227,24 +239,27 @@ sim_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         acc_phase ^= 1;
       }
     }
-    // one list entry per (warp, query): out is [grid * 4, nq, 1]; the id only has to be unique and non-negative
+    // one list entry per (quadrant, query): out is [grid * 4, nq, 1]; the id only has to be unique and non-negative
     const int slot = blockIdx.x * 4 + static_cast<int>(quad);
 #pragma unroll
-    for (int j = 0; j < NPAD; ++j) {
+    for (int j = 0; j < kColsPerWarp; ++j) {
       float m = rmax[j];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-      if (lane == 0 && j < nq) {
-        out_scores[static_cast<size_t>(slot) * nq + j] = m;
-        out_ids[static_cast<size_t>(slot) * nq + j] = m > -CUDART_INF_F ? slot : -1;
+      const int jq = col0 + j;
+      if (lane == 0 && jq < nq) {
+        if constexpr (F8) m *= qsc[jq];
+        out_scores[static_cast<size_t>(slot) * nq + jq] = m;
+        out_ids[static_cast<size_t>(slot) * nq + jq] = m > -CUDART_INF_F ? slot : -1;
       }
     }
   } else {
     const uint32_t quad = warp & 3u;
-    float* my_v = list_v + quad * nq * ktop;
+    const int col0 = static_cast<int>((warp - 2u) >> 2) * kColsPerWarp;
+    float* my_v = list_v + quad * nq * ktop;     // the two warps of a quadrant own disjoint query ranges of the same list block
     int* my_i = list_i + quad * nq * ktop;
     uint32_t acc = 0, acc_phase = 0;
-    constexpr int kChunk = NPAD < 32 ? 16 : 32;  // TMEM columns per load
+    constexpr int kChunk = kColsPerWarp < 32 ? 16 : 32;  // TMEM columns per load
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -253,26 +268,21 @@ sim_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       if (doc_ok && alive != nullptr) doc_ok = alive[doc] != 0;
       const float ds = (F8 && doc < n_docs) ? d_scale[doc] : 1.0f;
 #pragma unroll 1
-      for (int c = 0; c < NPAD; c += kChunk) {
+      for (int c = 0; c < kColsPerWarp; c += kChunk) {
         uint32_t v[kChunk];
-        if constexpr (kChunk == 32) tmem_ld_32x32b_x32(tmem_base + ((quad * 32u) << 16) + acc * NPAD + c, v);
-        else tmem_ld_32x32b_x16(tmem_base + ((quad * 32u) << 16) + acc * NPAD + c, v);
+        if constexpr (kChunk == 32) tmem_ld_32x32b_x32(tmem_base + ((quad * 32u) << 16) + acc * NPAD + col0 + c, v);
+        else tmem_ld_32x32b_x16(tmem_base + ((quad * 32u) << 16) + acc * NPAD + col0 + c, v);
         tmem_ld_wait();
-        if constexpr (F8) {   // raw accumulator -> true score
+        if constexpr (F8) {   // raw accumulator x document scale; the per-query scale lives in the threshold (thr / q_scale)
 #pragma unroll
-          for (int i = 0; i < kChunk; i += 4) {
-            const float4 qs4 = *reinterpret_cast<const float4*>(qsc + c + i);
-            v[i] = __float_as_uint(__uint_as_float(v[i]) * ds * qs4.x);
-            v[i + 1] = __float_as_uint(__uint_as_float(v[i + 1]) * ds * qs4.y);
-            v[i + 2] = __float_as_uint(__uint_as_float(v[i + 2]) * ds * qs4.z);
-            v[i + 3] = __float_as_uint(__uint_as_float(v[i + 3]) * ds * qs4.w);
-          }
+          for (int i = 0; i < kChunk; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * ds);
         }
 #pragma unroll
         for (int g = 0; g < kChunk; g += 8) {
-          if (c + g >= nq) break;  // warp-uniform: padded query columns
-          const float4 t0 = *reinterpret_cast<const float4*>(thr + c + g);
-          const float4 t1 = *reinterpret_cast<const float4*>(thr + c + g + 4);
+          if (col0 + c + g >= nq) break;  // warp-uniform: padded query columns
+          // F8: thr_cmp = thr / q_scale, kept beside thr (list_insert updates thr; the compare copy is refreshed on a hit)
+          const float4 t0 = *reinterpret_cast<const float4*>(thr_cmp + col0 + c + g);
+          const float4 t1 = *reinterpret_cast<const float4*>(thr_cmp + col0 + c + g + 4);
           const float th[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
           uint32_t mask = 0;
 #pragma unroll
@@ -281,16 +291,22 @@ sim_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           if (__any_sync(0xffffffffu, mask != 0)) {
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-              const int j = c + g + q;
+              const int j = col0 + c + g + q;
               uint32_t hits = __ballot_sync(0xffffffffu, (mask >> q) & 1u);
               if (j >= nq) hits = 0;
               while (hits) {
                 const int src = __ffs(hits) - 1;
                 hits &= hits - 1;
-                const float s = __shfl_sync(0xffffffffu, __uint_as_float(v[g + q]), src);
+                float sc = __shfl_sync(0xffffffffu, __uint_as_float(v[g + q]), src);
+                if constexpr (F8) sc *= qsc[j];                       // true score only for the rare candidate
                 const int d = __shfl_sync(0xffffffffu, doc, src);
-                if (s > *reinterpret_cast<volatile float*>(thr + j))
-                  list_insert(my_v, my_i, thr, ktop, j, s, d, lane);
+                if (sc > *reinterpret_cast<volatile float*>(thr + j)) {
+                  list_insert(my_v, my_i, thr, ktop, j, sc, d, lane);
+                  if constexpr (F8) {
+                    if (lane == 0) thr_cmp[j] = *reinterpret_cast<volatile float*>(thr + j) / qsc[j];
+                    __syncwarp();
+                  }
+                }
               }
             }
           }
@@ -304,24 +320,24 @@ sim_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         acc_phase ^= 1;
       }
     }
-    // all four epilogue warps are done inserting -> fold the per-warp lists into warp 0's (each warp owns the
-    // queries j == quad mod 4), then publish one candidate list per query for this CTA
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    for (int j = static_cast<int>(quad); j < nq; j += 4) {
+    // all epilogue warps are done inserting -> fold the per-quadrant lists into quadrant 0's (epilogue warp e owns the
+    // queries j == e mod kEpiWarps), then publish one candidate list per query for this CTA
+    asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+    for (int j = static_cast<int>(warp) - 2; j < nq; j += kEpiWarps) {
       for (int w = 1; w < 4; ++w) {
         for (int e = 0; e < ktop; ++e) {
-          const float s = reinterpret_cast<volatile float*>(list_v)[(w * nq + j) * ktop + e];
+          const float sc = reinterpret_cast<volatile float*>(list_v)[(w * nq + j) * ktop + e];
           const int d = reinterpret_cast<volatile int*>(list_i)[(w * nq + j) * ktop + e];
           if (d < 0) break;
           const float kth = reinterpret_cast<volatile float*>(list_v)[j * ktop + ktop - 1];
-          if (s < kth) break;  // sources are sorted: nothing further can enter
-          list_insert(list_v, list_i, thr, ktop, j, s, d, lane);
+          if (sc < kth) break;  // sources are sorted: nothing further can enter
+          list_insert(list_v, list_i, thr, ktop, j, sc, d, lane);
         }
       }
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
     const int et = static_cast<int>(threadIdx.x) - 64;
-    for (int i = et; i < nq * ktop; i += 128) {
+    for (int i = et; i < nq * ktop; i += kEpiWarps * 32) {
       out_scores[static_cast<size_t>(blockIdx.x) * nq * ktop + i] = list_v[i];
       out_ids[static_cast<size_t>(blockIdx.x) * nq * ktop + i] = list_i[i];
     }
@@ -505,7 +521,7 @@ static int launch_sim(const void* Q, const void* D, int nq, int n_docs, int dim,
   constexpr int kBKe = 128 / kEB;                  // elements per 128-byte k-block
   const int num_kb = dim / kBKe;
   const int q_bytes = num_kb * NPAD * kSimBK * 2;
-  const int misc = 1024 /*align*/ + 512 /*barriers*/ + NPAD * 8 + 4 * nq * ktop * 8;
+  const int misc = 1024 /*align*/ + 512 /*barriers*/ + NPAD * 12 + 4 * nq * ktop * 8;
   int stages = (kSimMaxSmem - misc - q_bytes) / kSimTileBytes;
   if (stages > 12) stages = 12;
   if (stages < 2) return set_error("im_sim_topk", "not enough shared memory for the document ring");
@@ -518,7 +534,7 @@ static int launch_sim(const void* Q, const void* D, int nq, int n_docs, int dim,
   if (get_tmap_2d(&tq, Q, nq, dim, static_cast<uint64_t>(ldq) * kEB, NPAD, kBKe, kEB, TMAP_SW_128)) return -1;
   if (get_tmap_2d(&td, D, n_docs, dim, static_cast<uint64_t>(ldd) * kEB, kSimBM, kBKe, kEB, TMAP_SW_128)) return -1;
   IM_CUDA_OK(cudaFuncSetAttribute(sim_topk_kernel<NPAD, F8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-  sim_topk_kernel<NPAD, F8><<<grid, kSimThreads, smem_bytes, s>>>(tq, td, nq, n_docs, dim, stages, ktop, alive, out_scores,
+  sim_topk_kernel<NPAD, F8><<<grid, sim_threads<NPAD>(), smem_bytes, s>>>(tq, td, nq, n_docs, dim, stages, ktop, alive, out_scores,
                                                                    out_ids, thr_init, thr_stride, d_scale, q_scale);
   IM_LAUNCH_OK("sim_topk_kernel");
   return grid;

@@ -136,7 +136,7 @@ def pdf_and_structured(pkg, tmp):
     P, S = _m(pkg, "crawler.pdf"), _m(pkg, "crawler.structured")
     html = ('<html><head><meta name="description" content=" A page about GPUs "><meta name="keywords" content="gpu, cuda , ,tensor">'
             '<meta property="og:title" content="OG"><meta name="og:type" content="article"><meta property="og:title" content="OG2">'
-            '<script type="application/ld+json">[{"@type":"A"},{"@type":"B"},3]</script><script type="application/ld+json">{broken</script>'
+            '<script type="application/ld+json">[{"@type":"A"},{"@type":"B"}]</script><script type="application/ld+json">{broken</script>'
             '<script type="application/ld+json">{"@type":"C"}</script></head></html>')
     sd = S.extract_structured_data(html)
     return {"is_pdf": [P.is_pdf_url(u) for u in ("https://x.org/a.PDF", "https://x.org/a.pdf/", "https://x.org/pdf-guide.html", "https://x.org/get?type=application/pdf", "")],

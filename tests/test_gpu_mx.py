@@ -198,7 +198,9 @@ def test_gpu_index_refresh_appends_without_rebuilding(tmp_path):
         add(i)
     dev = torch.device("cuda:0")
     small = BertConfig(name="tiny-enc", vocab_size=30522, hidden=384, layers=2, heads=12, ffn=1536, max_pos=512)
-    gi = GpuSearchIndex(store, device=dev, encoder=BertModel(small, device=dev, seed=1), query_batch=8, rank_signals=True)
+    # pure BM25 order (no freshness signal): document ages are taken against the build instant, which differs between an
+    # append and a rebuild and could swap exact near-ties
+    gi = GpuSearchIndex(store, device=dev, encoder=BertModel(small, device=dev, seed=1), query_batch=8)
     assert gi.rebuild() == 60
     vec_before = gi.engine.shard.vectors[:60].clone()
     gi.mark_deleted(int(gi.doc_ids[3]))
@@ -212,9 +214,9 @@ def test_gpu_index_refresh_appends_without_rebuilding(tmp_path):
     assert hit and hit[0]["url"] == "https://example.org/70" and "unique70" in hit[0]["snippet"]
     queries = ["kademlia routing", "merkle audit proofs", "tensor memory", "unique12", "sqlite ranking barrier"]
     appended = [[h["doc_id"] for h in hs] for hs in gi.search_many(queries, k=5)]
-    full = GpuSearchIndex(store, device=dev, encoder=gi.encoder, query_batch=8, rank_signals=True)
+    full = GpuSearchIndex(store, device=dev, encoder=gi.encoder, query_batch=8)
     full.rebuild()
     full.mark_deleted(int(full.doc_ids[3]))
     rebuilt = [[h["doc_id"] for h in hs] for hs in full.search_many(queries, k=5)]
-    assert [set(a) for a in appended] == [set(b) for b in rebuilt]
+    assert appended == rebuilt
     store.close()
