@@ -131,7 +131,7 @@ def main() -> int:
                     help="cross-encoder GEMM precision.  mxfp8 (default): block-scaled e4m3 x e4m3 with ue8m0 scales per 32 "
                          "(tcgen05 kind::mxf8f6f4.block_scale), fp32 accumulation, quantisers fused into LayerNorm / attention "
                          "/ GELU epilogues; bf16: round-1 configuration")
-    ap.add_argument("--dense", choices=["bf16", "fp8"], default=os.environ.get("INFOMESH_B200_BENCH_DENSE", "bf16"),
+    ap.add_argument("--dense", choices=["bf16", "fp8"], default=os.environ.get("INFOMESH_B200_BENCH_DENSE", "fp8"),
                     help="dense shard storage streamed by the similarity search.  fp8: e4m3 rows + per-row scale (half the HBM "
                          "bytes), 32-wide over-fetch re-scored exactly against the bf16 rows; `dense_recall_vs_bf16` reports "
                          "the agreement with the bf16 search on the timed batches")
@@ -411,10 +411,11 @@ def main() -> int:
         # ---- (f) A/B arms on the same shard: the PyTorch (cuBLAS/SDPA/NCCL) build, and bf16 when the headline is fp8 ----
         if args.impl == "fused":
 
-            if hcfg.rerank and precision != "bf16":
-                eng_b = HybridEngine(shard, _replace(hcfg, precision="bf16"), encoder=eng.encoder, reranker=eng.reranker, **ekw)
+            if hcfg.rerank and (precision != "bf16" or hcfg.dense_dtype != "bf16"):
+                eng_b = HybridEngine(shard, _replace(hcfg, precision="bf16", dense_dtype="bf16"), encoder=eng.encoder, reranker=eng.reranker, **ekw)
                 b_ms, b_per = timed(dev_step(eng_b), W, K)
-                extras["bf16_arm"] = summary(b_ms, b_per, K, note="same pipeline, cross-encoder GEMMs in bf16 (round-1 config), one batch in flight")
+                extras["bf16_arm"] = summary(b_ms, b_per, K, note="same pipeline, everything in bf16 (cross-encoder GEMMs and dense shard: the "
+                                                                   "round-1 configuration), one batch in flight")
                 eng_b._graph = None
                 del eng_b
             try:
