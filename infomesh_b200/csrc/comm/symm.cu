@@ -54,7 +54,7 @@ __device__ __forceinline__ void channel_advance(uint32_t* state) {
 __global__ void __launch_bounds__(kAgThreads)
 p2p_allgather_kernel(const uint8_t* __restrict__ src, size_t bytes, uint8_t* const* __restrict__ peer_buf,
                      uint32_t* const* __restrict__ peer_flag, uint32_t* __restrict__ state, int world, int rank,
-                     uint8_t* __restrict__ out) {
+                     uint8_t* __restrict__ out, int debug_poison) {
   const uint32_t step = *reinterpret_cast<volatile uint32_t*>(state);
   const size_t par_off = static_cast<size_t>(step & 1u) * world * bytes;
   const size_t n16 = bytes / 16;
@@ -81,7 +81,17 @@ p2p_allgather_kernel(const uint8_t* __restrict__ src, size_t bytes, uint8_t* con
   for (int p = 0; p < world; ++p) {
     const uint4* s4 = reinterpret_cast<const uint4*>(mine + static_cast<size_t>(p) * bytes);
     uint4* d4 = reinterpret_cast<uint4*>(out + static_cast<size_t>(p) * bytes);
-    for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) d4[i] = s4[i];
+    for (size_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+      const uint4 w = s4[i];
+      if (debug_poison) {   // INFOMESH_B200_POISON_SLOTS=1: consumed slots are poisoned; meeting poison = flag said "arrived" too early
+        if (w.x == 0xdeadbeefu && w.y == 0xdeadbeefu && w.z == 0xdeadbeefu && w.w == 0xdeadbeefu) {
+          printf("[infomesh_b200] p2p_allgather: consumed a POISONED slot (step %u, peer %d, word %llu)\n", step, p, (unsigned long long)i);
+          __trap();
+        }
+        const_cast<uint4*>(s4)[i] = make_uint4(0xdeadbeefu, 0xdeadbeefu, 0xdeadbeefu, 0xdeadbeefu);
+      }
+      d4[i] = w;
+    }
   }
   channel_advance(state);
 }
@@ -153,7 +163,7 @@ IM_API int im_p2p_allgather(const void* src, size_t bytes, void* const* peer_buf
   if (grid > 32) grid = 32;   // every CTA spins on peers: stay far below one wave so all are co-resident
   p2p_allgather_kernel<<<grid, kAgThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint8_t*>(src), bytes, reinterpret_cast<uint8_t* const*>(peer_buf), peer_flag, state, world,
-      rank, static_cast<uint8_t*>(out));
+      rank, static_cast<uint8_t*>(out), debug_poison_slots());
   IM_LAUNCH_OK("p2p_allgather_kernel");
   return grid;
 }

@@ -1,3 +1,4 @@
+#include <cstdlib>
 #include "host.h"
 
 #include <stdlib.h>
@@ -61,6 +62,15 @@ int sm_count() {
     if (n <= 0) n = 148;
   }
   return n;
+}
+
+int debug_poison_slots() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("INFOMESH_B200_POISON_SLOTS");
+    on = (e != nullptr && e[0] != '\0' && e[0] != '0') ? 1 : 0;
+  }
+  return on;
 }
 
 static int g_pdl = -1;

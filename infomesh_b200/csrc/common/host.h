@@ -42,6 +42,12 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
 
 int sm_count();
 
+// Debug build of the peer channels, switched at run time: INFOMESH_B200_POISON_SLOTS=1 makes every exchange consumer
+// overwrite the receive slots it has consumed with a poison pattern and trap when it ever READS that pattern -- which can
+// only happen if an arrival counter reported a delivery that has not landed (a flag-protocol or memory-ordering bug the
+// executable protocol model in parallel/sim.py cannot see).  Costs one extra store per consumed element; off by default.
+int debug_poison_slots();
+
 // Programmatic dependent launch (PDL): the kernel may start while its stream predecessor is still draining; it runs
 // its prologue (barrier init, TMEM alloc, descriptor prefetch) and blocks at pdl_wait() (ptx.cuh) until the predecessor
 // has completed and flushed.  Captured into CUDA graphs as programmatic dependency edges.  INFOMESH_B200_PDL=0

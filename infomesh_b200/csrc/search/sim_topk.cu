@@ -354,6 +354,7 @@ sim_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 // for all peers' slots first.  One CTA per query.
 // ------------------------------------------------------------------------------------------------
 constexpr int kMergeThreads = 256;
+constexpr int64_t kPoisonId = -0x6b6b6b6b6b6b6b6bLL;   // what a consumed receive slot holds in the debug build of the channel
 
 __global__ void __launch_bounds__(kMergeThreads)
 topk_merge_kernel(const float* __restrict__ cand_scores, const int64_t* __restrict__ cand_ids64,
@@ -361,7 +362,7 @@ topk_merge_kernel(const float* __restrict__ cand_scores, const int64_t* __restri
                   float* __restrict__ out_scores, int64_t* __restrict__ out_ids,
                   // fused exchange (all optional)
                   float* const* peer_scores, int64_t* const* peer_ids, uint32_t* const* peer_flags, int world, int rank,
-                  const uint32_t* wait_flags, uint32_t* state, uint32_t* status, uint32_t wait_limit) {
+                  const uint32_t* wait_flags, uint32_t* state, uint32_t* status, uint32_t wait_limit, int debug_poison) {
   extern __shared__ uint8_t msm[];
   const int q = blockIdx.x;
   const int n = P * k_in;
@@ -409,6 +410,16 @@ topk_merge_kernel(const float* __restrict__ cand_scores, const int64_t* __restri
     const size_t src = (static_cast<size_t>(p) * nq + q) * k_in + j;
     float sc = cand_scores[src];
     int64_t id = cand_ids64 ? cand_ids64[src] : static_cast<int64_t>(cand_ids32[src]);
+    if (debug_poison && wait_flags != nullptr && cand_ids64 != nullptr && !((dead_mask >> p) & 1u)) {
+      // debug build of the channel (INFOMESH_B200_POISON_SLOTS=1): every slot is poisoned once consumed, so reading poison
+      // means the arrival counter said "delivered" for a slot no producer has rewritten -- a protocol or ordering bug
+      if (id == kPoisonId) {
+        printf("[infomesh_b200] topk exchange: consumed a POISONED slot (step %u, peer %d, query %d, entry %d)\n", step, p, q, j);
+        __trap();
+      }
+      const_cast<int64_t*>(cand_ids64)[src] = kPoisonId;
+      const_cast<float*>(cand_scores)[src] = __uint_as_float(0x7fc0deadu);
+    }
     if (wait_flags != nullptr && ((dead_mask >> p) & 1u)) id = -1;
     if (id < 0) sc = -CUDART_INF_F;
     else if (cand_ids64 == nullptr) id += id_offset;
@@ -662,7 +673,7 @@ IM_API int im_topk_merge(const float* cand_scores, const int64_t* cand_ids64, co
     IM_CUDA_OK(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   topk_merge_kernel<<<nq, kMergeThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
       cand_scores, cand_ids64, cand_ids32, P, nq, k_in, k_out, id_offset, out_scores, out_ids, peer_scores, peer_ids,
-      peer_flags, world, rank, wait_flags, state, status, wait_limit);
+      peer_flags, world, rank, wait_flags, state, status, wait_limit, debug_poison_slots());
   IM_LAUNCH_OK("topk_merge_kernel");
   return 0;
 }

@@ -64,3 +64,16 @@ def test_multigpu_product_serving_matches_single_gpu():
                          env=dict(os.environ, PYTHONPATH=str(ROOT)))
     text = out.stdout + out.stderr
     assert out.returncode == 0 and "ALL OK" in text, text[-3000:]
+
+
+def test_exchange_channels_with_poisoned_slots_two_ranks():
+    """Debug build of the channels (INFOMESH_B200_POISON_SLOTS=1): consumers poison every slot they consume and trap if they
+    ever read poison; many back-to-back exchanges (graph replays included) must still come out identical to NCCL."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29616", str(ROOT / "scripts" / "gpu_check_p2p.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=420, cwd=str(ROOT),
+                         env=dict(os.environ, PYTHONPATH=str(ROOT), INFOMESH_B200_POISON_SLOTS="1"))
+    text = out.stdout + out.stderr
+    assert out.returncode == 0 and "ALL OK" in text and "POISONED" not in text, text[-3000:]
