@@ -405,33 +405,62 @@ topk_merge_kernel(const float* __restrict__ cand_scores, const int64_t* __restri
     if (cand_ids64 != nullptr) cand_ids64 += par;
     if (cand_ids32 != nullptr) cand_ids32 += par;
   }
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const int p = i / k_in, j = i % k_in;
-    const size_t src = (static_cast<size_t>(p) * nq + q) * k_in + j;
-    float sc = cand_scores[src];
-    int64_t id = cand_ids64 ? cand_ids64[src] : static_cast<int64_t>(cand_ids32[src]);
-    if (debug_poison && wait_flags != nullptr && cand_ids64 != nullptr && !((dead_mask >> p) & 1u)) {
-      // debug build of the channel (INFOMESH_B200_POISON_SLOTS=1): every slot is poisoned once consumed, so reading poison
-      // means the arrival counter said "delivered" for a slot no producer has rewritten -- a protocol or ordering bug
-      if (id == kPoisonId) {
-        printf("[infomesh_b200] topk exchange: consumed a POISONED slot (step %u, peer %d, query %d, entry %d)\n", step, p, q, j);
-        __trap();
-      }
-      const_cast<int64_t*>(cand_ids64)[src] = kPoisonId;
-      const_cast<float*>(cand_scores)[src] = __uint_as_float(0x7fc0deadu);
-    }
-    if (wait_flags != nullptr && ((dead_mask >> p) & 1u)) id = -1;
-    if (id < 0) sc = -CUDART_INF_F;
-    else if (cand_ids64 == nullptr) id += id_offset;
-    s_sc[i] = sc;
-    s_id[i] = id;
-  }
+  // ---- load + compact: with the threshold filter most per-CTA lists are (nearly) empty, so only live candidates are kept
+  // (positions [0, n_live) of the smem arrays); the selection rounds below then touch tens of entries instead of P * k_in.
+  __shared__ int n_live_s;
+  __shared__ int warp_cnt[kMergeThreads / 32];
+  __shared__ float w_sc[32];          // winners, written out (locally and to every peer) after the last round
+  __shared__ int64_t w_id[32];
+  if (threadIdx.x == 0) n_live_s = 0;
   __syncthreads();
+  for (int base = 0; base < n; base += kMergeThreads) {
+    const int i = base + static_cast<int>(threadIdx.x);
+    float sc = -CUDART_INF_F;
+    int64_t id = -1;
+    if (i < n) {
+      const int p = i / k_in, j = i % k_in;
+      const size_t src = (static_cast<size_t>(p) * nq + q) * k_in + j;
+      sc = cand_scores[src];
+      id = cand_ids64 ? cand_ids64[src] : static_cast<int64_t>(cand_ids32[src]);
+      if (debug_poison && wait_flags != nullptr && cand_ids64 != nullptr && !((dead_mask >> p) & 1u)) {
+        // debug build of the channel (INFOMESH_B200_POISON_SLOTS=1): every slot is poisoned once consumed, so reading poison
+        // means the arrival counter said "delivered" for a slot no producer has rewritten -- a protocol or ordering bug
+        if (id == kPoisonId) {
+          printf("[infomesh_b200] topk exchange: consumed a POISONED slot (step %u, peer %d, query %d, entry %d)\n", step, p, q, j);
+          __trap();
+        }
+        const_cast<int64_t*>(cand_ids64)[src] = kPoisonId;
+        const_cast<float*>(cand_scores)[src] = __uint_as_float(0x7fc0deadu);
+      }
+      if (wait_flags != nullptr && ((dead_mask >> p) & 1u)) id = -1;
+      if (id >= 0 && cand_ids64 == nullptr) id += id_offset;
+    }
+    const bool live = id >= 0;
+    const uint32_t bal = __ballot_sync(0xffffffffu, live);
+    const int wid = static_cast<int>(threadIdx.x >> 5), ln = static_cast<int>(threadIdx.x & 31);
+    if (ln == 0) warp_cnt[wid] = __popc(bal);
+    __syncthreads();
+    int off = n_live_s;
+    for (int w = 0; w < wid; ++w) off += warp_cnt[w];
+    if (live) {
+      const int pos = off + __popc(bal & ((1u << ln) - 1u));
+      s_sc[pos] = sc;
+      s_id[pos] = id;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int w = 0; w < kMergeThreads / 32; ++w) tot += warp_cnt[w];
+      n_live_s += tot;
+    }
+    __syncthreads();
+  }
+  const int n_live = n_live_s;
   for (int r = 0; r < k_out; ++r) {
     float bv = -CUDART_INF_F;
     int64_t bi = INT64_MAX;
     int bp = -1;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    for (int i = threadIdx.x; i < n_live; i += blockDim.x) {
       const float sc = s_sc[i];
       const int64_t id = s_id[i];
       if (id >= 0 && (sc > bv || (sc == bv && id < bi))) {
@@ -466,34 +495,41 @@ topk_merge_kernel(const float* __restrict__ cand_scores, const int64_t* __restri
         }
       }
       win_pos = bp;
-      const float osc = bp >= 0 ? bv : -CUDART_INF_F;
-      const int64_t oid = bp >= 0 ? bi : -1;
-      win_id = oid;
-      if (out_scores != nullptr) {
-        out_scores[static_cast<size_t>(q) * k_out + r] = osc;
-        out_ids[static_cast<size_t>(q) * k_out + r] = oid;
-      }
-      if (peer_scores != nullptr) {
-        for (int p = 0; p < world; ++p) {
-          const size_t dst = ((static_cast<size_t>(step & 1u) * world + rank) * nq + q) * k_out + r;
-          peer_scores[p][dst] = osc;
-          peer_ids[p][dst] = oid;
-        }
-      }
-      if (bp >= 0) {
-        // also drop duplicates of the winning id (same document reported by two lists)
-        s_id[bp] = -1;
-      }
+      win_id = bp >= 0 ? bi : -1;
+      w_sc[r] = bp >= 0 ? bv : -CUDART_INF_F;
+      w_id[r] = bp >= 0 ? bi : -1;
+      if (bp >= 0) s_id[bp] = -1;
     }
     __syncthreads();
     // duplicate suppression across lists: any other candidate with the same id is retired
     if (win_pos >= 0) {
       const int64_t wid = win_id;
-      if (wid >= 0)
-        for (int i = threadIdx.x; i < n; i += blockDim.x)
-          if (s_id[i] == wid) s_id[i] = -1;
+      for (int i = threadIdx.x; i < n_live; i += blockDim.x)
+        if (s_id[i] == wid) s_id[i] = -1;
     }
     __syncthreads();
+    if (win_pos < 0) {        // candidates exhausted: the remaining ranks are empty
+      for (int rr = r + 1 + static_cast<int>(threadIdx.x); rr < k_out; rr += blockDim.x) {
+        w_sc[rr] = -CUDART_INF_F;
+        w_id[rr] = -1;
+      }
+      __syncthreads();
+      break;
+    }
+  }
+  // ---- publish: the local result and, for the fused exchange, slot[rank] of every peer's receive area -- all threads store
+  for (int idx = threadIdx.x; idx < k_out * (1 + (peer_scores != nullptr ? world : 0)); idx += blockDim.x) {
+    const int r = idx % k_out, dst_rank = idx / k_out - 1;       // -1: local output
+    if (dst_rank < 0) {
+      if (out_scores != nullptr) {
+        out_scores[static_cast<size_t>(q) * k_out + r] = w_sc[r];
+        out_ids[static_cast<size_t>(q) * k_out + r] = w_id[r];
+      }
+    } else {
+      const size_t dst = ((static_cast<size_t>(step & 1u) * world + rank) * nq + q) * k_out + r;
+      peer_scores[dst_rank][dst] = w_sc[r];
+      peer_ids[dst_rank][dst] = w_id[r];
+    }
   }
   if (peer_flags != nullptr) {
     __threadfence_system();
@@ -666,6 +702,7 @@ IM_API int im_topk_merge(const float* cand_scores, const int64_t* cand_ids64, co
                          unsigned wait_limit) {
   using namespace im;
   if (nq <= 0) return 0;
+  if (k_out < 1 || k_out > 32) return set_error("im_topk_merge", "k_out must be in [1,32]");
   const size_t n = static_cast<size_t>(P) * k_in;
   const size_t smem = ((n * 4 + 7) & ~size_t(7)) + n * 8;
   if (smem > 200 * 1024) return set_error("im_topk_merge", "too many candidates per query");
