@@ -92,7 +92,7 @@ def main():
               f"top-1 {top1}/{len(queries)}, overlap@10 {over:.3f}, snippets equal on {snip}/{same}", flush=True)
         if name == "bm25+signals":
             # fused scores of near-tied documents may round differently once ages are taken against another build instant
-            ok &= same >= 0.95 * len(queries) and top1 >= 0.98 * len(queries) and snip == same and nonempty > len(queries) // 2
+            ok &= over >= 0.99 and same >= 0.85 * len(queries) and top1 >= 0.98 * len(queries) and snip == same and nonempty > len(queries) // 2
         else:
             ok &= top1 >= 0.9 * len(queries) and over >= 0.9
     st.close()
