@@ -70,7 +70,7 @@ class GpuSearchIndex:
                  reranker: BertModel | None = None, rerank: bool = True, query_batch: int = 64, passage_len: int = 96,
                  enc_doc_tokens: int = 128, embed_batch: int = 256, use_graph: bool = True, seed: int = 0,
                  encoder_path: str | None = None, reranker_path: str | None = None, allow_untrained: bool = False,
-                 rank_signals: bool = False, authority_fn=None, shard: tuple[int, int] | None = None):
+                 rank_signals: bool = False, authority_fn=None, shard: tuple[int, int] | None = None, dense_dtype: str = "bf16"):
         self.store = store
         self.device = torch.device(device)
         self.enc_tok = self.rr_tok = None
@@ -90,6 +90,7 @@ class GpuSearchIndex:
         self.rank_signals, self.authority_fn = bool(rank_signals), authority_fn
         # (rank, world) of a document-sharded deployment (engine/multigpu.py): this process indexes documents
         # [rank * per, (rank + 1) * per) of the store on its GPU; vocabulary / df / idf stay global
+        self.dense_dtype = dense_dtype if dense_dtype in ("bf16", "fp8") else "bf16"     # [gpu] shard_dtype
         self.shard_rank, self.shard_world = shard if shard is not None else (0, 1)
         self.row_base = 0
         self._pheap = None
@@ -380,7 +381,9 @@ class GpuSearchIndex:
             shard.authority = torch.from_numpy(passages["authority"]).to(dev) if passages.get("authority") is not None else None
             shard.signal_base = 0 if self.shard_world > 1 else self.row_base     # sharded: the signal arrays cover every document
         cfg = HybridConfig(nq=self.nq, rerank=self.rerank, k_fetch=20, n_rerank=20, k_out=10, pair_seq=min(128, 32 + self.passage_len),
-                           use_graph=self.use_graph, dense=self.use_dense, rank_signals=self.rank_signals)
+                           use_graph=self.use_graph, dense=self.use_dense, rank_signals=self.rank_signals,
+                           dense_dtype=self.dense_dtype if vectors.shape[1] % 128 == 0 else "bf16",
+                           degraded_ok=self.shard_world > 1)       # sharded serving answers without a silent / unhealthy shard
         engine = HybridEngine(shard, cfg, encoder=self.encoder, reranker=self.reranker, **ekw)
         engine.warm()           # graph capture belongs to the build, not to the first query (and never to a serving thread)
         pin = torch.cuda.is_available()
@@ -448,6 +451,15 @@ class GpuSearchIndex:
         with self._lock:      # staging buffers, graph-static device buffers and the row map are shared state
             if self.engine is None:
                 return {}
+            self._searches = getattr(self, "_searches", 0) + 1
+            if self.shard_world > 1 and self._searches % 256 == 1:       # ECC / Xid state -> degraded-mode mask of the exchange
+                from infomesh_b200.resources.gpu_health import GpuHealthMonitor
+
+                mon = self.__dict__.setdefault("_mesh_health", GpuHealthMonitor(None))
+                try:
+                    self.engine.apply_health(mon)
+                except Exception:  # noqa: BLE001 -- health polling must never fail a search
+                    pass
             self._stage(chunk)
             self.engine.search_batch(self._h_enc, self._h_enc_len, self._h_qtok, self._h_qlen, self._h_terms, self._h_scores, self._h_ids)
             # K11 on the device: best passage (coverage + 0.1 x density) of every returned (query, document) pair
@@ -619,6 +631,7 @@ def gpu_index_kwargs(gcfg) -> dict:
     if getattr(gcfg, "reranker_path", ""):
         kw["reranker_path"] = gcfg.reranker_path
     kw["rank_signals"] = True            # serving surfaces answer like search_local: ranking signals fused on the device
+    kw["dense_dtype"] = str(getattr(gcfg, "shard_dtype", "bf16"))
     kw["allow_untrained"] = bool(getattr(gcfg, "allow_untrained_models", False))
     return kw
 

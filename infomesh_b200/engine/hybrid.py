@@ -456,6 +456,22 @@ class HybridEngine:
             return []
         return sorted(set(self.ch_dense.dead_ranks()) | set(self.ch_bm25.dead_ranks()))
 
+    def apply_health(self, monitor) -> list[int]:
+        """Feed NVML health (ECC uncorrected errors, Xid events, a lost device: ``resources/gpu_health.py``) into the
+        degraded-mode mask of the exchange channels: the merge kernels read the status word first and ignore the lists of
+        masked shards without waiting for them, so an unhealthy GPU costs recall on its documents, not availability.
+        Only with ``degraded_ok`` and the p2p exchange; device index == local rank on a single node.  Returns the masked ranks."""
+        if self.heap is None or not self.cfg.degraded_ok:
+            return []
+        bad = [r for r in monitor.unhealthy_devices() if 0 <= r < self.ctx.world and r != self.ctx.rank]
+        if bad:
+            mask = 0
+            for r in bad:
+                mask |= 1 << r
+            for ch in (self.ch_dense, self.ch_bm25):
+                ch.status |= mask                       # sticky, like a timeout; clear_status() re-admits the shard
+        return bad
+
     def stage_times(self, iters: int = 5) -> dict:
         """Median device time (ms) of every pipeline stage, measured eagerly with CUDA events between the stages (so
         the sum exceeds a CUDA-graph replay of the whole step by the launch gaps).  Names the limiter at each N."""

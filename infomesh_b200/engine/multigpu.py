@@ -86,6 +86,8 @@ def _worker_main(rank: int, world: int, port: int, conn, store_path: str, kwargs
                 conn.send(("ok", int(index.rebuild())))
             elif op == "stats":
                 conn.send(("ok", _plain(index.stats())))
+            elif op == "delete":
+                conn.send(("ok", bool(index.mark_deleted(int(arg)))))
             elif op == "close":
                 conn.send(("ok", None))
                 break
@@ -139,6 +141,8 @@ class MultiGpuSearchIndex:
         self.healthy = False
         self.built_at = 0.0
         self.build_seconds = 0.0
+        self.reranker = None            # models live in the workers; host-side callers (mcp/handlers._reranker) must not reach for them
+        self.device = "cuda"
 
     # ------------------------------------------------------------------ lifecycle
     def _spawn(self) -> None:
@@ -220,6 +224,24 @@ class MultiGpuSearchIndex:
     def close(self) -> None:
         with self._lock:
             self._teardown()
+
+    @property
+    def engine(self):
+        """Truthy while the worker group serves (the serving surfaces test ``index.engine is not None``)."""
+        return self if self.healthy else None
+
+    def mark_deleted(self, doc_id: int) -> bool:
+        """Tombstone a document on whichever shard owns it."""
+        if not self.healthy:
+            return False
+        with self._lock:
+            try:
+                for conn in self._conns:
+                    conn.send(("delete", int(doc_id)))
+                return any(self._collect(min(self._call_timeout, 10.0)))
+            except Exception as exc:  # noqa: BLE001
+                logger.warning("multigpu_delete_failed", error=str(exc))
+                return False
 
     # ------------------------------------------------------------------ queries
     def search_many(self, queries: list[str], k: int = 10) -> list[list[dict[str, object]]]:

@@ -48,6 +48,13 @@ class FakeShardIndex:
                         best[i, j], span[i, j] = 0, (at, at + len(terms[0]))
         return {"scores": scores, "rows": rows, "doc_ids": ids, "pass": best, "span": span}
 
+    def mark_deleted(self, doc_id):
+        hit = np.nonzero(self.ids == int(doc_id))[0]
+        if hit.size == 0:
+            return False
+        self.all_text[self.lo + int(hit[0])] = []          # no term matches any more
+        return True
+
     def stats(self):
         return {"documents": int(self.ids.size), "hbm_bytes": 1000 + self.rank, "rank": self.rank}
 

@@ -74,3 +74,36 @@ def test_monitor_without_nvml_reports_unavailable(monkeypatch):
     mon = GH.GpuHealthMonitor()
     hs = mon.poll()
     assert len(hs) == 1 and not hs[0].available and hs[0].healthy and mon.summary()["all_healthy"]
+
+
+def test_apply_health_masks_unhealthy_peers_only():
+    """HybridEngine.apply_health: unhealthy device indices become bits of the channels' degraded-mode status word (own rank and
+    out-of-range indices excluded); nothing happens without degraded_ok or without a peer heap."""
+    from types import SimpleNamespace
+
+    import torch
+
+    from infomesh_b200.engine.hybrid import HybridEngine
+
+    class Mon:
+        def __init__(self, bad):
+            self.bad = bad
+
+        def unhealthy_devices(self):
+            return self.bad
+
+    def fake(world, rank, degraded_ok=True, heap=True):
+        e = HybridEngine.__new__(HybridEngine)
+        e.cfg = SimpleNamespace(degraded_ok=degraded_ok)
+        e.ctx = SimpleNamespace(world=world, rank=rank)
+        e.heap = object() if heap else None
+        e.ch_dense = SimpleNamespace(status=torch.zeros(1, dtype=torch.int32))
+        e.ch_bm25 = SimpleNamespace(status=torch.zeros(1, dtype=torch.int32))
+        return e
+
+    e = fake(8, 2)
+    assert e.apply_health(Mon([5, 2, 11, 0])) == [5, 0]
+    assert int(e.ch_dense.status.item()) == (1 << 5) | 1 and int(e.ch_bm25.status.item()) == (1 << 5) | 1
+    assert e.apply_health(Mon([])) == [] and int(e.ch_dense.status.item()) == (1 << 5) | 1        # sticky
+    assert fake(8, 2, degraded_ok=False).apply_health(Mon([5])) == []
+    assert fake(8, 2, heap=False).apply_health(Mon([5])) == []

@@ -56,6 +56,18 @@ def test_search_merges_rows_owned_by_different_ranks(front):
     assert min(urls) < 12 <= max(urls)
 
 
+def test_delete_reaches_the_owning_shard_and_surface_attributes(front):
+    f, st = front
+    assert f.engine is None and not f.mark_deleted(1)          # not serving yet
+    f.rebuild()
+    assert f.engine is not None and f.reranker is None
+    doc20 = f.search("unique20", k=1)[0]["doc_id"]
+    assert f.mark_deleted(doc20) and not f.mark_deleted(10 ** 9)
+    assert f.search("unique20", k=1) == []
+    f.note_added(3)
+    assert f.refresh() == 0                                    # rebuild in place: nothing new in the store
+
+
 def test_worker_crash_marks_front_unhealthy_and_rebuild_recovers(tmp_path):
     st = _store(tmp_path)
     f = MultiGpuSearchIndex(st, devices=2, store_path=str(tmp_path / "index.db"), query_batch=4,
