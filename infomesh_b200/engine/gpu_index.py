@@ -44,6 +44,7 @@ from infomesh_b200.utils.tokenizer import BERT_SPECIALS, XLMR_SPECIALS, HashToke
 
 logger = get_logger(__name__)
 
+LATENCY_NQ = 8          # queries per pass of the low-latency lane (interactive, one-at-a-time searches)
 UNKNOWN_TERM = -2       # out-of-vocabulary query term: makes the implicit AND empty (FTS5 semantics)
 
 
@@ -384,25 +385,36 @@ class GpuSearchIndex:
                            use_graph=self.use_graph, dense=self.use_dense, rank_signals=self.rank_signals,
                            dense_dtype=self.dense_dtype if vectors.shape[1] % 128 == 0 else "bf16",
                            degraded_ok=self.shard_world > 1)       # sharded serving answers without a silent / unhealthy shard
-        engine = HybridEngine(shard, cfg, encoder=self.encoder, reranker=self.reranker, **ekw)
-        engine.warm()           # graph capture belongs to the build, not to the first query (and never to a serving thread)
         pin = torch.cuda.is_available()
 
-        def mk(*shape, fill=0):
-            t = torch.full(shape, fill, dtype=torch.int32)
-            return t.pin_memory() if pin else t
+        def lane(nq: int):
+            """One serving lane: an engine captured for ``nq`` queries per pass + its pinned staging buffers."""
+            from dataclasses import replace as _r
 
-        h_scores = torch.empty((cfg.nq, cfg.k_out), dtype=torch.float32)
-        h_ids = torch.empty((cfg.nq, cfg.k_out), dtype=torch.int64)
-        if pin:
-            h_scores, h_ids = h_scores.pin_memory(), h_ids.pin_memory()
-        staging = (mk(cfg.nq, cfg.enc_seq), mk(cfg.nq, fill=1), mk(cfg.nq, cfg.max_q_tokens, fill=self.rr_tok.sp.pad),
-                   mk(cfg.nq, fill=1), mk(cfg.nq, cfg.max_terms, fill=-1), h_scores, h_ids)
+            eng = HybridEngine(shard, _r(cfg, nq=nq), encoder=self.encoder, reranker=self.reranker, **ekw)
+            eng.warm()          # graph capture belongs to the build, not to the first query (and never to a serving thread)
+
+            def mk(*shape, fill=0):
+                t = torch.full(shape, fill, dtype=torch.int32)
+                return t.pin_memory() if pin else t
+
+            h_scores = torch.empty((nq, cfg.k_out), dtype=torch.float32)
+            h_ids = torch.empty((nq, cfg.k_out), dtype=torch.int64)
+            if pin:
+                h_scores, h_ids = h_scores.pin_memory(), h_ids.pin_memory()
+            return eng, (mk(nq, cfg.enc_seq), mk(nq, fill=1), mk(nq, cfg.max_q_tokens, fill=self.rr_tok.sp.pad), mk(nq, fill=1),
+                         mk(nq, cfg.max_terms, fill=-1), h_scores, h_ids)
+
+        engine, staging = lane(cfg.nq)
+        # interactive queries arrive one at a time: a pass captured for LATENCY_NQ queries costs a fraction of a full-batch
+        # pass (the cross-encoder sees 8 x 20 pairs instead of 64 x 20), so single searches take the small lane
+        small = lane(LATENCY_NQ) if cfg.nq > LATENCY_NQ and LATENCY_NQ % max(self.shard_world, 1) == 0 else None
         row_of = {int(x): i for i, x in enumerate(doc_ids)}
         pass_dev = {k: torch.from_numpy(np.ascontiguousarray(passages[k])).to(dev) for k in ("terms", "off", "doc_off")}
         with self._lock:
             self._pass, self._pass_dev = passages, pass_dev
             self._csr, self.engine, self.builder = csr, engine, builder
+            self._small = small
             self.doc_ids, self._row_of, self._pending = doc_ids, row_of, 0
             (self._h_enc, self._h_enc_len, self._h_qtok, self._h_qlen, self._h_terms, self._h_scores, self._h_ids) = staging
 
@@ -423,26 +435,28 @@ class GpuSearchIndex:
         return self._pending > 0
 
     # ------------------------------------------------------------------ query
-    def _stage(self, queries: list[str]) -> None:
-        cfg = self.engine.cfg
-        self._h_enc.zero_()
-        self._h_enc_len.fill_(2)
-        self._h_qtok.fill_(self.rr_tok.sp.pad)
-        self._h_qlen.fill_(1)
-        self._h_terms.fill_(-1)
+    def _stage(self, queries: list[str], engine=None, staging=None) -> None:
+        engine = engine or self.engine
+        h_enc, h_enc_len, h_qtok, h_qlen, h_terms = (staging or (self._h_enc, self._h_enc_len, self._h_qtok, self._h_qlen, self._h_terms))[:5]
+        cfg = engine.cfg
+        h_enc.zero_()
+        h_enc_len.fill_(2)
+        h_qtok.fill_(self.rr_tok.sp.pad)
+        h_qlen.fill_(1)
+        h_terms.fill_(-1)
         for i, q in enumerate(queries):
             e = self.enc_tok.encode(q, cfg.enc_seq)
-            self._h_enc[i, :len(e)] = torch.tensor(e, dtype=torch.int32)
-            self._h_enc_len[i] = len(e)
+            h_enc[i, :len(e)] = torch.tensor(e, dtype=torch.int32)
+            h_enc_len[i] = len(e)
             t = self.rr_tok.encode_plain(q, cfg.max_q_tokens) or [self.rr_tok.sp.unk]
-            self._h_qtok[i, :len(t)] = torch.tensor(t, dtype=torch.int32)
-            self._h_qlen[i] = len(t)
+            h_qtok[i, :len(t)] = torch.tensor(t, dtype=torch.int32)
+            h_qlen[i] = len(t)
             terms = [int(x) if x >= 0 else UNKNOWN_TERM for x in dict.fromkeys(self.builder.tokenize(q).tolist())][:cfg.max_terms]
             if terms:
-                self._h_terms[i, :len(terms)] = torch.tensor(terms, dtype=torch.int32)
+                h_terms[i, :len(terms)] = torch.tensor(terms, dtype=torch.int32)
         for i in range(len(queries), cfg.nq):        # padding rows: a CLS/SEP-only query with no terms
             e = [self.enc_tok.sp.cls, self.enc_tok.sp.sep]
-            self._h_enc[i, :2] = torch.tensor(e, dtype=torch.int32)
+            h_enc[i, :2] = torch.tensor(e, dtype=torch.int32)
 
     def search_arrays(self, chunk: list[str]) -> dict[str, np.ndarray]:
         """One device pass over up to ``query_batch`` queries -> host arrays ``[nq, k_out]``: ``scores``, global ``rows``,
@@ -460,13 +474,16 @@ class GpuSearchIndex:
                     self.engine.apply_health(mon)
                 except Exception:  # noqa: BLE001 -- health polling must never fail a search
                     pass
-            self._stage(chunk)
-            self.engine.search_batch(self._h_enc, self._h_enc_len, self._h_qtok, self._h_qlen, self._h_terms, self._h_scores, self._h_ids)
+            small = getattr(self, "_small", None)
+            eng, st = small if (small is not None and len(chunk) <= small[0].cfg.nq) else (
+                self.engine, (self._h_enc, self._h_enc_len, self._h_qtok, self._h_qlen, self._h_terms, self._h_scores, self._h_ids))
+            self._stage(chunk, eng, st)
+            eng.search_batch(*st)
             # K11 on the device: best passage (coverage + 0.1 x density) of every returned (query, document) pair
-            best_pass = self._best_passages()
+            best_pass = self._best_passages(eng)
             torch.cuda.current_stream(self.device).synchronize()
-            scores, rows = self._h_scores.numpy().copy(), self._h_ids.numpy().copy()
-            best_pass = best_pass.cpu().numpy().reshape(rows.shape)
+            scores, rows = st[5].numpy()[:len(chunk)].copy(), st[6].numpy()[:len(chunk)].copy()
+            best_pass = best_pass.cpu().numpy().reshape(eng.cfg.nq, -1)[:len(chunk)]
             doc_ids, spans, doc_off = self.doc_ids, self._pass["span"], self._pass["doc_off"]
         local = rows - self.row_base
         own = (local >= 0) & (local < doc_ids.size)
@@ -491,11 +508,11 @@ class GpuSearchIndex:
             out.extend(format_hits(self.store, chunk, k, arr) if arr else [[] for _ in chunk])
         return out
 
-    def _best_passages(self) -> torch.Tensor:
+    def _best_passages(self, eng=None) -> torch.Tensor:
         """int32 ``[nq * k_out]``: index of the best passage inside each returned document (-1: none / no query terms)."""
         from infomesh_b200.ops.bm25 import passage_score
 
-        eng = self.engine
+        eng = eng or self.engine
         nq, k_out = eng.out_ids.shape
         pair_doc = eng.out_ids.reshape(-1) - self.row_base          # rows of other shards are not scored here
         pair_doc = torch.where((pair_doc >= 0) & (pair_doc < self.doc_ids.size), pair_doc, -1).to(torch.int32)
@@ -511,8 +528,10 @@ class GpuSearchIndex:
         """Drop the device structures (and, sharded, leave the symmetric heaps: peers must do the same collectively)."""
         with self._lock:
             eng, self.engine = self.engine, None
-            if eng is not None and getattr(eng, "heap", None) is not None:
-                eng.heap.close()
+            small, self._small = getattr(self, "_small", None), None
+            for e in (eng, small[0] if small else None):
+                if e is not None and getattr(e, "heap", None) is not None:
+                    e.heap.close()
             if self._pheap is not None:
                 self._pheap.close()
                 self._pheap = None
