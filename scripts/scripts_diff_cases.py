@@ -142,3 +142,55 @@ def _vec(pkg):
 
     VR = importlib.import_module(pkg + ".index.vector_store").VectorSearchResult
     return [VR(doc_id="2", url="https://b.org/2", title="B", text_preview="pb", score=0.9), VR(doc_id="3", url="https://c.org/3", title="C", text_preview="pc", score=0.5)]
+
+
+# ----------------------------------------------------------------------------- round 2: wider input sweeps over the same functions
+_URLS = ["https://Example.COM/a/../b/./c?x=1&utm_medium=m&y=2#top", "http://example.com:8080/path;params?q=1", "https://example.com/%7Euser/?a=1&a=2&b=",
+         "HTTP://EXAMPLE.COM", "https://example.com/a?", "https://example.com/a#", "https://example.com//double//slash/", "https://example.com/trailing/",
+         "https://example.com/index.html?ref=home&id=5", "https://xn--bcher-kva.example/ü?q=ä", "https://example.com/a b c", "https://example.com/?b=2&a=1&c=3",
+         "https://user@example.com/", "https://example.com:443", "http://example.com:80", "https://example.com/path?mc_cid=1&mc_eid=2&real=1",
+         "https://example.com/?utm_source=a", "ftp://example.com/file", "not a url", "", "https://example.com/%E2%9C%93", "https://EXAMPLE.com/CaseSensitive/Path"]
+_HOSTS = ["http://192.168.1.1/", "http://172.16.0.1/", "http://172.32.0.1/", "http://[fe80::1]/", "http://[fd00::1]/", "http://0.0.0.0/", "http://2130706433/",
+          "http://example.com@127.0.0.1/", "https://example.org:8443/x", "http://metadata.google.internal/", "https://sub.example.co.uk/a?b=c", "javascript:alert(1)",
+          "file:///etc/passwd", "http://100.64.0.1/", "http://198.18.0.1/", "https://1.1.1.1/"]
+_QUERIES = ["python asyncio tutorial", "how do i install cuda on ubuntu", "best GPU 2024", "\"exact phrase\" -excluded", "site:github.com tensor cores", "C++ templates",
+            "  spaces   everywhere  ", "UPPER lower MiXeD", "日本語のクエリ", "한국어 질문 입니다", "emoji 🚀 query", "a", "the of and", "x" * 300, "what is the capital of france?",
+            "login facebook", "buy cheap laptop online", "weather tomorrow", "define: tensor", "error: undefined reference to `main'"]
+_TEXTS = [T1, T2, T3, T4, "", "short", "One sentence only.", "Numbers 123 456.789 and symbols #!$%", "Line one\nLine two\n\nParagraph two starts here. It has two sentences.",
+          "ALL CAPS TEXT WITH MANY WORDS TO SEE HOW TOKENISATION BEHAVES", "mixed 한글 and English words together in one sentence", "repeat " * 50,
+          "Bonjour le monde, ceci est une phrase en français avec des accents éàç.", "Hola mundo, esta es una oración en español con eñe.",
+          "Привет мир, это предложение на русском языке.", "这是一个中文句子，用来测试分词。", "مرحبا بالعالم هذه جملة عربية"]
+
+CASES += [
+    ("crawler.dedup", "normalize_url", [_c(u) for u in _URLS]),
+    ("security", "validate_url", [_c(u) for u in _HOSTS]),
+    ("search.query", "_sanitize_fts_query", [_c(q) for q in _QUERIES]),
+    ("search.passage", "classify_intent", [_c(q) for q in _QUERIES]),
+    ("search.nlp", "expand_query", [_c(q) for q in _QUERIES[:12]]),
+    ("search.nlp", "parse_natural_query", [_c(q) for q in _QUERIES[:12]]),
+    ("search.cjk", "tokenize_query_cjk", [_c(q) for q in _QUERIES[:12]]),
+    ("search.cjk", "is_cjk_text", [_c(t) for t in _TEXTS]),
+    ("search.quality", "extract_temporal_hint", [_c(q) for q in ("latest news", "this week in ai", "yesterday's game", "2019 budget", "last year sales", "recent papers", "old maps")]),
+    ("crawler.simhash", "simhash", [_c(t) for t in _TEXTS]),
+    ("search.passage", "split_passages", [_c(t) for t in _TEXTS]),
+    ("search.passage", "select_best_passage", [_c(t, "tensor memory sentence") for t in _TEXTS[:10]]),
+    ("index.distributed", "extract_keywords", [_c(t) for t in _TEXTS]),
+    ("search.passage", "title_match_score", [_c(t[:60], "tensor memory") for t in _TEXTS[:8]]),
+    ("search.passage", "url_path_score", [_c(u, "example path index") for u in _URLS[:10]]),
+    ("p2p.protocol", "keyword_to_dht_key", [_c(w) for w in ("rust", "RUST", " rust ", "c++", "日本", "a" * 200)]),
+    ("p2p.protocol", "url_to_dht_key", [_c(u) for u in _URLS[:8]]),
+    ("hashing", "content_hash", [_c(t) for t in _TEXTS[:8]]),
+    ("crawler.simhash", "hamming_distance", [_c(a, b) for a, b in ((1, 2), (0xFFFF, 0xFFFE), (2 ** 63, 0), (12345678901234567890 % 2 ** 64, 987654321))]),
+    ("summarizer.verify", "compute_similarity", [_c(a, b) for a, b in ((T1, T1[:200]), (T1, T4), ("a b c d e", "e d c b a"), ("x", ""))]),
+    ("search.cross_validate", "snippet_similarity", [_c(a, b) for a, b in ((T1[:100], T1[50:150]), ("one two three", "three two one"), ("", ""))]),
+    ("data_quality", "compute_trust_grade", [_c(x / 20) for x in range(0, 21)]),
+    ("crawler.recrawl", "compute_recrawl_interval", [_c(x / 10) for x in range(0, 11)]),
+    ("index.ranking", "freshness_score", [_c(1_000_000.0 - d * 86400.0, now=1_000_000.0) for d in (0, 1, 3, 7, 14, 30, 90, 365)]),
+    ("index.ranking", "normalize_bm25", [_c(float(s), max_score=float(m)) for s, m in ((1, 1), (5, 10), (10, 5), (0.1, 20), (100, 1))]),
+    ("credits.scheduling", "is_off_peak_at", [_c(hour=h) for h in range(0, 24, 3)]),
+    ("version_check", "_parse_version", [_c(v) for v in ("0.1.0", "1.2.3rc1", "2024.01.15", "v2", "abc", "1.0.0+build.5", "10.20.30.40")]),
+    ("version_check", "is_newer", [_c(a, b) for a, b in (("1.2.4", "1.2.3"), ("1.2.3", "1.2.3"), ("2.0", "1.99.99"), ("0.9", "1.0"))]),
+    ("crawler.pdf", "is_pdf_url", [_c(u) for u in ("https://x.org/a.pdf", "https://x.org/a.PDF?dl=1", "https://x.org/pdf", "https://x.org/a.pdf#page=2", "")]),
+    ("p2p.peer_profile", "_percentile", [_c(v, q) for v, q in (([1.0, 2.0, 3.0], 50), ([1.0], 99), ([4.0, 1.0, 3.0, 2.0], 25), ([10.0, 20.0], 95))]),
+    ("crawler.freshness", "classify_freshness", [_c(1_000_000.0 - a, now=1_000_000.0) for a in (0, 1800, 3600, 7200, 86400, 172800, 604800, 1209600)]),
+]

@@ -84,3 +84,15 @@ def test_scenario_matches_reference(name, tmp_path):
         diff = {k: (theirs.get(k), ours.get(k)) for k in sorted(set(ours) | set(theirs)) if ours.get(k) != theirs.get(k)}
         assert not diff, f"(reference, ours) differ on: {diff}"
     assert ours == theirs
+
+
+def test_url_validation_is_stricter_than_the_reference_where_it_matters():
+    """Two inputs the reference accepts and this repo refuses on purpose (kept out of the sweep above): an IPv4-mapped IPv6
+    loopback literal (an SSRF bypass) and a URL far beyond any sane length."""
+    from infomesh.security import validate_url as theirs
+    from infomesh_b200.security import SSRFError, validate_url as ours
+
+    for url in ("http://[::ffff:127.0.0.1]/", "https://example.org/" + "a" * 3000):
+        assert theirs(url)            # accepted upstream
+        with pytest.raises(SSRFError):
+            ours(url)
