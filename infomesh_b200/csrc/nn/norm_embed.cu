@@ -236,6 +236,9 @@ struct SumLnComm {
   MxRowOut mx;            // optional MXFP8 copy of the normalised rows (feeds the block-scaled GEMMs)
 };
 
+// (Measured alternative, round 2: a "streaming" variant that keeps gamma / beta in registers and walks 4 rows per warp -- 9
+//  instead of 21 memory instructions per row, but 101 registers -> 2 CTAs per SM -- ran at 91 us against 77 us for this kernel on
+//  [90112, 768] with the MX output: fewer warps in flight cost more than the saved L1 wavefronts.  Not kept.)
 template <int VEC>
 __global__ void __launch_bounds__(kRowsPerBlock * 32)
 sum_ln_kernel(const __nv_bfloat16* in, size_t in_stride_p, int P,  // in / residual: NOT __restrict__ -- in TP mode peers
@@ -303,64 +306,6 @@ sum_ln_kernel(const __nv_bfloat16* in, size_t in_stride_p, int P,  // in / resid
 }
 
 
-
-// Streaming LayerNorm / RMSNorm + MX quantiser for the cross-encoder's hot path (one input, optional residual, bf16 + MX
-// outputs, no collectives).  ncu on sum_ln_kernel at [90k, 768]: 3.5 TB/s with `l1tex__data_pipe_lsu_wavefronts` as the top
-// unit -- 12 of the 21 memory instructions per row were the gamma / beta reloads.  Here a warp keeps gamma / beta in
-// registers and walks kRowsPerWarp consecutive rows, so a row costs 3 loads + 3 + 3 stores.
-constexpr int kLnRowsPerWarp = 4;
-template <int VEC>
-__global__ void __launch_bounds__(kRowsPerBlock * 32)
-ln_stream_kernel(const __nv_bfloat16* __restrict__ in, const __nv_bfloat16* __restrict__ residual,
-                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int rms_only, int n_rows,
-                 const int* __restrict__ n_rows_dev, __nv_bfloat16* __restrict__ out, const MxRowOut mx) {
-  constexpr int H = VEC * 128;
-  const int lane = threadIdx.x & 31;
-  // the affine parameters are weights: safe to read before the producer kernel has finished (PDL prologue)
-  float g[VEC][4], b[VEC][4];
-#pragma unroll
-  for (int v = 0; v < VEC; ++v) {
-    const int col = row_col<VEC>(v, lane);
-    const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + col));
-    g[v][0] = g4.x; g[v][1] = g4.y; g[v][2] = g4.z; g[v][3] = g4.w;
-    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (beta != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(beta + col));
-    b[v][0] = b4.x; b[v][1] = b4.y; b[v][2] = b4.z; b[v][3] = b4.w;
-  }
-  pdl_trigger();
-  pdl_wait();
-  if (n_rows_dev != nullptr) n_rows = min(n_rows, *n_rows_dev);
-  const int row0 = (blockIdx.x * kRowsPerBlock + (threadIdx.x >> 5)) * kLnRowsPerWarp;
-#pragma unroll 2
-  for (int r = 0; r < kLnRowsPerWarp; ++r) {
-    const int row = row0 + r;
-    if (row >= n_rows) break;
-    float x[VEC][4];
-    load_row<VEC, false>(in + static_cast<size_t>(row) * H, lane, x);
-    if (residual != nullptr) load_row<VEC, true>(residual + static_cast<size_t>(row) * H, lane, x);
-    float s = 0.f;
-#pragma unroll
-    for (int v = 0; v < VEC; ++v)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) s += x[v][j];
-    const float mean = rms_only ? 0.f : warp_sum(s) * (1.0f / H);
-    float q = 0.f;
-#pragma unroll
-    for (int v = 0; v < VEC; ++v)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float d = x[v][j] - mean;
-        q += d * d;
-      }
-    const float rstd = rsqrtf(warp_sum(q) * (1.0f / H) + eps);
-#pragma unroll
-    for (int v = 0; v < VEC; ++v)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) x[v][j] = (x[v][j] - mean) * rstd * g[v][j] + b[v][j];
-    if (out != nullptr) store_row<VEC>(out + static_cast<size_t>(row) * H, lane, x);
-    store_row_mx<VEC>(mx, row, lane, x);
-  }
-}
 
 // ---------------------------------------------------------------------------------------------------------------
 // Tensor-parallel all-reduce fused with residual add + LayerNorm / RMSNorm (TP without sequence sharding: T5 decode
@@ -808,20 +753,6 @@ static int sum_ln_impl(const void* in, long long in_stride_p, int P, const void*
   cm.mx.sf = reinterpret_cast<uint8_t*>(mx_sf);
   cm.mx.ld = mx_ld;
   auto s = reinterpret_cast<cudaStream_t>(stream);
-  static const bool stream_ln = []() {
-    const char* e = getenv("INFOMESH_B200_LN_STREAM");      // A/B switch; default on
-    return e == nullptr || e[0] != '0';
-  }();
-  if (stream_ln && mx_q != nullptr && P == 1 && sum_out == nullptr && arrive_flags == nullptr && peer_out == nullptr &&
-      peer_out_flags == nullptr) {
-    const int per_cta = kRowsPerBlock * kLnRowsPerWarp;
-    const int grid_s = (n_rows + per_cta - 1) / per_cta;
-    IM_DISPATCH_VEC(H, IM_CUDA_OK(launch_pdl(ln_stream_kernel<VEC>, dim3(grid_s), dim3(kRowsPerBlock * 32), 0, s,
-                                             (const __nv_bfloat16*)in, (const __nv_bfloat16*)residual, gamma, beta, eps, rms_only,
-                                             n_rows, n_rows_dev, (__nv_bfloat16*)out, cm.mx)));
-    IM_LAUNCH_OK("ln_stream_kernel");
-    return 0;
-  }
   const int grid = (n_rows + kRowsPerBlock - 1) / kRowsPerBlock;
   IM_DISPATCH_VEC(H, IM_CUDA_OK(launch_pdl(sum_ln_kernel<VEC>, dim3(grid), dim3(kRowsPerBlock * 32), 0, s,
                                            (const __nv_bfloat16*)in, (size_t)in_stride_p, P,
