@@ -73,6 +73,8 @@ class NetworkConfig:
     bootstrap_dns: bool = True
     bootstrap_github: bool = True
     bootstrap_dns_domain: str = "infomesh.io"
+    encrypt: bool = True              # offer / accept the IMN1 encrypted, mutually authenticated channel (p2p/secure_channel.py)
+    require_encrypted: bool = False   # refuse peers that only speak plaintext frames
 
 
 @dataclass(frozen=True)

@@ -218,7 +218,9 @@ class InfoMeshNode:
         cfg = self._config
         self._stop_async = asyncio.Event()
         self._prepare_identity()
-        self._transport = Transport(self._key_pair, throttle=self._throttle, is_isolated_fn=self._is_isolated)
+        self._transport = Transport(self._key_pair, throttle=self._throttle, is_isolated_fn=self._is_isolated,
+                                    encrypt=getattr(cfg.network, "encrypt", True),
+                                    require_encrypted=getattr(cfg.network, "require_encrypted", False))
         if self._index_submit_receiver is not None and hasattr(self._index_submit_receiver, "bind_key_registry"):
             self._index_submit_receiver.bind_key_registry(self._transport.keys)
         await self._transport.listen(cfg.node.listen_address, cfg.node.listen_port)
