@@ -26,6 +26,7 @@ from infomesh_b200.p2p.throttle import BandwidthThrottle
 from infomesh_b200.utils.log import get_logger
 
 logger = get_logger(__name__)
+SESSION_IDLE_S = 60.0          # an encrypted session without traffic is closed by the listener after this long
 
 Handler = Callable[[dict[str, Any], "PeerInfo"], Awaitable[tuple[MessageType, dict[str, Any]] | None]]
 
@@ -84,6 +85,10 @@ class Transport:
         self.encrypt = bool(encrypt and key_pair is not None)          # offer / accept the IMN1 encrypted channel
         self.require_encrypted = bool(require_encrypted)               # refuse plaintext peers altogether
         self._plain_peers: set[tuple[str, int]] = set()                # peers that turned the handshake down
+        self._links: dict[tuple[str, int], "_Link"] = {}               # idle encrypted sessions, one per peer address
+        self._link_locks: dict[tuple[str, int], asyncio.Lock] = {}
+        self.handshakes_out = 0
+        self._inbound: set[asyncio.StreamWriter] = set()               # accepted connections still open
         self.encrypted_in = self.encrypted_out = 0
         self.peer_id = key_pair.peer_id if key_pair is not None else ""
         self.throttle = throttle
@@ -111,7 +116,15 @@ class Transport:
         self.host, self.port = (host if host not in ("0.0.0.0", "::") else "127.0.0.1"), sock[1]
         return self.port
 
+    def _drop_links(self) -> None:
+        for link in self._links.values():
+            link.close()
+        self._links.clear()
+
     async def close(self) -> None:
+        self._drop_links()
+        for w in list(self._inbound):          # sessions that peers keep open would hold wait_closed() until they idle out
+            w.close()
         if self._server is not None:
             self._server.close()
             await self._server.wait_closed()
@@ -155,6 +168,7 @@ class Transport:
     async def _serve_conn(self, reader: asyncio.StreamReader, writer: asyncio.StreamWriter) -> None:
         peer = writer.get_extra_info("peername") or ("?", 0)
         session: SC.SecureSession | None = None
+        self._inbound.add(writer)
         try:
             prefix = await asyncio.wait_for(reader.readexactly(4), timeout=30.0)
             if prefix == SC.MAGIC:
@@ -174,10 +188,6 @@ class Transport:
                 if n > MAX_MESSAGE_SIZE:
                     raise ValueError(f"frame too large: {n}")
                 frame = prefix + await asyncio.wait_for(reader.readexactly(n), timeout=30.0)
-            self.bytes_in += len(frame)
-            if self.throttle:
-                await self.throttle.acquire_download(len(frame))
-
             async def answer(data: bytes) -> None:
                 if session is not None:
                     if self.throttle:
@@ -186,24 +196,40 @@ class Transport:
                 else:
                     await self._send(writer, data)
 
-            try:
-                kind, payload, sender = self._unwrap(frame, channel_sender=session.remote_peer_id if session else "")
-            except (MA.VerificationError, ValueError) as exc:
-                await answer(encode_message(MessageType.ERROR, {"error": str(exc)}))
-                return
-            handler = self._handlers.get(kind)
-            if handler is None:
-                await answer(encode_message(MessageType.ERROR, {"error": f"unsupported type {int(kind)}"}))
-                return
-            reply = await handler(payload, PeerInfo(sender, peer[0], peer[1]))
-            if reply is not None:
-                # inside an authenticated channel the reply needs no envelope of its own
-                await answer(encode_message(*reply) if session is not None else self._wrap(encode_message(*reply)))
+            while True:
+                self.bytes_in += len(frame)
+                if self.throttle:
+                    await self.throttle.acquire_download(len(frame))
+                try:
+                    kind, payload, sender = self._unwrap(frame, channel_sender=session.remote_peer_id if session else "")
+                except (MA.VerificationError, ValueError) as exc:
+                    await answer(encode_message(MessageType.ERROR, {"error": str(exc)}))
+                    return
+                handler = self._handlers.get(kind)
+                if handler is None:
+                    await answer(encode_message(MessageType.ERROR, {"error": f"unsupported type {int(kind)}"}))
+                    return
+                reply = await handler(payload, PeerInfo(sender, peer[0], peer[1]))
+                if reply is not None:
+                    # inside an authenticated channel the reply needs no envelope of its own
+                    await answer(encode_message(*reply) if session is not None else self._wrap(encode_message(*reply)))
+                if session is None:
+                    return                      # legacy plaintext peers: one request per connection, as before
+                # an encrypted session stays open: the handshake (2 x X25519 + 2 x Ed25519) is paid once per peer, not per
+                # request; the client closes it, or it is dropped after SESSION_IDLE_S without traffic
+                try:
+                    frame = await asyncio.wait_for(session.recv(reader), timeout=SESSION_IDLE_S)
+                except (asyncio.TimeoutError, asyncio.IncompleteReadError, ConnectionError):
+                    return
+                self.encrypted_in += 1
+                if self._isolated is not None and self._isolated(session.remote_peer_id):
+                    return
         except (asyncio.IncompleteReadError, asyncio.TimeoutError, ConnectionError, ValueError, SC.HandshakeError) as exc:
             logger.debug("transport_conn_error", error=str(exc))
         except Exception:  # noqa: BLE001 — a handler bug must not kill the listener
             logger.exception("transport_handler_failed")
         finally:
+            self._inbound.discard(writer)
             writer.close()
             try:
                 await writer.wait_closed()
@@ -227,26 +253,65 @@ class Transport:
         if expect_peer is None and not isinstance(addr, tuple):
             expect_peer = parse_multiaddr(addr)[2] or None             # /p2p/<peer_id> in the multiaddr pins the identity
 
-        async def _secure():
+        async def _dial():
             reader, writer = await asyncio.open_connection(host, port)
             try:
                 session = await SC.client_handshake(reader, writer, self.key_pair, expect_peer=expect_peer)
-                self.keys.register(session.remote_peer_id, session.remote_public_key)
-                data = encode_message(msg_type, payload)
-                if self.throttle:
-                    await self.throttle.acquire_upload(len(data))
-                self.bytes_out += await session.send(writer, data)
-                self.encrypted_out += 1
-                if not expect_reply:
-                    return None
-                frame = await session.recv(reader)
-                self.bytes_in += len(frame)
-                if self.throttle:
-                    await self.throttle.acquire_download(len(frame))
-                kind, body, _sender = self._unwrap(frame, channel_sender=session.remote_peer_id)
-                return kind, body
-            finally:
+            except BaseException:
                 writer.close()
+                raise
+            self.keys.register(session.remote_peer_id, session.remote_public_key)
+            self.handshakes_out += 1
+            return _Link(reader, writer, session)
+
+        async def _exchange(link: "_Link"):
+            data = encode_message(msg_type, payload)
+            if self.throttle:
+                await self.throttle.acquire_upload(len(data))
+            self.bytes_out += await link.session.send(link.writer, data)
+            self.encrypted_out += 1
+            if not expect_reply:
+                return None
+            frame = await link.session.recv(link.reader)
+            self.bytes_in += len(frame)
+            if self.throttle:
+                await self.throttle.acquire_download(len(frame))
+            kind, body, _sender = self._unwrap(frame, channel_sender=link.session.remote_peer_id)
+            link.last_used = time.monotonic()
+            return kind, body
+
+        async def _secure():
+            if not expect_reply:                  # fire-and-forget: a private connection, so a late reply cannot desynchronise
+                link = await _dial()              # a session that other requests share
+                try:
+                    return await _exchange(link)
+                finally:
+                    link.close()
+            key = (host, port)
+            lock = self._link_locks.setdefault(key, asyncio.Lock())
+            async with lock:                      # one request in flight per session: records are strictly ordered
+                link = self._links.pop(key, None)
+                if link is not None and (link.stale() or (expect_peer and link.session.remote_peer_id != expect_peer)):
+                    link.close()
+                    link = None
+                reused = link is not None
+                for attempt in (0, 1):
+                    if link is None:
+                        link = await _dial()
+                    try:
+                        out = await _exchange(link)
+                    except (asyncio.IncompleteReadError, ConnectionError, SC.HandshakeError):
+                        link.close()
+                        link = None
+                        if reused and attempt == 0:          # the peer dropped an idle session: dial again, once
+                            reused = False
+                            continue
+                        raise
+                    except BaseException:                     # timeout / cancellation mid-exchange: the stream position is unknown
+                        link.close()
+                        raise
+                    self._links[key] = link
+                    return out
 
         async def _plain():
             reader, writer = await asyncio.open_connection(host, port)
@@ -282,6 +347,23 @@ class Transport:
             return await _plain()
 
         return await asyncio.wait_for(_go(), timeout=timeout)
+
+
+class _Link:
+    """An established outbound encrypted session, kept for the next request to the same peer."""
+
+    def __init__(self, reader: asyncio.StreamReader, writer: asyncio.StreamWriter, session: "SC.SecureSession"):
+        self.reader, self.writer, self.session = reader, writer, session
+        self.last_used = time.monotonic()
+
+    def stale(self) -> bool:
+        return self.writer.is_closing() or time.monotonic() - self.last_used > SESSION_IDLE_S * 0.8 or self.reader.at_eof()
+
+    def close(self) -> None:
+        try:
+            self.writer.close()
+        except Exception:  # noqa: BLE001
+            pass
 
 
 __all__ = ["Transport", "PeerInfo", "format_multiaddr", "parse_multiaddr", "read_frame", "safe_unpackb"]

@@ -152,3 +152,56 @@ def test_unsigned_write_frames_are_refused_on_plaintext_connections():
         await t.close()
 
     asyncio.run(go())
+
+
+def test_encrypted_sessions_are_reused_and_redialled_after_a_drop():
+    """One handshake serves many requests to the same peer; a session the listener dropped is re-established transparently;
+    fire-and-forget messages never share a pooled session."""
+    import asyncio
+
+    from infomesh_b200.p2p import transport as T
+    from infomesh_b200.p2p.keys import KeyPair
+    from infomesh_b200.p2p.protocol import MessageType
+
+    async def go():
+        a, b = T.Transport(KeyPair.generate()), T.Transport(KeyPair.generate())
+        seen = []
+
+        async def ping(payload, peer):
+            seen.append((payload.get("n"), peer.peer_id))
+            return MessageType.PONG, {"n": payload.get("n")}
+
+        b.register(MessageType.PING, ping)
+        port = await b.listen("127.0.0.1", 0)
+        addr = ("127.0.0.1", port)
+        try:
+            for n in range(5):
+                kind, body = await a.request(addr, MessageType.PING, {"n": n})
+                assert kind == MessageType.PONG and body["n"] == n
+            assert a.handshakes_out == 1 and a.encrypted_out == 5 and b.encrypted_in == 5
+            assert {pid for _, pid in seen} == {a.peer_id}
+            # the listener drops every inbound connection (restart / idle timeout): the next request dials again, once
+            for w in list(b._inbound):
+                w.close()
+            await asyncio.sleep(0.05)
+            kind, body = await a.request(addr, MessageType.PING, {"n": 99})
+            assert body["n"] == 99 and a.handshakes_out == 2
+            # concurrent requests to one peer are serialised on its session, not interleaved
+            outs = await asyncio.gather(*(a.request(addr, MessageType.PING, {"n": 100 + i}) for i in range(8)))
+            assert sorted(o[1]["n"] for o in outs) == list(range(100, 108)) and a.handshakes_out == 2
+            # fire-and-forget uses a private connection
+            assert await a.request(addr, MessageType.PING, {"n": -1}, expect_reply=False) is None
+            assert a.handshakes_out == 3
+            kind, body = await a.request(addr, MessageType.PING, {"n": 7})
+            assert body["n"] == 7 and a.handshakes_out == 3
+            # identity pinning also applies to a pooled session
+            import pytest as _pt
+
+            from infomesh_b200.p2p import message_auth as MA
+            with _pt.raises((MA.VerificationError, Exception)):
+                await a.request(addr, MessageType.PING, {"n": 1}, expect_peer="f" * 40)
+        finally:
+            await a.close()
+            await asyncio.wait_for(b.close(), timeout=5)          # open inbound sessions must not hold the listener's shutdown
+
+    asyncio.run(go())
