@@ -41,6 +41,8 @@ class HybridConfig:
     rerank: bool = True
     dense: bool = True        # False: BM25-only retrieval (serving with an encoder that has no checkpoint weights)
     dense_dtype: str = "bf16"  # "fp8": e4m3 shard + row scales, 32-wide over-fetch re-scored against the bf16 rows (K3)
+    shard_encoder: bool = True  # multi-GPU + p2p exchange: each rank encodes nq / world queries and the embeddings are all-gathered
+                                # through the symmetric heap (one push kernel) instead of every rank encoding the whole batch
     retrieval_sms: int = 0     # pipelined serving: SMs left to the HBM-bound scan while the cross-encoder GEMMs of the previous
                                # batch run on the others (0 = no partition: the two streams time-share the whole GPU)
     rank_signals: bool = False  # BM25-only mode: order candidates with the six-signal rank fuse (K12) instead of raw BM25
@@ -99,6 +101,7 @@ class HybridEngine:
                 shard.vectors_f8, shard.vec_scale = N.quantize_rows_e4m3(shard.vectors)
             self.q8 = torch.zeros((cfg.nq, shard.vectors.shape[1]), device=dev, dtype=torch.uint8)
             self.q8_scale = torch.ones((cfg.nq,), device=dev, dtype=torch.float32)
+        self.ch_qemb = None
         self._graph = None
         self._graph_failed = False
         self.heap = None
@@ -116,6 +119,10 @@ class HybridEngine:
             n_log = self.nq_local * cfg.n_rerank
             self._log_pad = (n_log + 3) // 4 * 4           # 16-byte blocks
             self.ch_logits = symm.AllGatherChannel(self.heap, (self._log_pad,), torch.float32)
+            dim = shard.vectors.shape[1]
+            if cfg.shard_encoder and (self.nq_local * dim * 2) % 16 == 0:
+                self.ch_qemb = symm.AllGatherChannel(self.heap, (self.nq_local, dim), torch.bfloat16)
+                self._q_scratch = torch.empty((cfg.nq, dim), device=dev, dtype=torch.bfloat16)
             self._log_stage = torch.zeros((self._log_pad,), device=dev, dtype=torch.float32)
             self.heap.barrier()
 
@@ -123,6 +130,17 @@ class HybridEngine:
     def _encode(self):
         if self.cfg.backend == "torch":
             return self.encoder.embed_torch(self.in_enc_ids, self.in_enc_len)
+        if self.ch_qemb is not None:
+            # de-replicated query encoder: this rank's slice of the batch, then a push all-gather of the [nq/world, dim]
+            # embeddings (a few KB per rank) -- every rank ends up with the same [nq, dim] matrix the replicated form computes
+            lo = self.ctx.rank * self.nq_local
+            mine = self.encoder.embed(self.in_enc_ids[lo:lo + self.nq_local], self.in_enc_len[lo:lo + self.nq_local])
+            q_emb = self.ch_qemb(mine.contiguous()).view(self.cfg.nq, -1)
+            if self._f8:     # e4m3 copy + scales of the gathered matrix (the pooling kernel, sequence length 1)
+                from infomesh_b200.ops import nn as N
+
+                N.pool_norm(q_emb.view(self.cfg.nq, 1, -1), None, "cls", False, out=self._q_scratch, out_q8=self.q8, out_qscale=self.q8_scale)
+            return q_emb
         if self._f8:
             return self.encoder.embed(self.in_enc_ids, self.in_enc_len, out_q8=self.q8, out_qscale=self.q8_scale)
         return self.encoder.embed(self.in_enc_ids, self.in_enc_len)
