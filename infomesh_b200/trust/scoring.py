@@ -82,9 +82,10 @@ def _compute_trust(row: tuple[Any, ...]) -> PeerTrust:
     pid, up, contrib, a_tot, a_ok, s_sum, s_cnt, fails, iso, last = row
     s_avg = s_sum / s_cnt if s_cnt > 0 else 0.0
     score = compute_trust_score(up, contrib, a_tot, a_ok, s_avg, has_summary_data=s_cnt > 0)
-    return PeerTrust(pid, round(min(1.0, up / MAX_UPTIME_HOURS), 4), round(min(1.0, contrib / MAX_CONTRIBUTION_SCORE), 4),
-                     round(a_ok / a_tot if a_tot else 0.5, 4), round(s_avg if s_cnt else 0.5, 4), round(score, 4),
-                     trust_tier(score), int(fails), bool(iso), last)
+    # the record reports the raw component values (unrounded; a component without data reads 0.0 for summaries and the
+    # neutral 0.5 for audits, as in the reference) -- the neutral defaults live in compute_trust_score
+    return PeerTrust(pid, min(1.0, up / MAX_UPTIME_HOURS), min(1.0, contrib / MAX_CONTRIBUTION_SCORE),
+                     a_ok / a_tot if a_tot else 0.5, s_avg if s_cnt else 0.0, score, trust_tier(score), int(fails), bool(iso), last)
 
 
 class TrustStore(SQLiteStore):

@@ -558,3 +558,138 @@ SCENARIOS = {f.__name__: f for f in (
     scheduler_bookkeeping, freshness_queue, feed_monitor, crawl_intelligence, url_assignment, pdf_and_structured, plugin_registry, version_tracking,
     dx_helpers, runtime_files, shutdown_sequence, persistence_store, scalability_helpers, security_operations, peer_profiles, load_guard, merkle_tree,
     threat_detector, ranking_and_remote, timezone_table)}
+
+
+# ----------------------------------------------------------------------------- second batch: stores and accounting
+def query_cache(pkg, tmp):
+    C = _m(pkg, "search.cache")
+    c = C.QueryCache(max_size=3, ttl_seconds=1000.0)
+    trace = [c.get("a", 10)]
+    c.put("a", 10, [1, 2])
+    c.put("A ", 10, [9])                 # normalisation: same key or not -- both sides must agree
+    c.put("b", 10, [3])
+    c.put("b", 5, [4])
+    trace += [c.get("a", 10), c.get("a", 5), c.get("b", 10), c.get("b", 5), c.size]
+    c.put("c", 10, [5])
+    c.put("d", 10, [6])                  # evicts the least recently used
+    trace += [c.get("a", 10), c.get("b", 10), c.get("c", 10), c.get("d", 10), c.size, c.invalidate("c", 10), c.invalidate("zzz", 1), c.size]
+    st = c.stats
+    out = {"trace": trace, "stats": (st.hits, st.misses, st.evictions, st.total, round(st.hit_rate, 6))}
+    old = C.QueryCache(max_size=5, ttl_seconds=-1.0)
+    old.put("x", 1, [1])
+    out["expired"] = (old.get("x", 1), old.evict_expired(), old.size)
+    c.clear()
+    out["cleared"] = c.size
+    return out
+
+
+def credit_ledger(pkg, tmp):
+    L = _m(pkg, "credits.ledger")
+    T = _m(pkg, "credits.types")
+    led = L.CreditLedger(tmp / "credits.db", owner_email="dev@example.org")
+    A = T.ActionType
+    earned = [led.record_action(A.CRAWL, 10, note="ten pages"), led.record_action(A.QUERY_PROCESS, 4), led.record_action(A.LLM_SUMMARIZE_OWN, 2, off_peak=True),
+              led.record_action(A.DOC_HOSTING, 50), led.record_action(A.NETWORK_UPTIME, 3.5), led.record_action(A.LLM_SUMMARIZE_PEER, 100)]
+    spends = [led.spend(1.0), led.spend(0.25, reason="search"), led.spend(10_000.0)]
+    st = led.stats()
+    al = led.search_allowance()
+    out = {"earned": earned, "spends": spends, "totals": (round(led.total_earned(), 6), round(led.total_spent(), 6), round(led.balance(), 6), round(led.debt_amount(), 6)),
+           "score": round(led.contribution_score(), 6), "tier": led.tier().value, "cost": led.search_cost(), "state": led.credit_state().value,
+           "allowance": (al.state.value, al.search_cost, al.debt_amount), "stats": (round(st.total_earned, 6), round(st.total_spent, 6), round(st.balance, 6)),
+           "by_action": sorted((a, round(v, 6)) for a, v in led.earnings_by_action()),
+           "entries": [(e.action, e.quantity, e.weight, e.multiplier, round(e.credits, 6), e.note) for e in led.recent_entries(limit=3)],
+           "owner": led.owner_email, "off_peak": [L.is_off_peak(hour=h) for h in (0, 6, 7, 12, 22, 23)]}
+    led.close()
+    poor = L.CreditLedger(tmp / "poor.db")
+    out["poor"] = (poor.balance(), poor.spend(0.5), poor.credit_state().value, poor.search_allowance().state.value, poor.tier().value, poor.search_cost())
+    poor.close()
+    return out
+
+
+def trust_store(pkg, tmp):
+    S = _m(pkg, "trust.scoring")
+    ts = S.TrustStore(tmp / "trust.db")
+    ts.update_uptime("good", 200.0)
+    ts.update_contribution("good", 500.0)
+    for ok in (True, True, True, False, True):
+        ts.record_audit("good", passed=ok)
+    ts.record_summary_rating("good", 0.9)
+    for _ in range(4):
+        ts.record_audit("bad", passed=False)
+    ts.update_uptime("idle", 1.0)
+    ts.isolate_peer("bad")
+    def view(pid):
+        t = ts.get_trust(pid)
+        return None if t is None else (round(t.uptime_score, 6), round(t.contribution_score, 6), round(t.audit_pass_rate, 6), round(t.summary_quality, 6),
+                                       round(t.trust_score, 6), t.tier.value, t.consecutive_audit_failures, t.isolated)
+    out = {"good": view("good"), "bad": view("bad"), "idle": view("idle"), "none": view("ghost"), "score_ghost": ts.get_trust_score("ghost"),
+           "listed": sorted(t.peer_id for t in ts.list_peers()), "listed_all": sorted(t.peer_id for t in ts.list_peers(include_isolated=True)),
+           "isolated": [t.peer_id for t in ts.list_isolated()], "is_iso": (ts.is_isolated("bad"), ts.is_isolated("good"))}
+    ts.unisolate("bad")
+    out["after_unisolate"] = (ts.is_isolated("bad"), view("bad"))
+    out["formula"] = [round(S.compute_trust_score(*a), 6) for a in ((0, 0, 0, 0, 0.0), (100, 50, 10, 9, 0.8), (10_000, 10_000, 100, 100, 1.0), (24, 3, 4, 1, 0.2), (720, 1000, 0, 0, 0.5))]
+    out["tiers"] = [S.trust_tier(x).value for x in (0.0, 0.29, 0.3, 0.59, 0.6, 0.79, 0.8, 1.0)]
+    return out
+
+
+def dedup_store(pkg, tmp):
+    D = _m(pkg, "crawler.dedup")
+    H = _m(pkg, "hashing")
+    db = D.DeduplicatorDB(str(tmp / "dedup.db"))
+    text = "Tensor memory holds the accumulators of the fifth generation tensor cores. " * 6
+    near = text.replace("fifth", "5th", 1)
+    other = "Completely unrelated cooking instructions about pasta and tomato sauce for dinner tonight. " * 6
+    trace = [db.is_url_seen("https://Example.org/a?utm_source=x"), db.is_content_seen(H.content_hash(text)), db.is_near_duplicate(text)]
+    db.mark_seen("https://example.org/a", H.content_hash(text), text)
+    trace += [db.is_url_seen("https://Example.org/a?utm_source=x"), db.is_url_seen("https://example.org/a/"), db.is_url_seen("https://example.org/b"),
+              db.is_content_seen(H.content_hash(text)), db.is_content_seen(H.content_hash(near)), db.is_near_duplicate(near), db.is_near_duplicate(other),
+              db.is_near_duplicate(near, threshold=0)]
+    db.mark_seen("https://example.org/b", H.content_hash(other), other, commit=False)
+    db.flush()
+    db.close()
+    again = D.DeduplicatorDB(str(tmp / "dedup.db"))
+    trace += [again.is_url_seen("https://example.org/b"), again.is_near_duplicate(near), again.is_content_seen("nope")]
+    again.close()
+    return {"trace": trace}
+
+
+def peer_store(pkg, tmp):
+    P = _m(pkg, "p2p.peer_store")
+    ps = P.PeerStore(tmp)
+    ps.upsert("p1", "/ip4/10.0.0.1/tcp/4001")
+    ps.upsert("p2", "/ip4/10.0.0.2/tcp/4001")
+    ps.upsert("p1", "/ip4/10.0.0.9/tcp/4001")
+    ps.record_failure("p2")
+    ps.record_failure("p2")
+    ps.record_failure("ghost")
+    ps.save_connected([("p3", "/ip4/10.0.0.3/tcp/4001"), ("p1", "/ip4/10.0.0.9/tcp/4001")])
+    rows = {c.peer_id: (c.multiaddr, c.success_count, c.fail_count, round(c.success_rate, 6)) for c in ps.load_recent(limit=10)}
+    out = {"rows": rows, "count": ps.count(), "limit1": len(ps.load_recent(limit=1))}
+    ps.remove("p3")
+    out["after_remove"] = (ps.count(), sorted(c.peer_id for c in ps.load_recent()))
+    out["prune_none"] = ps.prune(max_age_hours=1000, max_peers=10)
+    out["prune_cap"] = (ps.prune(max_age_hours=1000, max_peers=1), ps.count())
+    out["prune_age"] = (ps.prune(max_age_hours=-1.0), ps.count())
+    return out
+
+
+def feedback_store(pkg, tmp):
+    F = _m(pkg, "search.feedback")
+    fs = F.FeedbackStore(str(tmp / "fb.db"))
+    fs.record_fetch("gpu tensor cores", "https://a.example/1", 1)
+    fs.record_fetch("gpu tensor cores", "https://a.example/1", 3)
+    fs.record_fetch("other", "https://a.example/2", 9)
+    fs.record_skip("gpu tensor cores", ["https://a.example/2", "https://a.example/3"])
+    fs.record_citation("gpu tensor cores", "https://a.example/1")
+    fs.record_reformulation("gpu tensor cores")
+    def boost(u):
+        b = fs.get_url_stats(u)
+        return None if b is None else (round(b.boost_score, 6), b.fetch_count, b.skip_count, b.cite_count)
+    out = {"boosts": {u: (round(fs.get_boost(u), 6), boost(u)) for u in ("https://a.example/1", "https://a.example/2", "https://a.example/3", "https://nobody.example/")},
+           "signals": fs.signal_count(), "top": [(b.url, round(b.boost_score, 6)) for b in fs.top_boosted_urls(limit=2)],
+           "reform": (fs.is_reformulation("gpu tensor cores"), fs.is_reformulation("never asked"), fs.is_reformulation("gpu tensor cores", window=-1.0))}
+    fs.close()
+    return out
+
+
+SCENARIOS.update({f.__name__: f for f in (query_cache, credit_ledger, trust_store, dedup_store, peer_store, feedback_store)})
