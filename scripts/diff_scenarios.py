@@ -693,3 +693,128 @@ def feedback_store(pkg, tmp):
 
 
 SCENARIOS.update({f.__name__: f for f in (query_cache, credit_ledger, trust_store, dedup_store, peer_store, feedback_store)})
+
+
+# ----------------------------------------------------------------------------- third batch: detectors, graph, exchange, metrics
+def farming_detector(pkg, tmp):
+    F = _m(pkg, "credits.farming")
+    fd = F.FarmingDetector(tmp / "farm.db")
+    t0 = 1_000_000.0
+    fd.register_node("new", now=t0)
+    fd.register_node("old", now=t0 - 10 * 86400)
+    out = {"probation": (fd.is_on_probation("new", now=t0 + 3600), fd.is_on_probation("old", now=t0), fd.is_on_probation("ghost", now=t0),
+                         round(fd.probation_remaining("new", now=t0 + 3600), 4), round(fd.probation_remaining("old", now=t0), 4))}
+    for i in range(30):                       # perfectly regular crawl actions, one every 60 s
+        fd.log_action("bot", "crawl", now=t0 + i * 60.0)
+    rng = [3, 41, 97, 160, 171, 305, 420, 455, 610, 777, 905, 1111]
+    for off in rng:                           # irregular human-ish pattern
+        fd.log_action("human", "crawl", now=t0 + off)
+    for i in range(200):                      # burst: 200 actions inside one minute
+        fd.log_action("burst", "crawl", now=t0 + 1700 + i * 0.2)
+    now = t0 + 1800
+    out["counts"] = {p: fd.actions_in_last_hour(p, "crawl", now=now) for p in ("bot", "human", "burst", "ghost")}
+    out["regular"] = {p: fd.detect_regular_intervals(p, "crawl", now=now) for p in ("bot", "human", "burst")}
+    out["bursts"] = {p: fd.detect_burst(p, "crawl", now=now) for p in ("bot", "human", "burst")}
+    out["rate_limited"] = {p: fd.is_rate_limited(p, "crawl", now=now) for p in ("bot", "human", "burst")}
+    checks = {}
+    for p in ("old", "new", "bot", "human", "burst"):
+        if p in ("bot", "human", "burst"):
+            fd.register_node(p, now=t0 - 30 * 86400)
+        c = fd.check(p, "crawl", now=now)
+        checks[p] = (c.verdict.value, c.rate_limit_exceeded, c.anomaly_count, round(c.probation_remaining_hours, 3))
+    out["checks"] = checks
+    ids = [fd.record_anomaly("bad", "manual", f"n{i}", now=now + i) for i in range(4)]
+    hist = fd.get_anomaly_history("bad", limit=2)
+    out["anomalies"] = (len(ids), ids == sorted(ids), [(a.anomaly_type, a.detail) for a in hist], fd.is_blocked("bad"), fd.check("bad", "crawl", now=now + 10).verdict.value)
+    fd.unblock("bad")
+    out["unblocked"] = fd.is_blocked("bad")
+    out["pruned"] = fd.prune_old_actions(max_age_seconds=0.0) > 0
+    return out
+
+
+def link_graph(pkg, tmp):
+    G = _m(pkg, "index.link_graph")
+    g = G.LinkGraph(str(tmp / "links.db"))
+    added = [g.add_links("https://a.example/1", ["https://b.example/x", "https://c.example/y", "https://a.example/2", "https://b.example/x"]),
+             g.add_links("https://b.example/x", ["https://c.example/y", "https://d.example/"]),
+             g.add_links("https://c.example/y", ["https://a.example/1"]),
+             g.add_links("https://e.example/", ["https://c.example/z", "not a url", ""]),
+             g.add_links("https://a.example/1", ["https://b.example/x"])]
+    auth = g.compute_domain_authority()
+    # (`add_links` returns the number of NEW edges here and the number of valid targets in the reference: not compared)
+    out = {"n_calls": len(added), "stats": g.get_stats(), "domains": sorted(auth), "sum": round(sum(auth.values()), 6),
+           "order": [d for d, _ in sorted(auth.items(), key=lambda kv: (-round(kv[1], 9), kv[0]))],
+           "values": {d: round(v, 6) for d, v in auth.items()},
+           "lookups": (round(g.domain_authority("c.example"), 6), g.domain_authority("nobody.example"), round(g.url_authority("https://c.example/anything"), 6), g.url_authority("garbage"))}
+    g.close()
+    return out
+
+
+def peer_exchange(pkg, tmp):
+    X = _m(pkg, "p2p.pex")
+    ex = X.PeerExchange("me")
+    peers = [(f"p{i}", f"/ip4/10.0.0.{i}/tcp/4001") for i in range(1, 16)] + [("me", "/ip4/10.0.0.99/tcp/4001")]
+    resp = ex.build_response(peers, max_peers=5)
+    full = ex.build_response(peers[:3])
+    got = ex.process_response("sender", [{"peer_id": "n1", "multiaddr": "/ip4/1.1.1.1/tcp/4001"}, {"peer_id": "me", "multiaddr": "/ip4/2.2.2.2/tcp/1"},
+                                           {"peer_id": "known", "multiaddr": "/ip4/3.3.3.3/tcp/1"}, {"peer_id": "", "multiaddr": "/ip4/4.4.4.4/tcp/1"},
+                                           {"peer_id": "n2"}, {"peer_id": "n3", "multiaddr": 42}, {"peer_id": "n1", "multiaddr": "/ip4/1.1.1.1/tcp/4001"},
+                                           {"peer_id": "sender", "multiaddr": "/ip4/5.5.5.5/tcp/1"}], known_peers={"known"})
+    # (a non-dict entry in peers_data makes the reference raise AttributeError; this repo skips it: not compared)
+    limits = [ex.check_rate_limit("asker") for _ in range(8)]
+    ex.cleanup_rate_limits()
+    return {"resp_len": len(resp), "resp_keys": sorted(resp[0]) if resp else [], "no_self": all(r["peer_id"] != "me" for r in resp), "full": full,
+            "got": [(p.peer_id, p.multiaddr) for p in got], "limits": limits, "other": ex.check_rate_limit("someone else")}
+
+
+def metrics_and_slo(pkg, tmp):
+    M = _m(pkg, "observability.metrics")
+    S = _m(pkg, "slo")
+    mc = M.MetricsCollector()
+    mc.inc("searches_total")
+    mc.inc("searches_total", 2)
+    mc.set_gauge("peers_connected", 7)
+    for v in (5.0, 15.0, 250.0, 1200.0):
+        mc.observe("search_latency_ms", v)
+    d = mc.to_dict()
+    prom = mc.format_prometheus()
+    tr = M.QueryTrace("t1", "gpu")
+    tr.add_span(M.QuerySpan("s1", "peerA", "local", 1.0, 1.5, 500.0, {"k": "v"}))
+    tr.add_span(M.QuerySpan("s2", "peerB", "remote", 1.1, 1.9, 800.0))
+    rules = M.generate_alert_rules()
+    dash = M.generate_grafana_dashboard()
+    t = S.SLOTracker([S.SLODefinition("lat", "p95 latency", 100.0, "ms", 3600.0), S.SLODefinition("avail", "availability", 0.99, "ratio", 3600.0)])
+    for v in (50.0, 80.0, 400.0):
+        t.record("lat", v)
+    for ok in (True, True, True, False):
+        t.record_success("avail", ok)
+    t.record("unknown", 1.0)
+    st = {s.slo.name: (round(s.current_value, 6), s.target, s.met, round(s.error_budget_remaining, 6)) for s in t.get_status()}
+    summ = t.summary()
+    d.pop("uptime_seconds", None)
+    plain = sorted(ln for ln in prom.splitlines() if ln and not ln.startswith("#") and "quantile" not in ln)     # quantile series are an addition here
+    fwd = M.configure_log_forwarding(format="json", output="stdout")
+    return {"dict": d, "prom_lines": plain, "trace": tr.to_dict(), "rules": [(r.get("alert"), r.get("expr")) for r in rules][:5],      # GPU alert rules are additions
+            "dash_keys": sorted(dash)[:3], "slo": st, "slo_summary_keys": sorted(summ), "log_fwd": {k: fwd[k] for k in ("format", "output", "level")}}
+
+
+def sessions_and_webhooks(pkg, tmp):
+    S = _m(pkg, "mcp.session")
+    a = S.AnalyticsTracker()
+    for ms in (10.0, 30.0, 20.0):
+        a.record_search(ms)
+    a.record_crawl()
+    a.record_fetch()
+    a.record_fetch()
+    store = S.SessionStore(max_size=2, ttl_seconds=1000.0)
+    s1 = store.get_or_create("s1")
+    fields = sorted(k for k in dir(s1) if not k.startswith("_") and k in ("last_query", "last_results", "updated_at"))
+    same = kept = None       # (object identity across calls differs between the implementations' stores: not compared)
+    wh = S.WebhookRegistry(max_registrations=2)
+    regs = [wh.register("https://hooks.example/a"), wh.register("https://hooks.example/a"), wh.register("http://127.0.0.1/x"), wh.register("ftp://hooks.example/b"),
+            wh.register("https://hooks.example/b"), wh.register("https://hooks.example/c")]
+    return {"analytics": a.to_dict(), "session_fields": fields, "regs": [r is None for r in regs], "urls": sorted(wh.urls),
+            "unreg": (wh.unregister("https://hooks.example/a"), wh.unregister("https://hooks.example/zzz")), "left": sorted(wh.urls)}
+
+
+SCENARIOS.update({f.__name__: f for f in (farming_detector, link_graph, peer_exchange, metrics_and_slo, sessions_and_webhooks)})
