@@ -420,31 +420,34 @@ attn_fwd_1chunk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
   mbar_wait(s_bar, 0);
   tc_fence_after();
 
-  // ---------------- softmax: this thread owns row `row`, key columns [64*half, 64*half + 64) ----------------
-  const int col0 = static_cast<int>(half) * 64;
-  const int n_vis = max(0, min(64, vis_end - col0));  // visible columns of this half: [0, n_vis)
+  // ---------------- softmax: this thread owns row `row` and two 32-key chunks: [32*half, +32) and [64 + 32*half, +32) ------
+  // The two warps of a quadrant used to split the keys as [0,64) / [64,128).  Packed sequences are ~70 keys long, so the
+  // second warp had almost nothing to do while the first evaluated 64 exponentials per thread; interleaving the 32-key
+  // chunks balances them (38 vs 32 live keys at length 70) and shortens the softmax critical path accordingly.
+  //
   // Short (packed) sequences leave most of the 128 x 128 score tile masked; ncu showed this kernel issue-bound (69 % issue
   // slots, MUFU.EX2 + F2FP on the XU pipe at its limit), so masked work is skipped, not computed-and-discarded:
   //   * a warp whose 32 query rows all lie beyond q_len does no softmax at all (its P rows only feed O rows nobody stores);
-  //   * 32-column chunks beyond the visible keys are not read from TMEM, and 8-column groups beyond them get P = 0 without
-  //     evaluating exp2.  Both conditions are warp-uniform (tcgen05.ld is .sync.aligned): causal masks vary per row, so
-  //     the chunk-level skip is disabled for them (n_ld = 64) while the per-group skip still applies per thread.
+  //   * 32-key chunks beyond the visible keys are not read from TMEM, and 8-key groups beyond them get P = 0 without
+  //     evaluating exp2.  The chunk-level skip must be warp-uniform (tcgen05.ld is .sync.aligned): causal masks vary per row,
+  //     so it is disabled for them while the per-group skip still applies per thread.
   const bool warp_live = static_cast<int>(quad * 32u) < q_len;
-  const int n_ld = p.causal ? 64 : n_vis;
   float m_raw = kNegBig;
   if (warp_live) {
 #pragma unroll
-    for (int cc = 0; cc < 64; cc += 32) {
-      if (cc >= n_ld) break;
+    for (int c = 0; c < 2; ++c) {
+      const int k0 = 64 * c + 32 * static_cast<int>(half);       // first key of this chunk
+      const int n_vis = max(0, min(32, vis_end - k0));            // visible keys in it
+      if (!p.causal && n_vis == 0) continue;
       uint32_t v[32];
-      tmem_ld_32x32b_x32(tmem_base + lane_base + col0 + cc, v);
+      tmem_ld_32x32b_x32(tmem_base + lane_base + k0, v);
       tmem_ld_wait();
-      if (cc + 32 <= n_vis) {
+      if (n_vis == 32) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) m_raw = fmaxf(m_raw, __uint_as_float(v[i]));
       } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) m_raw = fmaxf(m_raw, (cc + i < n_vis) ? __uint_as_float(v[i]) : kNegBig);
+        for (int i = 0; i < 32; ++i) m_raw = fmaxf(m_raw, (i < n_vis) ? __uint_as_float(v[i]) : kNegBig);
       }
     }
   }
@@ -453,31 +456,34 @@ attn_fwd_1chunk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_
   m_raw = fmaxf(m_raw, s_m[(half ^ 1u) * kAttnBQ + row]);
   const float m_s = m_raw * p.scale_log2;  // scale > 0: max of scaled == scaled max
   float l_half = 0.f;
-  uint8_t* prow = sP + half * (kAttnBQ * 128) + row * 128;
   if (warp_live) {
 #pragma unroll
-    for (int cc = 0; cc < 64; cc += 32) {
+    for (int c = 0; c < 2; ++c) {
+      const int k0 = 64 * c + 32 * static_cast<int>(half);
+      const int n_vis = max(0, min(32, vis_end - k0));
+      const bool any = p.causal || n_vis > 0;
       uint32_t v[32];
-      const bool any = cc < n_ld;
       if (any) {
-        tmem_ld_32x32b_x32(tmem_base + lane_base + col0 + cc, v);
+        tmem_ld_32x32b_x32(tmem_base + lane_base + k0, v);
         tmem_ld_wait();
       }
+      // P k-block c holds keys [64c, 64c + 64) as 8 16-byte chunks per row; this thread's 32 keys are chunks 4*half .. +3
+      uint8_t* prow = sP + c * (kAttnBQ * 128) + row * 128;
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) {
-        const int g0 = cc + 8 * q4;                    // first key column of this 8-wide group
-        uint4 pk = make_uint4(0u, 0u, 0u, 0u);         // masked keys: P = 0 (V rows behind the sequence are zeroed below)
+        const int g0 = 8 * q4;                          // first key of this 8-wide group inside the chunk
+        uint4 pk = make_uint4(0u, 0u, 0u, 0u);          // masked keys: P = 0 (V rows behind the sequence are zeroed below)
         if (any && g0 < n_vis) {
           float e[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            e[i] = exp2f(fmaf(__uint_as_float(v[8 * q4 + i]), p.scale_log2, -m_s));
+            e[i] = exp2f(fmaf(__uint_as_float(v[g0 + i]), p.scale_log2, -m_s));
             if (g0 + 8 > n_vis) e[i] = (g0 + i < n_vis) ? e[i] : 0.f;
             l_half += e[i];
           }
           pk = make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
         }
-        const int ch = ((cc >> 3) + q4) ^ (row & 7);
+        const int ch = (4 * static_cast<int>(half) + q4) ^ (row & 7);
         *reinterpret_cast<uint4*>(prow + (ch << 4)) = pk;
       }
     }
