@@ -72,6 +72,26 @@ class SearchResult:
     crawled_at: float
 
 
+def _serialised(cls):
+    """One SQLite connection is shared by every thread that touches the store (crawler, MCP handlers, GPU index workers);
+    the ``sqlite3`` module leaves serialising statement + fetch on a shared connection to the caller.  Every public method
+    therefore runs under the store's re-entrant lock (generators lock per batch themselves)."""
+    import functools
+    import inspect
+
+    for name, fn in list(vars(cls).items()):
+        if name.startswith("_") or not inspect.isfunction(fn) or inspect.isgeneratorfunction(fn) or inspect.iscoroutinefunction(fn):
+            continue
+
+        def locked(self, *a, __fn=fn, **kw):
+            with self._lock:
+                return __fn(self, *a, **kw)
+
+        setattr(cls, name, functools.wraps(fn)(locked))
+    return cls
+
+
+@_serialised
 class LocalStore:
     def __init__(self, db_path: Path | str | None = None, tokenizer: str = "unicode61", *,
                  compression_enabled: bool = False, compression_level: int = 3):
@@ -287,8 +307,9 @@ class LocalStore:
         """Stream every document with ``doc_id > after`` in doc_id order (GPU shard build / incremental append, snapshots)."""
         last = int(after)
         while True:
-            rows = self._conn.execute("SELECT * FROM documents WHERE doc_id > ? ORDER BY doc_id LIMIT ?",
-                                      (last, batch)).fetchall()
+            with self._lock:
+                rows = self._conn.execute("SELECT * FROM documents WHERE doc_id > ? ORDER BY doc_id LIMIT ?",
+                                          (last, batch)).fetchall()
             if not rows:
                 return
             for r in rows:

@@ -158,3 +158,41 @@ def test_commoncrawl_wet_import_and_starter_helpers(tmp_path):
     assert info.release_tag == "v1" and info.size_mb == 2.0 and ST.pick_asset([]) is None
     ST._write_cache(tmp_path, info)
     assert ST._read_cache(tmp_path).download_url == "https://x/s" and ST.needs_starter(3) and not ST.needs_starter(10)
+
+
+def test_local_store_survives_concurrent_readers_and_a_writer(tmp_path):
+    """One connection, many threads (MCP handlers + GPU index workers + crawler): reads and writes must serialise instead of
+    tripping sqlite3's 'bad parameter or other API misuse' on a shared connection."""
+    import threading
+
+    from infomesh_b200.index.local_store import LocalStore
+
+    st = LocalStore(tmp_path / "c.db")
+    for i in range(50):
+        st.add_document(url=f"https://e.example/{i}", title=f"T{i}", text=f"alpha beta gamma document {i} " * 5, raw_html_hash=f"r{i}", text_hash=f"t{i}")
+    errors, stop = [], threading.Event()
+
+    def reader():
+        try:
+            while not stop.is_set():
+                for i in range(1, 40, 3):
+                    d = st.get_document(i)
+                    assert d is not None and d.url.endswith(str(i - 1))
+                assert st.search("alpha beta", limit=5)
+                assert st.get_stats()["document_count"] >= 50
+                for _ in zip(range(5), st.iter_documents(batch=7)):
+                    pass
+        except Exception as exc:  # noqa: BLE001
+            errors.append(exc)
+
+    threads = [threading.Thread(target=reader) for _ in range(4)]
+    for t in threads:
+        t.start()
+    for i in range(50, 120):
+        st.add_document(url=f"https://e.example/{i}", title=f"T{i}", text=f"alpha beta delta document {i} " * 5, raw_html_hash=f"r{i}", text_hash=f"t{i}")
+    stop.set()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:2]
+    assert st.get_stats()["document_count"] == 120
+    st.close()
