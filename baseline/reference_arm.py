@@ -201,7 +201,9 @@ def run(args, ClockSampler=None) -> int:
     line = {
         "impl": "reference",
         "metric": "queries/sec, hybrid BM25+dense top-10 over a synthetic index (reference search_hybrid, no reranker)",
-        "value": round(qps, 2), "unit": "queries/s", "n_gpus": 1, "steps": K, "warmup": W,
+        "value": round(qps, 2), "unit": "queries/s", "n_gpus": int(getattr(args, "gpus", 1) or 1), "gpus_used": 1, "steps": K, "warmup": W,
+        "gpus_note": "the reference has no multi-GPU path: launched with N ranks, rank 0 runs its stock single-process search and the "
+                     "other ranks idle, so `value` is the same at every N",
         "ms_per_step": round(total_s * 1e3 / K, 3), "p50_step_ms": round(statistics.median(per), 3),
         "p50_query_ms": round(statistics.median(per) / B, 4),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
