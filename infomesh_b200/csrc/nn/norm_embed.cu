@@ -239,8 +239,8 @@ struct SumLnComm {
 // (Measured alternative, round 2: a "streaming" variant that keeps gamma / beta in registers and walks 4 rows per warp -- 9
 //  instead of 21 memory instructions per row, but 101 registers -> 2 CTAs per SM -- ran at 91 us against 77 us for this kernel on
 //  [90112, 768] with the MX output: fewer warps in flight cost more than the saved L1 wavefronts.  Not kept.)
-template <int VEC>
-__global__ void __launch_bounds__(kRowsPerBlock * 32)
+template <int VEC, int MINB = 1>
+__global__ void __launch_bounds__(kRowsPerBlock * 32, MINB)
 sum_ln_kernel(const __nv_bfloat16* in, size_t in_stride_p, int P,  // in / residual: NOT __restrict__ -- in TP mode peers
               const __nv_bfloat16* residual,                       // write them while the kernel waits (no ld.global.nc)
               const float* __restrict__ gamma,
@@ -754,6 +754,20 @@ static int sum_ln_impl(const void* in, long long in_stride_p, int P, const void*
   cm.mx.ld = mx_ld;
   auto s = reinterpret_cast<cudaStream_t>(stream);
   const int grid = (n_rows + kRowsPerBlock - 1) / kRowsPerBlock;
+  // Plain streaming use (one input, no collectives): the kernel is bound by bytes in flight, so it is compiled for 5 CTAs
+  // per SM (48 registers, a few spilled values) instead of 4 -- INFOMESH_B200_LN_OCC=4 selects the unconstrained build (A/B).
+  static const bool dense_occ = []() {
+    const char* e = getenv("INFOMESH_B200_LN_OCC");
+    return e == nullptr || e[0] != '4';
+  }();
+  if (dense_occ && P == 1 && arrive_flags == nullptr && peer_out == nullptr && peer_out_flags == nullptr) {
+    IM_DISPATCH_VEC(H, IM_CUDA_OK(launch_pdl(sum_ln_kernel<VEC, 5>, dim3(grid), dim3(kRowsPerBlock * 32), 0, s,
+                                             (const __nv_bfloat16*)in, (size_t)in_stride_p, P,
+                                             (const __nv_bfloat16*)residual, gamma, beta, eps, rms_only, n_rows,
+                                             (__nv_bfloat16*)out, (__nv_bfloat16*)sum_out, cm)));
+    IM_LAUNCH_OK("sum_ln_kernel");
+    return 0;
+  }
   IM_DISPATCH_VEC(H, IM_CUDA_OK(launch_pdl(sum_ln_kernel<VEC>, dim3(grid), dim3(kRowsPerBlock * 32), 0, s,
                                            (const __nv_bfloat16*)in, (size_t)in_stride_p, P,
                                            (const __nv_bfloat16*)residual, gamma, beta, eps, rms_only, n_rows,
