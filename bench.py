@@ -499,7 +499,8 @@ def main() -> int:
                                   (", passages replicated" if world > 1 else ", passages"))
                                + f") + data-parallel reranker x{world}",
                 "l2_policy": "inputs larger than L2: every step streams this rank's dense shard "
-                             f"({shard.vectors.numel() * shard.vectors.element_size() / 1e9:.2f} GB/rank) plus the query terms' "
+                             f"({(shard.vectors_f8.numel() + shard.vec_scale.numel() * 4 if hcfg.dense_dtype == 'fp8' else shard.vectors.numel() * shard.vectors.element_size()) / 1e9:.2f} GB/rank"
+                             f"{', e4m3 rows + scales' if hcfg.dense_dtype == 'fp8' else ''}) plus the query terms' "
                              "postings, and uses a distinct query batch",
                 "padding": pad_note,
                 "cuda_graph": bool(eng._graph is not None or getattr(eng, "_ga", None) is not None),
