@@ -173,7 +173,7 @@ def sim_topk(q, docs, k=10, alive=None, id_offset=0, push=None):
     return topk_merge(ps, pi, k, id_offset=id_offset, push=push)
 
 
-SAMPLE_FRACTION = 32          # threshold sample = n_docs / 32 ...
+SAMPLE_FRACTION = int(__import__("os").environ.get("INFOMESH_B200_SAMPLE_FRACTION", "32"))   # threshold sample = n_docs / 32 ...
 SAMPLE_MIN_DOCS = 148 * 256   # ... but at least two 128-document tiles per SM; smaller shards skip the pre-pass
 
 
