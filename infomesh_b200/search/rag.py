@@ -1,10 +1,24 @@
-"""RAG-side helpers on top of ranked results: chunked context windows, sentence-level answer extraction, multi-result
-summary prompts, pattern entity extraction, keyword toxicity filter, chain-of-thought rerank prompts
-(reference infomesh/search/rag.py:24-413)."""
+"""What an LLM client needs on top of ranked hits: context chunks, candidate answers, prompts, entities, a toxicity gate.
+
+Contract (SURVEY §2.1 search/ "RAG helpers"; reference infomesh/search/rag.py:24-413):
+
+* ``format_rag_output``: each hit's snippet is cut into ``chunk_size`` pieces (hit metadata rides only on uncut snippets),
+  at most ``max_chunks`` pieces overall; the context window joins ``[Source: title (url)]`` blocks with ``---`` rules.
+* ``extract_answers``: snippet sentences (>= 10 characters, each once) that share a word with the query; confidence is
+  ``0.8 x query-term coverage + 0.2 x hit score`` capped at 1, kept above 0.2, best ``max_answers`` returned.
+* ``build_summary_prompt`` / ``build_cot_rerank_prompt``: fixed prompt frames around numbered results.
+* ``extract_entities``: technology names from a fixed vocabulary and capitalised multi-word names (< 30 characters),
+  most frequent first.  ``compute_toxicity_score``: flagged words per word x 10, capped at 1.
+
+Implementation: chunking is a generator consumed through ``islice``; sentences, entities and prompts are each one small
+pipeline (``Counter`` for the entity tally) so no function carries loop state by hand."""
 from __future__ import annotations
 
 import re
-from dataclasses import dataclass, field
+from collections import Counter
+from dataclasses import asdict, dataclass, field
+from itertools import accumulate, islice, takewhile
+from typing import Iterator
 
 from infomesh_b200.index.ranking import RankedResult
 
@@ -19,8 +33,10 @@ class RAGChunk:
     metadata: dict[str, object] = field(default_factory=dict)
 
     def to_dict(self) -> dict[str, object]:
-        return {"text": self.text, "url": self.url, "title": self.title, "score": self.score, "chunk_index": self.chunk_index,
-                "metadata": self.metadata}
+        return asdict(self)
+
+    def cited(self) -> str:
+        return f"[Source: {self.title} ({self.url})]\n{self.text}"
 
 
 @dataclass
@@ -31,29 +47,32 @@ class RAGOutput:
     context_window: str = ""
 
     def to_dict(self) -> dict[str, object]:
-        return {"query": self.query, "chunks": [c.to_dict() for c in self.chunks], "total_results": self.total_results,
-                "context_window": self.context_window}
+        return asdict(self)
+
+
+_HIT_METADATA = ("bm25_score", "freshness_score", "trust_score", "crawled_at")
+_RULE = "\n\n---\n\n"
+
+
+def _pieces_of(hit: RankedResult, width: int, with_metadata: bool) -> Iterator[RAGChunk]:
+    body = hit.snippet or ""
+    cuts = [body[at:at + width] for at in range(0, len(body), width)] or [""]
+    whole = len(cuts) == 1
+    for number, piece in enumerate(cuts):
+        details = {name: getattr(hit, name) for name in _HIT_METADATA} if whole and with_metadata else {}
+        yield RAGChunk(piece, hit.url, hit.title, hit.combined_score, number, details)
 
 
 def format_rag_output(query: str, results: list[RankedResult], *, chunk_size: int = 500, max_chunks: int = 10,
                       include_metadata: bool = True) -> RAGOutput:
-    chunks: list[RAGChunk] = []
-    for r in results:
-        text = r.snippet or ""
-        meta = ({"bm25_score": r.bm25_score, "freshness_score": r.freshness_score, "trust_score": r.trust_score,
-                 "crawled_at": r.crawled_at} if include_metadata else {})
-        pieces = [text] if len(text) <= chunk_size else [text[i:i + chunk_size] for i in range(0, len(text), chunk_size)]
-        for i, piece in enumerate(pieces):
-            chunks.append(RAGChunk(piece, r.url, r.title, r.combined_score, i, meta if len(pieces) == 1 else {}))
-        if len(chunks) >= max_chunks:
-            break
-    chunks = chunks[:max_chunks]
-    window = "\n\n---\n\n".join(f"[Source: {c.title} ({c.url})]\n{c.text}" for c in chunks)
-    return RAGOutput(query, chunks, len(results), window)
+    stream = (chunk for hit in results for chunk in _pieces_of(hit, chunk_size, include_metadata))
+    chunks = list(islice(stream, max_chunks))
+    return RAGOutput(query, chunks, len(results), _RULE.join(chunk.cited() for chunk in chunks))
 
 
 _WORDS = re.compile(r"\w+")
 _MARKUP = re.compile(r"</?(?:b|mark|em)>")
+_SENTENCE_END = re.compile(r"[.!?]+")
 
 
 @dataclass(frozen=True)
@@ -65,37 +84,35 @@ class ExtractedAnswer:
     context: str = ""
 
 
+def _vocabulary(text: str) -> frozenset[str]:
+    return frozenset(_WORDS.findall(text.lower()))
+
+
 def extract_answers(query: str, results: list[RankedResult], *, max_answers: int = 3) -> list[ExtractedAnswer]:
     """Sentences sharing terms with the query; confidence = 0.8 * term coverage + 0.2 * result score."""
-    terms = set(_WORDS.findall(query.lower()))
-    found: list[ExtractedAnswer] = []
-    seen: set[str] = set()
-    for r in results:
-        text = _MARKUP.sub("", r.snippet or "")          # FTS snippet() highlight markers are not part of the answer
-        for sent in (s.strip() for s in re.split(r"[.!?]+", text)):
-            if len(sent) < 10 or sent in seen:
+    wanted = _vocabulary(query)
+    per_term = 0.8 / max(len(wanted), 1)
+    offered: dict[str, ExtractedAnswer | None] = {}          # sentence -> answer (None: seen but not an answer)
+    for hit in results:
+        plain = _MARKUP.sub("", hit.snippet or "")           # FTS snippet() highlight markers are not part of the answer
+        for sentence in map(str.strip, _SENTENCE_END.split(plain)):
+            if len(sentence) < 10 or sentence in offered:
                 continue
-            seen.add(sent)
-            overlap = len(terms & set(_WORDS.findall(sent.lower())))
-            if not overlap:
-                continue
-            conf = min(overlap / max(len(terms), 1) * 0.8 + r.combined_score * 0.2, 1.0)
-            if conf > 0.2:
-                found.append(ExtractedAnswer(sent, r.url, r.title, round(conf, 3), text[:200]))
-    return sorted(found, key=lambda a: a.confidence, reverse=True)[:max_answers]
+            shared = len(wanted & _vocabulary(sentence))
+            confidence = min(shared * per_term + 0.2 * hit.combined_score, 1.0)
+            keep = shared > 0 and confidence > 0.2
+            offered[sentence] = ExtractedAnswer(sentence, hit.url, hit.title, round(confidence, 3), plain[:200]) if keep else None
+    answers = [a for a in offered.values() if a is not None]
+    answers.sort(key=lambda a: a.confidence, reverse=True)
+    return answers[:max_answers]
 
 
 def build_summary_prompt(query: str, results: list[RankedResult], *, max_context: int = 3000) -> str:
-    parts, used = [], 0
-    for i, r in enumerate(results, 1):
-        entry = f"[{i}] {r.title}\n{r.snippet or ''}"
-        if used + len(entry) > max_context:
-            break
-        parts.append(entry)
-        used += len(entry)
-    ctx = "\n\n".join(parts)
+    blocks = [f"[{number}] {hit.title}\n{hit.snippet or ''}" for number, hit in enumerate(results, 1)]
+    running = accumulate(len(block) for block in blocks)
+    fitting = [block for block, _ in takewhile(lambda pair: pair[1] <= max_context, zip(blocks, running))]
     return (f'Based on the following search results for the query "{query}", provide a concise summary that answers the '
-            f"query.\n\nSearch Results:\n{ctx}\n\nSummary:")
+            "query.\n\nSearch Results:\n" + "\n\n".join(fitting) + "\n\nSummary:")
 
 
 @dataclass
@@ -106,44 +123,42 @@ class Entity:
     source_urls: list[str] = field(default_factory=list)
 
 
-_TECH = re.compile(r"\b(?:Python|JavaScript|TypeScript|Rust|Go|Java|C\+\+|Ruby|Swift|Kotlin|React|Vue|Angular|Django|Flask|FastAPI|"
-                   r"Node\.js|Docker|Kubernetes|PostgreSQL|MySQL|Redis|MongoDB|SQLite|AWS|Azure|GCP|Linux|macOS|Windows|GitHub|"
-                   r"GitLab|npm|pip|cargo|CUDA|PyTorch|NCCL)\b")
+_TECH_VOCABULARY = (
+    "Python JavaScript TypeScript Rust Go Java C++ Ruby Swift Kotlin React Vue Angular Django Flask FastAPI Node.js Docker "
+    "Kubernetes PostgreSQL MySQL Redis MongoDB SQLite AWS Azure GCP Linux macOS Windows GitHub GitLab npm pip cargo CUDA "
+    "PyTorch NCCL").split()
+_TECH = re.compile(r"\b(?:" + "|".join(map(re.escape, _TECH_VOCABULARY)) + r")\b")
 _NAME = re.compile(r"\b([A-Z][a-z]+(?:\s+[A-Z][a-z]+)+)\b")
 
 
 def extract_entities(text: str, *, source_url: str = "") -> list[Entity]:
-    bag: dict[tuple[str, str], Entity] = {}
-
-    def note(kind: str, name: str) -> None:
-        e = bag.get((kind, name))
-        if e:
-            e.count += 1
-        else:
-            bag[(kind, name)] = Entity(name, kind, 1, [source_url] if source_url else [])
-
-    for m in _TECH.finditer(text):
-        note("TECH", m.group(0))
-    for m in _NAME.finditer(text):
-        if len(m.group(1)) < 30:
-            note("NAME", m.group(1))
-    return sorted(bag.values(), key=lambda e: e.count, reverse=True)
+    mentions: Counter[tuple[str, str]] = Counter(("TECH", m.group(0)) for m in _TECH.finditer(text))
+    mentions.update(("NAME", m.group(1)) for m in _NAME.finditer(text) if len(m.group(1)) < 30)
+    origin = [source_url] if source_url else []
+    # most_common() is a stable sort on the count, so first-seen order breaks ties (technology names before person names)
+    return [Entity(name, kind, times, list(origin)) for (kind, name), times in mentions.most_common()]
 
 
 _TOXIC = re.compile(r"\b(hate|kill|violence|racist|sexist|porn|gambling|drugs|scam|phishing|malware)\b", re.IGNORECASE)
 
 
 def compute_toxicity_score(text: str) -> float:
-    words = len(text.split()) if text else 0
-    return min(len(_TOXIC.findall(text)) / words * 10, 1.0) if words else 0.0
+    n_words = len(text.split()) if text else 0
+    if not n_words:
+        return 0.0
+    return min(10.0 * len(_TOXIC.findall(text)) / n_words, 1.0)
 
 
 def filter_by_toxicity(results: list[RankedResult], *, threshold: float = 0.3) -> list[RankedResult]:
-    return [r for r in results if compute_toxicity_score(r.snippet or "") < threshold]
+    return [hit for hit in results if compute_toxicity_score(hit.snippet or "") < threshold]
+
+
+_COT_INSTRUCTIONS = ("For each candidate, think step by step:\n1. What is this result about?\n2. Does it directly answer the query?\n"
+                     "3. How relevant is it? (1-10)\n\nThen return a JSON array of objects with \"index\" and \"score\" fields, "
+                     "sorted by relevance (highest first).")
 
 
 def build_cot_rerank_prompt(query: str, results: list[RankedResult], *, max_candidates: int = 10) -> str:
-    cands = "\n".join(f"{i}. [{r.title}] {(r.snippet or '')[:200]}" for i, r in enumerate(results[:max_candidates], 1))
-    return (f'Query: "{query}"\n\nCandidates:\n{cands}\n\nFor each candidate, think step by step:\n1. What is this result about?\n'
-            "2. Does it directly answer the query?\n3. How relevant is it? (1-10)\n\nThen return a JSON array of objects with "
-            '"index" and "score" fields, sorted by relevance (highest first).')
+    listing = "\n".join(f"{number}. [{hit.title}] {(hit.snippet or '')[:200]}"
+                        for number, hit in enumerate(results[:max_candidates], 1))
+    return f'Query: "{query}"\n\nCandidates:\n{listing}\n\n{_COT_INSTRUCTIONS}'
