@@ -130,15 +130,22 @@ def index_import_urls(url_file: str, max_urls: int) -> None:
 @click.option("--no-rerank", is_flag=True, help="Skip loading the cross-encoder")
 @click.option("--save", "save_dir", default=None, help="Also write the device segments + manifest to this directory")
 def index_gpu_build(no_rerank: bool, save_dir: str | None) -> None:
-    """Build the HBM-resident mirror of the index on cuda:0 and report its footprint."""
-    from infomesh_b200.engine.gpu_index import GpuSearchIndex, gpu_index_kwargs
+    """Build the HBM-resident mirror of the index (one GPU, or ``[gpu] devices`` of them) and report its footprint."""
+    from infomesh_b200.engine.multigpu import make_index
 
     cfg = load_config()
+    gcfg = getattr(cfg, "gpu", None)
+    save_dir = save_dir or getattr(gcfg, "segments_dir", "") or None
     with _store(cfg) as st:
-        gi = GpuSearchIndex(st, rerank=not no_rerank, **gpu_index_kwargs(getattr(cfg, "gpu", None)))
-        n = gi.rebuild()
-        info = gi.stats()
-        if save_dir and n:
-            man = gi.save(save_dir)
-            click.echo(f"  segments written to {save_dir} ({sum(f['bytes'] for f in man['files'].values()) / 2 ** 20:.1f} MB)")
-    click.secho(f"✔ {n} documents resident: {info['hbm_bytes'] / 2 ** 20:.1f} MB HBM, vocabulary {info['vocab']}, built in {info['build_seconds']} s", fg="green")
+        gi = make_index(st, gcfg, rerank=not no_rerank)
+        try:
+            n = gi.rebuild()
+            info = gi.stats()
+            if save_dir and n:
+                man = gi.save(save_dir)
+                parts = man["shards"] if "shards" in man else [{"bytes": sum(f["bytes"] for f in man["files"].values())}]
+                click.echo(f"  segments written to {save_dir} ({sum(p_['bytes'] for p_ in parts) / 2 ** 20:.1f} MB, {len(parts)} shard(s))")
+        finally:
+            gi.close()
+    where = f"{info['gpus']} GPUs" if "gpus" in info else "1 GPU"
+    click.secho(f"✔ {n} documents resident on {where}: {info['hbm_bytes'] / 2 ** 20:.1f} MB HBM, built in {info['build_seconds']} s", fg="green")

@@ -57,7 +57,9 @@ def search(query: str, limit: int, local_only: bool, vector: bool, gpu: bool) ->
 
             gi = make_index(store, getattr(cfg, "gpu", None), query_batch=8)
             try:
-                gi.rebuild()
+                from infomesh_b200.engine.multigpu import warm_start
+
+                warm_start(gi, store, getattr(getattr(cfg, "gpu", None), "segments_dir", ""))   # `infomesh search --gpu` cold-starts from files
                 t0 = time.monotonic()
                 hits = gi.search(query, limit)
                 label = f"gpu hybrid x{gi.world}" if hasattr(gi, "world") else "gpu hybrid"

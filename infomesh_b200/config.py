@@ -159,6 +159,8 @@ class GpuConfig:
     encoder_path: str = ""           # HF-style checkpoint dir (config.json + model.safetensors + vocab.txt) for the encoder
     reranker_path: str = ""          # same for the cross-encoder; without checkpoints the device path serves BM25 order only
     allow_untrained_models: bool = False   # let random-init models rank (benchmarks / demos only)
+    segments_dir: str = ""           # device segment files (one sub-directory per GPU when sharded): cold starts load these
+                                     # instead of re-encoding the corpus, and every full build refreshes them
 
 
 @dataclass(frozen=True)

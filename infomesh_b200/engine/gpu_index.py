@@ -195,6 +195,7 @@ class GpuSearchIndex:
             if row:
                 ptok[i, :len(row)] = torch.tensor(row, dtype=torch.int32)
             plen[i] = max(len(row), 1)
+        self._builder_live = True
         self._install(builder, csr, vectors, ptok.to(dev), plen.to(dev), torch.ones((n,), dtype=torch.uint8, device=dev),
                       np.asarray(ids, dtype=np.int64), passages)
         shard = self.engine.shard
@@ -209,7 +210,8 @@ class GpuSearchIndex:
         (a memcpy-class pass over the postings) and the device structures are swapped in atomically.  Cost is
         O(new documents) model work + O(postings) copies, against O(corpus) model work for :meth:`rebuild`.
         Returns the number of documents appended.  (A sharded index re-balances its ranges, so it rebuilds.)"""
-        if self.engine is None or self.builder is None or self.shard_world > 1 or self.doc_ids.size == 0:
+        if (self.engine is None or self.builder is None or self.shard_world > 1 or self.doc_ids.size == 0
+                or not getattr(self, "_builder_live", True)):      # loaded segments: the builder holds the vocabulary only
             before = self.n_docs
             return max(0, self.rebuild() - before)
         t0 = time.time()
@@ -268,7 +270,7 @@ class GpuSearchIndex:
     # ------------------------------------------------------------------ persistence
     _FILES = ("vectors.bin", "csr_off.bin", "csr_doc.bin", "csr_tf.bin", "doc_len.bin", "df.bin", "passage_tok.bin",
               "passage_len.bin", "doc_ids.bin", "alive.bin", "vocab.txt", "pass_terms.bin", "pass_off.bin", "doc_pass_off.bin",
-              "pass_span.bin")
+              "pass_span.bin", "neg_age.bin", "authority.bin")
 
     def _model_tag(self) -> str:
         """Identifies the encoder whose vectors are stored: config + a checksum of its first projection matrix."""
@@ -295,6 +297,12 @@ class GpuSearchIndex:
                   "passage_tok.bin": sh.passage_tok.cpu().numpy(), "passage_len.bin": sh.passage_len.cpu().numpy(),
                   "doc_ids.bin": self.doc_ids, "alive.bin": sh.alive.cpu().numpy(), "pass_terms.bin": self._pass["terms"],
                   "pass_off.bin": self._pass["off"], "doc_pass_off.bin": self._pass["doc_off"], "pass_span.bin": self._pass["span"]}
+        # ranking signals (age at build time, authority) and the instant they are relative to: a loaded index must rank
+        # exactly like the one that was saved
+        if self._pass.get("neg_age") is not None:
+            arrays["neg_age.bin"] = np.asarray(self._pass["neg_age"], dtype=np.float64)
+        if self._pass.get("authority") is not None:
+            arrays["authority.bin"] = np.asarray(self._pass["authority"], dtype=np.float32)
         files = {}
         for name, arr in arrays.items():
             arr = np.ascontiguousarray(arr)
@@ -305,7 +313,13 @@ class GpuSearchIndex:
         files["vocab.txt"] = {"bytes": len(vocab.encode()), "dtype": "utf-8", "sha256": hashlib.sha256(vocab.encode()).hexdigest()}
         manifest = {"format": 1, "n_docs": self.n_docs, "dim": int(sh.vectors.shape[1]), "passage_len": self.passage_len, "vocab": self.builder.vocab,
                     "avg_len": bm.avg_len, "model": self._model_tag(), "doc_id_range": [int(self.doc_ids.min()), int(self.doc_ids.max())],
-                    "saved_at": time.time(), "files": files}
+                    "saved_at": time.time(), "t_ref": float(getattr(self, "_t_ref", 0.0)), "files": files}
+        if self.shard_world > 1:
+            # one directory per shard (engine/multigpu.py names them): the global BM25 statistics ride in the manifest, the
+            # global document frequencies are df.bin itself (the slice keeps the whole-corpus df)
+            manifest["shard"] = {"rank": self.shard_rank, "world": self.shard_world, "row_base": int(self.row_base),
+                                 "per_rank": int(csr["per_rank"]), "n_docs_global": int(csr["n_docs_global"]),
+                                 "avg_len_global": float(csr["avg_len_global"])}
         (d / "manifest.json").write_text(json.dumps(manifest, indent=1))
         return manifest
 
@@ -340,6 +354,18 @@ class GpuSearchIndex:
         doc_ids = read("doc_ids.bin", np.int64)
         passages = {"terms": read("pass_terms.bin", np.int32), "off": read("pass_off.bin", np.int64),
                     "doc_off": read("doc_pass_off.bin", np.int64), "span": read("pass_span.bin", np.int32).reshape(-1, 2)}
+        if "neg_age.bin" in man["files"]:
+            passages["neg_age"] = read("neg_age.bin", np.float64)
+            passages["authority"] = read("authority.bin", np.float32) if "authority.bin" in man["files"] else None
+            self._t_ref = float(man.get("t_ref", 0.0))
+        sh_meta = man.get("shard")
+        if (sh_meta is None) != (self.shard_world == 1) or (sh_meta and (sh_meta["rank"], sh_meta["world"]) != (self.shard_rank, self.shard_world)):
+            raise ValueError(f"segments are for shard {sh_meta and (sh_meta['rank'], sh_meta['world'])}, "
+                             f"this index is shard {(self.shard_rank, self.shard_world)}")
+        if sh_meta:
+            csr.update(df_global=csr["df"], n_docs_global=sh_meta["n_docs_global"], avg_len_global=sh_meta["avg_len_global"],
+                       per_rank=sh_meta["per_rank"])
+            self.row_base = int(sh_meta["row_base"])
         builder = HostIndexBuilder()
         terms = (d / "vocab.txt").read_text(encoding="utf-8")
         if terms:
@@ -347,6 +373,7 @@ class GpuSearchIndex:
         if builder.vocab != man["vocab"]:
             raise ValueError("vocabulary does not round-trip")
         self.passage_len = man["passage_len"]
+        self._builder_live = False
         self._install(builder, csr, vectors, ptok, plen, alive, doc_ids, passages)
         self.built_at, self.build_seconds = time.time(), time.time() - t0
         return n

@@ -68,8 +68,10 @@ def _worker_main(rank: int, world: int, port: int, conn, store_path: str, kwargs
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     try:
         make = _resolve(factory) if factory else _default_factory
-        index = make(store_path, rank, world, dict(kwargs))
-        n = index.rebuild()
+        kwargs = dict(kwargs)
+        segments = kwargs.pop("__segments__", None)       # cold start from per-shard segment files instead of a rebuild
+        index = make(store_path, rank, world, kwargs)
+        n = index.load(shard_dir(segments, rank, world)) if segments else index.rebuild()
         conn.send(("ready", {"rank": rank, "documents": int(n), "stats": _plain(index.stats())}))
     except Exception as exc:  # noqa: BLE001 -- the front must learn why the worker never became ready
         conn.send(("failed", f"{type(exc).__name__}: {exc}"))
@@ -86,6 +88,12 @@ def _worker_main(rank: int, world: int, port: int, conn, store_path: str, kwargs
                 conn.send(("ok", int(index.rebuild())))
             elif op == "stats":
                 conn.send(("ok", _plain(index.stats())))
+            elif op == "save":
+                man = index.save(shard_dir(arg, rank, world))
+                conn.send(("ok", {"rank": rank, "n_docs": int(man["n_docs"]), "model": man.get("model", ""),
+                                  "bytes": int(sum(f["bytes"] for f in man["files"].values()))}))
+            elif op == "load":
+                conn.send(("ok", int(index.load(shard_dir(arg, rank, world)))))
             elif op == "delete":
                 conn.send(("ok", bool(index.mark_deleted(int(arg)))))
             elif op == "close":
@@ -104,6 +112,13 @@ def _worker_main(rank: int, world: int, port: int, conn, store_path: str, kwargs
         D.shutdown()
     except Exception:  # noqa: BLE001
         pass
+
+
+def shard_dir(root, rank: int, world: int):
+    """Where shard ``rank`` of ``world`` keeps its segment files under ``root``."""
+    from pathlib import Path
+
+    return Path(root) / f"shard-{rank:02d}-of-{world:02d}"
 
 
 def _plain(obj: Any) -> Any:
@@ -145,13 +160,14 @@ class MultiGpuSearchIndex:
         self.device = "cuda"
 
     # ------------------------------------------------------------------ lifecycle
-    def _spawn(self) -> None:
+    def _spawn(self, segments: str | None = None) -> None:
         ctx = mp.get_context("spawn")
         port = _free_port()
+        kwargs = dict(self._kwargs, __segments__=str(segments)) if segments else self._kwargs
         for rank in range(self.world):
             parent, child = ctx.Pipe(duplex=True)
             p = ctx.Process(target=_worker_main, name=f"infomesh-gpu{rank}", daemon=True,
-                            args=(rank, self.world, port, child, self.store_path, self._kwargs, self._factory))
+                            args=(rank, self.world, port, child, self.store_path, kwargs, self._factory))
             p.start()
             child.close()
             self._procs.append(p)
@@ -196,6 +212,60 @@ class MultiGpuSearchIndex:
         self.n_docs, self._pending = n, 0
         self.built_at, self.build_seconds = time.time(), time.time() - t0
         logger.info("multigpu_index_built", docs=n, gpus=self.world, seconds=round(self.build_seconds, 2))
+        return n
+
+    # ------------------------------------------------------------------ persistence
+    def save(self, directory) -> dict:
+        """Every worker writes its shard's segment files under ``directory/shard-RR-of-WW`` (``GpuSearchIndex.save``); the
+        front adds ``manifest.json`` naming the shards.  A node restarts from these with file reads + ``cudaMemcpy`` per
+        GPU instead of re-tokenising and re-encoding the corpus on every rank."""
+        import json
+        from pathlib import Path
+
+        if not self.healthy:
+            raise RuntimeError("nothing to save: call rebuild() first")
+        root = Path(directory)
+        root.mkdir(parents=True, exist_ok=True)
+        with self._lock:
+            for conn in self._conns:
+                conn.send(("save", str(root)))
+            shards = self._collect(self._ready_timeout)
+        manifest = {"format": 1, "world": self.world, "n_docs": int(sum(s["n_docs"] for s in shards)), "saved_at": time.time(),
+                    "shards": [dict(s, dir=shard_dir("", s["rank"], self.world).name) for s in shards]}
+        (root / "manifest.json").write_text(json.dumps(manifest, indent=1))
+        return manifest
+
+    def load(self, directory) -> int:
+        """Inverse of :meth:`save`: (re)start the worker group from segment files written for the SAME number of GPUs.
+        Returns the total document count; raises when the layout does not match or a shard refuses its segments."""
+        import json
+        from pathlib import Path
+
+        root = Path(directory)
+        man = json.loads((root / "manifest.json").read_text())
+        if man.get("format") != 1 or int(man.get("world", 0)) != self.world:
+            raise ValueError(f"segments were written for {man.get('world')} GPUs, this index runs on {self.world}")
+        t0 = time.time()
+        with self._lock:
+            try:
+                if self.healthy:
+                    for conn in self._conns:
+                        conn.send(("load", str(root)))
+                    n = int(sum(self._collect(self._ready_timeout)))
+                else:
+                    self._teardown()
+                    self._spawn(segments=str(root))
+                    ready = self._collect(self._ready_timeout)
+                    self._worker_stats = [r["stats"] for r in ready]
+                    n = int(sum(r["documents"] for r in ready))
+                self.healthy = True
+            except Exception as exc:  # noqa: BLE001
+                logger.error("multigpu_load_failed", error=str(exc))
+                self._teardown()
+                raise
+        self.n_docs, self._pending = n, 0
+        self.built_at, self.build_seconds = time.time(), time.time() - t0
+        logger.info("multigpu_index_loaded", docs=n, gpus=self.world, seconds=round(self.build_seconds, 2))
         return n
 
     def refresh(self) -> int:
@@ -308,3 +378,53 @@ def make_index(store: Any, gcfg: Any = None, **overrides):
             return MultiGpuSearchIndex(store, devices=n, **kw)
     dev = int(getattr(gcfg, "device", 0)) if gcfg is not None else 0
     return GpuSearchIndex(store, device=f"cuda:{dev}", **kw)
+
+
+def warm_start(index: Any, store: Any, segments_dir: str | os.PathLike | None) -> int:
+    """Bring ``index`` (single- or multi-GPU) up: from the segment files under ``segments_dir`` when they describe the
+    store as it is now, else by a full build whose result is written back there.  Returns the document count.
+
+    "As it is now" = same document count and same highest document id as the store reports; anything else (documents
+    added or removed since the save, another GPU count, another encoder, a checksum failure) falls through to a rebuild --
+    stale segments are never served."""
+    import json
+    from pathlib import Path
+
+    if not segments_dir:
+        return int(index.rebuild())
+    root = Path(segments_dir)
+    stats = store.get_stats() if hasattr(store, "get_stats") else {}
+    want = int(stats.get("document_count", -1))
+    try:
+        man = json.loads((root / "manifest.json").read_text())
+        if want >= 0 and int(man.get("n_docs", -2)) == want and _segments_cover(man, root, store):
+            n = int(index.load(root))
+            logger.info("gpu_index_warm_start", docs=n, source=str(root))
+            return n
+    except FileNotFoundError:
+        pass
+    except Exception as exc:  # noqa: BLE001 -- unreadable / mismatching segments: rebuild
+        logger.warning("gpu_segments_rejected", error=str(exc))
+    n = int(index.rebuild())
+    if n:
+        try:
+            index.save(root)
+        except Exception as exc:  # noqa: BLE001 -- a full disk must not take the freshly built index down
+            logger.warning("gpu_segments_save_failed", error=str(exc))
+    return n
+
+
+def _segments_cover(man: dict, root, store: Any) -> bool:
+    """Does the highest document id in the segments equal the store's?  (Single-GPU manifests carry ``doc_id_range``; a
+    sharded save carries it per shard.)"""
+    import json
+
+    top = -1
+    if "doc_id_range" in man:
+        top = int(man["doc_id_range"][1])
+    for sh in man.get("shards", ()):
+        sub = root / sh["dir"] / "manifest.json"
+        if sub.exists():
+            top = max(top, int(json.loads(sub.read_text()).get("doc_id_range", [0, -1])[1]))
+    newest = getattr(store, "max_doc_id", None)
+    return top < 0 or newest is None or int(newest()) == top

@@ -320,6 +320,12 @@ class LocalStore:
         row = self._conn.execute("SELECT COUNT(*) AS n FROM documents").fetchone()
         return {"document_count": int(row["n"]) if row else 0}
 
+    def max_doc_id(self) -> int:
+        """Highest document id in the store (0 when empty): the GPU index uses it to tell whether saved device segments
+        still describe the store."""
+        row = self._conn.execute("SELECT MAX(doc_id) AS m FROM documents").fetchone()
+        return int(row["m"] or 0) if row else 0
+
     def get_top_domains(self, limit: int = 7) -> list[tuple[str, int]]:
         rows = self._conn.execute(f"SELECT {_HOST_SQL} AS domain, COUNT(*) AS cnt FROM documents GROUP BY domain "
                                   "ORDER BY cnt DESC LIMIT ?", (limit,)).fetchall()

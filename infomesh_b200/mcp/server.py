@@ -60,7 +60,9 @@ def attach_gpu_index(ctx: AppContext) -> Any | None:
 
         # [gpu] devices > 1 (or 0 = all visible): one worker process per GPU behind the same interface
         gi = make_index(ctx.store, gcfg, rerank=getattr(gcfg, "rerank", True), query_batch=getattr(gcfg, "query_batch", 64))
-        gi.rebuild()
+        from infomesh_b200.engine.multigpu import warm_start
+
+        warm_start(gi, ctx.store, getattr(gcfg, "segments_dir", ""))
         ctx.gpu_index = gi
     except Exception as exc:  # noqa: BLE001
         logger.warning("gpu_index_unavailable", error=str(exc))

@@ -65,8 +65,10 @@ class InfoMeshClient:
         if self._gpu:
             from infomesh_b200.engine.multigpu import make_index
 
+            from infomesh_b200.engine.multigpu import warm_start
+
             self._gpu_index = make_index(self._ctx.store, getattr(cfg, "gpu", None))
-            self._gpu_index.rebuild()
+            warm_start(self._gpu_index, self._ctx.store, getattr(getattr(cfg, "gpu", None), "segments_dir", ""))
 
     def close(self) -> None:
         if self._ctx is not None:

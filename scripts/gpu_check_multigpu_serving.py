@@ -79,7 +79,23 @@ def main():
         got = multi.search_many(queries)
         tn = time.time() - t0
         stats = multi.stats()
+        # per-shard segment files: save, drop the worker group, cold-start a new one from the files, expect identical answers
+        seg = Path(tmp) / f"segments-{name.replace('+', '-')}"
+        t0 = time.time()
+        man = multi.save(seg)
+        ts = time.time() - t0
         multi.close()
+        cold = MultiGpuSearchIndex(st, devices=a.gpus, store_path=db, query_batch=64, **kw)
+        t0 = time.time()
+        n_loaded = cold.load(seg)
+        tl = time.time() - t0
+        again = cold.search_many(queries)
+        cold.close()
+        seg_same = sum(([h["doc_id"] for h in x], [h["snippet"] for h in x]) == ([h["doc_id"] for h in y], [h["snippet"] for h in y])
+                       for x, y in zip(got, again))
+        print(f"[{name}] segments: {sum(s_['bytes'] for s_ in man['shards']) / 2 ** 20:.0f} MB saved in {ts:.1f}s, cold start from files "
+              f"{tl:.1f}s (rebuild {tbn:.1f}s), {n_loaded} docs, identical answers {seg_same}/{len(queries)}", flush=True)
+        ok &= n_loaded == a.docs and seg_same == len(queries)
         assert n == a.docs, (n, a.docs)
         same = sum([h["doc_id"] for h in w] == [h["doc_id"] for h in g] for w, g in zip(want, got))
         top1 = sum((w[0]["doc_id"] if w else None) == (g[0]["doc_id"] if g else None) for w, g in zip(want, got))

@@ -55,6 +55,25 @@ class FakeShardIndex:
         self.all_text[self.lo + int(hit[0])] = []          # no term matches any more
         return True
 
+    def save(self, directory):
+        import json
+        from pathlib import Path
+
+        d = Path(directory)
+        d.mkdir(parents=True, exist_ok=True)
+        blob = json.dumps({"all_text": self.all_text, "lo": self.lo, "hi": self.hi, "ids": self.ids.tolist(), "text": self.text})
+        (d / "fake.json").write_text(blob)
+        return {"n_docs": int(self.ids.size), "model": "fake", "files": {"fake.json": {"bytes": len(blob)}}}
+
+    def load(self, directory):
+        import json
+        from pathlib import Path
+
+        st = json.loads((Path(directory) / "fake.json").read_text())
+        self.all_text, self.lo, self.hi, self.text = st["all_text"], st["lo"], st["hi"], st["text"]
+        self.ids = np.array(st["ids"], dtype=np.int64)
+        return int(self.ids.size)
+
     def stats(self):
         return {"documents": int(self.ids.size), "hbm_bytes": 1000 + self.rank, "rank": self.rank}
 

@@ -83,6 +83,55 @@ def test_worker_crash_marks_front_unhealthy_and_rebuild_recovers(tmp_path):
         st.close()
 
 
+def test_per_shard_segments_round_trip(front, tmp_path):
+    f, st = front
+    f.rebuild()
+    before = f.search_many(["unique3", "unique20", "tensor kernel"], k=5)
+    man = f.save(tmp_path / "segments")
+    assert man["world"] == 2 and man["n_docs"] == 23 and [s["dir"] for s in man["shards"]] == ["shard-00-of-02", "shard-01-of-02"]
+    assert (tmp_path / "segments" / "shard-01-of-02" / "fake.json").exists()
+    # warm group: every worker swaps in its loaded shard
+    assert f.load(tmp_path / "segments") == 23
+    assert f.search_many(["unique3", "unique20", "tensor kernel"], k=5) == before
+    # cold start: a fresh front spawns its workers straight from the segments (no rebuild)
+    g = MultiGpuSearchIndex(st, devices=2, store_path=str(tmp_path / "index.db"), query_batch=4,
+                            index_factory="fake_shard_index:make", call_timeout=30, ready_timeout=60)
+    try:
+        assert g.load(tmp_path / "segments") == 23 and g.healthy
+        assert g.search_many(["unique3", "unique20", "tensor kernel"], k=5) == before
+    finally:
+        g.close()
+
+
+def test_segments_for_another_gpu_count_are_refused(front, tmp_path):
+    f, st = front
+    f.rebuild()
+    f.save(tmp_path / "segments")
+    g = MultiGpuSearchIndex(st, devices=4, store_path=str(tmp_path / "index.db"), query_batch=4,
+                            index_factory="fake_shard_index:make", call_timeout=30, ready_timeout=60)
+    with pytest.raises(ValueError, match="written for 2 GPUs"):
+        g.load(tmp_path / "segments")
+    g.close()
+
+
+def test_warm_start_loads_fresh_segments_and_rebuilds_stale_ones(front, tmp_path):
+    from infomesh_b200.engine.multigpu import warm_start
+
+    f, st = front
+    seg = tmp_path / "seg"
+    assert warm_start(f, st, seg) == 23 and (seg / "manifest.json").exists()          # first start: build + save
+    calls = []
+    real_rebuild, real_load = f.rebuild, f.load
+    f.rebuild = lambda: (calls.append("rebuild"), real_rebuild())[1]
+    f.load = lambda d: (calls.append("load"), real_load(d))[1]
+    assert warm_start(f, st, seg) == 23 and calls == ["load"]                          # unchanged store: files only
+    st.add_document(url="https://example.org/p/new", title="New", text="tensor unique99 body text", raw_html_hash="hn", text_hash="tn")
+    assert warm_start(f, st, seg) == 24 and calls == ["load", "rebuild"]               # grown store: stale segments are not served
+    assert [h["url"] for h in f.search("unique99", k=5)] == ["https://example.org/p/new"]
+    assert warm_start(f, st, seg) == 24 and calls[-1] == "load"                        # and the rebuild refreshed the files
+    assert warm_start(f, st, "") == 24 and calls[-1] == "rebuild"                      # no directory configured: plain build
+
+
 def test_failed_worker_start_raises(tmp_path):
     st = _store(tmp_path, 4)
     f = MultiGpuSearchIndex(st, devices=2, store_path=str(tmp_path / "index.db"), query_batch=4,
