@@ -47,6 +47,12 @@ struct MxEpilogue {
   int has_res;
   const int* m_dev;         // optional device-side row count (varlen batches under CUDA graphs)
   int n_per_unit;           // G: consecutive N tiles per work unit (1 unless the A-resident variant is used)
+  // fused LayerNorm variant (LNF): C = LN(acc + bias + residual) in bf16 AND its MXFP8 copy (q_out + c_sf)
+  const float* ln_g;        // [N]
+  const float* ln_b;        // [N] or null
+  float ln_eps;
+  uint8_t* q_out;           // [M, ldq] e4m3 bytes of the normalised rows
+  int ldq;
 };
 
 constexpr int kMxBM = 128;
@@ -65,6 +71,14 @@ constexpr int kMxSfaCol = 2 * kMxBN;                          // 384
 constexpr int kMxSfbCol = kMxSfaCol + 4;                      // 388
 constexpr int kMxBarBytes = 512;
 constexpr int kMxSmemBytes = kMxStages * (kMxABBytes + kMxSfBytes) + kMxStoreBytes + 1024 + kMxBarBytes;
+// fused-LayerNorm variant: a cluster of N / 192 CTAs owns one 128-row block; 3 operand stages make room for the row statistics
+constexpr int kLnfStages = 3;
+constexpr int kLnfMaxCtas = 4;                                // N <= 768
+constexpr int kLnfColWarps = kMxEpiWarps / 4;                 // 3 epilogue warps (64 columns each) per TMEM lane quadrant
+constexpr int kLnfStatBytes = 2 * kLnfMaxCtas * kLnfColWarps * kMxBM * 8;     // [buf][src cta][col warp][row] (sum, sum sq)
+constexpr int kLnfSfRing = ((kLnfStages * kMxSfBytes + 1023) / 1024) * 1024;
+constexpr int kLnfColBytes = 3 * kMxBN * 4;                   // bias | gamma | beta of this CTA's 192 columns
+constexpr int kLnfSmemBytes = kLnfStages * kMxABBytes + kLnfSfRing + kMxStoreBytes + 1024 + kMxBarBytes + kLnfStatBytes + kLnfColBytes;
 // A-resident variant
 constexpr int kAresMaxKb = 6;                                 // K <= 768
 constexpr int kAresBStages = 3;
@@ -99,7 +113,7 @@ __device__ __forceinline__ void mx_act32(float (&f)[32], int act) {
   }
 }
 
-template <bool ARES>
+template <bool ARES, bool LNF = false>
 __global__ void __launch_bounds__(kMxThreads, 1)
 gemm_mxf8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r,
@@ -110,14 +124,17 @@ gemm_mxf8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   // ring layout: [stage][A 16K | B 24K] ... [stage][SFA 512 | SFB 1024];  A-resident: A[kb] x6, B[stage] x3, SFA[kb] x6, SFB[stage] x3
   uint8_t* sA = smem;
   uint8_t* sB = ARES ? smem + kAresMaxKb * kAresABytes : smem + kMxBM * kMxBK;
-  uint8_t* sSFA = ARES ? sB + kAresBStages * kAresBBytes : smem + kMxStages * kMxABBytes;
+  static_assert(!(ARES && LNF), "the fused-LayerNorm epilogue runs on the operand-ring kernel");
+  constexpr int kRing = LNF ? kLnfStages : kMxStages;
+  uint8_t* sSFA = ARES ? sB + kAresBStages * kAresBBytes : smem + kRing * kMxABBytes;
   uint8_t* sSFB = ARES ? sSFA + kAresMaxKb * 512 : sSFA + 512;
-  uint8_t* smem_store = ARES ? sSFB + kAresBStages * 1024 : sSFA + kMxStages * kMxSfBytes;   // 1024-aligned in both layouts
+  uint8_t* smem_store = ARES ? sSFB + kAresBStages * 1024                                   // 1024-aligned in every layout
+                             : sSFA + (LNF ? kLnfSfRing : kMxStages * kMxSfBytes);
   constexpr uint32_t kAStride = ARES ? kAresABytes : kMxABBytes;      // bytes between consecutive A slots
   constexpr uint32_t kBStride = ARES ? kAresBBytes : kMxABBytes;
   constexpr uint32_t kSfaStride = ARES ? 512 : kMxSfBytes;
   constexpr uint32_t kSfbStride = ARES ? 1024 : kMxSfBytes;
-  constexpr uint32_t kBStages = ARES ? kAresBStages : kMxStages;
+  constexpr uint32_t kBStages = ARES ? kAresBStages : kRing;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_store + kMxStoreBytes);
   uint64_t* empty_bar = full_bar + kMxStages;
   uint64_t* tmem_full = empty_bar + kMxStages;
@@ -125,7 +142,10 @@ gemm_mxf8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint64_t* res_bar = tmem_empty + 2;      // [12] residual tiles of one epilogue warp
   uint64_t* a_full = res_bar + kMxEpiWarps;   // [6] A-resident: k-block kb of the unit's activation block has landed
   uint64_t* a_empty = a_full + kAresMaxKb;    // [6] ... and has been consumed by the unit's last N tile
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + kAresMaxKb);
+  uint64_t* stat_bar = a_empty + kAresMaxKb;  // [2] LNF: every epilogue warp of every CTA of the cluster has published its row sums
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stat_bar + 2);
+  float2* stats = reinterpret_cast<float2*>(smem_store + kMxStoreBytes + kMxBarBytes);   // LNF only
+  float* s_cols = reinterpret_cast<float*>(smem_store + kMxStoreBytes + kMxBarBytes + kLnfStatBytes);   // LNF: [3][192]
 
   const uint32_t warp = warp_id();
   const uint32_t lane = lane_id();
@@ -150,6 +170,9 @@ gemm_mxf8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
     }
+    if constexpr (LNF) {
+      for (int i = 0; i < 2; ++i) mbar_init(&stat_bar[i], 1);     // one local expect_tx arrival; the data arrive as transactions
+    }
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -158,6 +181,7 @@ gemm_mxf8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (LNF) cluster_sync_all();     // no peer may arrive on a barrier that is not initialised yet
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -256,6 +280,16 @@ gemm_mxf8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int c_lo = static_cast<int>(ew >> 2) * (32 * kMxChunks);  // this warp's 64 columns of the tile
     uint8_t* my_store = smem_store + ew * kMxChunks * kMxStoreTile;
     const int n_kb_out = N >> 7;                               // k-blocks of the NEXT GEMM (out_mx)
+    if constexpr (LNF) {
+      // this CTA always owns the same 192 columns (its rank in the cluster): bias / gamma / beta live in shared memory
+      const int c0 = static_cast<int>(cluster_ctarank()) * kMxBN;
+      for (int i = static_cast<int>(threadIdx.x) - 64; i < kMxBN; i += 32 * kMxEpiWarps) {
+        s_cols[i] = ep.bias != nullptr ? __ldg(ep.bias + c0 + i) : 0.f;
+        s_cols[kMxBN + i] = __ldg(ep.ln_g + c0 + i);
+        s_cols[2 * kMxBN + i] = ep.ln_b != nullptr ? __ldg(ep.ln_b + c0 + i) : 0.f;
+      }
+      named_bar_sync(1, 32 * kMxEpiWarps);
+    }
     uint32_t acc = 0, acc_phase = 0, tile_cnt = 0;
     for (int u = blockIdx.x; u < num_units; u += gridDim.x)
     for (int m_blk = u / n_groups, n_blk = (u % n_groups) * G, n_end = min(num_n, n_blk + G); n_blk < n_end; ++n_blk, ++tile_cnt) {
@@ -283,6 +317,120 @@ gemm_mxf8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (ep.has_res) mbar_wait(&res_bar[ew], tile_cnt & 1u);
+      if constexpr (LNF) {
+        // ---- fused LayerNorm: the cluster's N / 192 CTAs hold one full row block between them ----
+        // pass 1: y = acc + bias + residual stays in registers; per-row (sum, sum of squares) of this warp's 64 columns go to
+        // every CTA of the cluster with st.async (the 8 bytes complete 8 bytes of transaction count on the receiver's
+        // mbarrier when they land: no fence, no separate signal)
+        const uint32_t sw = (lane >> 1) & 3u;
+        const uint32_t n_cta = cluster_nctarank(), me = cluster_ctarank();
+        const uint32_t buf = tile_cnt & 1u;
+        if (ew == 0 && lane == 0) mbar_expect_tx(&stat_bar[buf], n_cta * kMxEpiWarps * 32u * 8u);
+        uint64_t acc1 = pk2(0.f, 0.f), acc2 = pk2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < kMxChunks; ++j) {
+          const uint8_t* tile = my_store + j * kMxStoreTile;
+          const float* bias_s = s_cols + c_lo + 32 * j;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + 8 * q4);
+            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + 8 * q4 + 4);
+            uint64_t y2[4] = {pk2(b0.x, b0.y), pk2(b0.z, b0.w), pk2(b1.x, b1.y), pk2(b1.z, b1.w)};
+            if (ep.has_res) {
+              const uint4 rq = *reinterpret_cast<const uint4*>(tile + lane * 64 + ((static_cast<uint32_t>(q4) ^ sw) << 4));
+              const float2 a = unpack_bf16x2(rq.x), b = unpack_bf16x2(rq.y), cc = unpack_bf16x2(rq.z), d = unpack_bf16x2(rq.w);
+              y2[0] = add2(y2[0], pk2(a.x, a.y));
+              y2[1] = add2(y2[1], pk2(b.x, b.y));
+              y2[2] = add2(y2[2], pk2(cc.x, cc.y));
+              y2[3] = add2(y2[3], pk2(d.x, d.y));
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint64_t yv = add2(y2[i], pk2u(v[j][8 * q4 + 2 * i], v[j][8 * q4 + 2 * i + 1]));
+              float lo, hi;
+              upk2(yv, lo, hi);
+              v[j][8 * q4 + 2 * i] = __float_as_uint(lo);
+              v[j][8 * q4 + 2 * i + 1] = __float_as_uint(hi);
+              acc1 = add2(acc1, yv);
+              acc2 = fma2(yv, yv, acc2);
+            }
+          }
+        }
+        float s1, s1b, s2, s2b;
+        upk2(acc1, s1, s1b);
+        upk2(acc2, s2, s2b);
+        s1 += s1b;
+        s2 += s2b;
+        const uint32_t row_in_blk = quad * 32u + lane;
+        const uint32_t mine = smem_u32(stats + ((buf * kLnfMaxCtas + me) * kLnfColWarps + (ew >> 2)) * kMxBM + row_in_blk);
+        const uint32_t bar = smem_u32(&stat_bar[buf]);
+        for (uint32_t p = 0; p < n_cta; ++p) st_async_f32x2(mapa_shared(mine, p), s1, s2, mapa_shared(bar, p));
+        mbar_wait(&stat_bar[buf], (tile_cnt >> 1) & 1u);
+        float S1 = 0.f, S2 = 0.f;
+        for (uint32_t p = 0; p < n_cta; ++p)
+#pragma unroll
+          for (int cw = 0; cw < kLnfColWarps; ++cw) {
+            const float2 t = stats[((buf * kLnfMaxCtas + p) * kLnfColWarps + cw) * kMxBM + row_in_blk];
+            S1 += t.x;
+            S2 += t.y;
+          }
+        const float inv_n = 1.0f / static_cast<float>(N);
+        const float mean = S1 * inv_n;
+        const float rstd = rsqrtf(fmaxf(fmaf(-mean, mean, S2 * inv_n), 0.f) + ep.ln_eps);
+        const uint64_t nmean2 = pk2(-mean, -mean), rstd2 = pk2(rstd, rstd);
+        // pass 2: normalise, write the bf16 tile through the staging buffer (TMA store) and the e4m3 copy + its scale bytes directly
+        const bool row_ok = tile_row0 + static_cast<int>(lane) < M;
+#pragma unroll
+        for (int j = 0; j < kMxChunks; ++j) {
+          const int col0 = col_base + 32 * j;
+          uint8_t* tile = my_store + j * kMxStoreTile;
+          const float* g_s = s_cols + kMxBN + c_lo + 32 * j;
+          const float* b_s = s_cols + 2 * kMxBN + c_lo + 32 * j;
+          float f[32];
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4) {
+            const float4 g4 = *reinterpret_cast<const float4*>(g_s + 4 * q4);
+            const float4 b4 = *reinterpret_cast<const float4*>(b_s + 4 * q4);
+            const uint64_t d0 = mul2(add2(pk2u(v[j][4 * q4 + 0], v[j][4 * q4 + 1]), nmean2), rstd2);
+            const uint64_t d1 = mul2(add2(pk2u(v[j][4 * q4 + 2], v[j][4 * q4 + 3]), nmean2), rstd2);
+            upk2(fma2(d0, pk2(g4.x, g4.y), pk2(b4.x, b4.y)), f[4 * q4 + 0], f[4 * q4 + 1]);
+            upk2(fma2(d1, pk2(g4.z, g4.w), pk2(b4.z, b4.w)), f[4 * q4 + 2], f[4 * q4 + 3]);
+          }
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            uint4 q;
+            q.x = pack_bf16x2(f[8 * q4 + 0], f[8 * q4 + 1]);
+            q.y = pack_bf16x2(f[8 * q4 + 2], f[8 * q4 + 3]);
+            q.z = pack_bf16x2(f[8 * q4 + 4], f[8 * q4 + 5]);
+            q.w = pack_bf16x2(f[8 * q4 + 6], f[8 * q4 + 7]);
+            *reinterpret_cast<uint4*>(tile + lane * 64 + ((static_cast<uint32_t>(q4) ^ sw) << 4)) = q;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) tma_store_2d(&tmap_c, tile, col0, tile_row0);
+          float amax = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) amax = fmaxf(amax, fabsf(f[i]));
+          float inv;
+          const uint32_t e = ue8m0_from_amax(amax, inv);
+          const uint64_t inv2 = pk2(inv, inv);
+          uint32_t w8[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float a0, a1, a2, a3;
+            upk2(mul2(pk2(f[4 * i], f[4 * i + 1]), inv2), a0, a1);
+            upk2(mul2(pk2(f[4 * i + 2], f[4 * i + 3]), inv2), a2, a3);
+            w8[i] = pack_e4m3x4(a0, a1, a2, a3);
+          }
+          if (row_ok) {
+            uint4* q_row = reinterpret_cast<uint4*>(ep.q_out + static_cast<size_t>(tile_row0 + static_cast<int>(lane)) * ep.ldq + col0);
+            q_row[0] = make_uint4(w8[0], w8[1], w8[2], w8[3]);      // 32 bytes = one full sector per row
+            q_row[1] = make_uint4(w8[4], w8[5], w8[6], w8[7]);
+            ep.c_sf[(static_cast<size_t>(m_blk) * n_kb_out + (col0 >> 7)) * 512 + lane * 16 + quad * 4 + ((col0 & 127) >> 5)] =
+                static_cast<uint8_t>(e);
+          }
+        }
+      } else {
 #pragma unroll
       for (int j = 0; j < kMxChunks; ++j) {
         const int col0 = col_base + 32 * j;
@@ -355,6 +503,7 @@ gemm_mxf8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         __syncwarp();
         if (lane == 0) tma_store_2d(&tmap_c, tile, col0, tile_row0);
       }
+      }
       if (lane == 0) tma_store_commit();   // one bulk group per tile
       if (++acc == 2) {
         acc = 0;
@@ -366,6 +515,7 @@ gemm_mxf8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (LNF) cluster_sync_all();     // a CTA's statistics slots and barriers stay valid until every peer is done
   if (warp == 2) tmem_dealloc(tmem_base, kMxTmemCols);
 }
 
@@ -412,6 +562,11 @@ IM_API int im_gemm_mxf8(const void* A, const void* SFA, const void* B, const voi
   ep.out_mx = out_mx;
   ep.has_res = residual != nullptr ? 1 : 0;
   ep.m_dev = m_dev;
+  ep.ln_g = nullptr;
+  ep.ln_b = nullptr;
+  ep.ln_eps = 0.f;
+  ep.q_out = nullptr;
+  ep.ldq = 0;
   const int num_m = (M + kMxBM - 1) / kMxBM, num_n = (N + kMxBN - 1) / kMxBN;
   // A-resident variant when the activation block fits (K <= 768) and there is enough parallelism left after grouping N
   // tiles: halve the group until the units cover the SMs at least twice (G = 1 degenerates to the ring kernel's order)
@@ -439,4 +594,81 @@ IM_API int im_gemm_mxf8(const void* A, const void* SFA, const void* B, const voi
     IM_CUDA_OK(launch_pdl(gemm_mxf8_kernel<false>, dim3(grid), dim3(kMxThreads), kMxSmemBytes, st, ta, tb, tc, tr, ep, M, N, K));
   IM_LAUNCH_OK("gemm_mxf8_kernel");
   return ares ? G : 0;
+}
+
+// C = LayerNorm(A·B^T + bias + residual) in bf16, plus the MXFP8 copy of C (Cq + Cq_sf: the next block-scaled GEMM's A
+// operand), in ONE kernel: N / 192 CTAs (2 or 4) form a thread-block cluster that owns a 128-row block, exchange per-row
+// (sum, sum of squares) through distributed shared memory and normalise their own 192 columns.  Replaces the
+// GEMM -> sum_ln_mx pair of the transformer's attention-output and FFN-down projections (one HBM round trip of the
+// [M, N] activations and one launch less per projection).
+IM_API int im_gemm_mxf8_ln(const void* A, const void* SFA, const void* B, const void* SFB, int n_chunks_b, void* C, void* Cq,
+                           void* Cq_sf, const float* bias, const void* residual, const float* gamma, const float* beta, float eps,
+                           int M, int N, int K, int lda, int ldb, int ldc, int ldr, int ldq, const int* m_dev, int max_ctas,
+                           void* stream) {
+  using namespace im;
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if (K % kMxBK) return set_error("im_gemm_mxf8_ln", "K must be a multiple of 128");
+  if (N % kMxBN || N / kMxBN < 2 || N / kMxBN > kLnfMaxCtas || (N / kMxBN) & (N / kMxBN - 1))
+    return set_error("im_gemm_mxf8_ln", "N must be 384 or 768 (a cluster of 2 or 4 CTAs owns a row block)");
+  if ((lda % 16) || (ldb % 16) || (ldq % 16)) return set_error("im_gemm_mxf8_ln", "row pitches must be multiples of 16 bytes");
+  if (gamma == nullptr || Cq == nullptr || Cq_sf == nullptr) return set_error("im_gemm_mxf8_ln", "gamma and the MXFP8 output are required");
+  if (n_chunks_b < (N + 127) / 128) return set_error("im_gemm_mxf8_ln", "SFB needs ceil(N/128) chunks per k-block");
+  const int n_cta = N / kMxBN;
+  static bool configured = false;
+  if (!configured) {
+    IM_CUDA_OK(cudaFuncSetAttribute(gemm_mxf8_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLnfSmemBytes));
+    configured = true;
+  }
+  CUtensorMap ta, tb, tc, tr;
+  if (get_tmap_2d(&ta, A, M, K, static_cast<uint64_t>(lda), kMxBM, kMxBK, 1, TMAP_SW_128)) return -1;
+  if (get_tmap_2d(&tb, B, N, K, static_cast<uint64_t>(ldb), kMxBN, kMxBK, 1, TMAP_SW_128)) return -1;
+  if (get_tmap_2d(&tc, C, M, N, static_cast<uint64_t>(ldc) * 2, 32, 32, 2, TMAP_SW_64)) return -1;
+  tr = tc;
+  if (residual != nullptr && get_tmap_2d(&tr, residual, M, N, static_cast<uint64_t>(ldr) * 2, 32, 32, 2, TMAP_SW_64)) return -1;
+  MxEpilogue ep;
+  ep.bias = bias;
+  ep.c_sf = reinterpret_cast<uint8_t*>(Cq_sf);
+  ep.sfa = reinterpret_cast<const uint8_t*>(SFA);
+  ep.sfb = reinterpret_cast<const uint8_t*>(SFB);
+  ep.n_chunks_b = n_chunks_b;
+  ep.act = 0;
+  ep.out_mx = 0;
+  ep.has_res = residual != nullptr ? 1 : 0;
+  ep.m_dev = m_dev;
+  ep.n_per_unit = 1;
+  ep.ln_g = gamma;
+  ep.ln_b = beta;
+  ep.ln_eps = eps;
+  ep.q_out = reinterpret_cast<uint8_t*>(Cq);
+  ep.ldq = ldq;
+  const int num_m = (M + kMxBM - 1) / kMxBM;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // one cluster per row block in flight; the grid is a whole number of clusters, at most as many as can be co-resident
+  static int max_clusters[kLnfMaxCtas + 1] = {0, 0, 0, 0, 0};
+  if (max_clusters[n_cta] == 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(sm_count() / n_cta * n_cta));
+    cfg.blockDim = dim3(kMxThreads);
+    cfg.dynamicSmemBytes = kLnfSmemBytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = static_cast<unsigned>(n_cta);
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_mxf8_kernel<false, true>, &cfg) != cudaSuccess || n < 1) {
+      cudaGetLastError();
+      n = sm_count() / n_cta;
+    }
+    max_clusters[n_cta] = n;
+  }
+  int clusters = num_m < max_clusters[n_cta] ? num_m : max_clusters[n_cta];
+  if (max_ctas > 0 && clusters * n_cta > max_ctas) clusters = max_ctas / n_cta;
+  if (clusters < 1) clusters = 1;
+  IM_CUDA_OK(launch_pdl_cluster(gemm_mxf8_kernel<false, true>, dim3(static_cast<unsigned>(clusters * n_cta)), dim3(kMxThreads),
+                                kLnfSmemBytes, st, static_cast<unsigned>(n_cta), ta, tb, tc, tr, ep, M, N, K));
+  IM_LAUNCH_OK("gemm_mxf8_kernel<ln>");
+  return clusters;
 }

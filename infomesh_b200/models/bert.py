@@ -209,12 +209,18 @@ class BertModel:
         q3 = qkv.view(B, S, 3 * H)
         ctx = MX.alloc_act(B * S, H, dev)
         A.attention_mx(q3[..., :H], q3[..., H:2 * H], q3[..., 2 * H:], cfg.heads, ctx, cu_seqlens=cu)
-        y = MX.linear_mx(ctx, lay["wo_mx"], lay["bo"], residual=x, m_dev=total)
         x1q = MX.alloc_act(B * S, H, dev)
+        x2q = MX.alloc_act(B * S, H, dev)
+        if MX.FUSED_LN and H in MX.FUSED_LN_WIDTHS:
+            # residual add + LayerNorm + MXFP8 quantisation run in the projection's epilogue (cluster of H / 192 CTAs per row block)
+            x1 = MX.linear_mx_ln(ctx, lay["wo_mx"], lay["bo"], x, lay["ln1_g"], lay["ln1_b"], cfg.eps, x1q, m_dev=total)
+            h = MX.linear_mx(x1q, lay["w1_mx"], lay["b1"], act="gelu", out_mx=True, m_dev=total)
+            x2 = MX.linear_mx_ln(h, lay["w2_mx"], lay["b2"], x1, lay["ln2_g"], lay["ln2_b"], cfg.eps, x2q, m_dev=total)
+            return x2, x2q
+        y = MX.linear_mx(ctx, lay["wo_mx"], lay["bo"], residual=x, m_dev=total)
         x1 = N.layernorm_mx(y, lay["ln1_g"], lay["ln1_b"], cfg.eps, x1q, n_rows_dev=total)
         h = MX.linear_mx(x1q, lay["w1_mx"], lay["b1"], act="gelu", out_mx=True, m_dev=total)
         y2 = MX.linear_mx(h, lay["w2_mx"], lay["b2"], residual=x1, m_dev=total)
-        x2q = MX.alloc_act(B * S, H, dev)
         x2 = N.layernorm_mx(y2, lay["ln2_g"], lay["ln2_b"], cfg.eps, x2q, n_rows_dev=total)
         return x2, x2q
 

@@ -14,6 +14,7 @@ reranker (infomesh/search/reranker.py:124-159) with block-scaled fp8 tensor-core
 from __future__ import annotations
 
 import ctypes
+import os
 from dataclasses import dataclass
 
 import torch
@@ -179,3 +180,48 @@ def linear_mx(a: MxTensor, w: MxWeight, bias=None, residual=None, act=None, out=
         _native.check(rc, "im_gemm_mxf8")
     _native.count_launch()
     return out
+
+
+FUSED_LN = os.environ.get("INFOMESH_B200_FUSED_LN", "1") != "0"     # models/bert.py: LayerNorm in the projection's epilogue
+FUSED_LN_WIDTHS = (384, 768)        # N = 2 or 4 tiles of 192 columns: a cluster of 2 / 4 CTAs owns a 128-row block
+
+
+def linear_mx_ln(a: MxTensor, w: MxWeight, bias, residual, gamma, beta, eps: float, mx_out: MxTensor, out=None, m_dev=None,
+                 max_ctas: int = 0):
+    """``LN(a @ w^T + bias + residual)`` -> bf16 ``[M, N]`` AND its MXFP8 copy in ``mx_out``, in one kernel.
+
+    The attention-output and FFN-down projections of a post-LN transformer block end in residual add + LayerNorm; with
+    ``N`` = 384 / 768 the ``N / 192`` CTAs that compute one 128-row block run as a thread-block cluster, exchange per-row
+    (sum, sum of squares) through distributed shared memory and normalise in the GEMM epilogue, so the ``[M, N]``
+    activations never make the extra HBM round trip through a standalone LayerNorm kernel."""
+    m, k = a.q.shape
+    n = w.q.shape[0]
+    assert n in FUSED_LN_WIDTHS, f"fused LayerNorm epilogue needs N in {FUSED_LN_WIDTHS}"
+    assert a.q.is_cuda and a.q.dtype == torch.uint8 and w.q.dtype == torch.uint8 and w.q.shape[1] == k and k % 128 == 0
+    assert a.q.stride(1) == 1 and w.q.stride(1) == 1 and a.sf.is_contiguous() and w.sf.is_contiguous()
+    assert mx_out.q.shape == (m, n) and mx_out.q.stride(1) == 1 and mx_out.sf.is_contiguous()
+    assert gamma.dtype == torch.float32 and gamma.numel() == n and (beta is None or (beta.dtype == torch.float32 and beta.numel() == n))
+    assert bias is None or (bias.dtype == torch.float32 and bias.numel() == n)
+    if out is None:
+        out = torch.empty((m, n), device=a.q.device, dtype=torch.bfloat16)
+    assert out.dtype == torch.bfloat16 and out.stride(1) == 1
+    if residual is not None:
+        assert residual.dtype == torch.bfloat16 and residual.shape == (m, n) and residual.stride(1) == 1
+    L = _native.require()
+    rc = L.im_gemm_mxf8_ln(_native.ptr(a.q), _native.ptr(a.sf), _native.ptr(w.q), _native.ptr(w.sf), ctypes.c_int(w.n_chunks),
+                           _native.ptr(out), _native.ptr(mx_out.q), _native.ptr(mx_out.sf), _native.ptr(bias), _native.ptr(residual),
+                           _native.ptr(gamma), _native.ptr(beta), ctypes.c_float(eps),
+                           ctypes.c_int(m), ctypes.c_int(n), ctypes.c_int(k), ctypes.c_int(a.q.stride(0)), ctypes.c_int(w.q.stride(0)),
+                           ctypes.c_int(out.stride(0)), ctypes.c_int(residual.stride(0) if residual is not None else 0),
+                           ctypes.c_int(mx_out.q.stride(0)), _native.ptr(m_dev), ctypes.c_int(max_ctas or _native.sm_budget("gemm")),
+                           _native.stream_ptr())
+    if rc < 0:
+        _native.check(rc, "im_gemm_mxf8_ln")
+    _native.count_launch()
+    return out
+
+
+def linear_mx_ln_ref(a: MxTensor, w: MxWeight, bias, residual, gamma, beta, eps: float, rows=None):
+    """fp32 oracle of :func:`linear_mx_ln`: dequantised GEMM + bias + residual, then LayerNorm."""
+    y = linear_mx_ref(a, w, bias, residual, None, rows)
+    return torch.nn.functional.layer_norm(y, (y.shape[-1],), gamma.float(), None if beta is None else beta.float(), eps)

@@ -82,6 +82,64 @@ def test_layernorm_mx_matches_oracle(h):
     assert ((mxo.float() - ref).abs() <= blk * 2 ** -3 + 1e-4).all()
 
 
+@pytest.mark.parametrize("m,n,k,rows", [(1000, 768, 768, None), (2000, 768, 3072, 1777), (300, 384, 384, None), (9000, 768, 768, 8900),
+                                      (128, 384, 1536, 1)])
+def test_gemm_with_layernorm_epilogue_matches_oracle(m, n, k, rows):
+    """GEMM + bias + residual + LayerNorm + MXFP8 quantisation in one clustered kernel vs the fp32 oracle of the same chain."""
+    from infomesh_b200.ops import mx as MX
+
+    a = MX.quantize_act_ref(torch.randn(m, k, device=DEV) * torch.logspace(-1, 1, m, device=DEV)[:, None])
+    w = MX.quantize_weight(torch.randn(n, k, device=DEV) * 0.05)
+    bias = torch.randn(n, device=DEV) * 0.3
+    res = (torch.randn(m, n, device=DEV) * 2).bfloat16()
+    g = torch.rand(n, device=DEV) + 0.5
+    b = torch.randn(n, device=DEV) * 0.1
+    m_dev = torch.tensor([rows], device=DEV, dtype=torch.int32) if rows else None
+    live = rows or m
+    mxo = MX.alloc_act(m, n, DEV, init=True)
+    out = torch.zeros((m, n), device=DEV, dtype=torch.bfloat16)
+    for _ in range(3):            # repeated launches: the statistics buffers and cluster barriers alternate cleanly
+        MX.linear_mx_ln(a, w, bias, res, g, b, 1e-5, mxo, out=out, m_dev=m_dev)
+    torch.cuda.synchronize()
+    ref = MX.linear_mx_ln_ref(a, w, bias, res[:live], g, b, 1e-5, rows=live)
+    assert torch.isfinite(out[:live].float()).all()
+    assert (out[:live].float() - ref).abs().max().item() < 0.03
+    if rows:
+        blocks = (rows + 127) // 128 * 128
+        assert (out[blocks:] == 0).all()          # row blocks past the device-side count were never written
+    e_ref = MX.quantize_ref(ref)[1].int()
+    e_got = MX.unpack_sfa(mxo.sf, live).int()
+    assert (e_ref - e_got).abs().max().item() <= 1 and (e_ref != e_got).float().mean().item() < 0.01
+    blk = ref.reshape(live, n // 32, 32).abs().amax(-1, keepdim=True).expand(-1, -1, 32).reshape(live, n)
+    assert ((mxo.float(live) - ref).abs() <= blk * 2 ** -3 + 1e-3).all()
+    # and it agrees with the two-kernel path it replaces (GEMM + residual -> bf16, then LayerNorm)
+    from infomesh_b200.ops import nn as N
+
+    y = MX.linear_mx(a, w, bias, res, m_dev=m_dev)
+    two = N.layernorm_mx(y, g, b, 1e-5, MX.alloc_act(m, n, DEV, init=True), n_rows_dev=m_dev)
+    assert (out[:live].float() - two[:live].float()).abs().max().item() < 0.06
+
+
+def test_cross_encoder_fused_layernorm_matches_unfused(monkeypatch):
+    from infomesh_b200.models.bert import BGE_RERANKER_BASE, BertModel
+    from infomesh_b200.ops import mx as MX
+
+    m = BertModel(replace(BGE_RERANKER_BASE, layers=3), device=DEV, seed=7)
+    g = torch.Generator(device="cpu").manual_seed(9)
+    ids = torch.randint(5, 5000, (48, 96), generator=g, dtype=torch.int32).to(DEV)
+    lens = torch.randint(10, 97, (48,), generator=g, dtype=torch.int32).to(DEV)
+    monkeypatch.setattr(MX, "FUSED_LN", False)
+    plain = m.score_packed(ids, lens, precision="mxfp8")
+    monkeypatch.setattr(MX, "FUSED_LN", True)
+    fused = m.score_packed(ids, lens, precision="mxfp8")
+    ref = m.score_ref(ids, lens)
+    spread = (ref.max() - ref.min()).item()
+    assert torch.isfinite(fused).all()
+    # the fused path normalises the fp32 accumulator instead of its bf16 rounding: it is at least as close to the oracle
+    assert (fused - ref).abs().max().item() <= (plain - ref).abs().max().item() + 0.05 * spread
+    assert (fused - plain).abs().max().item() < 0.15 * spread
+
+
 def test_attention_mx_matches_attention_then_quantise():
     from infomesh_b200.ops import attention as A
     from infomesh_b200.ops import mx as MX
