@@ -422,10 +422,24 @@ gemm_mxf8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             upk2(mul2(pk2(f[4 * i + 2], f[4 * i + 3]), inv2), a2, a3);
             w8[i] = pack_e4m3x4(a0, a1, a2, a3);
           }
+          {
+            // a row's 32 e4m3 bytes are one sector: lane pairs swap halves so that EACH store instruction writes whole sectors
+            // (even lane: low half of its own row, then low half of the odd lane's row; odd lane: the two high halves)
+            const bool odd = (lane & 1u) != 0u;
+            uint32_t mine_[4], got[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              mine_[i] = odd ? w8[i] : w8[4 + i];                 // the half this lane gives away
+              got[i] = __shfl_xor_sync(0xffffffffu, mine_[i], 1);
+            }
+            const int r_even = tile_row0 + static_cast<int>(lane & ~1u);
+            uint8_t* base = ep.q_out + col0 + (odd ? 16 : 0);
+            const uint4 first = odd ? make_uint4(got[0], got[1], got[2], got[3]) : make_uint4(w8[0], w8[1], w8[2], w8[3]);
+            const uint4 second = odd ? make_uint4(w8[4], w8[5], w8[6], w8[7]) : make_uint4(got[0], got[1], got[2], got[3]);
+            if (r_even < M) *reinterpret_cast<uint4*>(base + static_cast<size_t>(r_even) * ep.ldq) = first;           // row 2i
+            if (r_even + 1 < M) *reinterpret_cast<uint4*>(base + static_cast<size_t>(r_even + 1) * ep.ldq) = second;  // row 2i+1
+          }
           if (row_ok) {
-            uint4* q_row = reinterpret_cast<uint4*>(ep.q_out + static_cast<size_t>(tile_row0 + static_cast<int>(lane)) * ep.ldq + col0);
-            q_row[0] = make_uint4(w8[0], w8[1], w8[2], w8[3]);      // 32 bytes = one full sector per row
-            q_row[1] = make_uint4(w8[4], w8[5], w8[6], w8[7]);
             ep.c_sf[(static_cast<size_t>(m_blk) * n_kb_out + (col0 >> 7)) * 512 + lane * 16 + quad * 4 + ((col0 & 127) >> 5)] =
                 static_cast<uint8_t>(e);
           }
