@@ -12,9 +12,9 @@ from pathlib import Path
 LIB = Path(__file__).resolve().parent.parent / "infomesh_b200" / "_native" / "libinfomesh_b200.so"
 KEEP = re.compile(r"^(UTC[A-Z]*MMA|UTCCP|UTCBAR|UTCATOMSWS|UTCSHIFT|LDTM|STTM|UTMALDG|UTMASTG|UTMAREDG|UTMACCTL|UBLKCP|UBLKRED|LDGMC|"
                   r"SYNCS|ELECT|ACQBULK|FENCE\.VIEW\.ASYNC|MEMBAR\.[A-Z.]+|REDG|ATOMG|ATOMS|MUFU\.[A-Z0-9]+|FFMA2|FMUL2|FADD2|"
-                  r"F2FP[A-Z0-9.]*|HMMA|IMMA|QMMA|STG\.E\.MC|RED\.[A-Z.]*MC|ST\.MC|MULTIMEM|UCGABAR|CCTL)")
+                  r"F2FP[A-Z0-9.]*|HMMA|IMMA|QMMA|STG\.E\.MC|RED\.[A-Z.]*MC|ST\.MC|MULTIMEM|UCGABAR[A-Z_]*|STAS[A-Z0-9.]*|CCTL)")
 COLLAPSE = ("SYNCS", "UTCATOMSWS", "UTMALDG", "UTMASTG", "UTMACCTL", "LDTM", "REDG", "ATOMG", "ATOMS", "UBLKCP", "LDGMC", "UTCCP",
-            "UTCQMMA", "UTCHMMA", "UTCOMMA", "UTCBAR", "F2FP", "ELECT", "UTMAREDG")
+            "UTCQMMA", "UTCHMMA", "UTCOMMA", "UTCBAR", "F2FP", "ELECT", "UTMAREDG", "STAS", "UCGABAR")
 
 out = subprocess.run(["cuobjdump", "-sass", str(LIB)], capture_output=True, text=True, check=True).stdout
 per = collections.OrderedDict()
@@ -50,7 +50,8 @@ print("UTCHMMA = tcgen05.mma kind::f16 · **UTCQMMA** = tcgen05.mma kind::f8f6f4
       "**UTCCP** = tcgen05.cp (scale factors smem -> TMEM) · LDTM = tcgen05.ld · UTMALDG/UTMASTG = TMA tensor load/store · "
       "**UBLKCP** = cp.async.bulk (1-D bulk copy: scale-factor chunks) · UTCBAR = tcgen05.commit -> mbarrier · UTCATOMSWS = TMEM "
       "alloc/dealloc · SYNCS = mbarrier ops · ELECT = elect.sync · **LDGMC** = multimem.ld_reduce (NVLS in-switch reduction) · "
-      "REDG/STG on multicast addresses = multimem.red / multimem.st · F2FP = packed fp32 -> e4m3/bf16 conversion (fused quantisers) · "
+      "REDG/STG on multicast addresses = multimem.red / multimem.st · **STAS** = st.async.shared::cluster with mbarrier complete_tx "
+      "(distributed-shared-memory exchange of the fused LayerNorm epilogue) · UCGABAR = barrier.cluster · F2FP = packed fp32 -> e4m3/bf16 conversion (fused quantisers) · "
       "FFMA2/FMUL2/FADD2 = packed fp32x2 math · MUFU.* = SFU approximations · MEMBAR.*.SYS + REDG/ATOMG = system-scope release "
       "for peer flags.  HMMA / IMMA / QMMA (legacy mma.sync tensor-core paths) do not appear anywhere: "
       f"{'NONE FOUND' if not any(k in total for k in ('HMMA', 'IMMA', 'QMMA')) else 'PRESENT (!)'}.\n")
