@@ -9,21 +9,33 @@ from infomesh_b200.config import Config
 from infomesh_b200.runtime import read_live_pid, read_runtime_status
 
 
+_UPTIME_UNITS = (("d", 86400), ("h", 3600))
+_BYTE_UNITS = ("B", "KB", "MB", "GB", "TB")
+
+
 def format_uptime(seconds: float) -> str:
-    s = int(max(seconds, 0))
-    d, s = divmod(s, 86400)
-    h, s = divmod(s, 3600)
-    m, s = divmod(s, 60)
-    return f"{d}d {h}h {m}m" if d else f"{h}h {m}m {s}s" if h else f"{m}m {s}s" if m else f"{s}s"
+    """``1d 2h 5m`` -- zero days / hours are left out, minutes always shown, an em dash for "not running" (<= 0)."""
+    if seconds <= 0:
+        return "—"
+    left, shown = int(seconds), []
+    for suffix, span in _UPTIME_UNITS:
+        count, left = divmod(left, span)
+        if count:
+            shown.append(f"{count}{suffix}")
+    shown.append(f"{left // 60}m")
+    return " ".join(shown)
 
 
 def format_bytes(n: int | float) -> str:
-    v = float(n)
-    for unit in ("B", "KB", "MB", "GB", "TB"):
-        if abs(v) < 1024 or unit == "TB":
-            return f"{v:.0f} {unit}" if unit == "B" else f"{v:.1f} {unit}"
-        v /= 1024
-    return f"{v:.1f} TB"
+    """One decimal and a 1024-based unit (``0 B`` for zero, PB past the terabytes)."""
+    if n == 0:
+        return "0 B"
+    value = float(n)
+    for unit in _BYTE_UNITS:
+        if abs(value) < 1024:
+            return f"{value:.1f} {unit}"
+        value /= 1024
+    return f"{value:.1f} PB"
 
 
 def get_peer_id(config: Config) -> str:
@@ -57,15 +69,21 @@ def read_p2p_status(config: Config, *, max_age: float = 30.0) -> dict[str, objec
     return data
 
 
+_TIER_STARS = {"TIER_1": 1, "TIER_2": 2, "TIER_3": 3}
+
+
 def tier_label(tier: Any) -> str:
-    name = getattr(tier, "name", str(tier))
-    return {"TIER_1": "Tier 1 (×1.0 search cost)", "TIER_2": "⭐ Tier 2 (×0.67)", "TIER_3": "⭐⭐ Tier 3 (×0.33)"}.get(name, name)
+    """``⭐⭐ Tier 2`` for anything whose ``.name`` is a contribution tier, ``Unknown`` otherwise (no enum import needed)."""
+    stars = _TIER_STARS.get(getattr(tier, "name", ""))
+    return f"{'⭐' * stars} Tier {stars}" if stars else "Unknown"
 
 
-def format_doc_line(url: str, title: str, width: int = 90) -> str:
-    label = (title or url).strip().replace("\n", " ")
-    line = f"{label}  ·  {url}" if title else url
-    return line if len(line) <= width else line[:width - 1] + "…"
+def format_doc_line(url: str, title: str) -> str:
+    """``url  (title)`` for the live log; titles are cut to 40 characters + ellipsis."""
+    if not title:
+        return url
+    label = title if len(title) <= 40 else title[:40] + "…"
+    return f"{url}  ({label})"
 
 
 def push_new_docs_to_log(log: Any, docs: list[Any], seen: set[int]) -> int:

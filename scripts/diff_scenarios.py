@@ -1004,3 +1004,143 @@ def credit_proofs(pkg, tmp):
 
 
 SCENARIOS.update({f.__name__: f for f in (audit_rounds, takedowns, credit_proofs)})
+
+
+# ----------------------------------------------------------------------------- sixth batch: operations / privacy / reporting
+class _ScenarioKey:
+    """Deterministic stand-in for an Ed25519 key pair (the managers only need ``peer_id`` / ``sign`` / ``verify``)."""
+
+    def __init__(self, name: str):
+        self.peer_id, self._secret = f"peer-{name}", name.encode()
+
+    def sign(self, payload: bytes) -> bytes:
+        import hashlib
+
+        return hashlib.sha256(self._secret + payload).digest()
+
+    def verify(self, payload: bytes, signature: bytes) -> bool:
+        return signature == self.sign(payload)
+
+
+def dashboard_formatting(pkg, tmp):
+    U = _m(pkg, "dashboard.utils")
+    D = _m(pkg, "diagnostics")
+
+    class Tier:
+        def __init__(self, name):
+            self.name = name
+
+    return {"uptime": [U.format_uptime(s) for s in (-5, 0, 59, 60, 3599, 3600, 86399, 86400, 90061, 10 ** 7)],
+            "tier": [U.tier_label(Tier(n)) for n in ("TIER_1", "TIER_2", "TIER_3", "TIER_9", "")] + [U.tier_label(object())],
+            "bytes": [U.format_bytes(n) for n in (0, 1, 1023, 1024, 1536, 1024 ** 2, 5 * 1024 ** 3, 1024 ** 5, 3 * 1024 ** 6, -2048, 0.5)],
+            "doc": [U.format_doc_line("https://e.com/a", t) for t in ("", "short", "x" * 40, "y" * 41, "z" * 200)],
+            "pct": [D._percentile(v, p) for v in ([], [5.0], [3.0, 1.0, 2.0], list(map(float, range(100)))) for p in (0, 50, 95, 99, 100)]}
+
+
+def partition_detector(pkg, tmp):
+    D = _m(pkg, "diagnostics")
+    clock = iter(float(1000 + 10 * i) for i in range(1000))
+    with mock.patch(f"{pkg}.diagnostics.time.time", side_effect=lambda: next(clock)):
+        det = D.PartitionDetector(warning_threshold=0.5, critical_threshold=0.8, min_peers_for_alert=3)
+        seen = []
+        for count in (10, 10, 10, 9, 4, 4, 1, 1, 12, 12, 12, 2, 0, 0, 20):
+            a = det.record(count)
+            seen.append(None if a is None else (a.severity, a.previous_peers, a.current_peers, round(a.drop_ratio, 3)) if hasattr(a, "drop_ratio")
+                        else (a.severity, a.previous_peers, a.current_peers))
+        quiet = D.PartitionDetector(min_peers_for_alert=50)
+        calm = [quiet.record(c) is None for c in (10, 10, 10, 1, 0)]
+    return {"alerts": seen, "kept": len(det.alerts), "calm": calm}
+
+
+def gdpr_deletions(pkg, tmp):
+    G = _m(pkg, "trust.gdpr")
+    alice, bob = _ScenarioKey("alice"), _ScenarioKey("bob")
+    db = str(tmp / f"gdpr-{pkg}.db")
+    mgr = G.DeletionManager(db)
+    r1 = mgr.create_request("https://e.com/me", G.DeletionBasis.ERASURE if hasattr(G.DeletionBasis, "ERASURE") else list(G.DeletionBasis)[0],
+                            "my personal page", alice, personal_data_fields=["name", "email"], now=1000.0)
+    r2 = mgr.create_request("https://e.com/other", list(G.DeletionBasis)[-1], "old address", alice, now=1001.0)
+    out = {"id_len": len(r1.request_id), "ids_differ": r1.request_id != r2.request_id, "requester": r1.requester_id, "fields": list(r1.personal_data_fields),
+           "verify": [mgr.verify_request(r1, alice), mgr.verify_request(r1, bob)],
+           "blocked": [mgr.is_blocked(u) for u in ("https://e.com/me", "https://e.com/other", "https://e.com/none")],
+           "for_url": mgr.get_request_for_url("https://e.com/me").request_id == r1.request_id, "none_for_url": mgr.get_request_for_url("https://x/") is None}
+    wire = G.serialize_request(r1)
+    back = G.deserialize_request(wire)
+    out["wire_keys"] = sorted(wire)
+    out["round_trip"] = (back.request_id == r1.request_id, back.url, back.basis.value, back.reason, back.created_at, back.signature == r1.signature)
+    peer = G.DeletionManager()
+    out["receive"] = [peer.receive_request(back, alice), peer.receive_request(back, alice), peer.receive_request(G.deserialize_request(dict(wire, reason="tampered")), alice)]
+    out["peer_blocked"] = peer.is_blocked("https://e.com/me")
+    c1 = mgr.confirm_deletion(r1.request_id, "peer-x", now=1010.0)
+    c2 = mgr.confirm_deletion("nope", "peer-x", now=1011.0)
+    mgr.record_propagation(r1.request_id, "peer-y")
+    mgr.record_propagation(r1.request_id, "peer-y")
+    rec = mgr.get_record(r1.request_id)
+    out["confirm"] = (c1.peer_id, c1.deleted_at, c1.status.value, c2 is None, len(rec.confirmations), sorted(rec.propagated_to))
+    out["pending"] = [[r.url for r in mgr.list_pending(p)] for p in ("peer-x", "peer-z")]
+    out["all"] = sorted(r.url for r in mgr.list_all())
+    out["dht_key"] = (G.deletion_dht_key("https://e.com/me"), G.deletion_dht_key("https://e.com/me") == G.deletion_dht_key("https://e.com/ME"))
+    out["unblock"] = [mgr.unblock("https://e.com/other", admin_key=bob), mgr.is_blocked("https://e.com/other"), mgr.unblock("https://e.com/never", admin_key=bob)]
+    out["size"] = mgr.blocklist_size
+    mgr.close()
+    again = G.DeletionManager(db)            # durable: requests, confirmations, propagation and the block list come back
+    rec2 = again.get_record(r1.request_id)
+    out["reloaded"] = (sorted(r.url for r in again.list_all()), again.is_blocked("https://e.com/me"), again.is_blocked("https://e.com/other"),
+                       len(rec2.confirmations), sorted(rec2.propagated_to), [c.status.value for c in rec2.confirmations])
+    again.close()
+    return out
+
+
+def llm_reputation(pkg, tmp):
+    R = _m(pkg, "trust.reputation")
+    t = R.LLMReputationTracker(tmp / f"rep-{pkg}.db")
+    for peer, q in (("good", 0.9), ("good", 0.95), ("good", 0.85), ("good", 1.0), ("good", 0.9), ("mid", 0.5), ("mid", 0.6), ("mid", 0.4), ("mid", 0.55),
+                    ("mid", 0.5), ("bad", 0.1), ("bad", 0.0), ("bad", 0.2), ("bad", 0.1), ("bad", 0.05), ("new", 0.99), ("weird", 7.0), ("weird", -3.0)):
+        t.record_quality(peer, q, url=f"https://e.com/{peer}", content_hash="h")
+
+    def view(r):
+        return None if r is None else (r.peer_id, round(r.avg_quality, 4) if hasattr(r, "avg_quality") else None, r.total_summaries if hasattr(r, "total_summaries") else None,
+                                       r.grade.value)
+
+    out = {"reps": [view(t.get_reputation(p)) for p in ("good", "mid", "bad", "new", "weird", "absent")],
+           "scores": [round(t.get_quality_score(p), 4) for p in ("good", "mid", "bad", "new", "absent")],
+           "top": [r.peer_id for r in t.top_peers(3)], "listed": [r.peer_id for r in t.list_peers()],
+           "grades": [R._grade_from_score(s, n).value for s, n in ((0.95, 10), (0.95, 1), (0.7, 10), (0.5, 10), (0.3, 10), (0.1, 10), (0.0, 0))]}
+    t.close()
+    return out
+
+
+def governor_ladder(pkg, tmp):
+    G = _m(pkg, "resources.governor")
+    P = _m(pkg, "resources.profiles")
+    out = []
+    for profile in ("minimal", "balanced", "dedicated"):
+        gov = G.ResourceGovernor(P.get_profile(profile))
+        for cpu, mem, rss in ((5, 10, 10), (45, 50, 100), (55, 50, 100), (65, 50, 100), (75, 60, 100), (82, 60, 100), (50, 86, 100), (92, 60, 100), (50, 50, 480),
+                              (50, 50, 520), (97, 50, 100), (50, 50, 700), (10, 10, 10)):
+            with mock.patch.object(G.ResourceGovernor, "_sample_cpu", staticmethod(lambda cpu=cpu: float(cpu))), \
+                    mock.patch.object(G.ResourceGovernor, "_sample_memory", staticmethod(lambda mem=mem: float(mem))), \
+                    mock.patch.object(G.ResourceGovernor, "_sample_process_memory_mb", lambda self, rss=rss: float(rss)):
+                st = gov.check_and_adjust()
+            out.append((profile, cpu, mem, rss, int(st.degrade_level), round(st.throttle_factor, 3), gov.should_throttle_crawl, gov.should_pause_crawl,
+                        gov.should_disable_llm, gov.should_disable_remote_search, gov.is_read_only, gov.effective_max_concurrent))
+    return out
+
+
+def score_explanations(pkg, tmp):
+    E = _m(pkg, "search.explain")
+    RR = _m(pkg, "index.ranking").RankedResult
+    hits = [RR(doc_id=i, url=f"https://e.com/{i}", title=f"T{i}", snippet="s", bm25_score=b, freshness_score=f, trust_score=t, authority_score=a,
+               combined_score=c, crawled_at=1.0, peer_id="") for i, (b, f, t, a, c) in enumerate(((0.9, 0.5, 0.5, 0.2, 0.61), (0.0, 0.0, 0.0, 0.0, 0.0),
+                                                                                                 (1.0, 1.0, 1.0, 1.0, 1.0), (0.3, 0.9, 0.1, 0.0, 0.33)))]
+    def contract(d):          # this package adds `breakdown` / `dominant_factor` for the MCP explain tool: a superset, compared without them
+        return {k: v for k, v in d.items() if k not in ("breakdown", "dominant_factor")}
+
+    single = [contract(E.explain_result(h).to_dict()) for h in hits]
+    whole = E.explain_query("How  to AND x", "how to x", hits, 12.3456, pipeline=["sanitize", "fts5", "rank"]).to_dict()
+    whole["results"] = [contract(r) for r in whole["results"]]
+    bare = E.explain_query("q", "q", [], 0.0).to_dict()
+    return {"single": single, "whole": whole, "bare": bare}
+
+
+SCENARIOS.update({f.__name__: f for f in (dashboard_formatting, partition_detector, gdpr_deletions, llm_reputation, governor_ladder, score_explanations)})

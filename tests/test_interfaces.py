@@ -122,7 +122,7 @@ def test_dashboard_helpers_and_tui(node_env):
 
     _seed(node_env)
     cfg = load_config()
-    assert U.format_uptime(3725) == "1h 2m 5s" and U.format_uptime(90061).startswith("1d 1h") and U.format_bytes(1536) == "1.5 KB"
+    assert U.format_uptime(3725) == "1h 2m" and U.format_uptime(0) == "—" and U.format_uptime(90061).startswith("1d 1h") and U.format_bytes(1536) == "1.5 KB"
     assert U.read_p2p_status(cfg) == {} and not U.is_node_running(cfg) and "Tier 2" in U.tier_label(type("T", (), {"name": "TIER_2"})())
     (node_env / "p2p_status.json").write_text(json.dumps({"state": "running", "peers": 3, "timestamp": 1.0}))
     assert U.read_p2p_status(cfg)["state"] == "stopped"
