@@ -1144,3 +1144,93 @@ def score_explanations(pkg, tmp):
 
 
 SCENARIOS.update({f.__name__: f for f in (dashboard_formatting, partition_detector, gdpr_deletions, llm_reputation, governor_ladder, score_explanations)})
+
+
+# ----------------------------------------------------------------------------- seventh batch: wire envelopes, topology helpers, seeds
+def signed_envelopes(pkg, tmp):
+    """Both packages sign with a real Ed25519 key; canonical bytes, the wire dict and every rejection reason must agree, and an
+    envelope signed by one package must verify in the other (the caller compares ``cross``)."""
+    A = _m(pkg, "p2p.message_auth")
+    from cryptography.hazmat.primitives.asymmetric.ed25519 import Ed25519PrivateKey
+    from cryptography.hazmat.primitives.serialization import Encoding, PublicFormat
+
+    class Key:
+        def __init__(self, seed: bytes, peer_id: str):
+            self._k, self.peer_id = Ed25519PrivateKey.from_private_bytes(seed), peer_id
+
+        def sign(self, data: bytes) -> bytes:
+            return self._k.sign(data)
+
+        def public_key_bytes(self) -> bytes:
+            return self._k.public_key().public_bytes(Encoding.Raw, PublicFormat.Raw)
+
+    alice, mallory = Key(b"a" * 32, "12D3KooWAlice"), Key(b"m" * 32, "12D3KooWMallory")
+    out = {"canonical": [A._canonical_bytes(p, n, t, b).hex() for p, n, t, b in (("peer", 0, 0.0, b""), ("12D3KooWAlice", 7, 1700000000.123456789, b"\x01\x02"),
+                                                                                   ("p|q", 2 ** 40, 1.5, b"|"))]}
+    counter = A.NonceCounter()
+    env = [A.sign_envelope(bytes([i]) * 3, alice, counter, now=1000.0 + i) for i in range(4)]
+    out["nonces"] = [e.nonce for e in env] + [counter.current]
+    wire = A.envelope_to_dict(env[0])
+    out["wire"] = {k: (v.hex() if isinstance(v, bytes) else v) for k, v in sorted(wire.items())}
+    back = A.envelope_from_dict(wire)
+    out["round_trip"] = (back.payload, back.peer_id, back.nonce, back.timestamp, back.signature == env[0].signature)
+    reg, seen = A.PeerKeyRegistry(), A.NonceTracker()
+    reg.register(alice.peer_id, alice.public_key_bytes())
+
+    def attempt(e, **kw):
+        try:
+            return ("ok", A.verify_envelope(e, reg, seen, **kw).hex())
+        except A.VerificationError as exc:
+            return ("rejected", str(exc))
+
+    import dataclasses
+
+    forged = dataclasses.replace(env[2], payload=b"evil")
+    stranger = A.sign_envelope(b"x", mallory, A.NonceCounter(), now=1000.0)
+    # (an OLDER nonce arriving late is a deliberate difference: the reference demands strictly increasing nonces, this package
+    #  accepts anything inside a sliding window that it has not seen -- tests/test_p2p_* cover that; not compared here)
+    out["verify"] = [attempt(env[0], now=1001.0), attempt(env[1], now=1001.0), attempt(env[1], now=1001.0), attempt(forged, now=1002.0),
+                     attempt(env[3], now=1003.0 + 10_000), attempt(stranger, now=1000.0), attempt(env[3], now=1003.0, is_isolated_fn=lambda p: True),
+                     attempt(env[3], now=1003.0)]
+    out["highest"] = (seen.highest(alice.peer_id), seen.highest("nobody"), alice.peer_id in reg, len(reg))
+    reg.remove(alice.peer_id)
+    out["after_remove"] = (alice.peer_id in reg, reg.get(alice.peer_id))
+    return out
+
+
+def topology_helpers(pkg, tmp):
+    N = _m(pkg, "p2p.network_ext")
+    G = N.GeoLocation
+    seoul, tokyo, paris, origin = G("KR", "", "Seoul", 37.5665, 126.978), G("JP", "", "Tokyo", 35.6762, 139.6503), G("FR", "", "Paris", 48.8566, 2.3522), G()
+    out = {"km": [round(N.estimate_geo_distance(a, b), 3) for a, b in ((seoul, tokyo), (tokyo, seoul), (seoul, paris), (seoul, seoul), (origin, paris))],
+           "near": [(p, round(d, 1)) for p, d in N.sort_peers_by_proximity([("paris", paris), ("tokyo", tokyo), ("here", seoul), ("null", origin)], seoul)],
+           "relay": [N.select_relay(list(r)) for r in ([], [("a", 50.0)], [("slow", 200.0), ("fast", 20.0), ("mid", 90.0)], [("x", 5.0), ("y", 5.0)])]}
+    det = N.PartitionDetector(threshold=0.5)
+    steps = []
+    with mock.patch(f"{pkg}.p2p.network_ext.time.time", return_value=123.0):
+        # (one uninterrupted partition: this package resets the attempt counter once the partition heals, the reference never does)
+        for reachable, total in ((10, 10), (5, 10), (0, 0), (4, 10), (1, 10), (1, 10), (1, 10), (1, 10), (1, 10), (9, 10)):
+            st = det.check(reachable, total)
+            steps.append((st.is_partitioned, st.reachable_peers, st.expected_peers, det.get_recovery_actions()))
+    out["partition"] = steps
+    return out
+
+
+def seeds_and_identity(pkg, tmp):
+    S = _m(pkg, "crawler.seeds")
+    I = _m(pkg, "credits.github_identity")
+    d = tmp / f"seeds-{pkg}"
+    d.mkdir()
+    cats = list(S.CATEGORIES)
+    (d / f"{cats[0]}.txt").write_text("# comment\nhttps://a.example/\n\n  https://b.example/x  \nftp://nope.example\nnot a url\nhttp://c.example\n")
+    (d / f"{cats[1]}.txt").write_text("https://z.example/\n#https://commented.example\n")
+    (d / "zz-extra.txt").write_text("https://extra.example/\n")
+    (d / "ignored.md").write_text("https://md.example/\n")
+    return {"categories": sorted(cats), "one": S.load_seeds(cats[0], d), "two": S.load_seeds(cats[1], d), "missing_file": S.load_seeds(cats[2], d) if len(cats) > 2 else [],
+            "unknown": S.load_seeds("no-such-category", d), "all": sorted(S.load_seeds(None, d)), "no_dir": S.load_seeds(None, d / "absent"),
+            "bundled_nonempty": len(S.load_seeds()) > 0,
+            "emails": [I.is_valid_email(e) for e in ("a@b.co", "first.last+tag@sub.example.org", "no-at.example", "a@b", "@b.co", "a b@c.de", "", "a@b.c")],
+            "msg": [I.format_startup_message("me@example.org"), I.format_startup_message(None), I.format_startup_message("")]}
+
+
+SCENARIOS.update({f.__name__: f for f in (signed_envelopes, topology_helpers, seeds_and_identity)})
