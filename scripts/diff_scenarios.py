@@ -1234,3 +1234,121 @@ def seeds_and_identity(pkg, tmp):
 
 
 SCENARIOS.update({f.__name__: f for f in (signed_envelopes, topology_helpers, seeds_and_identity)})
+
+
+# ----------------------------------------------------------------------------- eighth batch: LLM glue, WET import, preflight
+class _ScriptedLLM:
+    """An LLM backend that answers from a script and records the prompts it was given."""
+
+    def __init__(self, pkg, answers):
+        E = _m(pkg, "summarizer.engine")
+        self._E, self.answers, self.prompts = E, list(answers), []
+
+    async def generate(self, prompt: str, *, max_tokens: int = 512) -> str:
+        self.prompts.append((prompt, max_tokens))
+        a = self.answers.pop(0)
+        if isinstance(a, Exception):
+            raise a
+        return a
+
+    async def is_available(self) -> bool:
+        return True
+
+    async def model_info(self):
+        return self._E.ModelInfo(name="scripted", runtime=self._E.LLMRuntime.OLLAMA, parameter_count="0", quantization="none", available=True) \
+            if "parameter_count" in self._E.ModelInfo.__dataclass_fields__ else self._E.ModelInfo(**{f: ("scripted" if f == "name" else self._E.LLMRuntime.OLLAMA if f == "runtime" else None)
+                                                                                                  for f in self._E.ModelInfo.__dataclass_fields__})
+
+
+def llm_rerank_and_summaries(pkg, tmp):
+    R = _m(pkg, "search.reranker")
+    E = _m(pkg, "summarizer.engine")
+    RR = _m(pkg, "index.ranking").RankedResult
+    hits = [RR(doc_id=i, url=f"https://e.com/{i}", title=f"Title {i}", snippet=("snippet %d " % i) * 30, bm25_score=0.5, freshness_score=0.5, trust_score=0.5,
+               authority_score=0.5, combined_score=1.0 - i / 10, crawled_at=1.0, peer_id="") for i in range(6)]
+    out = {"block": R._build_results_block(hits[:3], max_snippet=40),
+           "parse": [R._parse_ranking_response(t, 4) for t in ("3,1,2,4", "[2, 4, 1, 3]", "Ranking: 4 > 2 > 1 > 3", "1, 1, 2", "2,9,1", "", "no digits here",
+                                                                "3\n1\n2\n4", "1. 4\n2. 3", "4,3")]}
+
+    async def go():
+        orders = []
+        for answer, kw in (("3,1,2", dict(max_candidates=3)), ("2,1", dict(max_candidates=3)), ("garbage", dict(max_candidates=3)), (RuntimeError("down"), dict(max_candidates=3)),
+                           ("4,3,2,1", dict(max_candidates=4, top_n=2)), ("1", dict(max_candidates=1))):
+            llm = _ScriptedLLM(pkg, [answer])
+            res = await R.rerank_with_llm("what is tcgen05", hits, llm, **kw)
+            orders.append(([h.doc_id for h in res], len(llm.prompts), llm.prompts[0][1] if llm.prompts else None))
+        empty = await R.rerank_with_llm("q", [], _ScriptedLLM(pkg, []))
+        llm = _ScriptedLLM(pkg, ["  A short summary.  ", "", RuntimeError("boom")])
+        eng = E.SummarizationEngine(llm)
+        s1 = await eng.summarize("https://e.com/doc", "Doc title", "body text " * 2000, max_tokens=64, max_input_chars=500)
+        s2 = await eng.summarize("https://e.com/doc2", "", "tiny", max_tokens=32)
+        try:
+            s3 = await eng.summarize("https://e.com/doc3", "T", "text")
+            third = ("ok", s3.summary)
+        except Exception as exc:  # noqa: BLE001
+            third = ("raised", type(exc).__name__)
+        return orders, [h.doc_id for h in empty], (s1.url, s1.summary, s1.model, str(s1.runtime), s1.content_hash, s1.token_count), \
+            (s2.summary, s2.content_hash, s2.token_count), third, [(len(p), mt, p[:60], "body text body text" in p) for p, mt in llm.prompts], \
+            [E._estimate_tokens(t) for t in ("", "one", "four words right here", "x" * 400)]
+
+    out["orders"], out["empty"], out["summary1"], out["summary2"], out["summary3"], out["prompts"], out["tokens"] = asyncio.run(go())
+    return out
+
+
+WET = ("WARC/1.0\r\nWARC-Type: warcinfo\r\nContent-Length: 10\r\n\r\nsoftware x\r\n\r\n"
+       "WARC/1.0\r\nWARC-Type: conversion\r\nWARC-Target-URI: https://a.example/one\r\nWARC-Date: 2024-01-02T03:04:05Z\r\nContent-Length: 400\r\n\r\n" + "alpha beta gamma " * 30 + "\r\n\r\n"
+       "WARC/1.0\r\nWARC-Type: conversion\r\nWARC-Target-URI: https://a.example/short\r\nWARC-Date: 2024-01-02T03:04:06Z\r\nContent-Length: 5\r\n\r\ntiny\r\n\r\n"
+       "WARC/1.0\r\nWARC-Type: conversion\r\nWARC-Date: 2024-01-02T03:04:07Z\r\nContent-Length: 20\r\n\r\nno target uri here\r\n\r\n"
+       "WARC/1.0\r\nWARC-Type: conversion\r\nWARC-Target-URI: https://b.example/two\r\nContent-Length: 300\r\n\r\n" + "delta epsilon zeta " * 20 + "\r\n\r\n"
+       "WARC/1.0\r\nWARC-Type: conversion\r\nWARC-Target-URI: https://a.example/one\r\nWARC-Date: 2024-02-02T00:00:00Z\r\nContent-Length: 400\r\n\r\n" + "alpha beta gamma " * 30 + "\r\n\r\n")
+
+
+def wet_import(pkg, tmp):
+    C = _m(pkg, "index.commoncrawl")
+    LS = _m(pkg, "index.local_store").LocalStore
+    DD = _m(pkg, "crawler.dedup").DeduplicatorDB
+    recs = C.parse_wet_content(WET)
+    out = {"records": [(r.url, len(r.text), r.date, r.content_length) for r in recs], "none": C.parse_wet_content(""), "junk": C.parse_wet_content("not a warc file at all")}
+    wet_path = tmp / f"sample-{pkg}.wet"
+    wet_path.write_text(WET)
+    import gzip
+
+    gz_path = tmp / f"sample-{pkg}.wet.gz"
+    gz_path.write_bytes(gzip.compress(WET.encode()))
+    urls = tmp / f"urls-{pkg}.txt"
+    urls.write_text("https://a.example/one\n# c\nhttps://new.example/\n\nnot-a-url\nhttps://new.example/\nhttps://third.example/p?utm_source=x\n")
+    store, dedup = LS(tmp / f"cc-{pkg}.db"), DD(str(tmp / f"cc-dedup-{pkg}.db"))
+
+    async def go():
+        imp = C.CommonCrawlImporter(store, dedup)
+        a = await imp.import_wet_file(str(wet_path))
+        b = await imp.import_wet_file(str(gz_path))                  # everything is a duplicate now
+        c = await imp.import_url_list(str(urls), max_urls=10)
+        d = await imp.import_url_list(str(urls), max_urls=10)
+        try:
+            await imp.import_wet_file(str(tmp / "missing.wet"))
+            missing = "no error"
+        except Exception as exc:  # noqa: BLE001
+            missing = type(exc).__name__
+        return [(s.total_records, s.imported, s.skipped_duplicate, s.skipped_too_short, s.skipped_error) for s in (a, b, c, d)], missing
+
+    out["stats"], out["missing"] = asyncio.run(go())
+    out["stored"] = [store.get_document_by_url(u) is not None for u in ("https://a.example/one", "https://b.example/two", "https://a.example/short",
+                                                                          "https://new.example/")]
+    out["count"] = store.get_stats()["document_count"]
+    store.close()
+    dedup.close()
+    return out
+
+
+def preflight_checks(pkg, tmp):
+    P = _m(pkg, "resources.preflight")
+    out = {}
+    for free in (10_000.0, 1_500.0, 600.0, 450.0, 250.0, 150.0, 0.0):
+        with mock.patch(f"{pkg}.resources.preflight.get_disk_free_mb", return_value=free):
+            out[str(free)] = ([(i.severity.value, i.check) for i in P.check_disk_space(tmp)], P.is_disk_critically_low(tmp))
+    out["real_positive"] = P.get_disk_free_mb(tmp) > 0
+    return out
+
+
+SCENARIOS.update({f.__name__: f for f in (llm_rerank_and_summaries, wet_import, preflight_checks)})
