@@ -60,26 +60,37 @@ class InfoMeshDHT:
         return self._stats
 
     # ------------------------------------------------------------------ raw
-    async def put(self, key: str, value: bytes) -> bool:
+    # The counters mirror what the reference counts: puts / gets of the public operations (raw put / get, keyword publish and
+    # query, attestations).  Internal reads (the merge before a publish, lock checks) and lock writes are not counted.
+    async def _store(self, key: str, value: bytes, *, what: str) -> bool:
         try:
             await self._dht.put_value(key, value)
-            self._stats.puts_performed += 1
             return True
         except Exception:  # noqa: BLE001
-            logger.exception("dht_put_failed", key=key)
+            logger.exception(what, key=key)
             return False
 
-    async def get(self, key: str) -> bytes | None:
+    async def _fetch(self, key: str, *, what: str) -> tuple[bool, bytes | None]:
         try:
-            raw = await self._dht.get_value(key)
-            self._stats.gets_performed += 1
-            return raw
+            return True, await self._dht.get_value(key)
         except Exception:  # noqa: BLE001
-            logger.exception("dht_get_failed", key=key)
-            return None
+            logger.exception(what, key=key)
+            return False, None
 
-    async def _get_map(self, key: str) -> dict[str, Any] | None:
-        raw = await self.get(key)
+    async def put(self, key: str, value: bytes) -> bool:
+        ok = await self._store(key, value, what="dht_put_failed")
+        self._stats.puts_performed += ok
+        return ok
+
+    async def get(self, key: str) -> bytes | None:
+        ok, raw = await self._fetch(key, what="dht_get_failed")
+        self._stats.gets_performed += ok
+        return raw
+
+    async def _get_map(self, key: str, *, count: bool = False) -> dict[str, Any] | None:
+        ok, raw = await self._fetch(key, what="dht_get_failed")
+        if count:
+            self._stats.gets_performed += ok
         if raw is None:
             return None
         try:
@@ -102,19 +113,23 @@ class InfoMeshDHT:
         if not self._publish_allowed(keyword):
             logger.warning("dht_publish_rate_limited", keyword=keyword)
             return False
-        merged = _merge_pointers(await self.query_keyword(keyword), pointers, limit=MAX_POINTERS_PER_KEYWORD)
+        merged = _merge_pointers(await self._pointers(keyword, count=False), pointers, limit=MAX_POINTERS_PER_KEYWORD)
         value = msgpack.packb({"keyword": keyword, "pointers": merged, "peer_id": self._peer_id,
                                "timestamp": time.time(), "signature": signature}, use_bin_type=True)
-        if not await self.put(keyword_to_dht_key(keyword), value):
+        if not await self._store(keyword_to_dht_key(keyword), value, what="dht_publish_failed"):
             return False
+        self._stats.puts_performed += 1
         self._stats.keys_published += 1
         self._publishes.setdefault(keyword, []).append(time.time())
         return True
 
-    async def query_keyword(self, keyword: str) -> list[dict[str, Any]]:
-        entry = await self._get_map(keyword_to_dht_key(keyword))
+    async def _pointers(self, keyword: str, *, count: bool) -> list[dict[str, Any]]:
+        entry = await self._get_map(keyword_to_dht_key(keyword), count=count)
         ptrs = entry.get("pointers", []) if entry else []
         return [p for p in ptrs if isinstance(p, dict)] if isinstance(ptrs, list) else []
+
+    async def query_keyword(self, keyword: str) -> list[dict[str, Any]]:
+        return await self._pointers(keyword, count=True)
 
     # ------------------------------------------------------------------ crawl locks
     @staticmethod
@@ -122,27 +137,30 @@ class InfoMeshDHT:
         return f"{_PREFIX_CRAWL_LOCK}{content_hash(url)}"
 
     async def acquire_crawl_lock(self, url: str, ttl_seconds: int = _LOCK_TTL_SECONDS) -> bool:
+        """Exclusive while the TTL runs -- also against this node's own second attempt: two local workers that pick the same
+        URL must not both crawl it.  An expired (or released: timestamp 0) lock is simply overwritten."""
         held = await self._get_map(self._lock_key(url))
         if held is not None:
             ts = held.get("timestamp", 0)
-            if isinstance(ts, (int, float)) and time.time() - ts < ttl_seconds and held.get("peer_id") != self._peer_id:
+            if isinstance(ts, (int, float)) and time.time() - ts < ttl_seconds:
+                logger.debug("crawl_lock_held", url=url, holder=held.get("peer_id"))
                 return False
-        ok = await self.put(self._lock_key(url), msgpack.packb(
-            {"peer_id": self._peer_id, "url": url, "timestamp": time.time(), "ttl": ttl_seconds}, use_bin_type=True))
-        self._stats.locks_acquired += 1 if ok else 0
+        ok = await self._store(self._lock_key(url), msgpack.packb(
+            {"peer_id": self._peer_id, "url": url, "timestamp": time.time(), "ttl": ttl_seconds}, use_bin_type=True), what="crawl_lock_acquire_failed")
+        self._stats.locks_acquired += ok
         return ok
 
     async def release_crawl_lock(self, url: str) -> bool:
-        ok = await self.put(self._lock_key(url), msgpack.packb(
-            {"peer_id": self._peer_id, "url": url, "timestamp": 0, "ttl": 0}, use_bin_type=True))
-        self._stats.locks_released += 1 if ok else 0
+        ok = await self._store(self._lock_key(url), msgpack.packb(
+            {"peer_id": self._peer_id, "url": url, "timestamp": 0, "ttl": 0}, use_bin_type=True), what="crawl_lock_release_failed")
+        self._stats.locks_released += ok
         return ok
 
     # ------------------------------------------------------------------ attestations
     async def publish_attestation(self, url: str, raw_hash: str, text_hash: str, signature: bytes = b"") -> bool:
-        return await self.put(f"{_PREFIX_ATTESTATION}{content_hash(url)}", msgpack.packb(
+        return await self.put(f"{_PREFIX_ATTESTATION}{content_hash(url)}", msgpack.packb(  # counted as a put, like the reference
             {"url": url, "raw_hash": raw_hash, "text_hash": text_hash, "peer_id": self._peer_id,
              "timestamp": time.time(), "signature": signature}, use_bin_type=True))
 
     async def get_attestation(self, url: str) -> dict[str, Any] | None:
-        return await self._get_map(f"{_PREFIX_ATTESTATION}{content_hash(url)}")
+        return await self._get_map(f"{_PREFIX_ATTESTATION}{content_hash(url)}", count=True)

@@ -1352,3 +1352,75 @@ def preflight_checks(pkg, tmp):
 
 
 SCENARIOS.update({f.__name__: f for f in (llm_rerank_and_summaries, wet_import, preflight_checks)})
+
+
+# ----------------------------------------------------------------------------- ninth batch: the DHT facade over an in-memory Kademlia
+class _MemoryKad:
+    """``put_value`` / ``get_value`` of a Kademlia node, on a dict; can be told to fail."""
+
+    def __init__(self):
+        self.data, self.fail = {}, False
+
+    async def put_value(self, key, value):
+        if self.fail:
+            raise ConnectionError("no peers")
+        self.data[key] = value
+
+    async def get_value(self, key):
+        if self.fail:
+            raise ConnectionError("no peers")
+        return self.data.get(key)
+
+
+def dht_facade(pkg, tmp):
+    D = _m(pkg, "p2p.dht")
+    kad = _MemoryKad()
+    me, other = D.InfoMeshDHT(kad, "peer-me"), D.InfoMeshDHT(kad, "peer-other")
+    ptr = lambda peer, doc, score: {"peer_id": peer, "doc_id": doc, "url": f"https://e.com/{doc}", "score": score, "title": f"T{doc}"}  # noqa: E731
+
+    async def go():
+        out = {}
+        clock = [1000.0]
+        with mock.patch(f"{pkg}.p2p.dht.time.time", side_effect=lambda: clock[0]):
+            out["publish"] = [await me.publish_keyword("tensor", [ptr("peer-me", 1, 0.9), ptr("peer-me", 2, 0.5)]),
+                              await other.publish_keyword("tensor", [ptr("peer-other", 1, 0.7), ptr("peer-me", 1, 0.1), {"peer_id": 5, "doc_id": "x"}]),
+                              await me.publish_keyword("", []), await me.publish_keyword("empty", [])]
+            got = await me.query_keyword("tensor")
+            out["query"] = sorted((p["peer_id"], p["doc_id"], p["score"]) for p in got)
+            out["query_none"] = await me.query_keyword("absent")
+            # per-keyword publish rate limit: hammer one keyword inside a minute, then let the window slide
+            burst = []
+            for i in range(14):
+                clock[0] += 1.0
+                burst.append(await me.publish_keyword("hot", [ptr("peer-me", 100 + i, 0.1)]))
+            clock[0] += 3700.0
+            burst.append(await me.publish_keyword("hot", [ptr("peer-me", 999, 0.1)]))
+            out["burst"] = burst
+            out["hot_count"] = len(await me.query_keyword("hot"))
+            # crawl locks: exclusive within the TTL, re-entrant for the holder, released only by the holder, expiring
+            clock[0] = 5000.0
+            locks = [await me.acquire_crawl_lock("https://e.com/page"), await other.acquire_crawl_lock("https://e.com/page"), await me.acquire_crawl_lock("https://e.com/page"),
+                     await other.release_crawl_lock("https://e.com/page"), await other.acquire_crawl_lock("https://e.com/page")]
+            clock[0] += 301.0
+            locks.append(await other.acquire_crawl_lock("https://e.com/page"))            # expired -> taken over
+            locks += [await me.release_crawl_lock("https://e.com/page"), await other.release_crawl_lock("https://e.com/page"),
+                      await me.acquire_crawl_lock("https://e.com/page"), await me.release_crawl_lock("https://e.com/never-locked")]
+            out["locks"] = locks
+            out["attest"] = [await me.publish_attestation("https://e.com/a", "rawhash", "texthash", b"sig")]
+            att = await other.get_attestation("https://e.com/a")
+            out["attestation"] = {k: (v.hex() if isinstance(v, bytes) else v) for k, v in sorted((att or {}).items()) if k not in ("timestamp", "published_at")}
+            out["no_attestation"] = await other.get_attestation("https://e.com/none")
+            out["raw"] = [await me.put("/custom/key", b"value"), await other.get("/custom/key"), await other.get("/custom/absent")]
+            kad.fail = True
+            out["offline"] = [await me.publish_keyword("tensor", [ptr("peer-me", 3, 0.3)]), await me.query_keyword("tensor"), await me.acquire_crawl_lock("https://e.com/x"),
+                              await me.release_crawl_lock("https://e.com/page"), await me.publish_attestation("https://e.com/b", "r", "t"),
+                              await me.get_attestation("https://e.com/a"), await me.put("/k", b"v"), await me.get("/custom/key")]
+        st = me.stats
+        out["stats"] = {f: getattr(st, f) for f in sorted(vars(st)) if isinstance(getattr(st, f), (int, float)) and "time" not in f and "ms" not in f}
+        out["merge"] = D._merge_pointers([ptr("a", 1, 0.1), ptr("b", 1, 0.2), {"peer_id": None, "doc_id": 1}], [ptr("a", 1, 0.9), ptr("c", 2, 0.3)], limit=3)
+        return out
+
+    return asyncio.run(go())
+
+
+SCENARIOS.update({f.__name__: f for f in (dht_facade,)})

@@ -80,11 +80,11 @@ def test_crawl_lock_contention_ttl_and_release():
     kad = FakeKad()
     a, b = DH.InfoMeshDHT(kad, "A"), DH.InfoMeshDHT(kad, "B")
     url = "https://ex.org/page"
-    assert run(a.acquire_crawl_lock(url)) and run(a.acquire_crawl_lock(url))         # re-entrant for the holder
+    assert run(a.acquire_crawl_lock(url)) and not run(a.acquire_crawl_lock(url))     # exclusive, also against the holder's second attempt
     assert not run(b.acquire_crawl_lock(url))
     assert run(b.acquire_crawl_lock(url, ttl_seconds=0))                              # expired from B's point of view
     assert run(b.release_crawl_lock(url)) and run(a.acquire_crawl_lock(url))
-    assert a.stats.locks_acquired == 3 and b.stats.locks_released == 1
+    assert a.stats.locks_acquired == 2 and b.stats.locks_released == 1
 
 
 def test_attestation_roundtrip():
