@@ -303,7 +303,7 @@ def serve(seeds: str | None, role: str | None, no_crawl: bool) -> None:
                  asyncio.create_task(serve_admin_api(config, port=ADMIN_API_PORT, runtime=runtime, index_submit_receiver=ctx.index_submit_receiver))]
         if node is not None or dist_index is not None:
             tasks.append(asyncio.create_task(republish_local_index(ctx.store, p2p_node=node, distributed_index=dist_index)))
-        if config.node.role != NodeRole.SEARCH and not no_crawl:
+        if str(config.node.role).lower() != NodeRole.SEARCH and not no_crawl:
             tasks.append(asyncio.create_task(seed_and_crawl_loop(ctx, seed_category=seeds or "tech-docs")))
         else:
             log.info("waiting_mode: P2P active, crawl loop disabled")

@@ -184,7 +184,7 @@ _SECTIONS: dict[str, type] = {
     "search": SearchConfig, "gpu": GpuConfig,
 }
 
-# numeric ranges (out-of-range values fall back to the default with a warning)
+# numeric ranges (out-of-range values are clamped to the nearest bound, with a warning)
 _VALUE_CONSTRAINTS: dict[str, tuple[float, float]] = {
     "listen_port": (1, 65535), "max_concurrent": (1, 100), "politeness_delay": (0.1, 60.0),
     "urls_per_hour": (1, 10000), "pending_per_domain": (1, 1000), "upload_limit_mbps": (0.1, 1000.0),
@@ -255,13 +255,16 @@ def _default_of(f: dataclasses.Field) -> Any:
 
 
 def _validate(key: str, value: Any, default: Any) -> Any:
+    """Numbers outside their range are pulled to the nearest bound (an operator who asks for nice 25 gets 19, not the default);
+    strings outside their vocabulary -- compared case-insensitively, kept as written -- fall back to the default."""
     if key in _VALUE_CONSTRAINTS and isinstance(value, (int, float)) and not isinstance(value, bool):
         lo, hi = _VALUE_CONSTRAINTS[key]
         if not lo <= value <= hi:
-            logger.warning("config_value_out_of_range", key=key, value=value, min=lo, max=hi, using=default)
-            return default
-    if key in _ALLOWED_VALUES and isinstance(value, str) and value not in _ALLOWED_VALUES[key]:
-        logger.warning("config_value_not_allowed", key=key, value=value, using=default)
+            clamped = type(value)(min(max(value, lo), hi))
+            logger.warning("config_value_out_of_range", key=key, value=value, min=lo, max=hi, using=clamped)
+            return clamped
+    if key in _ALLOWED_VALUES and isinstance(value, str) and value.lower() not in _ALLOWED_VALUES[key]:
+        logger.warning("config_invalid_value", key=key, value=value, allowed=sorted(_ALLOWED_VALUES[key]), using=default)
         return default
     return value
 

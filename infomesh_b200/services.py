@@ -229,7 +229,7 @@ class AppContext:
         from infomesh_b200.resources.profiles import get_profile
 
         self.config = c = config or load_config()
-        role = c.node.role
+        role = str(c.node.role).lower()          # the loader keeps the value as written ("FULL" is valid)
         crawls, searches = role in (NodeRole.FULL, NodeRole.CRAWLER), role in (NodeRole.FULL, NodeRole.SEARCH)
         self.governor = ResourceGovernor(get_profile(c.resources.profile))
         if apply_os_priority:

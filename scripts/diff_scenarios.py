@@ -1424,3 +1424,130 @@ def dht_facade(pkg, tmp):
 
 
 SCENARIOS.update({f.__name__: f for f in (dht_facade,)})
+
+
+# ----------------------------------------------------------------------------- tenth batch: configuration, throttling, compression
+CONFIG_TOML = """
+[node]
+role = "search"
+log_level = "LOUD"
+listen_port = 70000
+[crawl]
+max_concurrent = 0
+politeness_delay = 0.01
+urls_per_hour = 500
+user_agent = "CustomBot/1.0"
+[network]
+upload_limit_mbps = 2000.0
+bootstrap_nodes = ["/ip4/10.0.0.1/tcp/4001/p2p/12D3KooWA", "/ip4/10.0.0.2/tcp/4001/p2p/12D3KooWB"]
+replication_factor = 5
+[index]
+fts_tokenizer = "klingon"
+[storage]
+compression_level = 99
+[resources]
+profile = "dedicated"
+cpu_nice = -5
+[dashboard]
+theme = "dracula"
+refresh_interval = 60.0
+[unknown_section]
+x = 1
+"""
+
+
+def config_loading(pkg, tmp):
+    C = _m(pkg, "config")
+    import os
+
+    path = tmp / f"config-{pkg}.toml"
+    path.write_text(CONFIG_TOML)
+    env = {"INFOMESH_CRAWL_MAX_DEPTH": "7", "INFOMESH_NODE_LISTEN_PORT": "4100", "INFOMESH_LLM_ENABLED": "yes", "INFOMESH_NETWORK_BOOTSTRAP_NODES": "/ip4/1.1.1.1/tcp/1 , ,/ip4/2.2.2.2/tcp/2",
+           "INFOMESH_STORAGE_COMPRESSION_ENABLED": "0", "INFOMESH_NODE_DATA_DIR": str(tmp / "data")}
+    with mock.patch.dict(os.environ, env, clear=False):
+        cfg = C.load_config(path)
+    plain = C.load_config(tmp / "does-not-exist.toml")
+
+    def view(c):
+        return {"role": c.node.role, "log_level": c.node.log_level, "port": c.node.listen_port, "data_dir_name": c.node.data_dir.name,
+                "max_concurrent": c.crawl.max_concurrent, "delay": c.crawl.politeness_delay, "per_hour": c.crawl.urls_per_hour, "depth": c.crawl.max_depth, "ua": c.crawl.user_agent,
+                "up": c.network.upload_limit_mbps, "boot": list(c.network.bootstrap_nodes)[:3], "repl": c.network.replication_factor, "tok": c.index.fts_tokenizer,
+                "zlevel": c.storage.compression_level, "zon": c.storage.compression_enabled, "profile": c.resources.profile, "nice": c.resources.cpu_nice,
+                "theme": c.dashboard.theme, "refresh": c.dashboard.refresh_interval, "llm": c.llm.enabled, "db_under_data": c.index.db_path.parent == c.node.data_dir}
+
+    out = {"loaded": view(cfg), "defaults": {k: v for k, v in view(plain).items() if k not in ("boot", "data_dir_name")}}
+    # out-of-range numbers are clamped, unknown enum strings fall back to the default: observed through the loader
+    probes = {}
+    for section, key, raw in (("node", "listen_port", "0"), ("node", "listen_port", "8080"), ("crawl", "politeness_delay", "100.0"), ("resources", "cpu_nice", "25"),
+                              ("node", "role", "FULL"), ("node", "role", "boss"), ("dashboard", "theme", "nord"), ("dashboard", "theme", "neon"),
+                              ("storage", "compression_level", "3"), ("llm", "enabled", "TRUE"), ("llm", "enabled", "0"), ("crawl", "max_depth", "12")):
+        with mock.patch.dict(os.environ, {f"INFOMESH_{section.upper()}_{key.upper()}": raw}, clear=False):
+            got = getattr(getattr(C.load_config(tmp / "does-not-exist.toml"), section), key)
+        probes[f"{section}.{key}={raw}"] = got
+    out["probes"] = probes
+    saved = tmp / f"saved-{pkg}" / "config.toml"
+    C.save_config(cfg, saved)
+    again = C.load_config(saved)
+    out["round_trip"] = view(again) == view(cfg)
+    out["saved_has_sections"] = {"crawl", "node", "network"} <= {line.strip("[]\n") for line in saved.read_text().splitlines() if line.startswith("[")}
+    return out
+
+
+def bandwidth_throttle(pkg, tmp):
+    T = _m(pkg, "p2p.throttle")
+    clock = [100.0]
+    slept = []
+
+    async def fake_sleep(seconds):
+        slept.append(round(seconds, 6))
+        clock[0] += seconds
+
+    async def go():
+        with mock.patch(f"{pkg}.p2p.throttle.time.monotonic", side_effect=lambda: clock[0]), mock.patch(f"{pkg}.p2p.throttle.asyncio.sleep", fake_sleep):
+            bucket = T.BandwidthBucket(8.0)                  # 1 MB/s, starts with one second of burst
+            waits = [round(await bucket.acquire(n), 6) for n in (0, -5, 400_000, 600_000, 500_000, 2_500_000)]
+            clock[0] += 10.0                                  # idle: refills, but never past one second of burst
+            waits.append(round(await bucket.acquire(1_000_000), 6))
+            waits.append(round(await bucket.acquire(250_000), 6))
+            free = T.BandwidthBucket(0.0)
+            waits.append(await free.acquire(10 ** 9))
+            thr = T.BandwidthThrottle(upload_mbps=8.0, download_mbps=0.8)
+            up = [round(await thr.acquire_upload(n), 6) for n in (1_000_000, 500_000)]
+            down = [round(await thr.acquire_download(n), 6) for n in (100_000, 50_000, 0)]
+            st = thr.stats
+            return waits, up, down, (st.upload_bytes, st.download_bytes, st.upload_waits, st.download_waits), bucket.rate_bytes_per_sec
+
+    waits, up, down, stats, rate = asyncio.run(go())
+    # (how a long wait is cut into sleeps is an implementation detail -- the reference naps once per second of burst, this
+    #  package once per request; the total per call is what callers see)
+    return {"waits": waits, "up": up, "down": down, "stats": stats, "rate": rate, "total_sleep": round(sum(slept), 6)}
+
+
+def compression_round_trips(pkg, tmp):
+    Z = _m(pkg, "compression.zstd")
+    text = "InfoMesh stores page text compressed. " * 200
+    c = Z.Compressor(level=3)
+    blob = c.compress(text.encode())
+    out = {"level": c.level, "smaller": len(blob) < len(text) // 5, "frame_magic": blob[:4].hex(), "round": c.decompress(blob) == text.encode(),
+           "text_round": c.decompress_text(c.compress_text(text)) == text, "empty": c.decompress(c.compress(b"")), "unicode": c.decompress_text(c.compress_text("한국어 텍스트 ✓")),
+           "levels": [Z.Compressor(level=lv).level for lv in (1, 9, 19)]}
+    for name, call in (("garbage", lambda: c.decompress(b"definitely not zstd")), ("bomb", lambda: c.decompress(blob, max_output_size=100))):
+        try:
+            call()
+            out[name] = "no error"
+        except Exception as exc:  # noqa: BLE001
+            out[name] = "raised"
+    other = Z.Compressor(level=19)
+    out["cross_level"] = other.decompress(blob) == text.encode()
+    samples = [(f"https://example.org/page/{i} " + "common boilerplate header footer navigation " * 5 + str(i) * 20).encode() for i in range(200)]
+    try:
+        d = Z.train_dictionary(samples, dict_size=4096)
+        with_dict = Z.Compressor(level=3, dict_data=d)
+        small = samples[7]
+        out["dictionary"] = (len(d) > 0, with_dict.decompress(with_dict.compress(small)) == small)
+    except Exception as exc:  # noqa: BLE001
+        out["dictionary"] = ("raised", type(exc).__name__)
+    return out
+
+
+SCENARIOS.update({f.__name__: f for f in (config_loading, bandwidth_throttle, compression_round_trips)})

@@ -43,11 +43,11 @@ tp = 99
     cfg = C.load_config(p)
     d = C.Config()
     assert cfg.node.role == d.node.role and cfg.node.log_level == "debug"                     # not allowed -> default
-    assert cfg.crawl.max_concurrent == d.crawl.max_concurrent                                   # out of range -> default
+    assert cfg.crawl.max_concurrent == 100                                                      # out of range -> clamped to the bound
     assert cfg.crawl.politeness_delay == 2.0 and isinstance(cfg.crawl.politeness_delay, float)  # int -> float
     assert cfg.crawl.urls_per_hour == d.crawl.urls_per_hour                                     # junk -> default
-    assert cfg.network.replication_factor == d.network.replication_factor and cfg.network.bootstrap_nodes == ["/ip4/1.2.3.4/tcp/4001/p2p/Qm"]
-    assert cfg.storage.compression_level == 19 and cfg.gpu.tp == d.gpu.tp
+    assert cfg.network.replication_factor == 10 and cfg.network.bootstrap_nodes == ["/ip4/1.2.3.4/tcp/4001/p2p/Qm"]
+    assert cfg.storage.compression_level == 19 and cfg.gpu.tp == 8
     assert cfg.index.db_path == tmp_path / "data" / "index.db" and (tmp_path / "data").is_dir()  # index follows data_dir
 
 

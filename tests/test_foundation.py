@@ -35,7 +35,7 @@ def test_config_toml_env_precedence_and_clamp(tmp_path, monkeypatch):
     monkeypatch.setenv("INFOMESH_CRAWL_RESPECT_ROBOTS", "no")
     cfg = C.load_config(p)
     assert cfg.crawl.max_concurrent == 7            # env beats file
-    assert cfg.crawl.politeness_delay == 1.0        # out of range -> default
+    assert cfg.crawl.politeness_delay == 60.0       # out of range -> clamped to the upper bound
     assert cfg.node.role == "full"                  # not in whitelist -> default
     assert cfg.node.listen_port == 4100
     assert cfg.network.peer_acl == ["a", "b", "c"] and cfg.crawl.respect_robots is False
