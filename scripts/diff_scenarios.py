@@ -1551,3 +1551,70 @@ def compression_round_trips(pkg, tmp):
 
 
 SCENARIOS.update({f.__name__: f for f in (config_loading, bandwidth_throttle, compression_round_trips)})
+
+
+# ----------------------------------------------------------------------------- eleventh batch: peer summarisation service, bootstrap helpers
+def peer_summarisation_service(pkg, tmp):
+    H = _m(pkg, "summarizer.peer_handler")
+    E = _m(pkg, "summarizer.engine")
+    clock = [10_000.0]
+
+    async def go():
+        with mock.patch(f"{pkg}.summarizer.peer_handler.time.time", side_effect=lambda: clock[0]):
+            llm = _ScriptedLLM(pkg, ["Summary one.", RuntimeError("model crashed"), "Summary three.", "Summary four."])
+            h = H.PeerSummarizationHandler(E.SummarizationEngine(llm), min_trust_score=0.3)
+
+            def req(i, peer="peer-a", text="body " * 50):
+                return H.SummarizeRequest(request_id=f"r{i}", requester_peer_id=peer, url=f"https://e.com/{i}", title=f"T{i}", text=text, max_tokens=64, timestamp=clock[0])
+
+            seq = []
+            for r, trust, dt in ((req(1), 0.9, 0), (req(2), 0.9, 1), (req(3), 0.1, 100), (req(4, text="x" * 20_000), 0.9, 100), (req(5), 0.9, 100), (req(6, peer="peer-b"), 0.9, 0),
+                                 (req(7), 0.9, 200)):
+                clock[0] += dt
+                resp = await h.handle_request(r, requester_trust=trust)
+                seq.append((resp.request_id, resp.status.value, resp.summary, resp.reject_reason.value if resp.reject_reason else None, resp.model, bool(resp.content_hash)))
+            counters = (h.active_count, h.total_served, h.total_rejected)
+            wire_req = H.serialize_request(req(9))
+            back_req = H.deserialize_request(wire_req)
+            ok = H.SummarizeResponse(request_id="r9", status=H.RequestStatus.COMPLETED if hasattr(H.RequestStatus, "COMPLETED") else list(H.RequestStatus)[0], summary="s",
+                                     content_hash="h", model="m", elapsed_ms=12.5)
+            no = H.SummarizeResponse(request_id="r10", status=list(H.RequestStatus)[-1], reject_reason=list(H.RejectReason)[0], detail="why")
+            wires = [H.serialize_response(ok), H.serialize_response(no)]
+            backs = [H.deserialize_response(w) for w in wires]
+            return {"sequence": seq, "counters": counters, "statuses": [s.value for s in H.RequestStatus], "reasons": [r.value for r in H.RejectReason],
+                    "wire_req": {k: v for k, v in sorted(wire_req.items())}, "req_round": (back_req.request_id, back_req.requester_peer_id, back_req.url, back_req.max_tokens, back_req.timestamp),
+                    "wire_resp": [{k: v for k, v in sorted(w.items())} for w in wires],
+                    "resp_round": [(b.request_id, b.status.value, b.summary, b.reject_reason.value if b.reject_reason else None, b.detail, b.elapsed_ms) for b in backs],
+                    "limits": (H.MAX_PENDING_PER_PEER, H.MAX_CONCURRENT_REQUESTS, H.MAX_TEXT_LENGTH, H.PEER_COOLDOWN_SECONDS, H.PROTOCOL_LLM)}
+
+    return asyncio.run(go())
+
+
+def bootstrap_helpers(pkg, tmp):
+    B = _m(pkg, "p2p.bootstrap")
+    nodes = B.discover_from_static([{"addr": "/ip4/203.0.113.5/tcp/4001/p2p/12D3KooWA", "region": "eu"}, {"addr": "/dns4/boot.example.org/tcp/4002"}, {"region": "no addr"},
+                                    "not a dict", {"addr": "/ip6/2001:db8::1/tcp/abc"}, {"addr": "garbage"}])
+    out = {"static": [(n.addr, n.source, n.region, n.host_port) for n in nodes]}
+    with mock.patch(f"{pkg}.p2p.bootstrap.time.time", return_value=1_000_000.0):
+        peers = [{"peer_id": "fresh-short", "addr": "a", "last_seen": 999_990.0, "uptime": 60}, {"peer_id": "fresh-long", "addr": "b", "last_seen": 999_000.0, "uptime": 90_000},
+                 {"peer_id": "stale-long", "addr": "c", "last_seen": 800_000.0, "uptime": 500_000}, {"peer_id": "junk", "addr": "d", "last_seen": "yesterday", "uptime": None},
+                 {"peer_id": "mid", "addr": "e", "last_seen": 960_000.0, "uptime": 40_000}]
+        out["seeds"] = [[p["peer_id"] for p in B.select_seed_peers(list(peers), max_peers=k)] for k in (2, 10)]
+        out["no_seeds"] = B.select_seed_peers([], max_peers=3)
+    clock = [0.0]
+    with mock.patch(f"{pkg}.p2p.bootstrap.time.time", side_effect=lambda: clock[0]), mock.patch(f"{pkg}.p2p.bootstrap.time.monotonic", side_effect=lambda: clock[0]):
+        rl = B.BootstrapRateLimiter(max_per_minute=3, window_seconds=60.0)
+        seq = []
+        for who, dt in (("a", 0), ("a", 1), ("a", 1), ("a", 1), ("b", 0), ("a", 58), ("a", 1), ("a", 0)):
+            clock[0] += dt
+            seq.append(rl.allow(who))
+        out["rate"] = seq
+        out["tracked"] = rl.tracked_clients
+        rl.reset("a")
+        out["after_reset"] = (rl.allow("a"), rl.tracked_clients)
+        clock[0] += 1000
+        out["cleanup"] = (rl.cleanup(), rl.tracked_clients)
+    return out
+
+
+SCENARIOS.update({f.__name__: f for f in (peer_summarisation_service, bootstrap_helpers)})
