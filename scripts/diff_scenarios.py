@@ -1693,7 +1693,7 @@ def resource_profiles(pkg, tmp):
 
 
 # (p2p.index_submit cannot be driven differentially here: the reference module imports trafilatura, which is not installed;
-#  its receiver / sender are covered by tests/test_index_submit*.py and the interop mode of scripts/diff_vs_reference.py)
+#  its receiver / sender are covered by tests/test_services_layer.py, tests/test_crawl_loop.py, tests/test_platform.py and the interop mode of scripts/diff_vs_reference.py)
 
 
 SCENARIOS.update({f.__name__: f for f in (robots_policy, resource_profiles)})
