@@ -1773,3 +1773,63 @@ def lan_discovery_frames(pkg, tmp):
 
 
 SCENARIOS.update({f.__name__: f for f in (credit_sync_across_nodes, lan_discovery_frames)})
+
+
+# ----------------------------------------------------------------------------- fourteenth batch: dashboard data cache, starter snapshot bookkeeping
+def dashboard_data_cache(pkg, tmp):
+    DC = _m(pkg, "dashboard.data_cache")
+    C = _m(pkg, "config")
+    LS = _m(pkg, "index.local_store").LocalStore
+    import dataclasses
+    import sqlite3
+
+    data = tmp / f"data-{pkg}"
+    base = C.load_config(tmp / "none.toml")
+    cfg = dataclasses.replace(base, node=dataclasses.replace(base.node, data_dir=data), index=dataclasses.replace(base.index, db_path=data / "index.db"))
+    cache = DC.DashboardDataCache(cfg, ttl=0.0)
+    before = cache.get_stats()                       # no database yet: an empty record, no exception
+    out = {"before": (before.document_count, before.top_domains, before.pages_last_hour, before.domain_count, before.recent_docs)}
+    data.mkdir(parents=True, exist_ok=True)
+    store = LS(data / "index.db")
+    hosts = ["docs.python.org", "docs.python.org", "docs.python.org", "en.wikipedia.org", "en.wikipedia.org", "example.org", "sub.example.org", "example.org"]
+    for i, h in enumerate(hosts):
+        store.add_document(url=f"https://{h}/page/{i}", title=f"Title {i}" if i % 3 else "", text=f"body text number {i} " * 10, raw_html_hash=f"r{i}", text_hash=f"t{i}")
+    store.close()
+    conn = sqlite3.connect(data / "index.db")        # spread the crawl times: three within the last hour, the rest older
+    import time as _t
+
+    now = _t.time()
+    for i in range(len(hosts)):
+        conn.execute("UPDATE documents SET crawled_at = ? WHERE url = ?", (now - (600 * i if i < 3 else 7200 + 100 * i), f"https://{hosts[i]}/page/{i}"))
+    conn.commit()
+    conn.close()
+    st = cache.get_stats()
+    out["after"] = {"docs": st.document_count, "top": [tuple(x) for x in st.top_domains][:4], "last_hour": st.pages_last_hour, "domains": st.domain_count,
+                    "recent": [(d.url, d.title) for d in st.recent_docs], "last_crawl_recent": now - st.last_crawl_at < 5}
+    cache.set_ttl(1000.0)
+    st2 = cache.get_stats()
+    out["cached_same_object"] = st2 is cache.get_stats()
+    cache.close()
+    cache.close()                                    # idempotent
+    return out
+
+
+def starter_snapshot_bookkeeping(pkg, tmp):
+    S = _m(pkg, "index.starter")
+    info = S.StarterAssetInfo("https://github.com/x/y/releases/download/v1/starter.infomesh-snapshot", 5 * 1024 * 1024 + 512, "v1.2.3", "2024-05-06T07:08:09Z")
+    d = tmp / f"starter-{pkg}"
+    d.mkdir()
+    out = {"needs": [S.needs_starter(n) for n in (0, 9, 10, 11, 10_000)], "size_mb": round(info.size_mb, 4), "empty_cache": S._read_cache(d)}
+    with mock.patch(f"{pkg}.index.starter.time.time", return_value=1_000_000.0):
+        S._write_cache(d, info)
+        back = S._read_cache(d)
+    out["round_trip"] = (back.download_url, back.size_bytes, back.release_tag, back.created_at)
+    with mock.patch(f"{pkg}.index.starter.time.time", return_value=1_000_000.0 + 30 * 86400):
+        out["expired"] = S._read_cache(d)
+    for f in d.iterdir():
+        f.write_text("{not json")
+    out["corrupt"] = S._read_cache(d)
+    return out
+
+
+SCENARIOS.update({f.__name__: f for f in (dashboard_data_cache, starter_snapshot_bookkeeping)})
