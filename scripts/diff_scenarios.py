@@ -1833,3 +1833,41 @@ def starter_snapshot_bookkeeping(pkg, tmp):
 
 
 SCENARIOS.update({f.__name__: f for f in (dashboard_data_cache, starter_snapshot_bookkeeping)})
+
+
+# ----------------------------------------------------------------------------- fifteenth batch: the Python SDK over a prepared data directory
+SDK_DOCS = [("https://docs.python.org/3/library/asyncio.html", "asyncio — Asynchronous I/O", "asyncio is a library to write concurrent code using the async await syntax. " * 6, "en"),
+            ("https://realpython.com/async-io-python/", "Async IO in Python: A Complete Walkthrough", "This tutorial covers asyncio coroutines event loop and tasks in python. " * 6, "en"),
+            ("https://doc.rust-lang.org/book/ch04-01-what-is-ownership.html", "What is Ownership?", "Ownership is a set of rules that govern how a rust program manages memory. " * 6, "en"),
+            ("https://ko.wikipedia.org/wiki/파이썬", "파이썬", "파이썬은 고급 프로그래밍 언어로 플랫폼에 독립적이며 인터프리터식 객체지향적 동적 타이핑 대화형 언어이다. " * 6, "ko"),
+            ("https://blog.example.org/python-packaging", "Packaging python projects", "How to package python projects with pyproject toml and publish them to an index. " * 6, "en")]
+
+
+def sdk_client(pkg, tmp):
+    K = _m(pkg, "sdk.client")
+    LS = _m(pkg, "index.local_store").LocalStore
+    data = tmp / f"sdk-{pkg}"
+    data.mkdir()
+    store = LS(str(data / "index.db"))
+    for i, (url, title, text, lang) in enumerate(SDK_DOCS):
+        store.add_document(url=url, title=title, text=text, raw_html_hash=f"r{i}", text_hash=f"t{i}", language=lang)
+    store.close()
+    try:
+        client = K.InfoMeshClient(data_dir=str(data), gpu=False)        # this package can attach a GPU index; the CPU contract is compared
+    except TypeError:
+        client = K.InfoMeshClient(data_dir=str(data))
+    with client as c:
+        def urls(**kw):
+            q = kw.pop("q")
+            return [r.url for r in c.search(q, **kw)]
+
+        out = {"python": urls(q="python"), "asyncio_top": urls(q="asyncio event loop", limit=1), "offset": urls(q="python", limit=1, offset=1), "none": urls(q="kubernetes"),
+               "lang": urls(q="python", language="en"), "include": urls(q="python", include_domains=["realpython.com"]),
+               "exclude": urls(q="python", exclude_domains=["docs.python.org", "realpython.com"]), "operators": urls(q='python AND "asyncio" NOT (rust) *'),
+               "korean": urls(q="파이썬"), "shape": sorted(c.search("python", limit=1)[0].to_dict()),
+               "scores_sorted": (lambda s: s == sorted(s, reverse=True))([r.score for r in c.search("python")]),
+               "suggest": [c.suggest(p, limit=3) for p in ("pyt", "async", "zzz", "")], "stats_docs": c.get_stats().get("document_count")}
+    return out
+
+
+SCENARIOS.update({f.__name__: f for f in (sdk_client,)})
