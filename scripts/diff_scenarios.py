@@ -1871,3 +1871,28 @@ def sdk_client(pkg, tmp):
 
 
 SCENARIOS.update({f.__name__: f for f in (sdk_client,)})
+
+
+# ----------------------------------------------------------------------------- sixteenth batch: replica placement (same peers chosen by both implementations)
+def replica_placement(pkg, tmp):
+    R = _m(pkg, "p2p.replication")
+    peers = [f"12D3KooW{name}" for name in ("Alpha", "Bravo", "Charlie", "Delta", "Echo", "Foxtrot", "Golf", "Hotel")]
+    me = peers[3]
+    urls = [f"https://e.com/page/{i}" for i in range(12)] + ["https://한국어.example/문서", ""]
+
+    class Host:
+        def get_connected_peers(self):
+            return list(peers)
+
+    async def reference_way(factor):
+        rep = R.Replicator(Host(), None, me, replication_factor=factor)
+        return [await rep._find_replica_peers(u) for u in urls]
+
+    def this_way(factor):
+        return [R.replica_peers(u, [p for p in peers if p != me], factor) for u in urls]
+
+    pick = (lambda f: asyncio.run(reference_way(f))) if pkg == "infomesh" else this_way
+    return {"three": pick(3), "one": pick(1), "more_than_available": pick(20), "default_factor": R.DEFAULT_REPLICATION_FACTOR}
+
+
+SCENARIOS.update({f.__name__: f for f in (replica_placement,)})
