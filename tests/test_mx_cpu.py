@@ -40,3 +40,20 @@ def test_sfb_pack_layout():
     n, s = 5 * 128 + 2 * 32 + 9, 13                 # chunk 5, m1 = 2, m0 = 9; kb 3, byte 1
     assert ch[3, 5, 9 * 16 + 2 * 4 + 1] == e[n, s]
     assert MX.sfb_chunks(384) == 3 and MX.sfb_chunks(2304) == 18 and MX.sfb_chunks(1152) == 9
+
+
+def test_fused_layernorm_oracle_is_gemm_then_layernorm():
+    """``linear_mx_ln_ref`` is what tests/test_gpu_mx.py holds the clustered kernel against: dequantised GEMM + bias + residual,
+    then LayerNorm over the full row; the fused kernel only exists for row widths made of 2 or 4 tiles of 192 columns."""
+    torch.manual_seed(1)
+    m, n, k = 40, 384, 256
+    a = MX.quantize_act_ref(torch.randn(m, k))
+    w = MX.quantize_weight(torch.randn(n, k) * 0.05)
+    bias, res = torch.randn(n), torch.randn(m, n).bfloat16()
+    g, b = torch.rand(n) + 0.5, torch.randn(n) * 0.1
+    got = MX.linear_mx_ln_ref(a, w, bias, res, g, b, 1e-5)
+    y = a.float() @ w.float().T + bias + res.float()
+    want = (y - y.mean(-1, keepdim=True)) / torch.sqrt(y.var(-1, unbiased=False, keepdim=True) + 1e-5) * g + b
+    assert got.shape == (m, n) and (got - want).abs().max().item() < 1e-4
+    assert (MX.linear_mx_ln_ref(a, w, None, None, torch.ones(n), None, 1e-5).mean(-1).abs() < 1e-4).all()   # unit gamma, no beta: zero-mean rows
+    assert all(width % 192 == 0 and width // 192 in (2, 4) for width in MX.FUSED_LN_WIDTHS)
