@@ -86,3 +86,11 @@ processors = _ns("processors", TimeStamper=_proc, JSONRenderer=_proc, StackInfoR
 dev = _ns("dev", ConsoleRenderer=_proc)
 contextvars = _ns("contextvars", bind_contextvars=lambda **k: None, clear_contextvars=lambda: None,
                   merge_contextvars=_proc())
+
+
+def PrintLoggerFactory(*_a, **_k):     # noqa: N802 -- structlog API name; the CLI entry point configures it
+    return None
+
+
+def make_filtering_bound_logger(*_a, **_k):
+    return BoundLogger

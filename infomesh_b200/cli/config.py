@@ -18,6 +18,7 @@ def config_show() -> None:
         click.secho(f"[{section}]", bold=True)
         for k, v in values.items():
             click.echo(f"  {k} = {v}")
+        click.echo()
 
 
 @config_group.command("set")

@@ -93,7 +93,7 @@ def dashboard(tab: str, text: bool) -> None:
 
 @click.group("feeds")
 def feeds_group() -> None:
-    """RSS / Atom feed subscriptions."""
+    """Manage RSS/Atom feed monitoring."""
 
 
 def _feeds_file():
@@ -103,12 +103,19 @@ def _feeds_file():
 @feeds_group.command("import")
 @click.argument("opml_file", type=click.Path(exists=True))
 def feeds_import(opml_file: str) -> None:
-    """Subscribe to every feed of an OPML file."""
+    """Import RSS/Atom feeds from an OPML file (the reference only lists them: cli/crawl.py:318-337; here they are also
+    remembered in ``<data_dir>/feeds.json`` so that the feed monitor polls them)."""
     from pathlib import Path
 
     from infomesh_b200.crawler.feed_monitor import parse_opml
 
     feeds = parse_opml(Path(opml_file).read_text(encoding="utf-8"))
+    if not feeds:
+        click.echo("No feeds found in OPML file.")
+        return
+    click.echo(f"Found {len(feeds)} feeds:")
+    for feed in feeds:
+        click.echo(f"  {feed.url}{f' ({feed.label})' if feed.label else ''}")
     path = _feeds_file()
     known = set(json.loads(path.read_text())) if path.exists() else set()
     new = [f.url for f in feeds if f.url not in known]
@@ -119,10 +126,16 @@ def feeds_import(opml_file: str) -> None:
 
 @feeds_group.command("list")
 def feeds_list() -> None:
-    """List subscribed feeds."""
+    """List currently configured RSS/Atom feeds."""
+    crawl = load_config().crawl
+    if crawl.rss_enabled:
+        click.echo(f"RSS monitoring: enabled (interval={crawl.rss_default_interval}s, max={crawl.rss_max_feeds}, "
+                   f"discovery={'on' if crawl.rss_discovery else 'off'})")
+    else:
+        click.echo("RSS feed monitoring is disabled. Enable with: infomesh config set crawl.rss_enabled true")
     path = _feeds_file()
     urls = json.loads(path.read_text()) if path.exists() else []
-    if not urls:
-        click.echo("No feeds. Import an OPML file with: infomesh feeds import FILE")
-    for u in urls:
-        click.echo(u)
+    if urls:
+        click.echo(f"Subscribed feeds ({len(urls)}):")
+        for u in urls:
+            click.echo(f"  {u}")

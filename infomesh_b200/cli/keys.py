@@ -13,21 +13,28 @@ def keys_group() -> None:
 
 @keys_group.command("export")
 def keys_export() -> None:
-    """Print the public key (PEM) and peer id."""
-    from infomesh_b200.p2p.keys import ensure_keys, export_public_key
+    """Export the public key (PEM).  Keys are created by ``infomesh start``; without them this says so and changes nothing."""
+    from infomesh_b200.p2p.keys import export_public_key
 
-    d = load_config().node.data_dir
-    kp = ensure_keys(d)
-    click.echo(f"Peer ID: {kp.peer_id}")
-    click.echo(export_public_key(d))
+    try:
+        click.echo(export_public_key(load_config().node.data_dir))      # the PEM and nothing else: `keys export > node.pem` must work
+    except FileNotFoundError as exc:
+        click.echo(str(exc))
 
 
 @keys_group.command("rotate")
 @click.confirmation_option(prompt="This will generate a new key pair. Are you sure?")
 def keys_rotate() -> None:
-    """Generate a new key pair; the old key signs a revocation record that peers can verify."""
+    """Rotate the Ed25519 key pair; the old key signs a revocation record that peers can verify."""
     from infomesh_b200.p2p.keys import rotate_keys
 
-    old, new, rec = rotate_keys(load_config().node.data_dir)
-    click.secho("✔ Key rotated", fg="green")
-    click.echo(f"  old peer id: {old.peer_id}\n  new peer id: {new.peer_id}\n  revocation record signed by both keys ({rec.reason})")
+    try:
+        old, new, record = rotate_keys(load_config().node.data_dir)
+    except FileNotFoundError as exc:
+        click.echo(str(exc))
+        return
+    click.echo("Old keys backed up. Revocation record saved.")
+    click.echo(f"  Old Peer ID: {old.peer_id}")
+    click.echo(f"  New Peer ID: {new.peer_id}")
+    click.echo(f"  Reason: {record.reason}")
+    click.echo("\nRevocation will be published to DHT on next node start.")

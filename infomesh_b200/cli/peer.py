@@ -2,7 +2,6 @@
 (reference infomesh/cli/peer.py:12-219)."""
 from __future__ import annotations
 
-import asyncio
 import json
 import time
 
@@ -20,27 +19,72 @@ def _resolve(nodes: list[str]) -> list[str]:
     return list(dict.fromkeys(out))
 
 
+_ADD_HINT = "Add with: infomesh peer add /ip4/<IP>/tcp/4001/p2p/<PEER_ID>"
+
+
+def _label(text: str, colour: str) -> str:
+    return click.style(text, fg=colour)
+
+
+def _host_port(multiaddr: str) -> tuple[str, int] | None:
+    """``(host, port)`` of a multiaddr (or ``HOST:PORT``), None when it has none."""
+    from infomesh_b200.p2p.transport import parse_multiaddr
+
+    try:
+        host, port, _ = parse_multiaddr(multiaddr)
+    except (ValueError, TypeError):
+        return None
+    return (host, int(port)) if host and port else None
+
+
+def _tcp_reachable(host: str, port: int, timeout: float = 5.0) -> bool:
+    import socket
+
+    try:
+        with socket.create_connection((host, port), timeout=timeout):
+            return True
+    except OSError:
+        return False
+
+
 @click.group(name="peer")
 def peer_group() -> None:
-    """Bootstrap peers and connectivity."""
+    """Manage P2P peers (add, list, remove bootstrap nodes)."""
 
 
 @peer_group.command("list")
 def list_peers() -> None:
-    """Configured bootstrap nodes and currently connected peers."""
+    """Show connected peers and bootstrap nodes."""
     cfg = load_config()
-    click.secho("Configured bootstrap nodes:", bold=True)
-    for a in _resolve(cfg.network.bootstrap_nodes) or ["(none)"]:
-        click.echo(f"  {a}")
+    click.echo("Bootstrap nodes:")
+    nodes = _resolve(cfg.network.bootstrap_nodes)
+    for line in nodes or ["(none configured)", _ADD_HINT]:
+        click.echo(f"  {line}")
+    click.echo()
     path = cfg.node.data_dir / "p2p_status.json"
+    if not path.exists():
+        click.echo("P2P state: not started")
+        return
     try:
         st = json.loads(path.read_text())
-        fresh = time.time() - float(st.get("timestamp", 0)) < 30
-        click.secho(f"\nNode {st.get('state', '?')}{'' if fresh else ' (stale status)'} — {st.get('peers', 0)} peer(s) connected", bold=True)
-        for pid in st.get("peer_ids", [])[:50]:
-            click.echo(f"  {pid}")
+        if not isinstance(st, dict):
+            raise ValueError("status is not an object")
     except (OSError, ValueError):
-        click.echo("\nNode not running (no live peer list).")
+        click.echo("P2P state: unknown (status file unreadable)")
+        return
+    stale = time.time() - float(st.get("timestamp", 0) or 0) >= 30 if "timestamp" in st else False
+    click.echo(f"P2P state: {st.get('state', 'stopped')}{' (stale status)' if stale else ''}")
+    peers = st.get("peer_ids", [])
+    peers = peers if isinstance(peers, list) else []
+    click.echo(f"Connected peers: {len(peers)}")
+    for pid in peers:
+        click.echo(f"  {pid}")
+    boot = st.get("bootstrap")
+    if isinstance(boot, dict) and boot:
+        click.echo(f"Bootstrap: {boot.get('connected', 0)} connected, {boot.get('failed', 0)} failed")
+        failed = boot.get("failed_addrs", [])
+        for addr in failed if isinstance(failed, list) else []:
+            click.echo("  " + _label(f"✗ {addr}", "red"))
 
 
 def _write_nodes(cfg, nodes: list[str]) -> None:
@@ -50,20 +94,31 @@ def _write_nodes(cfg, nodes: list[str]) -> None:
 @peer_group.command("add")
 @click.argument("multiaddr")
 def add(multiaddr: str) -> None:
-    """Add a bootstrap node (``/ip4/HOST/tcp/PORT[/p2p/ID]`` or ``HOST:PORT``)."""
-    from infomesh_b200.p2p.transport import parse_multiaddr
-
-    try:
-        parse_multiaddr(multiaddr)
-    except ValueError as exc:
-        raise click.ClickException(str(exc)) from None
+    """Add a bootstrap node: ``/ip4/1.2.3.4/tcp/4001/p2p/12D3KooW...``."""
+    if not multiaddr.startswith(("/ip4/", "/ip6/", "/dns4/", "/dns6/")):
+        click.echo(_label("Error: ", "red") + "Invalid multiaddr format.")
+        click.echo("Expected: /ip4/<IP>/tcp/<PORT>/p2p/<PEER_ID>")
+        return
+    if "/p2p/" not in multiaddr:
+        click.echo(_label("Warning: ", "yellow") + "No /p2p/<PEER_ID> in address. Connection may fail without peer ID.")
     cfg = load_config()
     nodes = list(cfg.network.bootstrap_nodes)
     if multiaddr in nodes:
-        click.echo("Already configured.")
+        click.echo("Already in bootstrap list.")
         return
-    _write_nodes(cfg, nodes + [multiaddr])
-    click.secho(f"✔ Added {multiaddr}. Restart the node to connect.", fg="green")
+    _write_nodes(cfg, [*nodes, multiaddr])
+    click.echo(_label("Added: ", "green") + multiaddr)
+    click.echo("Restart the node for changes to take effect: infomesh stop && infomesh start")
+    target = _host_port(multiaddr)
+    if target is None:
+        click.echo("(skipped — could not parse IP/port)")
+        return
+    click.echo(f"Testing TCP {target[0]}:{target[1]}... ", nl=False)
+    if _tcp_reachable(*target):
+        click.echo(_label("reachable ✓", "green"))
+    else:
+        click.echo(_label("unreachable ✗", "red"))
+        click.echo("  Ensure the bootstrap node is running and port is open (firewall/NSG).")
 
 
 @peer_group.command("remove")
@@ -73,23 +128,43 @@ def remove(multiaddr: str) -> None:
     cfg = load_config()
     nodes = list(cfg.network.bootstrap_nodes)
     if multiaddr not in nodes:
-        raise click.ClickException("not in the configured bootstrap list")
+        click.echo("Not found in bootstrap list.")
+        click.echo("Current nodes:")
+        for addr in nodes:
+            click.echo(f"  {addr}")
+        return
     nodes.remove(multiaddr)
     _write_nodes(cfg, nodes)
-    click.secho(f"✔ Removed {multiaddr}", fg="green")
+    click.echo(_label("Removed: ", "green") + multiaddr)
 
 
 @peer_group.command("test")
 def test() -> None:
-    """TCP-probe every configured bootstrap node."""
-    from infomesh_b200.p2p.bootstrap import BootstrapNode, check_all_bootstrap_health
-
-    nodes = [BootstrapNode(a, "config") for a in _resolve(load_config().network.bootstrap_nodes)]
+    """Test connectivity to all bootstrap nodes."""
+    nodes = _resolve(load_config().network.bootstrap_nodes)
     if not nodes:
         click.echo("No bootstrap nodes configured.")
+        click.echo(_ADD_HINT)
         return
-    for h in asyncio.run(check_all_bootstrap_health(nodes)):
-        if h.reachable:
-            click.secho(f"  ✔ {h.addr}  {h.latency_ms:.0f} ms", fg="green")
+    click.echo(f"Testing {len(nodes)} bootstrap node(s)...\n")
+    reachable = 0
+    for addr in nodes:
+        click.echo(f"  {addr}")
+        target = _host_port(addr)
+        if target is None:
+            click.echo(_label("    SKIP", "yellow") + " — could not parse address")
+            continue
+        click.echo(f"    TCP {target[0]}:{target[1]} ... ", nl=False)
+        if _tcp_reachable(*target):
+            reachable += 1
+            click.echo(_label("OK ✓", "green"))
         else:
-            click.secho(f"  ✖ {h.addr}  unreachable", fg="red")
+            click.echo(_label("FAIL ✗", "red"))
+            click.echo("    → Node not running or port blocked by firewall/NSG")
+    click.echo(f"\nResult: {reachable}/{len(nodes)} reachable")
+    if reachable == 0:
+        click.echo("\nNo bootstrap nodes reachable. Peers cannot be discovered.")
+        click.echo("Troubleshooting:")
+        for n, tip in enumerate(("Is the bootstrap node running?", "Is TCP port 4001 open in firewall / Azure NSG / AWS SG?", "Is the IP address correct?",
+                                 "Try: nc -zv <IP> 4001 (or Test-NetConnection on Windows)"), 1):
+            click.echo(f"  {n}. {tip}")

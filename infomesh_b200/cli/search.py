@@ -99,28 +99,34 @@ def search(query: str, limit: int, local_only: bool, vector: bool, gpu: bool) ->
 
 @click.group("feedback")
 def feedback_group() -> None:
-    """Implicit search-quality feedback (stored locally only)."""
+    """Inspect implicit search quality signals."""
 
 
 def _feedback_store():
+    """The feedback database, or None while no search has recorded a signal yet (the file does not exist)."""
     from infomesh_b200.search.feedback import FeedbackStore
 
-    return FeedbackStore(str(load_config().node.data_dir / "feedback.db"))
+    path = load_config().node.data_dir / "feedback.db"
+    return FeedbackStore(str(path)) if path.exists() else None
 
 
 @feedback_group.command("stats")
 def feedback_stats() -> None:
-    """Signal counts and the strongest boosts."""
+    """Show feedback signal statistics."""
     fb = _feedback_store()
+    if fb is None:
+        click.echo("No feedback data yet. Search more to collect signals.")
+        return
     try:
         count, top = fb.signal_count(), fb.top_boosted_urls(5)
         click.echo(f"Total signals: {count}")
         click.echo(f"Boosted URLs:  {len(top)}")
         if top:
-            click.echo(f"\n{'URL':<60} {'Boost':>8} {'Fetch':>6} {'Skip':>6} {'Cite':>6}")
-            click.echo("─" * 90)
+            click.echo(f"\n{'URL':<60} {'Boost':>8} {'Fetch':>6} {'Cite':>6}")
+            click.echo("─" * 82)
             for u in top:
-                click.echo(f"{u.url[:60]:<60} {u.boost_score:>+8.2f} {u.fetch_count:>6} {u.skip_count:>6} {u.cite_count:>6}")
+                shown = u.url if len(u.url) <= 60 else u.url[:58] + ".."
+                click.echo(f"{shown:<60} {u.boost_score:>8.2f} {u.fetch_count:>6} {u.cite_count:>6}")
     finally:
         fb.close()
 
@@ -128,10 +134,16 @@ def feedback_stats() -> None:
 @feedback_group.command("top-urls")
 @click.option("--limit", "-n", default=20, help="Number of URLs to show")
 def feedback_top_urls(limit: int) -> None:
-    """URLs ranked by accumulated positive feedback."""
+    """Show URLs with highest quality signals."""
     fb = _feedback_store()
+    if fb is None:
+        click.echo("No feedback data yet.")
+        return
     try:
-        for i, u in enumerate(fb.top_boosted_urls(limit), 1):
-            click.echo(f"{i:3d}. {u.boost_score:+.2f}  {u.url}")
+        top = fb.top_boosted_urls(limit)
+        if not top:
+            click.echo("No boosted URLs yet.")
+        for u in top:
+            click.echo(f"  {u.boost_score:+.2f}  {u.url}  (fetch={u.fetch_count} cite={u.cite_count})")
     finally:
         fb.close()

@@ -30,6 +30,18 @@ def _seed(data_dir):
                        "Ownership is a set of rules that govern how a Rust program manages memory. Borrowing keeps references valid. " * 3)
 
 
+def test_cli_keys_without_a_key_pair_change_nothing(tmp_path, monkeypatch):
+    from click.testing import CliRunner
+
+    from infomesh_b200.cli import cli
+
+    monkeypatch.setenv("INFOMESH_NODE_DATA_DIR", str(tmp_path / "fresh"))
+    out = CliRunner().invoke(cli, ["keys", "export"])
+    assert out.exit_code == 0 and "No public key found" in out.output and "Run 'infomesh start' first." in out.output
+    assert "No existing key pair to rotate" in CliRunner().invoke(cli, ["keys", "rotate", "--yes"]).output
+    assert not (tmp_path / "fresh" / "keys" / "public.pem").exists()          # the node mints keys on its first start, not this command
+
+
 def test_cli_commands(node_env):
     from infomesh_b200.cli import cli
 
@@ -52,18 +64,31 @@ def test_cli_commands(node_env):
     assert run(cli, ["config", "set", "nope.key", "1"]).exit_code != 0
     assert "✔ GitHub identity set" in run(cli, ["config", "github", "dev@example.com"]).output
     assert run(cli, ["config", "github", "not-an-email"]).exit_code != 0
+    from infomesh_b200.p2p.keys import ensure_keys
+
+    ensure_keys(node_env)
     kx = run(cli, ["keys", "export"])
-    assert kx.exit_code == 0 and "Peer ID:" in kx.output and "BEGIN PUBLIC KEY" in kx.output
-    assert "✔ Key rotated" in run(cli, ["keys", "rotate", "--yes"]).output
-    assert "✔ Added" in run(cli, ["peer", "add", "/ip4/127.0.0.1/tcp/1"]).output
+    assert kx.output.startswith("-----BEGIN PUBLIC KEY-----") and "END PUBLIC KEY" in kx.output        # pipeable PEM
+    rot = run(cli, ["keys", "rotate", "--yes"]).output
+    assert "Old keys backed up. Revocation record saved." in rot and "Old Peer ID:" in rot and "New Peer ID:" in rot
+    added = run(cli, ["peer", "add", "/ip4/127.0.0.1/tcp/1"]).output
+    assert "Added: /ip4/127.0.0.1/tcp/1" in added and "Warning: No /p2p/<PEER_ID>" in added and "Testing TCP 127.0.0.1:1... unreachable" in added
+    assert "Already in bootstrap list." in run(cli, ["peer", "add", "/ip4/127.0.0.1/tcp/1"]).output
     pl = run(cli, ["peer", "list"])
-    assert "/ip4/127.0.0.1/tcp/1" in pl.output and "Node not running" in pl.output
-    assert "unreachable" in run(cli, ["peer", "test"]).output
-    assert "✔ Removed" in run(cli, ["peer", "remove", "/ip4/127.0.0.1/tcp/1"]).output and run(cli, ["peer", "add", "udp://x"]).exit_code != 0
+    assert "Bootstrap nodes:\n" in pl.output and "/ip4/127.0.0.1/tcp/1" in pl.output and "P2P state: not started" in pl.output
+    pt = run(cli, ["peer", "test"]).output
+    assert "TCP 127.0.0.1:1 ... FAIL" in pt and "reachable" in pt.split("Result:")[1]
+    assert "Removed: /ip4/127.0.0.1/tcp/1" in run(cli, ["peer", "remove", "/ip4/127.0.0.1/tcp/1"]).output
+    assert "Not found in bootstrap list." in run(cli, ["peer", "remove", "/ip4/127.0.0.1/tcp/1"]).output
+    assert "Invalid multiaddr format." in run(cli, ["peer", "add", "udp://x"]).output
     (node_env / "feeds.opml").write_text('<opml><body><outline text="a" xmlUrl="https://a.example/feed.xml"/></body></opml>')
     assert "1 new feeds" in run(cli, ["feeds", "import", str(node_env / "feeds.opml")]).output
     assert "https://a.example/feed.xml" in run(cli, ["feeds", "list"]).output
-    assert "Total signals: 0" in run(cli, ["feedback", "stats"]).output and run(cli, ["feedback", "top-urls"]).exit_code == 0
+    assert "RSS feed monitoring is disabled." in run(cli, ["feeds", "list"]).output
+    fs = run(cli, ["feedback", "stats"]).output            # the searches above may already have created feedback.db
+    assert "Total signals: 0" in fs or "No feedback data yet. Search more to collect signals." in fs
+    ft = run(cli, ["feedback", "top-urls"]).output
+    assert "No boosted URLs yet." in ft or "No feedback data yet." in ft
     doc = run(cli, ["doctor"])
     assert doc.exit_code == 0 and "InfoMesh Doctor" in doc.output and "Summary:" in doc.output
     bench = run(cli, ["bench", "-n", "3"])
