@@ -42,58 +42,103 @@ def index_stats() -> None:
                 click.echo(f"  {cnt:6d}  {dom}")
 
 
+def _report(headline: str, details: list[tuple[str, object]], elapsed_ms: float | None = None) -> None:
+    """A headline followed by indented ``label value`` lines and the elapsed time: the layout every import / export prints."""
+    click.echo(headline)
+    for label, value in details:
+        click.echo(f"  {label} {value}")
+    if elapsed_ms is not None:
+        click.echo(f"  Time: {elapsed_ms:.0f}ms")
+
+
 @index_group.command("export")
 @click.argument("output", default="infomesh-index.infomesh-snapshot")
 def index_export(output: str) -> None:
-    """Write a portable compressed snapshot of the index."""
+    """Export the local index to a snapshot file."""
     from infomesh_b200.index.snapshot import export_snapshot
 
     with _store(load_config()) as st:
         stats = export_snapshot(st, output)
-    click.secho(f"✔ Exported {stats.total_documents} documents to {output} ({stats.file_size_bytes / 2 ** 20:.1f} MB, {stats.elapsed_ms:.0f} ms)", fg="green")
+    click.echo(f"Exported {stats.total_documents} documents to {output}")
+    click.echo(f"  File size: {stats.file_size_bytes / 2 ** 20:.2f} MB ({stats.elapsed_ms:.0f}ms)")
+
+
+def _import_starter(cfg, info_only: bool) -> None:
+    from infomesh_b200.index import starter as S
+    from infomesh_b200.index.snapshot import import_snapshot
+
+    click.echo("  ⏳ Checking for starter index on GitHub Releases...")
+    asset = asyncio.run(S.find_starter_asset(cache_dir=cfg.node.data_dir))
+    if asset is None:
+        click.secho("  No starter snapshot found in GitHub Releases.", fg="yellow")
+        click.echo("  The project maintainer has not published a starter index yet.")
+        raise SystemExit(0)
+    if info_only:
+        _report("Starter Index (remote)", [("Release: ", asset.release_tag), ("Size:    ", f"{asset.size_mb:.1f} MB"), ("Created: ", asset.created_at),
+                                           ("URL:     ", asset.download_url)])
+        return
+    click.echo(f"  Found starter index: {asset.size_mb:.1f} MB (release {asset.release_tag})")
+    import sys
+
+    if sys.stdin.isatty() and not click.confirm("  Download and import it?", default=True):
+        return
+    click.echo(f"  ⏳ Downloading {asset.size_mb:.1f} MB...")
+    shown = {"pct": -1}
+
+    def progress(done: int, total: int) -> None:
+        pct = int(done * 100 / max(total, 1)) // 10 * 10
+        if pct != shown["pct"]:
+            shown["pct"] = pct
+            click.echo(f"  ... {pct}%")
+
+    path = S.download_starter_sync(cfg.node.data_dir, progress_callback=progress)
+    if path is None:
+        click.secho("  Download failed.", fg="red")
+        raise SystemExit(1)
+    click.echo(f"  ✔ Downloaded to {path}")
+    click.echo("  ⏳ Importing into local index...")
+    with _store(cfg) as st:
+        stats = import_snapshot(st, path)
+    _report(f"  ✔ Imported {stats.exported} documents", [("Skipped (duplicate):", stats.skipped), ("Total in snapshot:  ", stats.total_documents)], stats.elapsed_ms)
+    click.secho("\n  Starter index loaded! Run 'infomesh search <query>' to try it out.", fg="green", bold=True)
 
 
 @index_group.command("import")
 @click.argument("input_path", required=False, default=None)
-@click.option("--starter", is_flag=True, help="Download and import the community starter snapshot")
-@click.option("--info", "info_only", is_flag=True, help="With --starter: only show the remote snapshot's metadata")
-def index_import(input_path: str | None, starter: bool, info_only: bool) -> None:
-    """Import a snapshot file (or the starter snapshot)."""
-    from infomesh_b200.index.snapshot import import_snapshot
+@click.option("--info", "info_only", is_flag=True, default=False, help="Show snapshot metadata only")
+@click.option("--starter", is_flag=True, default=False, help="Download and import the community starter index from GitHub Releases")
+def index_import(input_path: str | None, info_only: bool, starter: bool) -> None:
+    """Import a snapshot file into the local index.
+
+    \b
+    With --starter, downloads the community starter index from GitHub
+    Releases automatically (no INPUT_PATH needed). Use --starter --info
+    to check what's available without downloading."""
+    from infomesh_b200.index.snapshot import import_snapshot, read_snapshot_metadata
 
     cfg = load_config()
     if starter:
-        from infomesh_b200.index import starter as S
+        _import_starter(cfg, info_only)
+        return
+    if input_path is None:
+        click.echo("Error: Missing argument 'INPUT_PATH'.")
+        click.echo("  Use --starter to download the community index.")
+        raise SystemExit(1)
+    if info_only:
+        import datetime
 
-        info = asyncio.run(S.find_starter_asset(cache_dir=cfg.node.data_dir))
-        if info is None:
-            raise click.ClickException("no starter snapshot found (offline, or none has been published)")
-        click.echo(f"Starter snapshot {info.release_tag}: {info.size_mb:.1f} MB, created {info.created_at}")
-        if info_only:
-            return
-        bar = {"last": -1}
-
-        def progress(done: int, total: int) -> None:
-            pct = int(done * 100 / max(total, 1))
-            if pct // 10 != bar["last"]:
-                bar["last"] = pct // 10
-                click.echo(f"  {pct}%")
-
-        path = S.download_starter_sync(cfg.node.data_dir, progress_callback=progress)
-        if path is None:
-            raise click.ClickException("download failed")
-        input_path = str(path)
-    if not input_path:
-        raise click.UsageError("give a snapshot path or --starter")
+        meta = read_snapshot_metadata(input_path)
+        created = datetime.datetime.fromtimestamp(meta.get("created_at", 0), tz=datetime.UTC).isoformat()
+        _report(f"Snapshot: {input_path}", [("Format version:", meta.get("format_version")), ("Documents:     ", meta.get("document_count")), ("Created:       ", created)])
+        return
     with _store(cfg) as st:
         stats = import_snapshot(st, input_path)
-    click.secho(f"✔ Imported {stats.exported} of {stats.total_documents} documents ({stats.skipped} skipped) in {stats.elapsed_ms:.0f} ms", fg="green")
+    _report(f"Imported {stats.exported} documents from {input_path}", [("Skipped (duplicate):", stats.skipped), ("Total in snapshot:  ", stats.total_documents)],
+            stats.elapsed_ms)
 
 
-@index_group.command("import-wet")
-@click.argument("path_or_url")
-def index_import_wet(path_or_url: str) -> None:
-    """Import a Common Crawl WET file (local path or URL, .gz supported)."""
+def _with_importer(run):
+    """Open the store + dedup database, hand a ``CommonCrawlImporter`` to ``run`` (a coroutine function), close both."""
     from infomesh_b200.crawler.dedup import DeduplicatorDB
     from infomesh_b200.index.commoncrawl import CommonCrawlImporter
 
@@ -101,11 +146,18 @@ def index_import_wet(path_or_url: str) -> None:
     with _store(cfg) as st:
         dedup = DeduplicatorDB(str(cfg.node.data_dir / "dedup.db"))
         try:
-            s = asyncio.run(CommonCrawlImporter(st, dedup).import_wet_file(path_or_url))
+            return asyncio.run(run(CommonCrawlImporter(st, dedup)))
         finally:
             dedup.close()
-    click.secho(f"✔ {s.imported}/{s.total_records} records imported ({s.skipped_duplicate} duplicate, {s.skipped_too_short} short, "
-                f"{s.skipped_error} errors) in {s.elapsed_ms:.0f} ms", fg="green")
+
+
+@index_group.command("import-wet")
+@click.argument("path_or_url")
+def index_import_wet(path_or_url: str) -> None:
+    """Import a Common Crawl WET file (local path or URL, .gz supported)."""
+    s = _with_importer(lambda imp: imp.import_wet_file(path_or_url))
+    _report(f"Imported {s.imported} documents from WET file", [("Total records:   ", s.total_records), ("Skipped (dup):   ", s.skipped_duplicate),
+                                                                ("Skipped (short): ", s.skipped_too_short), ("Skipped (error): ", s.skipped_error)], s.elapsed_ms)
 
 
 @index_group.command("import-urls")
@@ -113,17 +165,8 @@ def index_import_wet(path_or_url: str) -> None:
 @click.option("--max", "-m", "max_urls", default=10000, help="Maximum URLs to import")
 def index_import_urls(url_file: str, max_urls: int) -> None:
     """Register the URLs of a text file for crawling."""
-    from infomesh_b200.crawler.dedup import DeduplicatorDB
-    from infomesh_b200.index.commoncrawl import CommonCrawlImporter
-
-    cfg = load_config()
-    with _store(cfg) as st:
-        dedup = DeduplicatorDB(str(cfg.node.data_dir / "dedup.db"))
-        try:
-            s = asyncio.run(CommonCrawlImporter(st, dedup).import_url_list(url_file, max_urls=max_urls))
-        finally:
-            dedup.close()
-    click.secho(f"✔ {s.imported} new URLs registered ({s.skipped_duplicate} already known)", fg="green")
+    s = _with_importer(lambda imp: imp.import_url_list(url_file, max_urls=max_urls))
+    _report(f"Registered {s.imported} URLs from {url_file}", [("Skipped (already seen):", s.skipped_duplicate)])
 
 
 @index_group.command("gpu-build")

@@ -53,10 +53,16 @@ def test_cli_commands(node_env):
     st = run(cli, ["index", "stats"])
     assert st.exit_code == 0 and "Documents:       2" in st.output and "Tokenizer:       unicode61" in st.output and "docs.python.org" in st.output
     snap = str(node_env / "out.infomesh-snapshot")
-    assert "Exported 2 documents" in run(cli, ["index", "export", snap]).output
-    assert "Imported 0 of 2" in run(cli, ["index", "import", snap]).output
+    exp = run(cli, ["index", "export", snap]).output
+    assert f"Exported 2 documents to {snap}" in exp and "  File size: " in exp
+    imp = run(cli, ["index", "import", snap]).output
+    assert f"Imported 0 documents from {snap}" in imp and "  Skipped (duplicate): 2" in imp and "  Total in snapshot:   2" in imp and "  Time: " in imp
+    meta = run(cli, ["index", "import", snap, "--info"]).output
+    assert meta.startswith(f"Snapshot: {snap}") and "  Documents:      2" in meta and "  Format version: " in meta
+    assert "Missing argument 'INPUT_PATH'" in run(cli, ["index", "import"]).output
     (node_env / "urls.txt").write_text("https://a.example/1\nhttps://a.example/2\n")
-    assert "2 new URLs registered" in run(cli, ["index", "import-urls", str(node_env / "urls.txt")]).output
+    reg = run(cli, ["index", "import-urls", str(node_env / "urls.txt")]).output
+    assert "Registered 2 URLs from " in reg and "  Skipped (already seen): 0" in reg
     show = run(cli, ["config", "show"])
     assert show.exit_code == 0 and "[crawl]" in show.output and "politeness_delay" in show.output
     setr = run(cli, ["config", "set", "crawl.politeness_delay", "2.5"])
