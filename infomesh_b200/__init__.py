@@ -5,3 +5,4 @@ Python; the hot paths (encoder / reranker / summariser GEMMs and attention, shar
 BM25 scoring, SimHash dedup, passage extraction) are hand-written CUDA kernels in ``csrc/``.
 """
 __version__ = "0.1.0"
+DISTRIBUTION = "infomesh-b200"      # the name this package is published and upgraded under (not the reference's `infomesh`)

@@ -187,7 +187,9 @@ def update(check: bool) -> None:
     if check:
         return
     uv = shutil.which("uv")
-    cmd = [uv, "pip", "install", "--upgrade", "infomesh"] if uv else [sys.executable, "-m", "pip", "install", "--upgrade", "infomesh"]
+    from infomesh_b200 import DISTRIBUTION
+
+    cmd = [uv, "pip", "install", "--upgrade", DISTRIBUTION] if uv else [sys.executable, "-m", "pip", "install", "--upgrade", DISTRIBUTION]
     click.echo(f"  Running: {' '.join(cmd)}")
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

@@ -16,9 +16,9 @@ from dataclasses import dataclass
 from itertools import takewhile
 from pathlib import Path
 
-from infomesh_b200 import __version__
+from infomesh_b200 import DISTRIBUTION, __version__
 
-_PYPI_URL = "https://pypi.org/pypi/infomesh/json"
+_PYPI_URL = f"https://pypi.org/pypi/{DISTRIBUTION}/json"      # releases of THIS distribution, never the reference's
 _CACHE_TTL_SECONDS = 86400
 _CACHE_FILE_NAME = "version_cache.json"
 _REQUEST_TIMEOUT = 5.0

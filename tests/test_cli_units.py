@@ -182,3 +182,17 @@ def test_search_command_formats_scores_and_falls_back_without_gpu(node_env):
     r = _run("search", "--local", "-n", "2", "distributed shared memory clusters")
     assert r.exit_code == 0 and r.output.count("https://example.org/doc") == 2
     assert "ms" in r.output and "[1] Cluster launch" in r.output and "    Source: https://example.org/doc" in r.output and "BM25=" in r.output
+
+
+def test_updates_target_this_distribution_not_the_reference_package(node_env, monkeypatch):
+    """``infomesh update`` must upgrade ``infomesh-b200``: installing the reference's ``infomesh`` over this package would replace it."""
+    import subprocess
+
+    from infomesh_b200 import DISTRIBUTION, version_check as V
+
+    assert DISTRIBUTION == "infomesh-b200" and V._PYPI_URL.endswith("/infomesh-b200/json")
+    V._write_cache(node_env, "999.0.0")
+    seen = []
+    monkeypatch.setattr(subprocess, "run", lambda cmd, **kw: seen.append(cmd) or subprocess.CompletedProcess(cmd, 0, "", ""))
+    _run("update")
+    assert seen and seen[0][-3:] == ["install", "--upgrade", "infomesh-b200"]
