@@ -91,3 +91,64 @@ def test_replica_placement_is_stable_under_candidate_order_and_growth(url, peers
     assert len(chosen) == min(n, len(peers)) and len(set(chosen)) == len(chosen) and set(chosen) <= set(peers)
     assert replica_peers(url, peers[::-1], n) == chosen                                      # order of the peer list does not matter
     assert replica_peers(url, peers, n + 1)[:len(chosen)] == chosen                          # asking for more keeps the closer ones first
+
+
+# ----------------------------------------------------------------------------- sharding invariants of the multi-GPU index (host side)
+import numpy as np  # noqa: E402
+
+from infomesh_b200.engine.gpu_index import _slice_csr, merge_shard_arrays  # noqa: E402
+
+
+@FAST
+@given(st.integers(1, 40), st.integers(1, 12), st.integers(1, 5), st.integers(0, 2 ** 31 - 1))
+def test_posting_slices_partition_the_global_index(n_docs, vocab, world, seed):
+    """Every posting of the global CSR lands in exactly one shard, re-based to that shard's rows, and every shard carries the
+    GLOBAL statistics (so BM25 scores do not depend on the number of GPUs)."""
+    rng = np.random.default_rng(seed)
+    postings = [sorted(rng.choice(n_docs, size=int(rng.integers(0, n_docs + 1)), replace=False).tolist()) for _ in range(vocab)]
+    off = np.zeros(vocab + 1, np.int64)
+    off[1:] = np.cumsum([len(p) for p in postings])
+    doc = np.array([d for p in postings for d in p], dtype=np.int32)
+    tf = rng.integers(1, 9, size=doc.size).astype(np.uint8)
+    csr = {"off": off, "doc": doc, "tf": tf, "doc_len": rng.integers(1, 50, size=n_docs).astype(np.int32), "df": np.diff(off).astype(np.int32)}
+    per = (n_docs + world - 1) // world
+    seen = [[] for _ in range(vocab)]
+    for r in range(world):
+        lo, hi = r * per, min(n_docs, (r + 1) * per)
+        if lo >= hi:
+            continue
+        part = _slice_csr(csr, lo, hi)
+        assert part["n_docs_global"] == n_docs and (part["df_global"] == csr["df"]).all() and len(part["doc_len"]) == hi - lo
+        assert abs(part["avg_len_global"] - csr["doc_len"].mean()) < 1e-9
+        for t in range(vocab):
+            rows = part["doc"][part["off"][t]:part["off"][t + 1]]
+            assert (rows >= 0).all() and (rows < hi - lo).all() and (np.diff(rows) > 0).all()          # local rows, still ascending
+            seen[t] += [(int(x) + lo, int(f)) for x, f in zip(rows, part["tf"][part["off"][t]:part["off"][t + 1]])]
+    for t in range(vocab):
+        want = [(int(d), int(f)) for d, f in zip(doc[off[t]:off[t + 1]], tf[off[t]:off[t + 1]])]
+        assert seen[t] == want
+
+
+@FAST
+@given(st.integers(1, 6), st.integers(1, 8), st.integers(2, 5), st.integers(0, 2 ** 31 - 1))
+def test_shard_views_merge_to_the_complete_answer(nq, k, world, seed):
+    """Rank 0 decides scores and rows; every other field comes from whichever rank owns the row -- wherever that rank happened
+    to place the row among near-ties."""
+    rng = np.random.default_rng(seed)
+    n_rows = k * 4
+    rows = np.stack([rng.choice(n_rows, size=k, replace=False) for _ in range(nq)]).astype(np.int64)
+    rows[rng.random(rows.shape) < 0.15] = -1                                   # empty result slots
+    owner = rng.integers(0, world, size=n_rows)
+    scores = -np.sort(-rng.random((nq, k)).astype(np.float32), axis=1)
+    parts = []
+    for r in range(world):
+        perm = np.stack([rng.permutation(k) for _ in range(nq)]) if r else np.tile(np.arange(k), (nq, 1))     # ranks > 0 order slots their own way
+        view = np.take_along_axis(rows, perm, axis=1)
+        mine = (view >= 0) & (owner[np.clip(view, 0, None)] == r)
+        parts.append({"scores": np.take_along_axis(scores, perm, axis=1), "rows": view, "doc_ids": np.where(mine, 1000 + view, -1),
+                      "pass": np.where(mine, view % 3, -1), "span": np.where(mine[..., None], np.stack([view, view + 5], axis=-1), -1)})
+    merged = merge_shard_arrays(parts)
+    assert (merged["rows"] == rows).all() and (merged["scores"] == scores).all()
+    live = rows >= 0
+    assert (merged["doc_ids"][live] == 1000 + rows[live]).all() and (merged["doc_ids"][~live] == -1).all()
+    assert (merged["pass"][live] == rows[live] % 3).all() and (merged["span"][live][:, 1] == rows[live] + 5).all()
