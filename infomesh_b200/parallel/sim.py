@@ -94,3 +94,110 @@ def favour(rank: int, weight: int = 20) -> Callable[[random.Random, list[int]], 
             return rank
         return rng.choice(runnable)
     return pick
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Cluster row-statistics exchange of the fused GEMM + LayerNorm epilogue (csrc/gemm/gemm_mxf8.cu, `LNF`)
+# ---------------------------------------------------------------------------------------------------------------------
+# Per tile every epilogue warp of every CTA of the cluster sends its partial row statistics to ALL CTAs with st.async: the
+# data lands in the receiver's slot and completes transaction bytes on the receiver's mbarrier in one step.  The receiver's
+# warp 0 posts `arrive.expect_tx(n_cta * warps)` once per tile (the barrier's arrival count is 1); slots and barriers are
+# double-buffered on `tile & 1`, a warp waits for phase `tile >> 1` of its buffer's barrier and then reads every slot.
+# What has to hold under ANY interleaving of warps and CTAs: a phase never completes before all of its data has landed (even
+# when data overtakes the expect_tx and the transaction count goes negative), and no slot is overwritten before every local
+# warp has read it.
+
+@dataclass
+class TxBarrier:
+    """mbarrier with an arrival count of 1 and a transaction count."""
+    phase: int = 0
+    pending: int = 1
+    tx: int = 0
+
+    def _maybe_complete(self) -> None:
+        if self.pending == 0 and self.tx == 0:
+            self.phase, self.pending = self.phase + 1, 1
+
+    def expect_tx(self, units: int) -> None:        # mbarrier.arrive.expect_tx: one arrival + `units` expected
+        self.tx += units
+        self.pending -= 1
+        if self.pending < 0:
+            raise Violation("two expect_tx arrivals in one phase")
+        self._maybe_complete()
+
+    def complete_tx(self, units: int = 1) -> None:  # the st.async data landing
+        self.tx -= units
+        self._maybe_complete()
+
+
+@dataclass
+class ClusterCta:
+    n_cta: int
+    warps: int
+    buffers: int = 2
+    slots: list = field(init=False)                 # [buffer][src cta][src warp]
+    bars: list = field(init=False)
+
+    def __post_init__(self) -> None:
+        self.slots = [[[None] * self.warps for _ in range(self.n_cta)] for _ in range(self.buffers)]
+        self.bars = [TxBarrier() for _ in range(self.buffers)]
+
+
+def stats_exchange_warp(cta: int, warp: int, ctas: list[ClusterCta], n_tiles: int, log: list) -> Iterator[None]:
+    me = ctas[cta]
+    for tile in range(n_tiles):
+        buf = tile % me.buffers
+        if warp == 0:
+            me.bars[buf].expect_tx(me.n_cta * me.warps)
+            yield
+        for p in range(me.n_cta):                    # st.async to every CTA of the cluster, own CTA included
+            ctas[p].slots[buf][cta][warp] = (tile, cta, warp)
+            ctas[p].bars[buf].complete_tx(1)
+            yield
+        want_phase = tile // me.buffers + 1          # the (tile // buffers)-th completion of this buffer's barrier
+        while me.bars[buf].phase < want_phase:       # mbarrier.try_wait.parity spin
+            yield
+        for src in range(me.n_cta):
+            for w in range(me.warps):
+                got = me.slots[buf][src][w]
+                if got != (tile, src, w):
+                    raise Violation(f"cta {cta} warp {warp} tile {tile}: slot[{src}][{w}] holds {got}")
+                yield
+        log.append((cta, warp, tile))
+
+
+def run_cluster(n_cta: int, warps: int, n_tiles: int, *, buffers: int = 2, seed: int = 0,
+                pick: Callable[[random.Random, list], object] | None = None, max_steps: int = 4_000_000) -> list:
+    """Interleave every (CTA, warp) of one cluster over ``n_tiles`` tiles; returns the completion log."""
+    rng = random.Random(seed)
+    ctas = [ClusterCta(n_cta, warps, buffers) for _ in range(n_cta)]
+    log: list = []
+    gens = {(c, w): stats_exchange_warp(c, w, ctas, n_tiles, log) for c in range(n_cta) for w in range(warps)}
+    steps = 0
+    while gens:
+        runnable = sorted(gens)
+        who = pick(rng, runnable) if pick else rng.choice(runnable)
+        try:
+            next(gens[who])
+        except StopIteration:
+            del gens[who]
+        steps += 1
+        if steps > max_steps:
+            raise RuntimeError("cluster schedule did not terminate (deadlock in the model?)")
+    return log
+
+
+def favour_cta(cta: int, weight: int = 30) -> Callable[[random.Random, list], object]:
+    """Let every warp of one CTA race ahead of the rest of the cluster."""
+    def pick(rng: random.Random, runnable: list):
+        mine = [x for x in runnable if x[0] == cta]
+        return rng.choice(mine) if mine and rng.randrange(weight) else rng.choice(runnable)
+    return pick
+
+
+def starve_warp0(weight: int = 30) -> Callable[[random.Random, list], object]:
+    """Delay the warps that post expect_tx, so that data overtakes it and the transaction count goes negative."""
+    def pick(rng: random.Random, runnable: list):
+        others = [x for x in runnable if x[1] != 0]
+        return rng.choice(others) if others and rng.randrange(weight) else rng.choice(runnable)
+    return pick

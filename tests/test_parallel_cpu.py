@@ -95,3 +95,40 @@ def test_checker_catches_the_overwrite_when_double_buffering_is_removed():
         except sim.Violation:
             hits += 1
     assert hits > 0, "single-buffered slots must be observably unsafe, otherwise the model proves nothing"
+
+
+# ------------------------------------------------------------------ cluster statistics exchange of the fused GEMM + LayerNorm epilogue
+def test_cluster_stats_exchange_model_survives_random_and_adversarial_schedules():
+    from infomesh_b200.parallel import sim
+
+    for n_cta, warps in ((2, 3), (4, 3), (4, 12)):
+        tiles = 5
+        for seed in range(12 if warps < 12 else 3):
+            log = sim.run_cluster(n_cta, warps, tiles, seed=seed)
+            assert len(log) == n_cta * warps * tiles
+        for fast in range(n_cta):                                   # one CTA as far ahead as the protocol lets it
+            sim.run_cluster(n_cta, warps, tiles, seed=fast, pick=sim.favour_cta(fast))
+        sim.run_cluster(n_cta, warps, tiles, seed=7, pick=sim.starve_warp0())       # data overtakes expect_tx: tx goes negative, phase must hold
+
+
+def test_cluster_stats_exchange_never_lets_a_cta_lead_by_more_than_one_tile():
+    from infomesh_b200.parallel import sim
+
+    log = sim.run_cluster(4, 3, 8, seed=1, pick=sim.favour_cta(2, weight=1000))
+    done: dict[tuple[int, int], int] = {}
+    for cta, warp, tile in log:
+        done[(cta, warp)] = tile
+        finished = [done.get((c, w), -1) for c in range(4) for w in range(3)]
+        assert max(finished) - min(finished) <= 2                   # finishing tile t needs every warp's tile-t data, i.e. every warp past t - 1
+
+
+def test_cluster_model_catches_the_overwrite_without_double_buffering():
+    from infomesh_b200.parallel import sim
+
+    hits = 0
+    for seed in range(40):
+        try:
+            sim.run_cluster(2, 2, 6, buffers=1, seed=seed, pick=sim.favour_cta(0))
+        except (sim.Violation, RuntimeError):
+            hits += 1
+    assert hits > 0, "single-buffered statistics must be observably unsafe, otherwise the model proves nothing"
