@@ -1896,3 +1896,60 @@ def replica_placement(pkg, tmp):
 
 
 SCENARIOS.update({f.__name__: f for f in (replica_placement,)})
+
+
+# ----------------------------------------------------------------------------- seventeenth batch: the services layer (needs baseline/shims/trafilatura)
+PAGES = [("https://docs.example.org/asyncio", "asyncio guide", "asyncio lets you write concurrent code with async and await. " * 8, "en"),
+         ("https://docs.example.org/asyncio?utm_source=x", "asyncio guide (tracked link)", "asyncio lets you write concurrent code with async and await. " * 8, "en"),
+         ("https://blog.example.org/rust", "Rust ownership", "ownership and borrowing make rust memory safe without a garbage collector. " * 8, None),
+         ("https://ko.example.org/python", "파이썬", "파이썬은 배우기 쉬운 프로그래밍 언어입니다. " * 12, "ko")]
+
+
+class _RecordingVectors:
+    def __init__(self):
+        self.added = []
+
+    def add_document(self, **kw):
+        self.added.append((kw["doc_id"], kw["url"], kw.get("language")))
+
+    def search(self, query, limit=10):
+        return []
+
+
+def services_indexing(pkg, tmp):
+    S = _m(pkg, "services")
+    PP = _m(pkg, "crawler.parser").ParsedPage
+    LS = _m(pkg, "index.local_store").LocalStore
+    H = _m(pkg, "hashing")
+    store, vec = LS(tmp / f"svc-{pkg}.db"), _RecordingVectors()
+    ids = []
+    for url, title, text, lang in PAGES:
+        page = PP(url=url, title=title, text=text, language=lang, raw_html_hash=H.content_hash("<html>" + text), text_hash=H.content_hash(text))
+        ids.append(S.index_document(page, store, vec, js_required=url.endswith("rust")))
+    again = S.index_document(PP(url=PAGES[0][0], title="changed title", text=PAGES[0][2], language="en", raw_html_hash="x", text_hash=H.content_hash(PAGES[0][2])), store, None)
+    out = {"ids": [i is not None for i in ids], "distinct": len({i for i in ids if i is not None}), "again": again is not None, "vectors": [(u, lg) for _, u, lg in vec.added],
+           "count": store.get_stats()["document_count"], "js": [bool(getattr(store.get_document_by_url(u), "js_required", False)) if store.get_document_by_url(u) else None
+                                                                  for u, *_ in PAGES],
+           "langs": [getattr(store.get_document_by_url(u), "language", None) if store.get_document_by_url(u) else None for u, *_ in PAGES],
+           "found": [r.url for r in _m(pkg, "search.query").search_local(store, "asyncio await", limit=5).results]}
+    store.close()
+    return out
+
+
+def parser_bookkeeping(pkg, tmp):
+    """Through ``extract_content``: only the fields that do not depend on extraction quality (hashes, language attribute, the
+    too-short rule) -- the reference runs on the tag-stripping stand-in for trafilatura here."""
+    P = _m(pkg, "crawler.parser")
+    H = _m(pkg, "hashing")
+    body = "<p>" + "Tensor memory holds the accumulators of the matrix units. " * 10 + "</p>"
+    html = f'<html lang="en-GB"><head><title>  Tensor   memory </title><style>p{{color:red}}</style></head><body>{body}<script>var x = 1;</script></body></html>'
+    page = P.extract_content(html, "https://e.com/tmem")
+    short = P.extract_content("<html><body><p>too short</p></body></html>", "https://e.com/short")
+    empty = P.extract_content("", "https://e.com/empty")
+    given = P.extract_content(html, "https://e.com/tmem", raw_hash="abc123")
+    return {"url": page.url, "title": " ".join(page.title.split()), "language": page.language, "raw_hash_is_html_hash": page.raw_html_hash == H.content_hash(html),
+            "text_hash_is_text_hash": page.text_hash == H.content_hash(page.text), "script_dropped": "var x" not in page.text, "style_dropped": "color:red" not in page.text,
+            "has_body": "Tensor memory holds" in page.text, "short": short is None, "empty": empty is None, "raw_hash_passed_through": given.raw_html_hash}
+
+
+SCENARIOS.update({f.__name__: f for f in (services_indexing, parser_bookkeeping)})
