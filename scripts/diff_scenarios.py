@@ -1953,3 +1953,92 @@ def parser_bookkeeping(pkg, tmp):
 
 
 SCENARIOS.update({f.__name__: f for f in (services_indexing, parser_bookkeeping)})
+
+
+# ----------------------------------------------------------------------------- eighteenth batch: the crawl worker over a scripted web site
+def _site():
+    long_a = "<p>" + "Tensor memory holds accumulators while the matrix units run. " * 12 + "</p>"
+    long_c = "<p>" + "Kademlia keeps buckets of contacts ordered by the XOR distance to the local id. " * 12 + "</p>"
+    return {
+        "https://site.example/robots.txt": (200, "User-agent: *\nDisallow: /blocked\nCrawl-delay: 0\nSitemap: https://site.example/sitemap.xml\n", "text/plain"),
+        "https://site.example/a": (200, f'<html lang="en"><head><title>Page A</title><link rel="alternate" type="application/rss+xml" href="/feed.xml"></head><body>{long_a}'
+                                        '<a href="/b">b</a> <a href="https://site.example/c#frag">c</a> <a href="https://other.example/x">ext</a> <a href="mailto:x@y.z">m</a>'
+                                        '<a href="/a">self</a> <a href="javascript:void(0)">js</a> <a href="/file.pdf">pdf</a></body></html>', "text/html"),
+        "https://site.example/b": (200, f"<html><head><title>Page B</title></head><body>{long_a}</body></html>", "text/html"),            # same text as /a
+        "https://site.example/c": (200, f"<html><head><title>Page C</title></head><body>{long_c}</body></html>", "text/html"),
+        "https://site.example/short": (200, "<html><body><p>tiny</p></body></html>", "text/html"),
+        "https://site.example/boom": (500, "server error", "text/html"),
+        "https://site.example/gone": (404, "not found", "text/html"),
+        "https://site.example/blocked/secret": (200, f"<html><body>{long_c}</body></html>", "text/html"),
+        "https://site.example/image.png": (200, "\x89PNG....", "image/png"),
+    }
+
+
+class _SiteClient:
+    """httpx.AsyncClient stand-in: ``get`` answers from the table and counts calls."""
+    is_closed = False
+
+    def __init__(self):
+        self.site, self.calls = _site(), []
+
+    async def get(self, url, **kw):
+        import httpx
+
+        url = str(url)
+        self.calls.append(url)
+        status, body, ctype = self.site.get(url, (404, "", "text/html"))
+        req = httpx.Request("GET", url)
+        return httpx.Response(status, text=body, headers={"content-type": ctype}, request=req)
+
+    async def aclose(self):
+        self.is_closed = True
+
+
+def crawl_worker_over_a_scripted_site(pkg, tmp):
+    W = _m(pkg, "crawler.worker")
+    Sch = _m(pkg, "crawler.scheduler").Scheduler
+    DD = _m(pkg, "crawler.dedup").DeduplicatorDB
+    RC = _m(pkg, "crawler.robots").RobotsChecker
+    C = _m(pkg, "config")
+    import dataclasses
+    import socket
+
+    crawl_cfg = dataclasses.replace(C.load_config(tmp / "none.toml").crawl, politeness_delay=0.1, max_depth=2, urls_per_hour=10000, pending_per_domain=100)
+
+    def public_dns(host, *a, **k):                      # every name resolves to a public address; literal IPs keep their own
+        try:
+            import ipaddress
+
+            ip = str(ipaddress.ip_address(host))
+        except ValueError:
+            ip = "93.184.216.34"
+        return [(socket.AF_INET, socket.SOCK_STREAM, 6, "", (ip, 0))]
+
+    async def no_sleep(_s):
+        return None
+
+    async def go():
+        sched, dedup = Sch(politeness_delay=0.0, urls_per_hour=0, pending_per_domain=100, max_depth=2), DD(str(tmp / f"w-dedup-{pkg}.db"))
+        worker = W.CrawlWorker(crawl_cfg, sched, dedup, RC(crawl_cfg.user_agent))
+        client = _SiteClient()
+        worker._client = client
+        rows = []
+        with mock.patch("socket.getaddrinfo", public_dns), mock.patch(f"{pkg}.crawler.worker.asyncio.sleep", no_sleep):
+            for url, kw in (("https://site.example/a", {}), ("https://site.example/b", {}), ("https://site.example/c", {"depth": 1}), ("https://site.example/short", {}),
+                            ("https://site.example/boom", {}), ("https://site.example/gone", {}), ("https://site.example/blocked/secret", {}), ("https://site.example/image.png", {}),
+                            ("http://127.0.0.1/admin", {}), ("http://169.254.169.254/latest/meta-data", {}), ("ftp://site.example/x", {}), ("https://site.example/a", {}),
+                            ("https://site.example/a", {"force": True}), ("https://site.example/a?utm_source=nl", {})):
+                r = await worker.crawl_url(url, **kw)
+                rows.append((url, kw.get("force", False), r.success, (r.error or "").split(":")[0][:40], r.page.title if r.page else None,
+                             sorted(l for l in r.discovered_links if "site.example" in l or "other.example" in l), sorted(getattr(r, "discovered_feeds", []) or []), r.js_required))
+        await worker.close()
+        out = {"rows": rows, "boom_attempts": client.calls.count("https://site.example/boom"), "robots_fetches": client.calls.count("https://site.example/robots.txt"),
+               "seen": [dedup.is_url_seen(u) for u in ("https://site.example/a", "https://site.example/b", "https://site.example/c", "https://site.example/short")],
+               "scheduled": sched.pending_count}
+        dedup.close()
+        return out
+
+    return asyncio.run(go())
+
+
+SCENARIOS.update({f.__name__: f for f in (crawl_worker_over_a_scripted_site,)})
