@@ -2042,3 +2042,33 @@ def crawl_worker_over_a_scripted_site(pkg, tmp):
 
 
 SCENARIOS.update({f.__name__: f for f in (crawl_worker_over_a_scripted_site,)})
+
+
+# ----------------------------------------------------------------------------- nineteenth batch: what an AppContext wires up for each role
+def app_context_wiring(pkg, tmp):
+    S = _m(pkg, "services")
+    C = _m(pkg, "config")
+    import dataclasses
+
+    names = ("store", "vector_store", "key_pair", "dedup", "robots", "scheduler", "worker", "link_graph", "ledger", "governor", "feed_monitor", "priority_queue", "llm_backend",
+             "index_submit_sender", "index_submit_receiver", "distributed_index", "p2p_node", "credit_sync_manager")
+    out = {}
+    for role in ("full", "crawler", "search"):
+        base = C.load_config(tmp / "none.toml")
+        data = tmp / f"ctx-{pkg}-{role}"
+        cfg = dataclasses.replace(base, node=dataclasses.replace(base.node, data_dir=data, role=role), index=dataclasses.replace(base.index, db_path=data / "index.db", vector_search=False),
+                                  network=dataclasses.replace(base.network, bootstrap_dns=False, bootstrap_github=False))
+        ctx = S.AppContext(cfg)
+        try:
+            out[role] = {n: getattr(ctx, n, None) is not None for n in names}
+            out[role]["keys_on_disk"] = (data / "keys" / "private.pem").exists()
+            out[role]["files"] = sorted(p.name for p in data.iterdir() if p.suffix == ".db")
+            out[role]["docs"] = ctx.store.get_stats()["document_count"]
+            out[role]["peer_id_len"] = len(ctx.key_pair.peer_id) if getattr(ctx, "key_pair", None) else 0
+        finally:
+            closer = getattr(ctx, "close_async", None)
+            asyncio.run(closer()) if closer else ctx.close()
+    return out
+
+
+SCENARIOS.update({f.__name__: f for f in (app_context_wiring,)})
