@@ -2072,3 +2072,76 @@ def app_context_wiring(pkg, tmp):
 
 
 SCENARIOS.update({f.__name__: f for f in (app_context_wiring,)})
+
+
+# ----------------------------------------------------------------------------- twentieth batch: publishing and page fetching through the services layer
+class _RecordingNetwork:
+    """Either a p2p node (``publish_document_to_network`` / ``publish_batch_to_network``) or a distributed index (``publish_document`` /
+    ``publish_batch``), recording what it is asked to publish."""
+
+    def __init__(self, kind: str, fail_on: int | None = None):
+        self.kind, self.calls, self.fail_on = kind, [], fail_on
+        if kind == "node":
+            self.publish_document_to_network = self._one_positional
+            self.publish_batch_to_network = self._batch
+        else:
+            self.publish_document = self._one_keyword
+            self.publish_batch = self._batch
+
+    async def _one_positional(self, doc_id, url, title, text):
+        self.calls.append(("doc", doc_id, url))
+        return 7
+
+    async def _one_keyword(self, *, doc_id, url, title, text):
+        self.calls.append(("doc", doc_id, url))
+        return 5
+
+    async def _batch(self, documents):
+        self.calls.append(("batch", len(documents)))
+        if self.fail_on is not None and len(self.calls) == self.fail_on:
+            raise ConnectionError("dht unreachable")
+        return 10 * len(documents)
+
+
+def services_publish_and_fetch(pkg, tmp):
+    S = _m(pkg, "services")
+    PP = _m(pkg, "crawler.parser").ParsedPage
+    LS = _m(pkg, "index.local_store").LocalStore
+    store = LS(tmp / f"pub-{pkg}.db")
+    for i in range(7):
+        store.add_document(url=f"https://e.com/{i}", title=f"T{i}", text=f"document number {i} about kernels and tiles " * 8, raw_html_hash=f"r{i}", text_hash=f"t{i}")
+    store.add_document(url="https://e.com/paywall", title="Premium", text="Subscribe to continue reading this article. " * 6, raw_html_hash="rp", text_hash="tp")
+    page = PP(url="https://e.com/0", title="T0", text="x", language="en", raw_html_hash="r", text_hash="t")
+
+    async def go():
+        node, index, broken = _RecordingNetwork("node"), _RecordingNetwork("index"), _RecordingNetwork("index", fail_on=2)
+        single = [await S.publish_document_to_network(page, 3, p2p_node=node), await S.publish_document_to_network(page, 3, distributed_index=index),
+                  await S.publish_document_to_network(page, None, p2p_node=node), await S.publish_document_to_network(page, 3),
+                  await S.publish_document_to_network(page, 3, p2p_node=node, distributed_index=index)]
+        rn, ri = _RecordingNetwork("node"), _RecordingNetwork("index")
+        bulk = [await S.republish_local_index(store, p2p_node=rn, batch_size=3), await S.republish_local_index(store, distributed_index=ri, batch_size=5, limit=6),
+                await S.republish_local_index(store), await S.republish_local_index(store, distributed_index=broken, batch_size=3),
+                await S.republish_local_index(store, distributed_index=_RecordingNetwork("index"), batch_size=0)]
+        return single, (node.calls, index.calls), bulk, (rn.calls, ri.calls, broken.calls)
+
+    single, single_calls, bulk, bulk_calls = asyncio.run(go())
+    old = store.get_document_by_url("https://e.com/1").crawled_at
+
+    def view(r):
+        return (r.success, r.url, r.title, len(r.text), r.is_cached, r.is_stale, r.is_paywall, (r.error or "").split(":")[0])
+
+    with mock.patch(f"{pkg}.services.time.time", return_value=old + 10):
+        fresh = S.fetch_page("https://e.com/1", store=store, worker=None)
+        clipped = S.fetch_page("https://e.com/1", store=store, worker=None, max_size_bytes=50)
+    with mock.patch(f"{pkg}.services.time.time", return_value=old + 8 * 86400):
+        stale = S.fetch_page("https://e.com/1", store=store, worker=None)
+    out = {"single": single, "single_calls": single_calls, "bulk": bulk, "bulk_calls": bulk_calls,
+           "fetch": [view(fresh), view(clipped), view(stale), view(S.fetch_page("https://e.com/unknown", store=store, worker=None)),
+                     view(S.fetch_page("http://127.0.0.1/x", store=store, worker=None)), view(S.fetch_page("file:///etc/passwd", store=store, worker=None))],
+           "paywall": [S.is_paywall_content(t) for t in ("Subscribe to continue reading", "plain article text about kernels", "", "Sign in to read the full story. Already a subscriber?")],
+           "truncate": [S._truncate_to_bytes(t, n) for t, n in (("hello world", 5), ("héllo", 2), ("한국어 텍스트", 7), ("short", 100), ("", 3))]}
+    store.close()
+    return out
+
+
+SCENARIOS.update({f.__name__: f for f in (services_publish_and_fetch,)})
