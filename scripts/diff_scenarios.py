@@ -2145,3 +2145,54 @@ def services_publish_and_fetch(pkg, tmp):
 
 
 SCENARIOS.update({f.__name__: f for f in (services_publish_and_fetch,)})
+
+
+# ----------------------------------------------------------------------------- twenty-first batch: crawl -> link graph -> index -> publish, and the peer-facing search function
+def crawl_and_index_pipeline(pkg, tmp):
+    S = _m(pkg, "services")
+    W = _m(pkg, "crawler.worker")
+    Sch = _m(pkg, "crawler.scheduler").Scheduler
+    DD = _m(pkg, "crawler.dedup").DeduplicatorDB
+    RC = _m(pkg, "crawler.robots").RobotsChecker
+    LS = _m(pkg, "index.local_store").LocalStore
+    LG = _m(pkg, "index.link_graph").LinkGraph
+    C = _m(pkg, "config")
+    import dataclasses
+    import socket
+
+    base = C.load_config(tmp / "none.toml")
+    data = tmp / f"pipe-{pkg}"
+    cfg = dataclasses.replace(base, node=dataclasses.replace(base.node, data_dir=data), index=dataclasses.replace(base.index, db_path=data / "index.db", vector_search=False))
+    data.mkdir()
+
+    def public_dns(host, *a, **k):
+        return [(socket.AF_INET, socket.SOCK_STREAM, 6, "", ("93.184.216.34", 0))]
+
+    async def no_sleep(_s):
+        return None
+
+    async def go():
+        store, dedup, graph = LS(data / "index.db"), DD(str(data / "dedup.db")), LG(str(data / "links.db"))
+        worker = W.CrawlWorker(cfg.crawl, Sch(politeness_delay=0.0, urls_per_hour=0, pending_per_domain=100, max_depth=2), dedup, RC(cfg.crawl.user_agent))
+        worker._client = _SiteClient()
+        net, vec = _RecordingNetwork("node"), _RecordingVectors()
+        rows = []
+        with mock.patch("socket.getaddrinfo", public_dns), mock.patch(f"{pkg}.crawler.worker.asyncio.sleep", no_sleep):
+            for url, kw in (("https://site.example/a", {}), ("https://site.example/c", {}), ("https://site.example/gone", {}), ("https://site.example/a", {}),
+                            ("https://site.example/a", {"force": True})):
+                r = await S.crawl_and_index(url, worker=worker, store=store, vector_store=vec, p2p_node=net, link_graph=graph, **kw)
+                rows.append((r.success, r.url, r.title, r.text_length > 0, r.links_discovered, (r.error or "").split(":")[0]))
+        await worker.close()
+        out = {"rows": rows, "docs": store.get_stats()["document_count"], "published": net.calls, "vectors": len(vec.added),
+               "out_links": sorted(graph.get_outlinks("https://site.example/a")) if hasattr(graph, "get_outlinks") else None}
+        search = S.create_local_search_fn(cfg)
+        hits = await search("tensor memory accumulators", 3)
+        out["peer_search"] = [(h["url"], h["title"], sorted(h)) for h in hits]
+        out["peer_search_empty"] = await search("zzzqqq", 3)
+        store.close(), dedup.close(), graph.close()
+        return out
+
+    return asyncio.run(go())
+
+
+SCENARIOS.update({f.__name__: f for f in (crawl_and_index_pipeline,)})
