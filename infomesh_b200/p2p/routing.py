@@ -58,21 +58,26 @@ def _payload_str(v: object, *, default: str = "") -> str:
     return v if isinstance(v, str) else default
 
 
+def _number(v: object, kinds: tuple[type, ...], parse: Callable[[Any], Any]) -> Any | None:
+    """``parse(v)`` for a value of one of ``kinds`` (booleans never count as numbers); None when it is not, or does not parse."""
+    if isinstance(v, bool) or not isinstance(v, kinds):
+        return None
+    try:
+        return parse(v)
+    except (TypeError, ValueError, OverflowError):
+        return None
+
+
 def _payload_int(v: object, *, default: int = 0) -> int:
-    if isinstance(v, bool):
-        return default
-    if isinstance(v, int):
-        return v
-    if isinstance(v, float) and v == v and abs(v) != float("inf"):
-        return int(v)
-    return default
+    """Integers and integer strings (peers on other stacks serialise numbers as text); floats are not silently truncated."""
+    n = _number(v, (int, str), int)
+    return default if n is None else n
 
 
 def _payload_float(v: object, *, default: float = 0.0) -> float:
-    if isinstance(v, bool) or not isinstance(v, (int, float)):
-        return default
-    f = float(v)
-    return f if f == f and abs(f) != float("inf") else default
+    """Finite numbers and numeric strings; NaN and the infinities fall back to the default."""
+    f = _number(v, (int, float, str), float)
+    return default if f is None or f != f or f in (float("inf"), -float("inf")) else f
 
 
 SendFn = Callable[[str, MessageType, dict[str, Any], float], Awaitable[tuple[MessageType, dict[str, Any]] | None]]

@@ -2196,3 +2196,15 @@ def crawl_and_index_pipeline(pkg, tmp):
 
 
 SCENARIOS.update({f.__name__: f for f in (crawl_and_index_pipeline,)})
+
+
+# ----------------------------------------------------------------------------- twenty-second batch: coercion of untrusted peer payloads in the query router
+def router_payload_coercion(pkg, tmp):
+    R = _m(pkg, "p2p.routing")
+    odd = [None, True, False, 0, 7, -3, 2.9, -2.9, float("nan"), float("inf"), -float("inf"), "12", " 12 ", "1e3", "0x10", "abc", "", b"5", [1], {"a": 1}, (2,), 10 ** 30, "9" * 400]
+    return {"str": [R._payload_str(v) for v in odd] + [R._payload_str(None, default="d"), R._payload_str(5, default="d")],
+            "int": [R._payload_int(v) for v in odd] + [R._payload_int("x", default=9), R._payload_int(None, default=-1)],
+            "float": [repr(R._payload_float(v)) for v in odd] + [repr(R._payload_float("x", default=0.5))]}
+
+
+SCENARIOS.update({f.__name__: f for f in (router_payload_coercion,)})

@@ -129,7 +129,7 @@ def resp(*rows):
 def test_route_query_merges_best_score_per_url_and_skips_self():
     table = {"python": [ptr("p1", 1, 2.0), ptr("me", 9), ptr("p2", 2, 1.0)], "rust": RuntimeError("dht hiccup")}
     replies = {"p1": resp({"url": "u1", "title": "A", "snippet": "s", "score": 0.4, "doc_id": 1}, {"url": "", "score": 9}, "junk"),
-               "p2": resp({"url": "u1", "title": "A2", "snippet": "s", "score": 0.9, "doc_id": 7}, {"url": "u2", "score": float("nan"), "doc_id": 2.0})}
+               "p2": resp({"url": "u1", "title": "A2", "snippet": "s", "score": 0.9, "doc_id": 7}, {"url": "u2", "score": float("nan"), "doc_id": "2"})}     # numbers may arrive as text; a float id would not be truncated
     r, sent = make_router(table, replies)
     out = run(r.route_query("python rust", ["python", "rust"], limit=5))
     assert [(x.url, x.peer_id, x.score) for x in out] == [("u1", "p2", 0.9), ("u2", "p2", 0.0)] and out[1].doc_id == 2
