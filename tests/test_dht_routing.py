@@ -173,8 +173,10 @@ def test_handle_search_request_limits_and_load_shedding():
 
 def test_payload_coercion_helpers():
     assert _payload_str(5, default="d") == "d" and _payload_str("x") == "x"
-    assert _payload_int(True, default=7) == 7 and _payload_int(3.9) == 3 and _payload_int(float("inf"), default=1) == 1 and _payload_int("4") == 0
-    assert _payload_float("1.5", default=2.0) == 2.0 and _payload_float(float("nan")) == 0.0 and _payload_float(2) == 2.0
+    # the reference's contract (p2p/routing.py:415-436): integer strings count, floats are never truncated into ids, NaN / inf are dropped
+    assert _payload_int(True, default=7) == 7 and _payload_int(3.9) == 0 and _payload_int(float("inf"), default=1) == 1 and _payload_int("4") == 4
+    assert _payload_int("x", default=9) == 9 and _payload_int(" 12 ") == 12 and _payload_int([1]) == 0
+    assert _payload_float("1.5", default=2.0) == 1.5 and _payload_float(float("nan")) == 0.0 and _payload_float(2) == 2.0 and _payload_float("inf", default=3.0) == 3.0
 
 
 # ------------------------------------------------------------------ kademlia routing table
