@@ -1692,8 +1692,7 @@ def resource_profiles(pkg, tmp):
     return out
 
 
-# (p2p.index_submit cannot be driven differentially here: the reference module imports trafilatura, which is not installed;
-#  its receiver / sender are covered by tests/test_services_layer.py, tests/test_crawl_loop.py, tests/test_platform.py and the interop mode of scripts/diff_vs_reference.py)
+# (p2p.index_submit is driven in the twenty-third batch, once baseline/shims/trafilatura lets the reference module import)
 
 
 SCENARIOS.update({f.__name__: f for f in (robots_policy, resource_profiles)})
@@ -2208,3 +2207,51 @@ def router_payload_coercion(pkg, tmp):
 
 
 SCENARIOS.update({f.__name__: f for f in (router_payload_coercion,)})
+
+
+# ----------------------------------------------------------------------------- twenty-third batch: crawler -> indexer submissions (enterprise split)
+def index_submission_flow(pkg, tmp):
+    S = _m(pkg, "p2p.index_submit")
+    P = _m(pkg, "p2p.protocol")
+    C = _m(pkg, "config")
+    PP = _m(pkg, "crawler.parser").ParsedPage
+    LS = _m(pkg, "index.local_store").LocalStore
+    H = _m(pkg, "hashing")
+    import dataclasses
+
+    base = C.load_config(tmp / "none.toml")
+
+    def cfg(**net):
+        return dataclasses.replace(base, network=dataclasses.replace(base.network, **net))
+
+    body = "Document body about tensors and kernels on one node. " * 12
+    page = PP(url="https://e.com/doc", title="Doc", text=body, language="en", raw_html_hash=H.content_hash("<html>" + body), text_hash=H.content_hash(body))
+    sender = S.IndexSubmitSender(cfg(index_submit_peers=["/ip4/10.0.0.9/tcp/4001/p2p/12D3KooWIndexer"]))
+    frame = sender.build_submit_message(page, ["https://e.com/next", "https://e.com/other"])
+    kind, payload = P.decode_message(frame)
+    sender.record_sent()
+    sender.record_sent()
+    sender.record_error()
+    out = {"kind": int(kind), "payload_keys": sorted(payload), "payload": {k: payload[k] for k in ("url", "title", "language", "text_hash", "raw_html_hash", "peer_id", "discovered_links")},
+           "signature_empty_without_key": payload["signature"] in (b"", ""), "sender": {"peers": sender.submit_peers, "stats": dict(sorted(sender.stats.items()))}}
+    store = LS(tmp / f"submit-{pkg}.db")
+    open_recv = S.IndexSubmitReceiver(cfg(), store)
+
+    def ack_view(a):
+        return (a.url, a.success, bool(a.doc_id) if hasattr(a, "doc_id") else None, (a.error or "")[:30])
+
+    acks = [open_recv.handle_submit(dict(payload)), open_recv.handle_submit(dict(payload)),                                   # second: duplicate content
+            open_recv.handle_submit(dict(payload, url="https://e.com/two", text=body + " more", text_hash=H.content_hash(body + " more")))]
+    out["open"] = {"acks": [ack_view(a) for a in acks], "stats": dict(sorted(open_recv.stats.items())), "docs": store.get_stats()["document_count"],
+                   "allowed_anyone": [open_recv.is_peer_allowed(p) for p in ("x", "")]}
+    ack_kind, ack_payload = P.decode_message(open_recv.build_ack_message(acks[0]))
+    out["ack_wire"] = (int(ack_kind), sorted(ack_payload))
+    gated = S.IndexSubmitReceiver(cfg(peer_acl=["12D3KooWCrawler"]), store)
+    out["gated"] = {"allowed": [gated.is_peer_allowed(p) for p in ("12D3KooWCrawler", "12D3KooWStranger", "")],
+                    "stranger": ack_view(gated.handle_submit(dict(payload, url="https://e.com/three", peer_id="12D3KooWStranger"))),
+                    "stats": dict(sorted(gated.stats.items()))}
+    store.close()
+    return out
+
+
+SCENARIOS.update({f.__name__: f for f in (index_submission_flow,)})
