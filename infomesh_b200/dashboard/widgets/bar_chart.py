@@ -29,5 +29,11 @@ def render_bars(items: "list[tuple[str, float] | BarItem]", *, width: int = 28, 
 
 
 class BarChart(Static):
+    """``BarChart(items=[BarItem("Crawling", 702, color="cyan"), ...], bar_width=20)`` as in the reference, or empty and fed by ``set_items``."""
+
+    def __init__(self, items: "list[tuple[str, float] | BarItem] | None" = None, *, bar_width: int = 28, **kw):
+        self._bar_width = int(bar_width)
+        super().__init__(render_bars(items or [], width=self._bar_width), **kw)
+
     def set_items(self, items: "list[tuple[str, float] | BarItem]") -> None:
-        self.update(render_bars(items))
+        self.update(render_bars(items, width=self._bar_width))

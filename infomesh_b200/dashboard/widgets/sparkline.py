@@ -18,10 +18,17 @@ def render_sparkline(values, width: int = 30) -> str:
 
 
 class SparklineChart(Static):
-    def __init__(self, label: str = "", *, width: int = 30, color: str = "cyan", **kw):
+    """``SparklineChart("docs/min")`` (label first, as the dashboard panes use it) or, like the reference widget,
+    ``SparklineChart([1, 4, 2], color="green")`` with the initial series first."""
+
+    def __init__(self, data: "list[float] | str | None" = None, *, label: str = "", width: int = 30, color: str = "cyan", **kw):
         super().__init__("", **kw)
+        if isinstance(data, str):
+            label, data = data, None
         self._label, self._width, self._color = label, width, color
-        self._values: deque[float] = deque(maxlen=width)
+        self._values: deque[float] = deque((float(v) for v in data or ()), maxlen=width)
+        if self._values:
+            self.update(f"[bold]{self._label:<10}[/] [{self._color}]{render_sparkline(self._values, self._width)}[/] {self._values[-1]:,.1f}")
 
     def push(self, value: float) -> None:
         self._values.append(float(value))

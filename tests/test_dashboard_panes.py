@@ -422,3 +422,21 @@ def test_panels_accept_push_style_updates(tmp_path):
             assert "v1.2.3" in _text(q("#e")) and "Error:" in _text(q("#f")) and "[locked]" in _text(q("#f"))
 
     asyncio.run(drive())
+
+
+def test_widgets_accept_the_reference_constructor_forms():
+    """Code that embeds the widgets the way the reference documents them (data / value first, bar_width, unit) keeps working."""
+    from infomesh_b200.dashboard.widgets.bar_chart import BarChart, BarItem
+    from infomesh_b200.dashboard.widgets.resource_bar import ResourceBar
+    from infomesh_b200.dashboard.widgets.sparkline import SparklineChart
+
+    spark = SparklineChart([1, 4, 2, 8], color="green")
+    spark.push_value(3, max_points=4)
+    assert spark.data == [4.0, 2.0, 8.0, 3.0] and SparklineChart("docs/min").data == []
+    bar = ResourceBar(label="CPU", value=38, max_value=100, unit="%", color="cyan", bar_width=12)
+    bar.update_value(95)
+    assert "95%" in str(bar.renderable if hasattr(bar, "renderable") else bar._bar_markup(0.95))
+    assert "40.0/180.0 GB" in ResourceBar("HBM", 40, 180, unit="GB")._bar_markup(40 / 180)
+    chart = BarChart(items=[BarItem("Crawling", 702, color="cyan"), BarItem("Uptime", 396)], bar_width=20)
+    chart.set_items([("a", 1.0)])
+    assert BarChart()._bar_width == 28 and chart._bar_width == 20
