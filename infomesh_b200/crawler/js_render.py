@@ -13,11 +13,11 @@ logger = get_logger(__name__)
 
 @dataclass
 class RenderResult:
-    url: str
-    html: str = ""
     success: bool = False
+    html: str = ""
     error: str | None = None
     elapsed_ms: float = 0.0
+    url: str = ""                # this build also records what was asked for and where the browser ended up
     final_url: str = ""
 
 
@@ -59,13 +59,13 @@ class JSRenderer:
     async def render(self, url: str) -> RenderResult:
         t0 = time.monotonic()
         if not self.available:
-            return RenderResult(url, error="playwright_not_installed")
+            return RenderResult(url=url, error="playwright_not_installed")
         from infomesh_b200.security import SSRFError, validate_url
 
         try:
             validate_url(url, resolve_dns=True)
         except SSRFError as exc:
-            return RenderResult(url, error=f"blocked: {exc}")
+            return RenderResult(url=url, error=f"blocked: {exc}")
         async with self._sem:
             page = None
             try:
@@ -73,10 +73,10 @@ class JSRenderer:
                 page = await browser.new_page(user_agent=self._ua)
                 await page.goto(url, timeout=self._timeout_ms, wait_until="networkidle")
                 html = await page.content()
-                return RenderResult(url, html, True, None, (time.monotonic() - t0) * 1000, page.url)
+                return RenderResult(True, html, None, (time.monotonic() - t0) * 1000, url=url, final_url=page.url)
             except Exception as exc:  # noqa: BLE001
                 logger.warning("js_render_failed", url=url, error=str(exc))
-                return RenderResult(url, error=str(exc), elapsed_ms=(time.monotonic() - t0) * 1000)
+                return RenderResult(url=url, error=str(exc), elapsed_ms=(time.monotonic() - t0) * 1000)
             finally:
                 if page is not None:
                     try:

@@ -78,14 +78,14 @@ class CreditSyncStore(SQLiteStore):
     def __init__(self, db_path: Path | str | None = None):
         super().__init__(db_path)
 
-    def store_summary(self, s: CreditSummary) -> None:
+    def store_summary(self, summary: CreditSummary) -> None:
         with self._lock:
             self._conn.execute(
                 "INSERT OR REPLACE INTO peer_credit_summaries (peer_id, owner_email_hash, total_earned, total_spent, "
                 "contribution_score, entry_count, tier, timestamp, signature, received_at) "
                 "VALUES (?, ?, ?, ?, ?, ?, ?, ?, ?, ?)",
-                (s.peer_id, s.owner_email_hash, s.total_earned, s.total_spent, s.contribution_score, s.entry_count,
-                 s.tier, s.timestamp, s.signature, time.time()))
+                (summary.peer_id, summary.owner_email_hash, summary.total_earned, summary.total_spent, summary.contribution_score, summary.entry_count,
+                 summary.tier, summary.timestamp, summary.signature, time.time()))
             self._conn.commit()
 
     def get_peer_summaries(self, owner_email_hash: str, *, include_stale: bool = False) -> list[CreditSummary]:

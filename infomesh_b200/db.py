@@ -10,15 +10,18 @@ from pathlib import Path
 class SQLiteStore:
     _SCHEMA: str = ""
 
-    def __init__(self, db_path: Path | str | None = None, *, check_same_thread: bool = False):
+    def __init__(self, db_path: Path | str | None = None, *, check_same_thread: bool = False, row_factory: type | None = None,
+                 extra_pragmas: list[str] | None = None):
         self._path = str(db_path) if db_path else ":memory:"
         if self._path != ":memory:":
             Path(self._path).parent.mkdir(parents=True, exist_ok=True)
         self._conn = sqlite3.connect(self._path, check_same_thread=check_same_thread)
-        self._conn.row_factory = sqlite3.Row
+        self._conn.row_factory = row_factory if row_factory is not None else sqlite3.Row      # stores here read columns by name
         self._lock = threading.RLock()
         self._conn.execute("PRAGMA journal_mode=WAL")
         self._conn.execute("PRAGMA busy_timeout=5000")
+        for pragma in extra_pragmas or ():
+            self._conn.execute(pragma)
         if self._SCHEMA:
             self._conn.executescript(self._SCHEMA)
             self._conn.commit()

@@ -79,9 +79,9 @@ async def detect_nat_type(stun_server: str = "stun.l.google.com", stun_port: int
 class DNSPeer:
     host: str
     port: int
-    source: str = "dns"
     peer_id: str = ""
     priority: int = 0
+    source: str = "dns"          # which record type produced it (after the reference's fields, so positional construction matches)
 
 
 def discover_peers_dns(domain: str = "infomesh.io", *, default_port: int = 4001) -> list[DNSPeer]:
@@ -90,13 +90,13 @@ def discover_peers_dns(domain: str = "infomesh.io", *, default_port: int = 4001)
 
     peers: list[DNSPeer] = []
     try:
-        peers += [DNSPeer(h, p, "dns_srv") for h, p in _resolve_srv(f"{SRV_SERVICE}.{domain}")]
+        peers += [DNSPeer(h, p, source="dns_srv") for h, p in _resolve_srv(f"{SRV_SERVICE}.{domain}")]
     except OSError:
         pass
     if not peers:
         try:
             for info in socket.getaddrinfo(f"peers.{domain}", default_port, proto=socket.IPPROTO_TCP):
-                peers.append(DNSPeer(info[4][0], default_port, "dns_a"))
+                peers.append(DNSPeer(info[4][0], default_port, source="dns_a"))
         except OSError:
             pass
     return list(dict.fromkeys(peers))
@@ -111,10 +111,10 @@ class GeoLocation:
     longitude: float = 0.0
 
 
-def estimate_geo_distance(a: GeoLocation, b: GeoLocation) -> float:
+def estimate_geo_distance(loc1: GeoLocation, loc2: GeoLocation) -> float:
     """Great-circle distance in km."""
-    p1, p2 = math.radians(a.latitude), math.radians(b.latitude)
-    dphi, dlmb = p2 - p1, math.radians(b.longitude - a.longitude)
+    p1, p2 = math.radians(loc1.latitude), math.radians(loc2.latitude)
+    dphi, dlmb = p2 - p1, math.radians(loc2.longitude - loc1.longitude)
     h = math.sin(dphi / 2) ** 2 + math.cos(p1) * math.cos(p2) * math.sin(dlmb / 2) ** 2
     return 6371.0 * 2 * math.atan2(math.sqrt(h), math.sqrt(1 - h))
 

@@ -46,10 +46,10 @@ class GovernorState:
     process_memory_mb: float = 0.0
     process_memory_limit_mb: int = 0
     process_memory_ratio: float = 0.0
-    gpu_memory_percent: float = 0.0
     throttle_factor: float = 1.0
     last_check: float = 0.0
     checks_performed: int = 0
+    gpu_memory_percent: float = 0.0      # new in this build; after the reference's fields so positional construction matches
 
 
 _LADDER = (  # (level, cpu >, mem >, process ratio >=)

@@ -66,8 +66,9 @@ class QueryCache:
     def _key(self, query_or_key: str, limit: int | None) -> str:
         return query_or_key if limit is None else self.make_key(query_or_key, limit)
 
-    def get(self, query_or_key: str, limit: int | None = None, *, now: float | None = None) -> Any | None:
-        key = self._key(query_or_key, limit)
+    def get(self, query: str, limit: int | None = None, *, now: float | None = None) -> Any | None:
+        """``get(query, limit)`` as in the reference, or ``get(key)`` with a key made by :meth:`make_key`."""
+        key = self._key(query, limit)
         now = time.monotonic() if now is None else now
         with self._lock:
             entry = self._data.get(key)
@@ -84,11 +85,12 @@ class QueryCache:
             self._hits += 1
             return entry.results
 
-    def put(self, query_or_key: str, limit_or_value: Any, results: Any = _UNSET, *, now: float | None = None) -> None:
+    def put(self, query: str, limit: Any, results: Any = _UNSET, *, now: float | None = None) -> None:
+        """``put(query, limit, results)`` as in the reference, or ``put(key, value)`` with a ready-made key."""
         if results is _UNSET:
-            key, value = query_or_key, limit_or_value
+            key, value = query, limit
         else:
-            key, value = self.make_key(query_or_key, int(limit_or_value)), results
+            key, value = self.make_key(query, int(limit)), results
         now = time.monotonic() if now is None else now
         with self._lock:
             self._data[key] = CacheEntry(value, now)
@@ -97,14 +99,14 @@ class QueryCache:
                 self._data.popitem(last=False)
                 self._evictions += 1
 
-    def invalidate(self, query_or_key: str | None = None, limit: int | None = None) -> bool:
+    def invalidate(self, query: str | None = None, limit: int | None = None) -> bool:
         """Drop one entry (True when it existed); with no arguments, drop everything."""
         with self._lock:
-            if query_or_key is None:
+            if query is None:
                 had = bool(self._data)
                 self._data.clear()
                 return had
-            return self._data.pop(self._key(query_or_key, limit), None) is not None
+            return self._data.pop(self._key(query, limit), None) is not None
 
     def clear(self) -> None:
         with self._lock:

@@ -68,15 +68,15 @@ def _notice_payload(notice_id: str, url: str, reason: str, created_at: float) ->
     return f"{notice_id}|{url}|{reason}|{created_at}".encode()
 
 
-def serialize_notice(n: TakedownNotice) -> dict[str, Any]:
-    return {"notice_id": n.notice_id, "url": n.url, "requester_id": n.requester_id, "reason": n.reason,
-            "signature": n.signature.hex(), "created_at": n.created_at, "deadline": n.deadline,
-            "contact_info": n.contact_info}
+def serialize_notice(notice: TakedownNotice) -> dict[str, Any]:
+    return {"notice_id": notice.notice_id, "url": notice.url, "requester_id": notice.requester_id, "reason": notice.reason,
+            "signature": notice.signature.hex(), "created_at": notice.created_at, "deadline": notice.deadline,
+            "contact_info": notice.contact_info}
 
 
-def deserialize_notice(d: dict[str, Any]) -> TakedownNotice:
-    return TakedownNotice(d["notice_id"], d["url"], d["requester_id"], d["reason"], bytes.fromhex(d["signature"]),
-                          d["created_at"], d["deadline"], d.get("contact_info", ""))
+def deserialize_notice(data: dict[str, Any]) -> TakedownNotice:
+    return TakedownNotice(data["notice_id"], data["url"], data["requester_id"], data["reason"], bytes.fromhex(data["signature"]),
+                          data["created_at"], data["deadline"], data.get("contact_info", ""))
 
 
 class _TakedownStore(SQLiteStore):

@@ -74,15 +74,15 @@ def _request_payload(request_id: str, url: str, basis: str, reason: str, created
     return f"{request_id}|{url}|{basis}|{reason}|{created_at}".encode()
 
 
-def serialize_request(r: DeletionRequest) -> dict[str, Any]:
-    return {"request_id": r.request_id, "url": r.url, "requester_id": r.requester_id, "basis": r.basis.value,
-            "reason": r.reason, "signature": r.signature.hex(), "created_at": r.created_at,
-            "personal_data_fields": list(r.personal_data_fields)}
+def serialize_request(request: DeletionRequest) -> dict[str, Any]:
+    return {"request_id": request.request_id, "url": request.url, "requester_id": request.requester_id, "basis": request.basis.value,
+            "reason": request.reason, "signature": request.signature.hex(), "created_at": request.created_at,
+            "personal_data_fields": list(request.personal_data_fields)}
 
 
-def deserialize_request(d: dict[str, Any]) -> DeletionRequest:
-    return DeletionRequest(d["request_id"], d["url"], d["requester_id"], DeletionBasis(d["basis"]), d["reason"],
-                           bytes.fromhex(d["signature"]), d["created_at"], list(d.get("personal_data_fields", [])))
+def deserialize_request(data: dict[str, Any]) -> DeletionRequest:
+    return DeletionRequest(data["request_id"], data["url"], data["requester_id"], DeletionBasis(data["basis"]), data["reason"],
+                           bytes.fromhex(data["signature"]), data["created_at"], list(data.get("personal_data_fields", [])))
 
 
 class _GDPRStore(SQLiteStore):
