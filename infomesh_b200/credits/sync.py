@@ -75,8 +75,8 @@ class CreditSyncStore(SQLiteStore):
         CREATE INDEX IF NOT EXISTS idx_pcs_owner ON peer_credit_summaries(owner_email_hash);
     """
 
-    def __init__(self, db_path: Path | str | None = None):
-        super().__init__(db_path)
+    def __init__(self, db_path: Path | str | None = None, **store_options):
+        super().__init__(db_path, **store_options)        # check_same_thread / row_factory / extra_pragmas of SQLiteStore
 
     def store_summary(self, summary: CreditSummary) -> None:
         with self._lock:

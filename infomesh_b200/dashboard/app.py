@@ -80,7 +80,7 @@ class DashboardApp(App[None]):
     BINDINGS = [*(Binding(str(i + 1), f"tab('{name}')", name.title()) for i, name in enumerate(TABS)), Binding("r", "refresh", "Refresh"),
                 Binding("m", "toggle_bgm", "Music"), Binding("question_mark", "help", "Help"), Binding("q", "quit", "Quit")]
 
-    def __init__(self, config: Config | None = None, *, initial_tab: str = "overview", node_pid: int | None = None):
+    def __init__(self, config: Config | None = None, initial_tab: str = "overview", node_pid: int | None = None):
         super().__init__()
         self.config = config or load_config()
         self.initial_tab = initial_tab if initial_tab in TABS else "overview"
@@ -232,7 +232,7 @@ class DashboardApp(App[None]):
         self.exit()
 
 
-def run_dashboard(config: Config | None = None, *, initial_tab: str = "overview", node_pid: int | None = None) -> str:
+def run_dashboard(config: Config | None = None, initial_tab: str = "overview", node_pid: int | None = None) -> str:
     """Blocks until the TUI exits; returns "stop_all" or "dashboard_only"."""
     app = DashboardApp(config, initial_tab=initial_tab, node_pid=node_pid)
     try:

@@ -107,9 +107,9 @@ class BGMPlayer:
         _record_pid(proc.pid)
         return proc
 
-    def play(self, path: str | Path, *, volume: int = 50) -> bool:
+    def play(self, path: str | Path, *, loop: bool = True, volume: int = 50) -> bool:
         self.stop()
-        self._proc = self._spawn(path, volume, loop=True)
+        self._proc = self._spawn(path, volume, loop=loop)
         self._track = (str(path), volume) if self._proc else None
         return self._proc is not None
 

@@ -11,6 +11,13 @@ from infomesh_b200.dashboard import utils as U
 from infomesh_b200.dashboard.widgets import BarChart, LiveLog
 
 
+
+def _own_cache(config):
+    """A pane constructed the reference's way (``Pane(config)``) reads through its own data cache."""
+    from infomesh_b200.dashboard.data_cache import DashboardDataCache
+
+    return DashboardDataCache(config, ttl=max(getattr(config.dashboard, "refresh_interval", 0.5), 0.2))
+
 class CrawlStatsPanel(Static):
     """One line of crawl throughput and the limits currently in force."""
 
@@ -61,9 +68,9 @@ class TopDomainsPanel(BarChart):
 
 
 class CrawlPane(Vertical):
-    def __init__(self, config, cache, **kw):
+    def __init__(self, config, cache=None, **kw):
         super().__init__(**kw)
-        self.config, self.cache = config, cache
+        self.config, self.cache = config, cache if cache is not None else _own_cache(config)
         self._seen: set[int] = set()
 
     def compose(self) -> ComposeResult:
@@ -81,4 +88,5 @@ class CrawlPane(Vertical):
         st = self.cache.get_stats()
         self.query_one(CrawlStatsPanel).show(st)
         self.query_one(TopDomainsPanel).show(st)
-        U.push_new_docs_to_log(self.query_one("#cr-log", LiveLog), st.recent_docs, self._seen)
+        self._seen, self._last_count = U.push_new_docs_to_log(st.recent_docs, st.document_count, self._seen, getattr(self, "_last_count", -1),
+                                                                  self.query_one("#cr-log", LiveLog))

@@ -28,8 +28,13 @@ def _read_ledger(config):
 
 
 class _LedgerPanel:
-    """Mixin: a panel that can also refresh itself straight from the ledger file when given a config."""
+    """Mixin: a panel that can also refresh itself straight from the ledger file when given a config
+    (``BalancePanel(config)`` / ``TransactionTable(config)``, the reference's form) -- or be fed by its parent pane."""
     config = None
+
+    def __init__(self, config=None, **kw):
+        super().__init__("", **kw)
+        self.config = config if config is not None and hasattr(config, "node") else None
 
     def on_mount(self) -> None:
         if self.config is not None:

@@ -13,12 +13,19 @@ from infomesh_b200.dashboard import utils as U
 from infomesh_b200.dashboard.widgets import LiveLog, ResourceBar, SparklineChart
 
 
+
+def _own_cache(config):
+    """A pane constructed the reference's way (``Pane(config)``) reads through its own data cache."""
+    from infomesh_b200.dashboard.data_cache import DashboardDataCache
+
+    return DashboardDataCache(config, ttl=max(getattr(config.dashboard, "refresh_interval", 0.5), 0.2))
+
 class NodeInfoPanel(Static):
     """Version, run state, uptime, identity, role and the index head-line numbers."""
 
-    def __init__(self, config, cache, **kw):
+    def __init__(self, config, cache=None, **kw):
         super().__init__("", **kw)
-        self.config, self.cache = config, cache
+        self.config, self.cache = config, cache if cache is not None else _own_cache(config)
 
     def on_mount(self) -> None:
         self.refresh_data()
@@ -76,9 +83,9 @@ class ResourcePanel(Vertical):
 class ActivityPanel(Vertical):
     """Indexing rate and CPU sparklines over a log of recently indexed documents."""
 
-    def __init__(self, config, cache, **kw):
+    def __init__(self, config, cache=None, **kw):
         super().__init__(**kw)
-        self.config, self.cache = config, cache
+        self.config, self.cache = config, cache if cache is not None else _own_cache(config)
         self._seen: set[int] = set()
         self._last_count = -1
 
@@ -106,13 +113,14 @@ class ActivityPanel(Vertical):
         if self._last_count >= 0:
             self.query_one("#ov-rate", SparklineChart).push(max(0, st.document_count - self._last_count) * 60 / period)
         self._last_count = st.document_count
-        U.push_new_docs_to_log(self.query_one("#ov-log", LiveLog), st.recent_docs, self._seen)
+        self._seen, self._last_count = U.push_new_docs_to_log(st.recent_docs, st.document_count, self._seen, getattr(self, "_last_count", -1),
+                                                                  self.query_one("#ov-log", LiveLog))
 
 
 class OverviewPane(Vertical):
-    def __init__(self, config, cache, **kw):
+    def __init__(self, config, cache=None, **kw):
         super().__init__(**kw)
-        self.config, self.cache = config, cache
+        self.config, self.cache = config, cache if cache is not None else _own_cache(config)
 
     def compose(self) -> ComposeResult:
         yield NodeInfoPanel(self.config, self.cache, id="ov-node")

@@ -29,9 +29,9 @@ class RestartConfirmScreen(ModalScreen[bool]):
     """-> True when the user wants the node restarted now."""
     DEFAULT_CSS = "RestartConfirmScreen {align: center middle;} #restart-box {width: 60; height: auto; border: round $warning; padding: 1 2; background: $surface;}"
 
-    def __init__(self, keys: list[str]):
+    def __init__(self, changed_keys: list[str]):
         super().__init__()
-        self.keys = keys
+        self.keys = list(changed_keys)
 
     def compose(self) -> ComposeResult:
         with Vertical(id="restart-box"):

@@ -86,10 +86,22 @@ def format_doc_line(url: str, title: str) -> str:
     return f"{url}  ({label})"
 
 
-def push_new_docs_to_log(log: Any, docs: list[Any], seen: set[int]) -> int:
-    """Write not-yet-seen recent documents (oldest first) to a log widget exposing ``write_line``."""
-    fresh = [d for d in reversed(docs) if d.doc_id not in seen]
-    for d in fresh:
-        seen.add(d.doc_id)
-        log.write_line(f"{time.strftime('%H:%M:%S', time.localtime(d.crawled_at))}  ✔ {format_doc_line(d.url, d.title)}")
-    return len(fresh)
+def push_new_docs_to_log(recent_docs: "list[Any]", doc_count: int, seen_ids: set[int], last_count: int, log_widget: Any) -> tuple[set[int], int]:
+    """Feed documents that were not shown yet (oldest first) to a live log and return the updated ``(seen_ids, last_count)``.
+
+    Nothing new and no growth -> unchanged; the seen set is mutated in place and trimmed to its newest 300 ids once it passes
+    500, so a pane that runs for weeks does not accumulate every document id it ever displayed."""
+    if doc_count <= last_count and not recent_docs:
+        return seen_ids, last_count
+    fresh = sorted((d for d in recent_docs if d.doc_id not in seen_ids), key=lambda d: d.crawled_at)
+    if not fresh:
+        return seen_ids, doc_count
+    for doc in fresh:
+        try:
+            log_widget.log_crawl(format_doc_line(doc.url, doc.title), success=True)
+        except Exception:  # noqa: BLE001 -- a log widget that is being torn down must not stop the pane's refresh
+            break
+        seen_ids.add(doc.doc_id)
+    if len(seen_ids) > 500:
+        seen_ids = set(sorted(seen_ids)[-300:])
+    return seen_ids, doc_count

@@ -38,8 +38,9 @@ class VectorSearchResult:
 
 
 class VectorStore:
-    def __init__(self, persist_dir: Path | str | None = None, *, model_name: str = DEFAULT_MODEL,
+    def __init__(self, persist_dir: Path | str | None = None, model_name: str = DEFAULT_MODEL, collection_name: str = "infomesh_docs", *,
                  device: str | None = None, max_seq_len: int = 256, capacity: int = 4096, seed: int = 0):
+        self._collection_name = collection_name          # kept for callers that name their collection; one collection per store here
         from infomesh_b200.models.bert import CONFIGS, BertModel
         from infomesh_b200.utils.tokenizer import BERT_SPECIALS, HashTokenizer
 
@@ -90,7 +91,7 @@ class VectorStore:
         v[:cap], a[:cap] = self._vecs, self._alive
         self._vecs, self._alive = v, a
 
-    def add_document(self, *, doc_id: int, url: str, title: str, text: str, language: str | None = None) -> None:
+    def add_document(self, doc_id: int, url: str, title: str, text: str, *, language: str | None = None) -> None:
         self.add_documents([dict(doc_id=doc_id, url=url, title=title, text=text, language=language)])
 
     def add_documents(self, docs: list[dict]) -> None:

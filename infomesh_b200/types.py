@@ -19,9 +19,9 @@ class KeyPairLike(Protocol):
 
 @runtime_checkable
 class VectorStoreLike(Protocol):
-    def add_document(self, *, doc_id: int, url: str, title: str, text: str, language: str | None = None) -> None: ...
+    def add_document(self, doc_id: int, url: str, title: str, text: str, language: str | None = None) -> None: ...
 
-    def search(self, query: str, *, limit: int = 10, min_score: float = 0.0) -> list[Any]: ...
+    def search(self, query: str, limit: int = 10) -> list[Any]: ...
 
     def delete_document(self, doc_id: int) -> None: ...
 

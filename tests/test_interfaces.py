@@ -164,11 +164,14 @@ def test_dashboard_helpers_and_tui(node_env):
     class Log:
         lines: list = []
 
-        def write_line(self, s):
-            self.lines.append(s)
+        def log_crawl(self, line, *, success=True, credits=0):
+            self.lines.append((line, success))
 
-    seen: set = set()
-    assert U.push_new_docs_to_log(Log(), st.recent_docs, seen) == 2 and U.push_new_docs_to_log(Log(), st.recent_docs, seen) == 0
+    log = Log()
+    seen, last = U.push_new_docs_to_log(st.recent_docs, st.document_count, set(), -1, log)          # the reference's calling convention
+    assert len(seen) == 2 and last == 2 and len(log.lines) == 2 and all(ok for _, ok in log.lines)
+    assert log.lines[0][0].startswith("https://") and U.push_new_docs_to_log(st.recent_docs, 2, seen, last, log) == (seen, 2) and len(log.lines) == 2
+    assert U.push_new_docs_to_log([], 2, seen, 2, log) == (seen, 2)
     cache.close()
     assert "95%" in _make_bar(0.95).plain and render_sparkline([1, 2, 3, 4], 4) == "▁▃▆█" and "█" in render_bars([("a.com", 3), ("b.com", 1)])
     assert "red" in render_resource("CPU", 0.95) and "no data" in render_bars([])
